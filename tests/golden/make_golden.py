@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures from the REFERENCE ITSELF.  Runs only in the dev
+container (needs /root/reference); the GPU box and the test-suite only read the .npz files.
+
+  frames_siso.npz     waveforms made by the reference's own generator tools/phy80211.py following
+                      the recipe of tools/pktGenExample.py:173-199 (payload "1234567890"x3, L MCS0-7,
+                      HT MCS0-7, VHT MCS0-8, multiplier 12, scrambler seed 93) + the MPDU each must
+                      decode to.  Config 1 of BASELINE.json is item 0 (gapLen 1200 as in the recipe).
+  frames_bench.npz    16 VHT MCS7 frames carrying random 1500-byte MPDUs (A-MPDU 1504 B, 47 symbols,
+                      4560 samples): the unique frames bench.py replicates for config 5.
+  ref_vectors.npz     input/output pairs of the unmodified lib/cloud80211phy.cc functions
+                      (through oracle/_ref/libc8p_ref.so) so GPU tests can compare with the
+                      reference's own outputs where /root/reference does not exist.
+
+usage: python tests/golden/make_golden.py
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+STUB = "/tmp/_mpl_stub"
+os.makedirs(os.path.join(STUB, "matplotlib"), exist_ok=True)
+open(os.path.join(STUB, "matplotlib", "__init__.py"), "w").close()
+with open(os.path.join(STUB, "matplotlib", "pyplot.py"), "w") as f:
+    f.write("def __getattr__(n):\n    return lambda *a, **k: None\n")
+sys.path.insert(0, STUB)
+sys.path.insert(0, "/root/reference/tools")
+
+with contextlib.redirect_stdout(io.StringIO()):
+    import mac80211  # noqa: E402
+    import phy80211  # noqa: E402
+    import phy80211header as p8h  # noqa: E402
+    import pktGenExample as pge  # noqa: E402
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def gen(phy, fmt, mcs, pkt, gap, cfo=0.0, mult=12.0, nsts=1):
+    mod = p8h.modulation(phyFormat=fmt, mcs=mcs, bw=p8h.BW.BW20, nSTS=nsts, shortGi=False)
+    if fmt == p8h.F.VHT:
+        quiet(phy.genFromAmpdu, pkt, mod, vhtPartialAid=0, vhtGroupId=0)
+    else:
+        quiet(phy.genFromMpdu, pkt, mod)
+    ss = quiet(phy.genFinalSig, multiplier=mult, cfoHz=cfo, num=1, gap=True, gapLen=gap)
+    return [np.asarray(s, dtype=np.complex64) for s in ss]
+
+
+def mac_mpdu(payload):
+    return quiet(pge.genMac80211UdpMPDU, payload)
+
+
+def mac_ampdu(payloads):
+    return quiet(pge.genMac80211UdpAmpduVht, payloads)
+
+
+def ampdu_split(ampdu):
+    """MPDUs inside a VHT A-MPDU built by tools/mac80211.py:333-360 (delimiter: EOF, rsvd, len[12:14], len[0:12], CRC8, 0x4E)."""
+    out, i, ampdu = [], 0, bytes(ampdu)
+    while i + 4 <= len(ampdu):
+        d0, d1 = ampdu[i], ampdu[i + 1]
+        ln = ((d0 >> 4) & 0xF) | (d1 << 4) | (((d0 >> 2) & 3) << 12)
+        out.append(ampdu[i + 4: i + 4 + ln])
+        i += 4 + (ln + 3) // 4 * 4
+    return out
+
+
+def frames_siso():
+    phy = phy80211.phy80211(ifDebug=False)
+    payload = "123456789012345678901234567890"
+    mpdu = mac_mpdu(payload)
+    ampdu = mac_ampdu([payload])
+    items, meta, exp = [], [], []
+    # config 1: exactly the reference recipe (gap 1200)
+    items.append(gen(phy, p8h.F.L, 0, mpdu, 1200)[0]); meta.append((0, 0, 0.0)); exp.append(bytes(mpdu))
+    for fmt, code, rng, pkt in ((p8h.F.L, 0, range(0, 8), mpdu), (p8h.F.HT, 1, range(0, 8), mpdu), (p8h.F.VHT, 2, range(0, 9), ampdu)):
+        for mcs in rng:
+            items.append(gen(phy, fmt, mcs, pkt, 400)[0]); meta.append((code, mcs, 0.0))
+            exp.append(ampdu_split(pkt)[0] if code == 2 else bytes(mpdu))
+    # CFO cases (generator applies the CFO itself): +/- 50 kHz, 233 kHz (tools/performance/perf_wime.py:134-137)
+    for fmt, code, mcs, pkt, cfo in ((p8h.F.L, 0, 4, mpdu, 50e3), (p8h.F.HT, 1, 7, mpdu, -50e3), (p8h.F.VHT, 2, 8, ampdu, 100e3),
+                                     (p8h.F.VHT, 2, 7, ampdu, -233e3)):
+        items.append(gen(phy, fmt, mcs, pkt, 400, cfo=cfo)[0]); meta.append((code, mcs, cfo))
+        exp.append(ampdu_split(pkt)[0] if code == 2 else bytes(mpdu))
+    # a 2-subframe VHT A-MPDU (exercises the de-aggregation walk, lib/decode_impl.cc:337-431)
+    ampdu2 = mac_ampdu([payload, "This is packet for station 001"])
+    items.append(gen(phy, p8h.F.VHT, 5, ampdu2, 400)[0]); meta.append((2, 5, 0.0)); exp.append(ampdu_split(ampdu2)[0])
+    offs = np.cumsum([0] + [len(x) for x in items]).astype(np.int64)
+    iq = np.concatenate(items).astype(np.complex64)
+    explen = np.array([len(e) for e in exp], np.int32)
+    expbuf = np.frombuffer(b"".join(exp), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "frames_siso.npz"), iq=iq, offs=offs, meta=np.array(meta, np.float64), exp_len=explen,
+                        exp_mpdu=expbuf, ampdu2_second=np.frombuffer(ampdu_split(ampdu2)[1], np.uint8))
+    print("frames_siso: %d items, %d samples" % (len(items), iq.size))
+
+
+def frames_bench():
+    phy = phy80211.phy80211(ifDebug=False)
+    rng = np.random.default_rng(80211)
+    frames, mpdus = [], []
+    for i in range(16):
+        # 1500-byte MPDU: 26-byte QoS 802.11 header + 8 LLC + 20 IPv4 + 8 UDP + payload + 4 FCS = 1500 -> payload 1434
+        # (the generator takes str payloads: latin-1 keeps one byte per char)
+        payload = bytes(rng.integers(1, 128, 1434, dtype=np.uint8)).decode("latin-1")
+        ampdu = mac_ampdu([payload])
+        mpdu = ampdu_split(ampdu)[0]
+        assert len(mpdu) == 1500 and len(ampdu) == 1504, (len(mpdu), len(ampdu))
+        s = gen(phy, p8h.F.VHT, 7, ampdu, 0)[0]
+        assert s.size == 4560, s.size
+        frames.append(s); mpdus.append(np.frombuffer(bytes(mpdu), np.uint8))
+    np.savez_compressed(os.path.join(HERE, "frames_bench.npz"), iq=np.stack(frames).astype(np.complex64), mpdu=np.stack(mpdus))
+    print("frames_bench: 16 x", frames[0].size)
+
+
+def ref_vectors():
+    import oracle_lib as ol
+    R = ol.ref()
+    rng = np.random.default_rng(20211)
+    out = {}
+    # tables (cloud80211phy.h:151-195)
+    for name, n in (("mapDeintLegacyBpsk", 48), ("mapDeintLegacyQpsk", 96), ("mapDeintLegacy16Qam", 192), ("mapDeintLegacy64Qam", 288),
+                    ("mapDeintNonlegacyBpsk", 52), ("mapDeintNonlegacyQpsk", 104), ("mapDeintNonlegacy16Qam", 208),
+                    ("mapDeintNonlegacy64Qam", 312), ("mapDeintNonlegacy256Qam", 416), ("mapDeintVhtSigB20", 52),
+                    ("SV_STATE_NEXT", 128), ("SV_STATE_OUTPUT", 128)):
+        buf = np.zeros(512, np.int32)
+        assert R.ref_table_i(name.encode(), buf) == n
+        out["tab_" + name] = buf[:n].copy()
+    for name, n in (("LTF_L_26_F_FLOAT", 64), ("LTF_NL_28_F_FLOAT", 64), ("LTF_NL_28_F_FLOAT_VHT22", 64), ("PILOT_P", 127)):
+        buf = np.zeros(128, np.float32)
+        assert R.ref_table_f(name.encode(), buf) == n
+        out["tab_" + name] = buf[:n].copy()
+    # 2-stream deinterleave maps are file-static in the reference: recover them by probing procSymDeintNL2SS2
+    for nb in (1, 2, 4, 6, 8):
+        n = 52 * nb
+        o = np.full(n, -1, np.float32)
+        R.ref_deint_nl(np.arange(n, dtype=np.float32), o, n, 2)
+        m = np.zeros(n, np.int32)
+        m[o.astype(np.int32)] = np.arange(n, dtype=np.int32)    # out[map[i]] = i  ->  map[i] = position holding i
+        out["tab_deintNL2_%d" % nb] = m
+    # soft Viterbi on noisy codewords, rate 1/2 (SV_Decode_Sig == decode block's ACS, c8p.cc:1890-1999)
+    for k, tl in enumerate((24, 48, 200, 1000, 4000)):
+        bits = rng.integers(0, 2, tl).astype(np.uint8); bits[-6:] = 0
+        coded = np.zeros(2 * tl, np.uint8); R.ref_bcc(bits, coded, tl)
+        llr = ((coded.astype(np.float32) * 2 - 1) * 1.0 + rng.normal(0, 0.9, 2 * tl)).astype(np.float32)
+        dec = np.zeros(tl, np.uint8); R.ref_sv_decode(llr, dec, tl)
+        out["vit_llr_%d" % k] = llr; out["vit_bits_%d" % k] = dec
+    # pure-noise input: exercises ties / survivor order, not just the easy path
+    llr = rng.normal(0, 1.0, 2 * 3000).astype(np.float32)
+    llr = np.round(llr * 4) / 4          # quantised -> many exact metric ties
+    dec = np.zeros(3000, np.uint8); R.ref_sv_decode(llr.astype(np.float32), dec, 3000)
+    out["vit_llr_tie"] = llr.astype(np.float32); out["vit_bits_tie"] = dec
+    # LLR demap (c8p.cc:2090-2148)
+    for mod, nsd in ((0, 48), (2, 48), (3, 48), (4, 48), (0, 52), (2, 52), (3, 52), (4, 52), (5, 52)):
+        q = (rng.normal(0, 0.8, nsd) + 1j * rng.normal(0, 0.8, nsd)).astype(np.complex64)
+        nb = {0: 1, 2: 2, 3: 4, 4: 6, 5: 8}[mod]
+        o = np.zeros(nsd * nb, np.float32)
+        R.ref_qam_to_llr(ol.c2f(q).copy(), o, mod, nsd)
+        out["llr_in_%d_%d" % (mod, nsd)] = q; out["llr_out_%d_%d" % (mod, nsd)] = o
+    # L-SIG / HT-SIG / VHT-SIG-A demod on random tones (c8p.cc:609-648)
+    s1 = (rng.normal(0, 1, 64) + 1j * rng.normal(0, 1, 64)).astype(np.complex64)
+    s2 = (s1 + 0.05 * (rng.normal(0, 1, 64) + 1j * rng.normal(0, 1, 64))).astype(np.complex64)
+    sg = (rng.normal(0, 1, 64) + 1j * rng.normal(0, 1, 64)).astype(np.complex64)
+    h = np.zeros(128, np.float32); l48 = np.zeros(48, np.float32)
+    R.ref_lsig_demod(ol.c2f(s1), ol.c2f(s2), ol.c2f(sg), h, l48)
+    out["lsig_s1"], out["lsig_s2"], out["lsig_sig"], out["lsig_h"], out["lsig_llr"] = s1, s2, sg, h.view(np.complex64).copy(), l48
+    lht = np.zeros(96, np.float32); lvht = np.zeros(96, np.float32)
+    hh = h.copy(); hh[hh == 0] = 1.0
+    R.ref_nlsig_demod(ol.c2f(s1), ol.c2f(sg), hh, lht, lvht)
+    out["nlsig_h"], out["nlsig_llrht"], out["nlsig_llrvht"] = hh.view(np.complex64).copy(), lht, lvht
+    np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **out)
+    print("ref_vectors: %d arrays" % len(out))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["siso", "bench", "ref"]
+    if "siso" in which:
+        frames_siso()
+    if "bench" in which:
+        frames_bench()
+    if "ref" in which:
+        ref_vectors()

@@ -1,0 +1,101 @@
+"""The oracle's whole chain on waveforms made by the reference's own generator (tools/phy80211.py):
+every frame must come back as its own MPDU with CRC-32 pass -- the end-to-end known-answer test the
+reference offers for this path (recipe tools/pktGenExample.py:173-199)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+
+def _items(g):
+    iq, offs = g["iq"], g["offs"]
+    el = g["exp_len"]
+    eo = np.cumsum(np.r_[0, el])
+    for i in range(len(offs) - 1):
+        yield i, iq[offs[i]:offs[i + 1]], bytes(g["exp_mpdu"][eo[i]:eo[i + 1]]), g["meta"][i]
+
+
+def test_config1_legacy_mcs0_plumbing(golden):
+    i, x, mpdu, meta = next(_items(golden["frames_siso"]))
+    fr, llr, pdu = ol.rx_item(x)
+    f = fr[0]
+    assert f["status"] == 0
+    assert (f["format"], f["mcs"], f["len"], f["nsym"], f["nsamp"], f["trellis"], f["total"]) == (0, 0, 94, 33, 2640, 774, 1584)
+    recs = ol.split_pdus(pdu)
+    assert len(recs) == 1
+    assert recs[0] == bytes([0, 94, 0]) + mpdu + bytes([0])      # [fmt][len lo][len hi][MPDU][mcs]
+    assert mpdu[:10].hex() == "08016e00f469d5800fa0"               # SURVEY 8c known answer
+
+
+def test_all_formats_clean(golden):
+    for i, x, mpdu, meta in _items(golden["frames_siso"]):
+        fr, llr, pdu = ol.rx_item(x)
+        f = fr[0]
+        assert f["status"] == 0, (i, meta, f["status"])
+        assert (f["format"], f["mcs"]) == (int(meta[0]), int(meta[1]))
+        recs = ol.split_pdus(pdu)
+        assert len(recs) >= 1 and recs[0][3:-1] == mpdu and recs[0][0] == int(meta[0]) and recs[0][-1] == int(meta[1]), (i, meta)
+        # CFO estimate: rad = -2 pi f / 20e6 (compensation sign, lib/sync_impl.cc:181-196)
+        assert abs(f["rad"] + 2 * np.pi * meta[2] / 20e6) < 2e-4
+
+
+def test_awgn_30db(golden):
+    rng = np.random.default_rng(13579)
+    sigma = np.sqrt(0.1875 ** 2 / 10 ** 3.0 / 2)                   # tools/performance/perf_siso.py:92 at 30 dB
+    ok = 0
+    items = list(_items(golden["frames_siso"]))
+    for i, x, mpdu, meta in items:
+        y = (x + sigma * (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size))).astype(np.complex64)
+        fr, llr, pdu = ol.rx_item(y)
+        recs = ol.split_pdus(pdu)
+        ok += int(len(recs) >= 1 and recs[0][3:-1] == mpdu)
+    assert ok == len(items)
+
+
+def test_two_subframe_ampdu_quirk(golden):
+    """lib/decode_impl.cc:336,346-351,415: tmpLen is OR-accumulated across subframes, so only the first
+    subframe of an A-MPDU is delivered.  The oracle reproduces that."""
+    g = golden["frames_siso"]
+    x = g["iq"][g["offs"][-2]:g["offs"][-1]]
+    fr, llr, pdu = ol.rx_item(x)
+    assert fr[0]["npdu"] == 1
+
+
+def test_noise_only_and_empty():
+    rng = np.random.default_rng(1)
+    x = (0.01 * (rng.standard_normal(5000) + 1j * rng.standard_normal(5000))).astype(np.complex64)
+    fr, llr, pdu = ol.rx_item(x)
+    assert fr[0]["status"] == 1 and pdu.size == 0
+    fr, llr, pdu = ol.rx_item(np.zeros(64, np.complex64))
+    assert fr[0]["status"] == 1
+
+
+def test_truncated_frame(golden):
+    i, x, mpdu, meta = next(_items(golden["frames_siso"]))
+    fr, llr, pdu = ol.rx_item(x[:2500])
+    assert fr[0]["status"] == 4 and pdu.size == 0
+
+
+def test_two_frames_in_one_item(golden):
+    items = list(_items(golden["frames_siso"]))
+    x = np.concatenate([items[3][1], items[20][1]])
+    fr, llr, pdu = ol.rx_item(x, max_frames=4)
+    recs = ol.split_pdus(pdu)
+    assert len(fr) == 2 and len(recs) == 2
+    assert recs[0][3:-1] == items[3][2] and recs[1][3:-1] == items[20][2]
+
+
+def test_batch_matches_item_loop(golden):
+    import ctypes as C
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    n = len(offs) - 1
+    lens = np.diff(offs).astype(np.int32)
+    frames = np.zeros(n, ol.FRAME_DTYPE)
+    stride = 4400
+    pdu = np.zeros(n * stride, np.uint8)
+    ol.oracle().orx_rx_batch(ol.c2f(g["iq"]), np.ascontiguousarray(offs[:-1]), lens, n, 4, frames.ctypes.data, pdu, stride)
+    for i, x, mpdu, meta in _items(g):
+        fr, llr, p1 = ol.rx_item(x, max_frames=1)
+        assert frames[i]["pdu_bytes"] == p1.size
+        assert bytes(pdu[i * stride: i * stride + p1.size]) == bytes(p1)
