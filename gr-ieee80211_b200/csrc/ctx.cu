@@ -1,0 +1,298 @@
+// ctx.cu -- context, scratch management and the C ABI of libc80211b200.so (include/c80211b200.h).
+// Host code only drives: every sample, soft bit and decoded byte is produced by the sm_100a kernels
+// in k_*.cu.  There is no CPU path: without a CUDA device c8b_create fails.
+#include <new>
+#include <string>
+#include <vector>
+#include <string.h>
+
+#include "common.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct c8b_ctx {
+    c8b_cfg cfg;
+    int device = 0, numSM = 0;
+    cudaStream_t st = nullptr, stCopy = nullptr;
+    std::string err;
+    c8b_lut* d_lut = nullptr;
+    bool lutLoaded = false;
+    unsigned* d_counter = nullptr;
+    // scratch (grown on demand)
+    DevBuf iq, preac, preconj, trig, off, len, frames, chan, hinv, llr, surv, pdu, scram, ev;
+    int survWarps = 0;
+    // timing
+    bool timing = false;
+    double ms[C8B_K_COUNT] = { 0 };
+    int64_t launches[C8B_K_COUNT] = { 0 };
+    struct Pending { int k; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> evPool;
+};
+
+static std::string g_createErr;
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return C8B_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static int ensure(c8b_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return C8B_OK;
+    if (b.p) { cudaStreamSynchronize(ctx->st); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+        return C8B_ERR_NOMEM;
+    }
+    b.cap = want;
+    return C8B_OK;
+}
+
+#define EN(buf, bytes)                                   \
+    do {                                                 \
+        int r_ = ensure(ctx, ctx->buf, (size_t)(bytes)); \
+        if (r_) return r_;                               \
+    } while (0)
+
+// ---- stage timing with CUDA events on the launching stream ---------------------------------------
+static cudaEvent_t ev_get(c8b_ctx* ctx)
+{
+    if (!ctx->evPool.empty()) { cudaEvent_t e = ctx->evPool.back(); ctx->evPool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct StageTimer {
+    c8b_ctx* ctx; int k; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(c8b_ctx* c, int kk) : ctx(c), k(kk)
+    {
+        if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, ctx->st); }
+    }
+    ~StageTimer()
+    {
+        if (ctx->timing) { cudaEventRecord(b, ctx->st); ctx->pending.push_back({ k, a, b }); }
+    }
+};
+static void timing_collect(c8b_ctx* ctx)
+{
+    for (auto& p : ctx->pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(p.b);
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { ctx->ms[p.k] += ms; ctx->launches[p.k]++; }
+        ctx->evPool.push_back(p.a);
+        ctx->evPool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+extern "C" {
+
+int c8b_abi_version(void) { return C8B_ABI_VERSION; }
+
+int c8b_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* c8b_last_error(const c8b_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createErr.c_str(); }
+
+int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
+{
+    if (!out) return C8B_ERR_ARG;
+    *out = nullptr;
+    int n = c8b_device_count();
+    if (n <= 0) { g_createErr = "no CUDA device visible: libc80211b200 has no CPU path"; return C8B_ERR_NO_DEVICE; }
+    c8b_ctx* ctx = new (std::nothrow) c8b_ctx();
+    if (!ctx) return C8B_ERR_NOMEM;
+    memset(&ctx->cfg, 0, sizeof(ctx->cfg));
+    if (cfg) ctx->cfg = *cfg;
+    if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = 16384;
+    if (ctx->cfg.ev_cap <= 0) ctx->cfg.ev_cap = 8;
+    ctx->device = ctx->cfg.device;
+    if (ctx->device < 0 || ctx->device >= n) { g_createErr = "bad device ordinal"; delete ctx; return C8B_ERR_ARG; }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stCopy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->numSM, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_lut, sizeof(c8b_lut));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 64);
+    if (e != cudaSuccess) { g_createErr = std::string("c8b_create: ") + cudaGetErrorString(e); delete ctx; return C8B_ERR_CUDA; }
+    *out = ctx;
+    return C8B_OK;
+}
+
+void c8b_destroy(c8b_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    timing_collect(ctx);
+    for (auto e : ctx->evPool) cudaEventDestroy(e);
+    DevBuf* bufs[] = { &ctx->iq, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
+                       &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev };
+    for (auto b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    if (ctx->stCopy) cudaStreamDestroy(ctx->stCopy);
+    delete ctx;
+}
+
+void* c8b_stream(c8b_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
+
+int c8b_sync(c8b_ctx* ctx)
+{
+    if (!ctx) return C8B_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+// ---- LUT ------------------------------------------------------------------------------------------
+size_t c8b_lut_size(void) { return sizeof(c8b_lut); }
+
+int c8b_lut_blob(void* buf, size_t cap)
+{
+    if (!buf || cap < sizeof(c8b_lut)) return C8B_ERR_ARG;
+    c8b_lut_build(reinterpret_cast<c8b_lut*>(buf));
+    return C8B_OK;
+}
+
+static int lut_check(c8b_ctx* ctx, const c8b_lut* h, size_t n)
+{
+    if (n != sizeof(c8b_lut) || h->magic != C8B_LUT_MAGIC || h->version != C8B_LUT_VERSION || h->bytes != sizeof(c8b_lut)) {
+        ctx->err = "LUT blob: wrong size/magic/version";
+        return C8B_ERR_LUT;
+    }
+    return C8B_OK;
+}
+
+int c8b_lut_load(c8b_ctx* ctx, const void* blob, size_t n)
+{
+    if (!ctx || !blob) return C8B_ERR_ARG;
+    int r = lut_check(ctx, reinterpret_cast<const c8b_lut*>(blob), n);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_lut, blob, n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->lutLoaded = true;
+    return C8B_OK;
+}
+
+int c8b_lut_load_dev(c8b_ctx* ctx, const void* d_blob, size_t n)
+{
+    if (!ctx || !d_blob || n != sizeof(c8b_lut)) return C8B_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    c8b_lut hdr;
+    CK(cudaMemcpy(&hdr, d_blob, sizeof(hdr), cudaMemcpyDeviceToHost));
+    int r = lut_check(ctx, &hdr, n);
+    if (r) return r;
+    CK(cudaMemcpyAsync(ctx->d_lut, d_blob, n, cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->lutLoaded = true;
+    return C8B_OK;
+}
+
+static int need_lut(c8b_ctx* ctx)
+{
+    if (!ctx->lutLoaded) { ctx->err = "LUT not loaded: call c8b_lut_load first"; return C8B_ERR_LUT; }
+    return C8B_OK;
+}
+
+// ---- timing ---------------------------------------------------------------------------------------
+int c8b_timing_enable(c8b_ctx* ctx, int on)
+{
+    if (!ctx) return C8B_ERR_ARG;
+    ctx->timing = on != 0;
+    return C8B_OK;
+}
+
+int c8b_timing_read(c8b_ctx* ctx, double ms[C8B_K_COUNT], int64_t launches[C8B_K_COUNT], int reset)
+{
+    if (!ctx) return C8B_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    timing_collect(ctx);
+    for (int i = 0; i < C8B_K_COUNT; i++) {
+        if (ms) ms[i] = ctx->ms[i];
+        if (launches) launches[i] = ctx->launches[i];
+        if (reset) { ctx->ms[i] = 0; ctx->launches[i] = 0; }
+    }
+    return C8B_OK;
+}
+
+// ---- decode stage ---------------------------------------------------------------------------------
+static int ensure_surv(c8b_ctx* ctx)
+{
+    int grid = c8b_viterbi_max_grid(ctx->numSM);
+    int warps = grid * C8B_VIT_WARPS;
+    if (ctx->survWarps >= warps) return C8B_OK;
+    EN(surv, (size_t)warps * C8B_VIT_TPAD * sizeof(uint2));
+    ctx->survWarps = warps;
+    return C8B_OK;
+}
+
+// device-resident decode of d_frames[0..n): LLR arena d_llr (nllr floats), PDUs to d_pdu
+static int decode_dev(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* d_llr, int64_t nllr, uint8_t* d_pdu,
+                      int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride)
+{
+    int r = ensure_surv(ctx);
+    if (r) return r;
+    StageTimer tm(ctx, C8B_K_VITERBI);
+    c8b_launch_viterbi(ctx->d_lut, d_frames, n, d_llr, nllr, (uint2*)ctx->surv.p, ctx->survWarps, d_pdu, pdu_stride, d_scram,
+                       scram_stride, ctx->d_counter, c8b_viterbi_max_grid(ctx->numSM), ctx->st);
+    CK(cudaGetLastError());
+    return C8B_OK;
+}
+
+int c8b_decode(c8b_ctx* ctx, const float* h_llr, int64_t nllr, c8b_frame* frames, int nframes, uint8_t* h_pdu,
+               int64_t pdu_stride, uint8_t* h_scram, int64_t scram_stride)
+{
+    if (!ctx || !h_llr || !frames || nframes < 0 || nllr < 0 || !h_pdu || pdu_stride <= 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nframes == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    EN(llr, (size_t)(nllr + 4) * sizeof(float));
+    EN(frames, (size_t)nframes * sizeof(c8b_frame));
+    EN(pdu, (size_t)nframes * pdu_stride);
+    if (h_scram) EN(scram, (size_t)nframes * scram_stride);
+    CK(cudaMemcpyAsync(ctx->llr.p, h_llr, (size_t)nllr * sizeof(float), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->frames.p, frames, (size_t)nframes * sizeof(c8b_frame), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->pdu.p, 0, (size_t)nframes * pdu_stride, ctx->st));
+    if (h_scram) CK(cudaMemsetAsync(ctx->scram.p, 0, (size_t)nframes * scram_stride, ctx->st));
+    r = decode_dev(ctx, (c8b_frame*)ctx->frames.p, nframes, (const float*)ctx->llr.p, nllr, (uint8_t*)ctx->pdu.p, pdu_stride,
+                   h_scram ? (uint8_t*)ctx->scram.p : nullptr, scram_stride);
+    if (r) return r;
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nframes * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_pdu, ctx->pdu.p, (size_t)nframes * pdu_stride, cudaMemcpyDeviceToHost, ctx->st));
+    if (h_scram) CK(cudaMemcpyAsync(h_scram, ctx->scram.p, (size_t)nframes * scram_stride, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+}  // extern "C"
+
+// ---- not yet wired (filled in as the kernels land) ------------------------------------------------
+extern "C" {
+#define C8B_TODO(ctx) do { if (ctx) (ctx)->err = "not implemented yet"; return C8B_ERR_ARG; } while (0)
+int c8b_rx_batch(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, uint8_t*, int64_t) { C8B_TODO(ctx); }
+int c8b_rx_batch_dev(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, uint8_t*, int64_t) { C8B_TODO(ctx); }
+int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, uint8_t*, int64_t) { C8B_TODO(ctx); }
+int c8b_presiso(c8b_ctx* ctx, const float*, int64_t, float*, float*) { C8B_TODO(ctx); }
+int c8b_trigger(c8b_ctx* ctx, const float*, int64_t, uint8_t*) { C8B_TODO(ctx); }
+int c8b_detect(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, float*) { C8B_TODO(ctx); }
+int c8b_demod(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, const float*, float*, int64_t) { C8B_TODO(ctx); }
+}

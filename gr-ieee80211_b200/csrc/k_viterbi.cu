@@ -1,0 +1,368 @@
+// k_viterbi.cu -- decode block on the GPU: depuncture + soft Viterbi (K=7, 64 states) + full
+// traceback + descramble + A-MPDU walk + CRC-32, one warp per frame, persistent CTAs.
+//
+// Replaces lib/decode_impl.cc:164-203 (vstb_init), :205-281 (vstb_update), :282-302 (vstb_end),
+// :304-323 (descramble), :325-520 (packetAssemble).  Results are bit-exact with the reference for
+// finite LLRs: path metrics are float32 sums formed in the reference's order (pre + tab[out],
+// tab = {0, t1, t0, t1+t0}), ties go to the even predecessor (strict '>' with 2k visited first),
+// the traceback starts in state 0 and runs over the whole packet.
+//
+// Forward pass.  A trellis step maps old states (2k, 2k+1) to new states (k, k+32): one butterfly.
+// Each lane keeps one butterfly's two old metrics in registers (x0 = metric[2k], x1 = metric[2k+1]),
+// so the add-compare-select needs no communication; the two results (k, k+32) then have to become
+// the (2k', 2k'+1) pair of some lane for the next step.  That is a swap of ONE lane-index bit with
+// the register index -- one __shfl_xor per step -- and the lane bit that is swapped rotates with
+// period 5 (phase P = t mod 5: the butterfly k of step t lives in lane rotl5(k, P)).
+// Branch metrics: the step's table {0, t1, t0, t1+t0} is staged in shared memory (depunctured on
+// load, 160 steps ahead) and each lane reads its two entries A = tab[c], B = tab[3-c] (c = encoder
+// output of 2k --0--> k; the other three branches of the butterfly follow from both generator
+// polynomials having taps at the newest and the oldest bit).
+// Decisions: the sign of (even - odd) is shifted into a per-lane 32-bit history word (one per
+// result), so after 32 steps every lane owns 2x32 decisions: 256 B per warp, one coalesced store.
+//
+// Traceback.  Runs in the same rotated domain: sigma = 2*lane + word selects the history word that
+// holds the decision of the current state; a step is a shared-memory read, a rotate and two LOP3.
+// All lanes execute it redundantly (uniform control flow); decoded bits are packed LSB-first into
+// 32-bit words in shared memory, which makes the word array the PSDU byte stream directly.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CH = C8B_VIT_CH;                 // 150 trellis steps per chunk
+constexpr int GS = 30;                         // steps per decision group (one 30-bit history word per lane and result)
+constexpr int NG = CH / GS;                    // 5 groups per chunk
+constexpr int NW = C8B_VIT_WARPS;
+constexpr int NLD = (CH + 31) / 32;            // table rows each lane fills per chunk
+constexpr int MAXG = (C8B_DECODE_T_MAX + GS - 1) / GS;   // 1093 groups in the longest packet
+constexpr int WORDS = (C8B_DECODE_T_MAX + 31) / 32 + 8;  // decoded-bit words per warp (+ slack)
+static_assert(CH % 5 == 0 && GS % 5 == 0 && CH % GS == 0, "phases must align with groups");
+static_assert(((C8B_DECODE_T_MAX + CH - 1) / CH) * NG * 32 <= C8B_VIT_TPAD, "survivor scratch too small");
+static_assert(MAXG * 4 <= 2 * CH * 16, "group bits must fit in the (dead) table buffers");
+
+struct __align__(16) WarpSmem {
+    float4 tab[2][CH];      // per step {0, t1, t0, t1+t0} (lib/decode_impl.cc:231-234), double buffered;
+                            // during traceback the same bytes hold gbits[MAXG]: 30 decoded bits per group
+    uint32_t surv[NG * 64]; // traceback: decision words of one chunk, [group][lane][lo,hi]
+    uint32_t words[WORDS];  // decoded bits packed LSB-first, descrambled in place -> PSDU bytes
+    uint32_t scr[8];        // scrambler sequence, 160 bits
+};
+
+__device__ __forceinline__ int rotr5(int x, int p) { return ((x >> p) | (x << (5 - p))) & 31; }
+
+// soft-bit indices of trellis step t for code rate cr; -1 = punctured position (metric 0.0f).
+// Puncture patterns of lib/cloud80211phy.cc:1857-1860 in closed form.
+__device__ __forceinline__ void depunc(int cr, int t, int& i0, int& i1)
+{
+    if (cr == C8B_CR_12) { i0 = 2 * t; i1 = 2 * t + 1; }
+    else if (cr == C8B_CR_23) { int q = t >> 1, b = 3 * q; if (t & 1) { i0 = b + 2; i1 = -1; } else { i0 = b; i1 = b + 1; } }
+    else if (cr == C8B_CR_34) {
+        int q = t / 3, r = t - 3 * q, b = 4 * q;
+        if (r == 0) { i0 = b; i1 = b + 1; } else if (r == 1) { i0 = b + 2; i1 = -1; } else { i0 = -1; i1 = b + 3; }
+    } else {
+        int q = t / 5, r = t - 5 * q, b = 6 * q;
+        if (r == 0) { i0 = b; i1 = b + 1; }
+        else if (r == 1) { i0 = b + 2; i1 = -1; }
+        else if (r == 2) { i0 = -1; i1 = b + 3; }
+        else if (r == 3) { i0 = b + 4; i1 = -1; }
+        else { i0 = -1; i1 = b + 5; }
+    }
+}
+
+__device__ __forceinline__ float4 load_tab(const float* __restrict__ llr, int total, int cr, int t, int T)
+{
+    float t0 = 0.f, t1 = 0.f;
+    if (t < T) {
+        int i0, i1;
+        depunc(cr, t, i0, i1);
+        if (i0 >= 0 && i0 < total) t0 = __ldg(llr + i0);
+        if (i1 >= 0 && i1 < total) t1 = __ldg(llr + i1);
+    }
+    return make_float4(0.0f, t1, t0, __fadd_rn(t1, t0));
+}
+
+// one add-compare-select step at layout phase P.  (x0,x1) in: metrics of old states (2k,2k+1);
+// out: metrics of (2k',2k'+1) for the next phase.  hLo/hHi: decision history of this lane.
+template <int P>
+__device__ __forceinline__ void acs_step(float& x0, float& x1, const float A, const float B, const uint32_t amask,
+                                         uint32_t& hLo, uint32_t& hHi)
+{
+    const float eLo = __fadd_rn(x0, A), oLo = __fadd_rn(x1, B);   // into state k      (input 0)
+    const float eHi = __fadd_rn(x0, B), oHi = __fadd_rn(x1, A);   // into state k + 32 (input 1)
+    // odd predecessor wins only if strictly larger  <=>  (even - odd) is negative
+    const uint32_t sLo = __float_as_uint(__fsub_rn(eLo, oLo)), sHi = __float_as_uint(__fsub_rn(eHi, oHi));
+    const uint32_t y0 = __float_as_uint(fmaxf(eLo, oLo)), y1 = __float_as_uint(fmaxf(eHi, oHi));
+    hLo = __funnelshift_l(sLo, hLo, 1);                            // (hLo << 1) | sign
+    hHi = __funnelshift_l(sHi, hHi, 1);
+    // swap lane bit P with the register index: lanes with the bit set send y0 and keep y1
+    const uint32_t send = (y0 & amask) | (y1 & ~amask);
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1 << P);
+    x0 = __uint_as_float((recv & amask) | (y0 & ~amask));
+    x1 = __uint_as_float((y1 & amask) | (recv & ~amask));
+}
+
+// traceback step for group-relative step index i (0..29); POS = ((i % 5) + 4) % 5.
+// sig4 = 4*(2*rho + h): byte offset of the decision word inside the group's 256-byte block;
+// the decision of step i sits at bit (GS-1-i) of that word.
+__device__ __forceinline__ void tb_step(uint32_t& sig4, uint32_t& acc, const uint32_t* __restrict__ grp, const int i)
+{
+    const int POS = ((i % 5) + 4) % 5;
+    const uint32_t M = 8u << POS;                                    // bit of rho[POS] inside sig4
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(grp) + sig4);
+    acc = (acc << 1) | ((sig4 >> 2) & 1u);                           // decoded bit = h (input bit of the state entered)
+    const uint32_t hn = (sig4 >> (POS + 1)) & 4u;                    // next h = old rho[POS], placed at bit 2
+    const uint32_t pre = (sig4 & ~(M | 4u)) | hn;
+    const uint32_t rot = __funnelshift_r(w, w, (GS - 1 - i - POS - 3) & 31);   // decision bit -> bit POS+3
+    sig4 = pre | (rot & M);
+}
+
+// CRC-32 (boost::crc_32_type, lib/decode_impl.h:84): reflected 0x04C11DB7, init/xorout ~0.
+__device__ __forceinline__ uint32_t crc32_smem(const uint32_t* __restrict__ tab, const uint8_t* __restrict__ p, int n)
+{
+    uint32_t c = 0xffffffffu;
+    for (int i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+    return ~c;
+}
+
+// append one record [fmt][len lo][len hi][MPDU][mcs] to the frame's PDU area (all lanes cooperate)
+__device__ __forceinline__ void emit_record(uint8_t* __restrict__ out, int& w, int cap, int& npdu, int fmt, int lenField,
+                                            const uint8_t* __restrict__ body, int nbody, int mcs, int lane)
+{
+    const int rec = nbody + 4;
+    if (w + rec > cap) return;
+    uint8_t* o = out + w;
+    if (lane == 0) { o[0] = (uint8_t)fmt; o[1] = (uint8_t)(lenField & 255); o[2] = (uint8_t)(lenField >> 8); o[3 + nbody] = (uint8_t)mcs; }
+    for (int i = lane; i < nbody; i += 32) o[3 + i] = body[i];
+    w += rec;
+    npdu++;
+}
+
+__global__ void __launch_bounds__(NW * 32, 5)
+k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
+          int64_t nllr, uint2* __restrict__ survScratch, uint8_t* __restrict__ pdu, int64_t pduStride,
+          uint8_t* __restrict__ scram, int64_t scramStride, unsigned* __restrict__ counter)
+{
+    __shared__ WarpSmem sm[NW];
+    __shared__ uint32_t crcTab[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 256; i += NW * 32) crcTab[i] = lut->crc32tab[i];
+    __syncthreads();
+    WarpSmem& S = sm[warp];
+    uint2* __restrict__ survG = survScratch + (size_t)(blockIdx.x * NW + warp) * C8B_VIT_TPAD;
+    const bool lane0 = lane == 0;
+
+    // per-phase: index of this lane's A entry in the step table, and its side in the exchange
+    int cA[5];
+    uint32_t amask[5];
+#pragma unroll
+    for (int p = 0; p < 5; p++) {
+        cA[p] = lut->bmClass[rotr5(lane, p)];
+        uint32_t m = ((lane >> p) & 1) ? 0xffffffffu : 0u;
+        asm volatile("" : "+r"(m));                                  // keep it a register mask (LOP3), not a predicate
+        amask[p] = m;
+    }
+
+    for (;;) {
+        int f = 0;
+        if (lane0) f = (int)atomicAdd(counter, 1u);
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (f >= nframes) break;
+        c8b_frame* fr = frames + f;
+        if (fr->status != C8B_ST_OK) {
+            if (lane0) { fr->npdu = 0; fr->pdu_bytes = 0; fr->pdu_off = (int64_t)f * pduStride; }
+            continue;
+        }
+        const int T = fr->trellis, cr = fr->cr & 3, total = fr->total, fmt = fr->format, len = fr->len, mcs = fr->mcs, ampdu = fr->ampdu;
+        const int64_t loff = fr->llr_off;
+        __syncwarp();
+        if (lane0) { fr->npdu = 0; fr->pdu_bytes = 0; fr->pdu_off = (int64_t)f * pduStride; }
+        if (len > C8B_DECODE_B_MAX || T > C8B_DECODE_T_MAX) {      // lib/decode_impl.cc:93-97
+            if (lane0) fr->status = C8B_ST_DECODE_RANGE;
+            continue;
+        }
+        if (T <= 0 || total < 0 || loff < 0 || loff + total > nllr) continue;
+        const float* __restrict__ llr = llrArena + loff;
+        const int nch = (T + CH - 1) / CH;
+
+        // ---------------- forward pass ----------------
+        float x0 = lane0 ? 0.0f : -1000000000000000.0f;          // lib/decode_impl.cc:171-176
+        float x1 = -1000000000000000.0f;
+        float4 pf[NLD];
+#pragma unroll
+        for (int j = 0; j < NLD; j++)
+            if (lane + 32 * j < CH) S.tab[0][lane + 32 * j] = load_tab(llr, total, cr, lane + 32 * j, T);
+        __syncwarp();
+        for (int c = 0; c < nch; c++) {
+            const int buf = c & 1;
+            const bool more = c + 1 < nch;
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < NLD; j++) pf[j] = load_tab(llr, total, cr, (c + 1) * CH + lane + 32 * j, T);
+            }
+            const float* __restrict__ tb = reinterpret_cast<const float*>(S.tab[buf]);
+            const float* pA0 = tb + 0 + cA[0], *pB0 = tb + 3 - cA[0];
+            const float* pA1 = tb + 4 + cA[1], *pB1 = tb + 7 - cA[1];
+            const float* pA2 = tb + 8 + cA[2], *pB2 = tb + 11 - cA[2];
+            const float* pA3 = tb + 12 + cA[3], *pB3 = tb + 15 - cA[3];
+            const float* pA4 = tb + 16 + cA[4], *pB4 = tb + 19 - cA[4];
+            uint2* __restrict__ sg = survG + (size_t)c * (NG * 32) + lane;
+#pragma unroll 1
+            for (int g = 0; g < NG; g++) {
+                uint32_t hLo = 0, hHi = 0;
+#pragma unroll
+                for (int i5 = 0; i5 < GS / 5; i5++) {               // 30 steps, all shared-memory offsets immediate
+                    const int o = (g * (GS / 5)) * 0 + i5 * 20;
+                    acs_step<0>(x0, x1, pA0[o], pB0[o], amask[0], hLo, hHi);
+                    acs_step<1>(x0, x1, pA1[o], pB1[o], amask[1], hLo, hHi);
+                    acs_step<2>(x0, x1, pA2[o], pB2[o], amask[2], hLo, hHi);
+                    acs_step<3>(x0, x1, pA3[o], pB3[o], amask[3], hLo, hHi);
+                    acs_step<4>(x0, x1, pA4[o], pB4[o], amask[4], hLo, hHi);
+                }
+                sg[g * 32] = make_uint2(hLo, hHi);
+                pA0 += GS * 4; pB0 += GS * 4; pA1 += GS * 4; pB1 += GS * 4; pA2 += GS * 4; pB2 += GS * 4;
+                pA3 += GS * 4; pB3 += GS * 4; pA4 += GS * 4; pB4 += GS * 4;
+            }
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < NLD; j++)
+                    if (lane + 32 * j < CH) S.tab[buf ^ 1][lane + 32 * j] = pf[j];
+            }
+            __syncwarp();
+        }
+
+        // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
+        // gbits[G] = decoded bits of steps 30G .. 30G+29 (bit i = step 30G+i); lives in the dead tab area
+        uint32_t* __restrict__ gbits = reinterpret_cast<uint32_t*>(&S.tab[0][0]);
+        {
+            uint32_t sig4 = 0;
+            for (int c = nch - 1; c >= 0; c--) {
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < NG; j++) {
+                    const uint2 v = survG[(size_t)c * (NG * 32) + j * 32 + lane];
+                    *reinterpret_cast<uint2*>(&S.surv[(j * 32 + lane) * 2]) = v;
+                }
+                __syncwarp();
+                for (int g = NG - 1; g >= 0; g--) {
+                    const int t0g = c * CH + g * GS;                 // first step of the group
+                    if (t0g >= T) continue;
+                    const uint32_t* __restrict__ grp = S.surv + g * 64;
+                    uint32_t acc = 0;
+                    if (t0g + GS <= T) {
+#pragma unroll
+                        for (int i = GS - 1; i >= 0; i--) tb_step(sig4, acc, grp, i);
+                    } else {                                         // the packet ends inside this group
+                        for (int i = T - t0g - 1; i >= 0; i--) tb_step(sig4, acc, grp, i);
+                    }
+                    if (lane0) gbits[c * NG + g] = acc;
+                }
+            }
+        }
+        __syncwarp();
+        // repack 30-bit groups into the 32-bit LSB-first word stream (word w = steps 32w .. 32w+31)
+        {
+            const int ngroups = (T + GS - 1) / GS;
+            for (int w = lane; w < ((T + 31) >> 5); w += 32) {
+                const int b0 = 32 * w, G = b0 / GS, off = b0 - G * GS;
+                uint32_t v = gbits[G] >> off;                        // GS-off bits
+                if (G + 1 < ngroups) v |= gbits[G + 1] << (GS - off);
+                if (2 * GS - off < 32 && G + 2 < ngroups) v |= gbits[G + 2] << (2 * GS - off);
+                S.words[w] = v;
+            }
+        }
+        __syncwarp();
+        const int nwords = (T + 31) >> 5;
+        if (scram != nullptr) {
+            uint8_t* so = scram + (size_t)f * scramStride;
+            for (int i = lane; i < T && i < scramStride; i += 32) so[i] = (uint8_t)((S.words[i >> 5] >> (i & 31)) & 1u);
+        }
+
+        // ---------------- descramble (lib/decode_impl.cc:304-323) ----------------
+        {
+            const uint32_t w0 = S.words[0];
+            int st = 0;
+#pragma unroll
+            for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
+            __syncwarp();
+            for (int wq = 0; wq < 5; wq++) {
+                uint32_t q = 0;
+#pragma unroll 8
+                for (int b = 0; b < 32; b++) {
+                    const int fb = ((st >> 6) ^ (st >> 3)) & 1;
+                    st = ((st << 1) & 0x7e) | fb;
+                    q |= (uint32_t)fb << b;
+                }
+                if (lane0) S.scr[wq] = q;
+            }
+            __syncwarp();
+            for (int w = lane; w < nwords; w += 32) {
+                uint32_t v = S.words[w];
+                if (w == 0) v = (v ^ (S.scr[0] << 7)) & ~0x7fu;
+                else {
+                    const int o = (32 * w - 7) % 127;
+                    v ^= __funnelshift_r(S.scr[o >> 5], S.scr[(o >> 5) + 1], o & 31);
+                }
+                S.words[w] = v;
+            }
+            __syncwarp();
+        }
+
+        // ---------------- packetAssemble (lib/decode_impl.cc:325-520) ----------------
+        {
+            const uint8_t* __restrict__ by = reinterpret_cast<const uint8_t*>(S.words);
+            uint8_t* out = pdu + (size_t)f * pduStride;
+            const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
+            int npdu = 0, w = 0;
+            if (fmt == C8B_F_VHT) {
+                int procd = 16;
+                if (procd < T) {
+                    int bp = 2;                                      // byte offset of the next delimiter
+                    int tl = 0;                                      // NOT reset per subframe (:336)
+                    while (true) {
+                        procd += 32;
+                        if (procd > T) break;
+                        const int d0 = by[bp], d1 = by[bp + 1];
+                        const int eof = d0 & 1;
+                        tl |= ((d0 >> 2) & 1) << 12;
+                        tl |= ((d0 >> 3) & 1) << 13;
+                        tl |= (d0 >> 4) | (d1 << 4);
+                        const int padded = (tl / 4 + ((tl % 4) != 0)) * 4;   // bytes
+                        procd += padded * 8;
+                        if (procd > T) break;
+                        bp += 4;
+                        const uint32_t crc = crc32_smem(crcTab, by + bp, tl);
+                        if (crc == 558161692u) {
+                            emit_record(out, w, cap, npdu, fmt, tl, by + bp, tl, mcs, lane);
+                            tl += 4;                                 // :415, carried into the next subframe
+                        }
+                        bp += padded;
+                        if (eof) break;
+                    }
+                }
+            } else if (!ampdu) {
+                if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
+                    const uint32_t crc = crc32_smem(crcTab, by + 2, len);
+                    if (crc == 558161692u) emit_record(out, w, cap, npdu, fmt, len, by + 2, len, mcs, lane);
+                }
+            }
+            if (lane0) { fr->npdu = npdu; fr->pdu_bytes = w; }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int c8b_viterbi_max_grid(int num_sm) { return num_sm * 5; }
+
+void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, uint2* d_surv,
+                        int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride,
+                        unsigned* d_counter, int grid, cudaStream_t st)
+{
+    if (nframes <= 0) return;
+    int need = (nframes + NW - 1) / NW;
+    if (grid > need) grid = need;
+    if (grid * NW > nwarps_alloc) grid = nwarps_alloc / NW;
+    cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st);
+    k_viterbi<<<grid, NW * 32, 0, st>>>(d_lut, d_frames, nframes, d_llr, nllr, d_surv, d_pdu, pdu_stride, d_scram, scram_stride,
+                                         d_counter);
+}

@@ -1,0 +1,27 @@
+// lut.h -- the lookup-table blob shared by all kernels (and broadcast between ranks).
+// Plain POD, built on the host by formula in lut.cc; lives in device global memory.
+// Equivalent reference tables: lib/cloud80211phy.cc:30-31 (SIG demap), :95-140 (LTF signs),
+// :160-174 (pilots), :1413-1831 (deinterleave maps), :1864-1887 (trellis), boost::crc_32_type.
+#pragma once
+#include <stdint.h>
+
+#define C8B_LUT_MAGIC 0x4c423843u /* "C8BL" */
+#define C8B_LUT_VERSION 2u
+
+struct c8b_lut {
+    uint32_t magic, version, bytes, pad0;
+    float ltfL[64];            // L-LTF sign per FFT bin (0 on unused bins)
+    float ltfNL[64];           // HT/VHT-LTF sign per FFT bin
+    float ltfNL22[64];         // second VHT-LTF as seen by user position 1 (pilot bins negated)
+    float pilotP[128];         // pilot polarity p_0..p_126 (+ pad)
+    float twr[64], twi[64];    // W64^k = exp(-2 pi j k / 64)
+    uint16_t deintL[4][288];   // legacy: nBPSC 1,2,4,6      out[map[i]] = in[i]
+    uint16_t deintNL[2][5][416]; // HT/VHT 20 MHz: [iss-1][nBPSCS 1,2,4,6,8]
+    int8_t sigDemap[64];       // FFT bin -> deinterleaved SIG llr index (-1: not a data tone)
+    uint8_t bmClass[32];       // butterfly k: encoder output (o0*2+o1) of transition 2k --0--> k
+    uint8_t binToDataL[64];    // FFT bin -> data index 0..47 in -26..26 order (255: null/pilot)
+    uint8_t binToDataNL[64];   // FFT bin -> data index 0..51 in -28..28 order (255: null/pilot)
+    uint32_t crc32tab[256];    // reflected 0xEDB88320
+};
+
+void c8b_lut_build(c8b_lut* L);   // host, by formula (lut.cc)

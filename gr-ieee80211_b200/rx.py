@@ -1,0 +1,162 @@
+"""Receiver: the batched, device-side counterpart of the reference flowgraph examples/rx.grc:753-767
+(file source -> presiso -> trigger -> sync -> signal -> demod -> decode -> PDUs), plus the staged
+entry points mirroring one reference block each (used by the parity tests and for profiling)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import C8bCfg, C8bError, FRAME_DTYPE, ptr
+
+
+def lut_blob():
+    """The lookup-table blob (uint8 array), built by formula on the host (csrc/lut.cc)."""
+    L = _cabi.lib()
+    n = L.c8b_lut_size()
+    buf = np.zeros(n, np.uint8)
+    rc = L.c8b_lut_blob(ptr(buf), n)
+    if rc:
+        raise C8bError("c8b_lut_blob failed: %d" % rc)
+    return buf
+
+
+def _c2f(x):
+    x = np.asarray(x)
+    if x.dtype == np.complex64:
+        return np.ascontiguousarray(x).view(np.float32)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def split_pdus(buf):
+    """PDU area -> list of records [fmt][len lo][len hi][MPDU][mcs] (lib/decode_impl.cc:359-361,414-419)."""
+    out, i, buf = [], 0, bytes(buf)
+    while i + 3 <= len(buf):
+        ln = buf[i + 1] | (buf[i + 2] << 8)
+        out.append(buf[i: i + ln + 4])
+        i += ln + 4
+    return out
+
+
+class Receiver:
+    """One context = one GPU + one stream.  `blob`: LUT blob to load (default: build locally; multi-GPU
+    runs pass the blob broadcast from rank 0)."""
+
+    def __init__(self, device=0, chunk_items=16384, max_item_len=0, ev_cap=8, mupos=0, mugid=0, blob=None):
+        self.L = _cabi.lib()
+        if self.L.c8b_device_count() <= 0:
+            raise C8bError("no CUDA device visible: gr-ieee80211_b200 has no CPU path")
+        cfg = C8bCfg(device=device, chunk_items=chunk_items, max_item_len=max_item_len, ev_cap=ev_cap, mupos=mupos, mugid=mugid)
+        h = C.c_void_p()
+        rc = self.L.c8b_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise C8bError("c8b_create: %d %s" % (rc, (self.L.c8b_last_error(None) or b"").decode()))
+        self.h = h
+        blob = lut_blob() if blob is None else np.ascontiguousarray(blob, dtype=np.uint8)
+        self._ck(self.L.c8b_lut_load(self.h, ptr(blob), blob.size), "c8b_lut_load")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.c8b_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc:
+            raise C8bError("%s: %d %s" % (what, rc, (self.L.c8b_last_error(self.h) or b"").decode()))
+
+    @property
+    def stream(self):
+        return self.L.c8b_stream(self.h)
+
+    def load_lut_device(self, dev_ptr, nbytes):
+        self._ck(self.L.c8b_lut_load_dev(self.h, C.c_void_p(dev_ptr), nbytes), "c8b_lut_load_dev")
+
+    def sync(self):
+        self._ck(self.L.c8b_sync(self.h), "c8b_sync")
+
+    # ---- timing -------------------------------------------------------------------------------
+    def timing(self, on=True):
+        self._ck(self.L.c8b_timing_enable(self.h, int(on)), "c8b_timing_enable")
+
+    def timing_read(self, reset=True):
+        ms = np.zeros(len(_cabi.K_NAMES), np.float64)
+        n = np.zeros(len(_cabi.K_NAMES), np.int64)
+        self._ck(self.L.c8b_timing_read(self.h, ptr(ms), ptr(n), int(reset)), "c8b_timing_read")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_cabi.K_NAMES)}
+
+    # ---- whole chain --------------------------------------------------------------------------
+    def rx_batch(self, iq, off, length, pdu_stride=4400):
+        """iq: complex64 host array; item i = iq[off[i]:off[i]+length[i]].  Returns (frames, pdu)."""
+        iqf = _c2f(iq)
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        n = off.size
+        frames = np.zeros(n, FRAME_DTYPE)
+        pdu = np.zeros(n * pdu_stride, np.uint8)
+        self._ck(self.L.c8b_rx_batch(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch")
+        return frames, pdu.reshape(n, pdu_stride)
+
+    def rx_batch_dev(self, d_iq_ptr, off, length, pdu_stride=4400, frames=None, pdu=None):
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        n = off.size
+        frames = np.zeros(n, FRAME_DTYPE) if frames is None else frames
+        pdu = np.zeros(n * pdu_stride, np.uint8) if pdu is None else pdu
+        self._ck(self.L.c8b_rx_batch_dev(self.h, C.c_void_p(d_iq_ptr), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride),
+                 "c8b_rx_batch_dev")
+        return frames, pdu.reshape(n, pdu_stride)
+
+    def rx_batch_dev_async(self, d_iq_ptr, off, length, d_frames_ptr, d_pdu_ptr, pdu_stride=4400):
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        self._ck(self.L.c8b_rx_batch_dev_async(self.h, C.c_void_p(d_iq_ptr), ptr(off), ptr(length), off.size, C.c_void_p(d_frames_ptr),
+                                               C.c_void_p(d_pdu_ptr), pdu_stride), "c8b_rx_batch_dev_async")
+
+    # ---- staged -------------------------------------------------------------------------------
+    def presiso(self, iq, want_conj=True):
+        iqf = _c2f(iq)
+        n = iqf.size // 2
+        preac = np.zeros(n, np.float32)
+        preconj = np.zeros(2 * n, np.float32) if want_conj else None
+        self._ck(self.L.c8b_presiso(self.h, ptr(iqf), n, ptr(preac), ptr(preconj)), "c8b_presiso")
+        return preac, (preconj.view(np.complex64) if want_conj else None)
+
+    def trigger(self, preac):
+        preac = np.ascontiguousarray(preac, np.float32)
+        out = np.zeros(preac.size, np.uint8)
+        self._ck(self.L.c8b_trigger(self.h, ptr(preac), preac.size, ptr(out)), "c8b_trigger")
+        return out
+
+    def detect(self, iq, off, length):
+        iqf = _c2f(iq)
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        n = off.size
+        frames = np.zeros(n, FRAME_DTYPE)
+        chan = np.zeros(n * 128, np.float32)
+        self._ck(self.L.c8b_detect(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(chan)), "c8b_detect")
+        return frames, chan.view(np.complex64).reshape(n, 64)
+
+    def demod(self, iq, off, length, frames, chan, llr_stride):
+        iqf = _c2f(iq)
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        n = off.size
+        frames = np.ascontiguousarray(frames).copy()
+        chanf = _c2f(chan)
+        llr = np.zeros(n * llr_stride, np.float32)
+        self._ck(self.L.c8b_demod(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(chanf), ptr(llr), llr_stride), "c8b_demod")
+        return frames, llr.reshape(n, llr_stride)
+
+    def decode(self, llr, frames, pdu_stride=4400, want_scram=False, scram_stride=0):
+        llr = np.ascontiguousarray(llr, np.float32).reshape(-1)
+        frames = np.ascontiguousarray(frames).copy()
+        n = frames.size
+        pdu = np.zeros(n * pdu_stride, np.uint8)
+        scram = None
+        if want_scram:
+            scram_stride = scram_stride or int(max(1, frames["trellis"].max()))
+            scram = np.zeros(n * scram_stride, np.uint8)
+        self._ck(self.L.c8b_decode(self.h, ptr(llr), llr.size, ptr(frames), n, ptr(pdu), pdu_stride, ptr(scram), scram_stride), "c8b_decode")
+        return frames, pdu.reshape(n, pdu_stride), (scram.reshape(n, scram_stride) if want_scram else None)

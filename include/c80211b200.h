@@ -1,0 +1,180 @@
+/* c80211b200.h -- C ABI of libc80211b200.so: the B200 (sm_100a) implementation of the
+ * gr-ieee80211 20 MHz OFDM receive chain  presiso -> trigger -> sync -> signal -> demod -> decode.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  A gr::block shell
+ * (or the ctypes host code in gr-ieee80211_b200/) calls these instead of the reference's scalar C++:
+ *
+ *   reference interface replaced                          entry point here
+ *   ---------------------------------------------------  ---------------------------------------
+ *   examples/presiso.grc:35-229 (stock GR hier block)     c8b_presiso
+ *   lib/trigger_impl.cc:59-117  trigger::general_work     c8b_trigger        (+ inside c8b_detect)
+ *   lib/sync_impl.cc:61-196     sync::general_work        c8b_detect         (trigger+sync+signal)
+ *   lib/signal_impl.cc:62-206   signal::general_work      c8b_detect / CFO copy fused in c8b_demod
+ *   lib/demod_impl.cc:59-557    demod::general_work       c8b_demod          (header + symbols)
+ *   lib/decode_impl.cc:60-520   decode::general_work      c8b_decode / c8b_viterbi
+ *   whole flowgraph examples/rx.grc:753-767               c8b_rx_batch / c8b_rx_batch_dev
+ *   LUTs of lib/cloud80211phy.cc (c8p.h:151-195)          c8b_lut_blob / c8b_lut_load
+ *
+ * Conventions: every function returns 0 on success or a negative C8B_ERR_* code (never throws,
+ * never aborts; c8b_last_error() gives the text).  The caller owns every buffer it passes.  One
+ * c8b_ctx = one CUDA device + one stream + its scratch; a ctx is not re-entrant, different ctxs
+ * are independent (thread-per-block safe, like the reference's blocks).  There is NO CPU
+ * fallback: without a CUDA device c8b_create fails with C8B_ERR_NO_DEVICE.
+ *
+ * IQ layout everywhere: interleaved float32 (re,im) = GNU Radio gr_complex = numpy complex64.
+ */
+#ifndef C80211B200_H
+#define C80211B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C8B_ABI_VERSION 1
+
+/* error codes (return values) */
+#define C8B_OK 0
+#define C8B_ERR_NO_DEVICE (-1)   /* no CUDA device / driver: the library refuses to run       */
+#define C8B_ERR_CUDA (-2)        /* a CUDA call failed (text in c8b_last_error)               */
+#define C8B_ERR_ARG (-3)         /* bad argument / size over the ctx capacity                 */
+#define C8B_ERR_LUT (-4)         /* LUT blob missing, wrong magic/version/size                */
+#define C8B_ERR_NOMEM (-5)
+
+/* per-frame status, in pipeline order (what the reference's blocks do at that point) */
+#define C8B_ST_OK 0              /* frame reached decode (PDU count may still be 0: CRC fail)  */
+#define C8B_ST_NO_TRIGGER 1      /* no 0x01 trigger in the item   (lib/trigger_impl.cc:101-109) */
+#define C8B_ST_SYNC 2            /* LTF autocorr max <= 0.5       (lib/sync_impl.cc:99)         */
+#define C8B_ST_LSIG 3            /* every L-SIG check failed      (lib/signal_impl.cc:156-160)  */
+#define C8B_ST_TRUNC 4           /* frame runs past the end of the item                         */
+#define C8B_ST_FORMAT 5          /* HT/VHT sanity failed -> CLEAN (lib/demod_impl.cc:167,194)   */
+#define C8B_ST_DECODE_RANGE 6    /* len>4095 or trellis>32782     (lib/decode_impl.cc:93-97)    */
+#define C8B_ST_NDP 7             /* VHT NDP (nSym==0): no PDU                                   */
+#define C8B_ST_OVERFLOW 8        /* more events in the item than the ctx was sized for          */
+
+/* formats / code rates: same numbering as lib/cloud80211phy.h:35-49 */
+#define C8B_F_L 0
+#define C8B_F_HT 1
+#define C8B_F_VHT 2
+#define C8B_CR_12 0
+#define C8B_CR_23 1
+#define C8B_CR_34 2
+#define C8B_CR_56 3
+
+/* One received frame: the union of the tags the reference's blocks attach
+ * (sync: rad/snr/rssi lib/sync_impl.cc:124-136; signal: cfo/mcs/len/nsamp lib/signal_impl.cc:135-152;
+ * demod: format/mcs/len/cr/ampdu/trellis/total/sssnr lib/demod_impl.cc:224-263) plus bookkeeping. */
+typedef struct c8b_frame {
+    int32_t status;
+    int32_t item;
+    int32_t trig_idx;      /* item-relative index of the 0x01 trigger                             */
+    int32_t sync_idx;      /* item-relative index of the sync flag (LTF start + 16)               */
+    float   rad;           /* CFO compensation step, rad/sample                                   */
+    float   snr;
+    float   rssi;
+    float   cfo_hz;        /* rad * 20e6 / (2 pi)                                                 */
+    int32_t l_mcs;         /* L-SIG rate index, length, nsamp                                     */
+    int32_t l_len;
+    int32_t nsamp;
+    int32_t format;        /* C8B_F_*                                                             */
+    int32_t mcs;
+    int32_t len;
+    int32_t cr;            /* C8B_CR_*                                                            */
+    int32_t ampdu;
+    int32_t nss;
+    int32_t nsym;
+    int32_t nsymsamp;
+    int32_t ncbps;
+    int32_t ndbps;
+    int32_t trellis;
+    int32_t total;         /* nSym * nCBPS soft bits                                              */
+    int32_t data_off;      /* sample index (relative to sync_idx+224) of the first DATA symbol    */
+    float   sssnr0;
+    float   sssnr1;
+    int64_t llr_off;       /* offset (floats) of this frame's LLR stream in the LLR arena         */
+    int64_t pdu_off;       /* offset (bytes) of this frame's PDU records in the PDU arena         */
+    int32_t npdu;          /* PDUs published; record = [fmt][len lo][len hi][MPDU][mcs]           */
+    int32_t pdu_bytes;     /* (lib/decode_impl.cc:359-361,414-419,439-441,512-516)                */
+} c8b_frame;
+
+typedef struct c8b_cfg {
+    int32_t device;          /* CUDA device ordinal                                               */
+    int32_t chunk_items;     /* items processed per pipeline pass (scratch is sized for this)     */
+    int32_t max_item_len;    /* longest item, complex samples                                     */
+    int32_t ev_cap;          /* sync events kept per item (0 -> 8)                                */
+    int32_t mupos;           /* demod(mupos, mugid) ctor args (lib/demod_impl.cc:28-32)           */
+    int32_t mugid;
+    int32_t reserved[8];
+} c8b_cfg;
+
+typedef struct c8b_ctx c8b_ctx;
+
+int  c8b_abi_version(void);
+/* number of visible CUDA devices (0 or negative error) -- lets hosts fail loudly before create */
+int  c8b_device_count(void);
+int  c8b_create(const c8b_cfg* cfg, c8b_ctx** out);
+void c8b_destroy(c8b_ctx* ctx);
+const char* c8b_last_error(const c8b_ctx* ctx);      /* ctx may be NULL: last create error         */
+void* c8b_stream(c8b_ctx* ctx);                      /* the ctx's cudaStream_t (for event timing)  */
+
+/* ---- lookup tables (the only thing ranks exchange: one NCCL broadcast at start-up) ------------
+ * c8b_lut_blob builds the blob on the host BY FORMULA (interleavers 802.11-2016 17.3.5.7 / 19.3.11.8.3,
+ * pilot polarity 17.3.5.10, LTF signs, trellis outputs of g0=133o g1=171o, CRC-32 table); the result
+ * equals the reference's transcribed tables c8p.cc:30-31,95-175,1413-1831,1864-1887 (tested). */
+size_t c8b_lut_size(void);
+int  c8b_lut_blob(void* buf, size_t cap);
+int  c8b_lut_load(c8b_ctx* ctx, const void* blob, size_t n);       /* host blob -> device          */
+int  c8b_lut_load_dev(c8b_ctx* ctx, const void* d_blob, size_t n); /* device blob (after ncclBcast) */
+
+/* ---- whole chain, batched: items are independent capture segments processed from reset state --
+ * iq: complex samples; item i = iq[off[i] .. off[i]+len[i]).  frames[i] = first frame accepted by
+ * L-SIG in item i (or a record carrying the drop status).  PDU records of item i are written at
+ * pdu + i*pdu_stride (at most pdu_stride bytes).  c8b_rx_batch takes HOST buffers (pinned or not)
+ * and pipelines H2D / kernels / D2H chunk by chunk; c8b_rx_batch_dev takes a DEVICE iq pointer and
+ * host off/len/frames/pdu. */
+int  c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems,
+                  c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
+int  c8b_rx_batch_dev(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const int32_t* len, int nitems,
+                      c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
+/* as c8b_rx_batch_dev but results stay on the device (d_frames: nitems c8b_frame, d_pdu:
+ * nitems*pdu_stride bytes); nothing is copied back and the call does not synchronise. */
+int  c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* h_off, const int32_t* h_len, int nitems,
+                            c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride);
+int  c8b_sync(c8b_ctx* ctx);                         /* wait for the ctx stream                    */
+
+/* per-kernel device time accumulated since the last reset (CUDA events on the ctx stream) */
+#define C8B_K_PRESISO 0
+#define C8B_K_DETECT 1
+#define C8B_K_HEADER 2
+#define C8B_K_DEMOD 3
+#define C8B_K_VITERBI 4
+#define C8B_K_COUNT 5
+int  c8b_timing_enable(c8b_ctx* ctx, int on);
+int  c8b_timing_read(c8b_ctx* ctx, double ms[C8B_K_COUNT], int64_t launches[C8B_K_COUNT], int reset);
+
+/* ---- staged entry points (host buffers in/out; used for parity tests and ncu captures) ---------
+ * Each mirrors one reference block on whole arrays. */
+/* presiso: preac[n] (float), preconj[n] (complex, may be NULL) */
+int  c8b_presiso(c8b_ctx* ctx, const float* h_iq, int64_t n, float* h_preac, float* h_preconj);
+/* trigger FSM over one array from reset state: out[n] flag bytes (0x01 trigger, 0x02 latch) */
+int  c8b_trigger(c8b_ctx* ctx, const float* h_preac, int64_t n, uint8_t* h_out);
+/* detect = presiso + trigger + sync + signal on items; fills status..nsamp of frames[i] and
+ * h_chan (64 complex per item: the legacy channel, tag "chan" lib/signal_impl.cc:146-152; may be NULL) */
+int  c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems,
+                c8b_frame* frames, float* h_chan);
+/* demod: for frames already detected (status C8B_ST_OK, sync_idx/rad/l_mcs/l_len/nsamp set, chan
+ * given): header states + per-symbol demod.  LLRs of frame i at h_llr + frames[i].llr_off, where the
+ * call sets llr_off = i*llr_stride. */
+int  c8b_demod(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems,
+               c8b_frame* frames, const float* h_chan, float* h_llr, int64_t llr_stride);
+/* decode: depuncture + Viterbi + descramble + assemble + CRC-32 for frames with cr/trellis/format/
+ * len/mcs/ampdu/total/llr_off set.  h_scram (may be NULL): one byte per decoded (still scrambled)
+ * bit, frame i at h_scram + i*scram_stride. */
+int  c8b_decode(c8b_ctx* ctx, const float* h_llr, int64_t nllr, c8b_frame* frames, int nframes,
+                uint8_t* h_pdu, int64_t pdu_stride, uint8_t* h_scram, int64_t scram_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+"""The C-ABI library loads and exports every symbol include/c80211b200.h declares; the LUT blob built
+by formula equals the reference's transcribed tables (no compute calls: runs without a GPU)."""
+import os
+import re
+
+import numpy as np
+
+from __graft_entry__ import ROOT, build, load_pkg
+
+
+def test_build_and_symbols():
+    build()
+    pkg = load_pkg()
+    L = pkg._cabi.lib()
+    hdr = open(os.path.join(ROOT, "include", "c80211b200.h")).read()
+    declared = set(re.findall(r"\b(c8b_[a-z0-9_]+)\s*\(", hdr))
+    bound = {s[0] for s in pkg._cabi.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.c8b_abi_version() == 1
+
+
+def test_no_device_fails_loudly():
+    import ctypes as C
+    pkg = load_pkg()
+    L = pkg._cabi.lib()
+    if L.c8b_device_count() > 0:
+        return
+    h = C.c_void_p()
+    assert L.c8b_create(None, C.byref(h)) == -1          # C8B_ERR_NO_DEVICE: no CPU fallback
+    assert b"no CPU path" in L.c8b_last_error(None)
+    try:
+        pkg.Receiver()
+    except pkg.C8bError:
+        pass
+    else:
+        raise AssertionError("Receiver() must raise without a GPU")
+
+
+def test_lut_blob_matches_reference_tables(golden):
+    pkg = load_pkg()
+    blob = pkg.lut_blob()
+    g = golden["ref_vectors"]
+    # layout of struct c8b_lut (csrc/lut.h)
+    o = 16
+    def take(n, dt):
+        nonlocal o
+        a = np.frombuffer(blob, dt, n, o)
+        o += n * np.dtype(dt).itemsize
+        return a
+    ltfL, ltfNL, ltfNL22 = take(64, "<f4"), take(64, "<f4"), take(64, "<f4")
+    pilotP = take(128, "<f4")
+    twr, twi = take(64, "<f4"), take(64, "<f4")
+    deintL = take(4 * 288, "<u2").reshape(4, 288)
+    deintNL = take(2 * 5 * 416, "<u2").reshape(2, 5, 416)
+    sigDemap = take(64, "i1")
+    bmClass = take(32, "u1")
+    binL, binNL = take(64, "u1"), take(64, "u1")
+    crc = take(256, "<u4")
+    assert o == blob.size
+    assert np.array_equal(ltfL, g["tab_LTF_L_26_F_FLOAT"]) and np.array_equal(ltfNL, g["tab_LTF_NL_28_F_FLOAT"])
+    assert np.array_equal(ltfNL22, g["tab_LTF_NL_28_F_FLOAT_VHT22"])
+    assert np.array_equal(pilotP[:127], g["tab_PILOT_P"])
+    names = {1: "Bpsk", 2: "Qpsk", 4: "16Qam", 6: "64Qam", 8: "256Qam"}
+    for m, nb in enumerate((1, 2, 4, 6)):
+        assert np.array_equal(deintL[m, :48 * nb], g["tab_mapDeintLegacy" + names[nb]])
+    for m, nb in enumerate((1, 2, 4, 6, 8)):
+        assert np.array_equal(deintNL[0, m, :52 * nb], g["tab_mapDeintNonlegacy" + names[nb]])
+        assert np.array_equal(deintNL[1, m, :52 * nb], g["tab_deintNL2_%d" % nb])
+    # trellis: class of 2k --0--> k from the reference's SV_STATE_OUTPUT[state*2 + input]
+    assert np.array_equal(bmClass, g["tab_SV_STATE_OUTPUT"][0::2][0::2])
+    nxt = g["tab_SV_STATE_NEXT"]
+    for k in range(32):
+        assert nxt[(2 * k) * 2] == k and nxt[(2 * k + 1) * 2] == k and nxt[(2 * k) * 2 + 1] == k + 32
+        o2 = g["tab_SV_STATE_OUTPUT"]
+        c = o2[(2 * k) * 2]
+        assert o2[(2 * k + 1) * 2] == c ^ 3 and o2[(2 * k) * 2 + 1] == c ^ 3 and o2[(2 * k + 1) * 2 + 1] == c
+    import zlib
+    assert crc[1] == 0x77073096 and zlib.crc32(b"123456789") == 0xCBF43926
+    w = np.exp(-2j * np.pi * np.arange(64) / 64)
+    assert np.allclose(twr, w.real, atol=1e-7) and np.allclose(twi, w.imag, atol=1e-7)
+    assert sigDemap[0] == -1 and (sigDemap >= 0).sum() == 48 and (binL < 255).sum() == 48 and (binNL < 255).sum() == 52
+    assert binNL[1] == 26 and binL[1] == 24 and binNL[36] == 0 and binL[38] == 0
