@@ -7,11 +7,6 @@
 #include "../../include/c80211b200.h"
 #include "lut.h"
 
-#define C8B_SYNC_BUF 240       // lib/sync_impl.h:30
-#define C8B_SYNC_RES 111       // lib/sync_impl.h:31
-#define C8B_SYM_SHIFT 8        // C8P_SYM_SAMP_SHIFT, lib/cloud80211phy.h:33
-#define C8B_DECODE_B_MAX 4095  // lib/decode_impl.h:35
-#define C8B_DECODE_T_MAX 32782 // lib/decode_impl.h:36
 
 // Viterbi kernel geometry (k_viterbi.cu)
 #define C8B_VIT_CH 150         // trellis steps per chunk: 5 decision groups of 30 (30 = 6 x 5 layout phases)
@@ -23,3 +18,13 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
                         uint2* d_surv, int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram,
                         int64_t scram_stride, unsigned* d_counter, int grid, cudaStream_t st);
 int c8b_viterbi_max_grid(int num_sm);
+
+void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int maxLen, int64_t outBase,
+                        float* preac, float2* preconj, cudaStream_t st);
+void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st);
+void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
+                       int64_t outBase, const float* preac, c8b_frame* frames, float2* chan, cudaStream_t st);
+void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int mupos, c8b_frame* frames,
+                       const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
+void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxSym, const c8b_frame* frames,
+                      const float2* hinv, float* llr, cudaStream_t st);

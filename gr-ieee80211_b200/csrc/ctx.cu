@@ -285,14 +285,307 @@ int c8b_decode(c8b_ctx* ctx, const float* h_llr, int64_t nllr, c8b_frame* frames
 
 }  // extern "C"
 
-// ---- not yet wired (filled in as the kernels land) ------------------------------------------------
-extern "C" {
-#define C8B_TODO(ctx) do { if (ctx) (ctx)->err = "not implemented yet"; return C8B_ERR_ARG; } while (0)
-int c8b_rx_batch(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, uint8_t*, int64_t) { C8B_TODO(ctx); }
-int c8b_rx_batch_dev(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, uint8_t*, int64_t) { C8B_TODO(ctx); }
-int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, uint8_t*, int64_t) { C8B_TODO(ctx); }
-int c8b_presiso(c8b_ctx* ctx, const float*, int64_t, float*, float*) { C8B_TODO(ctx); }
-int c8b_trigger(c8b_ctx* ctx, const float*, int64_t, uint8_t*) { C8B_TODO(ctx); }
-int c8b_detect(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, float*) { C8B_TODO(ctx); }
-int c8b_demod(c8b_ctx* ctx, const float*, const int64_t*, const int32_t*, int, c8b_frame*, const float*, float*, int64_t) { C8B_TODO(ctx); }
+// ---- front end + demod + whole chain -----------------------------------------------------------------
+struct ChunkPlan { int64_t base = 0, end = 0; int maxLen = 0; };
+
+static ChunkPlan plan(const int64_t* off, const int32_t* len, int n)
+{
+    ChunkPlan p;
+    if (n <= 0) return p;
+    p.base = off[0]; p.end = off[0] + len[0];
+    for (int i = 0; i < n; i++) {
+        if (off[i] < p.base) p.base = off[i];
+        if (off[i] + len[i] > p.end) p.end = off[i] + len[i];
+        if (len[i] > p.maxLen) p.maxLen = len[i];
+    }
+    return p;
 }
+
+static int64_t llr_stride_for(int maxLen)
+{
+    // every DATA symbol takes >= 72 samples and starts >= 224 samples after the sync index
+    int64_t nsym = maxLen / 72 + 1;
+    if (nsym > 1366) nsym = 1366;                       // lib/decode_impl.h:36: trellis <= 32782 -> <= 1366 BPSK symbols
+    return nsym * 416;
+}
+
+static int check_items(c8b_ctx* ctx, const int64_t* off, const int32_t* len, int n)
+{
+    for (int i = 0; i < n; i++)
+        if (off[i] < 0 || len[i] < 0) { ctx->err = "negative item offset/length"; return C8B_ERR_ARG; }
+    return C8B_OK;
+}
+
+// items [b, e) of a device-resident capture: all stages, results into d_frames[b..e) / d_pdu
+static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, const int32_t* d_len, const int64_t* h_off,
+                     const int32_t* h_len, int b, int e, c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride, int64_t iqShift)
+{
+    const int n = e - b;
+    const ChunkPlan pl = plan(h_off + b, h_len + b, n);
+    const int64_t span = pl.end - pl.base;
+    const int64_t llrStride = llr_stride_for(pl.maxLen);
+    EN(preac, (size_t)(span + 64) * sizeof(float));
+    EN(chan, (size_t)n * 64 * sizeof(float2));
+    EN(hinv, (size_t)n * 64 * sizeof(float2));
+    EN(llr, (size_t)n * llrStride * sizeof(float));
+    int r = ensure_surv(ctx);
+    if (r) return r;
+    // iqShift: the device buffer holds the capture from sample iqShift on (host-staged chunks)
+    const float2* iq = d_iq - iqShift;
+    {
+        StageTimer tm(ctx, C8B_K_PRESISO);
+        c8b_launch_presiso(iq, d_off + b, d_len + b, n, pl.maxLen, pl.base, (float*)ctx->preac.p, nullptr, ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_DETECT);
+        c8b_launch_detect(ctx->d_lut, iq, d_off + b, d_len + b, n, b, pl.base, (const float*)ctx->preac.p, d_frames + b,
+                          (float2*)ctx->chan.p, ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_HEADER);
+        c8b_launch_header(ctx->d_lut, iq, d_off + b, n, ctx->cfg.mupos, d_frames + b, (const float2*)ctx->chan.p, (float2*)ctx->hinv.p,
+                          llrStride, ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_DEMOD);
+        c8b_launch_demod(ctx->d_lut, iq, d_off + b, n, (int)(llrStride / 416), d_frames + b, (const float2*)ctx->hinv.p,
+                         (float*)ctx->llr.p, ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_VITERBI);
+        c8b_launch_viterbi(ctx->d_lut, d_frames + b, n, (const float*)ctx->llr.p, (int64_t)n * llrStride, (uint2*)ctx->surv.p,
+                           ctx->survWarps, d_pdu + (size_t)b * pdu_stride, pdu_stride, nullptr, 0, ctx->d_counter,
+                           c8b_viterbi_max_grid(ctx->numSM), ctx->st);
+    }
+    CK(cudaGetLastError());
+    return C8B_OK;
+}
+
+static int upload_items(c8b_ctx* ctx, const int64_t* off, const int32_t* len, int n)
+{
+    EN(off, (size_t)n * sizeof(int64_t));
+    EN(len, (size_t)n * sizeof(int32_t));
+    CK(cudaMemcpyAsync(ctx->off.p, off, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->len.p, len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->st));
+    return C8B_OK;
+}
+
+extern "C" {
+
+int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* d_frames,
+                           uint8_t* d_pdu, int64_t pdu_stride)
+{
+    if (!ctx || !d_iq || !off || !len || nitems < 0 || !d_frames || !d_pdu || pdu_stride <= 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nitems == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    if ((r = check_items(ctx, off, len, nitems))) return r;
+    if ((r = upload_items(ctx, off, len, nitems))) return r;
+    CK(cudaMemsetAsync(d_frames, 0, (size_t)nitems * sizeof(c8b_frame), ctx->st));
+    const int cs = ctx->cfg.chunk_items;
+    for (int b = 0; b < nitems; b += cs) {
+        const int e = b + cs < nitems ? b + cs : nitems;
+        r = run_chunk(ctx, (const float2*)d_iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, d_frames, d_pdu,
+                      pdu_stride, 0);
+        if (r) return r;
+    }
+    return C8B_OK;
+}
+
+int c8b_rx_batch_dev(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames,
+                     uint8_t* pdu, int64_t pdu_stride)
+{
+    if (!ctx || !frames || !pdu || nitems < 0 || pdu_stride <= 0) return C8B_ERR_ARG;
+    if (nitems == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    EN(frames, (size_t)nitems * sizeof(c8b_frame));
+    EN(pdu, (size_t)nitems * pdu_stride);
+    int r = c8b_rx_batch_dev_async(ctx, d_iq, off, len, nitems, (c8b_frame*)ctx->frames.p, (uint8_t*)ctx->pdu.p, pdu_stride);
+    if (r) return r;
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(pdu, ctx->pdu.p, (size_t)nitems * pdu_stride, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+// Host IQ: chunks are staged into two device buffers on the copy stream while the previous chunk is
+// processed on the compute stream; results of each chunk go back as soon as its Viterbi kernel ends.
+int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, uint8_t* pdu,
+                 int64_t pdu_stride)
+{
+    if (!ctx || !h_iq || !off || !len || nitems < 0 || !frames || !pdu || pdu_stride <= 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nitems == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    if ((r = check_items(ctx, off, len, nitems))) return r;
+    if ((r = upload_items(ctx, off, len, nitems))) return r;
+    EN(frames, (size_t)nitems * sizeof(c8b_frame));
+    EN(pdu, (size_t)nitems * pdu_stride);
+    CK(cudaMemsetAsync(ctx->frames.p, 0, (size_t)nitems * sizeof(c8b_frame), ctx->st));
+    const int cs = ctx->cfg.chunk_items;
+    const int nchunks = (nitems + cs - 1) / cs;
+    // size the two staging buffers for the largest chunk span
+    int64_t maxSpan = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const int b = c * cs, e = b + cs < nitems ? b + cs : nitems;
+        const ChunkPlan pl = plan(off + b, len + b, e - b);
+        if (pl.end - pl.base > maxSpan) maxSpan = pl.end - pl.base;
+    }
+    EN(iq, (size_t)2 * (maxSpan + 16) * sizeof(float2));
+    float2* buf[2] = { (float2*)ctx->iq.p, (float2*)ctx->iq.p + (maxSpan + 16) };
+    cudaEvent_t copied[2], freed[2];
+    for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming); }
+    int rc = C8B_OK;
+    auto stage = [&](int c) -> cudaError_t {
+        const int b = c * cs, e = b + cs < nitems ? b + cs : nitems, k = c & 1;
+        const ChunkPlan pl = plan(off + b, len + b, e - b);
+        if (c >= 2) cudaStreamWaitEvent(ctx->stCopy, freed[k], 0);
+        cudaError_t er = cudaMemcpyAsync(buf[k], reinterpret_cast<const float2*>(h_iq) + pl.base, (size_t)(pl.end - pl.base) * sizeof(float2),
+                                         cudaMemcpyHostToDevice, ctx->stCopy);
+        cudaEventRecord(copied[k], ctx->stCopy);
+        return er;
+    };
+    cudaError_t er = stage(0);
+    for (int c = 0; c < nchunks && er == cudaSuccess && rc == C8B_OK; c++) {
+        const int b = c * cs, e = b + cs < nitems ? b + cs : nitems, k = c & 1;
+        if (c + 1 < nchunks) er = stage(c + 1);
+        const ChunkPlan pl = plan(off + b, len + b, e - b);
+        cudaStreamWaitEvent(ctx->st, copied[k], 0);
+        rc = run_chunk(ctx, buf[k], (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, (c8b_frame*)ctx->frames.p,
+                       (uint8_t*)ctx->pdu.p, pdu_stride, pl.base);
+        cudaEventRecord(freed[k], ctx->st);
+        if (rc == C8B_OK) {
+            cudaMemcpyAsync(frames + b, (c8b_frame*)ctx->frames.p + b, (size_t)(e - b) * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st);
+            cudaMemcpyAsync(pdu + (size_t)b * pdu_stride, (uint8_t*)ctx->pdu.p + (size_t)b * pdu_stride, (size_t)(e - b) * pdu_stride,
+                            cudaMemcpyDeviceToHost, ctx->st);
+        }
+    }
+    cudaStreamSynchronize(ctx->stCopy);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->st);
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(copied[k]); cudaEventDestroy(freed[k]); }
+    if (rc) return rc;
+    if (er != cudaSuccess || e2 != cudaSuccess) { ctx->err = std::string("c8b_rx_batch: ") + cudaGetErrorString(er != cudaSuccess ? er : e2); return C8B_ERR_CUDA; }
+    return C8B_OK;
+}
+
+// ---- staged entry points (host buffers) -----------------------------------------------------------
+int c8b_presiso(c8b_ctx* ctx, const float* h_iq, int64_t n, float* h_preac, float* h_preconj)
+{
+    if (!ctx || !h_iq || n < 0 || n > 0x7fffffff || !h_preac) return C8B_ERR_ARG;
+    if (n == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    EN(iq, (size_t)n * sizeof(float2));
+    EN(preac, (size_t)(n + 64) * sizeof(float));
+    if (h_preconj) EN(preconj, (size_t)n * sizeof(float2));
+    const int64_t off = 0; const int32_t len = (int32_t)n;
+    int r = upload_items(ctx, &off, &len, 1);
+    if (r) return r;
+    CK(cudaMemcpyAsync(ctx->iq.p, h_iq, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
+    {
+        StageTimer tm(ctx, C8B_K_PRESISO);
+        c8b_launch_presiso((const float2*)ctx->iq.p, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, 1, len, 0, (float*)ctx->preac.p,
+                           h_preconj ? (float2*)ctx->preconj.p : nullptr, ctx->st);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_preac, ctx->preac.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+    if (h_preconj) CK(cudaMemcpyAsync(h_preconj, ctx->preconj.p, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+int c8b_trigger(c8b_ctx* ctx, const float* h_preac, int64_t n, uint8_t* h_out)
+{
+    if (!ctx || !h_preac || n < 0 || !h_out) return C8B_ERR_ARG;
+    if (n == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    EN(preac, (size_t)(n + 64) * sizeof(float));
+    EN(trig, (size_t)n);
+    CK(cudaMemcpyAsync(ctx->preac.p, h_preac, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->st));
+    c8b_launch_trigger((const float*)ctx->preac.p, n, (uint8_t*)ctx->trig.p, ctx->st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_out, ctx->trig.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+static int stage_items(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int n, ChunkPlan* pl)
+{
+    int r = check_items(ctx, off, len, n);
+    if (r) return r;
+    *pl = plan(off, len, n);
+    if ((r = upload_items(ctx, off, len, n))) return r;
+    EN(iq, (size_t)(pl->end - pl->base + 16) * sizeof(float2));
+    CK(cudaMemcpyAsync(ctx->iq.p, reinterpret_cast<const float2*>(h_iq) + pl->base, (size_t)(pl->end - pl->base) * sizeof(float2),
+                       cudaMemcpyHostToDevice, ctx->st));
+    return C8B_OK;
+}
+
+int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, float* h_chan)
+{
+    if (!ctx || !h_iq || !off || !len || nitems < 0 || !frames) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nitems == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    ChunkPlan pl;
+    if ((r = stage_items(ctx, h_iq, off, len, nitems, &pl))) return r;
+    EN(preac, (size_t)(pl.end - pl.base + 64) * sizeof(float));
+    EN(frames, (size_t)nitems * sizeof(c8b_frame));
+    EN(chan, (size_t)nitems * 64 * sizeof(float2));
+    CK(cudaMemsetAsync(ctx->frames.p, 0, (size_t)nitems * sizeof(c8b_frame), ctx->st));
+    const float2* iq = (const float2*)ctx->iq.p - pl.base;
+    {
+        StageTimer tm(ctx, C8B_K_PRESISO);
+        c8b_launch_presiso(iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, pl.maxLen, pl.base, (float*)ctx->preac.p, nullptr,
+                           ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_DETECT);
+        c8b_launch_detect(ctx->d_lut, iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, 0, pl.base, (const float*)ctx->preac.p,
+                          (c8b_frame*)ctx->frames.p, (float2*)ctx->chan.p, ctx->st);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    if (h_chan) CK(cudaMemcpyAsync(h_chan, ctx->chan.p, (size_t)nitems * 64 * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+int c8b_demod(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, const float* h_chan,
+              float* h_llr, int64_t llr_stride)
+{
+    if (!ctx || !h_iq || !off || !len || nitems < 0 || !frames || !h_chan || !h_llr || llr_stride <= 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nitems == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    ChunkPlan pl;
+    if ((r = stage_items(ctx, h_iq, off, len, nitems, &pl))) return r;
+    EN(frames, (size_t)nitems * sizeof(c8b_frame));
+    EN(chan, (size_t)nitems * 64 * sizeof(float2));
+    EN(hinv, (size_t)nitems * 64 * sizeof(float2));
+    EN(llr, (size_t)nitems * llr_stride * sizeof(float));
+    CK(cudaMemcpyAsync(ctx->frames.p, frames, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->chan.p, h_chan, (size_t)nitems * 64 * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->llr.p, 0, (size_t)nitems * llr_stride * sizeof(float), ctx->st));
+    const float2* iq = (const float2*)ctx->iq.p - pl.base;
+    {
+        StageTimer tm(ctx, C8B_K_HEADER);
+        c8b_launch_header(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, ctx->cfg.mupos, (c8b_frame*)ctx->frames.p,
+                          (const float2*)ctx->chan.p, (float2*)ctx->hinv.p, llr_stride, ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_DEMOD);
+        c8b_launch_demod(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, (int)(llr_stride / 48 + 1), (const c8b_frame*)ctx->frames.p,
+                         (const float2*)ctx->hinv.p, (float*)ctx->llr.p, ctx->st);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_llr, ctx->llr.p, (size_t)nitems * llr_stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+}  // extern "C"

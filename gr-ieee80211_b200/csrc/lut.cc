@@ -37,6 +37,7 @@ void c8b_lut_build(c8b_lut* L)
     for (int k = 0; k < 64; k++) {
         L->twr[k] = (float)cos(-2.0 * M_PI * k / 64.0);
         L->twi[k] = (float)sin(-2.0 * M_PI * k / 64.0);
+        if (k < 32) { L->twdr[k] = cos(-2.0 * M_PI * k / 64.0); L->twdi[k] = sin(-2.0 * M_PI * k / 64.0); }
     }
     // legacy interleaver 17.3.5.7: k -> i -> j; deinterleaver scatter map[j] = k
     const int nbL[4] = { 1, 2, 4, 6 };

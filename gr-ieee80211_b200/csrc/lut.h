@@ -5,8 +5,14 @@
 #pragma once
 #include <stdint.h>
 
+#define C8B_SYNC_BUF 240       // lib/sync_impl.h:30
+#define C8B_SYNC_RES 111       // lib/sync_impl.h:31
+#define C8B_SYM_SHIFT 8        // C8P_SYM_SAMP_SHIFT, lib/cloud80211phy.h:33
+#define C8B_DECODE_B_MAX 4095  // lib/decode_impl.h:35
+#define C8B_DECODE_T_MAX 32782 // lib/decode_impl.h:36
+
 #define C8B_LUT_MAGIC 0x4c423843u /* "C8BL" */
-#define C8B_LUT_VERSION 2u
+#define C8B_LUT_VERSION 3u
 
 struct c8b_lut {
     uint32_t magic, version, bytes, pad0;
@@ -15,6 +21,7 @@ struct c8b_lut {
     float ltfNL22[64];         // second VHT-LTF as seen by user position 1 (pilot bins negated)
     float pilotP[128];         // pilot polarity p_0..p_126 (+ pad)
     float twr[64], twi[64];    // W64^k = exp(-2 pi j k / 64)
+    double twdr[32], twdi[32]; // the same in double, k < 32 (per-frame DFTs)
     uint16_t deintL[4][288];   // legacy: nBPSC 1,2,4,6      out[map[i]] = in[i]
     uint16_t deintNL[2][5][416]; // HT/VHT 20 MHz: [iss-1][nBPSCS 1,2,4,6,8]
     int8_t sigDemap[64];       // FFT bin -> deinterleaved SIG llr index (-1: not a data tone)

@@ -52,6 +52,7 @@ def test_lut_blob_matches_reference_tables(golden):
     ltfL, ltfNL, ltfNL22 = take(64, "<f4"), take(64, "<f4"), take(64, "<f4")
     pilotP = take(128, "<f4")
     twr, twi = take(64, "<f4"), take(64, "<f4")
+    twdr, twdi = take(32, "<f8"), take(32, "<f8")
     deintL = take(4 * 288, "<u2").reshape(4, 288)
     deintNL = take(2 * 5 * 416, "<u2").reshape(2, 5, 416)
     sigDemap = take(64, "i1")

@@ -1,0 +1,101 @@
+"""Whole chain on the GPU (c8b_rx_batch, host buffers in, PDUs out) vs the oracle: the set of published
+PDUs must be identical byte for byte and in order (SURVEY 8d gate 4)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from __graft_entry__ import load_pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(pkg, iq, off, ln, **kw):
+    rx = pkg.Receiver(device=0, **kw)
+    fr, pdu = rx.rx_batch(iq, off, ln)
+    rx.close()
+    n = len(off)
+    fo = np.zeros(n, ol.FRAME_DTYPE)
+    stride = 4400
+    po = np.zeros(n * stride, np.uint8)
+    ol.oracle().orx_rx_batch(ol.c2f(iq), np.ascontiguousarray(off, np.int64), np.ascontiguousarray(ln, np.int32), n, 8, fo.ctypes.data, po, stride)
+    return fr, pdu, fo, po.reshape(n, stride)
+
+
+def _compare(fr, pdu, fo, po):
+    for i in range(fr.size):
+        assert fr[i]["status"] == fo[i]["status"], (i, fr[i]["status"], fo[i]["status"])
+        assert fr[i]["npdu"] == fo[i]["npdu"] and fr[i]["pdu_bytes"] == fo[i]["pdu_bytes"], (i, fr[i]["npdu"], fo[i]["npdu"])
+        nb = int(fo[i]["pdu_bytes"])
+        assert bytes(pdu[i, :nb]) == bytes(po[i, :nb]), i
+
+
+def test_config1_plumbing(golden):
+    """BASELINE config 1: tools/pktGenExample.py Legacy MCS0 frame -> PDU [0][len][MPDU][0]"""
+    pkg = load_pkg()
+    g = golden["frames_siso"]
+    x = g["iq"][g["offs"][0]:g["offs"][1]]
+    rx = pkg.Receiver(device=0)
+    fr, pdu = rx.rx_batch(x, [0], [x.size])
+    rx.close()
+    mpdu = bytes(g["exp_mpdu"][:g["exp_len"][0]])
+    assert fr[0]["status"] == 0 and fr[0]["npdu"] == 1 and (fr[0]["format"], fr[0]["mcs"], fr[0]["len"]) == (0, 0, 94)
+    assert bytes(pdu[0, :fr[0]["pdu_bytes"]]) == bytes([0, 94, 0]) + mpdu + bytes([0])
+    assert mpdu[:10].hex() == "08016e00f469d5800fa0"
+
+
+@pytest.mark.parametrize("snr", [None, 30.0, 12.0])
+@pytest.mark.parametrize("chunk", [16384, 7])
+def test_all_formats_vs_oracle(golden, snr, chunk):
+    pkg = load_pkg()
+    g = golden["frames_siso"]
+    iq = g["iq"].copy()
+    if snr is not None:
+        rng = np.random.default_rng(23)
+        s = 0.1875 / np.sqrt(2 * 10 ** (snr / 10))
+        iq = (iq + s * (rng.standard_normal(iq.size) + 1j * rng.standard_normal(iq.size))).astype(np.complex64)
+    offs = g["offs"]
+    off, ln = offs[:-1], np.diff(offs).astype(np.int32)
+    fr, pdu, fo, po = _run_both(pkg, iq, off, ln, chunk_items=chunk)
+    _compare(fr, pdu, fo, po)
+    if snr is None or snr >= 30:
+        el = g["exp_len"]
+        eo = np.cumsum(np.r_[0, el])
+        for i in range(len(off)):
+            assert fr[i]["npdu"] >= 1 and bytes(pdu[i, 3:3 + el[i]]) == bytes(g["exp_mpdu"][eo[i]:eo[i + 1]]), i
+
+
+def test_ragged_batch_vs_oracle(golden):
+    pkg = load_pkg()
+    g = golden["frames_siso"]
+    x = g["iq"][g["offs"][0]:g["offs"][1]]
+    y = g["iq"][g["offs"][20]:g["offs"][21]]
+    rng = np.random.default_rng(9)
+    parts = [x[:64], x[:1450], x[:1700], x[:2500], x, y, y[:900], (0.01 * (rng.standard_normal(5000) + 1j * rng.standard_normal(5000))).astype(np.complex64),
+             np.concatenate([x, y])]
+    iq = np.concatenate(parts).astype(np.complex64)
+    ln = np.array([p.size for p in parts], np.int32)
+    off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.int64)
+    fr, pdu, fo, po = _run_both(pkg, iq, off, ln, chunk_items=4)
+    _compare(fr, pdu, fo, po)
+
+
+def test_bench_frames_config5_shape(golden):
+    """16 VHT MCS7 1500-byte frames (config 5 units), 400-sample gaps, 30 dB: every MPDU comes back"""
+    pkg = load_pkg()
+    g = golden["frames_bench"]
+    fx, mp = g["iq"], g["mpdu"]
+    rng = np.random.default_rng(5)
+    items = []
+    for k in range(64):
+        f = fx[k % 16]
+        z = np.concatenate([np.zeros(200, np.complex64), f, np.zeros(200, np.complex64)])
+        s = 0.1875 / np.sqrt(2 * 10 ** 3.0)
+        items.append((z + s * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))).astype(np.complex64))
+    iq = np.concatenate(items)
+    ln = np.full(64, items[0].size, np.int32)
+    off = (np.arange(64) * items[0].size).astype(np.int64)
+    fr, pdu, fo, po = _run_both(pkg, iq, off, ln, chunk_items=24)
+    _compare(fr, pdu, fo, po)
+    for k in range(64):
+        assert fr[k]["npdu"] == 1 and (fr[k]["format"], fr[k]["mcs"], fr[k]["nsym"], fr[k]["trellis"], fr[k]["total"]) == (2, 7, 47, 12220, 14664)
+        assert bytes(pdu[k, 3:1503]) == bytes(mp[k % 16])

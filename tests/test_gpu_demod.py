@@ -1,0 +1,49 @@
+"""GPU demod (k_header + k_demod through the C ABI) vs the oracle: frame fields equal, LLRs within
+1e-4 * max(1, |llr|) (SURVEY 8d gate 2)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from __graft_entry__ import load_pkg
+
+pytestmark = pytest.mark.gpu
+
+HDR = ("status", "format", "mcs", "len", "cr", "ampdu", "nss", "nsym", "nsymsamp", "ncbps", "ndbps", "trellis", "total", "data_off")
+LLR_RTOL = 1e-4      # BASELINE.json north_star: "LLRs within 1e-4 relative"
+
+
+@pytest.fixture(scope="module")
+def rx():
+    r = load_pkg().Receiver(device=0)
+    yield r
+    r.close()
+
+
+@pytest.mark.parametrize("snr", [None, 30.0])
+def test_demod_llrs_match_oracle(rx, golden, snr):
+    g = golden["frames_siso"]
+    iq = g["iq"].copy()
+    if snr is not None:
+        rng = np.random.default_rng(17)
+        s = 0.1875 / np.sqrt(2 * 10 ** (snr / 10))
+        iq = (iq + s * (rng.standard_normal(iq.size) + 1j * rng.standard_normal(iq.size))).astype(np.complex64)
+    offs = g["offs"]
+    off, ln = offs[:-1], np.diff(offs).astype(np.int32)
+    fr, chan = rx.detect(iq, off, ln)
+    stride = 200 * 416
+    fr2, llr = rx.demod(iq, off, ln, fr, chan, stride)
+    worst = 0.0
+    for i in range(len(off)):
+        fo, lo, _ = ol.rx_item(iq[offs[i]:offs[i + 1]], max_frames=1)
+        for k in HDR:
+            assert fr2[i][k] == fo[0][k], (i, k, fr2[i][k], fo[0][k])
+        if fo[0]["format"] == 2:
+            assert abs(float(fr2[i]["sssnr0"]) - float(fo[0]["sssnr0"])) <= (1.0 if fo[0]["sssnr0"] > 60 else 0.01)
+        n = int(fo[0]["total"])
+        got = llr[i, :n]
+        err = np.abs(got - lo[:n]) / np.maximum(1.0, np.abs(lo[:n]))
+        worst = max(worst, float(err.max()))
+        assert err.max() <= LLR_RTOL, (i, int(np.argmax(err)), float(err.max()))
+    print("worst relative LLR error %.3g" % worst)

@@ -1,0 +1,128 @@
+"""Host logic: the product's per-frame routines (phy_serial.cuh, run one-thread-per-frame by k_detect /
+k_header on the GPU), compiled for the host, against the oracle on the reference generator's frames."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import hostsim_lib as hs
+import oracle_lib as ol
+from __graft_entry__ import load_pkg
+
+DET = ("status", "trig_idx", "sync_idx", "l_mcs", "l_len", "nsamp")
+HDR = ("status", "format", "mcs", "len", "cr", "ampdu", "nss", "nsym", "nsymsamp", "ncbps", "ndbps", "trellis", "total", "data_off")
+
+
+def _items(g, noise=0.0, seed=3):
+    iq, offs = g["iq"], g["offs"]
+    rng = np.random.default_rng(seed)
+    for i in range(len(offs) - 1):
+        x = iq[offs[i]:offs[i + 1]]
+        if noise:
+            x = (x + noise * (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size))).astype(np.complex64)
+        yield i, np.ascontiguousarray(x)
+
+
+def _detect(x):
+    pkg = load_pkg()
+    H, O = hs.lib(), ol.oracle()
+    xf = ol.c2f(x)
+    n = x.size
+    preac, preconj = np.zeros(n, np.float32), np.zeros(2 * n, np.float32)
+    O.orx_presiso(xf, n, preac, preconj)
+    f = np.zeros(1, pkg.FRAME_DTYPE)
+    chan = np.zeros(128, np.float32)
+    H.hs_detect(xf, preac, n, 0, f.ctypes.data, chan)
+    return f, chan, preac, preconj.view(np.complex64)
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.1875 / np.sqrt(2 * 10 ** 3.0), 0.1875 / np.sqrt(2 * 10 ** 1.0)])
+def test_detect_and_header_match_oracle(golden, noise):
+    H = hs.lib()
+    for i, x in _items(golden["frames_siso"], noise):
+        fo, llr, pdu = ol.rx_item(x, max_frames=1)
+        f, chan, _, _ = _detect(x)
+        want_det = fo[0]["status"] if fo[0]["status"] in (1, 2, 3, 4) and fo[0]["nsamp"] == 0 else 0
+        if fo[0]["nsamp"] == 0:                        # no frame record: only the drop code is comparable
+            assert f[0]["status"] == fo[0]["status"], (i, f[0]["status"], fo[0]["status"])
+            continue
+        for k in DET[1:]:
+            assert f[0][k] == fo[0][k], (i, k, f[0][k], fo[0][k])
+        # float tags: the routines evaluate cos/sin/atan2 in double where the reference calls cosf/sinf/atan2f
+        assert abs(float(f[0]["rad"]) - float(fo[0]["rad"])) <= 1e-8, (i, f[0]["rad"], fo[0]["rad"])
+        assert abs(float(f[0]["cfo_hz"]) - float(fo[0]["cfo_hz"])) <= 0.05
+        for k in ("snr", "rssi"):
+            assert np.allclose(f[0][k], fo[0][k], rtol=1e-5, atol=0, equal_nan=True), (i, k, f[0][k], fo[0][k])
+        if f[0]["status"] != 0:
+            assert fo[0]["status"] == 4
+            continue
+        hinv = np.zeros(128, np.float32)
+        H.hs_header(ol.c2f(x), f.ctypes.data, chan, 0, hinv)
+        for k in HDR:
+            assert f[0][k] == fo[0][k], (i, k, f[0][k], fo[0][k])
+        # per-stream SNR of a noiseless frame is pure rounding noise (~120 dB): compare loosely
+        assert abs(float(f[0]["sssnr0"]) - float(fo[0]["sssnr0"])) <= (0.5 if fo[0]["sssnr0"] > 60 else 0.01)
+
+
+def test_truncated_noise_and_empty_items(golden):
+    g = golden["frames_siso"]
+    x = np.ascontiguousarray(g["iq"][g["offs"][0]:g["offs"][1]])
+    for cut in (64, 200, 1000, 1450, 1500, 1700, 2500, x.size - 1):
+        fo, _, _ = ol.rx_item(x[:cut], max_frames=1)
+        f, _, _, _ = _detect(np.ascontiguousarray(x[:cut]))
+        assert f[0]["status"] == fo[0]["status"], (cut, f[0]["status"], fo[0]["status"])
+    rng = np.random.default_rng(5)
+    for amp in (0.01, 0.3):
+        z = (amp * (rng.standard_normal(6000) + 1j * rng.standard_normal(6000))).astype(np.complex64)
+        fo, _, _ = ol.rx_item(z, max_frames=1)
+        f, _, _, _ = _detect(z)
+        assert f[0]["status"] == fo[0]["status"]
+    # periodic-16 junk: triggers fire, LTF autocorrelation may or may not pass, L-SIG fails
+    t = np.tile((rng.standard_normal(16) + 1j * rng.standard_normal(16)).astype(np.complex64), 60)
+    z = np.concatenate([np.zeros(300, np.complex64), 0.2 * t, np.zeros(900, np.complex64)]).astype(np.complex64)
+    z += (0.002 * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))).astype(np.complex64)
+    fo, _, _ = ol.rx_item(z, max_frames=1)
+    f, _, _, _ = _detect(z)
+    assert f[0]["status"] == fo[0]["status"]
+
+
+def test_latch_value_equals_presiso_output(golden):
+    H = hs.lib()
+    g = golden["frames_siso"]
+    x = np.ascontiguousarray(g["iq"][g["offs"][5]:g["offs"][6]])
+    _, _, preac, preconj = _detect(x)
+    out = np.zeros(2, np.float32)
+    for i in (0, 3, 15, 16, 17, 31, 47, 48, 63, 64, 300, 450, 500, 1234):
+        H.hs_conj_at(ol.c2f(x), i, out)
+        assert out[0] == preconj[i].real and out[1] == preconj[i].imag, i
+
+
+def test_trigger_sigviterbi_fft_vs_oracle():
+    H, O = hs.lib(), ol.oracle()
+    rng = np.random.default_rng(11)
+    ac = np.clip(rng.normal(0.3, 0.25, 20000), 0, 1).astype(np.float32)
+    ac[5000:5300] = 0.7
+    ac[9000:9030] = 0.5
+    a, b = np.zeros(ac.size, np.uint8), np.zeros(ac.size, np.uint8)
+    H.hs_trigger(ac, ac.size, a)
+    O.orx_trigger(ac, ac.size, b, np.zeros(5, np.int32))
+    assert np.array_equal(a, b) and (a & 1).sum() > 0
+    for T in (24, 26, 48):
+        for trial in range(100):
+            llr = rng.normal(0, 1, 2 * T).astype(np.float32)
+            if trial % 2:
+                llr = (np.round(llr * 2) / 2).astype(np.float32)
+            x, y = np.zeros(T, np.uint8), np.zeros(T, np.uint8)
+            H.hs_sig_viterbi(llr, x, T)
+            O.orx_sig_viterbi(llr, y, T)
+            assert np.array_equal(x, y)
+    for _ in range(20):
+        z = ol.c2f((rng.standard_normal(64) + 1j * rng.standard_normal(64)).astype(np.complex64))
+        p, q = np.zeros(128, np.float32), np.zeros(128, np.float32)
+        H.hs_fft64(z, p)
+        O.orx_fft64(z, q)
+        assert np.array_equal(p, q)
+    for _ in range(300):
+        bits = rng.integers(0, 2, 34).astype(np.uint8)
+        crc = rng.integers(0, 2, 8).astype(np.uint8)
+        assert H.hs_crc8(bits, 34, crc) == O.orx_crc8_check(bits, 34, crc)
