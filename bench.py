@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- RX throughput of the 802.11 OFDM receive chain on B200 (BASELINE.json metric:
+"RX IQ samples/s & frames/s (20 MHz VHT MCS7)", workload = configs[4]: VHT MCS7 1500-byte frames as
+independent work items, 1M-frame batch per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # N>1: launched under torchrun, one rank per GPU
+  python bench.py --impl reference ...                         # CPU arm: the oracle port on all host cores
+
+A step = one pass of the whole chain (presiso -> trigger/sync/signal -> demod -> decode) over one batch.
+`value`  : samples/s with the batch resident in HBM (results stay on the device), CUDA events on the
+           launching stream, max over ranks, whole-job aggregate.
+`e2e`    : the same through c8b_rx_batch with HOST (pinned) buffers: H2D of the IQ and D2H of the frame
+           records + PDU bytes inside the timed region.
+`roofline`: the dominant kernel (Viterbi decode), algorithmic bytes / measured launch time vs the measured
+           HBM peak; `stages` gives every kernel (the HBM-streaming ones against the same peak).
+`cpu_baseline`: the CPU oracle (port of the reference path) on this host's cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GAP = 200                    # zeros before and after each frame (400-sample gaps)
+FRAME_SAMP = 4560            # VHT MCS7, 1500-byte MPDU: 47 symbols (SURVEY 8 sizes)
+ITEM = FRAME_SAMP + 2 * GAP
+NSYM, NCBPS, TRELLIS, TOTAL_LLR, MPDU_LEN = 47, 312, 12220, 14664, 1500
+PDU_STRIDE = 1536
+SNR_DB = 30.0
+WORKLOAD = "configs[4]: VHT MCS7 1500-byte MPDU (47 sym, 4560 samples + 400 gap), AWGN 30 dB, CFO U(-100,100) kHz"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batch_device(torch, dev, nframes, seed):
+    """Synthetic config-5 batch built ON THE DEVICE from the 16 unique frames the reference's generator made
+    (tests/golden/frames_bench.npz): per item gather + CFO + AWGN.  Returns complex64 tensor [nframes*ITEM]."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "frames_bench.npz"))
+    base = torch.zeros((16, ITEM), dtype=torch.complex64, device=dev)
+    base[:, GAP:GAP + FRAME_SAMP] = torch.from_numpy(g["iq"]).to(dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(13579 + seed)
+    sigma = 0.1875 / np.sqrt(2.0 * 10 ** (SNR_DB / 10))           # tools/performance/perf_siso.py:92
+    out = torch.empty(nframes * ITEM, dtype=torch.complex64, device=dev)
+    nidx = torch.arange(ITEM, device=dev, dtype=torch.float32)
+    step = 16384
+    for b in range(0, nframes, step):
+        e = min(nframes, b + step)
+        k = torch.arange(b, e, device=dev) % 16
+        cfo = (torch.rand(e - b, generator=gen, device=dev) * 2 - 1) * 100e3
+        ph = (2 * np.pi / 20e6) * cfo[:, None] * nidx[None, :]
+        x = base[k] * torch.polar(torch.ones_like(ph), ph)
+        noise = torch.randn((e - b, ITEM, 2), generator=gen, device=dev) * sigma
+        x = x + torch.view_as_complex(noise)
+        out[b * ITEM:e * ITEM] = x.reshape(-1)
+    return out, g["mpdu"]
+
+
+def cpu_arm(nframes, threads, seed=0):
+    """The oracle (CPU port of the reference path) on `nframes` config-5 items; returns (seconds, frames ok)."""
+    import oracle_lib as ol
+    g = np.load(os.path.join(ROOT, "tests", "golden", "frames_bench.npz"))
+    rng = np.random.default_rng(seed)
+    sigma = 0.1875 / np.sqrt(2.0 * 10 ** (SNR_DB / 10))
+    iq = np.zeros((nframes, ITEM), np.complex64)
+    n = np.arange(ITEM)
+    for i in range(nframes):
+        iq[i, GAP:GAP + FRAME_SAMP] = g["iq"][i % 16]
+        cfo = rng.uniform(-100e3, 100e3)
+        iq[i] *= np.exp(2j * np.pi * cfo * n / 20e6).astype(np.complex64)
+    iq = (iq + sigma * (rng.standard_normal(iq.shape) + 1j * rng.standard_normal(iq.shape))).astype(np.complex64).reshape(-1)
+    off = (np.arange(nframes) * ITEM).astype(np.int64)
+    ln = np.full(nframes, ITEM, np.int32)
+    fr = np.zeros(nframes, ol.FRAME_DTYPE)
+    pdu = np.zeros(nframes * PDU_STRIDE, np.uint8)
+    L = ol.oracle()
+    t0 = time.perf_counter()
+    L.orx_rx_batch(ol.c2f(iq), off, ln, nframes, threads, fr.ctypes.data, pdu, PDU_STRIDE)
+    dt = time.perf_counter() - t0
+    return dt, int((fr["npdu"] == 1).sum())
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port; the block bodies need GNU Radio, which this image
+    lacks, so oracle/_ref cannot run the whole chain) on all host threads."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    dt, _ = cpu_arm(2 * cores, cores)                                # calibrate
+    per_step = int(max(cores, min(4096, (2 * cores / dt) * 3.0)))   # ~3 s of CPU work per step
+    for _ in range(args.warmup):
+        cpu_arm(max(cores, per_step // 4), cores)
+    t = 0.0
+    ok = 0
+    for s in range(args.steps):
+        dt, k = cpu_arm(per_step, cores, seed=s)
+        t += dt
+        ok += k
+    v = per_step * args.steps * ITEM / t
+    line = {
+        "impl": "reference", "metric": "rx_iq_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "frames_per_s": per_step * args.steps / t,
+        "config": {"workload": WORKLOAD, "frames_per_step": per_step, "samples_per_item": ITEM, "frames_ok": ok},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d config-5 items through oracle/liboracle_rx.so (orx_rx_batch, %d threads)" % (args.steps, per_step, cores)},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU per step (config 5: 1M-frame batch)")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 17, help="frames per host-buffer call of the e2e arm")
+    ap.add_argument("--chunk", type=int, default=32768, help="items per pipeline pass inside the library")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_pkg
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    pkg = load_pkg()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- LUT: built on rank 0, broadcast over NCCL, loaded from device memory (the only exchange) ----
+    blob_n = pkg._cabi.lib().c8b_lut_size()
+    if rank == 0:
+        blob = torch.from_numpy(pkg.lut_blob()).to(dev)
+    else:
+        blob = torch.zeros(blob_n, dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.broadcast(blob, src=0)
+    rx = pkg.Receiver(device=local, chunk_items=args.chunk, blob=(blob.cpu().numpy() if world == 1 else None))
+    if world > 1:
+        torch.cuda.synchronize()
+        rx.load_lut_device(blob.data_ptr(), blob_n)
+
+    nfr = args.frames
+    iq, mpdus = make_batch_device(torch, dev, nfr, seed=rank)
+    off = (np.arange(nfr, dtype=np.int64) * ITEM)
+    ln = np.full(nfr, ITEM, np.int32)
+    d_frames = torch.zeros(nfr * pkg.FRAME_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_pdu = torch.zeros(nfr * PDU_STRIDE, dtype=torch.uint8, device=dev)
+    st = torch.cuda.ExternalStream(rx.stream, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        rx.rx_batch_dev_async(iq.data_ptr(), off, ln, d_frames.data_ptr(), d_pdu.data_ptr(), PDU_STRIDE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        rx.sync()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    rx.timing(True)
+    rx.timing_read(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(st)
+    for _ in range(args.steps):
+        step()
+    e1.record(st)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stage = rx.timing_read(reset=True)
+    rx.timing(False)
+
+    # ---- correctness of what was just timed (outside the timed region) ----
+    fr = np.frombuffer(d_frames.cpu().numpy().tobytes(), dtype=pkg.FRAME_DTYPE)
+    ok = (fr["status"] == 0) & (fr["npdu"] == 1) & (fr["pdu_bytes"] == MPDU_LEN + 4)
+    chk = np.random.default_rng(1).choice(nfr, size=min(nfr, 512), replace=False)
+    pd = d_pdu.view(nfr, PDU_STRIDE)[torch.from_numpy(chk).to(dev)].cpu().numpy()
+    bytes_ok = sum(int(bytes(pd[j, 3:3 + MPDU_LEN]) == bytes(mpdus[int(i) % 16])) for j, i in enumerate(chk) if ok[i])
+    frames_ok = int(ok.sum())
+
+    # ---- e2e: host (pinned) buffers through c8b_rx_batch, H2D + D2H inside the timed region ----
+    ne = min(args.e2e_frames, nfr)
+    calls = max(1, nfr // ne)
+    h_iq = torch.empty(ne * ITEM, dtype=torch.complex64, pin_memory=True)
+    h_iq.copy_(iq[:ne * ITEM])
+    h_np = h_iq.numpy()
+    h_frames = torch.zeros(ne * pkg.FRAME_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    h_pdu = torch.zeros(ne * PDU_STRIDE, dtype=torch.uint8, pin_memory=True)
+    fr_np = np.frombuffer(h_frames.numpy(), dtype=pkg.FRAME_DTYPE)
+    L = pkg._cabi.lib()
+    import ctypes as C
+    off_e, ln_e = off[:ne].copy(), ln[:ne].copy()
+
+    def e2e_step():
+        for _ in range(calls):
+            rc = L.c8b_rx_batch(rx.h, C.c_void_p(h_np.ctypes.data), pkg._cabi.ptr(off_e), pkg._cabi.ptr(ln_e), ne, C.c_void_p(fr_np.ctypes.data),
+                                C.c_void_p(h_pdu.data_ptr()), PDU_STRIDE)
+            if rc:
+                raise RuntimeError("c8b_rx_batch: %d" % rc)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_ok = int(((fr_np["status"] == 0) & (fr_np["npdu"] == 1)).sum())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- reduce over ranks: max time, sums of work ----
+    tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([frames_ok, nfr, nfr * ITEM, bytes_ok, len(chk), e2e_ok], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = float(tt[0]), float(tt[1])
+    frames_ok, frames_total, samples_total, bytes_ok, nchk, e2e_ok = [int(x) for x in cnt]
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        k = args.steps
+        value = samples_total * k / (ms * 1e-3)
+        e2e_frames_total = calls * ne * world
+        e2e_v = e2e_frames_total * ITEM * e2e_steps / (e2e_ms * 1e-3)
+        nch = (nfr + args.chunk - 1) // args.chunk
+        launches = sum(v[1] for v in stage.values())
+        # algorithmic bytes per launch, per kernel; one launch covers one chunk of items
+        per_launch_items = nfr / nch
+        alg = {
+            "presiso": per_launch_items * ITEM * (8 + 4),                       # 8 B/sample in, 4 B preac out
+            "detect": per_launch_items * ITEM * 4,                              # preac scan (+O(1) per frame)
+            "header": per_launch_items * 560 * 8,                               # SIG fields + LTF: 8 B/sample once
+            "demod": per_launch_items * NSYM * (640 + 4 * NCBPS),               # 1888 B/symbol
+            "viterbi": per_launch_items * (4 * TOTAL_LLR + MPDU_LEN + 4),       # LLR read + PDU written
+        }
+        stages = {}
+        for name, (tms, n) in stage.items():
+            if n:
+                per = tms / n
+                gbs = alg[name] / (per * 1e-3) / 1e9
+                stages[name] = {"ms_per_launch": per, "launches": n, "share": tms / ms, "alg_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+        vit = stages.get("viterbi", {})
+        acs = per_launch_items * TRELLIS * 64 / (vit.get("ms_per_launch", 1) * 1e-3) if vit else None
+        line = {
+            "metric": "rx_iq_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": k, "warmup": args.warmup,
+            "ms_per_step": ms / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_s": frames_total * k / (ms * 1e-3),
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": nfr, "samples_per_item": ITEM, "chunk_items": args.chunk,
+                       "l2": "inputs larger than L2 (%.1f GB of IQ per GPU per step)" % (nfr * ITEM * 8 / 1e9),
+                       "frames_ok": frames_ok, "frames_total": frames_total, "mpdu_bytes_checked": "%d/%d identical" % (bytes_ok, nchk)},
+            "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": calls * ne * ITEM * 8,
+                    "d2h_bytes_per_step": calls * ne * (pkg.FRAME_DTYPE.itemsize + PDU_STRIDE), "frames_per_s": e2e_frames_total * e2e_steps / (e2e_ms * 1e-3),
+                    "steps": e2e_steps, "calls_per_step": calls, "frames_per_call": ne, "frames_ok_last_call": e2e_ok,
+                    "api": "c8b_rx_batch (host pinned buffers; H2D double-buffered per chunk, D2H of frame records + PDU bytes)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_viterbi", "achieved": vit.get("alg_GBps"), "peak": peak, "unit": "GB/s",
+                         "frac": vit.get("frac_of_hbm_peak"), "traffic": None, "peak_source": peak_src,
+                         "note": "decode is issue-bound (64-state ACS per trellis step), not HBM-bound: see acs_per_s; "
+                                 "the HBM-streaming stage is 'demod' in stages",
+                         "acs_per_s": acs},
+            "stages": stages,
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            dt, _ = cpu_arm(2 * cores, cores)
+            nb = int(max(cores, min(16384, (2 * cores / dt) * 12.0)))       # ~12 s of CPU work
+            dt, okc = cpu_arm(nb, cores, seed=1)
+            dt1, _ = cpu_arm(max(8, nb // (4 * cores)), 1, seed=2)
+            line["cpu_baseline"] = {"value": nb * ITEM / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "frames_per_s": nb / dt, "single_thread_samples_per_s": max(8, nb // (4 * cores)) * ITEM / dt1,
+                                    "sample": "%d config-5 items through oracle/liboracle_rx.so (orx_rx_batch, %d threads), %d decoded"
+                                              % (nb, cores, okc)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    rx.close()
+
+
+if __name__ == "__main__":
+    main()
