@@ -199,13 +199,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- LUT: built on rank 0, broadcast over NCCL, loaded from device memory (the only exchange) ----
-    blob_n = pkg._cabi.lib().c8b_lut_size()
-    if rank == 0:
-        blob = torch.from_numpy(pkg.lut_blob()).to(dev)
-    else:
-        blob = torch.zeros(blob_n, dtype=torch.uint8, device=dev)
-    if world > 1:
-        dist.broadcast(blob, src=0)
+    blob = pkg.parallel.broadcast_lut(torch, dist, rank, world, dev)
+    blob_n = blob.numel()
     rx = pkg.Receiver(device=local, chunk_items=args.chunk, blob=(blob.cpu().numpy() if world == 1 else None))
     if world > 1:
         torch.cuda.synchronize()
@@ -288,13 +283,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks: max time, sums of work ----
-    tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([frames_ok, nfr, nfr * ITEM, bytes_ok, len(chk), e2e_ok], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, e2e_ms = float(tt[0]), float(tt[1])
-    frames_ok, frames_total, samples_total, bytes_ok, nchk, e2e_ok = [int(x) for x in cnt]
+    cnt, tt = pkg.parallel.reduce_stats(torch, dist, world, dev, [frames_ok, nfr, nfr * ITEM, bytes_ok, len(chk), e2e_ok], [ms, e2e_s * 1e3])
+    ms, e2e_ms = tt
+    frames_ok, frames_total, samples_total, bytes_ok, nchk, e2e_ok = cnt
 
     if rank == 0:
         peak, peak_src = peaks()

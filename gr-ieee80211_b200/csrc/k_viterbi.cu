@@ -37,14 +37,19 @@ constexpr int MAXG = (C8B_DECODE_T_MAX + GS - 1) / GS;   // 1093 groups in the l
 constexpr int WORDS = (C8B_DECODE_T_MAX + 31) / 32 + 8;  // decoded-bit words per warp (+ slack)
 static_assert(CH % 5 == 0 && GS % 5 == 0 && CH % GS == 0, "phases must align with groups");
 static_assert(((C8B_DECODE_T_MAX + CH - 1) / CH) * NG * 32 <= C8B_VIT_TPAD, "survivor scratch too small");
-static_assert(MAXG * 4 <= 2 * CH * 16, "group bits must fit in the (dead) table buffers");
 
+constexpr int TBW = 4;                         // traceback warm-up, in 30-step groups, before a lane's own segment
+constexpr int U_BYTES = 8192;                  // union area: forward tables | traceback staging | decoded words
+static_assert(2 * CH * 16 <= U_BYTES && 32 * 64 * 4 <= U_BYTES && WORDS * 4 <= U_BYTES, "union area too small");
+
+// Per-warp shared memory (dynamic).  The union area is used, in turn, as
+//   forward pass : float4 tab[2][CH]   per step {0, t1, t0, t1+t0} (lib/decode_impl.cc:231-234), double buffered
+//   traceback    : uint32 stage[32][64] decision words of the group each lane is walking, [lane][2*rho+h]
+//   afterwards   : uint32 words[WORDS]  decoded bits packed LSB-first, descrambled in place -> PSDU bytes
 struct __align__(16) WarpSmem {
-    float4 tab[2][CH];      // per step {0, t1, t0, t1+t0} (lib/decode_impl.cc:231-234), double buffered;
-                            // during traceback the same bytes hold gbits[MAXG]: 30 decoded bits per group
-    uint32_t surv[NG * 64]; // traceback: decision words of one chunk, [group][lane][lo,hi]
-    uint32_t words[WORDS];  // decoded bits packed LSB-first, descrambled in place -> PSDU bytes
-    uint32_t scr[8];        // scrambler sequence, 160 bits
+    uint4 u[U_BYTES / 16];
+    uint32_t gbits[MAXG + 3];   // 30 decoded bits per group (bit i = step 30G+i)
+    uint32_t scr[8];            // scrambler sequence, 160 bits
 };
 
 __device__ __forceinline__ int rotr5(int x, int p) { return ((x >> p) | (x << (5 - p))) & 31; }
@@ -136,17 +141,21 @@ __device__ __forceinline__ void emit_record(uint8_t* __restrict__ out, int& w, i
     npdu++;
 }
 
-__global__ void __launch_bounds__(NW * 32, 5)
+__global__ void __launch_bounds__(NW * 32, 4)
 k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
           int64_t nllr, uint2* __restrict__ survScratch, uint8_t* __restrict__ pdu, int64_t pduStride,
           uint8_t* __restrict__ scram, int64_t scramStride, unsigned* __restrict__ counter)
 {
-    __shared__ WarpSmem sm[NW];
-    __shared__ uint32_t crcTab[256];
+    extern __shared__ __align__(16) uint8_t dynsm[];
+    WarpSmem* sm = reinterpret_cast<WarpSmem*>(dynsm);
+    uint32_t* crcTab = reinterpret_cast<uint32_t*>(dynsm + NW * sizeof(WarpSmem));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 256; i += NW * 32) crcTab[i] = lut->crc32tab[i];
     __syncthreads();
     WarpSmem& S = sm[warp];
+    float4 (*Stab)[CH] = reinterpret_cast<float4 (*)[CH]>(S.u);       // [2][CH]
+    uint32_t* __restrict__ Sstage = reinterpret_cast<uint32_t*>(S.u); // [32][64]
+    uint32_t* __restrict__ Swords = reinterpret_cast<uint32_t*>(S.u); // [WORDS]
     uint2* __restrict__ survG = survScratch + (size_t)(blockIdx.x * NW + warp) * C8B_VIT_TPAD;
     const bool lane0 = lane == 0;
 
@@ -189,7 +198,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
         float4 pf[NLD];
 #pragma unroll
         for (int j = 0; j < NLD; j++)
-            if (lane + 32 * j < CH) S.tab[0][lane + 32 * j] = load_tab(llr, total, cr, lane + 32 * j, T);
+            if (lane + 32 * j < CH) Stab[0][lane + 32 * j] = load_tab(llr, total, cr, lane + 32 * j, T);
         __syncwarp();
         for (int c = 0; c < nch; c++) {
             const int buf = c & 1;
@@ -198,7 +207,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
 #pragma unroll
                 for (int j = 0; j < NLD; j++) pf[j] = load_tab(llr, total, cr, (c + 1) * CH + lane + 32 * j, T);
             }
-            const float* __restrict__ tb = reinterpret_cast<const float*>(S.tab[buf]);
+            const float* __restrict__ tb = reinterpret_cast<const float*>(Stab[buf]);
             const float* pA0 = tb + 0 + cA[0], *pB0 = tb + 3 - cA[0];
             const float* pA1 = tb + 4 + cA[1], *pB1 = tb + 7 - cA[1];
             const float* pA2 = tb + 8 + cA[2], *pB2 = tb + 11 - cA[2];
@@ -224,37 +233,66 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
             if (more) {
 #pragma unroll
                 for (int j = 0; j < NLD; j++)
-                    if (lane + 32 * j < CH) S.tab[buf ^ 1][lane + 32 * j] = pf[j];
+                    if (lane + 32 * j < CH) Stab[buf ^ 1][lane + 32 * j] = pf[j];
             }
             __syncwarp();
         }
 
         // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
-        // gbits[G] = decoded bits of steps 30G .. 30G+29 (bit i = step 30G+i); lives in the dead tab area
-        uint32_t* __restrict__ gbits = reinterpret_cast<uint32_t*>(&S.tab[0][0]);
+        // The reference walks the whole packet back from state 0.  Here the packet is cut into 32 runs of
+        // groups, one per lane; lane l starts TBW groups above its run from an arbitrary state (0), by the
+        // time it enters its own run its path has (almost surely) merged with the true one.  The run
+        // boundaries are then CHECKED: lane l's state on entering its run must equal the state lane l+1
+        // reached on leaving its own (the top lane starts from the true end).  If every boundary agrees
+        // the 32 pieces are exactly the reference's path; otherwise the packet is walked serially.
+        uint32_t* __restrict__ gbits = S.gbits;
+        const int NGR = (T + GS - 1) / GS;
+        bool merged;
         {
-            uint32_t sig4 = 0;
-            for (int c = nch - 1; c >= 0; c--) {
+            const int per = (NGR + 31) >> 5;                         // groups per lane
+            const int nseg = (NGR + per - 1) / per;                  // lanes that own a run
+            const int gs = lane * per, ge = min(gs + per, NGR);
+            const bool has = gs < NGR;
+            const int gtop = has ? min(ge + TBW, NGR) - 1 : -1;      // first (highest) group this lane walks
+            uint32_t sig4 = 0, sigEnd = 0, sigIn = 0;
+            const uint32_t* __restrict__ myrow = Sstage + lane * 64;
+            for (int r = 0; r < per + TBW; r++) {
                 __syncwarp();
-#pragma unroll
-                for (int j = 0; j < NG; j++) {
-                    const uint2 v = survG[(size_t)c * (NG * 32) + j * 32 + lane];
-                    *reinterpret_cast<uint2*>(&S.surv[(j * 32 + lane) * 2]) = v;
+                for (int q = 0; q < nseg; q++) {                     // stage the group lane q walks this round
+                    const int gsq = q * per, geq = min(gsq + per, NGR);
+                    const int gq = min(geq + TBW, NGR) - 1 - r;
+                    if (gq >= gsq) *reinterpret_cast<uint2*>(&Sstage[q * 64 + lane * 2]) = survG[(size_t)gq * 32 + lane];
                 }
                 __syncwarp();
-                for (int g = NG - 1; g >= 0; g--) {
-                    const int t0g = c * CH + g * GS;                 // first step of the group
-                    if (t0g >= T) continue;
-                    const uint32_t* __restrict__ grp = S.surv + g * 64;
+                const int G = gtop - r;
+                if (has && G >= gs) {
+                    if (G == ge - 1) sigEnd = sig4;                  // state at the upper boundary of the run
+                    const int lim = T - G * GS;                      // steps left in this group (>= GS unless it is the last)
                     uint32_t acc = 0;
-                    if (t0g + GS <= T) {
+                    if (lim >= GS) {
 #pragma unroll
-                        for (int i = GS - 1; i >= 0; i--) tb_step(sig4, acc, grp, i);
-                    } else {                                         // the packet ends inside this group
-                        for (int i = T - t0g - 1; i >= 0; i--) tb_step(sig4, acc, grp, i);
+                        for (int i = GS - 1; i >= 0; i--) tb_step(sig4, acc, myrow, i);
+                    } else {
+                        for (int i = lim - 1; i >= 0; i--) tb_step(sig4, acc, myrow, i);
                     }
-                    if (lane0) gbits[c * NG + g] = acc;
+                    if (G < ge) gbits[G] = acc;
+                    if (G == gs) sigIn = sig4;                       // state at the lower boundary of the run
                 }
+            }
+            const uint32_t above = __shfl_down_sync(0xffffffffu, sigIn, 1);
+            const bool ok = !(has && lane < nseg - 1) || sigEnd == above;
+            merged = __all_sync(0xffffffffu, ok);
+        }
+        if (!merged) {                                               // serial walk, all lanes redundantly
+            uint32_t sig4 = 0;
+            for (int G = NGR - 1; G >= 0; G--) {
+                __syncwarp();
+                *reinterpret_cast<uint2*>(&Sstage[lane * 2]) = survG[(size_t)G * 32 + lane];
+                __syncwarp();
+                uint32_t acc = 0;
+                const int lim = min(GS, T - G * GS);
+                for (int i = lim - 1; i >= 0; i--) tb_step(sig4, acc, Sstage, i);
+                if (lane0) gbits[G] = acc;
             }
         }
         __syncwarp();
@@ -266,19 +304,19 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                 uint32_t v = gbits[G] >> off;                        // GS-off bits
                 if (G + 1 < ngroups) v |= gbits[G + 1] << (GS - off);
                 if (2 * GS - off < 32 && G + 2 < ngroups) v |= gbits[G + 2] << (2 * GS - off);
-                S.words[w] = v;
+                Swords[w] = v;
             }
         }
         __syncwarp();
         const int nwords = (T + 31) >> 5;
         if (scram != nullptr) {
             uint8_t* so = scram + (size_t)f * scramStride;
-            for (int i = lane; i < T && i < scramStride; i += 32) so[i] = (uint8_t)((S.words[i >> 5] >> (i & 31)) & 1u);
+            for (int i = lane; i < T && i < scramStride; i += 32) so[i] = (uint8_t)((Swords[i >> 5] >> (i & 31)) & 1u);
         }
 
         // ---------------- descramble (lib/decode_impl.cc:304-323) ----------------
         {
-            const uint32_t w0 = S.words[0];
+            const uint32_t w0 = Swords[0];
             int st = 0;
 #pragma unroll
             for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
@@ -295,20 +333,20 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
             }
             __syncwarp();
             for (int w = lane; w < nwords; w += 32) {
-                uint32_t v = S.words[w];
+                uint32_t v = Swords[w];
                 if (w == 0) v = (v ^ (S.scr[0] << 7)) & ~0x7fu;
                 else {
                     const int o = (32 * w - 7) % 127;
                     v ^= __funnelshift_r(S.scr[o >> 5], S.scr[(o >> 5) + 1], o & 31);
                 }
-                S.words[w] = v;
+                Swords[w] = v;
             }
             __syncwarp();
         }
 
         // ---------------- packetAssemble (lib/decode_impl.cc:325-520) ----------------
         {
-            const uint8_t* __restrict__ by = reinterpret_cast<const uint8_t*>(S.words);
+            const uint8_t* __restrict__ by = reinterpret_cast<const uint8_t*>(Swords);
             uint8_t* out = pdu + (size_t)f * pduStride;
             const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
             int npdu = 0, w = 0;
@@ -352,7 +390,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
 
 }  // namespace
 
-int c8b_viterbi_max_grid(int num_sm) { return num_sm * 5; }
+int c8b_viterbi_max_grid(int num_sm) { return num_sm * 4; }
 
 void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, uint2* d_surv,
                         int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride,
@@ -362,7 +400,10 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
     int need = (nframes + NW - 1) / NW;
     if (grid > need) grid = need;
     if (grid * NW > nwarps_alloc) grid = nwarps_alloc / NW;
+    const size_t smem = NW * sizeof(WarpSmem) + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st);
-    k_viterbi<<<grid, NW * 32, 0, st>>>(d_lut, d_frames, nframes, d_llr, nllr, d_surv, d_pdu, pdu_stride, d_scram, scram_stride,
+    k_viterbi<<<grid, NW * 32, smem, st>>>(d_lut, d_frames, nframes, d_llr, nllr, d_surv, d_pdu, pdu_stride, d_scram, scram_stride,
                                          d_counter);
 }
