@@ -1,11 +1,12 @@
 // k_viterbi.cu -- decode block on the GPU: depuncture + soft Viterbi (K=7, 64 states) + full
-// traceback + descramble + A-MPDU walk + CRC-32, one warp per frame, persistent CTAs.
+// traceback + descramble + A-MPDU walk + CRC-32.  One warp decodes TWO frames at a time (two
+// independent add-compare-select chains interleaved for latency hiding), persistent CTAs.
 //
 // Replaces lib/decode_impl.cc:164-203 (vstb_init), :205-281 (vstb_update), :282-302 (vstb_end),
 // :304-323 (descramble), :325-520 (packetAssemble).  Results are bit-exact with the reference for
 // finite LLRs: path metrics are float32 sums formed in the reference's order (pre + tab[out],
 // tab = {0, t1, t0, t1+t0}), ties go to the even predecessor (strict '>' with 2k visited first),
-// the traceback starts in state 0 and runs over the whole packet.
+// the traceback starts in state 0 and covers the whole packet.
 //
 // Forward pass.  A trellis step maps old states (2k, 2k+1) to new states (k, k+32): one butterfly.
 // Each lane keeps one butterfly's two old metrics in registers (x0 = metric[2k], x1 = metric[2k+1]),
@@ -14,16 +15,20 @@
 // the register index -- one __shfl_xor per step -- and the lane bit that is swapped rotates with
 // period 5 (phase P = t mod 5: the butterfly k of step t lives in lane rotl5(k, P)).
 // Branch metrics: the step's table {0, t1, t0, t1+t0} is staged in shared memory (depunctured on
-// load, 160 steps ahead) and each lane reads its two entries A = tab[c], B = tab[3-c] (c = encoder
+// load, 150 steps ahead) and each lane reads its two entries A = tab[c], B = tab[3-c] (c = encoder
 // output of 2k --0--> k; the other three branches of the butterfly follow from both generator
 // polynomials having taps at the newest and the oldest bit).
-// Decisions: the sign of (even - odd) is shifted into a per-lane 32-bit history word (one per
-// result), so after 32 steps every lane owns 2x32 decisions: 256 B per warp, one coalesced store.
+// Decisions: the sign of (even - odd) is shifted into a per-lane history word (one per result), so
+// after 30 steps every lane owns 2x30 decisions: 256 B per warp and frame, one coalesced store.
+// 16 SASS instructions per step and frame: 2 LDS, 6 FADD, 2 FMNMX, 2 SHF, 3 LOP3, 1 SHFL; the step is
+// a ~100-cycle dependent chain (the shuffle alone ~40), hence two frames per warp.
 //
-// Traceback.  Runs in the same rotated domain: sigma = 2*lane + word selects the history word that
-// holds the decision of the current state; a step is a shared-memory read, a rotate and two LOP3.
-// All lanes execute it redundantly (uniform control flow); decoded bits are packed LSB-first into
-// 32-bit words in shared memory, which makes the word array the PSDU byte stream directly.
+// Traceback.  Runs in the same rotated domain: sig4 = 4*(2*lane + word) addresses the history word
+// that holds the decision of the current state; a step is a shared-memory read, a rotate and three
+// LOP3.  The packet is cut into 32 runs, one per lane, each started 4 groups (120 steps) early from
+// state 0; run boundaries are verified against the neighbouring lane, a mismatch (paths not yet
+// merged) falls back to the serial walk, so the result is always the reference's path.
+// Decoded bits are packed LSB-first into 32-bit words, which makes the word array the PSDU bytes.
 #include "common.cuh"
 
 namespace {
@@ -43,7 +48,7 @@ constexpr int U_BYTES = 8192;                  // union area: forward tables | t
 static_assert(2 * CH * 16 <= U_BYTES && 32 * 64 * 4 <= U_BYTES && WORDS * 4 <= U_BYTES, "union area too small");
 
 // Per-warp shared memory (dynamic).  The union area is used, in turn, as
-//   forward pass : float4 tab[2][CH]   per step {0, t1, t0, t1+t0} (lib/decode_impl.cc:231-234), double buffered
+//   forward pass : float4 tab[2][CH]   per step {0, t1, t0, t1+t0} (lib/decode_impl.cc:231-234), one table per frame
 //   traceback    : uint32 stage[32][64] decision words of the group each lane is walking, [lane][2*rho+h]
 //   afterwards   : uint32 words[WORDS]  decoded bits packed LSB-first, descrambled in place -> PSDU bytes
 struct __align__(16) WarpSmem {
@@ -73,17 +78,18 @@ __device__ __forceinline__ void depunc(int cr, int t, int& i0, int& i1)
     }
 }
 
-__device__ __forceinline__ float4 load_tab(const float* __restrict__ llr, int total, int cr, int t, int T)
+__device__ __forceinline__ float2 load_pair(const float* __restrict__ llr, int total, int cr, int t, int T)
 {
-    float t0 = 0.f, t1 = 0.f;
+    float2 v = make_float2(0.f, 0.f);
     if (t < T) {
         int i0, i1;
         depunc(cr, t, i0, i1);
-        if (i0 >= 0 && i0 < total) t0 = __ldg(llr + i0);
-        if (i1 >= 0 && i1 < total) t1 = __ldg(llr + i1);
+        if (i0 >= 0 && i0 < total) v.x = __ldg(llr + i0);
+        if (i1 >= 0 && i1 < total) v.y = __ldg(llr + i1);
     }
-    return make_float4(0.0f, t1, t0, __fadd_rn(t1, t0));
+    return v;
 }
+__device__ __forceinline__ float4 mk_tab(float2 p) { return make_float4(0.0f, p.y, p.x, __fadd_rn(p.y, p.x)); }   // {0, t1, t0, t1+t0}
 
 // one add-compare-select step at layout phase P.  (x0,x1) in: metrics of old states (2k,2k+1);
 // out: metrics of (2k',2k'+1) for the next phase.  hLo/hHi: decision history of this lane.
@@ -141,6 +147,35 @@ __device__ __forceinline__ void emit_record(uint8_t* __restrict__ out, int& w, i
     npdu++;
 }
 
+struct Job {          // one frame's decode parameters (uniform across the warp)
+    int f, T, cr, total, fmt, len, mcs, ampdu;
+    const float* llr;
+};
+
+// reads frame f; returns T (0 = nothing to decode).  Writes the reject status of lib/decode_impl.cc:93-97.
+__device__ __forceinline__ Job load_job(c8b_frame* __restrict__ frames, int f, int nframes, const float* __restrict__ llrArena,
+                                        int64_t nllr, int64_t pduStride, bool lane0)
+{
+    Job j;
+    j.f = f; j.T = 0; j.cr = 0; j.total = 0; j.fmt = 0; j.len = 0; j.mcs = 0; j.ampdu = 0; j.llr = llrArena;
+    if (f >= nframes) return j;
+    c8b_frame* fr = frames + f;
+    const int status = fr->status;
+    const int T = fr->trellis, total = fr->total, len = fr->len;
+    const int64_t loff = fr->llr_off;
+    j.cr = fr->cr & 3; j.total = total; j.fmt = fr->format; j.len = len; j.mcs = fr->mcs; j.ampdu = fr->ampdu;
+    __syncwarp();
+    if (lane0) { fr->npdu = 0; fr->pdu_bytes = 0; fr->pdu_off = (int64_t)f * pduStride; }
+    if (status != C8B_ST_OK) return j;
+    if (len > C8B_DECODE_B_MAX || T > C8B_DECODE_T_MAX) {          // lib/decode_impl.cc:93-97
+        if (lane0) fr->status = C8B_ST_DECODE_RANGE;
+        return j;
+    }
+    if (T <= 0 || total < 0 || loff < 0 || loff + total > nllr) return j;
+    j.T = T; j.llr = llrArena + loff;
+    return j;
+}
+
 __global__ void __launch_bounds__(NW * 32, 4)
 k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
           int64_t nllr, uint2* __restrict__ survScratch, uint8_t* __restrict__ pdu, int64_t pduStride,
@@ -153,10 +188,10 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
     for (int i = threadIdx.x; i < 256; i += NW * 32) crcTab[i] = lut->crc32tab[i];
     __syncthreads();
     WarpSmem& S = sm[warp];
-    float4 (*Stab)[CH] = reinterpret_cast<float4 (*)[CH]>(S.u);       // [2][CH]
-    uint32_t* __restrict__ Sstage = reinterpret_cast<uint32_t*>(S.u); // [32][64]
-    uint32_t* __restrict__ Swords = reinterpret_cast<uint32_t*>(S.u); // [WORDS]
-    uint2* __restrict__ survG = survScratch + (size_t)(blockIdx.x * NW + warp) * C8B_VIT_TPAD;
+    float4* __restrict__ Stab = reinterpret_cast<float4*>(S.u);        // [2 frames][CH]
+    uint32_t* __restrict__ Sstage = reinterpret_cast<uint32_t*>(S.u);  // [32][64]
+    uint32_t* __restrict__ Swords = reinterpret_cast<uint32_t*>(S.u);  // [WORDS]
+    uint2* __restrict__ survW = survScratch + (size_t)(blockIdx.x * NW + warp) * (2 * C8B_VIT_TPAD);
     const bool lane0 = lane == 0;
 
     // per-phase: index of this lane's A entry in the step table, and its side in the exchange
@@ -171,220 +206,234 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
     }
 
     for (;;) {
-        int f = 0;
-        if (lane0) f = (int)atomicAdd(counter, 1u);
-        f = __shfl_sync(0xffffffffu, f, 0);
-        if (f >= nframes) break;
-        c8b_frame* fr = frames + f;
-        if (fr->status != C8B_ST_OK) {
-            if (lane0) { fr->npdu = 0; fr->pdu_bytes = 0; fr->pdu_off = (int64_t)f * pduStride; }
-            continue;
-        }
-        const int T = fr->trellis, cr = fr->cr & 3, total = fr->total, fmt = fr->format, len = fr->len, mcs = fr->mcs, ampdu = fr->ampdu;
-        const int64_t loff = fr->llr_off;
-        __syncwarp();
-        if (lane0) { fr->npdu = 0; fr->pdu_bytes = 0; fr->pdu_off = (int64_t)f * pduStride; }
-        if (len > C8B_DECODE_B_MAX || T > C8B_DECODE_T_MAX) {      // lib/decode_impl.cc:93-97
-            if (lane0) fr->status = C8B_ST_DECODE_RANGE;
-            continue;
-        }
-        if (T <= 0 || total < 0 || loff < 0 || loff + total > nllr) continue;
-        const float* __restrict__ llr = llrArena + loff;
-        const int nch = (T + CH - 1) / CH;
+        int f0 = 0;
+        if (lane0) f0 = (int)atomicAdd(counter, 2u);
+        f0 = __shfl_sync(0xffffffffu, f0, 0);
+        if (f0 >= nframes) break;
+        Job jobs[2];
+        jobs[0] = load_job(frames, f0, nframes, llrArena, nllr, pduStride, lane0);
+        jobs[1] = load_job(frames, f0 + 1, nframes, llrArena, nllr, pduStride, lane0);
+        const int TA = jobs[0].T, TB = jobs[1].T;
+        const int nchA = (TA + CH - 1) / CH, nchB = (TB + CH - 1) / CH;
+        const int nch = max(nchA, nchB);
+        if (nch == 0) continue;
 
-        // ---------------- forward pass ----------------
-        float x0 = lane0 ? 0.0f : -1000000000000000.0f;          // lib/decode_impl.cc:171-176
-        float x1 = -1000000000000000.0f;
-        float4 pf[NLD];
+        // ---------------- forward pass, frames A and B interleaved ----------------
+        {
+            float xa0 = lane0 ? 0.0f : -1000000000000000.0f, xa1 = -1000000000000000.0f;   // lib/decode_impl.cc:171-176
+            float xb0 = xa0, xb1 = xa1;
+            float2 pfa[NLD], pfb[NLD];
+            __syncwarp();
 #pragma unroll
-        for (int j = 0; j < NLD; j++)
-            if (lane + 32 * j < CH) Stab[0][lane + 32 * j] = load_tab(llr, total, cr, lane + 32 * j, T);
-        __syncwarp();
-        for (int c = 0; c < nch; c++) {
-            const int buf = c & 1;
-            const bool more = c + 1 < nch;
-            if (more) {
-#pragma unroll
-                for (int j = 0; j < NLD; j++) pf[j] = load_tab(llr, total, cr, (c + 1) * CH + lane + 32 * j, T);
-            }
-            const float* __restrict__ tb = reinterpret_cast<const float*>(Stab[buf]);
-            const float* pA0 = tb + 0 + cA[0], *pB0 = tb + 3 - cA[0];
-            const float* pA1 = tb + 4 + cA[1], *pB1 = tb + 7 - cA[1];
-            const float* pA2 = tb + 8 + cA[2], *pB2 = tb + 11 - cA[2];
-            const float* pA3 = tb + 12 + cA[3], *pB3 = tb + 15 - cA[3];
-            const float* pA4 = tb + 16 + cA[4], *pB4 = tb + 19 - cA[4];
-            uint2* __restrict__ sg = survG + (size_t)c * (NG * 32) + lane;
-#pragma unroll 1
-            for (int g = 0; g < NG; g++) {
-                uint32_t hLo = 0, hHi = 0;
-#pragma unroll
-                for (int i5 = 0; i5 < GS / 5; i5++) {               // 30 steps, all shared-memory offsets immediate
-                    const int o = (g * (GS / 5)) * 0 + i5 * 20;
-                    acs_step<0>(x0, x1, pA0[o], pB0[o], amask[0], hLo, hHi);
-                    acs_step<1>(x0, x1, pA1[o], pB1[o], amask[1], hLo, hHi);
-                    acs_step<2>(x0, x1, pA2[o], pB2[o], amask[2], hLo, hHi);
-                    acs_step<3>(x0, x1, pA3[o], pB3[o], amask[3], hLo, hHi);
-                    acs_step<4>(x0, x1, pA4[o], pB4[o], amask[4], hLo, hHi);
+            for (int j = 0; j < NLD; j++)
+                if (lane + 32 * j < CH) {
+                    Stab[lane + 32 * j] = mk_tab(load_pair(jobs[0].llr, jobs[0].total, jobs[0].cr, lane + 32 * j, TA));
+                    Stab[CH + lane + 32 * j] = mk_tab(load_pair(jobs[1].llr, jobs[1].total, jobs[1].cr, lane + 32 * j, TB));
                 }
-                sg[g * 32] = make_uint2(hLo, hHi);
-                pA0 += GS * 4; pB0 += GS * 4; pA1 += GS * 4; pB1 += GS * 4; pA2 += GS * 4; pB2 += GS * 4;
-                pA3 += GS * 4; pB3 += GS * 4; pA4 += GS * 4; pB4 += GS * 4;
-            }
-            if (more) {
+            __syncwarp();
+            const float* __restrict__ tb = reinterpret_cast<const float*>(Stab);
+            for (int c = 0; c < nch; c++) {
+                const bool more = c + 1 < nch;
+                if (more) {
 #pragma unroll
-                for (int j = 0; j < NLD; j++)
-                    if (lane + 32 * j < CH) Stab[buf ^ 1][lane + 32 * j] = pf[j];
+                    for (int j = 0; j < NLD; j++) {
+                        pfa[j] = load_pair(jobs[0].llr, jobs[0].total, jobs[0].cr, (c + 1) * CH + lane + 32 * j, TA);
+                        pfb[j] = load_pair(jobs[1].llr, jobs[1].total, jobs[1].cr, (c + 1) * CH + lane + 32 * j, TB);
+                    }
+                }
+                const float* pA0 = tb + 0 + cA[0], *pB0 = tb + 3 - cA[0];
+                const float* pA1 = tb + 4 + cA[1], *pB1 = tb + 7 - cA[1];
+                const float* pA2 = tb + 8 + cA[2], *pB2 = tb + 11 - cA[2];
+                const float* pA3 = tb + 12 + cA[3], *pB3 = tb + 15 - cA[3];
+                const float* pA4 = tb + 16 + cA[4], *pB4 = tb + 19 - cA[4];
+                uint2* __restrict__ sgA = survW + (size_t)c * (NG * 32) + lane;
+                uint2* __restrict__ sgB = sgA + C8B_VIT_TPAD;
+                const bool stA = c < nchA, stB = c < nchB;
+#pragma unroll 1
+                for (int g = 0; g < NG; g++) {
+                    uint32_t haLo = 0, haHi = 0, hbLo = 0, hbHi = 0;
+#pragma unroll
+                    for (int i5 = 0; i5 < GS / 5; i5++) {           // 30 steps, all shared-memory offsets immediate
+                        const int o = i5 * 20, ob = o + CH * 4;     // frame B's table sits CH float4 further
+                        acs_step<0>(xa0, xa1, pA0[o], pB0[o], amask[0], haLo, haHi);
+                        acs_step<0>(xb0, xb1, pA0[ob], pB0[ob], amask[0], hbLo, hbHi);
+                        acs_step<1>(xa0, xa1, pA1[o], pB1[o], amask[1], haLo, haHi);
+                        acs_step<1>(xb0, xb1, pA1[ob], pB1[ob], amask[1], hbLo, hbHi);
+                        acs_step<2>(xa0, xa1, pA2[o], pB2[o], amask[2], haLo, haHi);
+                        acs_step<2>(xb0, xb1, pA2[ob], pB2[ob], amask[2], hbLo, hbHi);
+                        acs_step<3>(xa0, xa1, pA3[o], pB3[o], amask[3], haLo, haHi);
+                        acs_step<3>(xb0, xb1, pA3[ob], pB3[ob], amask[3], hbLo, hbHi);
+                        acs_step<4>(xa0, xa1, pA4[o], pB4[o], amask[4], haLo, haHi);
+                        acs_step<4>(xb0, xb1, pA4[ob], pB4[ob], amask[4], hbLo, hbHi);
+                    }
+                    if (stA) sgA[g * 32] = make_uint2(haLo, haHi);
+                    if (stB) sgB[g * 32] = make_uint2(hbLo, hbHi);
+                    pA0 += GS * 4; pB0 += GS * 4; pA1 += GS * 4; pB1 += GS * 4; pA2 += GS * 4; pB2 += GS * 4;
+                    pA3 += GS * 4; pB3 += GS * 4; pA4 += GS * 4; pB4 += GS * 4;
+                }
+                __syncwarp();
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < NLD; j++)
+                        if (lane + 32 * j < CH) { Stab[lane + 32 * j] = mk_tab(pfa[j]); Stab[CH + lane + 32 * j] = mk_tab(pfb[j]); }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---------------- per frame: traceback, descramble, assemble ----------------
+#pragma unroll 1
+        for (int which = 0; which < 2; which++) {
+            const Job jb = jobs[which];
+            const int T = jb.T;
+            if (T <= 0) continue;
+            const int f = jb.f, fmt = jb.fmt, len = jb.len, mcs = jb.mcs, ampdu = jb.ampdu;
+            c8b_frame* fr = frames + f;
+            const uint2* __restrict__ survG = survW + (size_t)which * C8B_VIT_TPAD;
+
+            // traceback (lib/decode_impl.cc:282-302), final state 0.  The packet is cut into 32 runs of groups,
+            // one per lane; lane l starts TBW groups above its run from an arbitrary state (0); by the time it
+            // enters its own run its path has (almost surely) merged with the true one.  The run boundaries are
+            // then CHECKED: lane l's state on entering its run must equal the state lane l+1 reached on leaving
+            // its own (the top lane starts from the true end).  If every boundary agrees the 32 pieces are
+            // exactly the reference's path; otherwise the packet is walked serially.
+            uint32_t* __restrict__ gbits = S.gbits;
+            const int NGR = (T + GS - 1) / GS;
+            bool merged;
+            {
+                const int per = (NGR + 31) >> 5;                     // groups per lane
+                const int nseg = (NGR + per - 1) / per;              // lanes that own a run
+                const int gs = lane * per, ge = min(gs + per, NGR);
+                const bool has = gs < NGR;
+                const int gtop = has ? min(ge + TBW, NGR) - 1 : -1;  // first (highest) group this lane walks
+                uint32_t sig4 = 0, sigEnd = 0, sigIn = 0;
+                const uint32_t* __restrict__ myrow = Sstage + lane * 64;
+                for (int r = 0; r < per + TBW; r++) {
+                    __syncwarp();
+                    for (int q = 0; q < nseg; q++) {                 // stage the group lane q walks this round
+                        const int gsq = q * per, geq = min(gsq + per, NGR);
+                        const int gq = min(geq + TBW, NGR) - 1 - r;
+                        if (gq >= gsq) *reinterpret_cast<uint2*>(&Sstage[q * 64 + lane * 2]) = survG[(size_t)gq * 32 + lane];
+                    }
+                    __syncwarp();
+                    const int G = gtop - r;
+                    if (has && G >= gs) {
+                        if (G == ge - 1) sigEnd = sig4;              // state at the upper boundary of the run
+                        const int lim = T - G * GS;                  // steps left in this group (>= GS unless it is the last)
+                        uint32_t acc = 0;
+                        if (lim >= GS) {
+#pragma unroll
+                            for (int i = GS - 1; i >= 0; i--) tb_step(sig4, acc, myrow, i);
+                        } else {
+                            for (int i = lim - 1; i >= 0; i--) tb_step(sig4, acc, myrow, i);
+                        }
+                        if (G < ge) gbits[G] = acc;
+                        if (G == gs) sigIn = sig4;                   // state at the lower boundary of the run
+                    }
+                }
+                const uint32_t above = __shfl_down_sync(0xffffffffu, sigIn, 1);
+                const bool ok = !(has && lane < nseg - 1) || sigEnd == above;
+                merged = __all_sync(0xffffffffu, ok);
+            }
+            if (!merged) {                                           // serial walk, all lanes redundantly
+                uint32_t sig4 = 0;
+                for (int G = NGR - 1; G >= 0; G--) {
+                    __syncwarp();
+                    *reinterpret_cast<uint2*>(&Sstage[lane * 2]) = survG[(size_t)G * 32 + lane];
+                    __syncwarp();
+                    uint32_t acc = 0;
+                    const int lim = min(GS, T - G * GS);
+                    for (int i = lim - 1; i >= 0; i--) tb_step(sig4, acc, Sstage, i);
+                    if (lane0) gbits[G] = acc;
+                }
             }
             __syncwarp();
-        }
-
-        // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
-        // The reference walks the whole packet back from state 0.  Here the packet is cut into 32 runs of
-        // groups, one per lane; lane l starts TBW groups above its run from an arbitrary state (0), by the
-        // time it enters its own run its path has (almost surely) merged with the true one.  The run
-        // boundaries are then CHECKED: lane l's state on entering its run must equal the state lane l+1
-        // reached on leaving its own (the top lane starts from the true end).  If every boundary agrees
-        // the 32 pieces are exactly the reference's path; otherwise the packet is walked serially.
-        uint32_t* __restrict__ gbits = S.gbits;
-        const int NGR = (T + GS - 1) / GS;
-        bool merged;
-        {
-            const int per = (NGR + 31) >> 5;                         // groups per lane
-            const int nseg = (NGR + per - 1) / per;                  // lanes that own a run
-            const int gs = lane * per, ge = min(gs + per, NGR);
-            const bool has = gs < NGR;
-            const int gtop = has ? min(ge + TBW, NGR) - 1 : -1;      // first (highest) group this lane walks
-            uint32_t sig4 = 0, sigEnd = 0, sigIn = 0;
-            const uint32_t* __restrict__ myrow = Sstage + lane * 64;
-            for (int r = 0; r < per + TBW; r++) {
-                __syncwarp();
-                for (int q = 0; q < nseg; q++) {                     // stage the group lane q walks this round
-                    const int gsq = q * per, geq = min(gsq + per, NGR);
-                    const int gq = min(geq + TBW, NGR) - 1 - r;
-                    if (gq >= gsq) *reinterpret_cast<uint2*>(&Sstage[q * 64 + lane * 2]) = survG[(size_t)gq * 32 + lane];
-                }
-                __syncwarp();
-                const int G = gtop - r;
-                if (has && G >= gs) {
-                    if (G == ge - 1) sigEnd = sig4;                  // state at the upper boundary of the run
-                    const int lim = T - G * GS;                      // steps left in this group (>= GS unless it is the last)
-                    uint32_t acc = 0;
-                    if (lim >= GS) {
-#pragma unroll
-                        for (int i = GS - 1; i >= 0; i--) tb_step(sig4, acc, myrow, i);
-                    } else {
-                        for (int i = lim - 1; i >= 0; i--) tb_step(sig4, acc, myrow, i);
-                    }
-                    if (G < ge) gbits[G] = acc;
-                    if (G == gs) sigIn = sig4;                       // state at the lower boundary of the run
-                }
-            }
-            const uint32_t above = __shfl_down_sync(0xffffffffu, sigIn, 1);
-            const bool ok = !(has && lane < nseg - 1) || sigEnd == above;
-            merged = __all_sync(0xffffffffu, ok);
-        }
-        if (!merged) {                                               // serial walk, all lanes redundantly
-            uint32_t sig4 = 0;
-            for (int G = NGR - 1; G >= 0; G--) {
-                __syncwarp();
-                *reinterpret_cast<uint2*>(&Sstage[lane * 2]) = survG[(size_t)G * 32 + lane];
-                __syncwarp();
-                uint32_t acc = 0;
-                const int lim = min(GS, T - G * GS);
-                for (int i = lim - 1; i >= 0; i--) tb_step(sig4, acc, Sstage, i);
-                if (lane0) gbits[G] = acc;
-            }
-        }
-        __syncwarp();
-        // repack 30-bit groups into the 32-bit LSB-first word stream (word w = steps 32w .. 32w+31)
-        {
-            const int ngroups = (T + GS - 1) / GS;
-            for (int w = lane; w < ((T + 31) >> 5); w += 32) {
+            // repack 30-bit groups into the 32-bit LSB-first word stream (word w = steps 32w .. 32w+31)
+            const int nwords = (T + 31) >> 5;
+            for (int w = lane; w < nwords; w += 32) {
                 const int b0 = 32 * w, G = b0 / GS, off = b0 - G * GS;
                 uint32_t v = gbits[G] >> off;                        // GS-off bits
-                if (G + 1 < ngroups) v |= gbits[G + 1] << (GS - off);
-                if (2 * GS - off < 32 && G + 2 < ngroups) v |= gbits[G + 2] << (2 * GS - off);
+                if (G + 1 < NGR) v |= gbits[G + 1] << (GS - off);
+                if (2 * GS - off < 32 && G + 2 < NGR) v |= gbits[G + 2] << (2 * GS - off);
                 Swords[w] = v;
             }
-        }
-        __syncwarp();
-        const int nwords = (T + 31) >> 5;
-        if (scram != nullptr) {
-            uint8_t* so = scram + (size_t)f * scramStride;
-            for (int i = lane; i < T && i < scramStride; i += 32) so[i] = (uint8_t)((Swords[i >> 5] >> (i & 31)) & 1u);
-        }
+            __syncwarp();
+            if (scram != nullptr) {
+                uint8_t* so = scram + (size_t)f * scramStride;
+                for (int i = lane; i < T && i < scramStride; i += 32) so[i] = (uint8_t)((Swords[i >> 5] >> (i & 31)) & 1u);
+            }
 
-        // ---------------- descramble (lib/decode_impl.cc:304-323) ----------------
-        {
-            const uint32_t w0 = Swords[0];
-            int st = 0;
+            // descramble (lib/decode_impl.cc:304-323)
+            {
+                const uint32_t w0 = Swords[0];
+                int st = 0;
 #pragma unroll
-            for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
-            __syncwarp();
-            for (int wq = 0; wq < 5; wq++) {
-                uint32_t q = 0;
+                for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
+                for (int wq = 0; wq < 5; wq++) {
+                    uint32_t q = 0;
 #pragma unroll 8
-                for (int b = 0; b < 32; b++) {
-                    const int fb = ((st >> 6) ^ (st >> 3)) & 1;
-                    st = ((st << 1) & 0x7e) | fb;
-                    q |= (uint32_t)fb << b;
+                    for (int b = 0; b < 32; b++) {
+                        const int fb = ((st >> 6) ^ (st >> 3)) & 1;
+                        st = ((st << 1) & 0x7e) | fb;
+                        q |= (uint32_t)fb << b;
+                    }
+                    if (lane0) S.scr[wq] = q;
                 }
-                if (lane0) S.scr[wq] = q;
-            }
-            __syncwarp();
-            for (int w = lane; w < nwords; w += 32) {
-                uint32_t v = Swords[w];
-                if (w == 0) v = (v ^ (S.scr[0] << 7)) & ~0x7fu;
-                else {
-                    const int o = (32 * w - 7) % 127;
-                    v ^= __funnelshift_r(S.scr[o >> 5], S.scr[(o >> 5) + 1], o & 31);
+                __syncwarp();
+                for (int w = lane; w < nwords; w += 32) {
+                    uint32_t v = Swords[w];
+                    if (w == 0) v = (v ^ (S.scr[0] << 7)) & ~0x7fu;
+                    else {
+                        const int o = (32 * w - 7) % 127;
+                        v ^= __funnelshift_r(S.scr[o >> 5], S.scr[(o >> 5) + 1], o & 31);
+                    }
+                    Swords[w] = v;
                 }
-                Swords[w] = v;
+                __syncwarp();
             }
-            __syncwarp();
-        }
 
-        // ---------------- packetAssemble (lib/decode_impl.cc:325-520) ----------------
-        {
-            const uint8_t* __restrict__ by = reinterpret_cast<const uint8_t*>(Swords);
-            uint8_t* out = pdu + (size_t)f * pduStride;
-            const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
-            int npdu = 0, w = 0;
-            if (fmt == C8B_F_VHT) {
-                int procd = 16;
-                if (procd < T) {
-                    int bp = 2;                                      // byte offset of the next delimiter
-                    int tl = 0;                                      // NOT reset per subframe (:336)
-                    while (true) {
-                        procd += 32;
-                        if (procd > T) break;
-                        const int d0 = by[bp], d1 = by[bp + 1];
-                        const int eof = d0 & 1;
-                        tl |= ((d0 >> 2) & 1) << 12;
-                        tl |= ((d0 >> 3) & 1) << 13;
-                        tl |= (d0 >> 4) | (d1 << 4);
-                        const int padded = (tl / 4 + ((tl % 4) != 0)) * 4;   // bytes
-                        procd += padded * 8;
-                        if (procd > T) break;
-                        bp += 4;
-                        const uint32_t crc = crc32_smem(crcTab, by + bp, tl);
-                        if (crc == 558161692u) {
-                            emit_record(out, w, cap, npdu, fmt, tl, by + bp, tl, mcs, lane);
-                            tl += 4;                                 // :415, carried into the next subframe
+            // packetAssemble (lib/decode_impl.cc:325-520)
+            {
+                const uint8_t* __restrict__ by = reinterpret_cast<const uint8_t*>(Swords);
+                uint8_t* out = pdu + (size_t)f * pduStride;
+                const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
+                int npdu = 0, w = 0;
+                if (fmt == C8B_F_VHT) {
+                    int procd = 16;
+                    if (procd < T) {
+                        int bp = 2;                                  // byte offset of the next delimiter
+                        int tl = 0;                                  // NOT reset per subframe (:336)
+                        while (true) {
+                            procd += 32;
+                            if (procd > T) break;
+                            const int d0 = by[bp], d1 = by[bp + 1];
+                            const int eof = d0 & 1;
+                            tl |= ((d0 >> 2) & 1) << 12;
+                            tl |= ((d0 >> 3) & 1) << 13;
+                            tl |= (d0 >> 4) | (d1 << 4);
+                            const int padded = (tl / 4 + ((tl % 4) != 0)) * 4;   // bytes
+                            procd += padded * 8;
+                            if (procd > T) break;
+                            bp += 4;
+                            const uint32_t crc = crc32_smem(crcTab, by + bp, tl);
+                            if (crc == 558161692u) {
+                                emit_record(out, w, cap, npdu, fmt, tl, by + bp, tl, mcs, lane);
+                                tl += 4;                             // :415, carried into the next subframe
+                            }
+                            bp += padded;
+                            if (eof) break;
                         }
-                        bp += padded;
-                        if (eof) break;
+                    }
+                } else if (!ampdu) {
+                    if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
+                        const uint32_t crc = crc32_smem(crcTab, by + 2, len);
+                        if (crc == 558161692u) emit_record(out, w, cap, npdu, fmt, len, by + 2, len, mcs, lane);
                     }
                 }
-            } else if (!ampdu) {
-                if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
-                    const uint32_t crc = crc32_smem(crcTab, by + 2, len);
-                    if (crc == 558161692u) emit_record(out, w, cap, npdu, fmt, len, by + 2, len, mcs, lane);
-                }
+                if (lane0) { fr->npdu = npdu; fr->pdu_bytes = w; }
             }
-            if (lane0) { fr->npdu = npdu; fr->pdu_bytes = w; }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -397,7 +446,7 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
                         unsigned* d_counter, int grid, cudaStream_t st)
 {
     if (nframes <= 0) return;
-    int need = (nframes + NW - 1) / NW;
+    int need = (nframes + 2 * NW - 1) / (2 * NW);
     if (grid > need) grid = need;
     if (grid * NW > nwarps_alloc) grid = nwarps_alloc / NW;
     const size_t smem = NW * sizeof(WarpSmem) + 1024;
@@ -405,5 +454,5 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
     if (!attr) { cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st);
     k_viterbi<<<grid, NW * 32, smem, st>>>(d_lut, d_frames, nframes, d_llr, nllr, d_surv, d_pdu, pdu_stride, d_scram, scram_stride,
-                                         d_counter);
+                                          d_counter);
 }
