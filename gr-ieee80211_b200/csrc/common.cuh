@@ -13,6 +13,8 @@
 #define C8B_VIT_WARPS 4        // warps (= frames in flight) per CTA
 #define C8B_VIT_TPAD 35040     // uint2 survivor slots per warp: ceil(32782/150) chunks x 160
 
+#define C8B_VIT_WARP_SLOTS (2 * C8B_VIT_TPAD + 640)   // per warp: two frames' survivors + 1093 group words (uint2 units)
+
 // kernel launchers (defined next to their kernels); all asynchronous on `st`
 void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr,
                         uint2* d_surv, int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram,

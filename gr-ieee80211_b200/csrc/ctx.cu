@@ -239,7 +239,7 @@ static int ensure_surv(c8b_ctx* ctx)
     int grid = c8b_viterbi_max_grid(ctx->numSM);
     int warps = grid * C8B_VIT_WARPS;
     if (ctx->survWarps >= warps) return C8B_OK;
-    EN(surv, (size_t)warps * 2 * C8B_VIT_TPAD * sizeof(uint2));   // two frames per warp
+    EN(surv, (size_t)warps * C8B_VIT_WARP_SLOTS * sizeof(uint2));   // two frames per warp + decoded group words
     ctx->survWarps = warps;
     return C8B_OK;
 }

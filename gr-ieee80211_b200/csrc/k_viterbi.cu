@@ -53,7 +53,6 @@ static_assert(2 * CH * 16 <= U_BYTES && 32 * 64 * 4 <= U_BYTES && WORDS * 4 <= U
 //   afterwards   : uint32 words[WORDS]  decoded bits packed LSB-first, descrambled in place -> PSDU bytes
 struct __align__(16) WarpSmem {
     uint4 u[U_BYTES / 16];
-    uint32_t gbits[MAXG + 3];   // 30 decoded bits per group (bit i = step 30G+i)
     uint32_t scr[8];            // scrambler sequence, 160 bits
 };
 
@@ -176,7 +175,7 @@ __device__ __forceinline__ Job load_job(c8b_frame* __restrict__ frames, int f, i
     return j;
 }
 
-__global__ void __launch_bounds__(NW * 32, 4)
+__global__ void __launch_bounds__(NW * 32, 5)
 k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
           int64_t nllr, uint2* __restrict__ survScratch, uint8_t* __restrict__ pdu, int64_t pduStride,
           uint8_t* __restrict__ scram, int64_t scramStride, unsigned* __restrict__ counter)
@@ -191,7 +190,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
     float4* __restrict__ Stab = reinterpret_cast<float4*>(S.u);        // [2 frames][CH]
     uint32_t* __restrict__ Sstage = reinterpret_cast<uint32_t*>(S.u);  // [32][64]
     uint32_t* __restrict__ Swords = reinterpret_cast<uint32_t*>(S.u);  // [WORDS]
-    uint2* __restrict__ survW = survScratch + (size_t)(blockIdx.x * NW + warp) * (2 * C8B_VIT_TPAD);
+    uint2* __restrict__ survW = survScratch + (size_t)(blockIdx.x * NW + warp) * C8B_VIT_WARP_SLOTS;
     const bool lane0 = lane == 0;
 
     // per-phase: index of this lane's A entry in the step table, and its side in the exchange
@@ -297,7 +296,8 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
             // then CHECKED: lane l's state on entering its run must equal the state lane l+1 reached on leaving
             // its own (the top lane starts from the true end).  If every boundary agrees the 32 pieces are
             // exactly the reference's path; otherwise the packet is walked serially.
-            uint32_t* __restrict__ gbits = S.gbits;
+            // gbits[G] = 30 decoded bits of group G (bit i = step 30G+i); lives behind the warp's survivor scratch
+            uint32_t* __restrict__ gbits = reinterpret_cast<uint32_t*>(survW + 2 * C8B_VIT_TPAD);
             const int NGR = (T + GS - 1) / GS;
             bool merged;
             {
@@ -439,7 +439,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
 
 }  // namespace
 
-int c8b_viterbi_max_grid(int num_sm) { return num_sm * 4; }
+int c8b_viterbi_max_grid(int num_sm) { return num_sm * 5; }
 
 void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, uint2* d_surv,
                         int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride,
