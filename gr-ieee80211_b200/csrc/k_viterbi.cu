@@ -44,12 +44,13 @@ static_assert(CH % 5 == 0 && GS % 5 == 0 && CH % GS == 0, "phases must align wit
 static_assert(((C8B_DECODE_T_MAX + CH - 1) / CH) * NG * 32 <= C8B_VIT_TPAD, "survivor scratch too small");
 
 constexpr int TBW = 4;                         // traceback warm-up, in 30-step groups, before a lane's own segment
-constexpr int U_BYTES = 8192;                  // union area: forward tables | traceback staging | decoded words
-static_assert(2 * CH * 16 <= U_BYTES && 32 * 64 * 4 <= U_BYTES && WORDS * 4 <= U_BYTES, "union area too small");
+constexpr int U_BYTES = 8704;                  // union area: forward tables | traceback staging | decoded words
+constexpr int ROW = 68;                        // words per lane row in the traceback staging (64 + pad: conflict-free 16-byte stores)
+static_assert(2 * CH * 16 <= U_BYTES && 32 * ROW * 4 <= U_BYTES && WORDS * 4 <= U_BYTES, "union area too small");
 
 // Per-warp shared memory (dynamic).  The union area is used, in turn, as
 //   forward pass : float4 tab[2][CH]   per step {0, t1, t0, t1+t0} (lib/decode_impl.cc:231-234), one table per frame
-//   traceback    : uint32 stage[32][64] decision words of the group each lane is walking, [lane][2*rho+h]
+//   traceback    : uint32 stage[32][ROW] decision words of the group each lane is walking, [lane][2*rho+h]
 //   afterwards   : uint32 words[WORDS]  decoded bits packed LSB-first, descrambled in place -> PSDU bytes
 struct __align__(16) WarpSmem {
     uint4 u[U_BYTES / 16];
@@ -126,11 +127,44 @@ __device__ __forceinline__ void tb_step(uint32_t& sig4, uint32_t& acc, const uin
 }
 
 // CRC-32 (boost::crc_32_type, lib/decode_impl.h:84): reflected 0x04C11DB7, init/xorout ~0.
-__device__ __forceinline__ uint32_t crc32_smem(const uint32_t* __restrict__ tab, const uint8_t* __restrict__ p, int n)
+// Lane-parallel: the message is cut into 64-byte segments aligned to its END; lane k runs the byte-wise
+// table CRC over segments k and k+32 (register preset to ~0 only for the head segment), advances the
+// result over the bytes that follow with the precomputed linear maps Z^(64*2^p), and the warp XORs the
+// pieces.  Same value as the serial loop for every length (tests/test_gpu_decode.py).
+__device__ __forceinline__ uint32_t crc_seg(const uint32_t* __restrict__ tab, const uint8_t* __restrict__ p, int n, uint32_t c)
 {
-    uint32_t c = 0xffffffffu;
     for (int i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
-    return ~c;
+    return c;
+}
+__device__ __forceinline__ uint32_t crc_advance(const uint32_t* __restrict__ zm, uint32_t c, int m)   // c * Z^(64 m)
+{
+#pragma unroll 1
+    for (int p = 0; p < 6; p++) {
+        if (!((m >> p) & 1)) continue;
+        const uint32_t* __restrict__ col = zm + p * 32;
+        uint32_t r = 0;
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) r ^= ((c >> i) & 1u) ? col[i] : 0u;
+        c = r;
+    }
+    return c;
+}
+__device__ __forceinline__ uint32_t crc32_warp(const uint32_t* __restrict__ tab, const uint32_t* __restrict__ zm,
+                                               const uint8_t* __restrict__ p, int n, int lane)
+{
+    if (n <= 0) return 0u;                                       // ~(~0) : CRC of the empty message
+    const int K = (n + 63) >> 6;                                 // segments, K <= 64 for n <= 4095 (A-MPDU: n < 4100)
+    const int head = n - 64 * (K - 1);                           // bytes in segment 0 (1..64)
+    uint32_t acc = 0;
+    for (int k = lane; k < K; k += 32) {
+        const int start = k == 0 ? 0 : head + 64 * (k - 1);
+        const int len = k == 0 ? head : 64;
+        uint32_t c = crc_seg(tab, p + start, len, k == 0 ? 0xffffffffu : 0u);
+        acc ^= crc_advance(zm, c, K - 1 - k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+    return ~acc;
 }
 
 // append one record [fmt][len lo][len hi][MPDU][mcs] to the frame's PDU area (all lanes cooperate)
@@ -175,7 +209,10 @@ __device__ __forceinline__ Job load_job(c8b_frame* __restrict__ frames, int f, i
     return j;
 }
 
-__global__ void __launch_bounds__(NW * 32, 5)
+#ifndef C8B_VIT_BLOCKS
+#define C8B_VIT_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(NW * 32, C8B_VIT_BLOCKS)
 k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
           int64_t nllr, uint2* __restrict__ survScratch, uint8_t* __restrict__ pdu, int64_t pduStride,
           uint8_t* __restrict__ scram, int64_t scramStride, unsigned* __restrict__ counter)
@@ -183,8 +220,10 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
     extern __shared__ __align__(16) uint8_t dynsm[];
     WarpSmem* sm = reinterpret_cast<WarpSmem*>(dynsm);
     uint32_t* crcTab = reinterpret_cast<uint32_t*>(dynsm + NW * sizeof(WarpSmem));
+    uint32_t* crcZ = crcTab + 256;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 256; i += NW * 32) crcTab[i] = lut->crc32tab[i];
+    for (int i = threadIdx.x; i < 192; i += NW * 32) crcZ[i] = lut->crcZ[i / 32][i % 32];
     __syncthreads();
     WarpSmem& S = sm[warp];
     float4* __restrict__ Stab = reinterpret_cast<float4*>(S.u);        // [2 frames][CH]
@@ -307,17 +346,21 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                 const bool has = gs < NGR;
                 const int gtop = has ? min(ge + TBW, NGR) - 1 : -1;  // first (highest) group this lane walks
                 uint32_t sig4 = 0, sigEnd = 0, sigIn = 0;
-                const uint32_t* __restrict__ myrow = Sstage + lane * 64;
+                uint32_t* __restrict__ myrow = Sstage + lane * ROW;
                 for (int r = 0; r < per + TBW; r++) {
-                    __syncwarp();
-                    for (int q = 0; q < nseg; q++) {                 // stage the group lane q walks this round
-                        const int gsq = q * per, geq = min(gsq + per, NGR);
-                        const int gq = min(geq + TBW, NGR) - 1 - r;
-                        if (gq >= gsq) *reinterpret_cast<uint2*>(&Sstage[q * 64 + lane * 2]) = survG[(size_t)gq * 32 + lane];
-                    }
-                    __syncwarp();
                     const int G = gtop - r;
-                    if (has && G >= gs) {
+                    const bool act = has && G >= gs;
+                    if (act) {                                       // copy the 256-byte row of group G next to the lane (lane-private)
+                        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(survG + (size_t)G * 32);
+                        uint4* __restrict__ dst = reinterpret_cast<uint4*>(myrow);
+#pragma unroll
+                        for (int h8 = 0; h8 < 16; h8 += 8) {
+                            uint4 v[8];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) v[k] = src[h8 + k];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) dst[h8 + k] = v[k];
+                        }
                         if (G == ge - 1) sigEnd = sig4;              // state at the upper boundary of the run
                         const int lim = T - G * GS;                  // steps left in this group (>= GS unless it is the last)
                         uint32_t acc = 0;
@@ -339,7 +382,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                 uint32_t sig4 = 0;
                 for (int G = NGR - 1; G >= 0; G--) {
                     __syncwarp();
-                    *reinterpret_cast<uint2*>(&Sstage[lane * 2]) = survG[(size_t)G * 32 + lane];
+                    *reinterpret_cast<uint2*>(&Sstage[lane * 2]) = survG[(size_t)G * 32 + lane];   // row 0 of the staging area
                     __syncwarp();
                     uint32_t acc = 0;
                     const int lim = min(GS, T - G * GS);
@@ -415,7 +458,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                             procd += padded * 8;
                             if (procd > T) break;
                             bp += 4;
-                            const uint32_t crc = crc32_smem(crcTab, by + bp, tl);
+                            const uint32_t crc = crc32_warp(crcTab, crcZ, by + bp, tl, lane);
                             if (crc == 558161692u) {
                                 emit_record(out, w, cap, npdu, fmt, tl, by + bp, tl, mcs, lane);
                                 tl += 4;                             // :415, carried into the next subframe
@@ -426,7 +469,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                     }
                 } else if (!ampdu) {
                     if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
-                        const uint32_t crc = crc32_smem(crcTab, by + 2, len);
+                        const uint32_t crc = crc32_warp(crcTab, crcZ, by + 2, len, lane);
                         if (crc == 558161692u) emit_record(out, w, cap, npdu, fmt, len, by + 2, len, mcs, lane);
                     }
                 }
@@ -439,7 +482,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
 
 }  // namespace
 
-int c8b_viterbi_max_grid(int num_sm) { return num_sm * 5; }
+int c8b_viterbi_max_grid(int num_sm) { return num_sm * C8B_VIT_BLOCKS; }
 
 void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, uint2* d_surv,
                         int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride,
@@ -449,7 +492,7 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
     int need = (nframes + 2 * NW - 1) / (2 * NW);
     if (grid > need) grid = need;
     if (grid * NW > nwarps_alloc) grid = nwarps_alloc / NW;
-    const size_t smem = NW * sizeof(WarpSmem) + 1024;
+    const size_t smem = NW * sizeof(WarpSmem) + 1024 + 768;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st);

@@ -89,4 +89,13 @@ void c8b_lut_build(c8b_lut* L)
         for (int k = 0; k < 8; k++) c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
         L->crc32tab[i] = c;
     }
+    // zero-byte advance of the (reflected) CRC register is linear: columns of Z^(64*2^p)
+    for (int i = 0; i < 32; i++) {
+        uint32_t c = 1u << i;
+        for (int p = 0; p < 6; p++) {
+            const int nb = p == 0 ? 64 : 64 << (p - 1);          // advance from Z^(64*2^(p-1)) to Z^(64*2^p)
+            for (int k = 0; k < nb; k++) c = L->crc32tab[c & 0xff] ^ (c >> 8);
+            L->crcZ[p][i] = c;
+        }
+    }
 }

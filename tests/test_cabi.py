@@ -59,6 +59,7 @@ def test_lut_blob_matches_reference_tables(golden):
     bmClass = take(32, "u1")
     binL, binNL = take(64, "u1"), take(64, "u1")
     crc = take(256, "<u4")
+    crcz = take(6 * 32, "<u4").reshape(6, 32)
     assert o == blob.size
     assert np.array_equal(ltfL, g["tab_LTF_L_26_F_FLOAT"]) and np.array_equal(ltfNL, g["tab_LTF_NL_28_F_FLOAT"])
     assert np.array_equal(ltfNL22, g["tab_LTF_NL_28_F_FLOAT_VHT22"])
@@ -79,6 +80,19 @@ def test_lut_blob_matches_reference_tables(golden):
         assert o2[(2 * k + 1) * 2] == c ^ 3 and o2[(2 * k) * 2 + 1] == c ^ 3 and o2[(2 * k + 1) * 2 + 1] == c
     import zlib
     assert crc[1] == 0x77073096 and zlib.crc32(b"123456789") == 0xCBF43926
+    # crcZ[p] advances the raw register by 64*2^p zero bytes: crc(m + zeros) follows from crc(m) linearly
+    def raw(data, c=0xFFFFFFFF):
+        for b in data:
+            c = int(crc[(c ^ b) & 0xFF]) ^ (c >> 8)
+        return c
+    c0 = raw(b"hello world")
+    for p_ in range(6):
+        want = raw(bytes(64 << p_), c0)
+        got = 0
+        for i in range(32):
+            if (c0 >> i) & 1:
+                got ^= int(crcz[p_, i])
+        assert got == want, p_
     w = np.exp(-2j * np.pi * np.arange(64) / 64)
     assert np.allclose(twr, w.real, atol=1e-7) and np.allclose(twi, w.imag, atol=1e-7)
     assert sigDemap[0] == -1 and (sigDemap >= 0).sum() == 48 and (binL < 255).sum() == 48 and (binNL < 255).sum() == 52

@@ -131,3 +131,57 @@ def test_decode_range_and_bad_status(rx):
     out, pdu, _ = rx.decode(llr, fr, pdu_stride=64)
     assert out[0]["status"] == 6 and out[1]["status"] == 6 and out[2]["status"] == 3
     assert out["npdu"].sum() == 0
+
+
+def _encode_legacy_psdu(psdu, seed=93):
+    """SERVICE(16 zero bits) + PSDU (LSB first) + 6 tail zeros -> scramble (x^7+x^4+1) -> BCC r=1/2 -> +-4 soft bits"""
+    bits = np.concatenate([np.zeros(16, np.uint8), np.unpackbits(np.frombuffer(psdu, np.uint8), bitorder="little"), np.zeros(6, np.uint8)])
+    st, out = seed, np.zeros(bits.size, np.uint8)
+    for i, b in enumerate(bits):
+        fb = ((st >> 6) ^ (st >> 3)) & 1
+        out[i] = b ^ fb
+        st = ((st << 1) & 0x7E) | fb
+    out[-6:] = 0                                                   # tail bits are zeroed after scrambling
+    reg, coded = 0, np.zeros(2 * out.size, np.float32)
+    for i, b in enumerate(out):
+        reg = ((reg << 1) & 0x7E) | int(b)
+        coded[2 * i] = 4.0 if bin(reg & 0o155).count("1") & 1 else -4.0
+        coded[2 * i + 1] = 4.0 if bin(reg & 0o117).count("1") & 1 else -4.0
+    return coded
+
+
+def test_crc32_and_assemble_all_lengths(rx):
+    """legacy PSDUs of many lengths with a valid FCS must all be published, byte for byte (lane-parallel CRC-32:
+    head segments of 1..64 bytes, 1..64 segments); a corrupted one must not"""
+    import zlib
+    pkg = load_pkg()
+    rng = np.random.default_rng(4)
+    lens = [14, 15, 16, 63, 64, 65, 66, 127, 128, 129, 191, 192, 193, 1000, 1500, 2047, 2048, 2049, 4031, 4032, 4033, 4095]
+    llrs, metas, o = [], [], 0
+    for k, n in enumerate(lens + [300]):
+        body = bytes(rng.integers(0, 256, n - 4, dtype=np.uint8))
+        psdu = body + zlib.crc32(body).to_bytes(4, "little")
+        if k == len(lens):
+            psdu = bytes([psdu[0] ^ 1]) + psdu[1:]                 # broken FCS
+        c = _encode_legacy_psdu(psdu, seed=1 + 5 * k)
+        llrs.append(c); metas.append((n, psdu, o)); o += c.size
+    fr = _frames(pkg, len(metas))
+    for i, (n, psdu, off) in enumerate(metas):
+        fr[i]["format"], fr[i]["mcs"], fr[i]["len"], fr[i]["cr"], fr[i]["ampdu"] = 0, 3, n, 0, 0
+        fr[i]["trellis"], fr[i]["total"], fr[i]["llr_off"] = 8 * n + 22, 2 * (8 * n + 22), off
+    llr = np.concatenate(llrs)
+    out, pdu, _ = rx.decode(llr, fr, pdu_stride=4400)
+    O = ol.oracle()
+    import ctypes as C
+    for i, (n, psdu, off) in enumerate(metas):
+        of = np.zeros(1, ol.FRAME_DTYPE)
+        for k in ("format", "mcs", "len", "cr", "ampdu", "trellis", "total"):
+            of[0][k] = fr[i][k]
+        buf, used = np.zeros(4400, np.uint8), C.c_int(0)
+        np_o = O.orx_decode(np.ascontiguousarray(llr[off:off + fr[i]["total"]]), of.ctypes.data_as(C.POINTER(ol.OrxFrame)), buf, 4400, C.byref(used), None)
+        assert out[i]["npdu"] == np_o and out[i]["pdu_bytes"] == used.value, (n, out[i]["npdu"], np_o)
+        assert bytes(pdu[i, :used.value]) == bytes(buf[:used.value]), n
+        if i < len(lens):
+            assert out[i]["npdu"] == 1 and bytes(pdu[i, :n + 4]) == bytes([0, n & 255, n >> 8]) + psdu + bytes([3]), n
+        else:
+            assert out[i]["npdu"] == 0
