@@ -78,15 +78,30 @@ __device__ __forceinline__ void depunc(int cr, int t, int& i0, int& i1)
     }
 }
 
-__device__ __forceinline__ float2 load_pair(const float* __restrict__ llr, int total, int cr, int t, int T)
+// soft bits consumed by the first T steps, and per chunk of CH steps (CH is a multiple of every puncture period)
+__device__ __forceinline__ int used_by(int cr, int T)
 {
-    float2 v = make_float2(0.f, 0.f);
-    if (t < T) {
-        int i0, i1;
-        depunc(cr, t, i0, i1);
-        if (i0 >= 0 && i0 < total) v.x = __ldg(llr + i0);
-        if (i1 >= 0 && i1 < total) v.y = __ldg(llr + i1);
-    }
+    if (cr == C8B_CR_12) return 2 * T;
+    if (cr == C8B_CR_23) return 3 * (T >> 1) + ((T & 1) ? 2 : 0);
+    if (cr == C8B_CR_34) { const int q = T / 3, r = T - 3 * q; return 4 * q + (r == 0 ? 0 : r + 1); }
+    const int q = T / 5, r = T - 5 * q;
+    return 6 * q + (r == 0 ? 0 : r + 1);
+}
+// packed chunk-relative indices of step s (0..CH-1): lo 16 bits -> t0, hi 16 bits -> t1, 0xffff = punctured
+__device__ __forceinline__ uint32_t rel_pack(int cr, int s)
+{
+    int i0, i1;
+    depunc(cr, s, i0, i1);
+    return (uint32_t)(i0 & 0xffff) | ((uint32_t)(i1 & 0xffff) << 16);
+}
+// (t0,t1) of one step: base = first soft bit of the chunk, lim = soft bits the packet consumes (pad steps read 0)
+__device__ __forceinline__ float2 load_pair(const float* __restrict__ llr, int base, int lim, uint32_t e)
+{
+    const int r0 = (int)(e & 0xffffu), r1 = (int)(e >> 16);
+    const int i0 = base + r0, i1 = base + r1;
+    float2 v;
+    v.x = (r0 != 0xffff && i0 < lim) ? __ldg(llr + i0) : 0.0f;
+    v.y = (r1 != 0xffff && i1 < lim) ? __ldg(llr + i1) : 0.0f;
     return v;
 }
 __device__ __forceinline__ float4 mk_tab(float2 p) { return make_float4(0.0f, p.y, p.x, __fadd_rn(p.y, p.x)); }   // {0, t1, t0, t1+t0}
@@ -261,12 +276,22 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
             float xa0 = lane0 ? 0.0f : -1000000000000000.0f, xa1 = -1000000000000000.0f;   // lib/decode_impl.cc:171-176
             float xb0 = xa0, xb1 = xa1;
             float2 pfa[NLD], pfb[NLD];
+            // chunk-relative soft-bit indices of this lane's table rows (same for every chunk)
+            uint32_t rela[NLD], relb[NLD];
+            const int nrawA = used_by(jobs[0].cr, CH), nrawB = used_by(jobs[1].cr, CH);
+            const int limA = min(jobs[0].total, used_by(jobs[0].cr, TA)), limB = min(jobs[1].total, used_by(jobs[1].cr, TB));
+#pragma unroll
+            for (int j = 0; j < NLD; j++) {
+                const int sidx = min(lane + 32 * j, CH - 1);
+                rela[j] = rel_pack(jobs[0].cr, sidx);
+                relb[j] = rel_pack(jobs[1].cr, sidx);
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < NLD; j++)
                 if (lane + 32 * j < CH) {
-                    Stab[lane + 32 * j] = mk_tab(load_pair(jobs[0].llr, jobs[0].total, jobs[0].cr, lane + 32 * j, TA));
-                    Stab[CH + lane + 32 * j] = mk_tab(load_pair(jobs[1].llr, jobs[1].total, jobs[1].cr, lane + 32 * j, TB));
+                    Stab[lane + 32 * j] = mk_tab(load_pair(jobs[0].llr, 0, limA, rela[j]));
+                    Stab[CH + lane + 32 * j] = mk_tab(load_pair(jobs[1].llr, 0, limB, relb[j]));
                 }
             __syncwarp();
             const float* __restrict__ tb = reinterpret_cast<const float*>(Stab);
@@ -275,8 +300,8 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                 if (more) {
 #pragma unroll
                     for (int j = 0; j < NLD; j++) {
-                        pfa[j] = load_pair(jobs[0].llr, jobs[0].total, jobs[0].cr, (c + 1) * CH + lane + 32 * j, TA);
-                        pfb[j] = load_pair(jobs[1].llr, jobs[1].total, jobs[1].cr, (c + 1) * CH + lane + 32 * j, TB);
+                        pfa[j] = load_pair(jobs[0].llr, (c + 1) * nrawA, limA, rela[j]);
+                        pfb[j] = load_pair(jobs[1].llr, (c + 1) * nrawB, limB, relb[j]);
                     }
                 }
                 const float* pA0 = tb + 0 + cA[0], *pB0 = tb + 3 - cA[0];
