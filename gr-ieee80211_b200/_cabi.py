@@ -52,6 +52,7 @@ SYMBOLS = [
     ("c8b_lut_load", _i, [_vp, _vp, _sz]),
     ("c8b_lut_load_dev", _i, [_vp, _vp, _sz]),
     ("c8b_rx_batch", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
+    ("c8b_rx_batch2", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch_dev", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch_dev_async", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_sync", _i, [_vp]),
@@ -61,6 +62,7 @@ SYMBOLS = [
     ("c8b_trigger", _i, [_vp, _vp, _i64, _vp]),
     ("c8b_detect", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     ("c8b_demod", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64]),
+    ("c8b_demod2", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64]),
     ("c8b_decode", _i, [_vp, _vp, _i64, _vp, _i, _vp, _i64, _vp, _i64]),
 ]
 

@@ -30,3 +30,7 @@ void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_of
                        const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
 void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxSym, const c8b_frame* frames,
                       const float2* hinv, float* llr, cudaStream_t st);
+void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, c8b_frame* frames,
+                        const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st);
+void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxSym,
+                       const c8b_frame* frames, const float2* w2, float* llr, cudaStream_t st);

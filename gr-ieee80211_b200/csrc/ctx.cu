@@ -22,7 +22,7 @@ struct c8b_ctx {
     bool lutLoaded = false;
     unsigned* d_counter = nullptr;
     // scratch (grown on demand)
-    DevBuf iq, preac, preconj, trig, off, len, frames, chan, hinv, llr, surv, pdu, scram, ev;
+    DevBuf iq, iq1, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
     int survWarps = 0;
     // timing
     bool timing = false;
@@ -141,7 +141,7 @@ void c8b_destroy(c8b_ctx* ctx)
     cudaStreamSynchronize(ctx->st);
     timing_collect(ctx);
     for (auto e : ctx->evPool) cudaEventDestroy(e);
-    DevBuf* bufs[] = { &ctx->iq, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
+    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
                        &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -318,12 +318,14 @@ static int check_items(c8b_ctx* ctx, const int64_t* off, const int32_t* len, int
 
 // items [b, e) of a device-resident capture: all stages, results into d_frames[b..e) / d_pdu
 static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, const int32_t* d_len, const int64_t* h_off,
-                     const int32_t* h_len, int b, int e, c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride, int64_t iqShift)
+                     const int32_t* h_len, int b, int e, c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride, int64_t iqShift,
+                     const float2* d_iq1 = nullptr)
 {
     const int n = e - b;
     const ChunkPlan pl = plan(h_off + b, h_len + b, n);
     const int64_t span = pl.end - pl.base;
-    const int64_t llrStride = llr_stride_for(pl.maxLen);
+    const int64_t llrStride = llr_stride_for(pl.maxLen) * (d_iq1 ? 2 : 1);
+    if (d_iq1) EN(w2, (size_t)n * 264 * sizeof(float2));
     EN(preac, (size_t)(span + 64) * sizeof(float));
     EN(chan, (size_t)n * 64 * sizeof(float2));
     EN(hinv, (size_t)n * 64 * sizeof(float2));
@@ -332,6 +334,7 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     if (r) return r;
     // iqShift: the device buffer holds the capture from sample iqShift on (host-staged chunks)
     const float2* iq = d_iq - iqShift;
+    const float2* iq1 = d_iq1 ? d_iq1 - iqShift : nullptr;
     {
         StageTimer tm(ctx, C8B_K_PRESISO);
         c8b_launch_presiso(iq, d_off + b, d_len + b, n, pl.maxLen, pl.base, (float*)ctx->preac.p, nullptr, ctx->st);
@@ -343,13 +346,19 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     }
     {
         StageTimer tm(ctx, C8B_K_HEADER);
-        c8b_launch_header(ctx->d_lut, iq, d_off + b, n, ctx->cfg.mupos, d_frames + b, (const float2*)ctx->chan.p, (float2*)ctx->hinv.p,
-                          llrStride, ctx->st);
+        if (iq1)
+            c8b_launch_header2(ctx->d_lut, iq, iq1, d_off + b, n, d_frames + b, (const float2*)ctx->chan.p, (float2*)ctx->hinv.p,
+                               (float2*)ctx->w2.p, llrStride, ctx->st);
+        else
+            c8b_launch_header(ctx->d_lut, iq, d_off + b, n, ctx->cfg.mupos, d_frames + b, (const float2*)ctx->chan.p, (float2*)ctx->hinv.p,
+                              llrStride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
-        c8b_launch_demod(ctx->d_lut, iq, d_off + b, n, (int)(llrStride / 416), d_frames + b, (const float2*)ctx->hinv.p,
-                         (float*)ctx->llr.p, ctx->st);
+        const int maxSym = (int)(llr_stride_for(pl.maxLen) / 416);
+        c8b_launch_demod(ctx->d_lut, iq, d_off + b, n, maxSym, d_frames + b, (const float2*)ctx->hinv.p, (float*)ctx->llr.p, ctx->st);
+        if (iq1)
+            c8b_launch_demod2(ctx->d_lut, iq, iq1, d_off + b, n, maxSym, d_frames + b, (const float2*)ctx->w2.p, (float*)ctx->llr.p, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_VITERBI);
@@ -411,8 +420,8 @@ int c8b_rx_batch_dev(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const 
 
 // Host IQ: chunks are staged into two device buffers on the copy stream while the previous chunk is
 // processed on the compute stream; results of each chunk go back as soon as its Viterbi kernel ends.
-int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, uint8_t* pdu,
-                 int64_t pdu_stride)
+static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems,
+                         c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride)
 {
     if (!ctx || !h_iq || !off || !len || nitems < 0 || !frames || !pdu || pdu_stride <= 0) return C8B_ERR_ARG;
     int r = need_lut(ctx);
@@ -434,7 +443,9 @@ int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int3
         if (pl.end - pl.base > maxSpan) maxSpan = pl.end - pl.base;
     }
     EN(iq, (size_t)2 * (maxSpan + 16) * sizeof(float2));
+    if (h_iq1) EN(iq1, (size_t)2 * (maxSpan + 16) * sizeof(float2));
     float2* buf[2] = { (float2*)ctx->iq.p, (float2*)ctx->iq.p + (maxSpan + 16) };
+    float2* buf1[2] = { h_iq1 ? (float2*)ctx->iq1.p : nullptr, h_iq1 ? (float2*)ctx->iq1.p + (maxSpan + 16) : nullptr };
     cudaEvent_t copied[2], freed[2];
     for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming); }
     int rc = C8B_OK;
@@ -444,6 +455,9 @@ int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int3
         if (c >= 2) cudaStreamWaitEvent(ctx->stCopy, freed[k], 0);
         cudaError_t er = cudaMemcpyAsync(buf[k], reinterpret_cast<const float2*>(h_iq) + pl.base, (size_t)(pl.end - pl.base) * sizeof(float2),
                                          cudaMemcpyHostToDevice, ctx->stCopy);
+        if (h_iq1 && er == cudaSuccess)
+            er = cudaMemcpyAsync(buf1[k], reinterpret_cast<const float2*>(h_iq1) + pl.base, (size_t)(pl.end - pl.base) * sizeof(float2),
+                                 cudaMemcpyHostToDevice, ctx->stCopy);
         cudaEventRecord(copied[k], ctx->stCopy);
         return er;
     };
@@ -454,7 +468,7 @@ int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int3
         const ChunkPlan pl = plan(off + b, len + b, e - b);
         cudaStreamWaitEvent(ctx->st, copied[k], 0);
         rc = run_chunk(ctx, buf[k], (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, (c8b_frame*)ctx->frames.p,
-                       (uint8_t*)ctx->pdu.p, pdu_stride, pl.base);
+                       (uint8_t*)ctx->pdu.p, pdu_stride, pl.base, buf1[k]);
         cudaEventRecord(freed[k], ctx->st);
         if (rc == C8B_OK) {
             cudaMemcpyAsync(frames + b, (c8b_frame*)ctx->frames.p + b, (size_t)(e - b) * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st);
@@ -468,6 +482,19 @@ int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int3
     if (rc) return rc;
     if (er != cudaSuccess || e2 != cudaSuccess) { ctx->err = std::string("c8b_rx_batch: ") + cudaGetErrorString(er != cudaSuccess ? er : e2); return C8B_ERR_CUDA; }
     return C8B_OK;
+}
+
+int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, uint8_t* pdu,
+                 int64_t pdu_stride)
+{
+    return rx_batch_host(ctx, h_iq, nullptr, off, len, nitems, frames, pdu, pdu_stride);
+}
+
+int c8b_rx_batch2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems,
+                  c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride)
+{
+    if (!h_iq1) return C8B_ERR_ARG;
+    return rx_batch_host(ctx, h_iq0, h_iq1, off, len, nitems, frames, pdu, pdu_stride);
 }
 
 // ---- staged entry points (host buffers) -----------------------------------------------------------
@@ -580,6 +607,49 @@ int c8b_demod(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t
         StageTimer tm(ctx, C8B_K_DEMOD);
         c8b_launch_demod(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, (int)(llr_stride / 48 + 1), (const c8b_frame*)ctx->frames.p,
                          (const float2*)ctx->hinv.p, (float*)ctx->llr.p, ctx->st);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_llr, ctx->llr.p, (size_t)nitems * llr_stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+int c8b_demod2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames,
+               const float* h_chan, float* h_llr, int64_t llr_stride)
+{
+    if (!ctx || !h_iq0 || !h_iq1 || !off || !len || nitems < 0 || !frames || !h_chan || !h_llr || llr_stride <= 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nitems == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    ChunkPlan pl;
+    if ((r = stage_items(ctx, h_iq0, off, len, nitems, &pl))) return r;
+    EN(iq1, (size_t)(pl.end - pl.base + 16) * sizeof(float2));
+    CK(cudaMemcpyAsync(ctx->iq1.p, reinterpret_cast<const float2*>(h_iq1) + pl.base, (size_t)(pl.end - pl.base) * sizeof(float2),
+                       cudaMemcpyHostToDevice, ctx->st));
+    EN(frames, (size_t)nitems * sizeof(c8b_frame));
+    EN(chan, (size_t)nitems * 64 * sizeof(float2));
+    EN(hinv, (size_t)nitems * 64 * sizeof(float2));
+    EN(w2, (size_t)nitems * 264 * sizeof(float2));
+    EN(llr, (size_t)nitems * llr_stride * sizeof(float));
+    CK(cudaMemcpyAsync(ctx->frames.p, frames, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->chan.p, h_chan, (size_t)nitems * 64 * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->llr.p, 0, (size_t)nitems * llr_stride * sizeof(float), ctx->st));
+    const float2* iq = (const float2*)ctx->iq.p - pl.base;
+    const float2* iq1 = (const float2*)ctx->iq1.p - pl.base;
+    {
+        StageTimer tm(ctx, C8B_K_HEADER);
+        c8b_launch_header2(ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, (c8b_frame*)ctx->frames.p, (const float2*)ctx->chan.p,
+                           (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llr_stride, ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_DEMOD);
+        const int maxSym = (int)(llr_stride / 48 + 1);
+        c8b_launch_demod(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxSym, (const c8b_frame*)ctx->frames.p, (const float2*)ctx->hinv.p,
+                         (float*)ctx->llr.p, ctx->st);
+        c8b_launch_demod2(ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, maxSym, (const c8b_frame*)ctx->frames.p,
+                          (const float2*)ctx->w2.p, (float*)ctx->llr.p, ctx->st);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));

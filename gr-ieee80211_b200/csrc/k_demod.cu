@@ -55,7 +55,7 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
     __shared__ uint16_t smap[416];
     const int item = blockIdx.y;
     const c8b_frame* __restrict__ fr = frames + item;
-    if (fr->status != C8B_ST_OK) return;
+    if (fr->status != C8B_ST_OK || fr->nss != 1) return;          // 2-stream frames: k_demod2
     const int nsym = fr->nsym;
     const int sym0 = blockIdx.x * SPB;
     if (sym0 >= nsym) return;
@@ -184,7 +184,189 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k_demod2: per-symbol loop of the 2x2 block (lib/demod2_impl.cc:279-330; htChanUpdate :471-551,
+// vhtChanUpdate :553-630; procSymDeintNL2SS1/SS2 c8p.cc:2238-2338; procSymDepasNL :2442-2451) for
+// 2-stream frames.  16 threads per symbol: threads 0-7 transform antenna 0, threads 8-15 antenna 1
+// (same 8x8 DFT as k_demod); the two halves swap spectra with 8 shuffles, then half a computes
+// stream a = F0*w[2a] + F1*w[2a+1] (the folded (H^H H)^-1 H^H), the 8-pilot common phase is shared
+// through shared memory, and each half demaps / deinterleaves its own stream straight into the
+// stream-deparsed position of the symbol's LLR line.
+// HBM traffic per symbol: 2 x 640 B in, 4*nCBPS B out (3776 B at HT MCS15).
+// ---------------------------------------------------------------------------------------------------
+constexpr int SPW2 = 2;             // symbols per warp
+constexpr int SPB2 = DW * SPW2;     // symbols per CTA
+
+struct __align__(16) WarpBuf2 {
+    float2 xch[SPW2 * 2 * XS];      // transpose buffers: [symbol][antenna]
+    float2 pil[SPW2 * 8];           // equalised pilots: [symbol][stream][7, 21, 43, 57]
+    float llr[SPW2 * 832];          // deparsed soft bits of the warp's symbols, contiguous
+};
+
+__global__ void __launch_bounds__(DW * 32)
+k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const float2* __restrict__ iq1,
+         const int64_t* __restrict__ off, const c8b_frame* __restrict__ frames, const float2* __restrict__ w2All,
+         float* __restrict__ llrArena)
+{
+    __shared__ WarpBuf2 wb[DW];
+    __shared__ uint16_t smap[2][416];
+    const int item = blockIdx.y;
+    const c8b_frame* __restrict__ fr = frames + item;
+    if (fr->status != C8B_ST_OK || fr->nss != 2) return;
+    const int nsym = fr->nsym;
+    const int sym0 = blockIdx.x * SPB2;
+    if (sym0 >= nsym) return;
+    const int fmt = fr->format, ncbps = fr->ncbps, ncbpss = ncbps >> 1;
+    const int nbpsc = ncbpss / 52;
+    const int mi = nbpsc == 1 ? 0 : nbpsc == 2 ? 1 : nbpsc == 4 ? 2 : nbpsc == 6 ? 3 : 4;
+    for (int i = threadIdx.x; i < ncbpss && i < 416; i += DW * 32) { smap[0][i] = lut->deintNL[0][mi][i]; smap[1][i] = lut->deintNL[1][mi][i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 4, a = (lane >> 3) & 1, j = lane & 7;   // symbol in warp, antenna / stream, thread in the DFT
+    WarpBuf2& W = wb[warp];
+    const int sidx = sym0 + warp * SPW2 + g;
+    const bool live = sidx < nsym;
+    const int nsymsamp = fr->nsymsamp;
+    const float rad = fr->rad;
+    const int k0 = fr->data_off + sidx * nsymsamp + C8B_SYM_SHIFT;
+    const float2* __restrict__ x = (a ? iq1 : iq0) + off[item] + fr->sync_idx + 224 + k0;
+
+    cpx v[8];
+    if (live) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int n = j + 8 * m;
+            const float2 s = __ldg(x + n);
+            float sn, cs;
+            sincosf(__fmul_rn((float)(k0 + n + 224), rad), &sn, &cs);     // lib/signal2_impl.cc:172-177
+            v[m] = { s.x * cs - s.y * sn, s.x * sn + s.y * cs };
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = { 0.f, 0.f };
+    }
+    dft8(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 8; k1++) {
+        const int t = (j * k1) & 63;
+        v[k1] = cmul(v[k1], cpx{ __ldg(&lut->twr[t]), __ldg(&lut->twi[t]) });
+    }
+    float2* __restrict__ xb = W.xch + (g * 2 + a) * XS;
+#pragma unroll
+    for (int k1 = 0; k1 < 8; k1++) xb[k1 * 9 + j] = make_float2(v[k1].x, v[k1].y);
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 8; n1++) { const float2 t = xb[j * 9 + n1]; v[n1] = { t.x, t.y }; }
+    dft8(v);                                               // v[k2] = bin j + 8*k2 of antenna a
+
+    // zero-forcing: stream a = F_ant0 * w[2a] + F_ant1 * w[2a+1]
+    const float2* __restrict__ w2 = w2All + (size_t)item * 264;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        cpx o;
+        o.x = __shfl_xor_sync(0xffffffffu, v[k2].x, 8);
+        o.y = __shfl_xor_sync(0xffffffffu, v[k2].y, 8);
+        const cpx f0 = a ? o : v[k2], f1 = a ? v[k2] : o;
+        const float2 wa = __ldg(w2 + 4 * (j + 8 * k2) + 2 * a), wb2 = __ldg(w2 + 4 * (j + 8 * k2) + 2 * a + 1);
+        const cpx p0 = cmul(f0, cpx{ wa.x, wa.y }), p1 = cmul(f1, cpx{ wb2.x, wb2.y });
+        v[k2] = p0 + p1;
+    }
+    float2* __restrict__ pl = W.pil + g * 8 + a * 4;
+    if (j == 7) pl[0] = make_float2(v[0].x, v[0].y);
+    if (j == 5) pl[1] = make_float2(v[2].x, v[2].y);
+    if (j == 3) pl[2] = make_float2(v[5].x, v[5].y);
+    if (j == 1) pl[3] = make_float2(v[7].x, v[7].y);
+    __syncwarp();
+    cpx ps;
+    {
+        // HT: stream 0 uses PILOT_HT_2_1 {1,1,-1,-1}, stream 1 PILOT_HT_2_2 {1,-1,-1,1}; VHT: {1,1,1,-1} for both;
+        // all rotate left once per symbol; polarity index starts at 3 (HT) / 4 (VHT) (lib/demod2_impl.cc:158,204)
+        const bool vht = fmt == C8B_F_VHT;
+        const float P = __ldg(&lut->pilotP[((vht ? 4 : 3) + sidx) % 127]);
+        const int sh = sidx & 3;
+        const uint32_t base0 = vht ? 0x8u : 0xCu, base1 = vht ? 0x8u : 0x6u;     // bit m set = pilot m is -1
+        float re = 0.f, im = 0.f;
+        const int binSlot[4] = { 2, 3, 0, 1 };                                   // bins 7,21,43,57 pair with d_pilot[2],[3],[0],[1]
+#pragma unroll
+        for (int st = 0; st < 2; st++) {
+            const uint32_t base = st ? base1 : base0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int m = binSlot[q];
+                const float sgn = ((base >> ((m + sh) & 3)) & 1u) ? -P : P;
+                const float2 sv = W.pil[g * 8 + st * 4 + q];
+                const float2 rf = __ldg(w2 + 256 + st * 4 + m);
+                const float tr = sv.x * sgn, ti = sv.y * sgn;                      // sig * pilot * P  (exact)
+                const float pr = tr * rf.x - ti * rf.y, pi = tr * rf.y + ti * rf.x;
+                re = (st == 0 && q == 0) ? pr : __fadd_rn(re, pr);
+                im = (st == 0 && q == 0) ? pi : __fadd_rn(im, pi);
+            }
+        }
+        const float inv = 1.0f / sqrtf(re * re + im * im);
+        ps = { re * inv, -im * inv };
+    }
+    float* __restrict__ L = W.llr + g * ncbps;
+    const int sp = nbpsc / 2 > 1 ? nbpsc / 2 : 1;                                // stream parser block (c8p.cc:2445)
+    if (live) {
+        const uint16_t* __restrict__ mapA = smap[a];
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            const int d = lut->binToDataNL[j + 8 * k2];
+            if (d == 255) continue;
+            cpx q = cmul(v[k2], ps);
+            float b[8];
+            if (nbpsc == 1) { b[0] = q.x; }
+            else if (nbpsc == 2) { q = { q.x * 1.4142135623730951f, q.y * 1.4142135623730951f }; b[0] = q.x; b[1] = q.y; }
+            else if (nbpsc == 4) {
+                q = { q.x * 3.1622776601683795f, q.y * 3.1622776601683795f };
+                b[0] = q.x; b[1] = 2.0f - fabsf(q.x); b[2] = q.y; b[3] = 2.0f - fabsf(q.y);
+            } else if (nbpsc == 6) {
+                q = { q.x * 6.48074069840786f, q.y * 6.48074069840786f };
+                const float aa = 4.0f - fabsf(q.x), bb = 4.0f - fabsf(q.y);
+                b[0] = q.x; b[1] = aa; b[2] = 2.0f - fabsf(aa); b[3] = q.y; b[4] = bb; b[5] = 2.0f - fabsf(bb);
+            } else {
+                q = { q.x * 13.038404810405298f, q.y * 13.038404810405298f };
+                const float aa = 8.0f - fabsf(q.x), bb = 8.0f - fabsf(q.y), a2 = 4.0f - fabsf(aa), b2 = 4.0f - fabsf(bb);
+                b[0] = q.x; b[1] = aa; b[2] = a2; b[3] = 2.0f - fabsf(a2); b[4] = q.y; b[5] = bb; b[6] = b2; b[7] = 2.0f - fabsf(b2);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                if (t < nbpsc) {
+                    const int k = mapA[d * nbpsc + t];                            // deinterleaved position in stream a
+                    const int blk = k / sp;
+                    L[(2 * blk + a) * sp + (k - blk * sp)] = b[t];               // stream de-parse
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int wsym0 = sym0 + warp * SPW2;
+    int nlive = nsym - wsym0;
+    nlive = nlive < 0 ? 0 : (nlive > SPW2 ? SPW2 : nlive);
+    const int nfl = nlive * ncbps;
+    float* __restrict__ out = llrArena + fr->llr_off + (int64_t)wsym0 * ncbps;
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
+        float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+        for (int i = lane; i < nfl / 4; i += 32) o4[i] = s4[i];
+    } else {
+        for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
+    }
+}
+
 }  // namespace
+
+void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxSym,
+                       const c8b_frame* frames, const float2* w2, float* llr, cudaStream_t st)
+{
+    if (nitems <= 0 || maxSym <= 0) return;
+    for (int base = 0; base < nitems; base += 65535) {
+        const int cnt = nitems - base < 65535 ? nitems - base : 65535;
+        dim3 grid((maxSym + SPB2 - 1) / SPB2, cnt);
+        k_demod2<<<grid, DW * 32, 0, st>>>(lut, iq0, iq1, d_off + base, frames + base, w2 + (size_t)base * 264, llr);
+    }
+}
 
 void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxSym, const c8b_frame* frames,
                       const float2* hinv, float* llr, cudaStream_t st)

@@ -140,7 +140,37 @@ k_header(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const i
     frames[i] = f;
 }
 
+// 2-antenna header states (demod2): per frame hinv (1-stream frames), w2 (2-stream frames: 256 ZF weights + 8 pilot refs)
+__global__ void __launch_bounds__(64)
+k_header2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const float2* __restrict__ iq1,
+          const int64_t* __restrict__ off, int nitems, c8b_frame* __restrict__ frames, const float2* __restrict__ chan,
+          float2* __restrict__ hinv, float2* __restrict__ w2, int64_t llrStride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    c8b_frame f = frames[i];
+    f.llr_off = (int64_t)i * llrStride;
+    if (f.status == C8B_ST_OK) {
+        cf hl[64], hv[64];
+        for (int k = 0; k < 64; k++) { const float2 c = chan[(size_t)i * 64 + k]; hl[k] = c8b::mk(c.x, c.y); }
+        RotSrc r0, r1;
+        r0.x = reinterpret_cast<const cf*>(iq0 + off[i]) + f.sync_idx + 224; r0.rad = f.rad; r0.nsamp = f.nsamp;
+        r1 = r0; r1.x = reinterpret_cast<const cf*>(iq1 + off[i]) + f.sync_idx + 224;
+        f.status = c8b::demod_header2(lut, r0, r1, f.nsamp, f.l_mcs, f.l_len, hl, &f, hv, reinterpret_cast<cf*>(w2 + (size_t)i * 264));
+        for (int k = 0; k < 64; k++) hinv[(size_t)i * 64 + k] = make_float2(hv[k].re, hv[k].im);
+        if (f.status == C8B_ST_OK && (int64_t)f.total > llrStride) f.status = C8B_ST_OVERFLOW;
+    }
+    frames[i] = f;
+}
+
 }  // namespace
+
+void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, c8b_frame* frames,
+                        const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st)
+{
+    if (nitems <= 0) return;
+    k_header2<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq0, iq1, d_off, nitems, frames, chan, hinv, w2, llrStride);
+}
 
 void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int maxLen, int64_t outBase,
                         float* preac, float2* preconj, cudaStream_t st)

@@ -615,4 +615,183 @@ C8B_HDN int demod_header(const c8b_lut* L, Rot rot, int nsamp, int lmcs, int lle
     return C8B_ST_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// demod2 header states (lib/demod2_impl.cc:72-277, :350-469, :632-758): as demod_header, for the
+// 2-antenna block.  rot0/rot1 = CFO-compensated streams of antenna 0/1 (signal2 copies both,
+// lib/signal2_impl.cc:164-192); format detection uses antenna 0 only.  Outputs, besides the frame
+// fields: hinv[64] when the frame is 1-stream (equalised as in the SISO block) and, for 2 streams,
+//   w2[4*bin + 2a + r] : s_a = F_ant0 * w2[..2a] + F_ant1 * w2[..2a+1]   ((H^H H)^-1 H^H folded, :498-501)
+//   w2[256 + q], w2[260 + q] : conj pilot references of stream 0 / 1 from the first LTF (:432-463),
+//                              q = slot in the d_pilot[] order {43, 57, 7, 21}.
+// ---------------------------------------------------------------------------------------------
+struct cd { double re, im; };
+C8B_HD cd dmk(double r, double i) { cd z; z.re = r; z.im = i; return z; }
+C8B_HD cd dcmul(cd a, cd b) { return dmk(dsub(dmul(a.re, b.re), dmul(a.im, b.im)), dadd(dmul(a.re, b.im), dmul(a.im, b.re))); }
+C8B_HD cd dcadd(cd a, cd b) { return dmk(dadd(a.re, b.re), dadd(a.im, b.im)); }
+C8B_HD cd dconj(cd a) { return dmk(a.re, -a.im); }
+C8B_HD cd tod(cf a) { return dmk((double)a.re, (double)a.im); }
+C8B_HD cf tof(cd a) { return mk((float)a.re, (float)a.im); }
+
+template <class Rot>
+C8B_HDN int demod_header2(const c8b_lut* L, Rot rot0, Rot rot1, int nsamp, int lmcs, int llen, const cf* hl, c8b_frame* f, cf* hinv, cf* w2)
+{
+    Mod m;
+    m.format = m.sumu = m.ampdu = m.nSym = m.nSymSamp = m.nSD = m.nSP = m.nSS = m.nLTF = 0;
+    m.mcs = m.len = m.mod = m.cr = m.nBPSCS = m.nDBPS = m.nCBPS = m.nCBPSS = 0;
+    cf H[64][4], HI[64][4], f1[64], f2[64], f12[64], f22[64], pnl[4], pnl2[4];
+    for (int i = 0; i < 64; i++) for (int k = 0; k < 4; k++) { H[i][k] = mk(0.f, 0.f); HI[i][k] = mk(0.f, 0.f); }
+    for (int q = 0; q < 4; q++) { pnl[q] = mk(0.f, 0.f); pnl2[q] = mk(0.f, 0.f); }
+    const int nsig = nsamp + 320;
+    int pos = 0, trellis = 0;
+    float sssnr0 = 0.f, sssnr1 = 0.f;
+    bool legacy = lmcs > 0;
+    auto win0 = [&](int start, cf* out) { for (int i = 0; i < 64; i++) out[i] = rot0(start + C8B_SYM_SHIFT + i); fft64(L, out, out); };
+    auto win1 = [&](int start, cf* out) { for (int i = 0; i < 64; i++) out[i] = rot1(start + C8B_SYM_SHIFT + i); fft64(L, out, out); };
+    // zero-forcing combine of one bin, the reference's operation order (:498-501)
+    auto zf = [&](int i, cf a1, cf a2, cf& s1, cf& s2) {
+        const cf t1 = cadd(cmul(a1, cconj(H[i][0])), cmul(a2, cconj(H[i][1])));
+        const cf t2 = cadd(cmul(a1, cconj(H[i][2])), cmul(a2, cconj(H[i][3])));
+        s1 = cadd(cmul(t1, HI[i][0]), cmul(t2, HI[i][2]));
+        s2 = cadd(cmul(t1, HI[i][1]), cmul(t2, HI[i][3]));
+    };
+    auto chan_estimate = [&](int start) {                          // nonLegacyChanEstimate :350-469
+        if (m.nSS == 1) {
+            if (m.nLTF == 1) { win0(start, f1); for (int i = 0; i < 64; i++) if (!nl_null(i)) H[i][0] = cdivs(f1[i], L->ltfNL[i]); }
+        } else if (m.nSS == 2) {
+            win0(start, f1); win1(start, f2); win0(start + 80, f12); win1(start + 80, f22);
+            for (int i = 0; i < 64; i++) {
+                if (nl_null(i)) continue;
+                const float l2 = fmul(L->ltfNL[i], 0.5f);             // LTF_NL_28_F_FLOAT2
+                H[i][0] = cscale(csub(f1[i], f12[i]), l2); H[i][1] = cscale(csub(f2[i], f22[i]), l2);
+                H[i][2] = cscale(cadd(f1[i], f12[i]), l2); H[i][3] = cscale(cadd(f2[i], f22[i]), l2);
+            }
+            const int pb[4] = { 7, 21, 43, 57 }, slot[4] = { 2, 3, 0, 1 };
+            if (m.format == C8B_F_VHT)                                // pilot tones interpolated :391-409
+                for (int q = 0; q < 4; q++) for (int k = 0; k < 4; k++) H[pb[q]][k] = cdivs(cadd(H[pb[q] - 1][k], H[pb[q] + 1][k]), 2.0f);
+            for (int i = 0; i < 64; i++) {
+                if (nl_null(i)) continue;
+                const cf a = cadd(cmul(H[i][0], cconj(H[i][0])), cmul(H[i][1], cconj(H[i][1])));
+                const cf b = cadd(cmul(H[i][0], cconj(H[i][2])), cmul(H[i][1], cconj(H[i][3])));
+                const cf c = cadd(cmul(H[i][2], cconj(H[i][0])), cmul(H[i][3], cconj(H[i][1])));
+                const cf d = cadd(cmul(H[i][2], cconj(H[i][2])), cmul(H[i][3], cconj(H[i][3])));
+                const cf inv = cdiv(mk(1.0f, 0.0f), csub(cmul(a, d), cmul(b, c)));
+                HI[i][0] = cmul(inv, d); HI[i][1] = cmul(mk(-inv.re, -inv.im), b);
+                HI[i][2] = cmul(mk(-inv.re, -inv.im), c); HI[i][3] = cmul(inv, a);
+            }
+            for (int q = 0; q < 4; q++) {
+                cf t1, t2;
+                zf(pb[q], f1[pb[q]], f2[pb[q]], t1, t2);
+                if (q == 3) { t1 = mk(-t1.re, -t1.im); t2 = mk(-t2.re, -t2.im); }
+                pnl[slot[q]] = cconj(t1); pnl2[slot[q]] = cconj(t2);
+            }
+        }
+    };
+    if (!legacy) {                                                // DEMOD_S_FORMAT :104-147
+        if (nsig < 160) return C8B_ST_TRUNC;
+        uint8_t vb[48], hb[48];
+        float llrht[96], llrvht[96];
+        win0(0, f1); win0(80, f2);
+        nlsig_demod(L, f1, f2, hl, llrht, llrvht);
+        sig_viterbi(L, llrvht, vb, 48);
+        if (check_vhta(vb)) {                                     // DEMOD_S_VHT :149-178
+            parse_vhta(vb, &m);
+            pos = 160;
+            const int need = 80 + m.nLTF * 80 + 80;
+            if (nsig - pos < need) return C8B_ST_TRUNC;
+            chan_estimate(pos + 80);
+            {                                                     // vhtSigBDemod :632-758
+                cf s1[64], s2[64], q0[52], q1[52];
+                float inted[52], coded[52];
+                uint8_t sb[26], enc[52];
+                const int st = pos + 80 + m.nLTF * 80;
+                bool have = true;
+                if (m.nSS == 1) {
+                    win0(st, f1);
+                    for (int i = 0; i < 64; i++) if (!nl_null(i)) s1[i] = cdiv(f1[i], H[i][0]);
+                    const cf ps = cconj(cadd(cadd(csub(s1[7], s1[21]), s1[43]), s1[57]));
+                    const float pa = cabsf_(ps);
+                    for (int i = 0; i < 64; i++) { const int d = L->binToDataNL[i]; if (d == 255) continue; q0[d] = cdivs(cmul(s1[i], ps), pa); inted[d] = q0[d].re; }
+                } else if (m.nSS == 2) {
+                    win0(st, f1); win1(st, f2);
+                    for (int i = 0; i < 64; i++) if (!nl_null(i)) zf(i, f1[i], f2[i], s1[i], s2[i]);
+                    cf acc = cmul(s1[7], pnl[2]);
+                    acc = csub(acc, cmul(s1[21], pnl[3])); acc = cadd(acc, cmul(s1[43], pnl[0])); acc = cadd(acc, cmul(s1[57], pnl[1]));
+                    acc = cadd(acc, cmul(s2[7], pnl2[2])); acc = csub(acc, cmul(s2[21], pnl2[3]));
+                    acc = cadd(acc, cmul(s2[43], pnl2[0])); acc = cadd(acc, cmul(s2[57], pnl2[1]));
+                    const cf ps = cconj(acc);
+                    const float pa = cabsf_(ps);
+                    for (int i = 0; i < 64; i++) {
+                        const int d = L->binToDataNL[i];
+                        if (d == 255) continue;
+                        q0[d] = cdivs(cmul(s1[i], ps), pa); q1[d] = cdivs(cmul(s2[i], ps), pa);
+                        inted[d] = fdiv(fadd(q0[d].re, q1[d].re), 2.0f);
+                    }
+                } else have = false;
+                if (have) {
+                    for (int i = 0; i < 52; i++) coded[L->deintNL[0][0][i]] = inted[i];
+                    sig_viterbi(L, coded, sb, 26);
+                    bcc_encode(sb, enc, 26);
+                    double n0 = 0.0, n1 = 0.0;
+                    for (int i = 0; i < 52; i++) {
+                        const float ref = enc[L->deintNL[0][0][i]] ? 1.0f : -1.0f;
+                        const cf e0 = mk(fsub(q0[i].re, ref), q0[i].im);
+                        n0 += (double)fadd(fmul(e0.re, e0.re), fmul(e0.im, e0.im));
+                        if (m.nSS == 2) { const cf e1 = mk(fsub(q1[i].re, ref), q1[i].im); n1 += (double)fadd(fmul(e1.re, e1.re), fmul(e1.im, e1.im)); }
+                    }
+                    sssnr0 = (float)(log10(52.0 / n0) * 10.0);
+                    if (m.nSS == 2) sssnr1 = (float)(log10(52.0 / n1) * 10.0);
+                } else {
+                    for (int i = 0; i < 26; i++) sb[i] = 0;
+                }
+                parse_vhtb(sb, &m);
+            }
+            const int nl = (llen * 8 + 22 + 23) / 24;
+            const bool ok = m.len > 0 && m.len <= 4095 && m.nSS <= 2 && (nl * 80) >= (m.nSym * m.nSymSamp + 160 + 80 + m.nLTF * 80 + 80);
+            pos += need;
+            if (!ok) return C8B_ST_FORMAT;
+            trellis = m.nSym * m.nDBPS;
+        } else {
+            sig_viterbi(L, llrht, hb, 48);
+            if (check_ht(hb)) {                                   // DEMOD_S_HT :180-216
+                parse_ht(hb, &m);
+                pos = 160;
+                const int need = 80 + m.nLTF * 80;
+                if (nsig - pos < need) return C8B_ST_TRUNC;
+                chan_estimate(pos + 80);
+                const int nl = (llen * 8 + 22 + 23) / 24;
+                const bool ok = m.len > 0 && m.len <= 4095 && m.nSS <= 2 && (nl * 80) >= (m.nSym * m.nSymSamp + 160 + 80 + m.nLTF * 80);
+                pos += need;
+                if (!ok) return C8B_ST_FORMAT;
+                trellis = m.len * 8 + 22;
+            } else legacy = true;
+        }
+    }
+    if (legacy) { parse_l(lmcs, llen, &m); trellis = m.len * 8 + 22; }
+    f->format = m.format; f->mcs = m.mcs; f->len = m.len; f->cr = m.cr; f->ampdu = m.ampdu;
+    f->nss = m.nSS; f->nsym = m.nSym; f->nsymsamp = m.nSymSamp; f->ncbps = m.nCBPS; f->ndbps = m.nDBPS;
+    f->trellis = trellis; f->total = m.nSym * m.nCBPS; f->data_off = pos;
+    f->sssnr0 = (m.format == C8B_F_VHT) ? sssnr0 : 0.f;
+    f->sssnr1 = (m.format == C8B_F_VHT && m.nSS == 2) ? sssnr1 : 0.f;
+    for (int i = 0; i < 64; i++) {
+        const cf hh = (m.format == C8B_F_L) ? hl[i] : H[i][0];
+        const bool used = (m.format == C8B_F_L) ? !l_null(i) : !nl_null(i);
+        const double den = dadd(dmul((double)hh.re, (double)hh.re), dmul((double)hh.im, (double)hh.im));
+        hinv[i] = (used && m.nSS == 1) ? mk((float)((double)hh.re / den), (float)(-(double)hh.im / den)) : mk(0.f, 0.f);
+        for (int k = 0; k < 4; k++) w2[4 * i + k] = mk(0.f, 0.f);
+        if (m.nSS == 2 && !nl_null(i)) {
+            const cd h0 = dconj(tod(H[i][0])), h1 = dconj(tod(H[i][1])), h2 = dconj(tod(H[i][2])), h3 = dconj(tod(H[i][3]));
+            const cd i0 = tod(HI[i][0]), i1 = tod(HI[i][1]), i2 = tod(HI[i][2]), i3 = tod(HI[i][3]);
+            w2[4 * i + 0] = tof(dcadd(dcmul(h0, i0), dcmul(h2, i2)));   // stream 0 <- antenna 0
+            w2[4 * i + 1] = tof(dcadd(dcmul(h1, i0), dcmul(h3, i2)));   // stream 0 <- antenna 1
+            w2[4 * i + 2] = tof(dcadd(dcmul(h0, i1), dcmul(h2, i3)));   // stream 1 <- antenna 0
+            w2[4 * i + 3] = tof(dcadd(dcmul(h1, i1), dcmul(h3, i3)));   // stream 1 <- antenna 1
+        }
+    }
+    for (int q = 0; q < 4; q++) { w2[256 + q] = pnl[q]; w2[260 + q] = pnl2[q]; }
+    if (m.nSS != 1 && m.nSS != 2) return C8B_ST_FORMAT;
+    if (m.nSS == 1 && m.format != C8B_F_L && m.nLTF != 1) return C8B_ST_FORMAT;   // reference leaves H unset (:355-372)
+    if (pos + m.nSym * m.nSymSamp > nsig) return C8B_ST_TRUNC;
+    return C8B_ST_OK;
+}
+
 }  // namespace c8b

@@ -97,6 +97,18 @@ class Receiver:
         self._ck(self.L.c8b_rx_batch(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch")
         return frames, pdu.reshape(n, pdu_stride)
 
+    def rx_batch2(self, iq0, iq1, off, length, pdu_stride=4400):
+        """2x2: antenna 0 drives detection, both antennas are demodulated (signal2 + demod2)."""
+        a, b = _c2f(iq0), _c2f(iq1)
+        assert a.size == b.size
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        n = off.size
+        frames = np.zeros(n, FRAME_DTYPE)
+        pdu = np.zeros(n * pdu_stride, np.uint8)
+        self._ck(self.L.c8b_rx_batch2(self.h, ptr(a), ptr(b), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch2")
+        return frames, pdu.reshape(n, pdu_stride)
+
     def rx_batch_dev(self, d_iq_ptr, off, length, pdu_stride=4400, frames=None, pdu=None):
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
@@ -147,6 +159,17 @@ class Receiver:
         chanf = _c2f(chan)
         llr = np.zeros(n * llr_stride, np.float32)
         self._ck(self.L.c8b_demod(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(chanf), ptr(llr), llr_stride), "c8b_demod")
+        return frames, llr.reshape(n, llr_stride)
+
+    def demod2(self, iq0, iq1, off, length, frames, chan, llr_stride):
+        a, b = _c2f(iq0), _c2f(iq1)
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        n = off.size
+        frames = np.ascontiguousarray(frames).copy()
+        chanf = _c2f(chan)
+        llr = np.zeros(n * llr_stride, np.float32)
+        self._ck(self.L.c8b_demod2(self.h, ptr(a), ptr(b), ptr(off), ptr(length), n, ptr(frames), ptr(chanf), ptr(llr), llr_stride), "c8b_demod2")
         return frames, llr.reshape(n, llr_stride)
 
     def decode(self, llr, frames, pdu_stride=4400, want_scram=False, scram_stride=0):

@@ -11,6 +11,7 @@
  *   lib/sync_impl.cc:61-196     sync::general_work        c8b_detect         (trigger+sync+signal)
  *   lib/signal_impl.cc:62-206   signal::general_work      c8b_detect / CFO copy fused in c8b_demod
  *   lib/demod_impl.cc:59-557    demod::general_work       c8b_demod          (header + symbols)
+ *   lib/signal2_impl.cc:63-212, lib/demod2_impl.cc:58-806 (2x2) c8b_demod2 / c8b_rx_batch2
  *   lib/decode_impl.cc:60-520   decode::general_work      c8b_decode / c8b_viterbi
  *   whole flowgraph examples/rx.grc:753-767               c8b_rx_batch / c8b_rx_batch_dev
  *   LUTs of lib/cloud80211phy.cc (c8p.h:151-195)          c8b_lut_blob / c8b_lut_load
@@ -137,6 +138,10 @@ int  c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int
                   c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
 int  c8b_rx_batch_dev(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const int32_t* len, int nitems,
                       c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
+/* 2x2 receive (examples/rx2.grc:676-692: antenna 0 feeds presiso/trigger/sync, both antennas feed signal2 ->
+ * demod2): h_iq0 / h_iq1 are the two antennas' captures with the SAME item offsets/lengths. */
+int  c8b_rx_batch2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems,
+                   c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
 /* as c8b_rx_batch_dev but results stay on the device (d_frames: nitems c8b_frame, d_pdu:
  * nitems*pdu_stride bytes); nothing is copied back and the call does not synchronise. */
 int  c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* h_off, const int32_t* h_len, int nitems,
@@ -168,6 +173,9 @@ int  c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32
  * call sets llr_off = i*llr_stride. */
 int  c8b_demod(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems,
                c8b_frame* frames, const float* h_chan, float* h_llr, int64_t llr_stride);
+/* demod2: as c8b_demod for the 2-antenna block (1- and 2-stream HT/VHT frames, legacy on antenna 0) */
+int  c8b_demod2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems,
+                c8b_frame* frames, const float* h_chan, float* h_llr, int64_t llr_stride);
 /* decode: depuncture + Viterbi + descramble + assemble + CRC-32 for frames with cr/trellis/format/
  * len/mcs/ampdu/total/llr_off set.  h_scram (may be NULL): one byte per decoded (still scrambled)
  * bit, frame i at h_scram + i*scram_stride. */

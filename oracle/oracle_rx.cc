@@ -749,6 +749,256 @@ int demodFrame(const cf* sig, int nsig, int lmcs, int llen, const cf* hl, orx_fr
 }
 
 // ------------------------------------------------------------------------------------------------
+// demod2: 2x2 SU-MIMO demod (ref: lib/demod2_impl.cc:58-348 state machine, :350-806 helpers).
+// sig1/sig2 = the two CFO-compensated streams signal2 copies out (lib/signal2_impl.cc:164-192).
+// ------------------------------------------------------------------------------------------------
+struct Demod2 {
+    Mod m;
+    cf HL[64], H[64][4], HI[64][4], sig1[64], sig2[64], qam[2][52], f1[64], f2[64], f12[64], f22[64];
+    cf pnl[4], pnl2[4];
+    float pilot[4], pilot2[4];
+    int pilotP;
+    float sssnr0, sssnr1;
+
+    static bool nlNull(int i) { return i == 0 || (i >= 29 && i <= 35); }
+    static bool lNull(int i) { return i == 0 || (i >= 27 && i <= 37); }
+    static bool isPilot(int i) { return i == 7 || i == 21 || i == 43 || i == 57; }
+    static void shift(float* p) { float t = p[0]; p[0] = p[1]; p[1] = p[2]; p[2] = p[3]; p[3] = t; }
+
+    void zf(int i, const cf& a1, const cf& a2, cf& s1, cf& s2)        // (H^H H)^-1 H^H y, :498-501
+    {
+        cf t1 = a1 * std::conj(H[i][0]) + a2 * std::conj(H[i][1]);
+        cf t2 = a1 * std::conj(H[i][2]) + a2 * std::conj(H[i][3]);
+        s1 = t1 * HI[i][0] + t2 * HI[i][2];
+        s2 = t1 * HI[i][1] + t2 * HI[i][3];
+    }
+
+    void chanEstimate(const cf* s1, const cf* s2)                     // :350-469
+    {
+        if (m.nSS == 1) {
+            if (m.nLTF == 1) {
+                fft64(s1 + SYM_SHIFT, f1);
+                for (int i = 0; i < 64; i++) if (!nlNull(i)) H[i][0] = f1[i] / T.ltfNL[i];
+            }
+        } else if (m.nSS == 2) {
+            fft64(s1 + SYM_SHIFT, f1); fft64(s2 + SYM_SHIFT, f2);
+            fft64(s1 + SYM_SHIFT + 80, f12); fft64(s2 + SYM_SHIFT + 80, f22);
+            for (int i = 0; i < 64; i++) {
+                if (nlNull(i)) continue;
+                float l2 = T.ltfNL[i] * 0.5f;                         // LTF_NL_28_F_FLOAT2 (c8p.cc:142-158) = LTF/2, exact
+                H[i][0] = (f1[i] - f12[i]) * l2; H[i][1] = (f2[i] - f22[i]) * l2;
+                H[i][2] = (f1[i] + f12[i]) * l2; H[i][3] = (f2[i] + f22[i]) * l2;
+            }
+            if (m.format == F_VHT) {                                  // pilot tones interpolated :391-409
+                const int pb[4] = { 7, 21, 43, 57 };
+                for (int q = 0; q < 4; q++) for (int k = 0; k < 4; k++) H[pb[q]][k] = (H[pb[q] - 1][k] + H[pb[q] + 1][k]) / 2.0f;
+            }
+            for (int i = 0; i < 64; i++) {
+                if (nlNull(i)) continue;
+                cf a = H[i][0] * std::conj(H[i][0]) + H[i][1] * std::conj(H[i][1]);
+                cf b = H[i][0] * std::conj(H[i][2]) + H[i][1] * std::conj(H[i][3]);
+                cf c = H[i][2] * std::conj(H[i][0]) + H[i][3] * std::conj(H[i][1]);
+                cf d = H[i][2] * std::conj(H[i][2]) + H[i][3] * std::conj(H[i][3]);
+                cf inv = 1.0f / (a * d - b * c);
+                HI[i][0] = inv * d; HI[i][1] = -inv * b; HI[i][2] = -inv * c; HI[i][3] = inv * a;
+            }
+            const int pb[4] = { 7, 21, 43, 57 }, slot[4] = { 2, 3, 0, 1 };
+            for (int q = 0; q < 4; q++) {                             // pilot references from the first LTF :432-463
+                cf t1, t2;
+                zf(pb[q], f1[pb[q]], f2[pb[q]], t1, t2);
+                if (q == 3) { t1 = -t1; t2 = -t2; }
+                pnl[slot[q]] = std::conj(t1); pnl2[slot[q]] = std::conj(t2);
+            }
+        }
+    }
+
+    cf pilotSum2(const float* pa, const float* pb_)                   // 8-term sum of htChanUpdate / vhtChanUpdate
+    {
+        float P = T.pilotP[pilotP];
+        return std::conj(sig1[7] * pa[2] * P * pnl[2] + sig1[21] * pa[3] * P * pnl[3] + sig1[43] * pa[0] * P * pnl[0] + sig1[57] * pa[1] * P * pnl[1] +
+                         sig2[7] * pb_[2] * P * pnl2[2] + sig2[21] * pb_[3] * P * pnl2[3] + sig2[43] * pb_[0] * P * pnl2[0] + sig2[57] * pb_[1] * P * pnl2[1]);
+    }
+
+    void symUpdate(const cf* s1, const cf* s2)                        // htChanUpdate :471-551 / vhtChanUpdate :553-630
+    {
+        if (m.nSS == 1) {
+            fft64(s1 + SYM_SHIFT, f1);
+            for (int i = 0; i < 64; i++) if (!nlNull(i)) sig1[i] = f1[i] / H[i][0];
+            float P = T.pilotP[pilotP];
+            cf ps = std::conj(sig1[7] * pilot[2] * P + sig1[21] * pilot[3] * P + sig1[43] * pilot[0] * P + sig1[57] * pilot[1] * P);
+            shift(pilot);
+            pilotP = (pilotP + 1) % 127;
+            float pa = std::abs(ps);
+            int j = 26;
+            for (int i = 0; i < 64; i++) { if (nlNull(i) || isPilot(i)) continue; qam[0][j] = sig1[i] * ps / pa; if (++j >= 52) j = 0; }
+        } else {
+            fft64(s1 + SYM_SHIFT, f1); fft64(s2 + SYM_SHIFT, f2);
+            for (int i = 0; i < 64; i++) if (!nlNull(i)) zf(i, f1[i], f2[i], sig1[i], sig2[i]);
+            cf ps = (m.format == F_VHT) ? pilotSum2(pilot, pilot) : pilotSum2(pilot, pilot2);
+            shift(pilot);
+            if (m.format != F_VHT) shift(pilot2);
+            pilotP = (pilotP + 1) % 127;
+            float pa = std::abs(ps);
+            int j = 26;
+            for (int i = 0; i < 64; i++) {
+                if (nlNull(i) || isPilot(i)) continue;
+                qam[0][j] = sig1[i] * ps / pa; qam[1][j] = sig2[i] * ps / pa;
+                if (++j >= 52) j = 0;
+            }
+        }
+    }
+
+    void legacyUpdate(const cf* s1)                                   // :760-786
+    {
+        fft64(s1 + SYM_SHIFT, f1);
+        for (int i = 0; i < 64; i++) if (!lNull(i)) sig1[i] = f1[i] / HL[i];
+        float P = T.pilotP[pilotP];
+        cf ps = std::conj(sig1[7] * pilot[2] * P + sig1[21] * pilot[3] * P + sig1[43] * pilot[0] * P + sig1[57] * pilot[1] * P);
+        pilotP = (pilotP + 1) % 127;
+        float pa = std::abs(ps);
+        int j = 24;
+        for (int i = 0; i < 64; i++) { if (lNull(i) || isPilot(i)) continue; qam[0][j] = sig1[i] * ps / pa; if (++j >= 48) j = 0; }
+    }
+
+    void sigB(const cf* s1, const cf* s2, uint8_t* bits26)            // vhtSigBDemod :632-758
+    {
+        cf q0[52], q1[52];
+        float inted[52], coded[52];
+        if (m.nSS == 1) {
+            fft64(s1 + SYM_SHIFT, f1);
+            for (int i = 0; i < 64; i++) if (!nlNull(i)) sig1[i] = f1[i] / H[i][0];
+            cf ps = std::conj(sig1[7] - sig1[21] + sig1[43] + sig1[57]);
+            float pa = std::abs(ps);
+            int j = 26;
+            for (int i = 0; i < 64; i++) { if (nlNull(i) || isPilot(i)) continue; q0[j] = sig1[i] * ps / pa; inted[j] = q0[j].real(); if (++j >= 52) j = 0; }
+        } else if (m.nSS == 2) {
+            fft64(s1 + SYM_SHIFT, f1); fft64(s2 + SYM_SHIFT, f2);
+            for (int i = 0; i < 64; i++) if (!nlNull(i)) zf(i, f1[i], f2[i], sig1[i], sig2[i]);
+            cf ps = std::conj(sig1[7] * pnl[2] - sig1[21] * pnl[3] + sig1[43] * pnl[0] + sig1[57] * pnl[1] +
+                              sig2[7] * pnl2[2] - sig2[21] * pnl2[3] + sig2[43] * pnl2[0] + sig2[57] * pnl2[1]);
+            float pa = std::abs(ps);
+            int j = 26;
+            for (int i = 0; i < 64; i++) {
+                if (nlNull(i) || isPilot(i)) continue;
+                q0[j] = sig1[i] * ps / pa; q1[j] = sig2[i] * ps / pa;
+                inted[j] = (q0[j].real() + q1[j].real()) / 2.0f;
+                if (++j >= 52) j = 0;
+            }
+        } else { memset(bits26, 0, 26); return; }
+        for (int i = 0; i < 52; i++) coded[T.deintNL[0][0][i]] = inted[i];
+        sigViterbi(coded, bits26, 26);
+        uint8_t enc[52], intl[52];
+        bcc(bits26, enc, 26);
+        for (int i = 0; i < 52; i++) intl[i] = enc[T.deintNL[0][0][i]];
+        double n0 = 0.0, n1 = 0.0;
+        for (int i = 0; i < 52; i++) {
+            cf ref = intl[i] ? cf(1.0f, 0.0f) : cf(-1.0f, 0.0f);
+            q0[i] -= ref;
+            n0 += (double)(q0[i].real() * q0[i].real() + q0[i].imag() * q0[i].imag());
+            if (m.nSS == 2) { q1[i] -= ref; n1 += (double)(q1[i].real() * q1[i].real() + q1[i].imag() * q1[i].imag()); }
+        }
+        sssnr0 = (float)(log10(52.0 / n0) * 10.0);
+        if (m.nSS == 2) sssnr1 = (float)(log10(52.0 / n1) * 10.0);
+    }
+};
+
+int demodFrame2(const cf* sig1, const cf* sig2, int nsig, int lmcs, int llen, const cf* hl, orx_frame* f, float* llrOut, int llrCap)
+{
+    static thread_local Demod2 d;
+    memset(&d.m, 0, sizeof(d.m));
+    for (int i = 0; i < 64; i++) { d.HL[i] = hl[i]; d.sig1[i] = d.sig2[i] = cf(0.f, 0.f); for (int k = 0; k < 4; k++) d.H[i][k] = d.HI[i][k] = cf(0.f, 0.f); }
+    d.sssnr0 = d.sssnr1 = 0.f;
+    int pos = 0, trellis = 0;
+    bool legacy = lmcs > 0;
+    if (!legacy) {                                                    // DEMOD_S_FORMAT :104-147 (antenna 0 only)
+        if (nsig < 160) return ORX_E_TRUNC;
+        uint8_t vb[48], hb[48];
+        float llrht[96], llrvht[96];
+        fft64(sig1 + SYM_SHIFT, d.f1); fft64(sig1 + SYM_SHIFT + 80, d.f2);
+        nlsigDemod(d.f1, d.f2, d.HL, llrht, llrvht);
+        sigViterbi(llrvht, vb, 48);
+        if (checkVhtA(vb)) {                                          // DEMOD_S_VHT :149-178
+            parseVhtA(vb, &d.m);
+            pos = 160;
+            int need = 80 + d.m.nLTF * 80 + 80;
+            if (nsig - pos < need) return ORX_E_TRUNC;
+            uint8_t sb[26];
+            d.chanEstimate(sig1 + pos + 80, sig2 + pos + 80);
+            d.sigB(sig1 + pos + 80 + d.m.nLTF * 80, sig2 + pos + 80 + d.m.nLTF * 80, sb);
+            parseVhtB(sb, &d.m);
+            int nl = (llen * 8 + 22 + 23) / 24;
+            bool ok = d.m.len > 0 && d.m.len <= 4095 && d.m.nSS <= 2 && (nl * 80) >= (d.m.nSym * d.m.nSymSamp + 160 + 80 + d.m.nLTF * 80 + 80);
+            pos += need;
+            if (!ok) return ORX_E_FORMAT;
+            trellis = d.m.nSym * d.m.nDBPS;
+            d.pilot[0] = 1.f; d.pilot[1] = 1.f; d.pilot[2] = 1.f; d.pilot[3] = -1.f;                 // PILOT_VHT
+            d.pilotP = 4;
+        } else {
+            sigViterbi(llrht, hb, 48);
+            if (checkHt(hb)) {                                        // DEMOD_S_HT :180-216
+                parseHt(hb, &d.m);
+                pos = 160;
+                int need = 80 + d.m.nLTF * 80;
+                if (nsig - pos < need) return ORX_E_TRUNC;
+                d.chanEstimate(sig1 + pos + 80, sig2 + pos + 80);
+                int nl = (llen * 8 + 22 + 23) / 24;
+                bool ok = d.m.len > 0 && d.m.len <= 4095 && d.m.nSS <= 2 && (nl * 80) >= (d.m.nSym * d.m.nSymSamp + 160 + 80 + d.m.nLTF * 80);
+                pos += need;
+                if (!ok) return ORX_E_FORMAT;
+                trellis = d.m.len * 8 + 22;
+                if (d.m.nSS == 1) { d.pilot[0] = 1.f; d.pilot[1] = 1.f; d.pilot[2] = 1.f; d.pilot[3] = -1.f; }     // PILOT_HT_1
+                else { d.pilot[0] = 1.f; d.pilot[1] = 1.f; d.pilot[2] = -1.f; d.pilot[3] = -1.f; }                 // PILOT_HT_2_1
+                d.pilot2[0] = 1.f; d.pilot2[1] = -1.f; d.pilot2[2] = -1.f; d.pilot2[3] = 1.f;                      // PILOT_HT_2_2
+                d.pilotP = 3;
+            } else legacy = true;
+        }
+    }
+    if (legacy) {                                                     // DEMOD_S_LEGACY :218-230
+        parseL(lmcs, llen, &d.m);
+        trellis = d.m.len * 8 + 22;
+        d.pilot[0] = 1.f; d.pilot[1] = 1.f; d.pilot[2] = 1.f; d.pilot[3] = -1.f;
+        d.pilotP = 1;
+    }
+    f->format = d.m.format; f->mcs = d.m.mcs; f->len = d.m.len; f->cr = d.m.cr; f->ampdu = d.m.ampdu;
+    f->nss = d.m.nSS; f->nsym = d.m.nSym; f->nsymsamp = d.m.nSymSamp; f->ncbps = d.m.nCBPS; f->ndbps = d.m.nDBPS;
+    f->trellis = trellis; f->total = d.m.nSym * d.m.nCBPS; f->data_off = pos;
+    f->sssnr0 = (d.m.format == F_VHT) ? d.sssnr0 : 0.f;
+    f->sssnr1 = (d.m.format == F_VHT && d.m.nSS == 2) ? d.sssnr1 : 0.f;
+    if (f->total > llrCap) return ORX_E_TRUNC;
+    float inted[2][416], spasd[2][416];
+    for (int sidx = 0; sidx < d.m.nSym; sidx++) {                     // DEMOD_S_DEMOD :279-330
+        int o1 = pos + sidx * d.m.nSymSamp;
+        if (o1 + d.m.nSymSamp > nsig) return ORX_E_TRUNC;
+        float* out = llrOut + (size_t)sidx * d.m.nCBPS;
+        if (d.m.format == F_L) {
+            d.legacyUpdate(sig1 + o1);
+            qamToLlr(d.qam[0], inted[0], d.m.mod, d.m.nSD);
+            const int* map = T.deintL[nbIndexL(d.m.nBPSCS)];
+            for (int i = 0; i < d.m.nCBPS; i++) out[map[i]] = inted[0][i];
+        } else {
+            d.symUpdate(sig1 + o1, sig2 + o1);
+            int bi = nbIndexNL(d.m.nBPSCS);
+            if (bi < 0) continue;
+            if (d.m.nSS == 1) {
+                qamToLlr(d.qam[0], inted[0], d.m.mod, d.m.nSD);
+                const int* map = T.deintNL[0][bi];
+                for (int i = 0; i < d.m.nCBPSS; i++) out[map[i]] = inted[0][i];
+            } else {
+                qamToLlr(d.qam[0], inted[0], d.m.mod, d.m.nSD);
+                qamToLlr(d.qam[1], inted[1], d.m.mod, d.m.nSD);
+                for (int i = 0; i < d.m.nCBPSS; i++) { spasd[0][T.deintNL[0][bi][i]] = inted[0][i]; spasd[1][T.deintNL[1][bi][i]] = inted[1][i]; }
+                int s = std::max(d.m.nBPSCS / 2, 1);                  // procSymDepasNL c8p.cc:2442-2451
+                for (int i = 0; i < d.m.nCBPSS / s; i++) {
+                    memcpy(&out[i * 2 * s], &spasd[0][i * s], sizeof(float) * s);
+                    memcpy(&out[(i * 2 + 1) * s], &spasd[1][i * s], sizeof(float) * s);
+                }
+            }
+        }
+    }
+    return ORX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // decode (ref: lib/decode_impl.cc:164-203 vstb_init, :205-281 vstb_update, :282-302 vstb_end,
 // :304-323 descramble, :325-520 packetAssemble)
 // ------------------------------------------------------------------------------------------------
@@ -860,7 +1110,7 @@ int decodeFrame(const float* llr, const orx_frame* f, uint8_t* pdu, int cap, int
 struct SyncEv { int trig, idx; float rad, snr, rssi; };
 
 int rxItem(const cf* x, int n, int item, int maxFrames, orx_frame* frames, float* llr, int64_t llrCap, int64_t* llrUsed,
-           uint8_t* pdu, int64_t pduCap, int64_t* pduUsed, std::vector<float>* llrScratch)
+           uint8_t* pdu, int64_t pduCap, int64_t* pduUsed, std::vector<float>* llrScratch, const cf* x2 = nullptr)
 {
     std::vector<float> preac(n);
     std::vector<cf> preconj(n);
@@ -891,7 +1141,7 @@ int rxItem(const cf* x, int n, int item, int maxFrames, orx_frame* frames, float
 
     int nf = 0, nLsigFail = 0;
     int pos = 0;
-    std::vector<cf> rot;
+    std::vector<cf> rot, rot2;
     for (size_t e = 0; e < evs.size() && nf < maxFrames; e++) {
         const SyncEv& ev = evs[e];
         if (ev.idx < pos) continue;                            // swallowed by S_COPY / skipped 80
@@ -920,7 +1170,16 @@ int rxItem(const cf* x, int n, int item, int maxFrames, orx_frame* frames, float
         float* lo = llr ? llr + *llrUsed : nullptr;
         int capI = (int)std::min<int64_t>(room, 1 << 30);
         if (!llr) { llrScratch->resize(1366 * 832 + 1024); lo = llrScratch->data(); capI = (int)llrScratch->size(); }
-        f->status = demodFrame(rot.data(), nsamp + 320, mcs, len, h, f, lo, capI);
+        if (x2) std::fill(lo, lo + std::min<int64_t>(capI, (int64_t)(nsamp / 72 + 2) * 832), 0.0f);
+        if (x2) {                                              // signal2: same rotation on antenna 1 (lib/signal2_impl.cc:177,190)
+            rot2.assign((size_t)nsamp + 320, cf(0.f, 0.f));
+            for (int k = 0; k < nsamp; k++) {
+                float ph = (float)(k + 224) * ev.rad;
+                rot2[k] = x2[start + k] * cf(cosf(ph), sinf(ph));
+            }
+            f->status = demodFrame2(rot.data(), rot2.data(), nsamp + 320, mcs, len, h, f, lo, capI);
+        } else
+            f->status = demodFrame(rot.data(), nsamp + 320, mcs, len, h, f, lo, capI);
         if (f->status != ORX_OK) continue;
         if (llr) *llrUsed += f->total;
         int used = 0;
@@ -1014,6 +1273,19 @@ int orx_rx_item(const float* iq, int n, int item, int maxFrames, orx_frame* fram
 {
     std::vector<float> scratch;
     return rxItem(reinterpret_cast<const cf*>(iq), n, item, maxFrames, frames, llr, llrCap, llrUsed, pdu, pduCap, pduUsed, &scratch);
+}
+
+int orx_rx_item2(const float* iq0, const float* iq1, int n, int item, int maxFrames, orx_frame* frames, float* llr, int64_t llrCap,
+                 int64_t* llrUsed, uint8_t* pdu, int64_t pduCap, int64_t* pduUsed)
+{
+    std::vector<float> scratch;
+    return rxItem(reinterpret_cast<const cf*>(iq0), n, item, maxFrames, frames, llr, llrCap, llrUsed, pdu, pduCap, pduUsed, &scratch,
+                  reinterpret_cast<const cf*>(iq1));
+}
+int orx_demod2(const float* sig1, const float* sig2, int nsig, int lmcs, int llen, const float* h, orx_frame* f, float* llrOut, int llrCap)
+{
+    return demodFrame2(reinterpret_cast<const cf*>(sig1), reinterpret_cast<const cf*>(sig2), nsig, lmcs, llen, reinterpret_cast<const cf*>(h), f,
+                       llrOut, llrCap);
 }
 
 int orx_rx_batch(const float* iq, const int64_t* offs, const int32_t* lens, int nitems, int nthreads, orx_frame* frames, uint8_t* pdu,

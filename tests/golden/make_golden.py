@@ -120,6 +120,30 @@ def frames_bench():
     print("frames_bench: 16 x", frames[0].size)
 
 
+def frames_mimo():
+    """2x2 SU-MIMO frames (tools/pktGenExample.py:206-217, tools/performance/perf_sumimo.py:139-148): HT MCS8-15 and
+    VHT 2SS MCS0-8, multiplier 12*sqrt(2), stream k -> antenna k (identity channel as tools/performance/gr_sumimo.py:70-78)."""
+    phy = phy80211.phy80211(ifDebug=False)
+    payload = "123456789012345678901234567890"
+    mpdu = mac_mpdu(payload)
+    ampdu = mac_ampdu([payload])
+    a0, a1, meta, exp = [], [], [], []
+    for fmt, code, rng, pkt in ((p8h.F.HT, 1, range(8, 16), mpdu), (p8h.F.VHT, 2, range(0, 9), ampdu)):
+        for mcs in rng:
+            ss = gen(phy, fmt, mcs, pkt, 400, mult=12.0 * np.sqrt(2), nsts=2)
+            assert len(ss) == 2 and ss[0].size == ss[1].size
+            a0.append(ss[0]); a1.append(ss[1]); meta.append((code, mcs, 0.0))
+            exp.append(ampdu_split(pkt)[0] if code == 2 else bytes(mpdu))
+    # one frame with CFO
+    ss = gen(phy, p8h.F.HT, 11, mpdu, 400, cfo=75e3, mult=12.0 * np.sqrt(2), nsts=2)
+    a0.append(ss[0]); a1.append(ss[1]); meta.append((1, 11, 75e3)); exp.append(bytes(mpdu))
+    offs = np.cumsum([0] + [len(x) for x in a0]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "frames_mimo.npz"), iq0=np.concatenate(a0).astype(np.complex64),
+                        iq1=np.concatenate(a1).astype(np.complex64), offs=offs, meta=np.array(meta, np.float64),
+                        exp_len=np.array([len(e) for e in exp], np.int32), exp_mpdu=np.frombuffer(b"".join(exp), np.uint8))
+    print("frames_mimo: %d items, %d samples per antenna" % (len(a0), offs[-1]))
+
+
 def ref_vectors():
     import oracle_lib as ol
     R = ol.ref()
@@ -180,10 +204,12 @@ def ref_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["siso", "bench", "ref"]
+    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo"]
     if "siso" in which:
         frames_siso()
     if "bench" in which:
         frames_bench()
     if "ref" in which:
         ref_vectors()
+    if "mimo" in which:
+        frames_mimo()

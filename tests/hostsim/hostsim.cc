@@ -41,4 +41,12 @@ void hs_header(const float* iq_item, c8b_frame* f, const float* chan, int mupos,
     f->status = demod_header(lut(), rot, f->nsamp, f->l_mcs, f->l_len, (const cf*)chan, mupos, f, (cf*)hinv);
 }
 
+void hs_header2(const float* iq0_item, const float* iq1_item, c8b_frame* f, const float* chan, float* hinv, float* w2)
+{
+    if (f->status != C8B_ST_OK) return;
+    RotSrc r0; r0.x = (const cf*)iq0_item + f->sync_idx + 224; r0.rad = f->rad; r0.nsamp = f->nsamp;
+    RotSrc r1 = r0; r1.x = (const cf*)iq1_item + f->sync_idx + 224;
+    f->status = demod_header2(lut(), r0, r1, f->nsamp, f->l_mcs, f->l_len, (const cf*)chan, f, (cf*)hinv, (cf*)w2);
+}
+
 }

@@ -27,5 +27,6 @@ def lib():
         L.hs_crc8.argtypes = [u8p, C.c_int, u8p]
         L.hs_detect.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_void_p, f32p]
         L.hs_header.argtypes = [f32p, C.c_void_p, f32p, C.c_int, f32p]
+        L.hs_header2.argtypes = [f32p, f32p, C.c_void_p, f32p, f32p, f32p]
         _lib = L
     return _lib

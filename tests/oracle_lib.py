@@ -82,6 +82,9 @@ def oracle():
         L.orx_crc32.restype = C.c_uint32
         L.orx_rx_item.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                   u8p, C.c_int64, C.POINTER(C.c_int64)]
+        L.orx_rx_item2.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                   u8p, C.c_int64, C.POINTER(C.c_int64)]
+        L.orx_demod2.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, f32p, C.POINTER(OrxFrame), f32p, C.c_int]
         L.orx_rx_batch.argtypes = [f32p, i64p, i32p, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int64]
         _oracle = L
     return _oracle
@@ -145,6 +148,21 @@ def rx_item(iq, item=0, max_frames=4, want_llr=True):
     lu, pu = C.c_int64(0), C.c_int64(0)
     nf = L.orx_rx_item(iqf, n, item, max_frames, frames.ctypes.data, llr.ctypes.data if want_llr else None, llr_cap, C.byref(lu),
                        pdu, pdu.size, C.byref(pu))
+    return frames[:nf], llr[: lu.value], pdu[: pu.value]
+
+
+def rx_item2(iq0, iq1, item=0, max_frames=4, want_llr=True):
+    """2x2 oracle chain (signal2 + demod2) on one item: antenna 0 drives detection."""
+    L = oracle()
+    a, b = c2f(iq0), c2f(iq1)
+    n = a.size // 2
+    frames = np.zeros(max_frames, dtype=FRAME_DTYPE)
+    llr_cap = max(1, (n // 80 + 2) * 832) if want_llr else 0
+    llr = np.zeros(max(llr_cap, 1), np.float32)
+    pdu = np.zeros(max(4096, n), np.uint8)
+    lu, pu = C.c_int64(0), C.c_int64(0)
+    nf = L.orx_rx_item2(a, b, n, item, max_frames, frames.ctypes.data, llr.ctypes.data if want_llr else None, llr_cap, C.byref(lu),
+                        pdu, pdu.size, C.byref(pu))
     return frames[:nf], llr[: lu.value], pdu[: pu.value]
 
 

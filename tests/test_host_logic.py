@@ -126,3 +126,36 @@ def test_trigger_sigviterbi_fft_vs_oracle():
         bits = rng.integers(0, 2, 34).astype(np.uint8)
         crc = rng.integers(0, 2, 8).astype(np.uint8)
         assert H.hs_crc8(bits, 34, crc) == O.orx_crc8_check(bits, 34, crc)
+
+
+@pytest.mark.parametrize("snr", [None, 30.0])
+def test_header2_matches_oracle(golden, snr):
+    """2-antenna header states (demod_header2) vs the oracle's demod2 on the reference generator's 2x2 frames"""
+    pkg = load_pkg()
+    H = hs.lib()
+    g = golden["frames_mimo"]
+    offs = g["offs"]
+    r0, r1 = np.random.default_rng(13579), np.random.default_rng(24680)
+    for i in range(len(offs) - 1):
+        a, b = g["iq0"][offs[i]:offs[i + 1]], g["iq1"][offs[i]:offs[i + 1]]
+        if snr is not None:
+            s = 0.1875 / np.sqrt(2 * 10 ** (snr / 10))
+            a = (a + s * (r0.standard_normal(a.size) + 1j * r0.standard_normal(a.size))).astype(np.complex64)
+            b = (b + s * (r1.standard_normal(b.size) + 1j * r1.standard_normal(b.size))).astype(np.complex64)
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        fo, llr, pdu = ol.rx_item2(a, b, max_frames=1)
+        f, chan, _, _ = _detect(a)
+        for k in DET[1:]:
+            assert f[0][k] == fo[0][k], (i, k, f[0][k], fo[0][k])
+        hinv, w2 = np.zeros(128, np.float32), np.zeros(2 * 264, np.float32)
+        H.hs_header2(ol.c2f(a), ol.c2f(b), f.ctypes.data, chan, hinv, w2)
+        for k in HDR:
+            assert f[0][k] == fo[0][k], (i, k, f[0][k], fo[0][k])
+        assert f[0]["nss"] == 2
+        if fo[0]["format"] == 2:
+            for k in ("sssnr0", "sssnr1"):
+                assert abs(float(f[0][k]) - float(fo[0][k])) <= (0.5 if fo[0][k] > 60 else 0.01), (i, k, f[0][k], fo[0][k])
+        # identity channel: the folded zero-forcing matrix is ~ diag(1/h) per antenna
+        w = w2.view(np.complex64)[:256].reshape(64, 4)
+        used = [k for k in range(64) if not (k == 0 or 29 <= k <= 35)]
+        assert np.all(np.abs(w[used, 1]) < 0.2 * np.abs(w[used, 0])) and np.all(np.abs(w[used, 2]) < 0.2 * np.abs(w[used, 3]))

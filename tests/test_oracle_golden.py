@@ -99,3 +99,43 @@ def test_batch_matches_item_loop(golden):
         fr, llr, p1 = ol.rx_item(x, max_frames=1)
         assert frames[i]["pdu_bytes"] == p1.size
         assert bytes(pdu[i * stride: i * stride + p1.size]) == bytes(p1)
+
+
+# ---------------------------------------------------------------- 2x2 (signal2 + demod2) ----------
+def _mimo_items(g):
+    offs, el = g["offs"], g["exp_len"]
+    eo = np.cumsum(np.r_[0, el])
+    for i in range(len(offs) - 1):
+        yield i, g["iq0"][offs[i]:offs[i + 1]], g["iq1"][offs[i]:offs[i + 1]], bytes(g["exp_mpdu"][eo[i]:eo[i + 1]]), g["meta"][i]
+
+
+@pytest.mark.parametrize("snr", [None, 30.0])
+def test_mimo_2x2_all_mcs(golden, snr):
+    """HT MCS8-15 and VHT 2SS MCS0-8 from the reference generator (tools/pktGenExample.py:206-217), identity channel
+    as tools/performance/gr_sumimo.py:70-78, independent noise per antenna (seeds 13579 / 24680)"""
+    r0, r1 = np.random.default_rng(13579), np.random.default_rng(24680)
+    for i, a, b, mpdu, meta in _mimo_items(golden["frames_mimo"]):
+        if snr is not None:
+            s = 0.1875 / np.sqrt(2 * 10 ** (snr / 10))
+            a = (a + s * (r0.standard_normal(a.size) + 1j * r0.standard_normal(a.size))).astype(np.complex64)
+            b = (b + s * (r1.standard_normal(b.size) + 1j * r1.standard_normal(b.size))).astype(np.complex64)
+        fr, llr, pdu = ol.rx_item2(a, b)
+        f = fr[0]
+        assert f["status"] == 0, (i, meta, f["status"])
+        assert (f["format"], f["mcs"], f["nss"]) == (int(meta[0]), int(meta[1]), 2), (i, f["format"], f["mcs"], f["nss"])
+        recs = ol.split_pdus(pdu)
+        assert len(recs) >= 1 and recs[0][3:-1] == mpdu and recs[0][-1] == int(meta[1]), (i, meta)
+        assert abs(f["rad"] + 2 * np.pi * meta[2] / 20e6) < 2e-4
+
+
+def test_mimo_tables_vs_reference(golden):
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref not built")
+    R = ol.ref()
+    f = np.zeros(128, np.float32)
+    assert R.ref_table_f(b"LTF_NL_28_F_FLOAT2", f) == 64
+    l = np.zeros(64, np.float32)
+    ol.oracle().orx_ltf(1, l)
+    assert np.array_equal(f[:64], l * 0.5)
+    for name, want in ((b"PILOT_HT_2_1", [1, 1, -1, -1]), (b"PILOT_HT_2_2", [1, -1, -1, 1]), (b"PILOT_VHT", [1, 1, 1, -1]), (b"PILOT_HT_1", [1, 1, 1, -1])):
+        assert R.ref_table_f(name, f) == 4 and list(f[:4]) == want
