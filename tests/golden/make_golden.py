@@ -144,6 +144,27 @@ def frames_mimo():
     print("frames_mimo: %d items, %d samples per antenna" % (len(a0), offs[-1]))
 
 
+def frames_564():
+    """BASELINE configs 2-4 units: 564-byte MPDUs (500 random UDP bytes, tools/performance/perf_siso.py:126,132) at every MCS:
+    legacy 0-7, VHT 1SS 0-8 (A-MPDU of one MPDU), HT 2x2 8-15 (two antennas).  No gaps: bench/tests add them."""
+    phy = phy80211.phy80211(ifDebug=False)
+    rng = np.random.default_rng(80211)
+    payload = bytes(rng.integers(1, 128, 500, dtype=np.uint8)).decode("latin-1")
+    mpdu = mac_mpdu(payload)
+    ampdu = mac_ampdu([payload])
+    assert len(mpdu) == 564, len(mpdu)
+    out = {"mpdu": np.frombuffer(bytes(mpdu), np.uint8), "vht_mpdu": np.frombuffer(ampdu_split(ampdu)[0], np.uint8)}
+    for mcs in range(8):
+        out["l%d" % mcs] = gen(phy, p8h.F.L, mcs, mpdu, 0)[0]
+    for mcs in range(9):
+        out["v%d" % mcs] = gen(phy, p8h.F.VHT, mcs, ampdu, 0)[0]
+    for mcs in range(8, 16):
+        ss = gen(phy, p8h.F.HT, mcs, mpdu, 0, mult=12.0 * np.sqrt(2), nsts=2)
+        out["h%d_0" % mcs], out["h%d_1" % mcs] = ss[0], ss[1]
+    np.savez_compressed(os.path.join(HERE, "frames_564.npz"), **out)
+    print("frames_564:", {k: v.size for k, v in out.items()})
+
+
 def ref_vectors():
     import oracle_lib as ol
     R = ol.ref()
@@ -204,7 +225,7 @@ def ref_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo"]
+    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564"]
     if "siso" in which:
         frames_siso()
     if "bench" in which:
@@ -213,3 +234,5 @@ if __name__ == "__main__":
         ref_vectors()
     if "mimo" in which:
         frames_mimo()
+    if "564" in which:
+        frames_564()
