@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libc80211b200.so")
 
 K_NAMES = ("presiso", "detect", "header", "demod", "viterbi")
 
-ST_OK, ST_NO_TRIGGER, ST_SYNC, ST_LSIG, ST_TRUNC, ST_FORMAT, ST_DECODE_RANGE, ST_NDP, ST_OVERFLOW = range(9)
+ST_OK, ST_NO_TRIGGER, ST_SYNC, ST_LSIG, ST_TRUNC, ST_FORMAT, ST_DECODE_RANGE, ST_NDP, ST_OVERFLOW, ST_EMPTY = range(10)
 
 
 class C8bFrame(C.Structure):
@@ -34,7 +34,7 @@ assert FRAME_DTYPE.itemsize == C.sizeof(C8bFrame)
 
 
 class C8bCfg(C.Structure):
-    _fields_ = [("device", C.c_int32), ("chunk_items", C.c_int32), ("max_item_len", C.c_int32), ("ev_cap", C.c_int32),
+    _fields_ = [("device", C.c_int32), ("chunk_items", C.c_int32), ("max_item_len", C.c_int32), ("max_frames", C.c_int32),
                 ("mupos", C.c_int32), ("mugid", C.c_int32), ("reserved", C.c_int32 * 8)]
 
 

@@ -25,12 +25,12 @@ void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d
                         float* preac, float2* preconj, cudaStream_t st);
 void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st);
 void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
-                       int64_t outBase, const float* preac, c8b_frame* frames, float2* chan, cudaStream_t st);
-void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int mupos, c8b_frame* frames,
+                       int maxf, int64_t outBase, const float* preac, c8b_frame* frames, float2* chan, cudaStream_t st);
+void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
                        const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
-void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxSym, const c8b_frame* frames,
+void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int maxSym, const c8b_frame* frames,
                       const float2* hinv, float* llr, cudaStream_t st);
-void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, c8b_frame* frames,
-                        const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st);
-void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxSym,
+void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf,
+                        c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st);
+void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf, int maxSym,
                        const c8b_frame* frames, const float2* w2, float* llr, cudaStream_t st);

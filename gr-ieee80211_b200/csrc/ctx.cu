@@ -120,7 +120,7 @@ int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
     memset(&ctx->cfg, 0, sizeof(ctx->cfg));
     if (cfg) ctx->cfg = *cfg;
     if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = 16384;
-    if (ctx->cfg.ev_cap <= 0) ctx->cfg.ev_cap = 8;
+    if (ctx->cfg.max_frames <= 0) ctx->cfg.max_frames = 1;
     ctx->device = ctx->cfg.device;
     if (ctx->device < 0 || ctx->device >= n) { g_createErr = "bad device ordinal"; delete ctx; return C8B_ERR_ARG; }
     cudaError_t e = cudaSetDevice(ctx->device);
@@ -321,15 +321,16 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
                      const int32_t* h_len, int b, int e, c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride, int64_t iqShift,
                      const float2* d_iq1 = nullptr)
 {
-    const int n = e - b;
+    const int n = e - b, maxf = ctx->cfg.max_frames;
+    const size_t ns = (size_t)n * maxf;                          // frame slots of this chunk
     const ChunkPlan pl = plan(h_off + b, h_len + b, n);
     const int64_t span = pl.end - pl.base;
     const int64_t llrStride = llr_stride_for(pl.maxLen) * (d_iq1 ? 2 : 1);
-    if (d_iq1) EN(w2, (size_t)n * 264 * sizeof(float2));
+    if (d_iq1) EN(w2, ns * 264 * sizeof(float2));
     EN(preac, (size_t)(span + 64) * sizeof(float));
-    EN(chan, (size_t)n * 64 * sizeof(float2));
-    EN(hinv, (size_t)n * 64 * sizeof(float2));
-    EN(llr, (size_t)n * llrStride * sizeof(float));
+    EN(chan, ns * 64 * sizeof(float2));
+    EN(hinv, ns * 64 * sizeof(float2));
+    EN(llr, ns * llrStride * sizeof(float));
     int r = ensure_surv(ctx);
     if (r) return r;
     // iqShift: the device buffer holds the capture from sample iqShift on (host-staged chunks)
@@ -341,29 +342,31 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     }
     {
         StageTimer tm(ctx, C8B_K_DETECT);
-        c8b_launch_detect(ctx->d_lut, iq, d_off + b, d_len + b, n, b, pl.base, (const float*)ctx->preac.p, d_frames + b,
+        c8b_launch_detect(ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, d_frames + (size_t)b * maxf,
                           (float2*)ctx->chan.p, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_HEADER);
         if (iq1)
-            c8b_launch_header2(ctx->d_lut, iq, iq1, d_off + b, n, d_frames + b, (const float2*)ctx->chan.p, (float2*)ctx->hinv.p,
-                               (float2*)ctx->w2.p, llrStride, ctx->st);
+            c8b_launch_header2(ctx->d_lut, iq, iq1, d_off + b, n, maxf, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
+                               (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llrStride, ctx->st);
         else
-            c8b_launch_header(ctx->d_lut, iq, d_off + b, n, ctx->cfg.mupos, d_frames + b, (const float2*)ctx->chan.p, (float2*)ctx->hinv.p,
-                              llrStride, ctx->st);
+            c8b_launch_header(ctx->d_lut, iq, d_off + b, n, maxf, ctx->cfg.mupos, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
+                              (float2*)ctx->hinv.p, llrStride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
         const int maxSym = (int)(llr_stride_for(pl.maxLen) / 416);
-        c8b_launch_demod(ctx->d_lut, iq, d_off + b, n, maxSym, d_frames + b, (const float2*)ctx->hinv.p, (float*)ctx->llr.p, ctx->st);
+        c8b_launch_demod(ctx->d_lut, iq, d_off + b, n, maxf, maxSym, d_frames + (size_t)b * maxf, (const float2*)ctx->hinv.p, (float*)ctx->llr.p,
+                         ctx->st);
         if (iq1)
-            c8b_launch_demod2(ctx->d_lut, iq, iq1, d_off + b, n, maxSym, d_frames + b, (const float2*)ctx->w2.p, (float*)ctx->llr.p, ctx->st);
+            c8b_launch_demod2(ctx->d_lut, iq, iq1, d_off + b, n, maxf, maxSym, d_frames + (size_t)b * maxf, (const float2*)ctx->w2.p,
+                              (float*)ctx->llr.p, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_VITERBI);
-        c8b_launch_viterbi(ctx->d_lut, d_frames + b, n, (const float*)ctx->llr.p, (int64_t)n * llrStride, (uint2*)ctx->surv.p,
-                           ctx->survWarps, d_pdu + (size_t)b * pdu_stride, pdu_stride, nullptr, 0, ctx->d_counter,
+        c8b_launch_viterbi(ctx->d_lut, d_frames + (size_t)b * maxf, (int)ns, (const float*)ctx->llr.p, (int64_t)ns * llrStride,
+                           (uint2*)ctx->surv.p, ctx->survWarps, d_pdu + (size_t)b * maxf * pdu_stride, pdu_stride, nullptr, 0, ctx->d_counter,
                            c8b_viterbi_max_grid(ctx->numSM), ctx->st);
     }
     CK(cudaGetLastError());
@@ -391,7 +394,7 @@ int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* off, 
     CK(cudaSetDevice(ctx->device));
     if ((r = check_items(ctx, off, len, nitems))) return r;
     if ((r = upload_items(ctx, off, len, nitems))) return r;
-    CK(cudaMemsetAsync(d_frames, 0, (size_t)nitems * sizeof(c8b_frame), ctx->st));
+    CK(cudaMemsetAsync(d_frames, 0, (size_t)nitems * ctx->cfg.max_frames * sizeof(c8b_frame), ctx->st));
     const int cs = ctx->cfg.chunk_items;
     for (int b = 0; b < nitems; b += cs) {
         const int e = b + cs < nitems ? b + cs : nitems;
@@ -408,12 +411,13 @@ int c8b_rx_batch_dev(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const 
     if (!ctx || !frames || !pdu || nitems < 0 || pdu_stride <= 0) return C8B_ERR_ARG;
     if (nitems == 0) return C8B_OK;
     CK(cudaSetDevice(ctx->device));
-    EN(frames, (size_t)nitems * sizeof(c8b_frame));
-    EN(pdu, (size_t)nitems * pdu_stride);
+    const size_t nsl = (size_t)nitems * (ctx->cfg.max_frames > 0 ? ctx->cfg.max_frames : 1);
+    EN(frames, nsl * sizeof(c8b_frame));
+    EN(pdu, nsl * pdu_stride);
     int r = c8b_rx_batch_dev_async(ctx, d_iq, off, len, nitems, (c8b_frame*)ctx->frames.p, (uint8_t*)ctx->pdu.p, pdu_stride);
     if (r) return r;
-    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(pdu, ctx->pdu.p, (size_t)nitems * pdu_stride, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, nsl * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(pdu, ctx->pdu.p, nsl * pdu_stride, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
 }
@@ -430,9 +434,10 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
     CK(cudaSetDevice(ctx->device));
     if ((r = check_items(ctx, off, len, nitems))) return r;
     if ((r = upload_items(ctx, off, len, nitems))) return r;
-    EN(frames, (size_t)nitems * sizeof(c8b_frame));
-    EN(pdu, (size_t)nitems * pdu_stride);
-    CK(cudaMemsetAsync(ctx->frames.p, 0, (size_t)nitems * sizeof(c8b_frame), ctx->st));
+    const size_t maxf = (size_t)ctx->cfg.max_frames;
+    EN(frames, (size_t)nitems * maxf * sizeof(c8b_frame));
+    EN(pdu, (size_t)nitems * maxf * pdu_stride);
+    CK(cudaMemsetAsync(ctx->frames.p, 0, (size_t)nitems * maxf * sizeof(c8b_frame), ctx->st));
     const int cs = ctx->cfg.chunk_items;
     const int nchunks = (nitems + cs - 1) / cs;
     // size the two staging buffers for the largest chunk span
@@ -471,8 +476,9 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
                        (uint8_t*)ctx->pdu.p, pdu_stride, pl.base, buf1[k]);
         cudaEventRecord(freed[k], ctx->st);
         if (rc == C8B_OK) {
-            cudaMemcpyAsync(frames + b, (c8b_frame*)ctx->frames.p + b, (size_t)(e - b) * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st);
-            cudaMemcpyAsync(pdu + (size_t)b * pdu_stride, (uint8_t*)ctx->pdu.p + (size_t)b * pdu_stride, (size_t)(e - b) * pdu_stride,
+            cudaMemcpyAsync(frames + b * maxf, (c8b_frame*)ctx->frames.p + b * maxf, (size_t)(e - b) * maxf * sizeof(c8b_frame),
+                            cudaMemcpyDeviceToHost, ctx->st);
+            cudaMemcpyAsync(pdu + b * maxf * pdu_stride, (uint8_t*)ctx->pdu.p + b * maxf * pdu_stride, (size_t)(e - b) * maxf * pdu_stride,
                             cudaMemcpyDeviceToHost, ctx->st);
         }
     }
@@ -558,10 +564,13 @@ int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_
     CK(cudaSetDevice(ctx->device));
     ChunkPlan pl;
     if ((r = stage_items(ctx, h_iq, off, len, nitems, &pl))) return r;
+    const int maxf = ctx->cfg.max_frames;
+    const size_t ns = (size_t)nitems * maxf;
     EN(preac, (size_t)(pl.end - pl.base + 64) * sizeof(float));
-    EN(frames, (size_t)nitems * sizeof(c8b_frame));
-    EN(chan, (size_t)nitems * 64 * sizeof(float2));
-    CK(cudaMemsetAsync(ctx->frames.p, 0, (size_t)nitems * sizeof(c8b_frame), ctx->st));
+    EN(frames, ns * sizeof(c8b_frame));
+    EN(chan, ns * 64 * sizeof(float2));
+    CK(cudaMemsetAsync(ctx->frames.p, 0, ns * sizeof(c8b_frame), ctx->st));
+    CK(cudaMemsetAsync(ctx->chan.p, 0, ns * 64 * sizeof(float2), ctx->st));
     const float2* iq = (const float2*)ctx->iq.p - pl.base;
     {
         StageTimer tm(ctx, C8B_K_PRESISO);
@@ -570,12 +579,12 @@ int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_
     }
     {
         StageTimer tm(ctx, C8B_K_DETECT);
-        c8b_launch_detect(ctx->d_lut, iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, 0, pl.base, (const float*)ctx->preac.p,
-                          (c8b_frame*)ctx->frames.p, (float2*)ctx->chan.p, ctx->st);
+        c8b_launch_detect(ctx->d_lut, iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, 0, maxf, pl.base,
+                          (const float*)ctx->preac.p, (c8b_frame*)ctx->frames.p, (float2*)ctx->chan.p, ctx->st);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
-    if (h_chan) CK(cudaMemcpyAsync(h_chan, ctx->chan.p, (size_t)nitems * 64 * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, ns * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    if (h_chan) CK(cudaMemcpyAsync(h_chan, ctx->chan.p, ns * 64 * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
 }
@@ -590,27 +599,29 @@ int c8b_demod(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t
     CK(cudaSetDevice(ctx->device));
     ChunkPlan pl;
     if ((r = stage_items(ctx, h_iq, off, len, nitems, &pl))) return r;
-    EN(frames, (size_t)nitems * sizeof(c8b_frame));
-    EN(chan, (size_t)nitems * 64 * sizeof(float2));
-    EN(hinv, (size_t)nitems * 64 * sizeof(float2));
-    EN(llr, (size_t)nitems * llr_stride * sizeof(float));
-    CK(cudaMemcpyAsync(ctx->frames.p, frames, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->chan.p, h_chan, (size_t)nitems * 64 * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemsetAsync(ctx->llr.p, 0, (size_t)nitems * llr_stride * sizeof(float), ctx->st));
+    const int maxf = ctx->cfg.max_frames;
+    const size_t ns = (size_t)nitems * maxf;
+    EN(frames, ns * sizeof(c8b_frame));
+    EN(chan, ns * 64 * sizeof(float2));
+    EN(hinv, ns * 64 * sizeof(float2));
+    EN(llr, ns * llr_stride * sizeof(float));
+    CK(cudaMemcpyAsync(ctx->frames.p, frames, ns * sizeof(c8b_frame), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->chan.p, h_chan, ns * 64 * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->llr.p, 0, ns * llr_stride * sizeof(float), ctx->st));
     const float2* iq = (const float2*)ctx->iq.p - pl.base;
     {
         StageTimer tm(ctx, C8B_K_HEADER);
-        c8b_launch_header(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, ctx->cfg.mupos, (c8b_frame*)ctx->frames.p,
+        c8b_launch_header(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxf, ctx->cfg.mupos, (c8b_frame*)ctx->frames.p,
                           (const float2*)ctx->chan.p, (float2*)ctx->hinv.p, llr_stride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
-        c8b_launch_demod(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, (int)(llr_stride / 48 + 1), (const c8b_frame*)ctx->frames.p,
+        c8b_launch_demod(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxf, (int)(llr_stride / 48 + 1), (const c8b_frame*)ctx->frames.p,
                          (const float2*)ctx->hinv.p, (float*)ctx->llr.p, ctx->st);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(h_llr, ctx->llr.p, (size_t)nitems * llr_stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, ns * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_llr, ctx->llr.p, ns * llr_stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
 }
@@ -628,32 +639,34 @@ int c8b_demod2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64
     EN(iq1, (size_t)(pl.end - pl.base + 16) * sizeof(float2));
     CK(cudaMemcpyAsync(ctx->iq1.p, reinterpret_cast<const float2*>(h_iq1) + pl.base, (size_t)(pl.end - pl.base) * sizeof(float2),
                        cudaMemcpyHostToDevice, ctx->st));
-    EN(frames, (size_t)nitems * sizeof(c8b_frame));
-    EN(chan, (size_t)nitems * 64 * sizeof(float2));
-    EN(hinv, (size_t)nitems * 64 * sizeof(float2));
-    EN(w2, (size_t)nitems * 264 * sizeof(float2));
-    EN(llr, (size_t)nitems * llr_stride * sizeof(float));
-    CK(cudaMemcpyAsync(ctx->frames.p, frames, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->chan.p, h_chan, (size_t)nitems * 64 * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemsetAsync(ctx->llr.p, 0, (size_t)nitems * llr_stride * sizeof(float), ctx->st));
+    const int maxf = ctx->cfg.max_frames;
+    const size_t ns = (size_t)nitems * maxf;
+    EN(frames, ns * sizeof(c8b_frame));
+    EN(chan, ns * 64 * sizeof(float2));
+    EN(hinv, ns * 64 * sizeof(float2));
+    EN(w2, ns * 264 * sizeof(float2));
+    EN(llr, ns * llr_stride * sizeof(float));
+    CK(cudaMemcpyAsync(ctx->frames.p, frames, ns * sizeof(c8b_frame), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->chan.p, h_chan, ns * 64 * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->llr.p, 0, ns * llr_stride * sizeof(float), ctx->st));
     const float2* iq = (const float2*)ctx->iq.p - pl.base;
     const float2* iq1 = (const float2*)ctx->iq1.p - pl.base;
     {
         StageTimer tm(ctx, C8B_K_HEADER);
-        c8b_launch_header2(ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, (c8b_frame*)ctx->frames.p, (const float2*)ctx->chan.p,
+        c8b_launch_header2(ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, maxf, (c8b_frame*)ctx->frames.p, (const float2*)ctx->chan.p,
                            (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llr_stride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
         const int maxSym = (int)(llr_stride / 48 + 1);
-        c8b_launch_demod(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxSym, (const c8b_frame*)ctx->frames.p, (const float2*)ctx->hinv.p,
-                         (float*)ctx->llr.p, ctx->st);
-        c8b_launch_demod2(ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, maxSym, (const c8b_frame*)ctx->frames.p,
+        c8b_launch_demod(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxf, maxSym, (const c8b_frame*)ctx->frames.p,
+                         (const float2*)ctx->hinv.p, (float*)ctx->llr.p, ctx->st);
+        c8b_launch_demod2(ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, maxf, maxSym, (const c8b_frame*)ctx->frames.p,
                           (const float2*)ctx->w2.p, (float*)ctx->llr.p, ctx->st);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(frames, ctx->frames.p, (size_t)nitems * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(h_llr, ctx->llr.p, (size_t)nitems * llr_stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, ns * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_llr, ctx->llr.p, ns * llr_stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
 }

@@ -48,7 +48,7 @@ struct __align__(16) WarpBuf {
 };
 
 __global__ void __launch_bounds__(DW * 32)
-k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
+k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int maxf,
         const c8b_frame* __restrict__ frames, const float2* __restrict__ hinvAll, float* __restrict__ llrArena)
 {
     __shared__ WarpBuf wb[DW];
@@ -77,7 +77,7 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
     const int nsymsamp = fr->nsymsamp;
     const float rad = fr->rad;
     const int k0 = fr->data_off + sidx * nsymsamp + C8B_SYM_SHIFT;       // index in the signal block's output stream
-    const float2* __restrict__ x = iq + off[item] + fr->sync_idx + 224 + k0;
+    const float2* __restrict__ x = iq + off[item / maxf] + fr->sync_idx + 224 + k0;      // blockIdx.y = frame slot
 
     cpx v[8];
     if (live) {
@@ -205,7 +205,7 @@ struct __align__(16) WarpBuf2 {
 
 __global__ void __launch_bounds__(DW * 32)
 k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const float2* __restrict__ iq1,
-         const int64_t* __restrict__ off, const c8b_frame* __restrict__ frames, const float2* __restrict__ w2All,
+         const int64_t* __restrict__ off, int maxf, const c8b_frame* __restrict__ frames, const float2* __restrict__ w2All,
          float* __restrict__ llrArena)
 {
     __shared__ WarpBuf2 wb[DW];
@@ -230,7 +230,7 @@ k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const 
     const int nsymsamp = fr->nsymsamp;
     const float rad = fr->rad;
     const int k0 = fr->data_off + sidx * nsymsamp + C8B_SYM_SHIFT;
-    const float2* __restrict__ x = (a ? iq1 : iq0) + off[item] + fr->sync_idx + 224 + k0;
+    const float2* __restrict__ x = (a ? iq1 : iq0) + off[item / maxf] + fr->sync_idx + 224 + k0;
 
     cpx v[8];
     if (live) {
@@ -357,24 +357,26 @@ k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const 
 
 }  // namespace
 
-void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxSym,
+void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf, int maxSym,
                        const c8b_frame* frames, const float2* w2, float* llr, cudaStream_t st)
 {
     if (nitems <= 0 || maxSym <= 0) return;
-    for (int base = 0; base < nitems; base += 65535) {
-        const int cnt = nitems - base < 65535 ? nitems - base : 65535;
-        dim3 grid((maxSym + SPB2 - 1) / SPB2, cnt);
-        k_demod2<<<grid, DW * 32, 0, st>>>(lut, iq0, iq1, d_off + base, frames + base, w2 + (size_t)base * 264, llr);
+    const int per = (65535 / maxf) > 0 ? (65535 / maxf) : 1;   // items per launch (grid.y <= 65535 slots)
+    for (int base = 0; base < nitems; base += per) {
+        const int cnt = nitems - base < per ? nitems - base : per;
+        dim3 grid((maxSym + SPB2 - 1) / SPB2, cnt * maxf);
+        k_demod2<<<grid, DW * 32, 0, st>>>(lut, iq0, iq1, d_off + base, maxf, frames + (size_t)base * maxf, w2 + (size_t)base * maxf * 264, llr);
     }
 }
 
-void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxSym, const c8b_frame* frames,
+void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int maxSym, const c8b_frame* frames,
                       const float2* hinv, float* llr, cudaStream_t st)
 {
     if (nitems <= 0 || maxSym <= 0) return;
-    for (int base = 0; base < nitems; base += 65535) {
-        const int cnt = nitems - base < 65535 ? nitems - base : 65535;
-        dim3 grid((maxSym + SPB - 1) / SPB, cnt);
-        k_demod<<<grid, DW * 32, 0, st>>>(lut, iq, d_off + base, frames + base, hinv + (size_t)base * 64, llr);
+    const int per = (65535 / maxf) > 0 ? (65535 / maxf) : 1;
+    for (int base = 0; base < nitems; base += per) {
+        const int cnt = nitems - base < per ? nitems - base : per;
+        dim3 grid((maxSym + SPB - 1) / SPB, cnt * maxf);
+        k_demod<<<grid, DW * 32, 0, st>>>(lut, iq, d_off + base, maxf, frames + (size_t)base * maxf, hinv + (size_t)base * maxf * 64, llr);
     }
 }

@@ -92,19 +92,14 @@ __global__ void k_trigger(const float* __restrict__ preac, int64_t n, uint8_t* _
 
 __global__ void __launch_bounds__(64)
 k_detect(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
-         const int32_t* __restrict__ len, int nitems, int itemBase, int64_t outBase, const float* __restrict__ preac,
+         const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preac,
          c8b_frame* __restrict__ frames, float2* __restrict__ chan)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nitems) return;
-    c8b_frame f = frames[i];
-    cf h[64];
-    for (int k = 0; k < 64; k++) h[k] = c8b::mk(0.f, 0.f);
-    c8b::detect_item(lut, reinterpret_cast<const cf*>(iq + off[i]), preac + (off[i] - outBase), len[i], itemBase + i, &f, h);
-    f.format = f.mcs = f.len = f.cr = f.ampdu = f.nss = f.nsym = f.nsymsamp = f.ncbps = f.ndbps = 0;
-    f.trellis = f.total = f.data_off = 0; f.sssnr0 = f.sssnr1 = 0.f; f.npdu = f.pdu_bytes = 0;
-    frames[i] = f;
-    for (int k = 0; k < 64; k++) chan[(size_t)i * 64 + k] = make_float2(h[k].re, h[k].im);
+    // records and channels are written in place (device global memory): frames[i*maxf ..], chan[i*maxf*64 ..]
+    c8b::detect_item(lut, reinterpret_cast<const cf*>(iq + off[i]), preac + (off[i] - outBase), len[i], itemBase + i, maxf,
+                     frames + (size_t)i * maxf, reinterpret_cast<cf*>(chan + (size_t)i * maxf * 64));
 }
 
 struct RotSrc {
@@ -119,19 +114,19 @@ struct RotSrc {
 };
 
 __global__ void __launch_bounds__(64)
-k_header(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int nitems,
+k_header(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int nslots, int maxf,
          int mupos, c8b_frame* __restrict__ frames, const float2* __restrict__ chan, float2* __restrict__ hinv,
          int64_t llrStride)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nitems) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // frame slot; its item is i / maxf
+    if (i >= nslots) return;
     c8b_frame f = frames[i];
     f.llr_off = (int64_t)i * llrStride;
     if (f.status == C8B_ST_OK) {
         cf hl[64], hv[64];
         for (int k = 0; k < 64; k++) { const float2 c = chan[(size_t)i * 64 + k]; hl[k] = c8b::mk(c.x, c.y); }
         RotSrc rot;
-        rot.x = reinterpret_cast<const cf*>(iq + off[i]) + f.sync_idx + 224;
+        rot.x = reinterpret_cast<const cf*>(iq + off[i / maxf]) + f.sync_idx + 224;
         rot.rad = f.rad; rot.nsamp = f.nsamp;
         f.status = c8b::demod_header(lut, rot, f.nsamp, f.l_mcs, f.l_len, hl, mupos, &f, hv);
         for (int k = 0; k < 64; k++) hinv[(size_t)i * 64 + k] = make_float2(hv[k].re, hv[k].im);
@@ -143,19 +138,19 @@ k_header(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const i
 // 2-antenna header states (demod2): per frame hinv (1-stream frames), w2 (2-stream frames: 256 ZF weights + 8 pilot refs)
 __global__ void __launch_bounds__(64)
 k_header2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const float2* __restrict__ iq1,
-          const int64_t* __restrict__ off, int nitems, c8b_frame* __restrict__ frames, const float2* __restrict__ chan,
+          const int64_t* __restrict__ off, int nslots, int maxf, c8b_frame* __restrict__ frames, const float2* __restrict__ chan,
           float2* __restrict__ hinv, float2* __restrict__ w2, int64_t llrStride)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nitems) return;
+    if (i >= nslots) return;
     c8b_frame f = frames[i];
     f.llr_off = (int64_t)i * llrStride;
     if (f.status == C8B_ST_OK) {
         cf hl[64], hv[64];
         for (int k = 0; k < 64; k++) { const float2 c = chan[(size_t)i * 64 + k]; hl[k] = c8b::mk(c.x, c.y); }
         RotSrc r0, r1;
-        r0.x = reinterpret_cast<const cf*>(iq0 + off[i]) + f.sync_idx + 224; r0.rad = f.rad; r0.nsamp = f.nsamp;
-        r1 = r0; r1.x = reinterpret_cast<const cf*>(iq1 + off[i]) + f.sync_idx + 224;
+        r0.x = reinterpret_cast<const cf*>(iq0 + off[i / maxf]) + f.sync_idx + 224; r0.rad = f.rad; r0.nsamp = f.nsamp;
+        r1 = r0; r1.x = reinterpret_cast<const cf*>(iq1 + off[i / maxf]) + f.sync_idx + 224;
         f.status = c8b::demod_header2(lut, r0, r1, f.nsamp, f.l_mcs, f.l_len, hl, &f, hv, reinterpret_cast<cf*>(w2 + (size_t)i * 264));
         for (int k = 0; k < 64; k++) hinv[(size_t)i * 64 + k] = make_float2(hv[k].re, hv[k].im);
         if (f.status == C8B_ST_OK && (int64_t)f.total > llrStride) f.status = C8B_ST_OVERFLOW;
@@ -165,11 +160,11 @@ k_header2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const
 
 }  // namespace
 
-void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, c8b_frame* frames,
-                        const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st)
+void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf,
+                        c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_header2<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq0, iq1, d_off, nitems, frames, chan, hinv, w2, llrStride);
+    k_header2<<<(nitems * maxf + 63) / 64, 64, 0, st>>>(lut, iq0, iq1, d_off, nitems * maxf, maxf, frames, chan, hinv, w2, llrStride);
 }
 
 void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int maxLen, int64_t outBase,
@@ -186,15 +181,15 @@ void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d
 void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st) { k_trigger<<<1, 32, 0, st>>>(preac, n, out); }
 
 void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
-                       int64_t outBase, const float* preac, c8b_frame* frames, float2* chan, cudaStream_t st)
+                       int maxf, int64_t outBase, const float* preac, c8b_frame* frames, float2* chan, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_detect<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, outBase, preac, frames, chan);
+    k_detect<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, frames, chan);
 }
 
-void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int mupos, c8b_frame* frames,
+void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
                        const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_header<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq, d_off, nitems, mupos, frames, chan, hinv, llrStride);
+    k_header<<<(nitems * maxf + 63) / 64, 64, 0, st>>>(lut, iq, d_off, nitems * maxf, maxf, mupos, frames, chan, hinv, llrStride);
 }

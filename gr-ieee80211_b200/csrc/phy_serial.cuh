@@ -325,16 +325,27 @@ C8B_HDN int signal_at(const c8b_lut* L, const cf* in, float rad, cf* h, int* mcs
 // lib/sync_impl.cc:73-147) -> signal (S_TRIGGER/S_DEMOD, lib/signal_impl.cc:75-162), evaluated over
 // the item from reset state.  preac = presiso output for the item.  Fills the detection fields of f.
 // ---------------------------------------------------------------------------------------------
-C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int n, int item, c8b_frame* f, cf* h)
+C8B_HD void frame_clear(c8b_frame* f, int item, int status)
+{
+    f->status = status; f->item = item;
+    f->trig_idx = 0; f->sync_idx = 0; f->rad = f->snr = f->rssi = f->cfo_hz = 0.f;
+    f->l_mcs = f->l_len = f->nsamp = 0;
+    f->format = f->mcs = f->len = f->cr = f->ampdu = f->nss = f->nsym = f->nsymsamp = f->ncbps = f->ndbps = 0;
+    f->trellis = f->total = f->data_off = 0; f->sssnr0 = f->sssnr1 = 0.f;
+    f->llr_off = 0; f->pdu_off = 0; f->npdu = f->pdu_bytes = 0;
+}
+
+// f[0..maxf): frame records of this item, h[0..maxf*64): their legacy channels.  Frames are found in stream order
+// exactly as the blocks would (S_COPY swallows the sync flags inside a copied frame, lib/signal_impl.cc:164-192);
+// unused records get C8B_ST_EMPTY, an item without any accepted frame reports its drop code in record 0.
+C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int n, int item, int maxf, c8b_frame* f, cf* h)
 {
     TrigState ts;
     trig_reset(ts);
-    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0;
-    bool syncStalled = false, sigStalled = false, found = false;
-    f->status = C8B_ST_NO_TRIGGER; f->item = item;
-    f->trig_idx = 0; f->sync_idx = 0; f->rad = f->snr = f->rssi = f->cfo_hz = 0.f;
-    f->l_mcs = f->l_len = f->nsamp = 0;
-    for (int i = 0; i < n && !found; i++) {
+    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0, nf = 0;
+    bool syncStalled = false, sigStalled = false, done = false;
+    for (int k = 0; k < maxf; k++) frame_clear(f + k, item, C8B_ST_EMPTY);
+    for (int i = 0; i < n && !done; i++) {
         const uint8_t fl = trig_step(ts, preac[i]);
         if (fl == 0 || i < skipUntil || syncStalled) continue;
         if (fl & 0x01) {
@@ -349,17 +360,22 @@ C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int 
             if (sigStalled || idx < pos) continue;                // swallowed by S_COPY / skipped 80
             if (n - idx < 224) { sigStalled = true; continue; }   // signal_impl.cc:110 stall
             int mcs = 0, len = 0, nsamp = 0;
-            if (!signal_at(L, x + idx, so.rad, h, &mcs, &len, &nsamp)) { nLsigFail++; pos = idx + 80; continue; }
-            found = true;
-            f->trig_idx = i; f->sync_idx = idx; f->rad = so.rad; f->snr = so.snr; f->rssi = so.rssi;
-            f->cfo_hz = fmul(so.rad, 3183098.8618379068f);        // signal_impl.cc:135
-            f->l_mcs = mcs; f->l_len = len; f->nsamp = nsamp;
-            f->status = (idx + 224 + nsamp > n) ? C8B_ST_TRUNC : C8B_ST_OK;
+            cf* hk = h + nf * 64;
+            if (!signal_at(L, x + idx, so.rad, hk, &mcs, &len, &nsamp)) { nLsigFail++; pos = idx + 80; continue; }
+            c8b_frame* fk = f + nf;
+            nf++;
+            fk->trig_idx = i; fk->sync_idx = idx; fk->rad = so.rad; fk->snr = so.snr; fk->rssi = so.rssi;
+            fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);       // signal_impl.cc:135
+            fk->l_mcs = mcs; fk->l_len = len; fk->nsamp = nsamp;
+            pos = idx + 224 + nsamp;
+            if (pos > n) { fk->status = C8B_ST_TRUNC; done = true; }   // S_COPY can never finish: nothing after it
+            else fk->status = C8B_ST_OK;
+            if (nf >= maxf) done = true;
         } else if (fl & 0x02) {
             latch = i;
         }
     }
-    if (!found) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
+    if (nf == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
 }
 
 // ---------------------------------------------------------------------------------------------

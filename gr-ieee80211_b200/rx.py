@@ -41,11 +41,12 @@ class Receiver:
     """One context = one GPU + one stream.  `blob`: LUT blob to load (default: build locally; multi-GPU
     runs pass the blob broadcast from rank 0)."""
 
-    def __init__(self, device=0, chunk_items=16384, max_item_len=0, ev_cap=8, mupos=0, mugid=0, blob=None):
+    def __init__(self, device=0, chunk_items=16384, max_item_len=0, max_frames=1, mupos=0, mugid=0, blob=None):
         self.L = _cabi.lib()
         if self.L.c8b_device_count() <= 0:
             raise C8bError("no CUDA device visible: gr-ieee80211_b200 has no CPU path")
-        cfg = C8bCfg(device=device, chunk_items=chunk_items, max_item_len=max_item_len, ev_cap=ev_cap, mupos=mupos, mugid=mugid)
+        cfg = C8bCfg(device=device, chunk_items=chunk_items, max_item_len=max_item_len, max_frames=max_frames, mupos=mupos, mugid=mugid)
+        self.max_frames = max(1, int(max_frames))
         h = C.c_void_p()
         rc = self.L.c8b_create(C.byref(cfg), C.byref(h))
         if rc:
@@ -91,11 +92,11 @@ class Receiver:
         iqf = _c2f(iq)
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
-        n = off.size
-        frames = np.zeros(n, FRAME_DTYPE)
-        pdu = np.zeros(n * pdu_stride, np.uint8)
+        n, ns = off.size, off.size * self.max_frames
+        frames = np.zeros(ns, FRAME_DTYPE)
+        pdu = np.zeros(ns * pdu_stride, np.uint8)
         self._ck(self.L.c8b_rx_batch(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch")
-        return frames, pdu.reshape(n, pdu_stride)
+        return frames, pdu.reshape(ns, pdu_stride)
 
     def rx_batch2(self, iq0, iq1, off, length, pdu_stride=4400):
         """2x2: antenna 0 drives detection, both antennas are demodulated (signal2 + demod2)."""
@@ -103,21 +104,21 @@ class Receiver:
         assert a.size == b.size
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
-        n = off.size
-        frames = np.zeros(n, FRAME_DTYPE)
-        pdu = np.zeros(n * pdu_stride, np.uint8)
+        n, ns = off.size, off.size * self.max_frames
+        frames = np.zeros(ns, FRAME_DTYPE)
+        pdu = np.zeros(ns * pdu_stride, np.uint8)
         self._ck(self.L.c8b_rx_batch2(self.h, ptr(a), ptr(b), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch2")
-        return frames, pdu.reshape(n, pdu_stride)
+        return frames, pdu.reshape(ns, pdu_stride)
 
     def rx_batch_dev(self, d_iq_ptr, off, length, pdu_stride=4400, frames=None, pdu=None):
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
-        n = off.size
-        frames = np.zeros(n, FRAME_DTYPE) if frames is None else frames
-        pdu = np.zeros(n * pdu_stride, np.uint8) if pdu is None else pdu
+        n, ns = off.size, off.size * self.max_frames
+        frames = np.zeros(ns, FRAME_DTYPE) if frames is None else frames
+        pdu = np.zeros(ns * pdu_stride, np.uint8) if pdu is None else pdu
         self._ck(self.L.c8b_rx_batch_dev(self.h, C.c_void_p(d_iq_ptr), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride),
                  "c8b_rx_batch_dev")
-        return frames, pdu.reshape(n, pdu_stride)
+        return frames, pdu.reshape(ns, pdu_stride)
 
     def rx_batch_dev_async(self, d_iq_ptr, off, length, d_frames_ptr, d_pdu_ptr, pdu_stride=4400):
         off = np.ascontiguousarray(off, np.int64)
@@ -144,33 +145,35 @@ class Receiver:
         iqf = _c2f(iq)
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
-        n = off.size
-        frames = np.zeros(n, FRAME_DTYPE)
-        chan = np.zeros(n * 128, np.float32)
+        n, ns = off.size, off.size * self.max_frames
+        frames = np.zeros(ns, FRAME_DTYPE)
+        chan = np.zeros(ns * 128, np.float32)
         self._ck(self.L.c8b_detect(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(chan)), "c8b_detect")
-        return frames, chan.view(np.complex64).reshape(n, 64)
+        return frames, chan.view(np.complex64).reshape(ns, 64)
 
     def demod(self, iq, off, length, frames, chan, llr_stride):
         iqf = _c2f(iq)
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
-        n = off.size
+        n, ns = off.size, off.size * self.max_frames
         frames = np.ascontiguousarray(frames).copy()
+        assert frames.size == ns
         chanf = _c2f(chan)
-        llr = np.zeros(n * llr_stride, np.float32)
+        llr = np.zeros(ns * llr_stride, np.float32)
         self._ck(self.L.c8b_demod(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(chanf), ptr(llr), llr_stride), "c8b_demod")
-        return frames, llr.reshape(n, llr_stride)
+        return frames, llr.reshape(ns, llr_stride)
 
     def demod2(self, iq0, iq1, off, length, frames, chan, llr_stride):
         a, b = _c2f(iq0), _c2f(iq1)
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
-        n = off.size
+        n, ns = off.size, off.size * self.max_frames
         frames = np.ascontiguousarray(frames).copy()
+        assert frames.size == ns
         chanf = _c2f(chan)
-        llr = np.zeros(n * llr_stride, np.float32)
+        llr = np.zeros(ns * llr_stride, np.float32)
         self._ck(self.L.c8b_demod2(self.h, ptr(a), ptr(b), ptr(off), ptr(length), n, ptr(frames), ptr(chanf), ptr(llr), llr_stride), "c8b_demod2")
-        return frames, llr.reshape(n, llr_stride)
+        return frames, llr.reshape(ns, llr_stride)
 
     def decode(self, llr, frames, pdu_stride=4400, want_scram=False, scram_stride=0):
         llr = np.ascontiguousarray(llr, np.float32).reshape(-1)

@@ -52,7 +52,8 @@ extern "C" {
 #define C8B_ST_FORMAT 5          /* HT/VHT sanity failed -> CLEAN (lib/demod_impl.cc:167,194)   */
 #define C8B_ST_DECODE_RANGE 6    /* len>4095 or trellis>32782     (lib/decode_impl.cc:93-97)    */
 #define C8B_ST_NDP 7             /* VHT NDP (nSym==0): no PDU                                   */
-#define C8B_ST_OVERFLOW 8        /* more events in the item than the ctx was sized for          */
+#define C8B_ST_OVERFLOW 8        /* frame needs more LLR scratch than the ctx sized per frame   */
+#define C8B_ST_EMPTY 9           /* unused frame record of an item (max_frames > frames found)  */
 
 /* formats / code rates: same numbering as lib/cloud80211phy.h:35-49 */
 #define C8B_F_L 0
@@ -103,7 +104,7 @@ typedef struct c8b_cfg {
     int32_t device;          /* CUDA device ordinal                                               */
     int32_t chunk_items;     /* items processed per pipeline pass (scratch is sized for this)     */
     int32_t max_item_len;    /* longest item, complex samples                                     */
-    int32_t ev_cap;          /* sync events kept per item (0 -> 8)                                */
+    int32_t max_frames;      /* frame records per item (0 -> 1); a long capture is one item with many */
     int32_t mupos;           /* demod(mupos, mugid) ctor args (lib/demod_impl.cc:28-32)           */
     int32_t mugid;
     int32_t reserved[8];
@@ -129,9 +130,10 @@ int  c8b_lut_load(c8b_ctx* ctx, const void* blob, size_t n);       /* host blob 
 int  c8b_lut_load_dev(c8b_ctx* ctx, const void* d_blob, size_t n); /* device blob (after ncclBcast) */
 
 /* ---- whole chain, batched: items are independent capture segments processed from reset state --
- * iq: complex samples; item i = iq[off[i] .. off[i]+len[i]).  frames[i] = first frame accepted by
- * L-SIG in item i (or a record carrying the drop status).  PDU records of item i are written at
- * pdu + i*pdu_stride (at most pdu_stride bytes).  c8b_rx_batch takes HOST buffers (pinned or not)
+ * iq: complex samples; item i = iq[off[i] .. off[i]+len[i]).  With F = cfg.max_frames (default 1), frames[i*F + k]
+ * is the k-th frame accepted by L-SIG in item i, in stream order (record i*F carries the drop status when there is
+ * none, unused records are C8B_ST_EMPTY); `frames` holds nitems*F records.  PDU records of frame slot s are written
+ * at pdu + s*pdu_stride (at most pdu_stride bytes), `pdu` holds nitems*F*pdu_stride bytes.  c8b_rx_batch takes HOST buffers (pinned or not)
  * and pipelines H2D / kernels / D2H chunk by chunk; c8b_rx_batch_dev takes a DEVICE iq pointer and
  * host off/len/frames/pdu. */
 int  c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems,

@@ -29,10 +29,10 @@ int hs_sync(const float* iq, float cre, float cim, int* mIndex, float* rad, floa
 }
 void hs_sig_viterbi(const float* llr, uint8_t* bits, int T) { sig_viterbi(lut(), llr, bits, T); }
 int hs_crc8(const uint8_t* bits, int len, const uint8_t* crc) { return crc8_check(bits, len, crc) ? 1 : 0; }
-void hs_detect(const float* iq, const float* preac, int n, int item, c8b_frame* f, float* chan)
+void hs_detect(const float* iq, const float* preac, int n, int item, int maxf, c8b_frame* f, float* chan)
 {
-    memset(f, 0, sizeof(*f));
-    detect_item(lut(), (const cf*)iq, preac, n, item, f, (cf*)chan);
+    memset(f, 0, sizeof(*f) * maxf);
+    detect_item(lut(), (const cf*)iq, preac, n, item, maxf, f, (cf*)chan);
 }
 void hs_header(const float* iq_item, c8b_frame* f, const float* chan, int mupos, float* hinv)
 {

@@ -99,3 +99,50 @@ def test_bench_frames_config5_shape(golden):
     for k in range(64):
         assert fr[k]["npdu"] == 1 and (fr[k]["format"], fr[k]["mcs"], fr[k]["nsym"], fr[k]["trellis"], fr[k]["total"]) == (2, 7, 47, 12220, 14664)
         assert bytes(pdu[k, 3:1503]) == bytes(mp[k % 16])
+
+
+def test_long_capture_many_frames_in_stream_order(golden):
+    """the reference demo: tools/pktGenExample.py:183-199 writes L MCS0-7, HT MCS0-7, VHT MCS0-8 into ONE capture that
+    examples/rx.grc decodes frame after frame.  Same here: one item, max_frames records, PDUs in stream order."""
+    pkg = load_pkg()
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    x = np.ascontiguousarray(g["iq"][offs[1]:offs[26]])              # 25 frames (the demo set), 400-sample gaps
+    rx = pkg.Receiver(device=0, max_frames=32)
+    fr, pdu = rx.rx_batch(x, [0], [x.size])
+    rx.close()
+    fo, _, po = ol.rx_item(x, max_frames=32)
+    recs = ol.split_pdus(po)
+    assert len(fo) == 25 and len(recs) == 25
+    el = g["exp_len"]
+    eo = np.cumsum(np.r_[0, el])
+    for k in range(32):
+        if k >= 25:
+            assert fr[k]["status"] == 9                                  # C8B_ST_EMPTY
+            continue
+        for key in ("status", "sync_idx", "trig_idx", "format", "mcs", "len", "nsym", "trellis", "npdu", "pdu_bytes"):
+            assert fr[k][key] == fo[k][key], (k, key, fr[k][key], fo[k][key])
+        assert bytes(pdu[k, :fr[k]["pdu_bytes"]]) == recs[k]
+        assert recs[k][3:-1] == bytes(g["exp_mpdu"][eo[k + 1]:eo[k + 2]])
+
+
+def test_two_items_each_with_several_frames(golden):
+    pkg = load_pkg()
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    a = g["iq"][offs[3]:offs[7]]
+    b = g["iq"][offs[20]:offs[23]]
+    iq = np.concatenate([a, b]).astype(np.complex64)
+    rx = pkg.Receiver(device=0, max_frames=5, chunk_items=1)
+    fr, pdu = rx.rx_batch(iq, [0, a.size], [a.size, b.size])
+    rx.close()
+    for it, x in enumerate((a, b)):
+        fo, _, po = ol.rx_item(np.ascontiguousarray(x), max_frames=5)
+        recs = ol.split_pdus(po)
+        for k in range(5):
+            s = it * 5 + k
+            if k < len(fo):
+                assert fr[s]["status"] == fo[k]["status"] and fr[s]["sync_idx"] == fo[k]["sync_idx"] and fr[s]["item"] == it
+                assert bytes(pdu[s, :fr[s]["pdu_bytes"]]) == recs[k]
+            else:
+                assert fr[s]["status"] == 9

@@ -23,16 +23,16 @@ def _items(g, noise=0.0, seed=3):
         yield i, np.ascontiguousarray(x)
 
 
-def _detect(x):
+def _detect(x, maxf=1):
     pkg = load_pkg()
     H, O = hs.lib(), ol.oracle()
     xf = ol.c2f(x)
     n = x.size
     preac, preconj = np.zeros(n, np.float32), np.zeros(2 * n, np.float32)
     O.orx_presiso(xf, n, preac, preconj)
-    f = np.zeros(1, pkg.FRAME_DTYPE)
-    chan = np.zeros(128, np.float32)
-    H.hs_detect(xf, preac, n, 0, f.ctypes.data, chan)
+    f = np.zeros(maxf, pkg.FRAME_DTYPE)
+    chan = np.zeros(128 * maxf, np.float32)
+    H.hs_detect(xf, preac, n, 0, maxf, f.ctypes.data, chan)
     return f, chan, preac, preconj.view(np.complex64)
 
 
@@ -159,3 +159,24 @@ def test_header2_matches_oracle(golden, snr):
         w = w2.view(np.complex64)[:256].reshape(64, 4)
         used = [k for k in range(64) if not (k == 0 or 29 <= k <= 35)]
         assert np.all(np.abs(w[used, 1]) < 0.2 * np.abs(w[used, 0])) and np.all(np.abs(w[used, 2]) < 0.2 * np.abs(w[used, 3]))
+
+
+def test_multi_frame_capture_matches_oracle(golden):
+    """a capture holding many frames back to back (the reference demo: tools/pktGenExample.py writes 25 frames into one
+    .bin): frames must be found in stream order with the flags inside a copied frame swallowed"""
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    x = np.ascontiguousarray(g["iq"][offs[1]:offs[12]])          # 11 frames, 400-sample gaps
+    fo, _, _ = ol.rx_item(x, max_frames=16)
+    f, chan, _, _ = _detect(x, maxf=16)
+    assert len(fo) == 11
+    for k in range(16):
+        if k < len(fo):
+            for key in DET:
+                assert f[k][key] == fo[k][key], (k, key, f[k][key], fo[k][key])
+        else:
+            assert f[k]["status"] == 9
+    # fewer records than frames: the first ones, in order
+    f4, _, _, _ = _detect(x, maxf=4)
+    for k in range(4):
+        assert f4[k]["sync_idx"] == fo[k]["sync_idx"]
