@@ -22,7 +22,7 @@ struct c8b_ctx {
     bool lutLoaded = false;
     unsigned* d_counter = nullptr;
     // scratch (grown on demand)
-    DevBuf iq, iq1, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
+    DevBuf iq, iq1, mask, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
     int survWarps = 0;
     // timing
     bool timing = false;
@@ -141,7 +141,7 @@ void c8b_destroy(c8b_ctx* ctx)
     cudaStreamSynchronize(ctx->st);
     timing_collect(ctx);
     for (auto e : ctx->evPool) cudaEventDestroy(e);
-    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
+    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
                        &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -327,7 +327,9 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     const int64_t span = pl.end - pl.base;
     const int64_t llrStride = llr_stride_for(pl.maxLen) * (d_iq1 ? 2 : 1);
     if (d_iq1) EN(w2, ns * 264 * sizeof(float2));
+    const int maskStride = (pl.maxLen + 31) / 32 + 1;
     EN(preac, (size_t)(span + 64) * sizeof(float));
+    EN(mask, (size_t)n * maskStride * sizeof(uint32_t));
     EN(chan, ns * 64 * sizeof(float2));
     EN(hinv, ns * 64 * sizeof(float2));
     EN(llr, ns * llrStride * sizeof(float));
@@ -338,12 +340,13 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     const float2* iq1 = d_iq1 ? d_iq1 - iqShift : nullptr;
     {
         StageTimer tm(ctx, C8B_K_PRESISO);
-        c8b_launch_presiso(iq, d_off + b, d_len + b, n, pl.maxLen, pl.base, (float*)ctx->preac.p, nullptr, ctx->st);
+        c8b_launch_presiso(iq, d_off + b, d_len + b, n, pl.maxLen, pl.base, (float*)ctx->preac.p, nullptr, (uint32_t*)ctx->mask.p, maskStride,
+                           ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DETECT);
-        c8b_launch_detect(ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, d_frames + (size_t)b * maxf,
-                          (float2*)ctx->chan.p, ctx->st);
+        c8b_launch_detect(ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p,
+                          maskStride, d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_HEADER);
@@ -519,7 +522,7 @@ int c8b_presiso(c8b_ctx* ctx, const float* h_iq, int64_t n, float* h_preac, floa
     {
         StageTimer tm(ctx, C8B_K_PRESISO);
         c8b_launch_presiso((const float2*)ctx->iq.p, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, 1, len, 0, (float*)ctx->preac.p,
-                           h_preconj ? (float2*)ctx->preconj.p : nullptr, ctx->st);
+                           h_preconj ? (float2*)ctx->preconj.p : nullptr, nullptr, 0, ctx->st);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_preac, ctx->preac.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
@@ -566,7 +569,9 @@ int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_
     if ((r = stage_items(ctx, h_iq, off, len, nitems, &pl))) return r;
     const int maxf = ctx->cfg.max_frames;
     const size_t ns = (size_t)nitems * maxf;
+    const int maskStride = (pl.maxLen + 31) / 32 + 1;
     EN(preac, (size_t)(pl.end - pl.base + 64) * sizeof(float));
+    EN(mask, (size_t)nitems * maskStride * sizeof(uint32_t));
     EN(frames, ns * sizeof(c8b_frame));
     EN(chan, ns * 64 * sizeof(float2));
     CK(cudaMemsetAsync(ctx->frames.p, 0, ns * sizeof(c8b_frame), ctx->st));
@@ -575,12 +580,13 @@ int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_
     {
         StageTimer tm(ctx, C8B_K_PRESISO);
         c8b_launch_presiso(iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, pl.maxLen, pl.base, (float*)ctx->preac.p, nullptr,
-                           ctx->st);
+                           (uint32_t*)ctx->mask.p, maskStride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DETECT);
         c8b_launch_detect(ctx->d_lut, iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, 0, maxf, pl.base,
-                          (const float*)ctx->preac.p, (c8b_frame*)ctx->frames.p, (float2*)ctx->chan.p, ctx->st);
+                          (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p, maskStride, (c8b_frame*)ctx->frames.p,
+                          (float2*)ctx->chan.p, ctx->st);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(frames, ctx->frames.p, ns * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));

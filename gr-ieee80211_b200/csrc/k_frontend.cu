@@ -21,7 +21,7 @@ constexpr int PTHREADS = 256;
 // sum48[n]=(s16[n-32]+s16[n-16])+s16[n]; sum64[n]=(s16[n-48]+s16[n-32])+(s16[n-16]+s16[n]).
 __global__ void __launch_bounds__(PTHREADS)
 k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int64_t outBase,
-          float* __restrict__ preac, float2* __restrict__ preconj)
+          float* __restrict__ preac, float2* __restrict__ preconj, uint32_t* __restrict__ mask, int maskStride)
 {
     __shared__ float4 s[PT + PH];                   // (re, im, |x|^2, -) of v at item index t0 - 64 + j
     const int item = blockIdx.y;
@@ -77,8 +77,14 @@ k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const 
         const float cr = __fadd_rn(__fadd_rn(a2.x, a1.x), a0.x), ci = __fadd_rn(__fadd_rn(a2.y, a1.y), a0.y);
         const float pw = __fadd_rn(__fadd_rn(a3.z, a2.z), __fadd_rn(a1.z, a0.z));
         const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));   // complex_to_mag
-        preac[ob + i] = __fdiv_rn(mag, pw);                                                 // divide_ff
+        const float ac = __fdiv_rn(mag, pw);                                                // divide_ff
+        preac[ob + i] = ac;
         if (preconj) preconj[ob + i] = make_float2(cr, ci);
+        if (mask) {                                        // threshold bitmap for the trigger scan (lib/trigger_impl.cc:79)
+            // i is a multiple of 32 at lane 0 (t0 and k are); lanes past the end of the item left the loop above
+            const uint32_t m = __ballot_sync(__activemask(), ac > 0.3f);
+            if ((threadIdx.x & 31) == 0) mask[(size_t)item * maskStride + (i >> 5)] = m;
+        }
     }
 }
 
@@ -93,13 +99,14 @@ __global__ void k_trigger(const float* __restrict__ preac, int64_t n, uint8_t* _
 __global__ void __launch_bounds__(64)
 k_detect(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
          const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preac,
-         c8b_frame* __restrict__ frames, float2* __restrict__ chan)
+         const uint32_t* __restrict__ mask, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nitems) return;
     // records and channels are written in place (device global memory): frames[i*maxf ..], chan[i*maxf*64 ..]
     c8b::detect_item(lut, reinterpret_cast<const cf*>(iq + off[i]), preac + (off[i] - outBase), len[i], itemBase + i, maxf,
-                     frames + (size_t)i * maxf, reinterpret_cast<cf*>(chan + (size_t)i * maxf * 64));
+                     frames + (size_t)i * maxf, reinterpret_cast<cf*>(chan + (size_t)i * maxf * 64),
+                     mask ? mask + (size_t)i * maskStride : nullptr);
 }
 
 struct RotSrc {
@@ -168,23 +175,25 @@ void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1
 }
 
 void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int maxLen, int64_t outBase,
-                        float* preac, float2* preconj, cudaStream_t st)
+                        float* preac, float2* preconj, uint32_t* mask, int maskStride, cudaStream_t st)
 {
     if (nitems <= 0 || maxLen <= 0) return;
     for (int base = 0; base < nitems; base += 65535) {
         const int cnt = nitems - base < 65535 ? nitems - base : 65535;
         dim3 grid((maxLen + PT - 1) / PT, cnt);
-        k_presiso<<<grid, PTHREADS, 0, st>>>(iq, d_off + base, d_len + base, outBase, preac, preconj);
+        k_presiso<<<grid, PTHREADS, 0, st>>>(iq, d_off + base, d_len + base, outBase, preac, preconj,
+                                              mask ? mask + (size_t)base * maskStride : nullptr, maskStride);
     }
 }
 
 void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st) { k_trigger<<<1, 32, 0, st>>>(preac, n, out); }
 
 void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
-                       int maxf, int64_t outBase, const float* preac, c8b_frame* frames, float2* chan, cudaStream_t st)
+                       int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
+                       float2* chan, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_detect<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, frames, chan);
+    k_detect<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask, maskStride, frames, chan);
 }
 
 void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,

@@ -44,12 +44,13 @@ static_assert(CH % 5 == 0 && GS % 5 == 0 && CH % GS == 0, "phases must align wit
 static_assert(((C8B_DECODE_T_MAX + CH - 1) / CH) * NG * 32 <= C8B_VIT_TPAD, "survivor scratch too small");
 
 constexpr int TBW = 4;                         // traceback warm-up, in 30-step groups, before a lane's own segment
-constexpr int U_BYTES = 8704;                  // union area: forward tables | traceback staging | decoded words
+constexpr int U_BYTES = 9600;                  // union area: forward tables | traceback staging | decoded words
 constexpr int ROW = 68;                        // words per lane row in the traceback staging (64 + pad: conflict-free 16-byte stores)
-static_assert(2 * CH * 16 <= U_BYTES && 32 * ROW * 4 <= U_BYTES && WORDS * 4 <= U_BYTES, "union area too small");
+static_assert(2 * CH * 32 <= U_BYTES && 32 * ROW * 4 <= U_BYTES && WORDS * 4 <= U_BYTES, "union area too small");
 
 // Per-warp shared memory (dynamic).  The union area is used, in turn, as
-//   forward pass : float4 tab[2][CH]   per step {0, t1, t0, t1+t0} (lib/decode_impl.cc:231-234), one table per frame
+//   forward pass : float2 tab[2][CH][4] per step and class c the pair (tab[c], tab[3-c]) of {0, t1, t0, t1+t0}
+//                  (lib/decode_impl.cc:231-234), one table per frame
 //   traceback    : uint32 stage[32][ROW] decision words of the group each lane is walking, [lane][2*rho+h]
 //   afterwards   : uint32 words[WORDS]  decoded bits packed LSB-first, descrambled in place -> PSDU bytes
 struct __align__(16) WarpSmem {
@@ -104,7 +105,14 @@ __device__ __forceinline__ float2 load_pair(const float* __restrict__ llr, int b
     v.y = (r1 != 0xffff && i1 < lim) ? __ldg(llr + i1) : 0.0f;
     return v;
 }
-__device__ __forceinline__ float4 mk_tab(float2 p) { return make_float4(0.0f, p.y, p.x, __fadd_rn(p.y, p.x)); }   // {0, t1, t0, t1+t0}
+// per step, per butterfly class c: the pair (A, B) = (tab[c], tab[3-c]) of tab = {0, t1, t0, t1+t0}, so a lane gets both
+// branch metrics with one 8-byte shared-memory read: {0,T3}, {t1,t0}, {t0,t1}, {T3,0}
+__device__ __forceinline__ void put_tab(float4* __restrict__ row, float2 p)
+{
+    const float t3 = __fadd_rn(p.y, p.x);
+    row[0] = make_float4(0.0f, t3, p.y, p.x);
+    row[1] = make_float4(p.x, p.y, t3, 0.0f);
+}
 
 // one add-compare-select step at layout phase P.  (x0,x1) in: metrics of old states (2k,2k+1);
 // out: metrics of (2k',2k'+1) for the next phase.  hLo/hHi: decision history of this lane.
@@ -290,11 +298,11 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
 #pragma unroll
             for (int j = 0; j < NLD; j++)
                 if (lane + 32 * j < CH) {
-                    Stab[lane + 32 * j] = mk_tab(load_pair(jobs[0].llr, 0, limA, rela[j]));
-                    Stab[CH + lane + 32 * j] = mk_tab(load_pair(jobs[1].llr, 0, limB, relb[j]));
+                    put_tab(Stab + 2 * (lane + 32 * j), load_pair(jobs[0].llr, 0, limA, rela[j]));
+                    put_tab(Stab + 2 * (CH + lane + 32 * j), load_pair(jobs[1].llr, 0, limB, relb[j]));
                 }
             __syncwarp();
-            const float* __restrict__ tb = reinterpret_cast<const float*>(Stab);
+            const float2* __restrict__ tb = reinterpret_cast<const float2*>(Stab);   // [frame][step][class] -> (A, B)
             for (int c = 0; c < nch; c++) {
                 const bool more = c + 1 < nch;
                 if (more) {
@@ -304,11 +312,7 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                         pfb[j] = load_pair(jobs[1].llr, (c + 1) * nrawB, limB, relb[j]);
                     }
                 }
-                const float* pA0 = tb + 0 + cA[0], *pB0 = tb + 3 - cA[0];
-                const float* pA1 = tb + 4 + cA[1], *pB1 = tb + 7 - cA[1];
-                const float* pA2 = tb + 8 + cA[2], *pB2 = tb + 11 - cA[2];
-                const float* pA3 = tb + 12 + cA[3], *pB3 = tb + 15 - cA[3];
-                const float* pA4 = tb + 16 + cA[4], *pB4 = tb + 19 - cA[4];
+                const float2* p0 = tb + 0 + cA[0], *p1 = tb + 4 + cA[1], *p2 = tb + 8 + cA[2], *p3 = tb + 12 + cA[3], *p4 = tb + 16 + cA[4];
                 uint2* __restrict__ sgA = survW + (size_t)c * (NG * 32) + lane;
                 uint2* __restrict__ sgB = sgA + C8B_VIT_TPAD;
                 const bool stA = c < nchA, stB = c < nchB;
@@ -317,28 +321,28 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
                     uint32_t haLo = 0, haHi = 0, hbLo = 0, hbHi = 0;
 #pragma unroll
                     for (int i5 = 0; i5 < GS / 5; i5++) {           // 30 steps, all shared-memory offsets immediate
-                        const int o = i5 * 20, ob = o + CH * 4;     // frame B's table sits CH float4 further
-                        acs_step<0>(xa0, xa1, pA0[o], pB0[o], amask[0], haLo, haHi);
-                        acs_step<0>(xb0, xb1, pA0[ob], pB0[ob], amask[0], hbLo, hbHi);
-                        acs_step<1>(xa0, xa1, pA1[o], pB1[o], amask[1], haLo, haHi);
-                        acs_step<1>(xb0, xb1, pA1[ob], pB1[ob], amask[1], hbLo, hbHi);
-                        acs_step<2>(xa0, xa1, pA2[o], pB2[o], amask[2], haLo, haHi);
-                        acs_step<2>(xb0, xb1, pA2[ob], pB2[ob], amask[2], hbLo, hbHi);
-                        acs_step<3>(xa0, xa1, pA3[o], pB3[o], amask[3], haLo, haHi);
-                        acs_step<3>(xb0, xb1, pA3[ob], pB3[ob], amask[3], hbLo, hbHi);
-                        acs_step<4>(xa0, xa1, pA4[o], pB4[o], amask[4], haLo, haHi);
-                        acs_step<4>(xb0, xb1, pA4[ob], pB4[ob], amask[4], hbLo, hbHi);
+                        const int o = i5 * 20, ob = o + CH * 4;     // frame B's table sits CH steps (x 4 classes) further
+                        float2 ab;
+                        ab = p0[o];  acs_step<0>(xa0, xa1, ab.x, ab.y, amask[0], haLo, haHi);
+                        ab = p0[ob]; acs_step<0>(xb0, xb1, ab.x, ab.y, amask[0], hbLo, hbHi);
+                        ab = p1[o];  acs_step<1>(xa0, xa1, ab.x, ab.y, amask[1], haLo, haHi);
+                        ab = p1[ob]; acs_step<1>(xb0, xb1, ab.x, ab.y, amask[1], hbLo, hbHi);
+                        ab = p2[o];  acs_step<2>(xa0, xa1, ab.x, ab.y, amask[2], haLo, haHi);
+                        ab = p2[ob]; acs_step<2>(xb0, xb1, ab.x, ab.y, amask[2], hbLo, hbHi);
+                        ab = p3[o];  acs_step<3>(xa0, xa1, ab.x, ab.y, amask[3], haLo, haHi);
+                        ab = p3[ob]; acs_step<3>(xb0, xb1, ab.x, ab.y, amask[3], hbLo, hbHi);
+                        ab = p4[o];  acs_step<4>(xa0, xa1, ab.x, ab.y, amask[4], haLo, haHi);
+                        ab = p4[ob]; acs_step<4>(xb0, xb1, ab.x, ab.y, amask[4], hbLo, hbHi);
                     }
                     if (stA) sgA[g * 32] = make_uint2(haLo, haHi);
                     if (stB) sgB[g * 32] = make_uint2(hbLo, hbHi);
-                    pA0 += GS * 4; pB0 += GS * 4; pA1 += GS * 4; pB1 += GS * 4; pA2 += GS * 4; pB2 += GS * 4;
-                    pA3 += GS * 4; pB3 += GS * 4; pA4 += GS * 4; pB4 += GS * 4;
+                    p0 += GS * 4; p1 += GS * 4; p2 += GS * 4; p3 += GS * 4; p4 += GS * 4;
                 }
                 __syncwarp();
                 if (more) {
 #pragma unroll
                     for (int j = 0; j < NLD; j++)
-                        if (lane + 32 * j < CH) { Stab[lane + 32 * j] = mk_tab(pfa[j]); Stab[CH + lane + 32 * j] = mk_tab(pfb[j]); }
+                        if (lane + 32 * j < CH) { put_tab(Stab + 2 * (lane + 32 * j), pfa[j]); put_tab(Stab + 2 * (CH + lane + 32 * j), pfb[j]); }
                 }
                 __syncwarp();
             }

@@ -338,7 +338,11 @@ C8B_HD void frame_clear(c8b_frame* f, int item, int status)
 // f[0..maxf): frame records of this item, h[0..maxf*64): their legacy channels.  Frames are found in stream order
 // exactly as the blocks would (S_COPY swallows the sync flags inside a copied frame, lib/signal_impl.cc:164-192);
 // unused records get C8B_ST_EMPTY, an item without any accepted frame reports its drop code in record 0.
-C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int n, int item, int maxf, c8b_frame* f, cf* h)
+// mask (may be null): bit (i & 31) of mask[i >> 5] = (preac[i] > 0.3f), written by k_presiso; lets the scan jump over
+// 32 samples at a time while the trigger is idle (no plateau, no count-down): such a stretch leaves the FSM in its
+// reset state, so skipping it is exact.
+C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int n, int item, int maxf, c8b_frame* f, cf* h,
+                         const uint32_t* mask = nullptr)
 {
     TrigState ts;
     trig_reset(ts);
@@ -346,6 +350,11 @@ C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int 
     bool syncStalled = false, sigStalled = false, done = false;
     for (int k = 0; k < maxf; k++) frame_clear(f + k, item, C8B_ST_EMPTY);
     for (int i = 0; i < n && !done; i++) {
+        if (mask && (i & 31) == 0 && i + 32 <= n && ts.fPlateau == 0 && mask[i >> 5] == 0u) {
+            ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;   // what 32 sub-threshold samples leave behind
+            i += 31;
+            continue;
+        }
         const uint8_t fl = trig_step(ts, preac[i]);
         if (fl == 0 || i < skipUntil || syncStalled) continue;
         if (fl & 0x01) {

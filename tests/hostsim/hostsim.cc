@@ -32,6 +32,13 @@ int hs_crc8(const uint8_t* bits, int len, const uint8_t* crc) { return crc8_chec
 void hs_detect(const float* iq, const float* preac, int n, int item, int maxf, c8b_frame* f, float* chan)
 {
     memset(f, 0, sizeof(*f) * maxf);
+    if (item < 0) {                                            // item < 0: scan with the threshold bitmap (as k_presiso + k_detect do)
+        uint32_t* mask = new uint32_t[n / 32 + 2]();
+        for (int i = 0; i < n; i++) if (preac[i] > 0.3f) mask[i >> 5] |= 1u << (i & 31);
+        detect_item(lut(), (const cf*)iq, preac, n, -item - 1, maxf, f, (cf*)chan, mask);
+        delete[] mask;
+        return;
+    }
     detect_item(lut(), (const cf*)iq, preac, n, item, maxf, f, (cf*)chan);
 }
 void hs_header(const float* iq_item, c8b_frame* f, const float* chan, int mupos, float* hinv)

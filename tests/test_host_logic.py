@@ -23,7 +23,7 @@ def _items(g, noise=0.0, seed=3):
         yield i, np.ascontiguousarray(x)
 
 
-def _detect(x, maxf=1):
+def _detect(x, maxf=1, bitmap=False):
     pkg = load_pkg()
     H, O = hs.lib(), ol.oracle()
     xf = ol.c2f(x)
@@ -32,7 +32,7 @@ def _detect(x, maxf=1):
     O.orx_presiso(xf, n, preac, preconj)
     f = np.zeros(maxf, pkg.FRAME_DTYPE)
     chan = np.zeros(128 * maxf, np.float32)
-    H.hs_detect(xf, preac, n, 0, maxf, f.ctypes.data, chan)
+    H.hs_detect(xf, preac, n, -1 if bitmap else 0, maxf, f.ctypes.data, chan)
     return f, chan, preac, preconj.view(np.complex64)
 
 
@@ -180,3 +180,19 @@ def test_multi_frame_capture_matches_oracle(golden):
     f4, _, _, _ = _detect(x, maxf=4)
     for k in range(4):
         assert f4[k]["sync_idx"] == fo[k]["sync_idx"]
+
+
+def test_bitmap_scan_is_exact(golden):
+    """skipping 32 idle samples at a time (threshold bitmap from k_presiso) must not change a single field"""
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    rng = np.random.default_rng(8)
+    caps = [np.ascontiguousarray(g["iq"][offs[1]:offs[12]]), np.ascontiguousarray(g["iq"][offs[20]:offs[21]][:1777])]
+    z = np.ascontiguousarray(g["iq"][offs[5]:offs[9]])
+    caps.append((z + 0.03 * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))).astype(np.complex64))
+    t = np.tile((rng.standard_normal(16) + 1j * rng.standard_normal(16)).astype(np.complex64), 40)
+    caps.append(np.concatenate([np.zeros(333, np.complex64), 0.2 * t, np.zeros(1000, np.complex64), 0.1 * t, np.zeros(500, np.complex64)]).astype(np.complex64))
+    for x in caps:
+        a, ca, _, _ = _detect(x, maxf=16)
+        b, cb, _, _ = _detect(x, maxf=16, bitmap=True)
+        assert a.tobytes() == b.tobytes() and np.array_equal(ca, cb)
