@@ -10,8 +10,8 @@
 //  * complex/complex division is evaluated in double and rounded once -- that is what
 //    std::complex<float>::operator/ compiles to in the reference (libgcc __divsc3 on x86-64);
 //  * |z| is (float)sqrt((double)re^2 + im^2) (glibc hypotf), sqrtf/float division are IEEE;
-//  * cosf/sinf/atan2f: evaluated in double on the float argument and rounded (matches glibc's
-//    correctly rounded results except in rare double-rounding cases);
+//  * atan2f: evaluated in double on the float arguments and rounded; cosf/sinf: sincosf on the device
+//    (<= 2 ulp of the reference's glibc results), double-rounded in the host build;
 //  * the 64-point DFT stands in for gr::fft (FFTW): double radix-2, rounded once to float.
 #pragma once
 #include <math.h>
@@ -74,7 +74,11 @@ C8B_HD float cabsf_(cf a) { return (float)sqrt(dadd(dmul((double)a.re, (double)a
 C8B_HD float cosf_(float x) { return (float)cos((double)x); }
 C8B_HD float sinf_(float x) { return (float)sin((double)x); }
 C8B_HD float atan2f_(float y, float x) { return (float)atan2((double)y, (double)x); }
+#ifdef __CUDA_ARCH__
+C8B_HD cf cis(float ph) { float sn, cs; sincosf(ph, &sn, &cs); return mk(cs, sn); }   // <= 2 ulp; the reference calls cosf / sinf
+#else
 C8B_HD cf cis(float ph) { return mk(cosf_(ph), sinf_(ph)); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // 64-point forward DFT, unnormalised, natural order (gr::fft::fft_complex_fwd(64) at
