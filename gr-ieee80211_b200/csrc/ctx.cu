@@ -16,13 +16,16 @@ struct DevBuf {
 struct c8b_ctx {
     c8b_cfg cfg;
     int device = 0, numSM = 0;
-    cudaStream_t st = nullptr, stCopy = nullptr;
+    cudaStream_t st = nullptr, stCopy = nullptr, stVit = nullptr;
+    cudaEvent_t evFront[2] = { nullptr, nullptr }, evVit[2] = { nullptr, nullptr };
+    unsigned chunkSeq = 0;
+    bool overlap = true;     // Viterbi of chunk k on its own stream, concurrent with the front end of chunk k+1
     std::string err;
     c8b_lut* d_lut = nullptr;
     bool lutLoaded = false;
     unsigned* d_counter = nullptr;
     // scratch (grown on demand)
-    DevBuf iq, iq1, mask, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
+    DevBuf iq, iq1, mask, llrB, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
     int survWarps = 0;
     // timing
     bool timing = false;
@@ -47,7 +50,7 @@ static std::string g_createErr;
 static int ensure(c8b_ctx* ctx, DevBuf& b, size_t bytes)
 {
     if (bytes <= b.cap) return C8B_OK;
-    if (b.p) { cudaStreamSynchronize(ctx->st); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    if (b.p) { cudaDeviceSynchronize(); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
@@ -73,14 +76,14 @@ static cudaEvent_t ev_get(c8b_ctx* ctx)
     return e;
 }
 struct StageTimer {
-    c8b_ctx* ctx; int k; cudaEvent_t a = nullptr, b = nullptr;
-    StageTimer(c8b_ctx* c, int kk) : ctx(c), k(kk)
+    c8b_ctx* ctx; int k; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(c8b_ctx* c, int kk, cudaStream_t ss = nullptr) : ctx(c), k(kk), s(ss ? ss : c->st)
     {
-        if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, ctx->st); }
+        if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, s); }
     }
     ~StageTimer()
     {
-        if (ctx->timing) { cudaEventRecord(b, ctx->st); ctx->pending.push_back({ k, a, b }); }
+        if (ctx->timing) { cudaEventRecord(b, s); ctx->pending.push_back({ k, a, b }); }
     }
 };
 static void timing_collect(c8b_ctx* ctx)
@@ -126,6 +129,12 @@ int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stCopy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stVit, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+        e = cudaEventCreateWithFlags(&ctx->evFront[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evVit[k], cudaEventDisableTiming);
+    }
+    ctx->overlap = ctx->cfg.no_overlap == 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->numSM, cudaDevAttrMultiProcessorCount, ctx->device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_lut, sizeof(c8b_lut));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 64);
@@ -138,10 +147,12 @@ void c8b_destroy(c8b_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->st);
+    cudaDeviceSynchronize();
     timing_collect(ctx);
     for (auto e : ctx->evPool) cudaEventDestroy(e);
-    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
+    for (int k = 0; k < 2; k++) { if (ctx->evFront[k]) cudaEventDestroy(ctx->evFront[k]); if (ctx->evVit[k]) cudaEventDestroy(ctx->evVit[k]); }
+    if (ctx->stVit) cudaStreamDestroy(ctx->stVit);
+    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
                        &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -158,6 +169,7 @@ int c8b_sync(c8b_ctx* ctx)
     if (!ctx) return C8B_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaStreamSynchronize(ctx->stVit));
     return C8B_OK;
 }
 
@@ -332,9 +344,16 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     EN(mask, (size_t)n * maskStride * sizeof(uint32_t));
     EN(chan, ns * 64 * sizeof(float2));
     EN(hinv, ns * 64 * sizeof(float2));
-    EN(llr, ns * llrStride * sizeof(float));
+    const int par = (int)(ctx->chunkSeq++ & 1u);
+    const bool ov = ctx->overlap;
+    DevBuf& llrBuf = (ov && par) ? ctx->llrB : ctx->llr;       // double-buffered when the Viterbi runs on its own stream
+    {
+        int r_ = ensure(ctx, llrBuf, ns * llrStride * sizeof(float));
+        if (r_) return r_;
+    }
     int r = ensure_surv(ctx);
     if (r) return r;
+    if (ov) cudaStreamWaitEvent(ctx->st, ctx->evVit[par], 0);   // the Viterbi pass that last read this LLR buffer
     // iqShift: the device buffer holds the capture from sample iqShift on (host-staged chunks)
     const float2* iq = d_iq - iqShift;
     const float2* iq1 = d_iq1 ? d_iq1 - iqShift : nullptr;
@@ -360,20 +379,37 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
         const int maxSym = (int)(llr_stride_for(pl.maxLen) / 416);
-        c8b_launch_demod(ctx->d_lut, iq, d_off + b, n, maxf, maxSym, d_frames + (size_t)b * maxf, (const float2*)ctx->hinv.p, (float*)ctx->llr.p,
+        c8b_launch_demod(ctx->d_lut, iq, d_off + b, n, maxf, maxSym, d_frames + (size_t)b * maxf, (const float2*)ctx->hinv.p, (float*)llrBuf.p,
                          ctx->st);
         if (iq1)
             c8b_launch_demod2(ctx->d_lut, iq, iq1, d_off + b, n, maxf, maxSym, d_frames + (size_t)b * maxf, (const float2*)ctx->w2.p,
-                              (float*)ctx->llr.p, ctx->st);
+                              (float*)llrBuf.p, ctx->st);
+    }
+    cudaStream_t sv = ctx->st;
+    if (ov) {
+        sv = ctx->stVit;
+        cudaEventRecord(ctx->evFront[par], ctx->st);
+        cudaStreamWaitEvent(sv, ctx->evFront[par], 0);
     }
     {
-        StageTimer tm(ctx, C8B_K_VITERBI);
-        c8b_launch_viterbi(ctx->d_lut, d_frames + (size_t)b * maxf, (int)ns, (const float*)ctx->llr.p, (int64_t)ns * llrStride,
+        StageTimer tm(ctx, C8B_K_VITERBI, sv);
+        // with the front end of the next chunk co-resident, one CTA per SM less (registers / shared memory)
+        const int grid = ov ? ctx->numSM * 4 : c8b_viterbi_max_grid(ctx->numSM);
+        c8b_launch_viterbi(ctx->d_lut, d_frames + (size_t)b * maxf, (int)ns, (const float*)llrBuf.p, (int64_t)ns * llrStride,
                            (uint2*)ctx->surv.p, ctx->survWarps, d_pdu + (size_t)b * maxf * pdu_stride, pdu_stride, nullptr, 0, ctx->d_counter,
-                           c8b_viterbi_max_grid(ctx->numSM), ctx->st);
+                           grid, sv);
     }
+    if (ov) cudaEventRecord(ctx->evVit[par], sv);
     CK(cudaGetLastError());
     return C8B_OK;
+}
+
+// make the ctx stream wait for every Viterbi pass in flight (end of a batched call)
+static void join_viterbi(c8b_ctx* ctx)
+{
+    if (!ctx->overlap) return;
+    cudaStreamWaitEvent(ctx->st, ctx->evVit[0], 0);
+    cudaStreamWaitEvent(ctx->st, ctx->evVit[1], 0);
 }
 
 static int upload_items(c8b_ctx* ctx, const int64_t* off, const int32_t* len, int n)
@@ -405,6 +441,7 @@ int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* off, 
                       pdu_stride, 0);
         if (r) return r;
     }
+    join_viterbi(ctx);
     return C8B_OK;
 }
 
@@ -477,15 +514,17 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
         cudaStreamWaitEvent(ctx->st, copied[k], 0);
         rc = run_chunk(ctx, buf[k], (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, (c8b_frame*)ctx->frames.p,
                        (uint8_t*)ctx->pdu.p, pdu_stride, pl.base, buf1[k]);
-        cudaEventRecord(freed[k], ctx->st);
+        cudaEventRecord(freed[k], ctx->st);                       // the front end is the last reader of the staged IQ
         if (rc == C8B_OK) {
+            cudaStream_t sr = ctx->overlap ? ctx->stVit : ctx->st; // results follow the Viterbi pass of this chunk
             cudaMemcpyAsync(frames + b * maxf, (c8b_frame*)ctx->frames.p + b * maxf, (size_t)(e - b) * maxf * sizeof(c8b_frame),
-                            cudaMemcpyDeviceToHost, ctx->st);
+                            cudaMemcpyDeviceToHost, sr);
             cudaMemcpyAsync(pdu + b * maxf * pdu_stride, (uint8_t*)ctx->pdu.p + b * maxf * pdu_stride, (size_t)(e - b) * maxf * pdu_stride,
-                            cudaMemcpyDeviceToHost, ctx->st);
+                            cudaMemcpyDeviceToHost, sr);
         }
     }
     cudaStreamSynchronize(ctx->stCopy);
+    cudaStreamSynchronize(ctx->stVit);
     cudaError_t e2 = cudaStreamSynchronize(ctx->st);
     for (int k = 0; k < 2; k++) { cudaEventDestroy(copied[k]); cudaEventDestroy(freed[k]); }
     if (rc) return rc;

@@ -107,7 +107,9 @@ typedef struct c8b_cfg {
     int32_t max_frames;      /* frame records per item (0 -> 1); a long capture is one item with many */
     int32_t mupos;           /* demod(mupos, mugid) ctor args (lib/demod_impl.cc:28-32)           */
     int32_t mugid;
-    int32_t reserved[8];
+    int32_t no_overlap;      /* 1: run every kernel on one stream (stage timing); 0: the decode kernel of chunk k overlaps
+                                the front end of chunk k+1 on a second stream                            */
+    int32_t reserved[7];
 } c8b_cfg;
 
 typedef struct c8b_ctx c8b_ctx;
