@@ -89,12 +89,20 @@ k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const 
     uint32_t bits = 0;
     if (outp) {
         float ac[PR];
+        // 16-byte reads of the lagged s16 values (scalar reads at an 8-word thread stride would be 8-way bank conflicts)
+        float re0[PR], re1[PR], re2[PR], im0[PR], im1[PR], im2[PR], pw0[PR], pw1[PR], pw2[PR], pw3[PR];
+        auto ld8 = [&](const float* base, int q, float* dst) {
+            const float4 a = *reinterpret_cast<const float4*>(base + q), b = *reinterpret_cast<const float4*>(base + q + 4);
+            dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+        };
+        ld8(s16re, q0 - 32, re2); ld8(s16re, q0 - 16, re1); ld8(s16re, q0, re0);
+        ld8(s16im, q0 - 32, im2); ld8(s16im, q0 - 16, im1); ld8(s16im, q0, im0);
+        ld8(s16pw, q0 - 48, pw3); ld8(s16pw, q0 - 32, pw2); ld8(s16pw, q0 - 16, pw1); ld8(s16pw, q0, pw0);
 #pragma unroll
         for (int k = 0; k < PR; k++) {
-            const int q = q0 + k;
-            const float cr = __fadd_rn(__fadd_rn(s16re[q - 32], s16re[q - 16]), s16re[q]);
-            const float ci = __fadd_rn(__fadd_rn(s16im[q - 32], s16im[q - 16]), s16im[q]);
-            const float pw = __fadd_rn(__fadd_rn(s16pw[q - 48], s16pw[q - 32]), __fadd_rn(s16pw[q - 16], s16pw[q]));
+            const float cr = __fadd_rn(__fadd_rn(re2[k], re1[k]), re0[k]);
+            const float ci = __fadd_rn(__fadd_rn(im2[k], im1[k]), im0[k]);
+            const float pw = __fadd_rn(__fadd_rn(pw3[k], pw2[k]), __fadd_rn(pw1[k], pw0[k]));
             const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));   // complex_to_mag
             ac[k] = __fdiv_rn(mag, pw);                                                         // divide_ff
             if (ac[k] > 0.3f && i0 + k < n) bits |= 1u << k;                                    // lib/trigger_impl.cc:79
