@@ -12,117 +12,79 @@ namespace {
 
 using c8b::cf;
 
+constexpr int PT = 1024;           // outputs per CTA
+constexpr int PH = 64;             // history of the 64-sample power window
 constexpr int PTHREADS = 256;
-constexpr int PR = 8;                         // consecutive samples per thread
-constexpr int PS16 = PTHREADS * PR;           // s16 values per CTA (2048)
-constexpr int PHALO = 64;                     // s16 values kept only as history (48 used, padded to a multiple of PR)
-constexpr int PT = PS16 - PHALO;              // outputs per CTA (1984)
-constexpr int PXN = PS16 + 32;                // x tile: the first s16 needs 31 samples of history (15 products + 16 delay)
-static_assert(PT % 32 == 0 && PHALO % 32 == 0 && PHALO >= 48, "bitmap words must align with CTA tiles");
 
-// x tile in shared memory with 2 pad slots after every 8 complex samples: a thread's 16-byte reads start 20 words apart,
-// which spreads the 8 lanes of a quarter-warp over all 32 banks
-__device__ __forceinline__ int xpos(int i) { return i + 2 * (i >> 3); }
-
-struct f3 { float x, y, z; };
-__device__ __forceinline__ f3 add3(f3 a, f3 b) { return { __fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z) }; }
-
-// The moving sums are evaluated as a fixed sliding tree so every output is a pure function of the 64 (80) samples
-// before it, independent of tiling: s2[n]=v[n-1]+v[n]; s4[n]=s2[n-2]+s2[n]; s8; s16;
+// The moving sums are evaluated as a fixed sliding tree so every output is a pure function of the 64
+// (80) samples before it, independent of tiling: s2[n]=v[n-1]+v[n]; s4[n]=s2[n-2]+s2[n]; s8; s16;
 // sum48[n]=(s16[n-32]+s16[n-16])+s16[n]; sum64[n]=(s16[n-48]+s16[n-32])+(s16[n-16]+s16[n]).
-// A thread forms the 23 products its 8 consecutive s16 need and runs the tree in registers (no barrier per level);
-// only s16 goes through shared memory for the 16/32/48-sample lags.
 __global__ void __launch_bounds__(PTHREADS)
 k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int64_t outBase,
           float* __restrict__ preac, float2* __restrict__ preconj, uint32_t* __restrict__ mask, int maskStride)
 {
-    __shared__ __align__(16) float2 xs[PXN + 2 * (PXN / 8) + 8];
-    __shared__ __align__(16) float s16re[PS16], s16im[PS16], s16pw[PS16];
+    __shared__ float4 s[PT + PH];                   // (re, im, |x|^2, -) of v at item index t0 - 64 + j
     const int item = blockIdx.y;
     const int n = len[item];
-    const int t0 = blockIdx.x * PT;                 // first output of this CTA
+    const int t0 = blockIdx.x * PT;
     if (t0 >= n) return;
     const float2* __restrict__ x = iq + off[item];
     const int64_t ob = off[item] - outBase;
-    const int s0 = t0 - PHALO;                      // item index of s16 slot 0
-    const int x0 = s0 - 32;                         // item index of x tile slot 0 (multiple of 8 relative to s0)
-    for (int j = threadIdx.x; j < PXN; j += PTHREADS) {
-        const int i = x0 + j;
-        xs[xpos(j)] = (i >= 0 && i < n) ? x[i] : make_float2(0.f, 0.f);
+    // products for j in [0, PT+64): index i = t0 - 64 + j
+    for (int j = threadIdx.x; j < PT + PH; j += PTHREADS) {
+        const int i = t0 - PH + j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= 0 && i < n) {
+            const float2 c = x[i];
+            v.z = __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y));          // complex_to_mag_squared
+            if (i >= 16) {
+                const float2 d = x[i - 16];                                     // delay(16), in0 * conj(in1)
+                v.x = __fadd_rn(__fmul_rn(d.x, c.x), __fmul_rn(d.y, c.y));
+                v.y = __fsub_rn(__fmul_rn(d.y, c.x), __fmul_rn(d.x, c.y));
+            }
+        }
+        s[j] = v;
     }
     __syncthreads();
-    const int q0 = threadIdx.x * PR;                // this thread's s16 slots q0 .. q0+7  <->  item index s0 + q0 + k
-    {
-        // samples x[s0+q0-31 .. s0+q0+7] = tile slots q0+1 .. q0+39; load slots q0 .. q0+39 as 20 aligned pairs
-        float2 xv[40];
+    constexpr int PER = (PT + PH + PTHREADS - 1) / PTHREADS;
 #pragma unroll
-        for (int k = 0; k < 40; k += 2) {
-            const float4 t = *reinterpret_cast<const float4*>(&xs[xpos(q0 + k)]);
-            xv[k] = make_float2(t.x, t.y); xv[k + 1] = make_float2(t.z, t.w);
+    for (int lag = 1; lag < 16; lag <<= 1) {
+        float4 r[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int j = threadIdx.x + q * PTHREADS;
+            if (j < PT + PH) {
+                const float4 b = s[j];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j >= lag) a = s[j - lag];
+                r[q] = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), 0.f);
+            }
         }
-        f3 v[23];                                   // v[m] <-> item index s0 + q0 - 15 + m  (tile slot q0 + 17 + m)
+        __syncthreads();
 #pragma unroll
-        for (int m = 0; m < 23; m++) {
-            const float2 c = xv[17 + m], d = xv[1 + m];     // x[i], x[i-16]   (delay(16), in0 * conj(in1))
-            v[m].x = __fadd_rn(__fmul_rn(d.x, c.x), __fmul_rn(d.y, c.y));
-            v[m].y = __fsub_rn(__fmul_rn(d.y, c.x), __fmul_rn(d.x, c.y));
-            v[m].z = __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y));       // complex_to_mag_squared
+        for (int q = 0; q < PER; q++) {
+            const int j = threadIdx.x + q * PTHREADS;
+            if (j < PT + PH) s[j] = r[q];
         }
-#pragma unroll
-        for (int m = 22; m >= 1; m--) v[m] = add3(v[m - 1], v[m]);              // s2 at m >= 1
-#pragma unroll
-        for (int m = 22; m >= 3; m--) v[m] = add3(v[m - 2], v[m]);              // s4 at m >= 3
-#pragma unroll
-        for (int m = 22; m >= 7; m--) v[m] = add3(v[m - 4], v[m]);              // s8 at m >= 7
-#pragma unroll
-        for (int m = 22; m >= 15; m--) v[m] = add3(v[m - 8], v[m]);             // s16 at m >= 15  <->  slots q0 .. q0+7
-        *reinterpret_cast<float4*>(&s16re[q0]) = make_float4(v[15].x, v[16].x, v[17].x, v[18].x);
-        *reinterpret_cast<float4*>(&s16re[q0 + 4]) = make_float4(v[19].x, v[20].x, v[21].x, v[22].x);
-        *reinterpret_cast<float4*>(&s16im[q0]) = make_float4(v[15].y, v[16].y, v[17].y, v[18].y);
-        *reinterpret_cast<float4*>(&s16im[q0 + 4]) = make_float4(v[19].y, v[20].y, v[21].y, v[22].y);
-        *reinterpret_cast<float4*>(&s16pw[q0]) = make_float4(v[15].z, v[16].z, v[17].z, v[18].z);
-        *reinterpret_cast<float4*>(&s16pw[q0 + 4]) = make_float4(v[19].z, v[20].z, v[21].z, v[22].z);
+        __syncthreads();
     }
-    __syncthreads();
-    const int i0 = s0 + q0;                         // first output index of this thread (multiple of 8)
-    const bool outp = q0 >= PHALO && i0 < n;        // history-only slots and slots past the item produce nothing
-    uint32_t bits = 0;
-    if (outp) {
-        float ac[PR];
-        // 16-byte reads of the lagged s16 values (scalar reads at an 8-word thread stride would be 8-way bank conflicts)
-        float re0[PR], re1[PR], re2[PR], im0[PR], im1[PR], im2[PR], pw0[PR], pw1[PR], pw2[PR], pw3[PR];
-        auto ld8 = [&](const float* base, int q, float* dst) {
-            const float4 a = *reinterpret_cast<const float4*>(base + q), b = *reinterpret_cast<const float4*>(base + q + 4);
-            dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
-        };
-        ld8(s16re, q0 - 32, re2); ld8(s16re, q0 - 16, re1); ld8(s16re, q0, re0);
-        ld8(s16im, q0 - 32, im2); ld8(s16im, q0 - 16, im1); ld8(s16im, q0, im0);
-        ld8(s16pw, q0 - 48, pw3); ld8(s16pw, q0 - 32, pw2); ld8(s16pw, q0 - 16, pw1); ld8(s16pw, q0, pw0);
-#pragma unroll
-        for (int k = 0; k < PR; k++) {
-            const float cr = __fadd_rn(__fadd_rn(re2[k], re1[k]), re0[k]);
-            const float ci = __fadd_rn(__fadd_rn(im2[k], im1[k]), im0[k]);
-            const float pw = __fadd_rn(__fadd_rn(pw3[k], pw2[k]), __fadd_rn(pw1[k], pw0[k]));
-            const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));   // complex_to_mag
-            ac[k] = __fdiv_rn(mag, pw);                                                         // divide_ff
-            if (ac[k] > 0.3f && i0 + k < n) bits |= 1u << k;                                    // lib/trigger_impl.cc:79
-            if (preconj && i0 + k < n) preconj[ob + i0 + k] = make_float2(cr, ci);
+    // s[j] = s16 at index t0-64+j (exact for j >= 15; outputs use j >= 16)
+    for (int k = threadIdx.x; k < PT; k += PTHREADS) {
+        const int i = t0 + k;
+        if (i >= n) break;
+        const int j = k + PH;
+        const float4 a0 = s[j], a1 = s[j - 16], a2 = s[j - 32], a3 = s[j - 48];
+        const float cr = __fadd_rn(__fadd_rn(a2.x, a1.x), a0.x), ci = __fadd_rn(__fadd_rn(a2.y, a1.y), a0.y);
+        const float pw = __fadd_rn(__fadd_rn(a3.z, a2.z), __fadd_rn(a1.z, a0.z));
+        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));   // complex_to_mag
+        const float ac = __fdiv_rn(mag, pw);                                                // divide_ff
+        preac[ob + i] = ac;
+        if (preconj) preconj[ob + i] = make_float2(cr, ci);
+        if (mask) {                                        // threshold bitmap for the trigger scan (lib/trigger_impl.cc:79)
+            // i is a multiple of 32 at lane 0 (t0 and k are); lanes past the end of the item left the loop above
+            const uint32_t m = __ballot_sync(__activemask(), ac > 0.3f);
+            if ((threadIdx.x & 31) == 0) mask[(size_t)item * maskStride + (i >> 5)] = m;
         }
-        if (i0 + PR <= n && ((ob + i0) & 3) == 0) {
-            *reinterpret_cast<float4*>(&preac[ob + i0]) = make_float4(ac[0], ac[1], ac[2], ac[3]);
-            *reinterpret_cast<float4*>(&preac[ob + i0 + 4]) = make_float4(ac[4], ac[5], ac[6], ac[7]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < PR; k++) if (i0 + k < n) preac[ob + i0 + k] = ac[k];
-        }
-    }
-    if (mask) {
-        // threshold bitmap for the trigger scan: s0 is a multiple of 32 (PT and PHALO are), so 4 neighbouring lanes
-        // hold the 4 bytes of one word
-        uint32_t w = bits << (8 * (threadIdx.x & 3));
-        w |= __shfl_xor_sync(0xffffffffu, w, 1);
-        w |= __shfl_xor_sync(0xffffffffu, w, 2);
-        if ((threadIdx.x & 3) == 0 && outp) mask[(size_t)item * maskStride + (i0 >> 5)] = w;
     }
 }
 
