@@ -38,11 +38,14 @@ constexpr int GS = 30;                         // steps per decision group (one 
 constexpr int NG = CH / GS;                    // 5 groups per chunk
 constexpr int NW = C8B_VIT_WARPS;
 constexpr int NLD = (CH + 31) / 32;            // table rows each lane fills per chunk
-constexpr int MAXG = (C8B_DECODE_T_MAX + GS - 1) / GS;   // 1093 groups in the longest packet
 constexpr int WORDS = (C8B_DECODE_T_MAX + 31) / 32 + 8;  // decoded-bit words per warp (+ slack)
 static_assert(CH % 5 == 0 && GS % 5 == 0 && CH % GS == 0, "phases must align with groups");
 static_assert(((C8B_DECODE_T_MAX + CH - 1) / CH) * NG * 32 <= C8B_VIT_TPAD, "survivor scratch too small");
 
+#ifndef C8B_VIT_UNROLL
+#define C8B_VIT_UNROLL 6
+#endif
+constexpr int VUNROLL = C8B_VIT_UNROLL;          // 5-step iterations unrolled in the forward loop (6 = a whole 30-step group)
 constexpr int TBW = 4;                         // traceback warm-up, in 30-step groups, before a lane's own segment
 constexpr int U_BYTES = 9600;                  // union area: forward tables | traceback staging | decoded words
 constexpr int ROW = 68;                        // words per lane row in the traceback staging (64 + pad: conflict-free 16-byte stores)
@@ -319,24 +322,24 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
 #pragma unroll 1
                 for (int g = 0; g < NG; g++) {
                     uint32_t haLo = 0, haHi = 0, hbLo = 0, hbHi = 0;
-#pragma unroll
-                    for (int i5 = 0; i5 < GS / 5; i5++) {           // 30 steps, all shared-memory offsets immediate
-                        const int o = i5 * 20, ob = o + CH * 4;     // frame B's table sits CH steps (x 4 classes) further
+#pragma unroll VUNROLL
+                    for (int i5 = 0; i5 < GS / 5; i5++) {           // 30 steps per group, 5 layout phases per iteration
+                        constexpr int ob = CH * 4;                  // frame B's table sits CH steps (x 4 classes) further
                         float2 ab;
-                        ab = p0[o];  acs_step<0>(xa0, xa1, ab.x, ab.y, amask[0], haLo, haHi);
+                        ab = p0[0];  acs_step<0>(xa0, xa1, ab.x, ab.y, amask[0], haLo, haHi);
                         ab = p0[ob]; acs_step<0>(xb0, xb1, ab.x, ab.y, amask[0], hbLo, hbHi);
-                        ab = p1[o];  acs_step<1>(xa0, xa1, ab.x, ab.y, amask[1], haLo, haHi);
+                        ab = p1[0];  acs_step<1>(xa0, xa1, ab.x, ab.y, amask[1], haLo, haHi);
                         ab = p1[ob]; acs_step<1>(xb0, xb1, ab.x, ab.y, amask[1], hbLo, hbHi);
-                        ab = p2[o];  acs_step<2>(xa0, xa1, ab.x, ab.y, amask[2], haLo, haHi);
+                        ab = p2[0];  acs_step<2>(xa0, xa1, ab.x, ab.y, amask[2], haLo, haHi);
                         ab = p2[ob]; acs_step<2>(xb0, xb1, ab.x, ab.y, amask[2], hbLo, hbHi);
-                        ab = p3[o];  acs_step<3>(xa0, xa1, ab.x, ab.y, amask[3], haLo, haHi);
+                        ab = p3[0];  acs_step<3>(xa0, xa1, ab.x, ab.y, amask[3], haLo, haHi);
                         ab = p3[ob]; acs_step<3>(xb0, xb1, ab.x, ab.y, amask[3], hbLo, hbHi);
-                        ab = p4[o];  acs_step<4>(xa0, xa1, ab.x, ab.y, amask[4], haLo, haHi);
+                        ab = p4[0];  acs_step<4>(xa0, xa1, ab.x, ab.y, amask[4], haLo, haHi);
                         ab = p4[ob]; acs_step<4>(xb0, xb1, ab.x, ab.y, amask[4], hbLo, hbHi);
+                        p0 += 20; p1 += 20; p2 += 20; p3 += 20; p4 += 20;
                     }
                     if (stA) sgA[g * 32] = make_uint2(haLo, haHi);
                     if (stB) sgB[g * 32] = make_uint2(hbLo, hbHi);
-                    p0 += GS * 4; p1 += GS * 4; p2 += GS * 4; p3 += GS * 4; p4 += GS * 4;
                 }
                 __syncwarp();
                 if (more) {
