@@ -25,7 +25,7 @@ struct c8b_ctx {
     bool lutLoaded = false;
     unsigned* d_counter = nullptr;
     // scratch (grown on demand)
-    DevBuf iq, iq1, mask, llrB, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
+    DevBuf iq, iq1, mask, llrB, tp, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
     int survWarps = 0;
     // timing
     bool timing = false;
@@ -152,7 +152,7 @@ void c8b_destroy(c8b_ctx* ctx)
     for (auto e : ctx->evPool) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) { if (ctx->evFront[k]) cudaEventDestroy(ctx->evFront[k]); if (ctx->evVit[k]) cudaEventDestroy(ctx->evVit[k]); }
     if (ctx->stVit) cudaStreamDestroy(ctx->stVit);
-    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
+    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->tp, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
                        &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -246,6 +246,7 @@ int c8b_timing_read(c8b_ctx* ctx, double ms[C8B_K_COUNT], int64_t launches[C8B_K
 }
 
 // ---- decode stage ---------------------------------------------------------------------------------
+
 static int ensure_surv(c8b_ctx* ctx)
 {
     int grid = c8b_viterbi_max_grid(ctx->numSM);
@@ -256,15 +257,36 @@ static int ensure_surv(c8b_ctx* ctx)
     return C8B_OK;
 }
 
+// Which decode kernel: one thread per frame (throughput, large batches) or one warp per frame pair (latency).
+static bool use_thread_per_frame(const c8b_ctx* ctx, int nframes)
+{
+    if (ctx->cfg.decode_mode == 1) return false;
+    if (ctx->cfg.decode_mode == 2) return true;
+    return nframes >= 4096;
+}
+
+static int launch_decode(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* d_llr, int64_t nllr, uint8_t* d_pdu, int64_t pdu_stride,
+                         uint8_t* d_scram, int64_t scram_stride, int grid, cudaStream_t st)
+{
+    if (use_thread_per_frame(ctx, n)) {
+        EN(tp, c8b_viterbi_tp_scratch_bytes(ctx->numSM));
+        c8b_launch_viterbi_tp(ctx->d_lut, d_frames, n, d_llr, nllr, ctx->tp.p, ctx->numSM, d_pdu, pdu_stride, d_scram, scram_stride, st);
+    } else {
+        int r = ensure_surv(ctx);
+        if (r) return r;
+        c8b_launch_viterbi(ctx->d_lut, d_frames, n, d_llr, nllr, (uint2*)ctx->surv.p, ctx->survWarps, d_pdu, pdu_stride, d_scram, scram_stride,
+                           ctx->d_counter, grid, st);
+    }
+    return C8B_OK;
+}
+
 // device-resident decode of d_frames[0..n): LLR arena d_llr (nllr floats), PDUs to d_pdu
 static int decode_dev(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* d_llr, int64_t nllr, uint8_t* d_pdu,
                       int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride)
 {
-    int r = ensure_surv(ctx);
-    if (r) return r;
     StageTimer tm(ctx, C8B_K_VITERBI);
-    c8b_launch_viterbi(ctx->d_lut, d_frames, n, d_llr, nllr, (uint2*)ctx->surv.p, ctx->survWarps, d_pdu, pdu_stride, d_scram,
-                       scram_stride, ctx->d_counter, c8b_viterbi_max_grid(ctx->numSM), ctx->st);
+    int r = launch_decode(ctx, d_frames, n, d_llr, nllr, d_pdu, pdu_stride, d_scram, scram_stride, c8b_viterbi_max_grid(ctx->numSM), ctx->st);
+    if (r) return r;
     CK(cudaGetLastError());
     return C8B_OK;
 }
@@ -351,8 +373,7 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
         int r_ = ensure(ctx, llrBuf, ns * llrStride * sizeof(float));
         if (r_) return r_;
     }
-    int r = ensure_surv(ctx);
-    if (r) return r;
+    int r = C8B_OK;
     if (ov) cudaStreamWaitEvent(ctx->st, ctx->evVit[par], 0);   // the Viterbi pass that last read this LLR buffer
     // iqShift: the device buffer holds the capture from sample iqShift on (host-staged chunks)
     const float2* iq = d_iq - iqShift;
@@ -395,9 +416,9 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
         StageTimer tm(ctx, C8B_K_VITERBI, sv);
         // with the front end of the next chunk co-resident, one CTA per SM less (registers / shared memory)
         const int grid = ov ? ctx->numSM * 4 : c8b_viterbi_max_grid(ctx->numSM);
-        c8b_launch_viterbi(ctx->d_lut, d_frames + (size_t)b * maxf, (int)ns, (const float*)llrBuf.p, (int64_t)ns * llrStride,
-                           (uint2*)ctx->surv.p, ctx->survWarps, d_pdu + (size_t)b * maxf * pdu_stride, pdu_stride, nullptr, 0, ctx->d_counter,
-                           grid, sv);
+        r = launch_decode(ctx, d_frames + (size_t)b * maxf, (int)ns, (const float*)llrBuf.p, (int64_t)ns * llrStride,
+                          d_pdu + (size_t)b * maxf * pdu_stride, pdu_stride, nullptr, 0, grid, sv);
+        if (r) return r;
     }
     if (ov) cudaEventRecord(ctx->evVit[par], sv);
     CK(cudaGetLastError());

@@ -109,7 +109,9 @@ typedef struct c8b_cfg {
     int32_t mugid;
     int32_t no_overlap;      /* 1: run every kernel on one stream (stage timing); 0: the decode kernel of chunk k overlaps
                                 the front end of chunk k+1 on a second stream                            */
-    int32_t reserved[7];
+    int32_t decode_mode;     /* 0: pick by batch size; 1: one warp per frame pair (k_viterbi, low latency);
+                                2: one thread per frame (k_viterbi_tp, throughput)                        */
+    int32_t reserved[6];
 } c8b_cfg;
 
 typedef struct c8b_ctx c8b_ctx;

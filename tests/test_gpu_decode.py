@@ -9,10 +9,11 @@ from __graft_entry__ import load_pkg
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def rx():
+@pytest.fixture(scope="module", params=[1, 2], ids=["warp_per_frame", "thread_per_frame"])
+def rx(request):
+    """every decode test runs against both kernels: k_viterbi (decode_mode 1) and k_viterbi_tp (decode_mode 2)"""
     pkg = load_pkg()
-    r = pkg.Receiver(device=0)
+    r = pkg.Receiver(device=0, decode_mode=request.param)
     yield r
     r.close()
 
