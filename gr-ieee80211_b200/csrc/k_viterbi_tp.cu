@@ -168,23 +168,32 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         if (Tmax == 0) continue;                                     // warp-uniform
         const int nch = (Tmax + CS - 1) / CS;
 
-        // stage chunk c of all 32 frames of the warp into pairs[warp][buf]
+        // stage chunk c of all 32 frames of the warp into pairs[warp][buf]; loads of 8 frames are in flight together
+        int i0s = -1, i1s = -1;                                      // this lane's step (= lane) in chunk-relative soft-bit indices, per cr
         auto stage = [&](int c, int buf) {
             float2* __restrict__ dst = pairs[warp][buf];
-            for (int j = 0; j < 32; j++) {
-                const int crj = __shfl_sync(0xffffffffu, cr, j);
-                const int limj = __shfl_sync(0xffffffffu, lim, j);
-                const int nrawj = __shfl_sync(0xffffffffu, nraw, j);
-                const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)llr, j);
-                const float* __restrict__ lj = reinterpret_cast<const float*>(pj);
+#pragma unroll 1
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int j = j8 + u;
+                    const int crj = __shfl_sync(0xffffffffu, cr, j);
+                    const int limj = __shfl_sync(0xffffffffu, lim, j);
+                    const int nrawj = __shfl_sync(0xffffffffu, nraw, j);
+                    const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)llr, j);
+                    const float* __restrict__ lj = reinterpret_cast<const float*>(pj);
+                    v[u] = make_float2(0.0f, 0.0f);
+                    if (lane < CS) {
+                        depunc(crj, lane, i0s, i1s);
+                        const int base = c * nrawj;
+                        if (i0s >= 0 && base + i0s < limj) v[u].x = __ldg(lj + base + i0s);
+                        if (i1s >= 0 && base + i1s < limj) v[u].y = __ldg(lj + base + i1s);
+                    }
+                }
                 if (lane < CS) {
-                    int i0, i1;
-                    depunc(crj, lane, i0, i1);
-                    const int base = c * nrawj;
-                    float2 v;
-                    v.x = (i0 >= 0 && base + i0 < limj) ? __ldg(lj + base + i0) : 0.0f;
-                    v.y = (i1 >= 0 && base + i1 < limj) ? __ldg(lj + base + i1) : 0.0f;
-                    dst[j * ROWF2 + lane] = v;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) dst[(j8 + u) * ROWF2 + lane] = v[u];
                 }
             }
         };
@@ -213,13 +222,20 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
         {
             uint32_t s = 0, acc = 0;
-            for (int t = Tmax - 1; t >= 0; t--) {
-                if (t < T) {
-                    const uint2 w = surv[(size_t)t * TPB];
-                    acc = (acc << 1) | (s >> 5);                     // decoded bit of step t = input bit of the state entered
-                    const uint32_t d = ((s & 32u ? w.y : w.x) >> (s & 31u)) & 1u;
-                    s = ((s & 31u) << 1) | d;
-                    if ((t & 31) == 0) { words[(size_t)(t >> 5) * TPB] = acc; acc = 0; }
+            constexpr int TB = 16;                                   // decision words fetched ahead of the dependent walk
+            for (int tb = ((Tmax - 1) / TB) * TB; tb >= 0; tb -= TB) {
+                uint2 w[TB];
+#pragma unroll
+                for (int k = 0; k < TB; k++) w[k] = (tb + k < T) ? surv[(size_t)(tb + k) * TPB] : make_uint2(0u, 0u);
+#pragma unroll
+                for (int k = TB - 1; k >= 0; k--) {
+                    const int t = tb + k;
+                    if (t < T) {
+                        acc = (acc << 1) | (s >> 5);                 // decoded bit of step t = input bit of the state entered
+                        const uint32_t d = ((s & 32u ? w[k].y : w[k].x) >> (s & 31u)) & 1u;
+                        s = ((s & 31u) << 1) | d;
+                        if ((t & 31) == 0) { words[(size_t)(t >> 5) * TPB] = acc; acc = 0; }
+                    }
                 }
             }
         }
