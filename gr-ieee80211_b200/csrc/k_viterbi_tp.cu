@@ -108,10 +108,21 @@ __device__ __forceinline__ uint32_t get_byte(const uint32_t* __restrict__ words,
     return (words[(size_t)(i >> 2) * TPB] >> (8 * (i & 3))) & 0xffu;
 }
 
+// CRC-32 (boost::crc_32_type, lib/decode_impl.h:84) over bytes [start, start+n) of the thread's word column
 __device__ uint32_t crc32_words(const uint32_t* __restrict__ tab, const uint32_t* __restrict__ words, int start, int n)
 {
     uint32_t c = 0xffffffffu;
-    for (int i = 0; i < n; i++) c = tab[(c ^ get_byte(words, start + i)) & 0xff] ^ (c >> 8);
+    int i = start;
+    const int end = start + n;
+    for (; i < end && (i & 3); i++) c = tab[(c ^ get_byte(words, i)) & 0xff] ^ (c >> 8);
+    for (; i + 4 <= end; i += 4) {
+        const uint32_t w = words[(size_t)(i >> 2) * TPB];
+        c = tab[(c ^ w) & 0xff] ^ (c >> 8);
+        c = tab[(c ^ (w >> 8)) & 0xff] ^ (c >> 8);
+        c = tab[(c ^ (w >> 16)) & 0xff] ^ (c >> 8);
+        c = tab[(c ^ (w >> 24)) & 0xff] ^ (c >> 8);
+    }
+    for (; i < end; i++) c = tab[(c ^ get_byte(words, i)) & 0xff] ^ (c >> 8);
     return ~c;
 }
 
@@ -123,7 +134,15 @@ __device__ void emit_record_t(uint8_t* __restrict__ out, int& w, int cap, int& n
     if (w + rec > cap) return;
     uint8_t* o = out + w;
     o[0] = (uint8_t)fmt; o[1] = (uint8_t)(lenField & 255); o[2] = (uint8_t)(lenField >> 8);
-    for (int i = 0; i < nbody; i++) o[3 + i] = (uint8_t)get_byte(words, start + i);
+    int i = 0;
+    // bytes until the destination is word aligned, then 4 bytes per store (source words funnel-shifted into place)
+    for (; i < nbody && (((uintptr_t)(o + 3 + i)) & 3); i++) o[3 + i] = (uint8_t)get_byte(words, start + i);
+    for (; i + 4 <= nbody; i += 4) {
+        const int k = start + i;
+        const uint32_t w0 = words[(size_t)(k >> 2) * TPB], w1 = words[(size_t)((k >> 2) + 1) * TPB];
+        *reinterpret_cast<uint32_t*>(o + 3 + i) = __funnelshift_r(w0, w1, 8 * (k & 3));
+    }
+    for (; i < nbody; i++) o[3 + i] = (uint8_t)get_byte(words, start + i);
     o[3 + nbody] = (uint8_t)mcs;
     w += rec;
     npdu++;
@@ -168,35 +187,36 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         if (Tmax == 0) continue;                                     // warp-uniform
         const int nch = (Tmax + CS - 1) / CS;
 
-        // stage chunk c of all 32 frames of the warp into pairs[warp][buf]; loads of 8 frames are in flight together
-        int i0s = -1, i1s = -1;                                      // this lane's step (= lane) in chunk-relative soft-bit indices, per cr
+        // stage chunk c of all 32 frames of the warp into pairs[warp][buf] with cp.async (LDGSTS): the copies of the next
+        // chunk run under the butterflies of the current one, no registers are held; a punctured or past-the-end
+        // position is a zero-fill copy (src-size 0)
+        uint32_t relv[4];                                            // this lane's step (= lane) per code rate: i0 | i1 << 16, 0xffff = punctured
+#pragma unroll
+        for (int q = 0; q < 4; q++) { int a0, a1; depunc(q, lane < CS ? lane : 0, a0, a1); relv[q] = (uint32_t)(a0 & 0xffff) | ((uint32_t)(a1 & 0xffff) << 16); }
         auto stage = [&](int c, int buf) {
             float2* __restrict__ dst = pairs[warp][buf];
-#pragma unroll 1
-            for (int j8 = 0; j8 < 32; j8 += 8) {
-                float2 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int j = j8 + u;
-                    const int crj = __shfl_sync(0xffffffffu, cr, j);
-                    const int limj = __shfl_sync(0xffffffffu, lim, j);
-                    const int nrawj = __shfl_sync(0xffffffffu, nraw, j);
-                    const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)llr, j);
-                    const float* __restrict__ lj = reinterpret_cast<const float*>(pj);
-                    v[u] = make_float2(0.0f, 0.0f);
-                    if (lane < CS) {
-                        depunc(crj, lane, i0s, i1s);
-                        const int base = c * nrawj;
-                        if (i0s >= 0 && base + i0s < limj) v[u].x = __ldg(lj + base + i0s);
-                        if (i1s >= 0 && base + i1s < limj) v[u].y = __ldg(lj + base + i1s);
-                    }
-                }
+#pragma unroll 4
+            for (int j = 0; j < 32; j++) {
+                const int crj = __shfl_sync(0xffffffffu, cr, j);
+                const int limj = __shfl_sync(0xffffffffu, lim, j);
+                const int nrawj = __shfl_sync(0xffffffffu, nraw, j);
+                const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)llr, j);
                 if (lane < CS) {
-#pragma unroll
-                    for (int u = 0; u < 8; u++) dst[(j8 + u) * ROWF2 + lane] = v[u];
+                    const uint32_t e = crj == 0 ? relv[0] : crj == 1 ? relv[1] : crj == 2 ? relv[2] : relv[3];
+                    const int r0 = (int)(e & 0xffffu), r1 = (int)(e >> 16);
+                    const int base = c * nrawj;
+                    const bool ok0 = r0 != 0xffff && base + r0 < limj, ok1 = r1 != 0xffff && base + r1 < limj;
+                    const float* lj = reinterpret_cast<const float*>(pj);
+                    const float* s0 = lj + (ok0 ? base + r0 : 0);
+                    const float* s1 = lj + (ok1 ? base + r1 : 0);
+                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + j * ROWF2 + lane);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(s0), "r"(ok0 ? 4 : 0) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4), "l"(s1), "r"(ok1 ? 4 : 0) : "memory");
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        auto stage_wait = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); };
 
         // ---------------- forward pass ----------------
         float m[64], n[64];
@@ -204,7 +224,7 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         for (int i = 0; i < 64; i++) m[i] = -1000000000000000.0f;     // lib/decode_impl.cc:171-176
         m[0] = 0.0f;
         stage(0, 0);
-        __syncwarp();
+        stage_wait();
         for (int c = 0; c < nch; c++) {
             if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
             const float2* __restrict__ row = pairs[warp][c & 1] + lane * ROWF2;
@@ -216,17 +236,19 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
                 const uint2 w1 = acs(n, m, row[s + 1]);
                 sv[(size_t)(s + 1) * TPB] = w1;
             }
-            __syncwarp();
+            stage_wait();
         }
 
         // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
         {
             uint32_t s = 0, acc = 0;
-            constexpr int TB = 16;                                   // decision words fetched ahead of the dependent walk
-            for (int tb = ((Tmax - 1) / TB) * TB; tb >= 0; tb -= TB) {
-                uint2 w[TB];
+            constexpr int TB = 16;                                   // decision words per block; the next block is in flight
+            uint2 wa[TB], wb[TB];
+            auto fetch = [&](uint2 (&w)[TB], int tb) {
 #pragma unroll
-                for (int k = 0; k < TB; k++) w[k] = (tb + k < T) ? surv[(size_t)(tb + k) * TPB] : make_uint2(0u, 0u);
+                for (int k = 0; k < TB; k++) w[k] = (tb >= 0 && tb + k < T) ? surv[(size_t)(tb + k) * TPB] : make_uint2(0u, 0u);
+            };
+            auto walk = [&](const uint2 (&w)[TB], int tb) {
 #pragma unroll
                 for (int k = TB - 1; k >= 0; k--) {
                     const int t = tb + k;
@@ -237,6 +259,14 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
                         if ((t & 31) == 0) { words[(size_t)(t >> 5) * TPB] = acc; acc = 0; }
                     }
                 }
+            };
+            int tb = ((Tmax - 1) / TB) * TB;
+            fetch(wa, tb);
+            for (; tb >= 0; tb -= 2 * TB) {
+                fetch(wb, tb - TB);
+                walk(wa, tb);
+                fetch(wa, tb - 2 * TB);
+                if (tb - TB >= 0) walk(wb, tb - TB);
             }
         }
         if (T <= 0) continue;                                        // (lanes without a frame are done; no warp-level sync below)
