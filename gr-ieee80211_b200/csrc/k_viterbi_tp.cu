@@ -156,7 +156,13 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
     extern __shared__ __align__(16) uint8_t dynsm[];
     float2 (*pairs)[2][32 * ROWF2] = reinterpret_cast<float2 (*)[2][32 * ROWF2]>(dynsm);   // [warp][buffer][frame row][step]
     uint32_t* crcTab = reinterpret_cast<uint32_t*>(dynsm + sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2);
+    uint32_t* relTab = crcTab + 256;                                 // [4 code rates][32]
     for (int i = threadIdx.x; i < 256; i += TPB) crcTab[i] = lut->crc32tab[i];
+    for (int i = threadIdx.x; i < 128; i += TPB) {
+        int a0, a1;
+        depunc(i >> 5, (i & 31) < CS ? (i & 31) : 0, a0, a1);
+        relTab[i] = (uint32_t)(a0 & 0xffff) | ((uint32_t)(a1 & 0xffff) << 16);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2* __restrict__ surv = survAll + (size_t)blockIdx.x * survPerCta + threadIdx.x;        // [t * TPB]
@@ -187,32 +193,22 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         if (Tmax == 0) continue;                                     // warp-uniform
         const int nch = (Tmax + CS - 1) / CS;
 
-        // stage chunk c of all 32 frames of the warp into pairs[warp][buf] with cp.async (LDGSTS): the copies of the next
-        // chunk run under the butterflies of the current one, no registers are held; a punctured or past-the-end
-        // position is a zero-fill copy (src-size 0)
-        uint32_t relv[4];                                            // this lane's step (= lane) per code rate: i0 | i1 << 16, 0xffff = punctured
-#pragma unroll
-        for (int q = 0; q < 4; q++) { int a0, a1; depunc(q, lane < CS ? lane : 0, a0, a1); relv[q] = (uint32_t)(a0 & 0xffff) | ((uint32_t)(a1 & 0xffff) << 16); }
+        // stage chunk c: every lane copies the (t0,t1) pairs of ITS frame into its shared-memory row with cp.async
+        // (LDGSTS): the copies of the next chunk run under the butterflies of the current one and hold no registers; a
+        // punctured or past-the-end position is a zero-fill copy (src-size 0).  relTab[cr][s] = chunk-relative soft-bit
+        // indices of step s (i0 | i1 << 16, 0xffff = punctured).
         auto stage = [&](int c, int buf) {
-            float2* __restrict__ dst = pairs[warp][buf];
-#pragma unroll 4
-            for (int j = 0; j < 32; j++) {
-                const int crj = __shfl_sync(0xffffffffu, cr, j);
-                const int limj = __shfl_sync(0xffffffffu, lim, j);
-                const int nrawj = __shfl_sync(0xffffffffu, nraw, j);
-                const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)llr, j);
-                if (lane < CS) {
-                    const uint32_t e = crj == 0 ? relv[0] : crj == 1 ? relv[1] : crj == 2 ? relv[2] : relv[3];
-                    const int r0 = (int)(e & 0xffffu), r1 = (int)(e >> 16);
-                    const int base = c * nrawj;
-                    const bool ok0 = r0 != 0xffff && base + r0 < limj, ok1 = r1 != 0xffff && base + r1 < limj;
-                    const float* lj = reinterpret_cast<const float*>(pj);
-                    const float* s0 = lj + (ok0 ? base + r0 : 0);
-                    const float* s1 = lj + (ok1 ? base + r1 : 0);
-                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + j * ROWF2 + lane);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(s0), "r"(ok0 ? 4 : 0) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4), "l"(s1), "r"(ok1 ? 4 : 0) : "memory");
-                }
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(pairs[warp][buf] + lane * ROWF2);
+            const float* __restrict__ lb = llr + (size_t)c * nraw;
+            const int rem = lim - c * nraw;                          // soft bits left from the start of this chunk
+            const uint32_t* __restrict__ rt = relTab + cr * 32;
+#pragma unroll
+            for (int sidx = 0; sidx < CS; sidx++) {
+                const uint32_t e = rt[sidx];
+                const int r0 = (int)(e & 0xffffu), r1 = (int)(e >> 16);
+                const bool ok0 = r0 != 0xffff && r0 < rem, ok1 = r1 != 0xffff && r1 < rem;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * sidx), "l"(lb + (ok0 ? r0 : 0)), "r"(ok0 ? 4 : 0) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * sidx + 4), "l"(lb + (ok1 ? r1 : 0)), "r"(ok1 ? 4 : 0) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -242,7 +238,7 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
         {
             uint32_t s = 0, acc = 0;
-            constexpr int TB = 16;                                   // decision words per block; the next block is in flight
+            constexpr int TB = 32;                                   // decision words per block; the next block is in flight
             uint2 wa[TB], wb[TB];
             auto fetch = [&](uint2 (&w)[TB], int tb) {
 #pragma unroll
@@ -366,7 +362,7 @@ void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframe
     if (grid > need) grid = need;
     uint2* surv = reinterpret_cast<uint2*>(d_scratch);
     uint32_t* words = reinterpret_cast<uint32_t*>(surv + (size_t)num_sm * 2 * survPerCta);
-    const size_t smem = sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2 + 1024;
+    const size_t smem = sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2 + 1024 + 512;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_viterbi_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     k_viterbi_tp<<<grid, TPB, smem, st>>>(d_lut, d_frames, nframes, d_llr, nllr, surv, words, survPerCta, wordsPerCta, d_pdu, pdu_stride,
