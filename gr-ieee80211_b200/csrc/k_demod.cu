@@ -42,12 +42,14 @@ __device__ __forceinline__ void dft8(cpx* v)
 }
 
 struct __align__(16) WarpBuf {
-    float2 xch[SPW * XS];           // transpose buffer
+    union {
+        float2 xch[SPW * XS];       // transpose buffer (dead once the second DFT has read it)
+        float llr[SPW * 416];       // deinterleaved soft bits of the warp's symbols, contiguous
+    };
     float2 pil[SPW * 4];            // equalised pilots of each symbol: bins 7, 21, 43, 57
-    float llr[SPW * 416];           // deinterleaved soft bits of the warp's symbols, contiguous
 };
 
-__global__ void __launch_bounds__(DW * 32)
+__global__ void __launch_bounds__(DW * 32, 8)
 k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int maxf,
         const c8b_frame* __restrict__ frames, const float2* __restrict__ hinvAll, float* __restrict__ llrArena)
 {
