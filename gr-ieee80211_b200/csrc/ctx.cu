@@ -122,7 +122,6 @@ int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
     if (!ctx) return C8B_ERR_NOMEM;
     memset(&ctx->cfg, 0, sizeof(ctx->cfg));
     if (cfg) ctx->cfg = *cfg;
-    if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = 16384;
     if (ctx->cfg.max_frames <= 0) ctx->cfg.max_frames = 1;
     ctx->device = ctx->cfg.device;
     if (ctx->device < 0 || ctx->device >= n) { g_createErr = "bad device ordinal"; delete ctx; return C8B_ERR_ARG; }
@@ -135,6 +134,7 @@ int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evVit[k], cudaEventDisableTiming);
     }
     ctx->overlap = ctx->cfg.no_overlap == 0;
+    if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = (e == cudaSuccess && ctx->numSM > 0 ? ctx->numSM : 148) * 256;   // one full wave of k_viterbi_tp
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->numSM, cudaDevAttrMultiProcessorCount, ctx->device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_lut, sizeof(c8b_lut));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 64);

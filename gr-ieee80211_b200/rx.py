@@ -41,7 +41,7 @@ class Receiver:
     """One context = one GPU + one stream.  `blob`: LUT blob to load (default: build locally; multi-GPU
     runs pass the blob broadcast from rank 0)."""
 
-    def __init__(self, device=0, chunk_items=16384, max_item_len=0, max_frames=1, mupos=0, mugid=0, blob=None, overlap=True, decode_mode=0):
+    def __init__(self, device=0, chunk_items=0, max_item_len=0, max_frames=1, mupos=0, mugid=0, blob=None, overlap=True, decode_mode=0):
         self.L = _cabi.lib()
         if self.L.c8b_device_count() <= 0:
             raise C8bError("no CUDA device visible: gr-ieee80211_b200 has no CPU path")
