@@ -165,6 +165,27 @@ def frames_564():
     print("frames_564:", {k: v.size for k, v in out.items()})
 
 
+def frames_sgi():
+    """HT / VHT frames whose SIG field announces short GI.  The reference TX has no short-GI waveform (lib/cloud80211phy.cc:2489,
+    tools/phy80211.py builds 80-sample symbols regardless) but its RX honours the bit (nSymSamp = 72, c8p.cc:898-902,1155-1159):
+    such frames demodulate on a 72-sample raster and fail the CRC -- a parity case for the nSymSamp = 72 path."""
+    phy = phy80211.phy80211(ifDebug=False)
+    payload = "123456789012345678901234567890"
+    mpdu, ampdu = mac_mpdu(payload), mac_ampdu([payload])
+    items = []
+    for fmt, pkt, mcs in ((p8h.F.HT, mpdu, 5), (p8h.F.VHT, ampdu, 7), (p8h.F.HT, mpdu, 0)):
+        mod = p8h.modulation(phyFormat=fmt, mcs=mcs, bw=p8h.BW.BW20, nSTS=1, shortGi=True)
+        if fmt == p8h.F.VHT:
+            quiet(phy.genFromAmpdu, pkt, mod, vhtPartialAid=0, vhtGroupId=0)
+        else:
+            quiet(phy.genFromMpdu, pkt, mod)
+        ss = quiet(phy.genFinalSig, multiplier=12.0, cfoHz=0.0, num=1, gap=True, gapLen=400)
+        items.append(np.asarray(ss[0], dtype=np.complex64))
+    offs = np.cumsum([0] + [len(x) for x in items]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "frames_sgi.npz"), iq=np.concatenate(items).astype(np.complex64), offs=offs)
+    print("frames_sgi:", [len(x) for x in items])
+
+
 def ref_vectors():
     import oracle_lib as ol
     R = ol.ref()
@@ -225,7 +246,7 @@ def ref_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564"]
+    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi"]
     if "siso" in which:
         frames_siso()
     if "bench" in which:
@@ -236,3 +257,5 @@ if __name__ == "__main__":
         frames_mimo()
     if "564" in which:
         frames_564()
+    if "sgi" in which:
+        frames_sgi()

@@ -47,3 +47,27 @@ def test_demod_llrs_match_oracle(rx, golden, snr):
         worst = max(worst, float(err.max()))
         assert err.max() <= LLR_RTOL, (i, int(np.argmax(err)), float(err.max()))
     print("worst relative LLR error %.3g" % worst)
+
+
+def test_short_gi_flag_uses_72_sample_raster(rx):
+    """frames announcing short GI: nSymSamp = 72 on the GPU exactly as in the oracle (fields, LLRs, no PDU)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frames_sgi.npz"))
+    iq, offs = g["iq"], g["offs"]
+    off, ln = offs[:-1], np.diff(offs).astype(np.int32)
+    fr, chan = rx.detect(iq, off, ln)
+    fr2, llr = rx.demod(iq, off, ln, fr, chan, 64 * 416)
+    for i in range(len(off)):
+        fo, lo, po = ol.rx_item(iq[offs[i]:offs[i + 1]], max_frames=1)
+        for k in HDR:
+            assert fr2[i][k] == fo[0][k], (i, k, fr2[i][k], fo[0][k])
+        assert fr2[i]["nsymsamp"] == 72
+        n = int(fo[0]["total"])
+        ok = np.isfinite(lo[:n])
+        err = np.abs(llr[i, :n][ok] - lo[:n][ok]) / np.maximum(1.0, np.abs(lo[:n][ok]))
+        assert err.max() <= LLR_RTOL, (i, float(err.max()))
+    pkg = load_pkg()
+    r2 = pkg.Receiver(device=0)
+    f3, pdu = r2.rx_batch(iq, off, ln)
+    r2.close()
+    assert list(f3["status"]) == [0, 0, 0] and f3["npdu"].sum() == 0
