@@ -35,7 +35,7 @@ assert FRAME_DTYPE.itemsize == C.sizeof(C8bFrame)
 
 class C8bCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("chunk_items", C.c_int32), ("max_item_len", C.c_int32), ("max_frames", C.c_int32),
-                ("mupos", C.c_int32), ("mugid", C.c_int32), ("no_overlap", C.c_int32), ("decode_mode", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("mupos", C.c_int32), ("mugid", C.c_int32), ("no_overlap", C.c_int32), ("decode_mode", C.c_int32), ("frontend_mode", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 # every symbol include/c80211b200.h declares: (name, restype, argtypes)

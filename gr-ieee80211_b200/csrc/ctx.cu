@@ -385,8 +385,9 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     }
     {
         StageTimer tm(ctx, C8B_K_DETECT);
-        c8b_launch_detect(ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p,
-                          maskStride, d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->st);
+        (ctx->cfg.frontend_mode == 1 ? c8b_launch_detect : c8b_launch_detect_w)(
+            ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p, maskStride,
+            d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_HEADER);
@@ -394,8 +395,9 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
             c8b_launch_header2(ctx->d_lut, iq, iq1, d_off + b, n, maxf, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
                                (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llrStride, ctx->st);
         else
-            c8b_launch_header(ctx->d_lut, iq, d_off + b, n, maxf, ctx->cfg.mupos, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
-                              (float2*)ctx->hinv.p, llrStride, ctx->st);
+            (ctx->cfg.frontend_mode == 1 ? c8b_launch_header : c8b_launch_header_w)(
+                ctx->d_lut, iq, d_off + b, n, maxf, ctx->cfg.mupos, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
+                (float2*)ctx->hinv.p, llrStride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
@@ -644,9 +646,9 @@ int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_
     }
     {
         StageTimer tm(ctx, C8B_K_DETECT);
-        c8b_launch_detect(ctx->d_lut, iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, 0, maxf, pl.base,
-                          (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p, maskStride, (c8b_frame*)ctx->frames.p,
-                          (float2*)ctx->chan.p, ctx->st);
+        (ctx->cfg.frontend_mode == 1 ? c8b_launch_detect : c8b_launch_detect_w)(
+            ctx->d_lut, iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, 0, maxf, pl.base, (const float*)ctx->preac.p,
+            (const uint32_t*)ctx->mask.p, maskStride, (c8b_frame*)ctx->frames.p, (float2*)ctx->chan.p, ctx->st);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(frames, ctx->frames.p, ns * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
@@ -677,8 +679,9 @@ int c8b_demod(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t
     const float2* iq = (const float2*)ctx->iq.p - pl.base;
     {
         StageTimer tm(ctx, C8B_K_HEADER);
-        c8b_launch_header(ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxf, ctx->cfg.mupos, (c8b_frame*)ctx->frames.p,
-                          (const float2*)ctx->chan.p, (float2*)ctx->hinv.p, llr_stride, ctx->st);
+        (ctx->cfg.frontend_mode == 1 ? c8b_launch_header : c8b_launch_header_w)(
+            ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxf, ctx->cfg.mupos, (c8b_frame*)ctx->frames.p, (const float2*)ctx->chan.p,
+            (float2*)ctx->hinv.p, llr_stride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);

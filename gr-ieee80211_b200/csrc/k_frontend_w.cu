@@ -1,0 +1,482 @@
+// k_frontend_w.cu -- warp-cooperative versions of the per-frame stages:
+//   k_detect_w : one WARP per item  : trigger FSM -> sync -> signal   (same results as k_detect)
+//   k_header_w : one WARP per frame : demod header states, 1 antenna  (same results as k_header)
+// The thread-per-item kernels in k_frontend.cu are latency-bound (5 KB of local arrays per thread, ~7 warps per
+// SM at a 37888-item chunk); here the control flow stays the reference's sequential state machine, executed
+// uniformly by all 32 lanes, while every heavy loop is spread over the lanes through a per-warp shared-memory
+// workspace: the 240 conjugate products / powers of the LTF autocorrelation, the per-lag normalisation, the CFO
+// rotations, the 64-point DFTs (8 lanes each, the same 8x8 scheme as k_demod), the per-tone SIG demodulation and the
+// 64-state SIG Viterbi (2 states per lane, decisions by ballot).  Sums whose order matters in the reference (the
+// running sums of lib/sync_impl.cc:155-179, the LTF CFO sum, pilot sums) are still formed sequentially, in order.
+// DFTs are float32 here (the thread kernels use a double DFT); both stand in for FFTW (unpinned).
+#include "common.cuh"
+#include "phy_serial.cuh"
+
+namespace {
+
+using namespace c8b;
+
+constexpr int FW = 4;                          // warps (= items / frames) per CTA
+constexpr unsigned FULL = 0xffffffffu;
+
+struct __align__(16) Ws {                       // per-warp workspace
+    float2 A[256];                              // complex scratch: products / rotated windows / spectra
+    float2 B[256];
+    float4 Lg[112];                             // per-lag (msum.re, msum.im, s1, s2)
+    float F[256];                               // float scratch: powers / ac / soft bits
+    float M[2][64];                             // Viterbi metrics
+    uint32_t Dec[48][2];                        // Viterbi decisions
+    float2 X[4][72];                            // DFT transposes (row stride 9)
+};
+
+struct cpx { float x, y; };
+__device__ __forceinline__ cpx operator+(cpx a, cpx b) { return { a.x + b.x, a.y + b.y }; }
+__device__ __forceinline__ cpx operator-(cpx a, cpx b) { return { a.x - b.x, a.y - b.y }; }
+__device__ __forceinline__ cpx cm(cpx a, cpx b) { return { a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x }; }
+__device__ __forceinline__ cpx mulmj(cpx a) { return { a.y, -a.x }; }
+__device__ __forceinline__ void dft8(cpx* v)
+{
+    const float r = 0.70710678118654752440f;
+    cpx a0 = v[0] + v[4], a1 = v[0] - v[4], a2 = v[2] + v[6], a3 = mulmj(v[2] - v[6]);
+    cpx a4 = v[1] + v[5], a5 = v[1] - v[5], a6 = v[3] + v[7], a7 = mulmj(v[3] - v[7]);
+    cpx b0 = a0 + a2, b2 = a0 - a2, b1 = a1 + a3, b3 = a1 - a3;
+    cpx b4 = a4 + a6, b6 = mulmj(a4 - a6), b5 = a5 + a7, b7 = a5 - a7;
+    b5 = { (b5.x + b5.y) * r, (b5.y - b5.x) * r };
+    b7 = { (b7.y - b7.x) * r, -(b7.x + b7.y) * r };
+    v[0] = b0 + b4; v[4] = b0 - b4; v[1] = b1 + b5; v[5] = b1 - b5;
+    v[2] = b2 + b6; v[6] = b2 - b6; v[3] = b3 + b7; v[7] = b3 - b7;
+}
+
+// up to 4 independent 64-point forward DFTs per warp: group g = lane/8 transforms buf + 64*g in place (g < nfft)
+__device__ __forceinline__ void fft64_groups(const c8b_lut* __restrict__ L, float2* buf, Ws& W, int nfft, int lane)
+{
+    const int g = lane >> 3, j = lane & 7;
+    cpx v[8];
+    float2* b = buf + 64 * g;
+    __syncwarp();
+    if (g < nfft) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) { const float2 t = b[j + 8 * m]; v[m] = { t.x, t.y }; }
+        dft8(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) { const int t = (j * k1) & 63; v[k1] = cm(v[k1], cpx{ L->twr[t], L->twi[t] }); }
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) W.X[g][k1 * 9 + j] = make_float2(v[k1].x, v[k1].y);
+    }
+    __syncwarp();
+    if (g < nfft) {
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) { const float2 t = W.X[g][j * 9 + n1]; v[n1] = { t.x, t.y }; }
+        dft8(v);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) b[j + 8 * k2] = make_float2(v[k2].x, v[k2].y);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ cf ld(const float2* p) { const float2 t = *p; return mk(t.x, t.y); }
+__device__ __forceinline__ float2 st(cf a) { return make_float2(a.re, a.im); }
+
+// SIG-field Viterbi (lib/cloud80211phy.cc:2001-2088), T <= 48: lane k owns the butterfly (2k, 2k+1) -> (k, k+32).
+// Returns the decoded bits packed LSB-first (bit t of lo/hi words).
+__device__ __forceinline__ uint64_t sig_viterbi_w(const c8b_lut* __restrict__ L, const float* __restrict__ llr, int T, Ws& W, int lane)
+{
+    const int c = L->bmClass[lane];
+    __syncwarp();
+    W.M[0][lane] = lane == 0 ? 0.0f : -1000000000000000.0f;
+    W.M[0][lane + 32] = -1000000000000000.0f;
+    __syncwarp();
+    for (int t = 0; t < T; t++) {
+        const float t0 = llr[2 * t], t1 = llr[2 * t + 1];
+        const float t3 = fadd(t1, t0);
+        const float A = c == 0 ? 0.0f : c == 1 ? t1 : c == 2 ? t0 : t3;
+        const float Bm = c == 0 ? t3 : c == 1 ? t0 : c == 2 ? t1 : 0.0f;
+        const float* __restrict__ pre = W.M[t & 1];
+        float* __restrict__ cur = W.M[(t & 1) ^ 1];
+        const float e = pre[2 * lane], o = pre[2 * lane + 1];
+        const float a0 = fadd(e, A), b0 = fadd(o, Bm), a1 = fadd(e, Bm), b1 = fadd(o, A);
+        float v0 = -1000000000000000.0f, v1 = -1000000000000000.0f;
+        bool d0 = false, d1 = false;
+        if (a0 > v0) v0 = a0;
+        if (b0 > v0) { v0 = b0; d0 = true; }
+        if (a1 > v1) v1 = a1;
+        if (b1 > v1) { v1 = b1; d1 = true; }
+        const uint32_t w0 = __ballot_sync(FULL, d0), w1 = __ballot_sync(FULL, d1);
+        if (lane == 0) { W.Dec[t][0] = w0; W.Dec[t][1] = w1; }
+        cur[lane] = v0; cur[lane + 32] = v1;
+        __syncwarp();
+    }
+    uint64_t bits = 0;
+    int s = 0;                                                    // final state 0
+    for (int t = T - 1; t >= 0; t--) {
+        bits |= (uint64_t)(s >> 5) << t;
+        s = ((s & 31) << 1) | (int)((W.Dec[t][s >> 5] >> (s & 31)) & 1u);
+    }
+    return bits;
+}
+
+__device__ __forceinline__ void unpack_bits(uint64_t v, uint8_t* b, int n) { for (int i = 0; i < n; i++) b[i] = (uint8_t)((v >> i) & 1u); }
+
+// ---------------------------------------------------------------------------------------------------
+// sync (lib/sync_impl.cc:92-147, :155-179, :181-196), sig = 240 samples from the trigger (global memory)
+// ---------------------------------------------------------------------------------------------------
+__device__ SyncOut sync_at_w(const cf* __restrict__ sig, cf conjAvg, Ws& W, int lane)
+{
+    __syncwarp();
+    for (int i = lane; i < C8B_SYNC_BUF; i += 32) {
+        const cf s = sig[i];
+        W.F[i] = abs2(s);
+        if (i < 176) W.A[i] = st(cmul(s, cconj(sig[i + 64])));
+    }
+    __syncwarp();
+    {   // the reference's running sums, in its order (uniform across lanes)
+        cf msum = mk(0.f, 0.f);
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < 64; i++) { msum = cadd(msum, ld(&W.A[i])); s1 = fadd(s1, W.F[i]); s2 = fadd(s2, W.F[i + 64]); }
+        for (int i = 0; i < C8B_SYNC_RES; i++) {
+            if (lane == 0) W.Lg[i] = make_float4(msum.re, msum.im, s1, s2);
+            msum = csub(msum, ld(&W.A[i])); s1 = fsub(s1, W.F[i]); s2 = fsub(s2, W.F[i + 64]);
+            msum = cadd(msum, ld(&W.A[i + 64])); s1 = fadd(s1, W.F[i + 64]); s2 = fadd(s2, W.F[i + 128]);
+        }
+    }
+    __syncwarp();
+    float* __restrict__ ac = reinterpret_cast<float*>(W.B);        // 111 normalised correlations
+    for (int i = lane; i < C8B_SYNC_RES; i += 32) {
+        const float4 g = W.Lg[i];
+        ac[i] = fdiv(fdiv(cabsf_(mk(g.x, g.y)), fsqrt(g.z)), fsqrt(g.w));
+    }
+    __syncwarp();
+    float best = -1.f;
+    int bi = 0;
+    for (int i = 0; i < C8B_SYNC_RES; i++) { const float a = ac[i]; if (i == 0 || a > best) { best = a; bi = i; } }   // first maximum (:97)
+    SyncOut o; o.ok = 0; o.mIndex = 0; o.rad = o.snr = o.rssi = 0.f;
+    if ((double)best > 0.5) {                                     // :99
+        const float thr = (float)((double)best * 0.8);
+        int l = bi, r = bi;
+        for (int j = bi; j >= 0; j--) if (ac[j] < thr) { l = j; break; }
+        for (int j = bi; j < C8B_SYNC_RES; j++) if (ac[j] < thr) { r = j; break; }
+        o.ok = 1; o.mIndex = (l + r) / 2;
+        const cf* __restrict__ s = sig + o.mIndex;                // ltf_cfo :181-196
+        const float radStf = fdiv(atan2f_(conjAvg.im, conjAvg.re), 16.0f);
+        const float bestPwr = W.Lg[bi].z;
+        __syncwarp();
+        for (int i = lane; i < 128; i += 32) W.A[i] = st(cmul(s[i], cis(fmul((float)i, radStf))));
+        __syncwarp();
+        for (int i = lane; i < 64; i += 32) W.A[128 + i] = st(cmul(ld(&W.A[i]), cconj(ld(&W.A[i + 64]))));
+        __syncwarp();
+        cf csum = mk(0.f, 0.f);
+        for (int i = 0; i < 64; i++) csum = cadd(csum, ld(&W.A[128 + i]));
+        const cf c64 = cdivs(csum, 64.0f);
+        const float radLtf = fdiv(atan2f_(c64.im, c64.re), 64.0f);
+        o.rad = fadd(radStf, radLtf);
+        const double maxD = (double)best;
+        o.snr = (float)(10.0 * log10(maxD / (1.0 - maxD)));
+        o.rssi = fdiv(bestPwr, 64.0f);
+    }
+    __syncwarp();
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// signal, S_DEMOD (lib/signal_impl.cc:108-162): in = samples from the sync index (>= 224); h -> global (64 complex)
+// ---------------------------------------------------------------------------------------------------
+__device__ int signal_at_w(const c8b_lut* __restrict__ L, const cf* __restrict__ in, float rad, float2* __restrict__ hOut, int* mcs, int* len,
+                           int* nsamp, Ws& W, int lane)
+{
+    __syncwarp();
+    for (int k = lane; k < 192; k += 32) {                        // :115-120, windows at 8, 72, 152
+        const int w = k >> 6, i = k & 63, off = w == 0 ? C8B_SYM_SHIFT : w == 1 ? C8B_SYM_SHIFT + 64 : C8B_SYM_SHIFT + 144;
+        W.A[k] = st(cmul(in[off + i], cis(fmul((float)(i + off), rad))));
+    }
+    fft64_groups(L, W.A, W, 3, lane);                             // A[0..63] = LTF1, [64..127] = LTF2, [128..191] = L-SIG
+    // procLHSigDemodDeint (lib/cloud80211phy.cc:609-627)
+    const int pb[4] = { 7, 21, 43, 57 };
+    cf hp[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) hp[q] = cdivs(cadd(ld(&W.A[pb[q]]), ld(&W.A[64 + pb[q]])), fmul(2.0f, L->ltfL[pb[q]]));
+    cf acc = cdiv(ld(&W.A[128 + 7]), hp[0]);
+    acc = csub(acc, cdiv(ld(&W.A[128 + 21]), hp[1]));
+    acc = cadd(acc, cdiv(ld(&W.A[128 + 43]), hp[2]));
+    acc = cadd(acc, cdiv(ld(&W.A[128 + 57]), hp[3]));
+    const cf ps = cconj(acc);
+    const float pa = cabsf_(ps);
+    for (int i = lane; i < 64; i += 32) {
+        cf h = mk(0.f, 0.f);
+        const int d = L->sigDemap[i];
+        const bool pil = i == 7 || i == 21 || i == 43 || i == 57;
+        if (d >= 0 || pil) h = cdivs(cadd(ld(&W.A[i]), ld(&W.A[64 + i])), fmul(2.0f, L->ltfL[i]));
+        if (d >= 0) W.F[d] = cdivs(cmul(cdiv(ld(&W.A[128 + i]), h), ps), pa).re;
+        hOut[i] = st(h);
+    }
+    __syncwarp();
+    const uint64_t bits = sig_viterbi_w(L, W.F, 24, W, lane);
+    uint8_t b[24];
+    unpack_bits(bits, b, 24);
+    if (!lsig_check(b, mcs, len)) return 0;
+    const int ndbps = lsig_ndbps(*mcs);
+    *nsamp = ((*len * 8 + 22 + ndbps - 1) / ndbps) * 80;          // :128
+    return 1;
+}
+
+__global__ void __launch_bounds__(FW * 32)
+k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
+           const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preacAll,
+           const uint32_t* __restrict__ maskAll, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan)
+{
+    __shared__ Ws ws[FW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int it = blockIdx.x * FW + warp;
+    if (it >= nitems) return;
+    Ws& W = ws[warp];
+    const cf* __restrict__ x = reinterpret_cast<const cf*>(iq + off[it]);
+    const float* __restrict__ preac = preacAll + (off[it] - outBase);
+    const uint32_t* __restrict__ mask = maskAll ? maskAll + (size_t)it * maskStride : nullptr;
+    const int n = len[it];
+    c8b_frame* __restrict__ f = frames + (size_t)it * maxf;
+    float2* __restrict__ h = chan + (size_t)it * maxf * 64;
+    if (lane == 0) for (int k = 0; k < maxf; k++) frame_clear(f + k, itemBase + it, C8B_ST_EMPTY);
+    for (int k = lane; k < maxf * 64; k += 32) h[k] = make_float2(0.f, 0.f);
+    __syncwarp();
+
+    // the blocks' state machines, evaluated uniformly by the warp (see detect_item in phy_serial.cuh)
+    TrigState ts;
+    trig_reset(ts);
+    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0, nf = 0;
+    bool syncStalled = false, sigStalled = false, done = false;
+    for (int i = 0; i < n && !done; i++) {
+        if (mask && (i & 31) == 0 && i + 32 <= n && ts.fPlateau == 0 && mask[i >> 5] == 0u) {
+            ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+            i += 31;
+            continue;
+        }
+        const uint8_t fl = trig_step(ts, preac[i]);
+        if (fl == 0 || i < skipUntil || syncStalled) continue;
+        if (fl & 0x01) {
+            nTrig++;
+            if (n - i < C8B_SYNC_BUF) { syncStalled = true; continue; }
+            const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
+            const SyncOut so = sync_at_w(x + i, cj, W, lane);
+            skipUntil = i + C8B_SYNC_RES;
+            if (!so.ok) continue;
+            nEv++;
+            const int idx = i + so.mIndex;
+            if (sigStalled || idx < pos) continue;
+            if (n - idx < 224) { sigStalled = true; continue; }
+            int mcs = 0, ln = 0, nsamp = 0;
+            if (!signal_at_w(lut, x + idx, so.rad, h + nf * 64, &mcs, &ln, &nsamp, W, lane)) {
+                for (int k = lane; k < 64; k += 32) h[nf * 64 + k] = make_float2(0.f, 0.f);
+                nLsigFail++; pos = idx + 80; continue;
+            }
+            c8b_frame* fk = f + nf;
+            nf++;
+            pos = idx + 224 + nsamp;
+            const int status = pos > n ? C8B_ST_TRUNC : C8B_ST_OK;
+            if (lane == 0) {
+                fk->trig_idx = i; fk->sync_idx = idx; fk->rad = so.rad; fk->snr = so.snr; fk->rssi = so.rssi;
+                fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);
+                fk->l_mcs = mcs; fk->l_len = ln; fk->nsamp = nsamp; fk->status = status;
+            }
+            if (pos > n || nf >= maxf) done = true;
+        } else if (fl & 0x02) {
+            latch = i;
+        }
+    }
+    if (nf == 0 && lane == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// demod header states, one antenna (lib/demod_impl.cc:72-277, :344-505): warp version of demod_header
+// ---------------------------------------------------------------------------------------------------
+struct RotW {
+    const cf* x; float rad; int nsamp;
+    __device__ __forceinline__ cf at(int k) const
+    {
+        if (k >= nsamp) return mk(0.f, 0.f);
+        return cmul(x[k], cis(fmul((float)(k + 224), rad)));
+    }
+};
+
+__global__ void __launch_bounds__(FW * 32)
+k_header_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int nslots, int maxf,
+           int mupos, c8b_frame* __restrict__ frames, const float2* __restrict__ chan, float2* __restrict__ hinvAll, int64_t llrStride)
+{
+    __shared__ Ws ws[FW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = blockIdx.x * FW + warp;
+    if (sl >= nslots) return;
+    Ws& W = ws[warp];
+    c8b_frame* __restrict__ fr = frames + sl;
+    float2* __restrict__ hinv = hinvAll + (size_t)sl * 64;
+    if (lane == 0) fr->llr_off = (int64_t)sl * llrStride;
+    if (fr->status != C8B_ST_OK) return;
+    const c8b_lut* L = lut;
+    RotW rot;
+    rot.x = reinterpret_cast<const cf*>(iq + off[sl / maxf]) + fr->sync_idx + 224;
+    rot.rad = fr->rad; rot.nsamp = fr->nsamp;
+    const int nsamp = fr->nsamp, lmcs = fr->l_mcs, llen = fr->l_len;
+    const float2* __restrict__ hl = chan + (size_t)sl * 64;
+
+    Mod m;
+    m.format = m.sumu = m.ampdu = m.nSym = m.nSymSamp = m.nSD = m.nSP = m.nSS = m.nLTF = 0;
+    m.mcs = m.len = m.mod = m.cr = m.nBPSCS = m.nDBPS = m.nCBPS = m.nCBPSS = 0;
+    const int nsig = nsamp + 320;
+    int pos = 0, trellis = 0, status = C8B_ST_OK;
+    float sssnr = 0.f;
+    bool legacy = lmcs > 0, haveNL = false;
+    // window k (0..3) of 64 rotated samples starting at stream index `start` -> W.A[64*k ..]
+    auto win = [&](int k, int start) { for (int i = lane; i < 64; i += 32) W.A[64 * k + i] = st(rot.at(start + C8B_SYM_SHIFT + i)); };
+    float2* __restrict__ HNL = W.B;                                // [64] non-legacy channel (W.B[0..63])
+    float* __restrict__ llrht = W.F, *llrvht = W.F + 96;           // 96 + 96 soft bits
+
+    if (!legacy) {                                                // DEMOD_S_FORMAT :106-148
+        if (nsig < 160) status = C8B_ST_TRUNC;
+        else {
+            __syncwarp();
+            win(0, 0); win(1, 80);
+            fft64_groups(L, W.A, W, 2, lane);
+            {   // procNLSigDemodDeint (lib/cloud80211phy.cc:629-648)
+                cf a1 = cdiv(ld(&W.A[7]), ld((const float2*)&hl[7])), a2 = cdiv(ld(&W.A[64 + 7]), ld(&hl[7]));
+                a1 = csub(a1, cdiv(ld(&W.A[21]), ld(&hl[21]))); a2 = csub(a2, cdiv(ld(&W.A[64 + 21]), ld(&hl[21])));
+                a1 = cadd(a1, cdiv(ld(&W.A[43]), ld(&hl[43]))); a2 = cadd(a2, cdiv(ld(&W.A[64 + 43]), ld(&hl[43])));
+                a1 = cadd(a1, cdiv(ld(&W.A[57]), ld(&hl[57]))); a2 = cadd(a2, cdiv(ld(&W.A[64 + 57]), ld(&hl[57])));
+                const cf p1 = cconj(a1), p2 = cconj(a2);
+                const float m1 = cabsf_(p1), m2 = cabsf_(p2);
+                for (int i = lane; i < 64; i += 32) {
+                    const int d = L->sigDemap[i];
+                    if (d < 0) continue;
+                    const cf h = ld(&hl[i]);
+                    const cf q1 = cdivs(cmul(cdiv(ld(&W.A[i]), h), p1), m1);
+                    const cf q2 = cdivs(cmul(cdiv(ld(&W.A[64 + i]), h), p2), m2);
+                    llrht[d] = q1.im; llrht[d + 48] = q2.im;
+                    llrvht[d] = q1.re; llrvht[d + 48] = q2.im;
+                }
+            }
+            __syncwarp();
+            uint8_t vb[48];
+            unpack_bits(sig_viterbi_w(L, llrvht, 48, W, lane), vb, 48);
+            if (check_vhta(vb)) {                                 // DEMOD_S_VHT :150-178
+                parse_vhta(vb, &m);
+                pos = 160;
+                const int need = 80 + m.nLTF * 80 + 80;
+                if (nsig - pos < need) status = C8B_ST_TRUNC;
+                else {
+                    __syncwarp();
+                    if (m.sumu) {                                 // nonLegacyChanEstimate :344-411
+                        win(0, pos + 80); win(1, pos + 160);
+                        fft64_groups(L, W.A, W, 2, lane);
+                        for (int i = lane; i < 64; i += 32) {
+                            cf h = mk(0.f, 0.f);
+                            if (!nl_null(i)) {
+                                if (mupos == 0) h = cdivs(csub(ld(&W.A[i]), ld(&W.A[64 + i])), fmul(L->ltfNL[i], 2.0f));
+                                else h = cdivs(cadd(cdivs(ld(&W.A[i]), L->ltfNL[i]), cdivs(ld(&W.A[64 + i]), L->ltfNL22[i])), 2.0f);
+                            }
+                            HNL[i] = st(h);
+                        }
+                    } else {
+                        win(0, pos + 80);
+                        fft64_groups(L, W.A, W, 1, lane);
+                        for (int i = lane; i < 64; i += 32) HNL[i] = nl_null(i) ? make_float2(0.f, 0.f) : st(cdivs(ld(&W.A[i]), L->ltfNL[i]));
+                    }
+                    haveNL = true;
+                    __syncwarp();
+                    // vhtSigBDemod :449-505
+                    win(0, pos + 80 + m.nLTF * 80);
+                    fft64_groups(L, W.A, W, 1, lane);
+                    for (int i = lane; i < 64; i += 32) if (!nl_null(i)) W.A[64 + i] = st(cdiv(ld(&W.A[i]), ld(&HNL[i])));   // sig1
+                    __syncwarp();
+                    const cf ps = cconj(cadd(cadd(csub(ld(&W.A[64 + 7]), ld(&W.A[64 + 21])), ld(&W.A[64 + 43])), ld(&W.A[64 + 57])));
+                    const float pa = cabsf_(ps);
+                    float2* __restrict__ bq = W.A + 128;              // [52] equalised SIG-B tones
+                    float* __restrict__ coded = W.F + 192;            // [52]
+                    for (int i = lane; i < 64; i += 32) {
+                        const int d = L->binToDataNL[i];
+                        if (d == 255) continue;
+                        const cf q = cdivs(cmul(ld(&W.A[64 + i]), ps), pa);
+                        bq[d] = st(q);
+                        coded[L->deintNL[0][0][d]] = q.re;            // mapDeintVhtSigB20
+                    }
+                    __syncwarp();
+                    uint8_t sb[26], enc[52];
+                    unpack_bits(sig_viterbi_w(L, coded, 26, W, lane), sb, 26);
+                    bcc_encode(sb, enc, 26);
+                    double np = 0.0;
+                    for (int i = 0; i < 52; i++) {                // procIntelVhtB20 + noise power :488-504
+                        const cf q = ld(&bq[i]);
+                        const cf e = mk(fsub(q.re, enc[L->deintNL[0][0][i]] ? 1.0f : -1.0f), q.im);
+                        np += (double)fadd(fmul(e.re, e.re), fmul(e.im, e.im));
+                    }
+                    sssnr = (float)(log10(52.0 / np) * 10.0);
+                    parse_vhtb(sb, &m);
+                    const int nl = (llen * 8 + 22 + 23) / 24;
+                    const bool ok = m.len >= 0 && m.len <= 4095 && m.nSS <= 2 && (nl * 80) >= (m.nSym * m.nSymSamp + 160 + 80 + m.nLTF * 80 + 80);
+                    pos += need;
+                    if (!ok) status = C8B_ST_FORMAT;
+                    trellis = m.nSym * m.nDBPS;
+                }
+            } else {
+                uint8_t hb[48];
+                unpack_bits(sig_viterbi_w(L, llrht, 48, W, lane), hb, 48);
+                if (check_ht(hb)) {                               // DEMOD_S_HT :180-205
+                    parse_ht(hb, &m);
+                    pos = 160;
+                    const int need = 80 + m.nLTF * 80;
+                    if (nsig - pos < need) status = C8B_ST_TRUNC;
+                    else {
+                        __syncwarp();
+                        win(0, pos + 80);
+                        fft64_groups(L, W.A, W, 1, lane);
+                        for (int i = lane; i < 64; i += 32) HNL[i] = nl_null(i) ? make_float2(0.f, 0.f) : st(cdivs(ld(&W.A[i]), L->ltfNL[i]));
+                        haveNL = true;
+                        __syncwarp();
+                        const int nl = (llen * 8 + 22 + 23) / 24;
+                        const bool ok = m.len > 0 && m.len <= 4095 && m.nSS <= 2 && (nl * 80) >= (m.nSym * m.nSymSamp + 160 + 80 + m.nLTF * 80);
+                        pos += need;
+                        if (!ok) status = C8B_ST_FORMAT;
+                        trellis = m.len * 8 + 22;
+                    }
+                } else legacy = true;
+            }
+        }
+    }
+    if (status == C8B_ST_OK && legacy) { parse_l(lmcs, llen, &m); trellis = m.len * 8 + 22; }
+    if (status != C8B_ST_OK) { if (lane == 0) fr->status = status; return; }
+    // DEMOD_S_WRTAG :221-277
+    for (int i = lane; i < 64; i += 32) {
+        const cf hh = (m.format == C8B_F_L) ? ld(&hl[i]) : (haveNL ? ld(&HNL[i]) : mk(0.f, 0.f));
+        const bool used = (m.format == C8B_F_L) ? !l_null(i) : !nl_null(i);
+        float2 r = make_float2(0.f, 0.f);
+        if (used) { const double den = c8b::dadd(c8b::dmul((double)hh.re, (double)hh.re), c8b::dmul((double)hh.im, (double)hh.im)); r = make_float2((float)((double)hh.re / den), (float)(-(double)hh.im / den)); }
+        hinv[i] = r;
+    }
+    int total = m.nSym * m.nCBPS;
+    if (m.nSym == 0) { total = 1024; status = C8B_ST_NDP; }
+    else if (m.nSS != 1) status = C8B_ST_FORMAT;                  // 2-stream frames need the demod2 path
+    else if (pos + m.nSym * m.nSymSamp > nsig) status = C8B_ST_TRUNC;
+    else if ((int64_t)total > llrStride) status = C8B_ST_OVERFLOW;
+    if (lane == 0) {
+        fr->format = m.format; fr->mcs = m.mcs; fr->len = m.len; fr->cr = m.cr; fr->ampdu = m.ampdu;
+        fr->nss = m.nSS; fr->nsym = m.nSym; fr->nsymsamp = m.nSymSamp; fr->ncbps = m.nCBPS; fr->ndbps = m.nDBPS;
+        fr->trellis = trellis; fr->total = total; fr->data_off = pos;
+        fr->sssnr0 = (m.format == C8B_F_VHT) ? sssnr : 0.f; fr->sssnr1 = 0.f;
+        fr->status = status;
+    }
+}
+
+}  // namespace
+
+void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
+                         int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
+                         float2* chan, cudaStream_t st)
+{
+    if (nitems <= 0) return;
+    k_detect_w<<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask, maskStride,
+                                                            frames, chan);
+}
+
+void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
+                         const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st)
+{
+    if (nitems <= 0) return;
+    const int ns = nitems * maxf;
+    k_header_w<<<(ns + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, ns, maxf, mupos, frames, chan, hinv, llrStride);
+}

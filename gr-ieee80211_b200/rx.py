@@ -41,11 +41,11 @@ class Receiver:
     """One context = one GPU + one stream.  `blob`: LUT blob to load (default: build locally; multi-GPU
     runs pass the blob broadcast from rank 0)."""
 
-    def __init__(self, device=0, chunk_items=0, max_item_len=0, max_frames=1, mupos=0, mugid=0, blob=None, overlap=True, decode_mode=0):
+    def __init__(self, device=0, chunk_items=0, max_item_len=0, max_frames=1, mupos=0, mugid=0, blob=None, overlap=True, decode_mode=0, frontend_mode=0):
         self.L = _cabi.lib()
         if self.L.c8b_device_count() <= 0:
             raise C8bError("no CUDA device visible: gr-ieee80211_b200 has no CPU path")
-        cfg = C8bCfg(device=device, chunk_items=chunk_items, max_item_len=max_item_len, max_frames=max_frames, mupos=mupos, mugid=mugid, no_overlap=0 if overlap else 1, decode_mode=decode_mode)
+        cfg = C8bCfg(device=device, chunk_items=chunk_items, max_item_len=max_item_len, max_frames=max_frames, mupos=mupos, mugid=mugid, no_overlap=0 if overlap else 1, decode_mode=decode_mode, frontend_mode=frontend_mode)
         self.max_frames = max(1, int(max_frames))
         h = C.c_void_p()
         rc = self.L.c8b_create(C.byref(cfg), C.byref(h))

@@ -111,7 +111,8 @@ typedef struct c8b_cfg {
                                 the front end of chunk k+1 on a second stream                            */
     int32_t decode_mode;     /* 0: pick by batch size; 1: one warp per frame pair (k_viterbi, low latency);
                                 2: one thread per frame (k_viterbi_tp, throughput)                        */
-    int32_t reserved[6];
+    int32_t frontend_mode;   /* 0: warp-cooperative detect / header kernels; 1: one thread per item (k_detect, k_header) */
+    int32_t reserved[5];
 } c8b_cfg;
 
 typedef struct c8b_ctx c8b_ctx;

@@ -14,9 +14,10 @@ HDR = ("status", "format", "mcs", "len", "cr", "ampdu", "nss", "nsym", "nsymsamp
 LLR_RTOL = 1e-4      # BASELINE.json north_star: "LLRs within 1e-4 relative"
 
 
-@pytest.fixture(scope="module")
-def rx():
-    r = load_pkg().Receiver(device=0)
+@pytest.fixture(scope="module", params=[0, 1], ids=["warp_frontend", "thread_frontend"])
+def rx(request):
+    """every test runs against both front ends: warp-cooperative (k_detect_w / k_header_w) and one thread per item"""
+    r = load_pkg().Receiver(device=0, frontend_mode=request.param)
     yield r
     r.close()
 

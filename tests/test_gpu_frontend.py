@@ -8,9 +8,10 @@ from __graft_entry__ import load_pkg
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def rx():
-    r = load_pkg().Receiver(device=0)
+@pytest.fixture(scope="module", params=[0, 1], ids=["warp_frontend", "thread_frontend"])
+def rx(request):
+    """every test runs against both front ends: warp-cooperative (k_detect_w / k_header_w) and one thread per item"""
+    r = load_pkg().Receiver(device=0, frontend_mode=request.param)
     yield r
     r.close()
 
