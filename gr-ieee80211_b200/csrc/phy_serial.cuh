@@ -22,10 +22,10 @@
 
 #ifdef __CUDACC__
 #define C8B_HD __host__ __device__ __forceinline__
-#define C8B_HDN __host__ __device__ __noinline__
+#define C8B_HDN static __host__ __device__ __noinline__
 #else
 #define C8B_HD inline
-#define C8B_HDN
+#define C8B_HDN static
 #endif
 
 namespace c8b {
