@@ -41,7 +41,9 @@ def test_demod_llrs_match_oracle(rx, golden, snr):
         for k in HDR:
             assert fr2[i][k] == fo[0][k], (i, k, fr2[i][k], fo[0][k])
         if fo[0]["format"] == 2:
-            assert abs(float(fr2[i]["sssnr0"]) - float(fo[0]["sssnr0"])) <= (1.0 if fo[0]["sssnr0"] > 60 else 0.01)
+            # per-stream SNR from VHT-SIG-B: on a noiseless frame it measures DFT rounding (> 100 dB), else it must agree
+            a, b = float(fr2[i]["sssnr0"]), float(fo[0]["sssnr0"])
+            assert (a > 100 and b > 100) or abs(a - b) <= 0.05, (i, a, b)
         n = int(fo[0]["total"])
         got = llr[i, :n]
         err = np.abs(got - lo[:n]) / np.maximum(1.0, np.abs(lo[:n]))
