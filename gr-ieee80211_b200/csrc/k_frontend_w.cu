@@ -243,11 +243,26 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     trig_reset(ts);
     int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0, nf = 0;
     bool syncStalled = false, sigStalled = false, done = false;
+    int blkBase = -(1 << 30);                                        // 32 bitmap words [blkBase, blkBase+32) summarised in nz
+    uint32_t nz = 0;                                              // bit k: word blkBase+k has a sample above threshold (or is partial)
     for (int i = 0; i < n && !done; i++) {
-        if (mask && (i & 31) == 0 && i + 32 <= n && ts.fPlateau == 0 && mask[i >> 5] == 0u) {
-            ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
-            i += 31;
-            continue;
+        if (mask && (i & 31) == 0 && ts.fPlateau == 0) {
+            // idle trigger at a word boundary: jump over every all-below-threshold word at once (such a stretch leaves the
+            // FSM in its reset state, lib/trigger_impl.cc:95-100); the lanes fetch 32 bitmap words together
+            const int w = i >> 5;
+            if (w < blkBase || w >= blkBase + 32) {
+                blkBase = w;
+                const int ww = w + lane;
+                const uint32_t mv = (ww * 32 + 32 <= n) ? mask[ww] : 0xffffffffu;      // a partial last word is walked sample by sample
+                nz = __ballot_sync(FULL, mv != 0u);
+            }
+            const uint32_t rem = nz >> (w - blkBase);
+            if (!(rem & 1u)) {
+                const int skipw = rem ? __ffs(rem) - 1 : 32 - (w - blkBase);
+                ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+                i += 32 * skipw - 1;
+                continue;
+            }
         }
         const uint8_t fl = trig_step(ts, preac[i]);
         if (fl == 0 || i < skipUntil || syncStalled) continue;

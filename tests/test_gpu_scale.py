@@ -113,3 +113,31 @@ def test_config4_ht_2x2_mcs8_15_50k_frames():
     mp = bytes(g["mpdu"])
     good = _check(pkg, fr, pdu, kind, [1] * 8, list(range(8, 16)), [mp] * 8, 0.995, "config 4")
     _oracle_agrees(fr, pdu, good, lambda i: (ha[off[i]:off[i] + ln[i]], hb[off[i]:off[i] + ln[i]]), two=True)
+
+
+def test_config5_vht_mcs7_1500B_shard():
+    """config 5 units (VHT MCS7, 1500-byte MPDU, 4960-sample items): two full pipeline chunks; every item the GPU does not
+    decode must fail identically in the oracle, a sample of decoded ones must match byte for byte"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    pkg = load_pkg()
+    dev = torch.device("cuda", 0)
+    n = 2 * 37888
+    iq, mpdus = bench.make_batch_device(torch, dev, n, seed=5)
+    off = np.arange(n, dtype=np.int64) * bench.ITEM
+    ln = np.full(n, bench.ITEM, np.int32)
+    rx = pkg.Receiver(device=0)
+    fr, pdu = rx.rx_batch_dev(iq.data_ptr(), off, ln, pdu_stride=bench.PDU_STRIDE)
+    rx.close()
+    good = (fr["status"] == 0) & (fr["npdu"] == 1) & (fr["pdu_bytes"] == 1504)
+    assert good.mean() > 0.9995
+    sel = np.concatenate([np.nonzero(~good)[0], np.random.default_rng(2).choice(np.nonzero(good)[0], 96, replace=False)])
+    h = iq.view(n, bench.ITEM)[torch.from_numpy(sel).to(dev)].cpu().numpy()
+    for k, i in enumerate(sel):
+        fo, _, po = ol.rx_item(np.ascontiguousarray(h[k]), max_frames=1)
+        assert fo[0]["status"] == fr[i]["status"] and fo[0]["npdu"] == fr[i]["npdu"] and fo[0]["sync_idx"] == fr[i]["sync_idx"], int(i)
+        assert bytes(po) == bytes(pdu[i, :po.size]), int(i)
+        if good[i]:
+            assert bytes(pdu[i, 3:1503]) == bytes(mpdus[int(i) % 16])
