@@ -243,58 +243,75 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     trig_reset(ts);
     int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0, nf = 0;
     bool syncStalled = false, sigStalled = false, done = false;
+    // The scan goes bitmap word by bitmap word (32 samples).  A complete word without a sample above the threshold is
+    // not walked: with the trigger idle the FSM stays in its reset state (lib/trigger_impl.cc:95-100) -- all such words up
+    // to the next flagged one are skipped with one ballot over 32 prefetched words; during the 80-sample count-down
+    // (:101-109) the counter is simply advanced.  Flagged words are walked sample by sample from a lane-held copy of
+    // their 32 preac values.
     int blkBase = -(1 << 30);                                        // 32 bitmap words [blkBase, blkBase+32) summarised in nz
-    uint32_t nz = 0;                                              // bit k: word blkBase+k has a sample above threshold (or is partial)
-    for (int i = 0; i < n && !done; i++) {
-        if (mask && (i & 31) == 0 && ts.fPlateau == 0) {
-            // idle trigger at a word boundary: jump over every all-below-threshold word at once (such a stretch leaves the
-            // FSM in its reset state, lib/trigger_impl.cc:95-100); the lanes fetch 32 bitmap words together
-            const int w = i >> 5;
+    uint32_t nz = 0;                                              // bit k: word blkBase+k must be walked
+    const int nwords = (n + 31) >> 5;
+    for (int w = 0; w < nwords && !done;) {
+        if (mask) {
             if (w < blkBase || w >= blkBase + 32) {
                 blkBase = w;
                 const int ww = w + lane;
-                const uint32_t mv = (ww * 32 + 32 <= n) ? mask[ww] : 0xffffffffu;      // a partial last word is walked sample by sample
+                const uint32_t mv = (ww * 32 + 32 <= n) ? mask[ww] : 0xffffffffu;      // a partial last word is always walked
                 nz = __ballot_sync(FULL, mv != 0u);
             }
             const uint32_t rem = nz >> (w - blkBase);
             if (!(rem & 1u)) {
-                const int skipw = rem ? __ffs(rem) - 1 : 32 - (w - blkBase);
-                ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
-                i += 32 * skipw - 1;
-                continue;
+                if (ts.fPlateau == 0) {
+                    w += rem ? __ffs(rem) - 1 : 32 - (w - blkBase);
+                    ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+                    continue;
+                }
+                if (ts.countDown > 32) {                          // 32 sub-threshold samples of the count-down
+                    ts.countDown -= 32;
+                    ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+                    w++;
+                    continue;
+                }
             }
         }
-        const uint8_t fl = trig_step(ts, preac[i]);
-        if (fl == 0 || i < skipUntil || syncStalled) continue;
-        if (fl & 0x01) {
-            nTrig++;
-            if (n - i < C8B_SYNC_BUF) { syncStalled = true; continue; }
-            const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
-            const SyncOut so = sync_at_w(x + i, cj, W, lane);
-            skipUntil = i + C8B_SYNC_RES;
-            if (!so.ok) continue;
-            nEv++;
-            const int idx = i + so.mIndex;
-            if (sigStalled || idx < pos) continue;
-            if (n - idx < 224) { sigStalled = true; continue; }
-            int mcs = 0, ln = 0, nsamp = 0;
-            if (!signal_at_w(lut, x + idx, so.rad, h + nf * 64, &mcs, &ln, &nsamp, W, lane)) {
-                for (int k = lane; k < 64; k += 32) h[nf * 64 + k] = make_float2(0.f, 0.f);
-                nLsigFail++; pos = idx + 80; continue;
+        const int i0 = w * 32;
+        const float pv = (i0 + lane < n) ? preac[i0 + lane] : 0.0f;
+        const int kmax = min(32, n - i0);
+        for (int k = 0; k < kmax && !done; k++) {
+            const int i = i0 + k;
+            const uint8_t fl = trig_step(ts, __shfl_sync(FULL, pv, k));
+            if (fl == 0 || i < skipUntil || syncStalled) continue;
+            if (fl & 0x01) {
+                nTrig++;
+                if (n - i < C8B_SYNC_BUF) { syncStalled = true; continue; }
+                const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
+                const SyncOut so = sync_at_w(x + i, cj, W, lane);
+                skipUntil = i + C8B_SYNC_RES;
+                if (!so.ok) continue;
+                nEv++;
+                const int idx = i + so.mIndex;
+                if (sigStalled || idx < pos) continue;
+                if (n - idx < 224) { sigStalled = true; continue; }
+                int mcs = 0, ln = 0, nsamp = 0;
+                if (!signal_at_w(lut, x + idx, so.rad, h + nf * 64, &mcs, &ln, &nsamp, W, lane)) {
+                    for (int q = lane; q < 64; q += 32) h[nf * 64 + q] = make_float2(0.f, 0.f);
+                    nLsigFail++; pos = idx + 80; continue;
+                }
+                c8b_frame* fk = f + nf;
+                nf++;
+                pos = idx + 224 + nsamp;
+                const int status = pos > n ? C8B_ST_TRUNC : C8B_ST_OK;
+                if (lane == 0) {
+                    fk->trig_idx = i; fk->sync_idx = idx; fk->rad = so.rad; fk->snr = so.snr; fk->rssi = so.rssi;
+                    fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);
+                    fk->l_mcs = mcs; fk->l_len = ln; fk->nsamp = nsamp; fk->status = status;
+                }
+                if (pos > n || nf >= maxf) done = true;
+            } else if (fl & 0x02) {
+                latch = i;
             }
-            c8b_frame* fk = f + nf;
-            nf++;
-            pos = idx + 224 + nsamp;
-            const int status = pos > n ? C8B_ST_TRUNC : C8B_ST_OK;
-            if (lane == 0) {
-                fk->trig_idx = i; fk->sync_idx = idx; fk->rad = so.rad; fk->snr = so.snr; fk->rssi = so.rssi;
-                fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);
-                fk->l_mcs = mcs; fk->l_len = ln; fk->nsamp = nsamp; fk->status = status;
-            }
-            if (pos > n || nf >= maxf) done = true;
-        } else if (fl & 0x02) {
-            latch = i;
         }
+        w++;
     }
     if (nf == 0 && lane == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
 }
