@@ -20,6 +20,15 @@ def lut_blob():
     return buf
 
 
+def _producer_sync():
+    """Device-pointer entry points run on the context's own (non-blocking) stream: if the caller produced the buffer with
+    torch, wait for torch's current stream first (the library knows nothing about the producer's stream)."""
+    import sys
+    t = sys.modules.get("torch")
+    if t is not None and t.cuda.is_available():
+        t.cuda.current_stream().synchronize()
+
+
 def _c2f(x):
     x = np.asarray(x)
     if x.dtype == np.complex64:
@@ -116,6 +125,7 @@ class Receiver:
         n, ns = off.size, off.size * self.max_frames
         frames = np.zeros(ns, FRAME_DTYPE) if frames is None else frames
         pdu = np.zeros(ns * pdu_stride, np.uint8) if pdu is None else pdu
+        _producer_sync()
         self._ck(self.L.c8b_rx_batch_dev(self.h, C.c_void_p(d_iq_ptr), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride),
                  "c8b_rx_batch_dev")
         return frames, pdu.reshape(ns, pdu_stride)
@@ -123,6 +133,7 @@ class Receiver:
     def rx_batch_dev_async(self, d_iq_ptr, off, length, d_frames_ptr, d_pdu_ptr, pdu_stride=4400):
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)
+        _producer_sync()
         self._ck(self.L.c8b_rx_batch_dev_async(self.h, C.c_void_p(d_iq_ptr), ptr(off), ptr(length), off.size, C.c_void_p(d_frames_ptr),
                                                C.c_void_p(d_pdu_ptr), pdu_stride), "c8b_rx_batch_dev_async")
 
