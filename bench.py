@@ -190,8 +190,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU per step (config 5: 1M-frame batch)")
-    ap.add_argument("--e2e-frames", type=int, default=1 << 17, help="frames per host-buffer call of the e2e arm")
-    ap.add_argument("--chunk", type=int, default=37888, help="items per pipeline pass inside the library (2 CTAs x 148 SMs x 128 frames: one full wave of k_viterbi_tp)")
+    ap.add_argument("--e2e-frames", type=int, default=4 * 56832, help="frames per host-buffer call of the e2e arm (4 pipeline chunks)")
+    ap.add_argument("--chunk", type=int, default=56832, help="items per pipeline pass inside the library (3 CTAs x 148 SMs x 128 frames: one full wave of k_viterbi_tp)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -43,3 +43,4 @@ void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_
                          float2* chan, cudaStream_t st);
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
                          const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
+int c8b_viterbi_tp_wave(int num_sm);

@@ -134,7 +134,7 @@ int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evVit[k], cudaEventDisableTiming);
     }
     ctx->overlap = ctx->cfg.no_overlap == 0;
-    if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = (e == cudaSuccess && ctx->numSM > 0 ? ctx->numSM : 148) * 256;   // one full wave of k_viterbi_tp
+    if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = c8b_viterbi_tp_wave(e == cudaSuccess && ctx->numSM > 0 ? ctx->numSM : 148);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->numSM, cudaDevAttrMultiProcessorCount, ctx->device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_lut, sizeof(c8b_lut));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 64);

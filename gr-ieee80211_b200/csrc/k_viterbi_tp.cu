@@ -148,7 +148,10 @@ __device__ void emit_record_t(uint8_t* __restrict__ out, int& w, int cap, int& n
     npdu++;
 }
 
-__global__ void __launch_bounds__(TPB, 2)
+#ifndef C8B_TP_CTAS
+#define C8B_TP_CTAS 3                          // CTAs per SM (168 registers per thread, no spills; 4 would spill the metrics)
+#endif
+__global__ void __launch_bounds__(TPB, C8B_TP_CTAS)
 k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
              int64_t nllr, uint2* __restrict__ survAll, uint32_t* __restrict__ wordsAll, size_t survPerCta, size_t wordsPerCta,
              uint8_t* __restrict__ pdu, int64_t pduStride, uint8_t* __restrict__ scram, int64_t scramStride)
@@ -348,8 +351,10 @@ size_t c8b_viterbi_tp_scratch_bytes(int num_sm)
 {
     const size_t survPerCta = (size_t)(C8B_DECODE_T_MAX + CS + 2) * TPB;                 // uint2
     const size_t wordsPerCta = (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB;        // uint32
-    return (size_t)num_sm * 2 * (survPerCta * sizeof(uint2) + wordsPerCta * sizeof(uint32_t));
+    return (size_t)num_sm * C8B_TP_CTAS * (survPerCta * sizeof(uint2) + wordsPerCta * sizeof(uint32_t));
 }
+
+int c8b_viterbi_tp_wave(int num_sm) { return num_sm * C8B_TP_CTAS * TPB; }   // frames in one full wave
 
 void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, void* d_scratch,
                            int num_sm, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride, cudaStream_t st)
@@ -357,11 +362,11 @@ void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframe
     if (nframes <= 0) return;
     const size_t survPerCta = (size_t)(C8B_DECODE_T_MAX + CS + 2) * TPB;
     const size_t wordsPerCta = (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB;
-    int grid = num_sm * 2;
+    int grid = num_sm * C8B_TP_CTAS;
     const int need = (nframes + TPB - 1) / TPB;
     if (grid > need) grid = need;
     uint2* surv = reinterpret_cast<uint2*>(d_scratch);
-    uint32_t* words = reinterpret_cast<uint32_t*>(surv + (size_t)num_sm * 2 * survPerCta);
+    uint32_t* words = reinterpret_cast<uint32_t*>(surv + (size_t)num_sm * C8B_TP_CTAS * survPerCta);
     const size_t smem = sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2 + 1024 + 512;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_viterbi_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }

@@ -124,7 +124,7 @@ def test_config5_vht_mcs7_1500B_shard():
     import bench
     pkg = load_pkg()
     dev = torch.device("cuda", 0)
-    n = 2 * 37888
+    n = 2 * 56832
     iq, mpdus = bench.make_batch_device(torch, dev, n, seed=5)
     off = np.arange(n, dtype=np.int64) * bench.ITEM
     ln = np.full(n, bench.ITEM, np.int32)
