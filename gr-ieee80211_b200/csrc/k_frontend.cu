@@ -12,78 +12,99 @@ namespace {
 
 using c8b::cf;
 
-constexpr int PT = 1024;           // outputs per CTA
-constexpr int PH = 64;             // history of the 64-sample power window
-constexpr int PTHREADS = 256;
+constexpr int PWARPS = 4;           // warps per CTA, each sweeping its own segment
+constexpr int PSEG = 160;           // rows (32 samples) of output per warp segment
+constexpr int PDEPTH = 4;           // rows of iq in flight per warp
+constexpr unsigned PFULL = 0xffffffffu;
+
+struct f3 { float x, y, z; };       // (re, im) of the lag-16 product sum and |x|^2 sum
+__device__ __forceinline__ f3 add3(f3 a, f3 b) { return { __fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z) }; }
+
+// value `lag` samples back along the stream: lane - lag of this row, or of the previous row for the first `lag` lanes
+__device__ __forceinline__ float back(float cur, float prev, int lane, int lag)
+{
+    return __shfl_sync(PFULL, lane >= 32 - lag ? prev : cur, (lane - lag) & 31);
+}
+__device__ __forceinline__ f3 back3(f3 cur, f3 prev, int lane, int lag)
+{
+    return { back(cur.x, prev.x, lane, lag), back(cur.y, prev.y, lane, lag), back(cur.z, prev.z, lane, lag) };
+}
+// value 16 samples back: the partner lane (lane ^ 16) of this row for the upper half-warp, of the previous row for the lower
+__device__ __forceinline__ float back16(float cur, float prev, int lane)
+{
+    return __shfl_xor_sync(PFULL, lane < 16 ? cur : prev, 16);
+}
 
 // The moving sums are evaluated as a fixed sliding tree so every output is a pure function of the 64
 // (80) samples before it, independent of tiling: s2[n]=v[n-1]+v[n]; s4[n]=s2[n-2]+s2[n]; s8; s16;
 // sum48[n]=(s16[n-32]+s16[n-16])+s16[n]; sum64[n]=(s16[n-48]+s16[n-32])+(s16[n-16]+s16[n]).
-__global__ void __launch_bounds__(PTHREADS)
-k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int64_t outBase,
-          float* __restrict__ preac, float2* __restrict__ preconj, uint32_t* __restrict__ mask, int maskStride)
+// A warp sweeps a segment of one item row by row (lane l <-> sample 32 r + l): each sample is loaded once, coalesced,
+// and every lag is a register of the previous row or one shuffle -- no shared memory, no barrier.  A segment that
+// does not start the item first runs 3 rows of history (x[i-16] of the products + the 15-sample tree + the 48 lag).
+__global__ void __launch_bounds__(PWARPS * 32)
+k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int nitems, int nseg,
+          int64_t outBase, float* __restrict__ preac, float2* __restrict__ preconj, uint32_t* __restrict__ mask, int maskStride)
 {
-    __shared__ float4 s[PT + PH];                   // (re, im, |x|^2, -) of v at item index t0 - 64 + j
-    const int item = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * PWARPS + (threadIdx.x >> 5);
+    const int item = (int)(wid / nseg), seg = (int)(wid % nseg);
+    if (item >= nitems) return;
     const int n = len[item];
-    const int t0 = blockIdx.x * PT;
-    if (t0 >= n) return;
+    const int r0 = seg * PSEG;                                  // first output row
+    if (r0 * 32 >= n) return;
+    const int rEnd = min(r0 + PSEG, (n + 31) >> 5);
+    const int rStart = max(0, r0 - 3);
     const float2* __restrict__ x = iq + off[item];
     const int64_t ob = off[item] - outBase;
-    // products for j in [0, PT+64): index i = t0 - 64 + j
-    for (int j = threadIdx.x; j < PT + PH; j += PTHREADS) {
-        const int i = t0 - PH + j;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i >= 0 && i < n) {
-            const float2 c = x[i];
-            v.z = __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y));          // complex_to_mag_squared
-            if (i >= 16) {
-                const float2 d = x[i - 16];                                     // delay(16), in0 * conj(in1)
-                v.x = __fadd_rn(__fmul_rn(d.x, c.x), __fmul_rn(d.y, c.y));
-                v.y = __fsub_rn(__fmul_rn(d.y, c.x), __fmul_rn(d.x, c.y));
+    uint32_t* __restrict__ mrow = mask ? mask + (size_t)item * maskStride : nullptr;
+
+    auto fetch = [&](int r) {
+        const int i = r * 32 + lane;
+        return (r < rEnd && i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+    };
+    float2 q[PDEPTH];
+#pragma unroll
+    for (int d = 0; d < PDEPTH; d++) q[d] = fetch(rStart + d);
+
+    const f3 z3 = { 0.f, 0.f, 0.f };
+    float2 xp = make_float2(0.f, 0.f);                          // previous row: samples, products, tree levels
+    f3 vp = z3, s2p = z3, s4p = z3, s8p = z3, s16p = z3;
+    float pw2p = 0.f;                                           // |x|^2 s16 two rows back
+    for (int rb = rStart; rb < rEnd; rb += PDEPTH) {
+#pragma unroll
+        for (int d = 0; d < PDEPTH; d++) {
+            const int r = rb + d;                               // rows past rEnd (at most PDEPTH - 1) are zeros, not stored
+            const float2 c = q[d];
+            q[d] = fetch(r + PDEPTH);
+            const int i = r * 32 + lane;
+            const float2 dl = make_float2(back16(c.x, xp.x, lane), back16(c.y, xp.y, lane));     // delay(16)
+            f3 v;
+            v.x = __fadd_rn(__fmul_rn(dl.x, c.x), __fmul_rn(dl.y, c.y));                        // in0 * conj(in1)
+            v.y = __fsub_rn(__fmul_rn(dl.y, c.x), __fmul_rn(dl.x, c.y));
+            v.z = __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y));                          // complex_to_mag_squared
+            if (i < 16) { v.x = 0.f; v.y = 0.f; }
+            const f3 s2 = add3(back3(v, vp, lane, 1), v);
+            const f3 s4 = add3(back3(s2, s2p, lane, 2), s2);
+            const f3 s8 = add3(back3(s4, s4p, lane, 4), s4);
+            const f3 s16 = add3(back3(s8, s8p, lane, 8), s8);
+            const f3 a1 = { back16(s16.x, s16p.x, lane), back16(s16.y, s16p.y, lane), back16(s16.z, s16p.z, lane) };
+            const float pw3 = back16(s16p.z, pw2p, lane);
+            const float cr = __fadd_rn(__fadd_rn(s16p.x, a1.x), s16.x), ci = __fadd_rn(__fadd_rn(s16p.y, a1.y), s16.y);
+            const float pw = __fadd_rn(__fadd_rn(pw3, s16p.z), __fadd_rn(a1.z, s16.z));
+            xp = c; vp = v; s2p = s2; s4p = s4; s8p = s8; pw2p = s16p.z; s16p = s16;
+            if (r >= r0 && r < rEnd) {                                                          // warp-uniform
+                const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));  // complex_to_mag
+                const float ac = __fdiv_rn(mag, pw);                                            // divide_ff
+                const bool in = i < n;
+                if (in) {
+                    preac[ob + i] = ac;
+                    if (preconj) preconj[ob + i] = make_float2(cr, ci);
+                }
+                if (mrow) {                                     // threshold bitmap for the trigger scan (lib/trigger_impl.cc:79)
+                    const uint32_t m = __ballot_sync(PFULL, in && ac > 0.3f);
+                    if (lane == 0) mrow[r] = m;
+                }
             }
-        }
-        s[j] = v;
-    }
-    __syncthreads();
-    constexpr int PER = (PT + PH + PTHREADS - 1) / PTHREADS;
-#pragma unroll
-    for (int lag = 1; lag < 16; lag <<= 1) {
-        float4 r[PER];
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            const int j = threadIdx.x + q * PTHREADS;
-            if (j < PT + PH) {
-                const float4 b = s[j];
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j >= lag) a = s[j - lag];
-                r[q] = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), 0.f);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            const int j = threadIdx.x + q * PTHREADS;
-            if (j < PT + PH) s[j] = r[q];
-        }
-        __syncthreads();
-    }
-    // s[j] = s16 at index t0-64+j (exact for j >= 15; outputs use j >= 16)
-    for (int k = threadIdx.x; k < PT; k += PTHREADS) {
-        const int i = t0 + k;
-        if (i >= n) break;
-        const int j = k + PH;
-        const float4 a0 = s[j], a1 = s[j - 16], a2 = s[j - 32], a3 = s[j - 48];
-        const float cr = __fadd_rn(__fadd_rn(a2.x, a1.x), a0.x), ci = __fadd_rn(__fadd_rn(a2.y, a1.y), a0.y);
-        const float pw = __fadd_rn(__fadd_rn(a3.z, a2.z), __fadd_rn(a1.z, a0.z));
-        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));   // complex_to_mag
-        const float ac = __fdiv_rn(mag, pw);                                                // divide_ff
-        preac[ob + i] = ac;
-        if (preconj) preconj[ob + i] = make_float2(cr, ci);
-        if (mask) {                                        // threshold bitmap for the trigger scan (lib/trigger_impl.cc:79)
-            // i is a multiple of 32 at lane 0 (t0 and k are); lanes past the end of the item left the loop above
-            const uint32_t m = __ballot_sync(__activemask(), ac > 0.3f);
-            if ((threadIdx.x & 31) == 0) mask[(size_t)item * maskStride + (i >> 5)] = m;
         }
     }
 }
@@ -178,12 +199,10 @@ void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d
                         float* preac, float2* preconj, uint32_t* mask, int maskStride, cudaStream_t st)
 {
     if (nitems <= 0 || maxLen <= 0) return;
-    for (int base = 0; base < nitems; base += 65535) {
-        const int cnt = nitems - base < 65535 ? nitems - base : 65535;
-        dim3 grid((maxLen + PT - 1) / PT, cnt);
-        k_presiso<<<grid, PTHREADS, 0, st>>>(iq, d_off + base, d_len + base, outBase, preac, preconj,
-                                              mask ? mask + (size_t)base * maskStride : nullptr, maskStride);
-    }
+    const int nseg = (maxLen + PSEG * 32 - 1) / (PSEG * 32);
+    const int64_t warps = (int64_t)nitems * nseg;
+    k_presiso<<<(unsigned)((warps + PWARPS - 1) / PWARPS), PWARPS * 32, 0, st>>>(iq, d_off, d_len, nitems, nseg, outBase, preac, preconj,
+                                                                               mask, maskStride);
 }
 
 void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st) { k_trigger<<<1, 32, 0, st>>>(preac, n, out); }

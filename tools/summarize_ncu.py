@@ -24,7 +24,7 @@ for r in rows:
     a[1] += float(r[-1].replace(",", ""))
 tot = sum(v[1] for k, v in agg.items() if k.startswith("k_"))
 with open(os.path.join(out, "launches_%s.md" % rnd), "w") as f:
-    f.write("# ncu launch list, %s (`--metrics gpu__time_duration.sum --clock-control none`, bench.py --frames 65536 --steps 2 --warmup 1)\n\n" % rnd)
+    f.write("# ncu launch list, %s (`--metrics gpu__time_duration.sum --clock-control none`, bench.py --frames 113664 --steps 2 --warmup 1 --no-cpu: two chunks per step)\n\n" % rnd)
     f.write("Per-launch times are cold-cache and serialised by ncu: compare SHARES with bench.py's `stages`, not absolutes.\n\n")
     f.write("| kernel | launches | total ms | avg ms | share of our kernels |\n|---|---|---|---|---|\n")
     for k, v in agg.items():
@@ -75,7 +75,7 @@ for d in data:
     kernels.append(k)
 json.dump(kernels, open(os.path.join(out, "ncu_%s.json" % rnd), "w"), indent=1)
 with open(os.path.join(out, "ncu_%s.md" % rnd), "w") as f:
-    f.write("# ncu --set full --clock-control none, %s (one launch per kernel, bench.py --frames 32768: one chunk of config-5 items)\n\n" % rnd)
+    f.write("# ncu --set full --clock-control none, %s (one launch per kernel, bench.py --frames 56832: one chunk of config-5 items)\n\n" % rnd)
     for k in kernels:
         f.write("## %s\n\n" % k["kernel"])
         for kk, vv in k.items():
