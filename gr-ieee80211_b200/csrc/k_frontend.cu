@@ -14,25 +14,67 @@ using c8b::cf;
 
 constexpr int PWARPS = 4;           // warps per CTA, each sweeping its own segment
 constexpr int PSEG = 160;           // rows (32 samples) of output per warp segment
-constexpr int PDEPTH = 4;           // rows of iq in flight per warp
+constexpr int PDEPTH = 4;           // rows of iq in flight per warp = rows per unrolled group
 constexpr unsigned PFULL = 0xffffffffu;
+static_assert(PSEG % PDEPTH == 0, "a segment is a whole number of row groups");
 
 struct f3 { float x, y, z; };       // (re, im) of the lag-16 product sum and |x|^2 sum
 __device__ __forceinline__ f3 add3(f3 a, f3 b) { return { __fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z) }; }
 
-// value `lag` samples back along the stream: lane - lag of this row, or of the previous row for the first `lag` lanes
-__device__ __forceinline__ float back(float cur, float prev, int lane, int lag)
+// per-lane all-ones / all-zeros words: "this lane sends its previous-row value" for the lags 1, 2, 4, 8, 16.  Kept opaque
+// so the selects stay single LOP3s on registers instead of a compare + FSEL per row.
+struct PMasks { uint32_t m1, m2, m4, m8, m16; };
+__device__ __forceinline__ uint32_t opaque(uint32_t m) { asm volatile("" : "+r"(m)); return m; }
+__device__ __forceinline__ float selm(uint32_t m, float a, float b)          // m ? a : b
 {
-    return __shfl_sync(PFULL, lane >= 32 - lag ? prev : cur, (lane - lag) & 31);
+    return __uint_as_float((__float_as_uint(a) & m) | (__float_as_uint(b) & ~m));
 }
-__device__ __forceinline__ f3 back3(f3 cur, f3 prev, int lane, int lag)
+// value `lag` samples back along the stream: lane - lag of this row, or of the previous row for the first `lag` lanes
+__device__ __forceinline__ f3 back3(f3 cur, f3 prev, uint32_t m, int src)
 {
-    return { back(cur.x, prev.x, lane, lag), back(cur.y, prev.y, lane, lag), back(cur.z, prev.z, lane, lag) };
+    return { __shfl_sync(PFULL, selm(m, prev.x, cur.x), src), __shfl_sync(PFULL, selm(m, prev.y, cur.y), src),
+             __shfl_sync(PFULL, selm(m, prev.z, cur.z), src) };
 }
 // value 16 samples back: the partner lane (lane ^ 16) of this row for the upper half-warp, of the previous row for the lower
-__device__ __forceinline__ float back16(float cur, float prev, int lane)
+__device__ __forceinline__ float back16(float cur, float prev, uint32_t m16) { return __shfl_xor_sync(PFULL, selm(m16, prev, cur), 16); }
+
+struct PState {                     // previous row: samples, products, tree levels; |x|^2 s16 two rows back
+    float2 xp; f3 vp, s2p, s4p, s8p, s16p; float pw2p;
+};
+
+// one row: lane l <-> sample i = 32 r + l.  pa / pc / pm point at this row's outputs (pm: the row's bitmap word).
+template <bool OUT, bool CONJ, bool MASK>
+__device__ __forceinline__ void presiso_row(PState& S, const float2 c, const int i, const int n, const PMasks& M, const int lane,
+                                            float* __restrict__ pa, float2* __restrict__ pc, uint32_t* __restrict__ pm)
 {
-    return __shfl_xor_sync(PFULL, lane < 16 ? cur : prev, 16);
+    const float2 dl = make_float2(back16(c.x, S.xp.x, M.m16), back16(c.y, S.xp.y, M.m16));      // delay(16)
+    f3 v;
+    v.x = __fadd_rn(__fmul_rn(dl.x, c.x), __fmul_rn(dl.y, c.y));                                // in0 * conj(in1)
+    v.y = __fsub_rn(__fmul_rn(dl.y, c.x), __fmul_rn(dl.x, c.y));
+    v.z = __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y));                                  // complex_to_mag_squared
+    if (i < 16) { v.x = 0.f; v.y = 0.f; }
+    const f3 s2 = add3(back3(v, S.vp, M.m1, (lane - 1) & 31), v);
+    const f3 s4 = add3(back3(s2, S.s2p, M.m2, (lane - 2) & 31), s2);
+    const f3 s8 = add3(back3(s4, S.s4p, M.m4, (lane - 4) & 31), s4);
+    const f3 s16 = add3(back3(s8, S.s8p, M.m8, (lane - 8) & 31), s8);
+    if (OUT) {
+        const f3 a1 = { back16(s16.x, S.s16p.x, M.m16), back16(s16.y, S.s16p.y, M.m16), back16(s16.z, S.s16p.z, M.m16) };
+        const float pw3 = back16(S.s16p.z, S.pw2p, M.m16);
+        const float cr = __fadd_rn(__fadd_rn(S.s16p.x, a1.x), s16.x), ci = __fadd_rn(__fadd_rn(S.s16p.y, a1.y), s16.y);
+        const float pw = __fadd_rn(__fadd_rn(pw3, S.s16p.z), __fadd_rn(a1.z, s16.z));
+        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));          // complex_to_mag
+        const float ac = __fdiv_rn(mag, pw);                                                    // divide_ff
+        const bool in = i < n;
+        if (in) {
+            *pa = ac;
+            if (CONJ) *pc = make_float2(cr, ci);
+        }
+        if (MASK) {                                             // threshold bitmap for the trigger scan (lib/trigger_impl.cc:79)
+            const uint32_t m = __ballot_sync(PFULL, in && ac > 0.3f);
+            if (lane == 0 && in) *pm = m;
+        }
+    }
+    S.xp = c; S.vp = v; S.s2p = s2; S.s4p = s4; S.s8p = s8; S.pw2p = S.s16p.z; S.s16p = s16;
 }
 
 // The moving sums are evaluated as a fixed sliding tree so every output is a pure function of the 64
@@ -40,8 +82,10 @@ __device__ __forceinline__ float back16(float cur, float prev, int lane)
 // sum48[n]=(s16[n-32]+s16[n-16])+s16[n]; sum64[n]=(s16[n-48]+s16[n-32])+(s16[n-16]+s16[n]).
 // A warp sweeps a segment of one item row by row (lane l <-> sample 32 r + l): each sample is loaded once, coalesced,
 // and every lag is a register of the previous row or one shuffle -- no shared memory, no barrier.  A segment that
-// does not start the item first runs 3 rows of history (x[i-16] of the products + the 15-sample tree + the 48 lag).
-__global__ void __launch_bounds__(PWARPS * 32)
+// does not start the item first runs one group of history rows (3 are needed: x[i-16] of the products, the 15-sample
+// tree, the 48 lag) without output.
+template <bool CONJ, bool MASK>
+__global__ void __launch_bounds__(PWARPS * 32, 6)
 k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int nitems, int nseg,
           int64_t outBase, float* __restrict__ preac, float2* __restrict__ preconj, uint32_t* __restrict__ mask, int maskStride)
 {
@@ -52,60 +96,49 @@ k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const 
     const int n = len[item];
     const int r0 = seg * PSEG;                                  // first output row
     if (r0 * 32 >= n) return;
-    const int rEnd = min(r0 + PSEG, (n + 31) >> 5);
-    const int rStart = max(0, r0 - 3);
+    const int nEnd = min(n, (r0 + PSEG) * 32);                  // one past the last sample this warp needs
+    const int rStart = r0 > 0 ? r0 - PDEPTH : 0;
+    int i = rStart * 32 + lane;
     const float2* __restrict__ x = iq + off[item];
+    const int iLast = nEnd - 1;                                 // loads past the end re-read this sample: those lanes store nothing
     const int64_t ob = off[item] - outBase;
-    uint32_t* __restrict__ mrow = mask ? mask + (size_t)item * maskStride : nullptr;
+    float* __restrict__ pa = preac + ob + i;
+    float2* __restrict__ pc = CONJ ? preconj + ob + i : nullptr;
+    uint32_t* __restrict__ pm = MASK ? mask + (size_t)item * maskStride + rStart : nullptr;
+    PMasks M;
+    M.m1 = opaque(lane >= 31 ? ~0u : 0u); M.m2 = opaque(lane >= 30 ? ~0u : 0u); M.m4 = opaque(lane >= 28 ? ~0u : 0u);
+    M.m8 = opaque(lane >= 24 ? ~0u : 0u); M.m16 = opaque(lane >= 16 ? ~0u : 0u);
 
-    auto fetch = [&](int r) {
-        const int i = r * 32 + lane;
-        return (r < rEnd && i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
-    };
+    const float2 z2 = make_float2(0.f, 0.f);
     float2 q[PDEPTH];
 #pragma unroll
-    for (int d = 0; d < PDEPTH; d++) q[d] = fetch(rStart + d);
-
+    for (int d = 0; d < PDEPTH; d++) q[d] = __ldg(x + min(i + 32 * d, iLast));
     const f3 z3 = { 0.f, 0.f, 0.f };
-    float2 xp = make_float2(0.f, 0.f);                          // previous row: samples, products, tree levels
-    f3 vp = z3, s2p = z3, s4p = z3, s8p = z3, s16p = z3;
-    float pw2p = 0.f;                                           // |x|^2 s16 two rows back
-    for (int rb = rStart; rb < rEnd; rb += PDEPTH) {
+    PState S = { z2, z3, z3, z3, z3, z3, 0.f };
+    if (r0 > 0) {                                               // history rows of a later segment
+        float2 nq[PDEPTH];                                      // the next group's rows, requested back to back (1 KB contiguous)
 #pragma unroll
-        for (int d = 0; d < PDEPTH; d++) {
-            const int r = rb + d;                               // rows past rEnd (at most PDEPTH - 1) are zeros, not stored
-            const float2 c = q[d];
-            q[d] = fetch(r + PDEPTH);
-            const int i = r * 32 + lane;
-            const float2 dl = make_float2(back16(c.x, xp.x, lane), back16(c.y, xp.y, lane));     // delay(16)
-            f3 v;
-            v.x = __fadd_rn(__fmul_rn(dl.x, c.x), __fmul_rn(dl.y, c.y));                        // in0 * conj(in1)
-            v.y = __fsub_rn(__fmul_rn(dl.y, c.x), __fmul_rn(dl.x, c.y));
-            v.z = __fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y));                          // complex_to_mag_squared
-            if (i < 16) { v.x = 0.f; v.y = 0.f; }
-            const f3 s2 = add3(back3(v, vp, lane, 1), v);
-            const f3 s4 = add3(back3(s2, s2p, lane, 2), s2);
-            const f3 s8 = add3(back3(s4, s4p, lane, 4), s4);
-            const f3 s16 = add3(back3(s8, s8p, lane, 8), s8);
-            const f3 a1 = { back16(s16.x, s16p.x, lane), back16(s16.y, s16p.y, lane), back16(s16.z, s16p.z, lane) };
-            const float pw3 = back16(s16p.z, pw2p, lane);
-            const float cr = __fadd_rn(__fadd_rn(s16p.x, a1.x), s16.x), ci = __fadd_rn(__fadd_rn(s16p.y, a1.y), s16.y);
-            const float pw = __fadd_rn(__fadd_rn(pw3, s16p.z), __fadd_rn(a1.z, s16.z));
-            xp = c; vp = v; s2p = s2; s4p = s4; s8p = s8; pw2p = s16p.z; s16p = s16;
-            if (r >= r0 && r < rEnd) {                                                          // warp-uniform
-                const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci)));  // complex_to_mag
-                const float ac = __fdiv_rn(mag, pw);                                            // divide_ff
-                const bool in = i < n;
-                if (in) {
-                    preac[ob + i] = ac;
-                    if (preconj) preconj[ob + i] = make_float2(cr, ci);
-                }
-                if (mrow) {                                     // threshold bitmap for the trigger scan (lib/trigger_impl.cc:79)
-                    const uint32_t m = __ballot_sync(PFULL, in && ac > 0.3f);
-                    if (lane == 0) mrow[r] = m;
-                }
-            }
-        }
+        for (int d = 0; d < PDEPTH; d++) nq[d] = __ldg(x + min(i + 32 * (d + PDEPTH), iLast));
+#pragma unroll
+        for (int d = 0; d < PDEPTH; d++) presiso_row<false, CONJ, MASK>(S, q[d], i + 32 * d, n, M, lane, nullptr, nullptr, nullptr);
+#pragma unroll
+        for (int d = 0; d < PDEPTH; d++) q[d] = nq[d];
+        i += 32 * PDEPTH; pa += 32 * PDEPTH;
+        if (CONJ) pc += 32 * PDEPTH;
+        if (MASK) pm += PDEPTH;
+    }
+    for (; i - lane < nEnd; i += 32 * PDEPTH) {                 // causal sums: samples at or past n never reach a stored output
+        float2 nq[PDEPTH];
+#pragma unroll
+        for (int d = 0; d < PDEPTH; d++) nq[d] = __ldg(x + min(i + 32 * (d + PDEPTH), iLast));
+#pragma unroll
+        for (int d = 0; d < PDEPTH; d++)
+            presiso_row<true, CONJ, MASK>(S, q[d], i + 32 * d, n, M, lane, pa + 32 * d, CONJ ? pc + 32 * d : nullptr, MASK ? pm + d : nullptr);
+#pragma unroll
+        for (int d = 0; d < PDEPTH; d++) q[d] = nq[d];
+        pa += 32 * PDEPTH;
+        if (CONJ) pc += 32 * PDEPTH;
+        if (MASK) pm += PDEPTH;
     }
 }
 
@@ -201,8 +234,11 @@ void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d
     if (nitems <= 0 || maxLen <= 0) return;
     const int nseg = (maxLen + PSEG * 32 - 1) / (PSEG * 32);
     const int64_t warps = (int64_t)nitems * nseg;
-    k_presiso<<<(unsigned)((warps + PWARPS - 1) / PWARPS), PWARPS * 32, 0, st>>>(iq, d_off, d_len, nitems, nseg, outBase, preac, preconj,
-                                                                               mask, maskStride);
+    const unsigned grid = (unsigned)((warps + PWARPS - 1) / PWARPS);
+#define C8B_PRESISO(CJ, MK) k_presiso<CJ, MK><<<grid, PWARPS * 32, 0, st>>>(iq, d_off, d_len, nitems, nseg, outBase, preac, preconj, mask, maskStride)
+    if (preconj) { if (mask) C8B_PRESISO(true, true); else C8B_PRESISO(true, false); }
+    else         { if (mask) C8B_PRESISO(false, true); else C8B_PRESISO(false, false); }
+#undef C8B_PRESISO
 }
 
 void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st) { k_trigger<<<1, 32, 0, st>>>(preac, n, out); }
