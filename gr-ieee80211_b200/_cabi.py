@@ -56,6 +56,9 @@ SYMBOLS = [
     ("c8b_rx_batch_dev", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch_dev_async", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_sync", _i, [_vp]),
+    ("c8b_stream_begin", _i, [_vp, _i, _i64]),
+    ("c8b_stream_push", _i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _i64]),
+    ("c8b_stream_state", _i, [_vp, _vp, _vp, _vp]),
     ("c8b_timing_enable", _i, [_vp, _i]),
     ("c8b_timing_read", _i, [_vp, _vp, _vp, _i]),
     ("c8b_presiso", _i, [_vp, _vp, _i64, _vp, _vp]),

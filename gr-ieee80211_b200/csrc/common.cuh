@@ -26,7 +26,7 @@ void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d
 void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st);
 void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                        int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
-                       float2* chan, cudaStream_t st);
+                       float2* chan, c8b_scan* scans, cudaStream_t st);
 void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
                        const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
 void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int maxSym, const c8b_frame* frames,
@@ -40,7 +40,7 @@ void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframe
                            int num_sm, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride, cudaStream_t st);
 void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                          int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
-                         float2* chan, cudaStream_t st);
+                         float2* chan, c8b_scan* scans, cudaStream_t st);
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
                          const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
 int c8b_viterbi_tp_wave(int num_sm);

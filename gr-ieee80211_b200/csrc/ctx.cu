@@ -27,6 +27,19 @@ struct c8b_ctx {
     // scratch (grown on demand)
     DevBuf iq, iq1, mask, llrB, tp, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
     int survWarps = 0;
+    // live-stream session (c8b_stream_*): a device-resident window of the capture, ping-pong compacted
+    struct Stream {
+        bool open = false;
+        int nant = 1, cur = 0;
+        int64_t cap = 0;        // window capacity, samples
+        int64_t base = 0;       // absolute stream index of window sample 0
+        int64_t fill = 0;       // samples in the window
+        int32_t from = 0;       // first window sample the trigger FSM sees
+        int64_t posAbs = 0;     // signal block's consumed-until, absolute
+        int64_t overruns = 0;   // windows dropped because nothing in them could be decided
+    } strm;
+    DevBuf sw[2][2], scan;      // [antenna][ping-pong]
+    c8b_scan* scanDev = nullptr;   // non-null while run_chunk serves a stream window
     // timing
     bool timing = false;
     double ms[C8B_K_COUNT] = { 0 };
@@ -134,8 +147,8 @@ int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evVit[k], cudaEventDisableTiming);
     }
     ctx->overlap = ctx->cfg.no_overlap == 0;
-    if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = c8b_viterbi_tp_wave(e == cudaSuccess && ctx->numSM > 0 ? ctx->numSM : 148);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->numSM, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = c8b_viterbi_tp_wave(e == cudaSuccess && ctx->numSM > 0 ? ctx->numSM : 148);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_lut, sizeof(c8b_lut));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 64);
     if (e != cudaSuccess) { g_createErr = std::string("c8b_create: ") + cudaGetErrorString(e); delete ctx; return C8B_ERR_CUDA; }
@@ -153,7 +166,8 @@ void c8b_destroy(c8b_ctx* ctx)
     for (int k = 0; k < 2; k++) { if (ctx->evFront[k]) cudaEventDestroy(ctx->evFront[k]); if (ctx->evVit[k]) cudaEventDestroy(ctx->evVit[k]); }
     if (ctx->stVit) cudaStreamDestroy(ctx->stVit);
     DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->tp, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
-                       &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev };
+                       &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev, &ctx->scan, &ctx->sw[0][0], &ctx->sw[0][1],
+                       &ctx->sw[1][0], &ctx->sw[1][1] };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -387,7 +401,7 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
         StageTimer tm(ctx, C8B_K_DETECT);
         (ctx->cfg.frontend_mode == 1 ? c8b_launch_detect : c8b_launch_detect_w)(
             ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p, maskStride,
-            d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->st);
+            d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->scanDev, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_HEADER);
@@ -648,7 +662,7 @@ int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_
         StageTimer tm(ctx, C8B_K_DETECT);
         (ctx->cfg.frontend_mode == 1 ? c8b_launch_detect : c8b_launch_detect_w)(
             ctx->d_lut, iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, nitems, 0, maxf, pl.base, (const float*)ctx->preac.p,
-            (const uint32_t*)ctx->mask.p, maskStride, (c8b_frame*)ctx->frames.p, (float2*)ctx->chan.p, ctx->st);
+            (const uint32_t*)ctx->mask.p, maskStride, (c8b_frame*)ctx->frames.p, (float2*)ctx->chan.p, nullptr, ctx->st);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(frames, ctx->frames.p, ns * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
@@ -737,6 +751,156 @@ int c8b_demod2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64
     CK(cudaMemcpyAsync(frames, ctx->frames.p, ns * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(h_llr, ctx->llr.p, ns * llr_stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
+// ---- live stream ------------------------------------------------------------------------------------
+// The reference's blocks run on an endless stream and keep their state between general_work calls.  Here the
+// session keeps a device-resident window of the capture.  Every push appends samples and runs the whole chain on
+// the window as ONE item; the detect kernel reports the latest point `safe` before which everything is decided
+// and at which the trigger FSM is in its reset state (c8b_scan, lut.h).  Frames triggered before `safe` are
+// returned; the window is then cut to [safe - 64, fill) -- 64 samples of presiso history -- and the next scan
+// starts the FSM at `safe` with the signal block's consumed-until position carried over.  Because presiso is a
+// pure function of the 64 previous samples and the FSM restarts from a state it provably had, the frames and
+// PDUs are the ones a single pass over the whole capture finds, whatever the push sizes.
+int c8b_stream_begin(c8b_ctx* ctx, int nant, int64_t window_samples)
+{
+    if (!ctx || (nant != 1 && nant != 2)) return C8B_ERR_ARG;
+    if (window_samples <= 0) window_samples = (int64_t)1 << 22;
+    if (window_samples < 4096 || window_samples > 0x7ffffff0) { ctx->err = "stream window: 4096 .. 2^31-16 samples"; return C8B_ERR_ARG; }
+    if (ctx->cfg.max_frames < 2) { ctx->err = "c8b_stream_*: the ctx needs max_frames >= 2"; return C8B_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    for (int a = 0; a < nant; a++)
+        for (int k = 0; k < 2; k++) {
+            int r = ensure(ctx, ctx->sw[a][k], (size_t)(window_samples + 16) * sizeof(float2));
+            if (r) return r;
+        }
+    EN(scan, sizeof(c8b_scan));
+    ctx->strm = c8b_ctx::Stream();
+    ctx->strm.open = true; ctx->strm.nant = nant; ctx->strm.cap = window_samples;
+    return C8B_OK;
+}
+
+// one pass of the chain over the current window; appends the decided frames to the caller's arrays
+static int stream_process(c8b_ctx* ctx, bool flush, c8b_frame* frames, int frames_cap, int* nframes, int64_t* frame_base, uint8_t* pdu,
+                          int64_t pdu_stride, int* stalled)
+{
+    c8b_ctx::Stream& S = ctx->strm;
+    *stalled = 0;
+    if (S.fill <= S.from && !flush) return C8B_OK;                 // nothing new to scan
+    if (S.fill == 0) return C8B_OK;
+    const int maxf = ctx->cfg.max_frames;
+    const int64_t off = 0;
+    const int32_t len = (int32_t)S.fill;
+    int r = upload_items(ctx, &off, &len, 1);
+    if (r) return r;
+    c8b_scan sc;
+    memset(&sc, 0, sizeof sc);
+    const int64_t p0 = S.posAbs - S.base;
+    sc.from = S.from; sc.flush = flush ? 1 : 0;
+    sc.pos0 = p0 < -0x40000000 ? -0x40000000 : (p0 > 0x7fffffff ? 0x7fffffff : (int32_t)p0);
+    CK(cudaMemcpyAsync(ctx->scan.p, &sc, sizeof sc, cudaMemcpyHostToDevice, ctx->st));
+    EN(frames, (size_t)maxf * sizeof(c8b_frame));
+    EN(pdu, (size_t)maxf * pdu_stride);
+    CK(cudaMemsetAsync(ctx->frames.p, 0, (size_t)maxf * sizeof(c8b_frame), ctx->st));
+    ctx->scanDev = (c8b_scan*)ctx->scan.p;
+    r = run_chunk(ctx, (const float2*)ctx->sw[0][S.cur].p, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, &off, &len, 0, 1,
+                  (c8b_frame*)ctx->frames.p, (uint8_t*)ctx->pdu.p, pdu_stride, 0, S.nant == 2 ? (const float2*)ctx->sw[1][S.cur].p : nullptr);
+    ctx->scanDev = nullptr;
+    if (r) return r;
+    join_viterbi(ctx);
+    std::vector<c8b_frame> fr((size_t)maxf);
+    CK(cudaMemcpyAsync(fr.data(), ctx->frames.p, (size_t)maxf * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&sc, ctx->scan.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    *stalled = sc.stalled;
+    int take = sc.nf;
+    if (flush) {                                                   // end of stream: every record the batch semantics produced
+        take = 0;
+        while (take < maxf && fr[take].status != C8B_ST_EMPTY && fr[take].nsamp > 0) take++;
+    }
+    for (int k = 0; k < take; k++) {
+        if (*nframes >= frames_cap) { ctx->err = "c8b_stream_push: more frames than frames_cap"; return C8B_ERR_FULL; }
+        const int o = (*nframes)++;
+        frames[o] = fr[k];
+        frames[o].item = o;
+        frames[o].pdu_off = (int64_t)o * pdu_stride;
+        frame_base[o] = S.base;
+        if (fr[k].pdu_bytes > 0)
+            CK(cudaMemcpyAsync(pdu + (size_t)o * pdu_stride, (const uint8_t*)ctx->pdu.p + (size_t)k * pdu_stride, (size_t)fr[k].pdu_bytes,
+                               cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    if (flush) {
+        S.base += S.fill; S.fill = 0; S.from = 0; S.posAbs = S.base;
+        return C8B_OK;
+    }
+    int64_t keep = sc.safe > 64 ? sc.safe - 64 : 0;                // 64 samples of presiso history before the restart point
+    S.posAbs = S.base + sc.pos;
+    if (keep == 0 && S.fill >= S.cap) {                            // a full window without one decidable point: drop it
+        S.overruns++;
+        S.base += S.fill; S.fill = 0; S.from = 0;
+        if (S.posAbs < S.base) S.posAbs = S.base;
+        return C8B_OK;
+    }
+    if (keep > 0) {
+        const int64_t rest = S.fill - keep;
+        for (int a = 0; a < S.nant; a++)
+            CK(cudaMemcpyAsync(ctx->sw[a][S.cur ^ 1].p, (const float2*)ctx->sw[a][S.cur].p + keep, (size_t)rest * sizeof(float2),
+                               cudaMemcpyDeviceToDevice, ctx->st));
+        S.cur ^= 1; S.base += keep; S.fill = rest;
+    }
+    S.from = (int32_t)(sc.safe - keep);
+    return C8B_OK;
+}
+
+int c8b_stream_push(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, int64_t n, int flush, c8b_frame* frames, int frames_cap,
+                    int* nframes, int64_t* frame_base, uint8_t* pdu, int64_t pdu_stride)
+{
+    if (!ctx || n < 0 || (n > 0 && !h_iq0) || !frames || frames_cap < 0 || !nframes || !frame_base || !pdu || pdu_stride <= 0) return C8B_ERR_ARG;
+    *nframes = 0;
+    if (!ctx->strm.open) { ctx->err = "c8b_stream_push: no session (call c8b_stream_begin)"; return C8B_ERR_ARG; }
+    c8b_ctx::Stream& S = ctx->strm;
+    if (S.nant == 2 && n > 0 && !h_iq1) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    int64_t done = 0;
+    for (;;) {
+        const int64_t room = S.cap - S.fill;
+        const int64_t take = n - done < room ? n - done : room;
+        if (take > 0) {
+            CK(cudaMemcpyAsync((float2*)ctx->sw[0][S.cur].p + S.fill, reinterpret_cast<const float2*>(h_iq0) + done, (size_t)take * sizeof(float2),
+                               cudaMemcpyHostToDevice, ctx->st));
+            if (S.nant == 2)
+                CK(cudaMemcpyAsync((float2*)ctx->sw[1][S.cur].p + S.fill, reinterpret_cast<const float2*>(h_iq1) + done,
+                                   (size_t)take * sizeof(float2), cudaMemcpyHostToDevice, ctx->st));
+            S.fill += take; done += take;
+        }
+        const bool last = done == n;
+        int stalled = 0;
+        do {                                                       // frame records used up: the window holds more frames, go again
+            const int64_t before = S.base + S.from;
+            r = stream_process(ctx, false, frames, frames_cap, nframes, frame_base, pdu, pdu_stride, &stalled);
+            if (r) return r;
+            if (S.base + S.from == before) break;                  // no progress: wait for more samples
+        } while (stalled == 2);
+        if (!last) continue;
+        if (flush) {
+            r = stream_process(ctx, true, frames, frames_cap, nframes, frame_base, pdu, pdu_stride, &stalled);
+            if (r) return r;
+        }
+        break;
+    }
+    return C8B_OK;
+}
+
+int c8b_stream_state(const c8b_ctx* ctx, int64_t* base, int64_t* fill, int64_t* overruns)
+{
+    if (!ctx || !ctx->strm.open) return C8B_ERR_ARG;
+    if (base) *base = ctx->strm.base;
+    if (fill) *fill = ctx->strm.fill;
+    if (overruns) *overruns = ctx->strm.overruns;
     return C8B_OK;
 }
 

@@ -153,14 +153,15 @@ __global__ void k_trigger(const float* __restrict__ preac, int64_t n, uint8_t* _
 __global__ void __launch_bounds__(64)
 k_detect(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
          const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preac,
-         const uint32_t* __restrict__ mask, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan)
+         const uint32_t* __restrict__ mask, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan,
+         c8b_scan* __restrict__ scans)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nitems) return;
     // records and channels are written in place (device global memory): frames[i*maxf ..], chan[i*maxf*64 ..]
     c8b::detect_item(lut, reinterpret_cast<const cf*>(iq + off[i]), preac + (off[i] - outBase), len[i], itemBase + i, maxf,
                      frames + (size_t)i * maxf, reinterpret_cast<cf*>(chan + (size_t)i * maxf * 64),
-                     mask ? mask + (size_t)i * maskStride : nullptr);
+                     mask ? mask + (size_t)i * maskStride : nullptr, scans ? scans + i : nullptr);
 }
 
 struct RotSrc {
@@ -245,10 +246,11 @@ void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_
 
 void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                        int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
-                       float2* chan, cudaStream_t st)
+                       float2* chan, c8b_scan* scans, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_detect<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask, maskStride, frames, chan);
+    k_detect<<<(nitems + 63) / 64, 64, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask, maskStride, frames, chan,
+                                                  scans);
 }
 
 void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,

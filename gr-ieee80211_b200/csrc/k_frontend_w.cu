@@ -221,7 +221,8 @@ __device__ int signal_at_w(const c8b_lut* __restrict__ L, const cf* __restrict__
 __global__ void __launch_bounds__(FW * 32)
 k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
            const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preacAll,
-           const uint32_t* __restrict__ maskAll, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan)
+           const uint32_t* __restrict__ maskAll, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan,
+           c8b_scan* __restrict__ scans)
 {
     __shared__ Ws ws[FW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -241,7 +242,11 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     // the blocks' state machines, evaluated uniformly by the warp (see detect_item in phy_serial.cuh)
     TrigState ts;
     trig_reset(ts);
-    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0, nf = 0;
+    c8b_scan* sc = scans ? scans + it : nullptr;                  // window of a live stream (see phy_serial.cuh)
+    const bool live = sc && !sc->flush;
+    const int from = sc ? sc->from : 0;
+    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = sc ? sc->pos0 : 0, nf = 0;
+    int safe = from, posS = pos, nfS = 0, stalled = 0;
     bool syncStalled = false, sigStalled = false, done = false;
     // The scan goes bitmap word by bitmap word (32 samples).  A complete word without a sample above the threshold is
     // not walked: with the trigger idle the FSM stays in its reset state (lib/trigger_impl.cc:95-100) -- all such words up
@@ -251,8 +256,9 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     int blkBase = -(1 << 30);                                        // 32 bitmap words [blkBase, blkBase+32) summarised in nz
     uint32_t nz = 0;                                              // bit k: word blkBase+k must be walked
     const int nwords = (n + 31) >> 5;
-    for (int w = 0; w < nwords && !done;) {
-        if (mask) {
+    for (int w = from >> 5; w < nwords && !done;) {
+        const int kfirst = w == (from >> 5) ? (from & 31) : 0;     // a window may start the FSM inside a word
+        if (mask && kfirst == 0) {
             if (w < blkBase || w >= blkBase + 32) {
                 blkBase = w;
                 const int ww = w + lane;
@@ -264,6 +270,7 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
                 if (ts.fPlateau == 0) {
                     w += rem ? __ffs(rem) - 1 : 32 - (w - blkBase);
                     ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+                    if (w * 32 >= skipUntil) { safe = w * 32; posS = pos; nfS = nf; }
                     continue;
                 }
                 if (ts.countDown > 32) {                          // 32 sub-threshold samples of the count-down
@@ -277,13 +284,17 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
         const int i0 = w * 32;
         const float pv = (i0 + lane < n) ? preac[i0 + lane] : 0.0f;
         const int kmax = min(32, n - i0);
-        for (int k = 0; k < kmax && !done; k++) {
+        for (int k = kfirst; k < kmax && !done; k++) {
             const int i = i0 + k;
+            if (ts.nPlateau == 0 && ts.fPlateau == 0 && i >= skipUntil) { safe = i; posS = pos; nfS = nf; }
             const uint8_t fl = trig_step(ts, __shfl_sync(FULL, pv, k));
             if (fl == 0 || i < skipUntil || syncStalled) continue;
             if (fl & 0x01) {
                 nTrig++;
-                if (n - i < C8B_SYNC_BUF) { syncStalled = true; continue; }
+                if (n - i < C8B_SYNC_BUF) {
+                    if (live) { stalled = 1; done = true; } else syncStalled = true;
+                    continue;
+                }
                 const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
                 const SyncOut so = sync_at_w(x + i, cj, W, lane);
                 skipUntil = i + C8B_SYNC_RES;
@@ -291,7 +302,10 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
                 nEv++;
                 const int idx = i + so.mIndex;
                 if (sigStalled || idx < pos) continue;
-                if (n - idx < 224) { sigStalled = true; continue; }
+                if (n - idx < 224) {
+                    if (live) { stalled = 1; done = true; } else sigStalled = true;
+                    continue;
+                }
                 int mcs = 0, ln = 0, nsamp = 0;
                 if (!signal_at_w(lut, x + idx, so.rad, h + nf * 64, &mcs, &ln, &nsamp, W, lane)) {
                     for (int q = lane; q < 64; q += 32) h[nf * 64 + q] = make_float2(0.f, 0.f);
@@ -306,13 +320,16 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
                     fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);
                     fk->l_mcs = mcs; fk->l_len = ln; fk->nsamp = nsamp; fk->status = status;
                 }
-                if (pos > n || nf >= maxf) done = true;
+                if (pos > n) { done = true; stalled = 1; }
+                else if (nf >= maxf) { done = true; stalled = 2; }
             } else if (fl & 0x02) {
                 latch = i;
             }
         }
         w++;
     }
+    if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && n >= skipUntil) { safe = n; posS = pos; nfS = nf; }
+    if (sc && lane == 0) { sc->safe = safe; sc->pos = posS; sc->nf = nfS; sc->stalled = stalled; }
     if (nf == 0 && lane == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
 }
 
@@ -498,11 +515,11 @@ k_header_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
 
 void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                          int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
-                         float2* chan, cudaStream_t st)
+                         float2* chan, c8b_scan* scans, cudaStream_t st)
 {
     if (nitems <= 0) return;
     k_detect_w<<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask, maskStride,
-                                                            frames, chan);
+                                                            frames, chan, scans);
 }
 
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,

@@ -33,3 +33,18 @@ struct c8b_lut {
 };
 
 void c8b_lut_build(c8b_lut* L);   // host, by formula (lut.cc)
+
+// Scan parameters of one item when it is a window of a live stream (c8b_stream_push): the blocks keep their state across
+// general_work calls (lib/trigger_impl.cc:59, sync_impl.cc:61, signal_impl.cc:62); here a window restarts from a point
+// where that state is known -- the trigger FSM in its reset state, no sync hold-off pending -- and carries only the
+// signal block's consumed-until position.
+struct c8b_scan {
+    int32_t from;        // in:  first sample the trigger FSM sees (samples before it are presiso history only)
+    int32_t pos0;        // in:  signal's consumed-until position, window relative (may be negative)
+    int32_t flush;       // in:  1 = end of stream: stalls are final (batch semantics), 0 = stop at the first stall
+    int32_t safe;        // out: latest sample s with the FSM reset before s and s >= sync hold-off: everything before s is decided
+    int32_t pos;         // out: consumed-until as of `safe`
+    int32_t nf;          // out: frame records that belong to the decided part (their trigger precedes `safe`)
+    int32_t stalled;     // out: 0 scanned to the end, 1 an event needs samples past the window, 2 frame records used up
+    int32_t pad;
+};

@@ -346,24 +346,32 @@ C8B_HD void frame_clear(c8b_frame* f, int item, int status)
 // 32 samples at a time while the trigger is idle (no plateau, no count-down): such a stretch leaves the FSM in its
 // reset state, so skipping it is exact.
 C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int n, int item, int maxf, c8b_frame* f, cf* h,
-                         const uint32_t* mask = nullptr)
+                         const uint32_t* mask = nullptr, c8b_scan* sc = nullptr)
 {
     TrigState ts;
     trig_reset(ts);
-    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0, nf = 0;
+    const bool live = sc && !sc->flush;                           // stop at the first event that needs more samples
+    const int from = sc ? sc->from : 0;
+    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = sc ? sc->pos0 : 0, nf = 0;
+    int safe = from, posS = pos, nfS = 0, stalled = 0;
     bool syncStalled = false, sigStalled = false, done = false;
     for (int k = 0; k < maxf; k++) frame_clear(f + k, item, C8B_ST_EMPTY);
-    for (int i = 0; i < n && !done; i++) {
+    for (int i = from; i < n && !done; i++) {
         if (mask && (i & 31) == 0 && i + 32 <= n && ts.fPlateau == 0 && mask[i >> 5] == 0u) {
             ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;   // what 32 sub-threshold samples leave behind
             i += 31;
+            if (i + 1 >= skipUntil) { safe = i + 1; posS = pos; nfS = nf; }
             continue;
         }
+        if (ts.nPlateau == 0 && ts.fPlateau == 0 && i >= skipUntil) { safe = i; posS = pos; nfS = nf; }
         const uint8_t fl = trig_step(ts, preac[i]);
         if (fl == 0 || i < skipUntil || syncStalled) continue;
         if (fl & 0x01) {
             nTrig++;
-            if (n - i < C8B_SYNC_BUF) { syncStalled = true; continue; }   // sync_impl.cc:94 never satisfied
+            if (n - i < C8B_SYNC_BUF) {                           // sync_impl.cc:94 not satisfied yet / ever
+                if (live) { stalled = 1; done = true; } else syncStalled = true;
+                continue;
+            }
             const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
             const SyncOut so = sync_at(x + i, cj);
             skipUntil = i + C8B_SYNC_RES;
@@ -371,7 +379,10 @@ C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int 
             nEv++;
             const int idx = i + so.mIndex;
             if (sigStalled || idx < pos) continue;                // swallowed by S_COPY / skipped 80
-            if (n - idx < 224) { sigStalled = true; continue; }   // signal_impl.cc:110 stall
+            if (n - idx < 224) {                                  // signal_impl.cc:110 stall
+                if (live) { stalled = 1; done = true; } else sigStalled = true;
+                continue;
+            }
             int mcs = 0, len = 0, nsamp = 0;
             cf* hk = h + nf * 64;
             if (!signal_at(L, x + idx, so.rad, hk, &mcs, &len, &nsamp)) { nLsigFail++; pos = idx + 80; continue; }
@@ -381,13 +392,15 @@ C8B_HDN void detect_item(const c8b_lut* L, const cf* x, const float* preac, int 
             fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);       // signal_impl.cc:135
             fk->l_mcs = mcs; fk->l_len = len; fk->nsamp = nsamp;
             pos = idx + 224 + nsamp;
-            if (pos > n) { fk->status = C8B_ST_TRUNC; done = true; }   // S_COPY can never finish: nothing after it
+            if (pos > n) { fk->status = C8B_ST_TRUNC; done = true; stalled = 1; }   // S_COPY can never finish: nothing after it
             else fk->status = C8B_ST_OK;
-            if (nf >= maxf) done = true;
+            if (nf >= maxf) { done = true; if (!stalled) stalled = 2; }
         } else if (fl & 0x02) {
             latch = i;
         }
     }
+    if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && n >= skipUntil) { safe = n; posS = pos; nfS = nf; }
+    if (sc) { sc->safe = safe; sc->pos = posS; sc->nf = nfS; sc->stalled = stalled; }
     if (nf == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
 }
 

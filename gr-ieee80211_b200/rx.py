@@ -119,6 +119,32 @@ class Receiver:
         self._ck(self.L.c8b_rx_batch2(self.h, ptr(a), ptr(b), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch2")
         return frames, pdu.reshape(ns, pdu_stride)
 
+    # ---- live stream ---------------------------------------------------------------------------
+    def stream_begin(self, nant=1, window=0):
+        """start a session: the capture arrives in pieces (a block shell's general_work calls); needs max_frames >= 2"""
+        self._ck(self.L.c8b_stream_begin(self.h, nant, window), "c8b_stream_begin")
+        self._stream_nant = nant
+
+    def stream_push(self, iq0, iq1=None, flush=False, frames_cap=4096, pdu_stride=4400):
+        """append samples; returns (frames, base, pdu): the frames that became decidable, the absolute stream index
+        their trig_idx / sync_idx are relative to, and their PDU records"""
+        a = _c2f(iq0)
+        b = _c2f(iq1) if iq1 is not None else None
+        n = a.size // 2
+        frames = np.zeros(frames_cap, FRAME_DTYPE)
+        base = np.zeros(frames_cap, np.int64)
+        pdu = np.zeros(frames_cap * pdu_stride, np.uint8)
+        nf = C.c_int(0)
+        self._ck(self.L.c8b_stream_push(self.h, ptr(a) if n else None, ptr(b) if (b is not None and n) else None, n, 1 if flush else 0,
+                                        ptr(frames), frames_cap, C.byref(nf), ptr(base), ptr(pdu), pdu_stride), "c8b_stream_push")
+        k = nf.value
+        return frames[:k].copy(), base[:k].copy(), pdu.reshape(frames_cap, pdu_stride)[:k].copy()
+
+    def stream_state(self):
+        b, f, o = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.c8b_stream_state(self.h, C.byref(b), C.byref(f), C.byref(o)), "c8b_stream_state")
+        return {"base": b.value, "fill": f.value, "overruns": o.value}
+
     def rx_batch_dev(self, d_iq_ptr, off, length, pdu_stride=4400, frames=None, pdu=None):
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)

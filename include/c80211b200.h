@@ -42,6 +42,7 @@ extern "C" {
 #define C8B_ERR_ARG (-3)         /* bad argument / size over the ctx capacity                 */
 #define C8B_ERR_LUT (-4)         /* LUT blob missing, wrong magic/version/size                */
 #define C8B_ERR_NOMEM (-5)
+#define C8B_ERR_FULL (-6)        /* c8b_stream_push: more frames decided than frames_cap      */
 
 /* per-frame status, in pipeline order (what the reference's blocks do at that point) */
 #define C8B_ST_OK 0              /* frame reached decode (PDU count may still be 0: CRC fail)  */
@@ -156,6 +157,22 @@ int  c8b_rx_batch2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const i
 int  c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* h_off, const int32_t* h_len, int nitems,
                             c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride);
 int  c8b_sync(c8b_ctx* ctx);                         /* wait for the ctx stream                    */
+
+/* ---- live stream: what the gr::block shells' general_work calls feed ------------------------------
+ * The reference's blocks keep their state between general_work calls (trigger FSM lib/trigger_impl.cc:59-117, sync
+ * hold-off lib/sync_impl.cc:73-147, signal's S_COPY position lib/signal_impl.cc:164-192, demod / decode packet
+ * state lib/demod_impl.cc:59-342, lib/decode_impl.cc:60-162).  A session keeps a device-resident window of the
+ * capture (nant = 1: rx.grc, nant = 2: rx2.grc; the ctx needs max_frames >= 2 = frame records per window pass).
+ * c8b_stream_push appends n samples (any n, any split) and returns the frames that became fully decidable:
+ * frames[k] (k < *nframes <= frames_cap) with trig_idx / sync_idx relative to absolute stream sample
+ * frame_base[k], PDU records at pdu + k*pdu_stride.  flush != 0 ends the stream: what is left is processed with
+ * the whole-capture (c8b_rx_batch) semantics, truncated frames included.  The frames and PDUs of a stream are the
+ * ones one c8b_rx_batch call over the whole capture (one item) returns, independent of the push sizes.
+ * A window that fills up without any decidable point is dropped and counted (c8b_stream_state). */
+int  c8b_stream_begin(c8b_ctx* ctx, int nant, int64_t window_samples /* 0: 4 Mi samples */);
+int  c8b_stream_push(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1 /* NULL for nant 1 */, int64_t n, int flush,
+                     c8b_frame* frames, int frames_cap, int* nframes, int64_t* frame_base, uint8_t* pdu, int64_t pdu_stride);
+int  c8b_stream_state(const c8b_ctx* ctx, int64_t* base, int64_t* fill, int64_t* overruns);
 
 /* per-kernel device time accumulated since the last reset (CUDA events on the ctx stream) */
 #define C8B_K_PRESISO 0

@@ -41,6 +41,18 @@ void hs_detect(const float* iq, const float* preac, int n, int item, int maxf, c
     }
     detect_item(lut(), (const cf*)iq, preac, n, item, maxf, f, (cf*)chan);
 }
+// window of a live stream: scan = {from, pos0, flush | safe, pos, nf, stalled} (c8b_scan, lut.h), bitmap scan like the GPU path
+void hs_detect_scan(const float* iq, const float* preac, int n, int maxf, c8b_frame* f, float* chan, int32_t* scan, int bitmap)
+{
+    memset(f, 0, sizeof(*f) * maxf);
+    uint32_t* mask = nullptr;
+    if (bitmap) {
+        mask = new uint32_t[n / 32 + 2]();
+        for (int i = 0; i < n; i++) if (preac[i] > 0.3f) mask[i >> 5] |= 1u << (i & 31);
+    }
+    detect_item(lut(), (const cf*)iq, preac, n, 0, maxf, f, (cf*)chan, mask, reinterpret_cast<c8b_scan*>(scan));
+    delete[] mask;
+}
 void hs_header(const float* iq_item, c8b_frame* f, const float* chan, int mupos, float* hinv)
 {
     if (f->status != C8B_ST_OK) return;

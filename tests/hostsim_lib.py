@@ -26,6 +26,7 @@ def lib():
         L.hs_sig_viterbi.argtypes = [f32p, u8p, C.c_int]
         L.hs_crc8.argtypes = [u8p, C.c_int, u8p]
         L.hs_detect.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, f32p]
+        L.hs_detect_scan.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_void_p, f32p, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_int]
         L.hs_header.argtypes = [f32p, C.c_void_p, f32p, C.c_int, f32p]
         L.hs_header2.argtypes = [f32p, f32p, C.c_void_p, f32p, f32p, f32p]
         _lib = L

@@ -1,0 +1,123 @@
+"""Live-stream session (c8b_stream_begin / c8b_stream_push): a capture pushed in arbitrary pieces -- what a gr::block
+shell's general_work calls deliver -- must yield exactly the frames and PDUs of one whole-capture pass (c8b_rx_batch over
+one item), and those are checked against the oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from __graft_entry__ import load_pkg
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("status", "l_mcs", "l_len", "nsamp", "format", "mcs", "len", "cr", "ampdu", "nss", "nsym", "trellis", "total", "npdu", "pdu_bytes")
+
+
+def _capture(golden, snr=None, lo=0, hi=25, seed=5):
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    x = np.ascontiguousarray(g["iq"][offs[lo]:offs[hi]])
+    if snr is not None:
+        rng = np.random.default_rng(seed)
+        s = 0.1875 / np.sqrt(2 * 10 ** (snr / 10))
+        x = (x + s * (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size))).astype(np.complex64)
+    return x
+
+
+def _rows(fr, base, pdu):
+    out = []
+    for k in range(fr.size):
+        f = fr[k]
+        out.append((int(base[k]) + int(f["trig_idx"]), int(base[k]) + int(f["sync_idx"])) + tuple(int(f[q]) for q in KEYS) + (bytes(pdu[k, :f["pdu_bytes"]]),))
+    return out
+
+
+def _stream(rx, x, pushes, x1=None, **kw):
+    rows, done = [], 0
+    for i, p in enumerate(pushes):
+        a = x[done:done + p]
+        b = None if x1 is None else x1[done:done + p]
+        fr, base, pdu = rx.stream_push(a, b, flush=(i == len(pushes) - 1), **kw)
+        rows += _rows(fr, base, pdu)
+        done += p
+    assert done == x.size
+    return rows
+
+
+def _pushes(rng, n, k):
+    cuts = np.sort(rng.integers(1, n, size=k))
+    return np.diff(np.concatenate([[0], cuts, [n]])).tolist()
+
+
+@pytest.mark.parametrize("frontend_mode", [0, 1])
+@pytest.mark.parametrize("snr", [None, 25.0])
+def test_stream_equals_one_pass_and_oracle(golden, snr, frontend_mode):
+    pkg = load_pkg()
+    x = _capture(golden, snr)
+    rx = pkg.Receiver(device=0, max_frames=32, chunk_items=1, frontend_mode=frontend_mode)
+    fr, pdu = rx.rx_batch(x, [0], [x.size])
+    keep = (fr["status"] != 9) & (fr["nsamp"] > 0)
+    want = _rows(fr[keep], np.zeros(int(keep.sum()), np.int64), pdu[keep])
+    assert len(want) == 25 and all(r[2] == 0 for r in want)
+    # the oracle on the whole capture: same frames, same PDU bytes
+    fo, _, po = ol.rx_item(x, max_frames=32)
+    assert [r[1] for r in want] == [int(f["sync_idx"]) for f in fo]
+    assert b"".join(r[-1] for r in want) == bytes(po)
+    rng = np.random.default_rng(77)
+    for k in (1, 4, 23, 300):
+        rx.stream_begin(1, 0)
+        got = _stream(rx, x, _pushes(rng, x.size, k))
+        assert got == want, k
+    rx.close()
+    # few frame records per pass and a window smaller than the capture: compaction and record exhaustion
+    rx = pkg.Receiver(device=0, max_frames=3, chunk_items=1, frontend_mode=frontend_mode)
+    for window in (8192, 20000):
+        rx.stream_begin(1, window)
+        got = _stream(rx, x, _pushes(rng, x.size, 6))
+        assert got == want, window
+        st = rx.stream_state()
+        assert st["overruns"] == 0 and st["base"] == x.size and st["fill"] == 0
+    rx.close()
+
+
+def test_stream_truncated_tail_and_errors(golden):
+    pkg = load_pkg()
+    x = _capture(golden, 30.0, lo=1, hi=8)
+    x = x[:x.size - 700]                                           # the last frame misses its end
+    rx = pkg.Receiver(device=0, max_frames=16, chunk_items=1)
+    fr, pdu = rx.rx_batch(x, [0], [x.size])
+    keep = (fr["status"] != 9) & (fr["nsamp"] > 0)
+    want = _rows(fr[keep], np.zeros(int(keep.sum()), np.int64), pdu[keep])
+    assert want[-1][2] == 4                                        # C8B_ST_TRUNC, reported at flush like the batch pass
+    rx.stream_begin(1, 0)
+    assert _stream(rx, x, [3000, 5000, x.size - 8000]) == want
+    # more frames than the caller's arrays hold
+    rx.stream_begin(1, 0)
+    with pytest.raises(RuntimeError):
+        rx.stream_push(x, flush=True, frames_cap=2)
+    rx.close()
+    # a session needs frame records to make progress; pushing without a session is an error
+    rx1 = pkg.Receiver(device=0, max_frames=1)
+    with pytest.raises(RuntimeError):
+        rx1.stream_begin(1, 0)
+    with pytest.raises(RuntimeError):
+        rx1.stream_push(x[:100])
+    rx1.close()
+
+
+def test_stream_two_antennas(golden):
+    """rx2.grc as a stream: signal2 + demod2 on both antennas, HT MCS8-15 and VHT 2SS frames back to back"""
+    pkg = load_pkg()
+    g = golden["frames_mimo"]
+    rng = np.random.default_rng(9)
+    s = 0.1875 / np.sqrt(2 * 10 ** 3.0)
+    a = (g["iq0"] + s * (rng.standard_normal(g["iq0"].size) + 1j * rng.standard_normal(g["iq0"].size))).astype(np.complex64)
+    b = (g["iq1"] + s * (rng.standard_normal(g["iq1"].size) + 1j * rng.standard_normal(g["iq1"].size))).astype(np.complex64)
+    rx = pkg.Receiver(device=0, max_frames=32, chunk_items=1)
+    fr, pdu = rx.rx_batch2(a, b, [0], [a.size])
+    keep = (fr["status"] != 9) & (fr["nsamp"] > 0)
+    want = _rows(fr[keep], np.zeros(int(keep.sum()), np.int64), pdu[keep])
+    assert len(want) == len(g["offs"]) - 1 and sum(r[-3] for r in want) >= len(want) - 1
+    for k in (2, 17):
+        rx.stream_begin(2, 0)
+        assert _stream(rx, a, _pushes(rng, a.size, k), x1=b) == want
+    rx.close()
