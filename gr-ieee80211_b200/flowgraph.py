@@ -133,7 +133,9 @@ class decode(_Block):
 def _tags_of(f, chan, seq):
     sy = {"rad": float(f["rad"]), "snr": float(f["snr"]), "rssi": float(f["rssi"])}
     sg = {"cfo": float(f["cfo_hz"]), "snr": float(f["snr"]), "rssi": float(f["rssi"]), "seq": seq, "mcs": int(f["l_mcs"]),
-          "len": int(f["l_len"]), "nsamp": int(f["nsamp"]), "chan": np.asarray(chan, np.complex64)}
+          "len": int(f["l_len"]), "nsamp": int(f["nsamp"])}
+    if chan is not None:                                        # signal -> demod tag; internal to the fused path when streaming
+        sg["chan"] = np.asarray(chan, np.complex64)
     dm = {"cfo": float(f["cfo_hz"]), "snr": float(f["snr"]), "rssi": float(f["rssi"]), "format": int(f["format"]), "mcs": int(f["mcs"]),
           "len": int(f["len"]), "cr": int(f["cr"]), "ampdu": int(f["ampdu"]), "trellis": int(f["trellis"]), "total": int(f["total"])}
     if f["format"] == 2:
@@ -156,6 +158,7 @@ class rx_top_block:
         self.max_frames = max_frames
         self.rx = Receiver(device=device, chunk_items=1, max_frames=max_frames, mupos=mupos, mugid=mugid, blob=blob)
         self.frames = None
+        self._streaming = False
 
     def close(self):
         self.rx.close()
@@ -173,15 +176,32 @@ class rx_top_block:
         keep = fr["status"] != 9                                # C8B_ST_EMPTY
         self.frames = fr[keep]
         for k in np.nonzero(keep)[0]:
-            f = fr[k]
-            if f["nsamp"] == 0:                                 # no frame accepted by L-SIG in the capture
-                continue
-            sy, sg, dm = _tags_of(f, chan[k], self.signal.seq)
-            self.signal.seq = (self.signal.seq + 1) % 1000000000
-            self.sync.tags.append(sy)
-            self.signal.tags.append(sg)
-            if f["status"] in (0, 6, 7):                        # reached WRTAG (decode may still reject: DECODE_RANGE / NDP)
-                self.demod.tags.append(dm)
-            if f["status"] == 0:
-                self.decode.handle(f, pdu[k, :f["pdu_bytes"]])
+            self._publish(fr[k], chan[k], pdu[k], 0)
         return self.frames
+
+    def _publish(self, f, chan, pdu, base):
+        if f["nsamp"] == 0:                                     # no frame accepted by L-SIG in the capture
+            return
+        sy, sg, dm = _tags_of(f, chan, self.signal.seq)
+        sy["offset"] = sg["offset"] = int(base) + int(f["sync_idx"])        # absolute item the tags sit on (nitems_written + idx)
+        self.signal.seq = (self.signal.seq + 1) % 1000000000
+        self.sync.tags.append(sy)
+        self.signal.tags.append(sg)
+        if f["status"] in (0, 6, 7):                            # reached WRTAG (decode may still reject: DECODE_RANGE / NDP)
+            self.demod.tags.append(dm)
+        if f["status"] == 0:
+            self.decode.handle(f, pdu[:f["pdu_bytes"]])
+
+    def work(self, x0, x1=None, flush=False, window=0):
+        """the scheduler's general_work calls: feed the next piece of the capture (any size); frames are published as soon
+        as they are decidable, identically to run() over the whole capture.  flush=True ends the stream."""
+        if not self._streaming:
+            self.rx.stream_begin(self.nant, window)
+            self._streaming = True
+        fr, base, pdu = self.rx.stream_push(np.asarray(x0, np.complex64), None if x1 is None else np.asarray(x1, np.complex64),
+                                            flush=flush, frames_cap=max(self.max_frames, 64))
+        for k in range(fr.size):
+            self._publish(fr[k], None, pdu[k], base[k])
+        if flush:
+            self._streaming = False
+        return fr, base

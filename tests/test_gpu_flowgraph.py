@@ -67,3 +67,26 @@ def test_rx2_grc_capture(golden, tmp_path):
     assert len(fr) == 18 and len(tb.decode.out) == 18 and tb.decode.d_nPktCorrect == 0     # counters only move with ifdebug
     assert [int(r[0]) for r in tb.decode.out] == [1] * 8 + [2] * 9 + [1]
     assert "sssnr1" in tb.demod.tags[10]
+
+
+def test_work_calls_equal_run(golden):
+    """the capture delivered in general_work-sized pieces publishes the same PDUs, tags and debug lines as run()"""
+    pkg = load_pkg()
+    fg = pkg.flowgraph
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    x = np.ascontiguousarray(g["iq"][offs[1]:offs[26]])
+    a, b = [], []
+    tb = fg.rx_top_block(nant=1, ifdebug=True, printer=a.append)
+    tb.run(x)
+    out_run, tags_run = list(tb.decode.out), [dict(t) for t in tb.demod.tags]
+    sync_run = [t["offset"] for t in tb.sync.tags]
+    tb.close()
+    tb = fg.rx_top_block(nant=1, ifdebug=True, printer=b.append, max_frames=8)
+    for k in range(0, x.size, 4096):                                  # 4096 items per call, like a GNU Radio buffer
+        tb.work(x[k:k + 4096], flush=k + 4096 >= x.size)
+    assert tb.decode.out == out_run and len(out_run) == 25
+    assert [dict(t) for t in tb.demod.tags] == tags_run
+    assert [t["offset"] for t in tb.sync.tags] == sync_run
+    assert a == b
+    tb.close()
