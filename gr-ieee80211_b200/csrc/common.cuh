@@ -28,7 +28,7 @@ void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_of
                        int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
                        float2* chan, c8b_scan* scans, cudaStream_t st);
 void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
-                       const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
+                       const float2* chan, float2* hinv, int64_t llrStride, float* llr, cudaStream_t st);
 void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int maxSym, const c8b_frame* frames,
                       const float2* hinv, float* llr, cudaStream_t st);
 void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf,
@@ -42,5 +42,6 @@ void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_
                          int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
                          float2* chan, c8b_scan* scans, cudaStream_t st);
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
-                         const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st);
+                         const float2* chan, float2* hinv, int64_t llrStride, float* llr, cudaStream_t st);
 int c8b_viterbi_tp_wave(int num_sm);
+void c8b_launch_ndp(c8b_frame* frames, int nframes, const float* llr, int64_t nllr, uint8_t* pdu, int64_t pduStride, cudaStream_t st);

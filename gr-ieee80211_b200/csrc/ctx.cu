@@ -291,6 +291,7 @@ static int launch_decode(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* 
         c8b_launch_viterbi(ctx->d_lut, d_frames, n, d_llr, nllr, (uint2*)ctx->surv.p, ctx->survWarps, d_pdu, pdu_stride, d_scram, scram_stride,
                            ctx->d_counter, grid, st);
     }
+    c8b_launch_ndp(d_frames, n, d_llr, nllr, d_pdu, pdu_stride, st);    // VHT NDP channel reports (lib/decode_impl.cc:100-121)
     return C8B_OK;
 }
 
@@ -411,7 +412,7 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
         else
             (ctx->cfg.frontend_mode == 1 ? c8b_launch_header : c8b_launch_header_w)(
                 ctx->d_lut, iq, d_off + b, n, maxf, ctx->cfg.mupos, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
-                (float2*)ctx->hinv.p, llrStride, ctx->st);
+                (float2*)ctx->hinv.p, llrStride, (float*)llrBuf.p, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
@@ -695,7 +696,7 @@ int c8b_demod(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t
         StageTimer tm(ctx, C8B_K_HEADER);
         (ctx->cfg.frontend_mode == 1 ? c8b_launch_header : c8b_launch_header_w)(
             ctx->d_lut, iq, (const int64_t*)ctx->off.p, nitems, maxf, ctx->cfg.mupos, (c8b_frame*)ctx->frames.p, (const float2*)ctx->chan.p,
-            (float2*)ctx->hinv.p, llr_stride, ctx->st);
+            (float2*)ctx->hinv.p, llr_stride, (float*)ctx->llr.p, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);

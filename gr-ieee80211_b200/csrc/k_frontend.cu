@@ -178,7 +178,7 @@ struct RotSrc {
 __global__ void __launch_bounds__(64)
 k_header(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int nslots, int maxf,
          int mupos, c8b_frame* __restrict__ frames, const float2* __restrict__ chan, float2* __restrict__ hinv,
-         int64_t llrStride)
+         int64_t llrStride, float* __restrict__ llr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // frame slot; its item is i / maxf
     if (i >= nslots) return;
@@ -193,6 +193,15 @@ k_header(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const i
         f.status = c8b::demod_header(lut, rot, f.nsamp, f.l_mcs, f.l_len, hl, mupos, &f, hv);
         for (int k = 0; k < 64; k++) hinv[(size_t)i * 64 + k] = make_float2(hv[k].re, hv[k].im);
         if (f.status == C8B_ST_OK && (int64_t)f.total > llrStride) f.status = C8B_ST_OVERFLOW;
+        if (f.status == C8B_ST_NDP && llr && llrStride >= 256) {
+            // tag "mu2x1chan" (lib/demod_impl.cc:238-249): the 2 x 64 time samples of the two VHT-LTFs that the sounding
+            // branch of nonLegacyChanEstimate keeps (:391-394); a one-stream NDP never fills them (zeros here)
+            float* o = llr + f.llr_off;
+            for (int k = 0; k < 128; k++) {
+                const cf c = f.nss != 1 ? rot(240 + C8B_SYM_SHIFT + (k & 63) + (k >> 6) * 80) : c8b::mk(0.f, 0.f);
+                o[2 * k] = c.re; o[2 * k + 1] = c.im;
+            }
+        }
     }
     frames[i] = f;
 }
@@ -254,8 +263,8 @@ void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_of
 }
 
 void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
-                       const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st)
+                       const float2* chan, float2* hinv, int64_t llrStride, float* llr, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_header<<<(nitems * maxf + 63) / 64, 64, 0, st>>>(lut, iq, d_off, nitems * maxf, maxf, mupos, frames, chan, hinv, llrStride);
+    k_header<<<(nitems * maxf + 63) / 64, 64, 0, st>>>(lut, iq, d_off, nitems * maxf, maxf, mupos, frames, chan, hinv, llrStride, llr);
 }

@@ -347,7 +347,8 @@ struct RotW {
 
 __global__ void __launch_bounds__(FW * 32)
 k_header_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int nslots, int maxf,
-           int mupos, c8b_frame* __restrict__ frames, const float2* __restrict__ chan, float2* __restrict__ hinvAll, int64_t llrStride)
+           int mupos, c8b_frame* __restrict__ frames, const float2* __restrict__ chan, float2* __restrict__ hinvAll, int64_t llrStride,
+           float* __restrict__ llrAll)
 {
     __shared__ Ws ws[FW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -502,6 +503,13 @@ k_header_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     else if (m.nSS != 1) status = C8B_ST_FORMAT;                  // 2-stream frames need the demod2 path
     else if (pos + m.nSym * m.nSymSamp > nsig) status = C8B_ST_TRUNC;
     else if ((int64_t)total > llrStride) status = C8B_ST_OVERFLOW;
+    if (status == C8B_ST_NDP && llrAll && llrStride >= 256) {
+        // tag "mu2x1chan" (lib/demod_impl.cc:238-249): the 2 x 64 time samples of the two VHT-LTFs that the sounding branch
+        // of nonLegacyChanEstimate keeps (:391-394); a one-stream NDP never fills them (zeros here)
+        float2* __restrict__ o = reinterpret_cast<float2*>(llrAll + (size_t)sl * llrStride);
+        for (int k = lane; k < 128; k += 32)
+            o[k] = m.nSS != 1 ? st(rot.at(240 + C8B_SYM_SHIFT + (k & 63) + (k >> 6) * 80)) : make_float2(0.f, 0.f);
+    }
     if (lane == 0) {
         fr->format = m.format; fr->mcs = m.mcs; fr->len = m.len; fr->cr = m.cr; fr->ampdu = m.ampdu;
         fr->nss = m.nSS; fr->nsym = m.nSym; fr->nsymsamp = m.nSymSamp; fr->ncbps = m.nCBPS; fr->ndbps = m.nDBPS;
@@ -523,9 +531,9 @@ void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_
 }
 
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
-                         const float2* chan, float2* hinv, int64_t llrStride, cudaStream_t st)
+                         const float2* chan, float2* hinv, int64_t llrStride, float* llr, cudaStream_t st)
 {
     if (nitems <= 0) return;
     const int ns = nitems * maxf;
-    k_header_w<<<(ns + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, ns, maxf, mupos, frames, chan, hinv, llrStride);
+    k_header_w<<<(ns + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, ns, maxf, mupos, frames, chan, hinv, llrStride, llr);
 }

@@ -531,3 +531,31 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
     k_viterbi<<<grid, NW * 32, smem, st>>>(d_lut, d_frames, nframes, d_llr, nllr, d_surv, d_pdu, pdu_stride, d_scram, scram_stride,
                                           d_counter);
 }
+
+// VHT NDP (lib/decode_impl.cc:100-121: v_trellis == 0): the decode block turns the tag "mu2x1chan" -- here the 128 complex
+// samples the header kernel left at the frame's place in the LLR arena -- into the channel report
+// [C8P_F_VHT_CHAN = 20][len lo][len hi][128 x (re, im) float32], len = 1024.  Runs after the Viterbi kernel (which clears
+// npdu / pdu_bytes of every slot); one thread per frame slot, NDP frames are rare.
+namespace {
+__global__ void k_ndp(c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llr, int64_t nllr, uint8_t* __restrict__ pdu,
+                      int64_t pduStride)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    c8b_frame* fr = frames + f;
+    if (fr->status != C8B_ST_NDP || pduStride < 1027) return;
+    const int64_t lo = fr->llr_off;
+    if (lo < 0 || lo + 256 > nllr) return;
+    uint8_t* __restrict__ p = pdu + (size_t)f * pduStride;
+    const uint8_t* __restrict__ s = reinterpret_cast<const uint8_t*>(llr + lo);
+    p[0] = 20; p[1] = 1024 % 256; p[2] = 1024 / 256;
+    for (int k = 0; k < 1024; k++) p[3 + k] = s[k];
+    fr->npdu = 1; fr->pdu_bytes = 1027; fr->pdu_off = (int64_t)f * pduStride;
+}
+}  // namespace
+
+void c8b_launch_ndp(c8b_frame* frames, int nframes, const float* llr, int64_t nllr, uint8_t* pdu, int64_t pduStride, cudaStream_t st)
+{
+    if (nframes <= 0) return;
+    k_ndp<<<(nframes + 255) / 256, 256, 0, st>>>(frames, nframes, llr, nllr, pdu, pduStride);
+}

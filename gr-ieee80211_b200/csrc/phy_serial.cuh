@@ -493,13 +493,17 @@ C8B_HD void parse_vhta(const uint8_t* b, Mod* m)                  // signalParse
 
 C8B_HD void parse_vhtb(const uint8_t* b, Mod* m)                  // signalParserVhtB c8p.cc:1180-1223
 {
+    // An MCS field outside 0..9 leaves nDBPS unset (c8p.cc:1225-1294 default case; the reference then divides by a stale
+    // member or by zero): such a frame is dropped at the sanity check (len = nSym = -1), as the oracle does.
     if (m->sumu) {
         const int len = bits_le(b, 16), mcs = bits_le(b + 16, 4);
         mod_vht(mcs, m);
+        m->nLTF = 2;
+        if (m->nDBPS <= 0) { m->len = -1; m->nSym = -1; return; }
         m->len = len * 4;
         m->nSym = nsym_of(m->len, 22, m->nDBPS);
-        m->nLTF = 2;
     } else if ((b[17] + b[18] + b[19]) == 3) {
+        if (m->nDBPS <= 0) { m->len = -1; m->nSym = -1; return; }
         m->len = bits_le(b, 17) * 4;
         m->nSym = nsym_of(m->len, 22, m->nDBPS);
     } else {

@@ -36,6 +36,7 @@ class _Block:
     def __init__(self, name):
         self.name = name
         self.tags = []          # one dict per frame, keys as in the reference
+        self.offsets = []       # absolute stream item each tag set sits on (add_item_tag's offset)
 
 
 class trigger(_Block):
@@ -123,11 +124,15 @@ class decode(_Block):
                 else:
                     self.d_htMcsCount[mcs % 8] += 1
                 self._line(fmt, True, f)
-            self.out.append(r)
-            if self.on_pdu:
-                self.on_pdu(r)
-            if self.sock is not None:
-                self.sock.sendto(r, self.udp)
+            self.publish(r)
+
+    def publish(self, r):
+        """message port `out`"""
+        self.out.append(r)
+        if self.on_pdu:
+            self.on_pdu(r)
+        if self.sock is not None:
+            self.sock.sendto(r, self.udp)
 
 
 def _tags_of(f, chan, seq):
@@ -183,14 +188,21 @@ class rx_top_block:
         if f["nsamp"] == 0:                                     # no frame accepted by L-SIG in the capture
             return
         sy, sg, dm = _tags_of(f, chan, self.signal.seq)
-        sy["offset"] = sg["offset"] = int(base) + int(f["sync_idx"])        # absolute item the tags sit on (nitems_written + idx)
+        self.sync.offsets.append(int(base) + int(f["sync_idx"]))           # nitems_written(0) + idx  (lib/sync_impl.cc:124-136)
+        self.signal.offsets.append(int(base) + int(f["sync_idx"]))
         self.signal.seq = (self.signal.seq + 1) % 1000000000
         self.sync.tags.append(sy)
         self.signal.tags.append(sg)
-        if f["status"] in (0, 6, 7):                            # reached WRTAG (decode may still reject: DECODE_RANGE / NDP)
+        if f["status"] == 7:                                    # VHT NDP: tag mu2x1chan, total 1024 (lib/demod_impl.cc:238-249)
+            dm["total"] = 1024
+            if f["pdu_bytes"] == 1027:
+                dm["mu2x1chan"] = np.frombuffer(bytes(pdu[3:1027]), np.float32).view(np.complex64).copy()
+        if f["status"] in (0, 6, 7):                            # reached WRTAG (decode may still reject: DECODE_RANGE)
             self.demod.tags.append(dm)
         if f["status"] == 0:
             self.decode.handle(f, pdu[:f["pdu_bytes"]])
+        elif f["status"] == 7 and f["pdu_bytes"] == 1027:       # channel report blob, no counters / debug line (decode_impl.cc:100-121)
+            self.decode.publish(bytes(pdu[:1027]))
 
     def work(self, x0, x1=None, flush=False, window=0):
         """the scheduler's general_work calls: feed the next piece of the capture (any size); frames are published as soon

@@ -479,13 +479,19 @@ void parseVhtA(const uint8_t* b, Mod* m)
 
 void parseVhtB(const uint8_t* b, Mod* m)
 {
+    // An MCS field outside 0..9 leaves nDBPS at whatever the block's member held (c8p.cc:1225-1294 default case): the
+    // reference then divides by a stale value, or by zero on a fresh block.  Documented delta: such a frame is dropped
+    // at the sanity check (len = nSym = -1).
     if (m->sumu) {
         int len = bitsToInt(b, 16), mcs = bitsToInt(b + 16, 4);
         modVht(mcs, m);
+        m->nLTF = 2;
+        if (m->nDBPS <= 0) { m->len = -1; m->nSym = -1; return; }
         m->len = len * 4;
         m->nSym = (m->len * 8 + 16 + 6) / m->nDBPS + (((m->len * 8 + 16 + 6) % m->nDBPS) != 0);
         m->nLTF = 2;
     } else if ((b[17] + b[18] + b[19]) == 3) {
+        if (m->nDBPS <= 0) { m->len = -1; m->nSym = -1; return; }
         m->len = bitsToInt(b, 17) * 4;
         m->nSym = (m->len * 8 + 16 + 6) / m->nDBPS + (((m->len * 8 + 16 + 6) % m->nDBPS) != 0);
     } else {
@@ -725,7 +731,16 @@ int demodFrame(const cf* sig, int nsig, int lmcs, int llen, const cf* hl, orx_fr
     f->nss = d.m.nSS; f->nsym = d.m.nSym; f->nsymsamp = d.m.nSymSamp; f->ncbps = d.m.nCBPS; f->ndbps = d.m.nDBPS;
     f->trellis = trellis; f->total = d.m.nSym * d.m.nCBPS; f->data_off = pos;
     f->sssnr0 = (d.m.format == F_VHT) ? d.sssnr : 0.f; f->sssnr1 = 0.f;
-    if (d.m.nSym == 0) { f->total = 1024; return ORX_E_NDP; }
+    if (d.m.nSym == 0) {                                      // :238-249, :264-270: tag mu2x1chan, 1024 items of no content
+        f->total = 1024;
+        // the tag carries d_mu2x1Chan, which only the sounding branch of nonLegacyChanEstimate fills (:391-394); for a
+        // one-stream NDP the reference would publish whatever the member held before -- modelled as zeros
+        if (llrOut && llrCap >= 256) {
+            if (d.m.nSS == 1 && d.m.nLTF == 1) memset(llrOut, 0, 256 * sizeof(float));
+            else memcpy(llrOut, d.mu2x1, 256 * sizeof(float));
+        }
+        return ORX_E_NDP;
+    }
     if (f->total > llrCap) return ORX_E_TRUNC;
     // DEMOD_S_DEMOD :279-314 ; "(o1 + nSymSamp) < d_nProc" needs one spare input sample
     float inted[416];
@@ -1180,6 +1195,15 @@ int rxItem(const cf* x, int n, int item, int maxFrames, orx_frame* frames, float
             f->status = demodFrame2(rot.data(), rot2.data(), nsamp + 320, mcs, len, h, f, lo, capI);
         } else
             f->status = demodFrame(rot.data(), nsamp + 320, mcs, len, h, f, lo, capI);
+        if (f->status == ORX_E_NDP && !x2 && pduCap - *pduUsed >= 1027 && capI >= 256) {
+            // decode_impl.cc:100-121: v_trellis == 0 -> channel report [C8P_F_VHT_CHAN = 20][len lo][len hi][128 x (re, im) float]
+            uint8_t* p = pdu + *pduUsed;
+            p[0] = 20; p[1] = 1024 % 256; p[2] = 1024 / 256;
+            memcpy(p + 3, lo, 1024);
+            f->npdu = 1; f->pdu_bytes = 1027;
+            *pduUsed += 1027;
+            continue;
+        }
         if (f->status != ORX_OK) continue;
         if (llr) *llrUsed += f->total;
         int used = 0;

@@ -19,6 +19,6 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     g = {}
-    for n in ("frames_siso", "frames_bench", "ref_vectors", "frames_mimo"):
+    for n in ("frames_siso", "frames_bench", "ref_vectors", "frames_mimo", "frames_mu"):
         g[n] = np.load(os.path.join(HERE, "golden", n + ".npz"))
     return g

@@ -12,6 +12,9 @@ container (needs /root/reference); the GPU box and the test-suite only read the 
                       (through oracle/_ref/libc8p_ref.so) so GPU tests can compare with the
                       reference's own outputs where /root/reference does not exist.
 
+  frames_mu.npz       VHT NDP (2 transmit streams, one receive antenna) and 2-user MU-MIMO frames seen at each user
+                      position (tools/cmu_ap.py recipe with a flat 2x2 channel and its zero-forcing precoder).
+
 usage: python tests/golden/make_golden.py
 """
 import contextlib
@@ -186,6 +189,40 @@ def frames_sgi():
     print("frames_sgi:", [len(x) for x in items])
 
 
+def frames_mu():
+    """VHT sounding and MU-MIMO as one station antenna sees them (tools/cmu_ap.py:64-200 is the reference's recipe):
+      * NDP: genFromAmpdu with an empty A-MPDU, nSTS = 2 -> two transmit streams; the station receives h0*tx0 + h1*tx1.
+        demod reports the two VHT-LTFs ("mu2x1chan", lib/demod_impl.cc:238-249), decode publishes the channel report.
+      * MU-MIMO: genAmpduMu for two users, group id 2, zero-forcing precoder Q = H^H (H H^H)^-1 for a flat 2x2 channel H
+        (rows = users); user u receives sum_t H[u, t] * tx_t and decodes with demod(mupos = u, mugid = 2)."""
+    phy = phy80211.phy80211(ifDebug=False)
+    H = np.array([[1.0, 0.5 * np.exp(0.9j)], [0.6 * np.exp(-0.4j), 0.9 * np.exp(2.0j)]])
+    items, meta, exp = [], [], []
+    for cfo in (0.0, 40e3):
+        mod = p8h.modulation(phyFormat=p8h.F.VHT, mcs=0, bw=p8h.BW.BW20, nSTS=2, shortGi=False)
+        quiet(phy.genFromAmpdu, b"", mod, vhtPartialAid=0, vhtGroupId=0)
+        ss = quiet(phy.genFinalSig, multiplier=12.0 * np.sqrt(2), cfoHz=cfo, num=1, gap=True, gapLen=400)
+        ss = [np.asarray(x, np.complex128) for x in ss]
+        items.append((H[0, 0] * ss[0] + H[0, 1] * ss[1]).astype(np.complex64)); meta.append((3, 0, cfo)); exp.append(b"")
+    Q = H.conj().T @ np.linalg.inv(H @ H.conj().T)
+    Q = Q / np.linalg.norm(Q) * np.sqrt(2)
+    bfQ = [Q.copy() for _ in range(64)]
+    pk = [mac_ampdu(["1234567 packet for station 000"]), mac_ampdu(["7654321 packet for station 111"])]
+    for mcs0, mcs1 in ((0, 0), (4, 2)):
+        quiet(phy.genAmpduMu, nUser=2, bfQ=bfQ, groupId=2, ampdu0=pk[0], mod0=p8h.modulation(p8h.F.VHT, mcs0, p8h.BW.BW20, 1, False),
+              ampdu1=pk[1], mod1=p8h.modulation(p8h.F.VHT, mcs1, p8h.BW.BW20, 1, False))
+        ss = quiet(phy.genFinalSig, multiplier=18.0, cfoHz=0.0, num=1, gap=True, gapLen=400)
+        ss = [np.asarray(x, np.complex128) for x in ss]
+        for u in range(2):
+            items.append((H[u, 0] * ss[0] + H[u, 1] * ss[1]).astype(np.complex64)); meta.append((4, (mcs0, mcs1)[u], float(u)))
+            exp.append(ampdu_split(pk[u])[0])
+    offs = np.cumsum([0] + [len(x) for x in items]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "frames_mu.npz"), iq=np.concatenate(items).astype(np.complex64), offs=offs,
+                        meta=np.array(meta, np.float64), exp_len=np.array([len(e) for e in exp], np.int32),
+                        exp_mpdu=np.frombuffer(b"".join(exp), np.uint8), chan=H.astype(np.complex64))
+    print("frames_mu: %d items, %d samples; meta = (3 NDP | 4 MU, mcs, cfo | user position)" % (len(items), offs[-1]))
+
+
 def ref_vectors():
     import oracle_lib as ol
     R = ol.ref()
@@ -246,7 +283,9 @@ def ref_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi"]
+    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi", "mu"]
+    if "mu" in which:
+        frames_mu()
     if "siso" in which:
         frames_siso()
     if "bench" in which:

@@ -80,6 +80,8 @@ def oracle():
         L.orx_decode.argtypes = [f32p, C.POINTER(OrxFrame), u8p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         L.orx_crc32.argtypes = [u8p, C.c_int]
         L.orx_crc32.restype = C.c_uint32
+        L.orx_set_mupos.argtypes = [C.c_int]
+        L.orx_set_mupos.restype = None
         L.orx_rx_item.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                   u8p, C.c_int64, C.POINTER(C.c_int64)]
         L.orx_rx_item2.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),

@@ -139,3 +139,60 @@ def test_mimo_tables_vs_reference(golden):
     assert np.array_equal(f[:64], l * 0.5)
     for name, want in ((b"PILOT_HT_2_1", [1, 1, -1, -1]), (b"PILOT_HT_2_2", [1, -1, -1, 1]), (b"PILOT_VHT", [1, 1, 1, -1]), (b"PILOT_HT_1", [1, 1, 1, -1])):
         assert R.ref_table_f(name, f) == 4 and list(f[:4]) == want
+
+
+def _mu_items(g):
+    offs = g["offs"]
+    el = g["exp_len"]
+    eo = np.cumsum(np.r_[0, el])
+    for i in range(len(offs) - 1):
+        kind, mcs, par = g["meta"][i]
+        yield i, int(kind), int(mcs), par, np.ascontiguousarray(g["iq"][offs[i]:offs[i + 1]]), bytes(g["exp_mpdu"][eo[i]:eo[i + 1]])
+
+
+def test_mu_mimo_user_positions(golden):
+    """2-user VHT MU-MIMO frames of the reference generator (tools/phy80211.py genAmpduMu, zero-forcing precoder of a flat
+    2x2 channel): each station decodes its own A-MPDU with demod(mupos, mugid = 2) (lib/demod_impl.cc:347-380)"""
+    O = ol.oracle()
+    try:
+        n = 0
+        for i, kind, mcs, par, x, mpdu in _mu_items(golden["frames_mu"]):
+            if kind != 4:
+                continue
+            O.orx_set_mupos(int(par))
+            fo, _, po = ol.rx_item(x, max_frames=2)
+            assert len(fo) == 1 and fo[0]["status"] == 0 and (fo[0]["format"], fo[0]["mcs"], fo[0]["nss"]) == (2, mcs, 1)
+            recs = ol.split_pdus(po)
+            assert len(recs) == 1 and recs[0][3:-1] == mpdu and recs[0][0] == 2 and recs[0][-1] == mcs
+            # the wrong user position estimates the other user's channel: the frame must not pass
+            O.orx_set_mupos(1 - int(par))
+            fw, _, pw = ol.rx_item(x, max_frames=2)
+            assert pw.size == 0 or ol.split_pdus(pw)[0][3:-1] != mpdu
+            n += 1
+        assert n == 4
+    finally:
+        O.orx_set_mupos(0)
+
+
+def test_ndp_channel_report(golden):
+    """VHT NDP (empty A-MPDU, 2 transmit streams, one receive antenna): demod tags the two VHT-LTFs (mu2x1chan,
+    lib/demod_impl.cc:238-249), decode publishes [20][len lo][len hi][128 x (re, im) float32] (lib/decode_impl.cc:100-121).
+    With P = [[1, -1], [1, 1]] the LTF spectra separate the two transmit streams: |F1 - F2| / |F1 + F2| = |h0| / |h1|."""
+    g = golden["frames_mu"]
+    H = g["chan"]
+    n = 0
+    for i, kind, mcs, par, x, _ in _mu_items(g):
+        if kind != 3:
+            continue
+        fo, _, po = ol.rx_item(x, max_frames=2)
+        f = fo[0]
+        assert len(fo) == 1 and f["status"] == 7 and (f["format"], f["nss"], f["nsym"], f["len"], f["total"]) == (2, 2, 0, 0, 1024)
+        assert (f["npdu"], f["pdu_bytes"]) == (1, 1027) and bytes(po[:3]) == bytes([20, 0, 4])
+        assert abs(f["cfo_hz"] + par) < 300.0                          # the receiver's correction = minus the applied CFO
+        c = np.frombuffer(bytes(po[3:]), np.float32).view(np.complex64)
+        F1, F2 = np.fft.fft(c[:64]), np.fft.fft(c[64:])
+        used = [k for k in range(64) if not (k == 0 or 29 <= k <= 35 or k in (7, 21, 43, 57))]      # pilots carry no P matrix
+        r = np.abs(F1 - F2)[used] / np.abs(F1 + F2)[used]
+        assert np.allclose(r, abs(H[0, 0]) / abs(H[0, 1]), rtol=2e-3), (r.min(), r.max())
+        n += 1
+    assert n == 2
