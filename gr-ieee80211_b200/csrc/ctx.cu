@@ -291,7 +291,6 @@ static int launch_decode(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* 
         c8b_launch_viterbi(ctx->d_lut, d_frames, n, d_llr, nllr, (uint2*)ctx->surv.p, ctx->survWarps, d_pdu, pdu_stride, d_scram, scram_stride,
                            ctx->d_counter, grid, st);
     }
-    c8b_launch_ndp(d_frames, n, d_llr, nllr, d_pdu, pdu_stride, st);    // VHT NDP channel reports (lib/decode_impl.cc:100-121)
     return C8B_OK;
 }
 
@@ -299,9 +298,12 @@ static int launch_decode(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* 
 static int decode_dev(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* d_llr, int64_t nllr, uint8_t* d_pdu,
                       int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride)
 {
-    StageTimer tm(ctx, C8B_K_VITERBI);
-    int r = launch_decode(ctx, d_frames, n, d_llr, nllr, d_pdu, pdu_stride, d_scram, scram_stride, c8b_viterbi_max_grid(ctx->numSM), ctx->st);
-    if (r) return r;
+    {
+        StageTimer tm(ctx, C8B_K_VITERBI);
+        int r = launch_decode(ctx, d_frames, n, d_llr, nllr, d_pdu, pdu_stride, d_scram, scram_stride, c8b_viterbi_max_grid(ctx->numSM), ctx->st);
+        if (r) return r;
+    }
+    c8b_launch_ndp(d_frames, n, d_llr, nllr, d_pdu, pdu_stride, ctx->st);    // VHT NDP channel reports (lib/decode_impl.cc:100-121)
     CK(cudaGetLastError());
     return C8B_OK;
 }
@@ -437,6 +439,8 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
                           d_pdu + (size_t)b * maxf * pdu_stride, pdu_stride, nullptr, 0, grid, sv);
         if (r) return r;
     }
+    c8b_launch_ndp(d_frames + (size_t)b * maxf, (int)ns, (const float*)llrBuf.p, (int64_t)ns * llrStride, d_pdu + (size_t)b * maxf * pdu_stride,
+                   pdu_stride, sv);                                  // VHT NDP channel reports (lib/decode_impl.cc:100-121)
     if (ov) cudaEventRecord(ctx->evVit[par], sv);
     CK(cudaGetLastError());
     return C8B_OK;
