@@ -218,6 +218,7 @@ __device__ int signal_at_w(const c8b_lut* __restrict__ L, const cf* __restrict__
     return 1;
 }
 
+template <bool SCAN>                             // SCAN: the item is a window of a live stream (c8b_scan in / out)
 __global__ void __launch_bounds__(FW * 32)
 k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
            const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preacAll,
@@ -242,10 +243,10 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     // the blocks' state machines, evaluated uniformly by the warp (see detect_item in phy_serial.cuh)
     TrigState ts;
     trig_reset(ts);
-    c8b_scan* sc = scans ? scans + it : nullptr;                  // window of a live stream (see phy_serial.cuh)
-    const bool live = sc && !sc->flush;
-    const int from = sc ? sc->from : 0;
-    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = sc ? sc->pos0 : 0, nf = 0;
+    c8b_scan* sc = SCAN ? scans + it : nullptr;                   // window of a live stream (see lut.h)
+    const bool live = SCAN && !sc->flush;
+    const int from = SCAN ? sc->from : 0;
+    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = SCAN ? sc->pos0 : 0, nf = 0;
     int safe = from, posS = pos, nfS = 0, stalled = 0;
     bool syncStalled = false, sigStalled = false, done = false;
     // The scan goes bitmap word by bitmap word (32 samples).  A complete word without a sample above the threshold is
@@ -270,7 +271,7 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
                 if (ts.fPlateau == 0) {
                     w += rem ? __ffs(rem) - 1 : 32 - (w - blkBase);
                     ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
-                    if (w * 32 >= skipUntil) { safe = w * 32; posS = pos; nfS = nf; }
+                    if (SCAN && w * 32 >= skipUntil) { safe = w * 32; posS = pos; nfS = nf; }
                     continue;
                 }
                 if (ts.countDown > 32) {                          // 32 sub-threshold samples of the count-down
@@ -286,7 +287,7 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
         const int kmax = min(32, n - i0);
         for (int k = kfirst; k < kmax && !done; k++) {
             const int i = i0 + k;
-            if (ts.nPlateau == 0 && ts.fPlateau == 0 && i >= skipUntil) { safe = i; posS = pos; nfS = nf; }
+            if (SCAN && ts.nPlateau == 0 && ts.fPlateau == 0 && i >= skipUntil) { safe = i; posS = pos; nfS = nf; }
             const uint8_t fl = trig_step(ts, __shfl_sync(FULL, pv, k));
             if (fl == 0 || i < skipUntil || syncStalled) continue;
             if (fl & 0x01) {
@@ -328,8 +329,10 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
         }
         w++;
     }
-    if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && n >= skipUntil) { safe = n; posS = pos; nfS = nf; }
-    if (sc && lane == 0) { sc->safe = safe; sc->pos = posS; sc->nf = nfS; sc->stalled = stalled; }
+    if (SCAN) {
+        if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && n >= skipUntil) { safe = n; posS = pos; nfS = nf; }
+        if (lane == 0) { sc->safe = safe; sc->pos = posS; sc->nf = nfS; sc->stalled = stalled; }
+    }
     if (nf == 0 && lane == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
 }
 
@@ -526,8 +529,12 @@ void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_
                          float2* chan, c8b_scan* scans, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_detect_w<<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask, maskStride,
-                                                            frames, chan, scans);
+    if (scans)
+        k_detect_w<true><<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask,
+                                                                      maskStride, frames, chan, scans);
+    else
+        k_detect_w<false><<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask,
+                                                                       maskStride, frames, chan, nullptr);
 }
 
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,

@@ -15,10 +15,16 @@ rnd, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 
+def kname(s):
+    """'void k_presiso<0, 1>(const float2 *, ...)' -> 'k_presiso<0, 1>'"""
+    s = s.split("(")[0].replace("<unnamed>::", "").strip()
+    return s[5:] if s.startswith("void ") else s
+
+
 rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
 agg = collections.OrderedDict()
 for r in rows:
-    name = r[4].split("(")[0].replace("<unnamed>::", "")
+    name = kname(r[4])
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += float(r[-1].replace(",", ""))
@@ -60,7 +66,7 @@ want = {
 }
 kernels = []
 for d in data:
-    k = {"kernel": d[hdr.index("Kernel Name")].split("(")[0].replace("<unnamed>::", "")}
+    k = {"kernel": kname(d[hdr.index("Kernel Name")])}
     for m, short in want.items():
         if m in hdr:
             k[short] = "%s %s" % (d[hdr.index(m)], units[hdr.index(m)])
