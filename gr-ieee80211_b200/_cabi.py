@@ -33,6 +33,16 @@ FRAME_DTYPE = np.dtype([(n, {C.c_int32: "<i4", C.c_float: "<f4", C.c_int64: "<i8
 assert FRAME_DTYPE.itemsize == C.sizeof(C8bFrame)
 
 
+class C8bTxFrame(C.Structure):
+    _fields_ = [("format", C.c_int32), ("mcs", C.c_int32), ("psdu_off", C.c_int64), ("psdu_len", C.c_int32), ("cfo_hz", C.c_float),
+                ("out_off", C.c_int64)]
+
+
+TXFRAME_DTYPE = np.dtype([("format", "<i4"), ("mcs", "<i4"), ("psdu_off", "<i8"), ("psdu_len", "<i4"), ("cfo_hz", "<f4"), ("out_off", "<i8")],
+                         align=True)
+assert TXFRAME_DTYPE.itemsize == C.sizeof(C8bTxFrame)
+
+
 class C8bCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("chunk_items", C.c_int32), ("max_item_len", C.c_int32), ("max_frames", C.c_int32),
                 ("mupos", C.c_int32), ("mugid", C.c_int32), ("no_overlap", C.c_int32), ("decode_mode", C.c_int32), ("frontend_mode", C.c_int32), ("reserved", C.c_int32 * 5)]
@@ -59,6 +69,9 @@ SYMBOLS = [
     ("c8b_stream_begin", _i, [_vp, _i, _i64]),
     ("c8b_stream_push", _i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _i64]),
     ("c8b_stream_state", _i, [_vp, _vp, _vp, _vp]),
+    ("c8b_tx_nsamp", _i, [_i, _i, _i]),
+    ("c8b_tx_batch", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _i64]),
+    ("c8b_tx_batch_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _i64]),
     ("c8b_timing_enable", _i, [_vp, _i]),
     ("c8b_timing_read", _i, [_vp, _vp, _vp, _i]),
     ("c8b_presiso", _i, [_vp, _vp, _i64, _vp, _vp]),

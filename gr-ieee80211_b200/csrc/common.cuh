@@ -45,3 +45,9 @@ void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_
                          const float2* chan, float2* hinv, int64_t llrStride, float* llr, cudaStream_t st);
 int c8b_viterbi_tp_wave(int num_sm);
 void c8b_launch_ndp(c8b_frame* frames, int nframes, const float* llr, int64_t nllr, uint8_t* pdu, int64_t pduStride, cudaStream_t st);
+int c8b_tx_geometry_host(int format, int mcs, int len, int* nsym, int* nslots);
+size_t c8b_tx_plan_bytes(int nframes);
+uint32_t c8b_tx_eof_word(void);
+void c8b_tx_scrambler(int seed, uint32_t out[4]);
+void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
+                   float2* d_out, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);

@@ -39,6 +39,7 @@ struct c8b_ctx {
         int64_t overruns = 0;   // windows dropped because nothing in them could be decided
     } strm;
     DevBuf sw[2][2], scan;      // [antenna][ping-pong]
+    DevBuf txf, txplan, txpsdu, txiq;   // transmit synthesiser: descriptors, plans, staged PSDU bytes / samples
     c8b_scan* scanDev = nullptr;   // non-null while run_chunk serves a stream window
     // timing
     bool timing = false;
@@ -167,7 +168,7 @@ void c8b_destroy(c8b_ctx* ctx)
     if (ctx->stVit) cudaStreamDestroy(ctx->stVit);
     DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->tp, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
                        &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev, &ctx->scan, &ctx->sw[0][0], &ctx->sw[0][1],
-                       &ctx->sw[1][0], &ctx->sw[1][1] };
+                       &ctx->sw[1][0], &ctx->sw[1][1], &ctx->txf, &ctx->txplan, &ctx->txpsdu, &ctx->txiq };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -906,6 +907,74 @@ int c8b_stream_state(const c8b_ctx* ctx, int64_t* base, int64_t* fill, int64_t* 
     if (base) *base = ctx->strm.base;
     if (fill) *fill = ctx->strm.fill;
     if (overruns) *overruns = ctx->strm.overruns;
+    return C8B_OK;
+}
+
+// ---- transmit synthesiser ---------------------------------------------------------------------------
+int c8b_tx_nsamp(int format, int mcs, int psdu_len)
+{
+    int nsym = 0, nslots = 0;
+    if (!c8b_tx_geometry_host(format, mcs, psdu_len, &nsym, &nslots)) return C8B_ERR_ARG;
+    return nslots * 80;
+}
+
+static int tx_run(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                  int seed, float* d_iq, int64_t iq_samples)
+{
+    if (seed < 1 || seed > 127) { ctx->err = "c8b_tx_batch: scrambler seed 1..127"; return C8B_ERR_ARG; }
+    int maxSlots = 0;
+    for (int i = 0; i < nframes; i++) {
+        int nsym = 0, nslots = 0;
+        const c8b_txframe& f = frames[i];
+        if (!c8b_tx_geometry_host(f.format, f.mcs, f.psdu_len, &nsym, &nslots)) { ctx->err = "c8b_tx_batch: unsupported format / mcs / length"; return C8B_ERR_ARG; }
+        if (f.psdu_off < 0 || f.psdu_off + f.psdu_len > psdu_bytes || f.out_off < 0 || f.out_off + (int64_t)nslots * 80 > iq_samples) {
+            ctx->err = "c8b_tx_batch: frame outside the PSDU / IQ arena";
+            return C8B_ERR_ARG;
+        }
+        if (nslots > maxSlots) maxSlots = nslots;
+    }
+    EN(txf, (size_t)nframes * sizeof(c8b_txframe));
+    EN(txplan, c8b_tx_plan_bytes(nframes));
+    CK(cudaMemcpyAsync(ctx->txf.p, frames, (size_t)nframes * sizeof(c8b_txframe), cudaMemcpyHostToDevice, ctx->st));
+    uint32_t scr[4];
+    c8b_tx_scrambler(seed, scr);
+    c8b_launch_tx(ctx->d_lut, (const c8b_txframe*)ctx->txf.p, nframes, maxSlots, ctx->txplan.p, d_psdu, (float2*)d_iq, multiplier, scr,
+                  c8b_tx_eof_word(), ctx->st);
+    CK(cudaGetLastError());
+    return C8B_OK;
+}
+
+int c8b_tx_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                     int scrambler_seed, float* d_iq, int64_t iq_samples)
+{
+    if (!ctx || !d_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !d_iq || iq_samples < 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nframes == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    r = tx_run(ctx, d_psdu, psdu_bytes, frames, nframes, multiplier, scrambler_seed, d_iq, iq_samples);
+    if (r) return r;
+    CK(cudaStreamSynchronize(ctx->st));                            // the descriptor array is the caller's again
+    return C8B_OK;
+}
+
+int c8b_tx_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                 int scrambler_seed, float* h_iq, int64_t iq_samples)
+{
+    if (!ctx || !h_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !h_iq || iq_samples < 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    EN(txpsdu, (size_t)psdu_bytes + 16);
+    EN(txiq, (size_t)(iq_samples + 16) * sizeof(float2));
+    CK(cudaMemcpyAsync(ctx->txpsdu.p, h_psdu, (size_t)psdu_bytes, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->txiq.p, 0, (size_t)iq_samples * sizeof(float2), ctx->st));
+    if (nframes > 0) {
+        r = tx_run(ctx, (const uint8_t*)ctx->txpsdu.p, psdu_bytes, frames, nframes, multiplier, scrambler_seed, (float*)ctx->txiq.p, iq_samples);
+        if (r) return r;
+    }
+    CK(cudaMemcpyAsync(h_iq, ctx->txiq.p, (size_t)iq_samples * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
 }
 

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from ._cabi import C8bCfg, C8bError, FRAME_DTYPE, ptr
+from ._cabi import C8bCfg, C8bError, FRAME_DTYPE, TXFRAME_DTYPE, ptr
 
 
 def lut_blob():
@@ -144,6 +144,40 @@ class Receiver:
         b, f, o = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         self._ck(self.L.c8b_stream_state(self.h, C.byref(b), C.byref(f), C.byref(o)), "c8b_stream_state")
         return {"base": b.value, "fill": f.value, "overruns": o.value}
+
+    # ---- transmit synthesiser -------------------------------------------------------------------
+    def tx_layout(self, psdus, fmt, mcs, gap=400, cfo=None):
+        """descriptors for one item per PSDU laid out [gap zeros][frame][gap zeros] (genFinalSig gap=True): returns
+        (descriptor array, PSDU arena, item offsets)"""
+        n = len(psdus)
+        fmt = np.broadcast_to(np.asarray(fmt, np.int32), (n,))
+        mcs = np.broadcast_to(np.asarray(mcs, np.int32), (n,))
+        gap = np.broadcast_to(np.asarray(gap, np.int64), (n,))
+        cfo = np.zeros(n, np.float32) if cfo is None else np.broadcast_to(np.asarray(cfo, np.float32), (n,))
+        d = np.zeros(n, TXFRAME_DTYPE)
+        offs = np.zeros(n + 1, np.int64)
+        po = 0
+        for i, p in enumerate(psdus):
+            ns = self.L.c8b_tx_nsamp(int(fmt[i]), int(mcs[i]), len(p))
+            if ns < 0:
+                raise ValueError("unsupported format / mcs / length: %d %d %d" % (fmt[i], mcs[i], len(p)))
+            d[i] = (fmt[i], mcs[i], po, len(p), cfo[i], offs[i] + gap[i])
+            offs[i + 1] = offs[i] + 2 * gap[i] + ns
+            po += len(p)
+        arena = np.frombuffer(b"".join(bytes(p) for p in psdus) + b"\0", np.uint8).copy()
+        return d, arena, offs
+
+    def tx_batch(self, psdus, fmt, mcs, gap=400, cfo=None, multiplier=12.0, seed=93):
+        """waveforms of tools/phy80211.py genFromMpdu / genFromAmpdu + genFinalSig(multiplier, cfoHz, gap): (iq, item offsets)"""
+        d, arena, offs = self.tx_layout(psdus, fmt, mcs, gap, cfo)
+        iq = np.zeros(int(offs[-1]), np.complex64)
+        self._ck(self.L.c8b_tx_batch(self.h, ptr(arena), arena.size, ptr(d), d.size, multiplier, seed, ptr(iq.view(np.float32)), iq.size), "c8b_tx_batch")
+        return iq, offs
+
+    def tx_batch_dev(self, d_psdu_ptr, psdu_bytes, desc, d_iq_ptr, iq_samples, multiplier=12.0, seed=93):
+        _producer_sync()
+        self._ck(self.L.c8b_tx_batch_dev(self.h, C.c_void_p(d_psdu_ptr), psdu_bytes, ptr(desc), desc.size, multiplier, seed,
+                                         C.c_void_p(d_iq_ptr), iq_samples), "c8b_tx_batch_dev")
 
     def rx_batch_dev(self, d_iq_ptr, off, length, pdu_stride=4400, frames=None, pdu=None):
         off = np.ascontiguousarray(off, np.int64)

@@ -184,6 +184,30 @@ int  c8b_stream_state(const c8b_ctx* ctx, int64_t* base, int64_t* fill, int64_t*
 int  c8b_timing_enable(c8b_ctx* ctx, int on);
 int  c8b_timing_read(c8b_ctx* ctx, double ms[C8B_K_COUNT], int64_t launches[C8B_K_COUNT], int reset);
 
+/* ---- transmit waveform synthesiser ---------------------------------------------------
+ * The reference's encode -> modulation -> IFFT/CP -> pad chain (lib/encode_impl.cc:130-241, lib/modulation_impl.cc,
+ * lib/pad_impl.cc:37-80, lib/cloud80211phy.cc:2594-3161) as its Python twin tools/phy80211.py produces it
+ * (genFromMpdu / genFromAmpdu + genFinalSig): 20 MHz, one spatial stream, long GI, legacy MCS 0-7, HT MCS 0-7
+ * (non-aggregated MPDU), VHT MCS 0-8 (A-MPDU, group id 0, partial AID 0; psdu_len 0 = NDP).  The samples equal the
+ * generator's (float32 rounding apart); they are what the receive entry points above are tested with. */
+typedef struct c8b_txframe {
+    int32_t format;        /* C8B_F_L / C8B_F_HT / C8B_F_VHT                                         */
+    int32_t mcs;
+    int64_t psdu_off;      /* byte offset of the MPDU (L, HT) or A-MPDU (VHT) in the PSDU arena       */
+    int32_t psdu_len;      /* bytes, <= 4095                                                          */
+    float   cfo_hz;        /* carrier offset applied to the frame (genFinalSig cfoHz)                 */
+    int64_t out_off;       /* sample index of the frame's first sample in the IQ arena                */
+} c8b_txframe;
+/* samples of the frame (a multiple of 80), or C8B_ERR_ARG for an unsupported format / mcs / length; no GPU needed */
+int  c8b_tx_nsamp(int format, int mcs, int psdu_len);
+/* host buffers: the IQ arena (iq_samples complex) is zero-filled, then every frame is written at its out_off.
+ * multiplier = genFinalSig's amplitude (the reference recipes use 12), scrambler_seed 1..127 (the generator uses 93) */
+int  c8b_tx_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                  int scrambler_seed, float* h_iq, int64_t iq_samples);
+/* device buffers: only the frames' own samples are written (gaps keep what they hold); asynchronous on the ctx stream */
+int  c8b_tx_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                      int scrambler_seed, float* d_iq, int64_t iq_samples);
+
 /* ---- staged entry points (host buffers in/out; used for parity tests and ncu captures) ---------
  * Each mirrors one reference block on whole arrays. */
 /* presiso: preac[n] (float), preconj[n] (complex, may be NULL) */

@@ -15,6 +15,9 @@ container (needs /root/reference); the GPU box and the test-suite only read the 
   frames_mu.npz       VHT NDP (2 transmit streams, one receive antenna) and 2-user MU-MIMO frames seen at each user
                       position (tools/cmu_ap.py recipe with a flat 2x2 channel and its zero-forcing precoder).
 
+  frames_tx.npz       the PSDU bytes behind frames_siso / frames_bench (inputs of genFromMpdu / genFromAmpdu) for the
+                      transmit synthesiser test.
+
 usage: python tests/golden/make_golden.py
 """
 import contextlib
@@ -223,6 +226,27 @@ def frames_mu():
     print("frames_mu: %d items, %d samples; meta = (3 NDP | 4 MU, mcs, cfo | user position)" % (len(items), offs[-1]))
 
 
+def frames_tx():
+    """The PSDUs (MPDU for legacy / HT, A-MPDU for VHT) behind the waveforms of frames_siso.npz and frames_bench.npz, in the
+    same order, so the transmit synthesiser (c8b_tx_batch) can be compared with the generator's samples."""
+    payload = "123456789012345678901234567890"
+    mpdu, ampdu = bytes(mac_mpdu(payload)), bytes(mac_ampdu([payload]))
+    ampdu2 = bytes(mac_ampdu([payload, "This is packet for station 001"]))
+    ps = [mpdu] + [mpdu] * 8 + [mpdu] * 8 + [ampdu] * 9 + [mpdu, mpdu, ampdu, ampdu] + [ampdu2]
+    gaps = [1200] + [400] * 30
+    g = np.load(os.path.join(HERE, "frames_siso.npz"))
+    assert len(ps) == len(g["offs"]) - 1
+    rng = np.random.default_rng(80211)
+    bench = []
+    for i in range(16):
+        pl = bytes(rng.integers(1, 128, 1434, dtype=np.uint8)).decode("latin-1")
+        bench.append(bytes(mac_ampdu([pl])))
+    np.savez_compressed(os.path.join(HERE, "frames_tx.npz"), psdu=np.frombuffer(b"".join(ps), np.uint8),
+                        psdu_len=np.array([len(p) for p in ps], np.int32), gap=np.array(gaps, np.int32),
+                        bench_psdu=np.frombuffer(b"".join(bench), np.uint8), bench_len=np.array([len(b) for b in bench], np.int32))
+    print("frames_tx: %d PSDUs (%d bytes), %d bench A-MPDUs" % (len(ps), sum(len(p) for p in ps), len(bench)))
+
+
 def ref_vectors():
     import oracle_lib as ol
     R = ol.ref()
@@ -283,9 +307,11 @@ def ref_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi", "mu"]
+    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi", "mu", "tx"]
     if "mu" in which:
         frames_mu()
+    if "tx" in which:
+        frames_tx()
     if "siso" in which:
         frames_siso()
     if "bench" in which:

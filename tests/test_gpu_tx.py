@@ -1,0 +1,118 @@
+"""Transmit synthesiser (c8b_tx_batch) against the reference's own generator: the waveforms of
+tools/phy80211.py (genFromMpdu / genFromAmpdu + genFinalSig) stored in tests/golden/frames_siso.npz and frames_bench.npz,
+regenerated on the GPU from the PSDU bytes (tests/golden/frames_tx.npz), must agree sample for sample; and the loop
+TX -> RX must return the MPDUs."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from __graft_entry__ import load_pkg
+
+pytestmark = pytest.mark.gpu
+HERE = __import__("os").path.dirname(__import__("os").path.abspath(__file__))
+
+
+def _tx_golden():
+    return np.load(HERE + "/golden/frames_tx.npz")
+
+
+def _psdus(t, key="psdu", lkey="psdu_len"):
+    o = np.cumsum(np.r_[0, t[lkey]])
+    return [bytes(t[key][o[i]:o[i + 1]]) for i in range(len(t[lkey]))]
+
+
+def test_waveforms_equal_the_generator(golden):
+    pkg = load_pkg()
+    g, t = golden["frames_siso"], _tx_golden()
+    ps = _psdus(t)
+    fmt = g["meta"][:, 0].astype(np.int32)
+    mcs = g["meta"][:, 1].astype(np.int32)
+    cfo = g["meta"][:, 2].astype(np.float32)
+    rx = pkg.Receiver(device=0)
+    iq, offs = rx.tx_batch(ps, fmt, mcs, gap=t["gap"], cfo=cfo, multiplier=12.0, seed=93)
+    rx.close()
+    assert np.array_equal(offs, g["offs"])
+    ref = g["iq"]
+    peak = float(np.max(np.abs(ref)))
+    for i in range(len(ps)):
+        a, b = iq[offs[i]:offs[i + 1]], ref[offs[i]:offs[i + 1]]
+        err = float(np.max(np.abs(a - b)))
+        # float32 synthesis vs the generator's float64 rounded to float32 (CFO frames: phase of up to 7000 samples in float32)
+        assert err <= (2e-6 if cfo[i] == 0 else 2e-5) * peak, (i, fmt[i], mcs[i], cfo[i], err)
+        assert np.all(a[:t["gap"][i]] == 0) and np.all(a[-t["gap"][i]:] == 0)
+
+
+def test_bench_frames_and_loopback(golden):
+    """config-5 frames (VHT MCS7, 1504-byte A-MPDU): same samples as the generator's, and TX -> RX returns every MPDU"""
+    pkg = load_pkg()
+    gb, t = golden["frames_bench"], _tx_golden()
+    ps = _psdus(t, "bench_psdu", "bench_len")
+    rx = pkg.Receiver(device=0)
+    iq, offs = rx.tx_batch(ps, 2, 7, gap=0)
+    assert offs[1] == 4560
+    got = iq.reshape(16, 4560)
+    assert float(np.max(np.abs(got - gb["iq"]))) <= 2e-6 * float(np.max(np.abs(gb["iq"])))
+    # loop back with gaps and noise
+    rng = np.random.default_rng(3)
+    iq, offs = rx.tx_batch(ps, 2, 7, gap=400, cfo=rng.uniform(-1e5, 1e5, 16))
+    s = 0.1875 / np.sqrt(2 * 10 ** 3.0)
+    x = (iq + s * (rng.standard_normal(iq.size) + 1j * rng.standard_normal(iq.size))).astype(np.complex64)
+    fr, pdu = rx.rx_batch(x, offs[:-1], np.diff(offs).astype(np.int32))
+    rx.close()
+    for i in range(16):
+        assert fr[i]["status"] == 0 and fr[i]["npdu"] == 1 and (fr[i]["format"], fr[i]["mcs"], fr[i]["len"]) == (2, 7, 1504)
+        assert bytes(pdu[i, 3:1503]) == bytes(gb["mpdu"][i]) == ps[i][4:1504]
+
+
+@pytest.mark.parametrize("fmt,mcss", [(0, range(8)), (1, range(8)), (2, range(9))])
+def test_loopback_every_rate_and_length(fmt, mcss):
+    """random PSDU lengths at every MCS: what the synthesiser emits, the receiver (and the oracle) decodes"""
+    pkg = load_pkg()
+    rng = np.random.default_rng(100 + fmt)
+    rx = pkg.Receiver(device=0)
+    ps, ms = [], []
+    for mcs in mcss:
+        for ln in (rng.integers(30, 200), rng.integers(200, 1600), 4 * rng.integers(400, 900)):
+            body = bytes(rng.integers(0, 256, int(ln), dtype=np.uint8))
+            crc = __import__("zlib").crc32(body) & 0xffffffff
+            mpdu = body + crc.to_bytes(4, "little")
+            if fmt == 2:                                          # one-MPDU A-MPDU: delimiter (tools/mac80211.py:333-360) + pad to 4
+                n = len(mpdu)
+                d0 = ((n & 0xf) << 4) | (((n >> 12) & 3) << 2) | 1   # EOF = 1 (single MPDU), reserved, len[12:14], len[0:4]
+                d1 = (n >> 4) & 0xff
+                bits = [(d0 >> k) & 1 for k in range(8)] + [(d1 >> k) & 1 for k in range(8)]
+                c = [1] * 8
+                for b in bits:
+                    f = b ^ c[7]
+                    c = [f, f ^ c[0], f ^ c[1], c[2], c[3], c[4], c[5], c[6]]
+                crc8 = sum((1 - c[7 - k]) << k for k in range(8))
+                mpdu_padded = mpdu + bytes((-n) % 4)
+                ps.append(bytes([d0, d1, crc8, 0x4E]) + mpdu_padded)
+            else:
+                ps.append(mpdu)
+            ms.append(mcs)
+    iq, offs = rx.tx_batch(ps, fmt, ms, gap=300)
+    s = 0.1875 / np.sqrt(2 * 10 ** 3.5)
+    x = (iq + s * (rng.standard_normal(iq.size) + 1j * rng.standard_normal(iq.size))).astype(np.complex64)
+    fr, pdu = rx.rx_batch(x, offs[:-1], np.diff(offs).astype(np.int32))
+    rx.close()
+    for i, p in enumerate(ps):
+        want = p[4:4 + (len(p) - 4)] if fmt == 2 else p
+        assert fr[i]["status"] == 0 and fr[i]["npdu"] == 1 and fr[i]["format"] == fmt and fr[i]["mcs"] == ms[i], (i, ms[i], len(p), fr[i]["status"], fr[i]["npdu"])
+        nb = int(fr[i]["pdu_bytes"])
+        got = bytes(pdu[i, 3:nb - 1])
+        assert got == (want[:len(got)] if fmt == 2 else want), (i, ms[i])
+        fo, _, po = ol.rx_item(x[offs[i]:offs[i + 1]], max_frames=1)
+        assert bytes(po) == bytes(pdu[i, :nb])
+
+
+def test_tx_argument_errors():
+    pkg = load_pkg()
+    rx = pkg.Receiver(device=0)
+    assert rx.L.c8b_tx_nsamp(0, 0, 100) == (5 + 35) * 80 and rx.L.c8b_tx_nsamp(2, 7, 1504) == 4560
+    assert rx.L.c8b_tx_nsamp(2, 9, 100) < 0 and rx.L.c8b_tx_nsamp(0, 8, 100) < 0 and rx.L.c8b_tx_nsamp(1, 0, 0) < 0 and rx.L.c8b_tx_nsamp(0, 0, 4096) < 0
+    with pytest.raises(ValueError):
+        rx.tx_batch([b"x" * 50], 3, 0)
+    with pytest.raises(RuntimeError):
+        rx.tx_batch([b"x" * 50], 0, 0, seed=0)
+    rx.close()
