@@ -129,6 +129,33 @@ def make_batch_device(torch, dev, nframes, seed):
     return out, g["mpdu"]
 
 
+def make_batch_tx(torch, dev, pkg, rx, nframes, seed):
+    """Synthetic config-5 batch made entirely ON THE DEVICE by the transmit synthesiser: every item carries its OWN random
+    1500-byte MPDU (valid FCS, one-MPDU A-MPDU), VHT MCS7, a CFO drawn from U(-100, 100) kHz, AWGN at 30 dB.
+    Returns (iq tensor [nframes*ITEM], psdu tensor [nframes, 1504] = what every frame must decode to)."""
+    rng = np.random.default_rng(13579 + seed)
+    d = np.zeros(nframes, pkg.TXFRAME_DTYPE)
+    d["format"], d["mcs"], d["psdu_len"] = 2, 7, MPDU_LEN + 4
+    d["psdu_off"] = np.arange(nframes, dtype=np.int64) * (MPDU_LEN + 4)
+    d["out_off"] = np.arange(nframes, dtype=np.int64) * ITEM + GAP
+    d["cfo_hz"] = rng.uniform(-100e3, 100e3, nframes).astype(np.float32)
+    psdu = torch.zeros(nframes * (MPDU_LEN + 4) + 16, dtype=torch.uint8, device=dev)
+    out = torch.zeros(nframes * ITEM, dtype=torch.complex64, device=dev)
+    torch.cuda.synchronize()
+    rx.tx_random_psdu_dev(psdu.data_ptr(), nframes * (MPDU_LEN + 4), d, seed=0x80211 + seed)
+    rx.tx_batch_dev(psdu.data_ptr(), nframes * (MPDU_LEN + 4), d, out.data_ptr(), nframes * ITEM, multiplier=12.0, seed=93)
+    rx.sync()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(13579 + seed)
+    sigma = 0.1875 / np.sqrt(2.0 * 10 ** (SNR_DB / 10))           # tools/performance/perf_siso.py:92
+    step = 16384 * ITEM
+    ov = torch.view_as_real(out)
+    for b in range(0, nframes * ITEM, step):
+        e = min(nframes * ITEM, b + step)
+        ov[b:e] += torch.randn((e - b, 2), generator=gen, device=dev) * sigma
+    return out, psdu[:nframes * (MPDU_LEN + 4)].view(nframes, MPDU_LEN + 4)
+
+
 def cpu_arm(nframes, threads, seed=0):
     """The oracle (CPU port of the reference path) on `nframes` config-5 items; returns (seconds, frames ok)."""
     import oracle_lib as ol
@@ -193,6 +220,8 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=4 * 56832, help="frames per host-buffer call of the e2e arm (4 pipeline chunks)")
     ap.add_argument("--chunk", type=int, default=56832, help="items per pipeline pass inside the library (3 CTAs x 148 SMs x 128 frames: one full wave of k_viterbi_tp)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--synth", default="tx", choices=["tx", "golden"],
+                    help="tx: every frame unique, made on the device by the transmit synthesiser; golden: the generator's 16 frames replicated")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,7 +251,11 @@ def main():
         rx.load_lut_device(blob.data_ptr(), blob_n)
 
     nfr = args.frames
-    iq, mpdus = make_batch_device(torch, dev, nfr, seed=rank)
+    psdu_sent = None
+    if args.synth == "tx":
+        iq, psdu_sent = make_batch_tx(torch, dev, pkg, rx, nfr, seed=rank)
+    else:
+        iq, mpdus = make_batch_device(torch, dev, nfr, seed=rank)
     off = (np.arange(nfr, dtype=np.int64) * ITEM)
     ln = np.full(nfr, ITEM, np.int32)
     d_frames = torch.zeros(nfr * pkg.FRAME_DTYPE.itemsize, dtype=torch.uint8, device=dev)
@@ -275,10 +308,19 @@ def main():
     # ---- correctness of what was just timed (outside the timed region) ----
     fr = np.frombuffer(d_frames.cpu().numpy().tobytes(), dtype=pkg.FRAME_DTYPE)
     ok = (fr["status"] == 0) & (fr["npdu"] == 1) & (fr["pdu_bytes"] == MPDU_LEN + 4)
-    chk = np.random.default_rng(1).choice(nfr, size=min(nfr, 512), replace=False)
-    pd = d_pdu.view(nfr, PDU_STRIDE)[torch.from_numpy(chk).to(dev)].cpu().numpy()
-    bytes_ok = sum(int(bytes(pd[j, 3:3 + MPDU_LEN]) == bytes(mpdus[int(i) % 16])) for j, i in enumerate(chk) if ok[i])
     frames_ok = int(ok.sum())
+    if psdu_sent is not None:                                        # EVERY decoded MPDU against the bytes its frame was built from
+        okd = torch.from_numpy(ok).to(dev)
+        same = torch.zeros(nfr, dtype=torch.bool, device=dev)
+        for b in range(0, nfr, 65536):
+            e = min(nfr, b + 65536)
+            same[b:e] = (d_pdu.view(nfr, PDU_STRIDE)[b:e, 3:3 + MPDU_LEN] == psdu_sent[b:e, 4:4 + MPDU_LEN]).all(dim=1)
+        bytes_ok, nchk = int((same & okd).sum().item()), frames_ok
+    else:
+        chk = np.random.default_rng(1).choice(nfr, size=min(nfr, 512), replace=False)
+        pd = d_pdu.view(nfr, PDU_STRIDE)[torch.from_numpy(chk).to(dev)].cpu().numpy()
+        bytes_ok = sum(int(bytes(pd[j, 3:3 + MPDU_LEN]) == bytes(mpdus[int(i) % 16])) for j, i in enumerate(chk) if ok[i])
+        nchk = int(ok[chk].sum())
 
     # ---- e2e: host (pinned) buffers through c8b_rx_batch, H2D + D2H inside the timed region ----
     ne = min(args.e2e_frames, nfr)
@@ -312,7 +354,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks: max time, sums of work ----
-    cnt, tt = pkg.parallel.reduce_stats(torch, dist, world, dev, [frames_ok, nfr, nfr * ITEM, bytes_ok, len(chk), e2e_ok], [ms, e2e_s * 1e3])
+    cnt, tt = pkg.parallel.reduce_stats(torch, dist, world, dev, [frames_ok, nfr, nfr * ITEM, bytes_ok, nchk, e2e_ok], [ms, e2e_s * 1e3])
     ms, e2e_ms = tt
     frames_ok, frames_total, samples_total, bytes_ok, nchk, e2e_ok = cnt
 
@@ -347,6 +389,8 @@ def main():
             "frames_per_s": frames_total * k / (ms * 1e-3),
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": nfr, "samples_per_item": ITEM, "chunk_items": args.chunk,
                        "l2": "inputs larger than L2 (%.1f GB of IQ per GPU per step)" % (nfr * ITEM * 8 / 1e9),
+                       "input": ("every frame unique: random 1500-byte MPDUs modulated on the device by the transmit synthesiser (c8b_tx_batch_dev)"
+                                 if args.synth == "tx" else "the reference generator's 16 frames replicated on the device"),
                        "frames_ok": frames_ok, "frames_total": frames_total, "mpdu_bytes_checked": "%d/%d identical" % (bytes_ok, nchk)},
             "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": calls * ne * ITEM * 8,
                     "d2h_bytes_per_step": calls * ne * (pkg.FRAME_DTYPE.itemsize + PDU_STRIDE), "frames_per_s": e2e_frames_total * e2e_steps / (e2e_ms * 1e-3),

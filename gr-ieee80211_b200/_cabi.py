@@ -72,6 +72,7 @@ SYMBOLS = [
     ("c8b_tx_nsamp", _i, [_i, _i, _i]),
     ("c8b_tx_batch", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _i64]),
     ("c8b_tx_batch_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _i64]),
+    ("c8b_tx_random_psdu_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_uint64]),
     ("c8b_timing_enable", _i, [_vp, _i]),
     ("c8b_timing_read", _i, [_vp, _vp, _vp, _i]),
     ("c8b_presiso", _i, [_vp, _vp, _i64, _vp, _vp]),

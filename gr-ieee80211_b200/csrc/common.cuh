@@ -51,3 +51,4 @@ uint32_t c8b_tx_eof_word(void);
 void c8b_tx_scrambler(int seed, uint32_t out[4]);
 void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
                    float2* d_out, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);
+void c8b_launch_tx_fill(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, uint8_t* d_psdu, uint64_t seed, cudaStream_t st);

@@ -958,6 +958,29 @@ int c8b_tx_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, co
     return C8B_OK;
 }
 
+int c8b_tx_random_psdu_dev(c8b_ctx* ctx, uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, uint64_t seed)
+{
+    if (!ctx || !d_psdu || psdu_bytes < 0 || !frames || nframes < 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nframes == 0) return C8B_OK;
+    for (int i = 0; i < nframes; i++) {
+        const c8b_txframe& f = frames[i];
+        const bool vht = f.format == C8B_F_VHT;
+        if (f.psdu_off < 0 || f.psdu_len < (vht ? 12 : 5) || f.psdu_len > 4095 || (vht && (f.psdu_len & 3)) || f.psdu_off + f.psdu_len > psdu_bytes) {
+            ctx->err = "c8b_tx_random_psdu_dev: PSDU region (VHT: 12.. bytes, multiple of 4; else 5.. bytes) outside the arena";
+            return C8B_ERR_ARG;
+        }
+    }
+    CK(cudaSetDevice(ctx->device));
+    EN(txf, (size_t)nframes * sizeof(c8b_txframe));
+    CK(cudaMemcpyAsync(ctx->txf.p, frames, (size_t)nframes * sizeof(c8b_txframe), cudaMemcpyHostToDevice, ctx->st));
+    c8b_launch_tx_fill(ctx->d_lut, (const c8b_txframe*)ctx->txf.p, nframes, d_psdu, seed, ctx->st);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
 int c8b_tx_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
                  int scrambler_seed, float* h_iq, int64_t iq_samples)
 {

@@ -293,7 +293,49 @@ k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int n
     }
 }
 
+// Synthetic traffic: every frame gets its own random MPDU with a valid FCS (CRC-32 as tools/mac80211.py:36-47 appends it),
+// wrapped for VHT in a one-MPDU A-MPDU (delimiter of tools/mac80211.py:333-360: EOF, reserved, len[12:14], len[0:12], CRC-8,
+// 0x4E) -- so a decoded PDU can be compared byte for byte with what was sent.  One thread per frame.
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_tx_fill(const c8b_lut* __restrict__ L, const c8b_txframe* __restrict__ fr, int n, uint8_t* __restrict__ psduAll, uint64_t seed)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const c8b_txframe f = fr[i];
+    uint8_t* __restrict__ p = psduAll + f.psdu_off;
+    int mlen = f.psdu_len;
+    if (f.format == C8B_F_VHT) {
+        mlen = f.psdu_len - 4;
+        const uint32_t d = 1u | (((uint32_t)mlen >> 12) & 3u) << 2 | ((uint32_t)mlen & 0xfffu) << 4;
+        const uint32_t c = crc8_bits(d, 16);
+        p[0] = (uint8_t)d; p[1] = (uint8_t)(d >> 8); p[2] = (uint8_t)c; p[3] = 0x4E;
+        p += 4;
+    }
+    if (mlen < 4) return;
+    uint32_t crc = 0xffffffffu;
+    for (int k = 0; k < mlen - 4; k++) {
+        const uint64_t r = mix64(seed ^ ((uint64_t)i << 24) ^ (uint64_t)(k >> 3));
+        const uint8_t b = (uint8_t)(r >> (8 * (k & 7)));
+        p[k] = b;
+        crc = L->crc32tab[(crc ^ b) & 0xff] ^ (crc >> 8);
+    }
+    crc = ~crc;
+    for (int k = 0; k < 4; k++) p[mlen - 4 + k] = (uint8_t)(crc >> (8 * k));
+}
+
 }  // namespace
+
+void c8b_launch_tx_fill(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, uint8_t* d_psdu, uint64_t seed, cudaStream_t st)
+{
+    if (nframes <= 0) return;
+    k_tx_fill<<<(nframes + 127) / 128, 128, 0, st>>>(lut, d_frames, nframes, d_psdu, seed);
+}
 
 // C_VHT_EOF (tools/phy80211header.py:737): EOF delimiter of length 0, bit k = element k
 uint32_t c8b_tx_eof_word(void) { return 1u | (crc8_bits(1u, 16) << 16) | (0x4Eu << 24); }

@@ -174,6 +174,10 @@ class Receiver:
         self._ck(self.L.c8b_tx_batch(self.h, ptr(arena), arena.size, ptr(d), d.size, multiplier, seed, ptr(iq.view(np.float32)), iq.size), "c8b_tx_batch")
         return iq, offs
 
+    def tx_random_psdu_dev(self, d_psdu_ptr, psdu_bytes, desc, seed=1):
+        _producer_sync()
+        self._ck(self.L.c8b_tx_random_psdu_dev(self.h, C.c_void_p(d_psdu_ptr), psdu_bytes, ptr(desc), desc.size, seed), "c8b_tx_random_psdu_dev")
+
     def tx_batch_dev(self, d_psdu_ptr, psdu_bytes, desc, d_iq_ptr, iq_samples, multiplier=12.0, seed=93):
         _producer_sync()
         self._ck(self.L.c8b_tx_batch_dev(self.h, C.c_void_p(d_psdu_ptr), psdu_bytes, ptr(desc), desc.size, multiplier, seed,

@@ -208,6 +208,11 @@ int  c8b_tx_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const
 int  c8b_tx_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
                       int scrambler_seed, float* d_iq, int64_t iq_samples);
 
+/* synthetic traffic for closed-loop runs: fills every frame's PSDU region (device memory) with a random MPDU carrying a valid
+ * FCS (tools/mac80211.py:36-47); VHT regions (psdu_len a multiple of 4) get the one-MPDU A-MPDU delimiter of
+ * tools/mac80211.py:333-360 in front.  A frame decoded by the receive path returns exactly these bytes. */
+int  c8b_tx_random_psdu_dev(c8b_ctx* ctx, uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, uint64_t seed);
+
 /* ---- staged entry points (host buffers in/out; used for parity tests and ncu captures) ---------
  * Each mirrors one reference block on whole arrays. */
 /* presiso: preac[n] (float), preconj[n] (complex, may be NULL) */

@@ -116,3 +116,51 @@ def test_tx_argument_errors():
     with pytest.raises(RuntimeError):
         rx.tx_batch([b"x" * 50], 0, 0, seed=0)
     rx.close()
+
+
+def test_device_traffic_closed_loop():
+    """c8b_tx_random_psdu_dev + c8b_tx_batch_dev + c8b_rx_batch_dev: 3000 frames with their own random MPDUs (all three formats,
+    every MCS, mixed lengths) never leave the device until the decoded bytes are compared with what was sent"""
+    import torch
+    pkg = load_pkg()
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(11)
+    n = 3000
+    d = np.zeros(n, pkg.TXFRAME_DTYPE)
+    d["format"] = rng.integers(0, 3, n)
+    d["mcs"] = np.where(d["format"] == 2, rng.integers(0, 9, n), rng.integers(0, 8, n))
+    d["psdu_len"] = 4 * rng.integers(10, 380, n)
+    d["psdu_off"] = np.concatenate([[0], np.cumsum(d["psdu_len"])[:-1]])
+    d["cfo_hz"] = rng.uniform(-8e4, 8e4, n).astype(np.float32)
+    rx = pkg.Receiver(device=0)
+    ns = np.array([rx.L.c8b_tx_nsamp(int(f), int(m), int(l)) for f, m, l in zip(d["format"], d["mcs"], d["psdu_len"])], np.int64)
+    item = ns + 600
+    off = np.concatenate([[0], np.cumsum(item)[:-1]]).astype(np.int64)
+    d["out_off"] = off + 300
+    nb, nsamp = int(d["psdu_len"].sum()), int(item.sum())
+    psdu = torch.zeros(nb + 16, dtype=torch.uint8, device=dev)
+    iq = torch.zeros(nsamp, dtype=torch.complex64, device=dev)
+    torch.cuda.synchronize()
+    rx.tx_random_psdu_dev(psdu.data_ptr(), nb, d, seed=7)
+    rx.tx_batch_dev(psdu.data_ptr(), nb, d, iq.data_ptr(), nsamp)
+    rx.sync()
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    iq += torch.view_as_complex(torch.randn((nsamp, 2), generator=g, device=dev) * (0.1875 / np.sqrt(2 * 10 ** 3.3)))
+    fr, pdu = rx.rx_batch_dev(iq.data_ptr(), off, item.astype(np.int32))
+    rx.close()
+    sent = psdu.cpu().numpy()
+    x = iq.cpu().numpy()
+    lost = []
+    for i in range(n):
+        f = fr[i]
+        vht = d["format"][i] == 2
+        want = bytes(sent[d["psdu_off"][i] + (4 if vht else 0): d["psdu_off"][i] + d["psdu_len"][i]])
+        assert __import__("zlib").crc32(want[:-4]) & 0xffffffff == int.from_bytes(want[-4:], "little")
+        if f["status"] == 0 and f["npdu"] == 1:
+            assert f["format"] == d["format"][i] and f["mcs"] == d["mcs"][i] and bytes(pdu[i, 3:f["pdu_bytes"] - 1]) == want, i
+        else:                                                      # lost to the noise: the oracle must lose it the same way
+            fo, _, po = ol.rx_item(x[off[i]:off[i] + item[i]], max_frames=1)
+            assert (f["status"], f["npdu"]) == (fo[0]["status"], fo[0]["npdu"]), (i, d[i], f["status"], fo[0]["status"])
+            lost.append((i, int(f["status"])))
+    assert len(lost) <= n // 200, lost
