@@ -52,3 +52,7 @@ void c8b_tx_scrambler(int seed, uint32_t out[4]);
 void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
                    float2* d_out, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);
 void c8b_launch_tx_fill(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, uint8_t* d_psdu, uint64_t seed, cudaStream_t st);
+size_t c8b_detect_multi_scratch(int nitems, int maxCand);
+void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
+                             int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
+                             float2* chan, c8b_scan* scans, void* scratch, int maxCand, cudaStream_t st);

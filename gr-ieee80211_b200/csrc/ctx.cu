@@ -39,6 +39,7 @@ struct c8b_ctx {
         int64_t overruns = 0;   // windows dropped because nothing in them could be decided
     } strm;
     DevBuf sw[2][2], scan;      // [antenna][ping-pong]
+    DevBuf cand;                // candidate records of the multi-frame detect path
     DevBuf txf, txplan, txpsdu, txiq;   // transmit synthesiser: descriptors, plans, staged PSDU bytes / samples
     c8b_scan* scanDev = nullptr;   // non-null while run_chunk serves a stream window
     // timing
@@ -168,7 +169,7 @@ void c8b_destroy(c8b_ctx* ctx)
     if (ctx->stVit) cudaStreamDestroy(ctx->stVit);
     DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->tp, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
                        &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev, &ctx->scan, &ctx->sw[0][0], &ctx->sw[0][1],
-                       &ctx->sw[1][0], &ctx->sw[1][1], &ctx->txf, &ctx->txplan, &ctx->txpsdu, &ctx->txiq };
+                       &ctx->sw[1][0], &ctx->sw[1][1], &ctx->txf, &ctx->txplan, &ctx->txpsdu, &ctx->txiq, &ctx->cand };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
@@ -402,10 +403,19 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
                            ctx->st);
     }
     {
+        // few long items with many frames each (a capture, a stream window): the per-trigger work runs in parallel
+        const bool multi = ctx->cfg.frontend_mode == 0 && maxf > 1 && n <= 64;
+        const int maxCand = 4 * maxf + 64;
+        if (multi) EN(cand, c8b_detect_multi_scratch(n, maxCand));
         StageTimer tm(ctx, C8B_K_DETECT);
-        (ctx->cfg.frontend_mode == 1 ? c8b_launch_detect : c8b_launch_detect_w)(
-            ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p, maskStride,
-            d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->scanDev, ctx->st);
+        if (multi)
+            c8b_launch_detect_multi(ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p,
+                                    (const uint32_t*)ctx->mask.p, maskStride, d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->scanDev,
+                                    ctx->cand.p, maxCand, ctx->st);
+        else
+            (ctx->cfg.frontend_mode == 1 ? c8b_launch_detect : c8b_launch_detect_w)(
+                ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p, maskStride,
+                d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->scanDev, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_HEADER);

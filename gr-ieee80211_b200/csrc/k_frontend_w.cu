@@ -218,12 +218,91 @@ __device__ int signal_at_w(const c8b_lut* __restrict__ L, const cf* __restrict__
     return 1;
 }
 
-template <bool SCAN>                             // SCAN: the item is a window of a live stream (c8b_scan in / out)
+// A complete word that ends below the threshold, holds no run of 21 (counting what the previous word left in nPlateau) and
+// meets the trigger idle with no hold-off pending cannot leave a trace (see the short-run rule in walk_word): the FSM is
+// in its reset state after it.
+__device__ __forceinline__ bool word_traceless(const TrigState& ts, const uint32_t m, const int kmax, const int i0, const int skipUntil,
+                                               const bool muted)
+{
+    if (ts.fPlateau || kmax < 32 || (m >> 31) || !(i0 >= skipUntil || muted)) return false;
+    uint32_t x = m;
+    x &= x >> 1; x &= x >> 2; x &= x >> 4; x &= x >> 8; x &= x >> 5;         // a bit survives iff a run of >= 21 ones exists
+    return x == 0u && ts.nPlateau + (__ffs(~m) - 1) <= 20;
+}
+
+// One bitmap word (samples i0 .. i0 + kmax) of the trigger FSM (lib/trigger_impl.cc:59-117, trig_step in phy_serial.cuh), evaluated
+// by the warp without walking every sample.  pv = this lane's preac value.  The word is cut at the only samples where the
+// FSM changes course -- the 21st sample of a plateau (count-down armed) and the last sample of the count-down (trigger) --
+// which go through trig_step itself; everything between is applied in bulk:
+//   * a stretch below the threshold resets the plateau state and advances the count-down,
+//   * a short run that ends inside the word with the trigger idle is stepped over (it cannot leave a trace),
+//   * a run above the threshold adds to nPlateau / the count-down; the flag 0x02 ("new maximum", the latch of sync's input
+//     2) fires at every sample that beats the running maximum, the last of which is the FIRST occurrence of the run's
+//     maximum -- one warp max + ballot instead of a walk.
+// Events before skipUntil (sync's 111-sample hold-off, lib/sync_impl.cc:141-146) or after a stall are dropped exactly as
+// the serial loop drops them.  TRACK (stream windows): safe = latest sample before which the FSM is in its reset state.
+// Resumable: returns the index of the next trigger (0x01) the caller has to act on, with k advanced past it, or -1 when the
+// word is finished; the caller handles the trigger (it may move skipUntil / set muted) and calls again.
+template <bool TRACK>
+__device__ __forceinline__ int walk_word(TrigState& ts, const uint32_t m, int& k, const int i0, const int kmax, const float pv, const int lane,
+                                         const int skipUntil, const bool muted, int& latch, int& safe)
+{
+    while (k < kmax) {
+        const int i = i0 + k;
+        if (TRACK && ts.nPlateau == 0 && ts.fPlateau == 0 && i >= skipUntil) safe = i;
+        const uint32_t rest = m >> k;
+        if (!(rest & 1u)) {                                                 // below the threshold: samples k .. k + gap - 1
+            const int gap = rest ? __ffs(rest) - 1 : kmax - k;
+            ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+            if (ts.fPlateau) {
+                if (ts.countDown <= gap) {                                  // the count-down ends in here: 0x01 at its last sample
+                    k += ts.countDown;
+                    ts.countDown = 0; ts.fPlateau = 0;
+                    const int t = i0 + k - 1;
+                    if (t >= skipUntil && !muted) return t;
+                    continue;
+                }
+                ts.countDown -= gap;
+            }
+            k += gap;
+            continue;
+        }
+        const uint32_t inv = ~rest;
+        int P = min(inv ? __ffs(inv) - 1 : 32, kmax - k);                   // run of samples above the threshold
+        // A short run that ends inside the word while the trigger is idle leaves nothing behind: the sample after it resets
+        // nPlateau / conjAc, and its 0x02 flags only move a latch that the first sample of the next plateau overwrites
+        // before any trigger can read it (no hold-off is pending, so that flag is honoured).
+        if (!ts.fPlateau && k + P < kmax && ts.nPlateau + P <= 20 && (i >= skipUntil || muted)) { k += P; continue; }
+        if (ts.fPlateau) P = min(P, ts.countDown - 1);                      // ... up to the sample that ends the count-down
+        else if (ts.fPlateauEnd == 0) P = min(P, max(0, 20 - ts.nPlateau)); // ... up to the sample that arms it (nPlateau 21)
+        if (P > 0) {
+            const float v = (lane >= k && lane < k + P) ? pv : -1.0f;       // preac >= 0
+            float mx = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+            if (mx > ts.conjAc) {                                           // :82-87, the last 0x02 of the run
+                const int first = i0 + __ffs(__ballot_sync(FULL, v == mx)) - 1;
+                ts.conjAc = mx;
+                if (first >= skipUntil && !muted) latch = first;
+            }
+            ts.nPlateau += P;
+            if (ts.fPlateau) ts.countDown -= P;
+            k += P;
+            continue;
+        }
+        const uint8_t fl = trig_step(ts, __shfl_sync(FULL, pv, k));         // the sample that arms or ends the count-down
+        k++;
+        if (fl == 0 || i < skipUntil || muted) continue;
+        if (fl & 0x01) return i;
+        if (fl & 0x02) latch = i;
+    }
+    return -1;
+}
+
 __global__ void __launch_bounds__(FW * 32)
 k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
            const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preacAll,
-           const uint32_t* __restrict__ maskAll, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan,
-           c8b_scan* __restrict__ scans)
+           const uint32_t* __restrict__ maskAll, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan)
 {
     __shared__ Ws ws[FW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -243,23 +322,18 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     // the blocks' state machines, evaluated uniformly by the warp (see detect_item in phy_serial.cuh)
     TrigState ts;
     trig_reset(ts);
-    c8b_scan* sc = SCAN ? scans + it : nullptr;                   // window of a live stream (see lut.h)
-    const bool live = SCAN && !sc->flush;
-    const int from = SCAN ? sc->from : 0;
-    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = SCAN ? sc->pos0 : 0, nf = 0;
-    int safe = from, posS = pos, nfS = 0, stalled = 0;
+    int latch = -1, skipUntil = 0, nTrig = 0, nEv = 0, nLsigFail = 0, pos = 0, nf = 0;
     bool syncStalled = false, sigStalled = false, done = false;
     // The scan goes bitmap word by bitmap word (32 samples).  A complete word without a sample above the threshold is
     // not walked: with the trigger idle the FSM stays in its reset state (lib/trigger_impl.cc:95-100) -- all such words up
     // to the next flagged one are skipped with one ballot over 32 prefetched words; during the 80-sample count-down
-    // (:101-109) the counter is simply advanced.  Flagged words are walked sample by sample from a lane-held copy of
-    // their 32 preac values.
+    // (:101-109) the counter is simply advanced.  Flagged words go through walk_word with a lane-held copy of their 32
+    // preac values.
     int blkBase = -(1 << 30);                                        // 32 bitmap words [blkBase, blkBase+32) summarised in nz
     uint32_t nz = 0;                                              // bit k: word blkBase+k must be walked
     const int nwords = (n + 31) >> 5;
-    for (int w = from >> 5; w < nwords && !done;) {
-        const int kfirst = w == (from >> 5) ? (from & 31) : 0;     // a window may start the FSM inside a word
-        if (mask && kfirst == 0) {
+    for (int w = 0; w < nwords && !done;) {
+        if (mask) {
             if (w < blkBase || w >= blkBase + 32) {
                 blkBase = w;
                 const int ww = w + lane;
@@ -271,7 +345,6 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
                 if (ts.fPlateau == 0) {
                     w += rem ? __ffs(rem) - 1 : 32 - (w - blkBase);
                     ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
-                    if (SCAN && w * 32 >= skipUntil) { safe = w * 32; posS = pos; nfS = nf; }
                     continue;
                 }
                 if (ts.countDown > 32) {                          // 32 sub-threshold samples of the count-down
@@ -285,55 +358,247 @@ k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
         const int i0 = w * 32;
         const float pv = (i0 + lane < n) ? preac[i0 + lane] : 0.0f;
         const int kmax = min(32, n - i0);
-        for (int k = kfirst; k < kmax && !done; k++) {
-            const int i = i0 + k;
-            if (SCAN && ts.nPlateau == 0 && ts.fPlateau == 0 && i >= skipUntil) { safe = i; posS = pos; nfS = nf; }
-            const uint8_t fl = trig_step(ts, __shfl_sync(FULL, pv, k));
-            if (fl == 0 || i < skipUntil || syncStalled) continue;
-            if (fl & 0x01) {
-                nTrig++;
-                if (n - i < C8B_SYNC_BUF) {
-                    if (live) { stalled = 1; done = true; } else syncStalled = true;
-                    continue;
-                }
-                const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
-                const SyncOut so = sync_at_w(x + i, cj, W, lane);
-                skipUntil = i + C8B_SYNC_RES;
-                if (!so.ok) continue;
-                nEv++;
-                const int idx = i + so.mIndex;
-                if (sigStalled || idx < pos) continue;
-                if (n - idx < 224) {
-                    if (live) { stalled = 1; done = true; } else sigStalled = true;
-                    continue;
-                }
-                int mcs = 0, ln = 0, nsamp = 0;
-                if (!signal_at_w(lut, x + idx, so.rad, h + nf * 64, &mcs, &ln, &nsamp, W, lane)) {
-                    for (int q = lane; q < 64; q += 32) h[nf * 64 + q] = make_float2(0.f, 0.f);
-                    nLsigFail++; pos = idx + 80; continue;
-                }
-                c8b_frame* fk = f + nf;
-                nf++;
-                pos = idx + 224 + nsamp;
-                const int status = pos > n ? C8B_ST_TRUNC : C8B_ST_OK;
-                if (lane == 0) {
-                    fk->trig_idx = i; fk->sync_idx = idx; fk->rad = so.rad; fk->snr = so.snr; fk->rssi = so.rssi;
-                    fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);
-                    fk->l_mcs = mcs; fk->l_len = ln; fk->nsamp = nsamp; fk->status = status;
-                }
-                if (pos > n) { done = true; stalled = 1; }
-                else if (nf >= maxf) { done = true; stalled = 2; }
-            } else if (fl & 0x02) {
-                latch = i;
+        auto onTrig = [&](int i) {
+            nTrig++;
+            if (n - i < C8B_SYNC_BUF) { syncStalled = true; return; }
+            const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
+            const SyncOut so = sync_at_w(x + i, cj, W, lane);
+            skipUntil = i + C8B_SYNC_RES;
+            if (!so.ok) return;
+            nEv++;
+            const int idx = i + so.mIndex;
+            if (sigStalled || idx < pos) return;
+            if (n - idx < 224) { sigStalled = true; return; }
+            int mcs = 0, ln = 0, nsamp = 0;
+            if (!signal_at_w(lut, x + idx, so.rad, h + nf * 64, &mcs, &ln, &nsamp, W, lane)) {
+                for (int q = lane; q < 64; q += 32) h[nf * 64 + q] = make_float2(0.f, 0.f);
+                nLsigFail++; pos = idx + 80; return;
             }
-        }
+            c8b_frame* fk = f + nf;
+            nf++;
+            pos = idx + 224 + nsamp;
+            const int status = pos > n ? C8B_ST_TRUNC : C8B_ST_OK;
+            if (lane == 0) {
+                fk->trig_idx = i; fk->sync_idx = idx; fk->rad = so.rad; fk->snr = so.snr; fk->rssi = so.rssi;
+                fk->cfo_hz = fmul(so.rad, 3183098.8618379068f);
+                fk->l_mcs = mcs; fk->l_len = ln; fk->nsamp = nsamp; fk->status = status;
+            }
+            if (pos > n || nf >= maxf) done = true;
+        };
+        const uint32_t above = __ballot_sync(FULL, lane < kmax && pv > 0.3f);      // lib/trigger_impl.cc:79
+        if (word_traceless(ts, above, kmax, i0, skipUntil, syncStalled)) { ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f; w++; continue; }
+        int unused = 0;
+        for (int k = 0, t; !done && (t = walk_word<false>(ts, above, k, i0, kmax, pv, lane, skipUntil, syncStalled, latch, unused)) >= 0;) onTrig(t);
         w++;
     }
-    if (SCAN) {
-        if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && n >= skipUntil) { safe = n; posS = pos; nfS = nf; }
-        if (lane == 0) { sc->safe = safe; sc->pos = posS; sc->nf = nfS; sc->stalled = stalled; }
-    }
     if (nf == 0 && lane == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Many frames per item (a long capture, a window of a live stream): the serial part of detection is only the trigger
+// FSM and the accept rules; sync + signal of every trigger are independent of each other.  Three passes:
+//   k_trig_scan  : one warp per item -- the FSM scan of k_detect_w without the per-trigger work; emits the triggers that
+//                  survive the sync hold-off as candidates (index, latch, safe point before their plateau)
+//   k_cand_eval  : one warp per candidate -- sync_at_w, then signal_at_w when the LTF correlation passes
+//   k_cand_accept: one thread per item -- S_COPY swallow rule, stalls, frame records, stream restart point
+// Same results as the one-thread routine detect_item (phy_serial.cuh; frontend_mode 1 -- the tests run both); used when few
+// items may hold many frames each.
+// ---------------------------------------------------------------------------------------------------
+struct Cand {
+    int32_t trig, latch, safe;      // trigger index, argmax of preac in its plateau, restart point before the plateau
+    int32_t stall;                  // 1: fewer than 240 samples after the trigger (sync_impl.cc:94)
+    int32_t ok, idx, sig;           // sync passed, sync index, signal: 0 not run (stall), 1 L-SIG ok, 2 L-SIG failed
+    int32_t mcs, len, nsamp;
+    float rad, snr, rssi;
+    float2 chan[64];
+};
+struct CandHead { int32_t n, overflow, safeEnd, nTrig; };
+
+__global__ void __launch_bounds__(32)
+k_trig_scan(const int32_t* __restrict__ len, int nitems, int64_t outBase, const int64_t* __restrict__ off, const float* __restrict__ preacAll,
+            const uint32_t* __restrict__ maskAll, int maskStride, const c8b_scan* __restrict__ scans, Cand* __restrict__ cands,
+            CandHead* __restrict__ heads, int maxCand)
+{
+    const int lane = threadIdx.x, it = blockIdx.x;
+    if (it >= nitems) return;
+    const float* __restrict__ preac = preacAll + (off[it] - outBase);
+    const uint32_t* __restrict__ mask = maskAll + (size_t)it * maskStride;
+    const int n = len[it];
+    Cand* __restrict__ cd = cands + (size_t)it * maxCand;
+    const int from = scans ? scans[it].from : 0;
+    TrigState ts;
+    trig_reset(ts);
+    int latch = -1, skipUntil = 0, nc = 0, nTrig = 0, safe = from, overflow = 0;
+    bool done = false;
+    // This warp is alone with its item, so nothing hides a dependent load: the bitmap words of 4 x 32 x 32 samples are fetched
+    // at once (four per lane) and the preac values of the flagged words among them are staged in shared memory in one go.
+    constexpr int SB = 4;                                            // sub-blocks of 32 words per fetch
+    __shared__ float pvb[SB * 1024];
+    int supBase = -(1 << 30);
+    uint32_t nzs[SB] = { 0, 0, 0, 0 }, mvs[SB] = { 0, 0, 0, 0 };
+    const int nwords = (n + 31) >> 5;
+    for (int w = from >> 5; w < nwords && !done;) {
+        const int kfirst = w == (from >> 5) ? (from & 31) : 0;
+        int jb = 0, blkBase = 0;
+        uint32_t nz = 0, mvLane = 0;
+        if (kfirst == 0) {
+            if (w < supBase || w >= supBase + 32 * SB) {
+                supBase = w;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < SB; j++) {
+                    const int ww = supBase + 32 * j + lane;
+                    const bool part = ww * 32 < n && ww * 32 + 32 > n;        // the partial last word is always walked
+                    mvs[j] = ww * 32 < n ? mask[ww] : 0u;
+                    nzs[j] = __ballot_sync(FULL, part || mvs[j] != 0u);
+                }
+#pragma unroll
+                for (int j = 0; j < SB; j++) {
+#pragma unroll 8
+                    for (int r = 0; r < 32; r++)
+                        if ((nzs[j] >> r) & 1u) {
+                            const int idx = (supBase + 32 * j + r) * 32 + lane;
+                            pvb[(32 * j + r) * 32 + lane] = idx < n ? preac[idx] : 0.0f;
+                        }
+                }
+                __syncwarp();
+            }
+            jb = (w - supBase) >> 5;
+            blkBase = supBase + 32 * jb;
+            nz = jb == 0 ? nzs[0] : jb == 1 ? nzs[1] : jb == 2 ? nzs[2] : nzs[3];
+            mvLane = jb == 0 ? mvs[0] : jb == 1 ? mvs[1] : jb == 2 ? mvs[2] : mvs[3];
+            const uint32_t rem = nz >> (w - blkBase);
+            if (!(rem & 1u)) {
+                if (ts.fPlateau == 0) {
+                    w += rem ? __ffs(rem) - 1 : 32 - (w - blkBase);
+                    ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+                    if (w * 32 >= skipUntil) safe = w * 32;
+                    continue;
+                }
+                if (ts.countDown > 32) {
+                    ts.countDown -= 32;
+                    ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f;
+                    w++;
+                    continue;
+                }
+            }
+        }
+        const int i0 = w * 32;
+        const int kmax = min(32, n - i0);
+        float pv;
+        uint32_t above;                                               // bit k: sample i0 + k is above the threshold (lib/trigger_impl.cc:79)
+        if (kfirst == 0) {
+            const int r = w - blkBase;
+            pv = ((nz >> r) & 1u) ? pvb[(32 * jb + r) * 32 + lane] : 0.0f;
+            above = __shfl_sync(FULL, mvLane, r);                     // k_presiso's bitmap is this very comparison
+        } else {                                                      // a window that starts the FSM inside a word
+            pv = (i0 + lane < n) ? preac[i0 + lane] : 0.0f;
+            above = __ballot_sync(FULL, lane < kmax && pv > 0.3f);
+        }
+        auto onTrig = [&](int i) {
+            nTrig++;
+            if (nc >= maxCand) { overflow = 1; done = true; return; }
+            const int stall = n - i < C8B_SYNC_BUF;
+            if (lane == 0) { cd[nc].trig = i; cd[nc].latch = latch; cd[nc].safe = safe; cd[nc].stall = stall; cd[nc].ok = 0; cd[nc].sig = 0; }
+            nc++;
+            if (stall) { done = true; return; }                   // live: wait for more samples; batch: nothing after it is looked at
+            skipUntil = i + C8B_SYNC_RES;
+        };
+        if (kfirst == 0 && word_traceless(ts, above, kmax, i0, skipUntil, false)) { ts.nPlateau = 0; ts.fPlateauEnd = 0; ts.conjAc = 0.0f; w++; continue; }
+        for (int k = kfirst, t; !done && (t = walk_word<true>(ts, above, k, i0, kmax, pv, lane, skipUntil, false, latch, safe)) >= 0;) onTrig(t);
+        w++;
+    }
+    int safeEnd = -1;                                             // scan ran to the end in the reset state: everything is decided
+    if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && n >= skipUntil) safeEnd = n;
+    if (lane == 0) { heads[it].n = nc; heads[it].overflow = overflow; heads[it].safeEnd = safeEnd >= 0 ? safeEnd : safe; heads[it].nTrig = nTrig; }
+}
+
+__global__ void __launch_bounds__(FW * 32)
+k_cand_eval(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
+            int nitems, Cand* __restrict__ cands, const CandHead* __restrict__ heads, int maxCand)
+{
+    __shared__ Ws ws[FW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gid = (int64_t)blockIdx.x * FW + warp;
+    const int it = (int)(gid / maxCand), c = (int)(gid % maxCand);
+    if (it >= nitems || c >= heads[it].n) return;
+    Ws& W = ws[warp];
+    Cand* __restrict__ cd = cands + (size_t)it * maxCand + c;
+    if (cd->stall) return;
+    const cf* __restrict__ x = reinterpret_cast<const cf*>(iq + off[it]);
+    const int n = len[it], i = cd->trig, latch = cd->latch;
+    const cf cj = latch >= 0 ? presiso_conj_at(x, latch) : mk(0.f, 0.f);
+    const SyncOut so = sync_at_w(x + i, cj, W, lane);
+    int sig = 0, mcs = 0, ln = 0, nsamp = 0;
+    const int idx = i + so.mIndex;
+    if (so.ok && n - idx >= 224) {
+        __syncwarp();
+        sig = signal_at_w(lut, x + idx, so.rad, cd->chan, &mcs, &ln, &nsamp, W, lane) ? 1 : 2;
+    }
+    if (lane == 0) {
+        cd->ok = so.ok; cd->idx = idx; cd->rad = so.rad; cd->snr = so.snr; cd->rssi = so.rssi;
+        cd->sig = sig; cd->mcs = mcs; cd->len = ln; cd->nsamp = nsamp;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_cand_accept(const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, const Cand* __restrict__ cands,
+              const CandHead* __restrict__ heads, int maxCand, c8b_frame* __restrict__ frames, float2* __restrict__ chan,
+              c8b_scan* __restrict__ scans)
+{
+    const int it = blockIdx.x, lane = threadIdx.x;                // one warp per item: the rules run uniformly, the copies by lane
+    if (it >= nitems) return;
+    const int n = len[it];
+    const Cand* __restrict__ cd = cands + (size_t)it * maxCand;
+    const CandHead hd = heads[it];
+    c8b_frame* __restrict__ f = frames + (size_t)it * maxf;
+    float2* __restrict__ h = chan + (size_t)it * maxf * 64;
+    c8b_scan* sc = scans ? scans + it : nullptr;
+    const bool live = sc && !sc->flush;
+    for (int k = lane; k < maxf; k += 32) frame_clear(f + k, itemBase + it, C8B_ST_EMPTY);
+    for (int k = lane; k < maxf * 64; k += 32) h[k] = make_float2(0.f, 0.f);
+    __syncwarp();
+    int pos = sc ? sc->pos0 : 0, nf = 0, nEv = 0, nLsigFail = 0;
+    int safe = sc ? sc->from : 0, posS = pos, nfS = 0, stalled = 0;
+    bool syncStalled = false, sigStalled = false, done = false;
+    for (int c = 0; c < hd.n && !done; c++) {
+        const Cand& q = cd[c];
+        if (q.safe > safe || c == 0) { safe = q.safe; posS = pos; nfS = nf; }     // the restart point before this trigger's plateau
+        if (syncStalled) continue;
+        if (q.stall) {
+            if (live) { stalled = 1; done = true; } else syncStalled = true;
+            continue;
+        }
+        if (!q.ok) continue;
+        nEv++;
+        if (sigStalled || q.idx < pos) continue;                  // swallowed by S_COPY / skipped 80
+        if (n - q.idx < 224) {
+            if (live) { stalled = 1; done = true; } else sigStalled = true;
+            continue;
+        }
+        if (q.sig != 1) { nLsigFail++; pos = q.idx + 80; continue; }
+        c8b_frame* fk = f + nf;
+        for (int k = lane; k < 64; k += 32) h[nf * 64 + k] = q.chan[k];
+        nf++;
+        pos = q.idx + 224 + q.nsamp;
+        if (lane == 0) {
+            fk->trig_idx = q.trig; fk->sync_idx = q.idx; fk->rad = q.rad; fk->snr = q.snr; fk->rssi = q.rssi;
+            fk->cfo_hz = fmul(q.rad, 3183098.8618379068f);
+            fk->l_mcs = q.mcs; fk->l_len = q.len; fk->nsamp = q.nsamp;
+            fk->status = pos > n ? C8B_ST_TRUNC : C8B_ST_OK;
+        }
+        if (pos > n) { done = true; stalled = 1; }
+        if (nf >= maxf) { done = true; if (!stalled) stalled = 2; }
+    }
+    if (!done && hd.overflow) { done = true; stalled = 2; }       // candidate records used up: the scan stopped there
+    if (!done && !syncStalled) {
+        // the scan's own end state: the restart point it reached after the last candidate
+        if (hd.safeEnd > safe || hd.n == 0) { safe = hd.safeEnd; posS = pos; nfS = nf; }
+    }
+    if (lane == 0) {
+        if (sc) { sc->safe = safe; sc->pos = posS; sc->nf = nfS; sc->stalled = stalled; }
+        if (nf == 0) f->status = hd.nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -529,12 +794,27 @@ void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_
                          float2* chan, c8b_scan* scans, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    if (scans)
-        k_detect_w<true><<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask,
-                                                                      maskStride, frames, chan, scans);
-    else
-        k_detect_w<false><<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask,
-                                                                       maskStride, frames, chan, nullptr);
+    // one warp per item, frames of an item found serially: the batch path (many items).  Stream windows (scans) and
+    // long captures go through c8b_launch_detect_multi.
+    (void)scans;
+    k_detect_w<<<(nitems + FW - 1) / FW, FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, itemBase, maxf, outBase, preac, mask, maskStride,
+                                                            frames, chan);
+}
+
+size_t c8b_detect_multi_scratch(int nitems, int maxCand) { return (size_t)nitems * maxCand * sizeof(Cand) + (size_t)nitems * sizeof(CandHead) + 256; }
+
+// few long items with many frames each: trigger scan -> per-trigger sync / signal in parallel -> accept rules
+void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
+                             int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
+                             float2* chan, c8b_scan* scans, void* scratch, int maxCand, cudaStream_t st)
+{
+    if (nitems <= 0) return;
+    CandHead* heads = reinterpret_cast<CandHead*>(scratch);
+    Cand* cands = reinterpret_cast<Cand*>(reinterpret_cast<char*>(scratch) + (((size_t)nitems * sizeof(CandHead) + 255) & ~(size_t)255));
+    k_trig_scan<<<nitems, 32, 0, st>>>(d_len, nitems, outBase, d_off, preac, mask, maskStride, scans, cands, heads, maxCand);
+    const int64_t warps = (int64_t)nitems * maxCand;
+    k_cand_eval<<<(unsigned)((warps + FW - 1) / FW), FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, cands, heads, maxCand);
+    k_cand_accept<<<nitems, 32, 0, st>>>(d_len, nitems, itemBase, maxf, cands, heads, maxCand, frames, chan, scans);
 }
 
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,
