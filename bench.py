@@ -365,7 +365,7 @@ def main():
         e2e_frames_total = calls * ne * world
         e2e_v = e2e_frames_total * ITEM * e2e_steps / (e2e_ms * 1e-3)
         nch = (nfr + args.chunk - 1) // args.chunk
-        launches = (sum(v[1] for v in stage.values()) + nch) * k    # kernels launched inside the timed region: 5 stage kernels + k_ndp per chunk
+        launches = (sum(v[1] for v in stage.values()) + nch) * k * world   # kernels launched inside the timed region, all ranks: 5 stage kernels + k_ndp per chunk
         # algorithmic bytes per launch, per kernel; one launch covers one chunk of items
         per_launch_items = nfr / nch
         alg = {

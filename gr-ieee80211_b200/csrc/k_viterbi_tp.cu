@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int TPB = 128;                       // threads (= frames) per CTA
+constexpr int TPB = 128;                       // threads (= frames) per CTA (224 x 2 CTAs = 14 warps per SM at 144 registers spills: slower)
 constexpr int CS = 30;                         // trellis steps per staged chunk (multiple of every puncture period and of 2)
 constexpr int ROWF2 = CS + 1;                  // float2 per shared-memory row (odd -> conflict-free 8-byte column walks)
 
