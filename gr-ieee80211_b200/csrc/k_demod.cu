@@ -49,6 +49,19 @@ struct __align__(16) WarpBuf {
     float2 pil[SPW * 4];            // equalised pilots of each symbol: bins 7, 21, 43, 57
 };
 
+// cos / sin of the CFO phase the reference evaluates with cosf / sinf (lib/signal_impl.cc:172-173).  The phase itself is the
+// reference's float product (up to ~150 rad, so its own rounding is ~1e-5 rad); reduced to [-pi, pi] with a two-constant
+// Cody-Waite step it goes through the SFU approximations, whose 4e-7 absolute error is far inside the 1e-4 LLR tolerance
+// and an order of magnitude cheaper than the full-range sincosf.
+__device__ __forceinline__ void cfo_rot(float ph, float* sn, float* cs)
+{
+    const float k = rintf(ph * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, ph);            // 2 pi = 6.2831854820251465 - 1.7484555e-7
+    r = fmaf(k, 1.7484555e-7f, r);
+    *sn = __sinf(r);
+    *cs = __cosf(r);
+}
+
 __global__ void __launch_bounds__(DW * 32, 8)
 k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int maxf,
         const c8b_frame* __restrict__ frames, const float2* __restrict__ hinvAll, float* __restrict__ llrArena)
@@ -88,7 +101,7 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
             const int n = j + 8 * m;
             const float2 s = __ldg(x + n);
             float sn, cs;
-            sincosf(__fmul_rn((float)(k0 + n + 224), rad), &sn, &cs);     // lib/signal_impl.cc:172-173
+            cfo_rot(__fmul_rn((float)(k0 + n + 224), rad), &sn, &cs);     // lib/signal_impl.cc:172-173
             v[m] = { s.x * cs - s.y * sn, s.x * sn + s.y * cs };
         }
     } else {
@@ -241,7 +254,7 @@ k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const 
             const int n = j + 8 * m;
             const float2 s = __ldg(x + n);
             float sn, cs;
-            sincosf(__fmul_rn((float)(k0 + n + 224), rad), &sn, &cs);     // lib/signal2_impl.cc:172-177
+            cfo_rot(__fmul_rn((float)(k0 + n + 224), rad), &sn, &cs);     // lib/signal2_impl.cc:172-177
             v[m] = { s.x * cs - s.y * sn, s.x * sn + s.y * cs };
         }
     } else {
