@@ -28,14 +28,16 @@ for r in rows:
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += float(r[-1].replace(",", ""))
-tot = sum(v[1] for k, v in agg.items() if k.startswith("k_"))
+SETUP = ("k_tx_",)                                              # input synthesis: launched before the timed region
+tot = sum(v[1] for k, v in agg.items() if k.startswith("k_") and not k.startswith(SETUP))
 with open(os.path.join(out, "launches_%s.md" % rnd), "w") as f:
     f.write("# ncu launch list, %s (`--metrics gpu__time_duration.sum --clock-control none`, bench.py --frames 113664 --steps 2 --warmup 1 --no-cpu: two chunks per step)\n\n" % rnd)
     f.write("Per-launch times are cold-cache and serialised by ncu: compare SHARES with bench.py's `stages`, not absolutes.\n\n")
-    f.write("| kernel | launches | total ms | avg ms | share of our kernels |\n|---|---|---|---|---|\n")
+    f.write("| kernel | launches | total ms | avg ms | share of the step's kernels |\n|---|---|---|---|---|\n")
     for k, v in agg.items():
         if k.startswith("k_"):
-            f.write("| %s | %d | %.3f | %.3f | %.3f |\n" % (k, v[0], v[1] / 1e6, v[1] / v[0] / 1e6, v[1] / tot))
+            share = "(input synthesis, outside the timed region)" if k.startswith(SETUP) else "%.3f" % (v[1] / tot)
+            f.write("| %s | %d | %.3f | %.3f | %s |\n" % (k, v[0], v[1] / 1e6, v[1] / v[0] / 1e6, share))
     f.write("\n(torch kernels that build the synthetic batch are in the csv but not listed here.)\n")
 subprocess.call(["cp", launches, os.path.join(out, "launches_%s.csv" % rnd)])
 
