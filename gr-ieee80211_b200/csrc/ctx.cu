@@ -25,7 +25,7 @@ struct c8b_ctx {
     bool lutLoaded = false;
     unsigned* d_counter = nullptr;
     // scratch (grown on demand)
-    DevBuf iq, iq1, mask, llrB, tp, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram, ev;
+    DevBuf iq, iq1, mask, llrB, tp, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram;
     int survWarps = 0;
     // live-stream session (c8b_stream_*): a device-resident window of the capture, ping-pong compacted
     struct Stream {
@@ -168,7 +168,7 @@ void c8b_destroy(c8b_ctx* ctx)
     for (int k = 0; k < 2; k++) { if (ctx->evFront[k]) cudaEventDestroy(ctx->evFront[k]); if (ctx->evVit[k]) cudaEventDestroy(ctx->evVit[k]); }
     if (ctx->stVit) cudaStreamDestroy(ctx->stVit);
     DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->tp, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
-                       &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->ev, &ctx->scan, &ctx->sw[0][0], &ctx->sw[0][1],
+                       &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->scan, &ctx->sw[0][0], &ctx->sw[0][1],
                        &ctx->sw[1][0], &ctx->sw[1][1], &ctx->txf, &ctx->txplan, &ctx->txpsdu, &ctx->txiq, &ctx->cand };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);

@@ -1,10 +1,12 @@
 // k_frontend.cu -- everything before the per-symbol loop:
 //   k_presiso : the presiso hier block (examples/presiso.grc:35-229): x[n-16]*conj(x[n]) -> moving
 //               sum 48, |x|^2 -> moving sum 64, preac = |c| / p.  Data-parallel, HBM streaming:
-//               8 B read + 4 B (preac) [+ 8 B preconj] written per sample.
+//               8 B read + 4 B (preac) [+ 8 B preconj] written per sample; a warp sweeps its segment with the
+//               sliding tree in registers.  Also writes the 1-bit-per-sample threshold bitmap.
 //   k_trigger : trigger FSM over one array (staged entry point, lib/trigger_impl.cc:59-117)
-//   k_detect  : one thread per item: trigger FSM -> sync -> signal (phy_serial.cuh::detect_item)
-//   k_header  : one thread per frame: format detection, SIG fields, channel estimate
+//   k_detect  : one thread per item: trigger FSM -> sync -> signal (phy_serial.cuh::detect_item)      } frontend_mode 1; the
+//   k_header  : one thread per frame: format detection, SIG fields, channel estimate                  } default kernels are
+//   k_header2 : the same for the 2-antenna block (signal2 / demod2)                                   } in k_frontend_w.cu
 #include "common.cuh"
 #include "phy_serial.cuh"
 

@@ -1,6 +1,7 @@
 // k_frontend_w.cu -- warp-cooperative versions of the per-frame stages:
 //   k_detect_w : one WARP per item  : trigger FSM -> sync -> signal   (same results as k_detect)
 //   k_header_w : one WARP per frame : demod header states, 1 antenna  (same results as k_header)
+//   k_trig_scan / k_cand_eval / k_cand_accept : few long items with many frames each (a capture, a stream window)
 // The thread-per-item kernels in k_frontend.cu are latency-bound (5 KB of local arrays per thread, ~7 warps per
 // SM at a 37888-item chunk); here the control flow stays the reference's sequential state machine, executed
 // uniformly by all 32 lanes, while every heavy loop is spread over the lanes through a per-warp shared-memory

@@ -98,10 +98,9 @@ __device__ __forceinline__ int used_by(int cr, int T)
     return 6 * q + (r == 0 ? 0 : r + 1);
 }
 
-struct TpScratch {             // per resident CTA, in global memory
-    uint2* surv;               // [C8B_DECODE_T_MAX + CS][TPB] decision words
-    uint32_t* words;           // [(C8B_DECODE_T_MAX + 63) / 32][TPB] decoded bits, LSB first; descrambled in place
-};
+// Scratch per resident CTA, in global memory:
+//   surv  [C8B_DECODE_T_MAX + CS][TPB] uint2     decision words, one per trellis step and thread
+//   words [(C8B_DECODE_T_MAX + 63) / 32][TPB]    decoded bits, LSB first; descrambled in place
 
 __device__ __forceinline__ uint32_t get_byte(const uint32_t* __restrict__ words, int i)
 {

@@ -104,7 +104,7 @@ typedef struct c8b_frame {
 typedef struct c8b_cfg {
     int32_t device;          /* CUDA device ordinal                                               */
     int32_t chunk_items;     /* items processed per pipeline pass (scratch is sized for this)     */
-    int32_t max_item_len;    /* longest item, complex samples                                     */
+    int32_t max_item_len;    /* reserved (scratch is sized on demand from the items of each call)  */
     int32_t max_frames;      /* frame records per item (0 -> 1); a long capture is one item with many */
     int32_t mupos;           /* demod(mupos, mugid) ctor args (lib/demod_impl.cc:28-32)           */
     int32_t mugid;
