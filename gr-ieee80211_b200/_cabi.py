@@ -65,6 +65,7 @@ SYMBOLS = [
     ("c8b_rx_batch2", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch_dev", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch_dev_async", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
+    ("c8b_rx_batch2_dev", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_sync", _i, [_vp]),
     ("c8b_stream_begin", _i, [_vp, _i, _i64]),
     ("c8b_stream_push", _i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _i64]),

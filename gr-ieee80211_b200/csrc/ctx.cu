@@ -476,8 +476,8 @@ static int upload_items(c8b_ctx* ctx, const int64_t* off, const int32_t* len, in
 
 extern "C" {
 
-int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* d_frames,
-                           uint8_t* d_pdu, int64_t pdu_stride)
+static int rx_batch_dev_async2(c8b_ctx* ctx, const float* d_iq, const float* d_iq1, const int64_t* off, const int32_t* len, int nitems,
+                               c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride)
 {
     if (!ctx || !d_iq || !off || !len || nitems < 0 || !d_frames || !d_pdu || pdu_stride <= 0) return C8B_ERR_ARG;
     int r = need_lut(ctx);
@@ -491,10 +491,33 @@ int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* off, 
     for (int b = 0; b < nitems; b += cs) {
         const int e = b + cs < nitems ? b + cs : nitems;
         r = run_chunk(ctx, (const float2*)d_iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, d_frames, d_pdu,
-                      pdu_stride, 0);
+                      pdu_stride, 0, (const float2*)d_iq1);
         if (r) return r;
     }
     join_viterbi(ctx);
+    return C8B_OK;
+}
+
+int c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* d_frames,
+                           uint8_t* d_pdu, int64_t pdu_stride)
+{
+    return rx_batch_dev_async2(ctx, d_iq, nullptr, off, len, nitems, d_frames, d_pdu, pdu_stride);
+}
+
+int c8b_rx_batch2_dev(c8b_ctx* ctx, const float* d_iq0, const float* d_iq1, const int64_t* off, const int32_t* len, int nitems,
+                      c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride)
+{
+    if (!ctx || !d_iq1 || !frames || !pdu || nitems < 0 || pdu_stride <= 0) return C8B_ERR_ARG;
+    if (nitems == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nsl = (size_t)nitems * (ctx->cfg.max_frames > 0 ? ctx->cfg.max_frames : 1);
+    EN(frames, nsl * sizeof(c8b_frame));
+    EN(pdu, nsl * pdu_stride);
+    int r = rx_batch_dev_async2(ctx, d_iq0, d_iq1, off, len, nitems, (c8b_frame*)ctx->frames.p, (uint8_t*)ctx->pdu.p, pdu_stride);
+    if (r) return r;
+    CK(cudaMemcpyAsync(frames, ctx->frames.p, nsl * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(pdu, ctx->pdu.p, nsl * pdu_stride, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
 }
 

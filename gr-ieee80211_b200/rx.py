@@ -194,6 +194,17 @@ class Receiver:
                  "c8b_rx_batch_dev")
         return frames, pdu.reshape(ns, pdu_stride)
 
+    def rx_batch2_dev(self, d_iq0_ptr, d_iq1_ptr, off, length, pdu_stride=4400):
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        n, ns = off.size, off.size * self.max_frames
+        frames = np.zeros(ns, FRAME_DTYPE)
+        pdu = np.zeros(ns * pdu_stride, np.uint8)
+        _producer_sync()
+        self._ck(self.L.c8b_rx_batch2_dev(self.h, C.c_void_p(d_iq0_ptr), C.c_void_p(d_iq1_ptr), ptr(off), ptr(length), n, ptr(frames), ptr(pdu),
+                                          pdu_stride), "c8b_rx_batch2_dev")
+        return frames, pdu.reshape(ns, pdu_stride)
+
     def rx_batch_dev_async(self, d_iq_ptr, off, length, d_frames_ptr, d_pdu_ptr, pdu_stride=4400):
         off = np.ascontiguousarray(off, np.int64)
         length = np.ascontiguousarray(length, np.int32)

@@ -156,6 +156,9 @@ int  c8b_rx_batch2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const i
  * nitems*pdu_stride bytes); nothing is copied back and the call does not synchronise. */
 int  c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* h_off, const int32_t* h_len, int nitems,
                             c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride);
+/* 2x2 with both antennas resident in device memory (same item table for both), results to host buffers */
+int  c8b_rx_batch2_dev(c8b_ctx* ctx, const float* d_iq0, const float* d_iq1, const int64_t* h_off, const int32_t* h_len, int nitems,
+                       c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
 int  c8b_sync(c8b_ctx* ctx);                         /* wait for the ctx stream                    */
 
 /* ---- live stream: what the gr::block shells' general_work calls feed ------------------------------

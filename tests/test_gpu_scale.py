@@ -109,7 +109,9 @@ def test_config4_ht_2x2_mcs8_15_50k_frames():
     ha, hb = a.cpu().numpy(), b.cpu().numpy()
     rx = pkg.Receiver(device=0, chunk_items=8192)
     fr, pdu = rx.rx_batch2(ha, hb, off, ln, pdu_stride=640)
+    frd, pdud = rx.rx_batch2_dev(a.data_ptr(), b.data_ptr(), off, ln, pdu_stride=640)      # same capture, device resident
     rx.close()
+    assert frd.tobytes() == fr.tobytes() and np.array_equal(pdud, pdu)
     mp = bytes(g["mpdu"])
     good = _check(pkg, fr, pdu, kind, [1] * 8, list(range(8, 16)), [mp] * 8, 0.995, "config 4")
     _oracle_agrees(fr, pdu, good, lambda i: (ha[off[i]:off[i] + ln[i]], hb[off[i]:off[i] + ln[i]]), two=True)
