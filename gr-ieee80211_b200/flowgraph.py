@@ -211,7 +211,7 @@ class rx_top_block:
             self.rx.stream_begin(self.nant, window)
             self._streaming = True
         fr, base, pdu = self.rx.stream_push(np.asarray(x0, np.complex64), None if x1 is None else np.asarray(x1, np.complex64),
-                                            flush=flush, frames_cap=max(self.max_frames, 64))
+                                            flush=flush, frames_cap=max(self.max_frames, 64) + len(x0) // 320)    # a frame is at least 400 samples
         for k in range(fr.size):
             self._publish(fr[k], None, pdu[k], base[k])
         if flush:

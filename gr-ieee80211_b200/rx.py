@@ -125,12 +125,14 @@ class Receiver:
         self._ck(self.L.c8b_stream_begin(self.h, nant, window), "c8b_stream_begin")
         self._stream_nant = nant
 
-    def stream_push(self, iq0, iq1=None, flush=False, frames_cap=4096, pdu_stride=4400):
+    def stream_push(self, iq0, iq1=None, flush=False, frames_cap=None, pdu_stride=4400):
         """append samples; returns (frames, base, pdu): the frames that became decidable, the absolute stream index
         their trig_idx / sync_idx are relative to, and their PDU records"""
         a = _c2f(iq0)
         b = _c2f(iq1) if iq1 is not None else None
         n = a.size // 2
+        if frames_cap is None:
+            frames_cap = n // 400 + 4 * self.max_frames + 64     # more than one push can release (see the header)
         frames = np.zeros(frames_cap, FRAME_DTYPE)
         base = np.zeros(frames_cap, np.int64)
         pdu = np.zeros(frames_cap * pdu_stride, np.uint8)

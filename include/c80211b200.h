@@ -171,7 +171,9 @@ int  c8b_sync(c8b_ctx* ctx);                         /* wait for the ctx stream 
  * frame_base[k], PDU records at pdu + k*pdu_stride.  flush != 0 ends the stream: what is left is processed with
  * the whole-capture (c8b_rx_batch) semantics, truncated frames included.  The frames and PDUs of a stream are the
  * ones one c8b_rx_batch call over the whole capture (one item) returns, independent of the push sizes.
- * A window that fills up without any decidable point is dropped and counted (c8b_stream_state). */
+ * A window that fills up without any decidable point is dropped and counted (c8b_stream_state).  frames_cap must cover what
+ * one push can release (a frame is at least 400 samples: n / 400 + max_frames is always enough); C8B_ERR_FULL means frames
+ * were lost and the session has to be restarted with c8b_stream_begin. */
 int  c8b_stream_begin(c8b_ctx* ctx, int nant, int64_t window_samples /* 0: 4 Mi samples */);
 int  c8b_stream_push(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1 /* NULL for nant 1 */, int64_t n, int flush,
                      c8b_frame* frames, int frames_cap, int* nframes, int64_t* frame_base, uint8_t* pdu, int64_t pdu_stride);
