@@ -78,6 +78,7 @@ SYMBOLS = [
     ("c8b_timing_read", _i, [_vp, _vp, _vp, _i]),
     ("c8b_presiso", _i, [_vp, _vp, _i64, _vp, _vp]),
     ("c8b_trigger", _i, [_vp, _vp, _i64, _vp]),
+    ("c8b_trigger_events", _i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     ("c8b_detect", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     ("c8b_demod", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64]),
     ("c8b_demod2", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64]),

@@ -56,3 +56,5 @@ size_t c8b_detect_multi_scratch(int nitems, int maxCand);
 void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                              int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
                              float2* chan, c8b_scan* scans, void* scratch, int maxCand, cudaStream_t st);
+void c8b_launch_trigger_events(const float* d_preac, int n, const int64_t* d_off, const int32_t* d_len, uint32_t* d_mask, const c8b_scan* d_scan,
+                               void* scratch, int maxCand, int32_t* d_out, cudaStream_t st);

@@ -673,6 +673,36 @@ static int stage_items(c8b_ctx* ctx, const float* h_iq, const int64_t* off, cons
     return C8B_OK;
 }
 
+int c8b_trigger_events(c8b_ctx* ctx, const float* h_preac, int64_t n, int from, int32_t* h_events, int cap, int* count, int* safe_end)
+{
+    if (!ctx || !h_preac || n <= 0 || n > 0x7ffffff0 || from < 0 || !h_events || cap <= 0 || !count) return C8B_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    EN(preac, (size_t)(n + 64) * sizeof(float));
+    EN(mask, (size_t)((n + 31) / 32 + 2) * sizeof(uint32_t));
+    EN(cand, c8b_detect_multi_scratch(1, cap));
+    EN(scan, sizeof(c8b_scan));
+    EN(trig, (size_t)(4 + 4 * cap) * sizeof(int32_t));
+    const int64_t off = 0;
+    const int32_t len = (int32_t)n;
+    int r = upload_items(ctx, &off, &len, 1);
+    if (r) return r;
+    c8b_scan sc;
+    memset(&sc, 0, sizeof sc);
+    sc.from = from;
+    CK(cudaMemcpyAsync(ctx->scan.p, &sc, sizeof sc, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->preac.p, h_preac, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->st));
+    c8b_launch_trigger_events((const float*)ctx->preac.p, (int)n, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, (uint32_t*)ctx->mask.p,
+                              (const c8b_scan*)ctx->scan.p, ctx->cand.p, cap, (int32_t*)ctx->trig.p, ctx->st);
+    CK(cudaGetLastError());
+    std::vector<int32_t> out((size_t)4 + 4 * cap);
+    CK(cudaMemcpyAsync(out.data(), ctx->trig.p, out.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    *count = out[0];
+    if (safe_end) *safe_end = out[1];
+    for (int c = 0; c < out[0] && c < cap; c++) for (int k = 0; k < 4; k++) h_events[4 * c + k] = out[4 + 4 * c + k];
+    return out[2] ? C8B_ERR_FULL : C8B_OK;
+}
+
 int c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, float* h_chan)
 {
     if (!ctx || !h_iq || !off || !len || nitems < 0 || !frames) return C8B_ERR_ARG;

@@ -802,6 +802,35 @@ void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_
                                                             frames, chan);
 }
 
+// staged entry point for the trigger scan alone (c8b_trigger_events): bitmap of a given preac array, then k_trig_scan
+namespace {
+__global__ void k_preac_mask(const float* __restrict__ preac, int n, uint32_t* __restrict__ mask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m = __ballot_sync(FULL, i < n && preac[i < n ? i : 0] > 0.3f);
+    if ((threadIdx.x & 31) == 0 && i < n) mask[i >> 5] = m;
+}
+__global__ void k_cand_export(const Cand* __restrict__ cands, const CandHead* __restrict__ heads, int cap, int32_t* __restrict__ out)
+{
+    const int n = heads[0].n;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = n; out[1] = heads[0].safeEnd; out[2] = heads[0].overflow; out[3] = heads[0].nTrig; }
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n && c < cap; c += gridDim.x * blockDim.x) {
+        out[4 + 4 * c + 0] = cands[c].trig; out[4 + 4 * c + 1] = cands[c].latch; out[4 + 4 * c + 2] = cands[c].safe; out[4 + 4 * c + 3] = cands[c].stall;
+    }
+}
+}  // namespace
+
+// d_item: {int64 off = 0; int32 len = n} already on the device; out = 4 header ints + 4 ints per event
+void c8b_launch_trigger_events(const float* d_preac, int n, const int64_t* d_off, const int32_t* d_len, uint32_t* d_mask, const c8b_scan* d_scan,
+                               void* scratch, int maxCand, int32_t* d_out, cudaStream_t st)
+{
+    CandHead* heads = reinterpret_cast<CandHead*>(scratch);
+    Cand* cands = reinterpret_cast<Cand*>(reinterpret_cast<char*>(scratch) + 256);
+    k_preac_mask<<<(n + 255) / 256, 256, 0, st>>>(d_preac, n, d_mask);
+    k_trig_scan<<<1, 32, 0, st>>>(d_len, 1, 0, d_off, d_preac, d_mask, (n + 31) / 32 + 1, d_scan, cands, heads, maxCand);
+    k_cand_export<<<4, 256, 0, st>>>(cands, heads, maxCand, d_out);
+}
+
 size_t c8b_detect_multi_scratch(int nitems, int maxCand) { return (size_t)nitems * maxCand * sizeof(Cand) + (size_t)nitems * sizeof(CandHead) + 256; }
 
 // few long items with many frames each: trigger scan -> per-trigger sync / signal in parallel -> accept rules

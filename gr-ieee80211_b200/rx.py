@@ -229,6 +229,14 @@ class Receiver:
         self._ck(self.L.c8b_trigger(self.h, ptr(preac), preac.size, ptr(out)), "c8b_trigger")
         return out
 
+    def trigger_events(self, preac, start=0, cap=4096):
+        """the warp trigger scan on a preac array: (events [n, 4] = trig, latch, safe, stall; safe_end)"""
+        p = np.ascontiguousarray(preac, np.float32)
+        ev = np.zeros((cap, 4), np.int32)
+        cnt, se = C.c_int(0), C.c_int(0)
+        self._ck(self.L.c8b_trigger_events(self.h, ptr(p), p.size, start, ptr(ev), cap, C.byref(cnt), C.byref(se)), "c8b_trigger_events")
+        return ev[:cnt.value].copy(), se.value
+
     def detect(self, iq, off, length):
         iqf = _c2f(iq)
         off = np.ascontiguousarray(off, np.int64)

@@ -224,6 +224,12 @@ int  c8b_tx_random_psdu_dev(c8b_ctx* ctx, uint8_t* d_psdu, int64_t psdu_bytes, c
 int  c8b_presiso(c8b_ctx* ctx, const float* h_iq, int64_t n, float* h_preac, float* h_preconj);
 /* trigger FSM over one array from reset state: out[n] flag bytes (0x01 trigger, 0x02 latch) */
 int  c8b_trigger(c8b_ctx* ctx, const float* h_preac, int64_t n, uint8_t* h_out);
+/* the trigger scan as the batched path runs it (bitmap words, bulk updates, skipped idle stretches) on a given preac array:
+ * events[k] = {index of the 0x01 flag, index latched by the last honoured 0x02 flag (-1: none), restart point before its
+ * plateau, 1 if fewer than 240 samples follow (the scan stops there)}.  Only triggers that survive sync's 111-sample
+ * hold-off (lib/sync_impl.cc:141-146) are reported; the scan starts at sample `from`.  safe_end: restart point at the end. */
+int  c8b_trigger_events(c8b_ctx* ctx, const float* h_preac, int64_t n, int from, int32_t* h_events /* [cap][4] */, int cap, int* count,
+                        int* safe_end);
 /* detect = presiso + trigger + sync + signal on items; fills status..nsamp of frames[i] and
  * h_chan (64 complex per item: the legacy channel, tag "chan" lib/signal_impl.cc:146-152; may be NULL) */
 int  c8b_detect(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems,
