@@ -6,5 +6,6 @@ from . import _cabi
 from . import parallel  # noqa: F401
 from . import synth  # noqa: F401
 from . import flowgraph  # noqa: F401
+from . import blocks  # noqa: F401
 from .rx import Receiver, lut_blob  # noqa: F401
 from ._cabi import C8bError, FRAME_DTYPE, TXFRAME_DTYPE, K_NAMES  # noqa: F401

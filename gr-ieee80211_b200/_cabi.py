@@ -33,6 +33,11 @@ FRAME_DTYPE = np.dtype([(n, {C.c_int32: "<i4", C.c_float: "<f4", C.c_int64: "<i8
 assert FRAME_DTYPE.itemsize == C.sizeof(C8bFrame)
 
 
+# c8b_tag: one stream tag group of the per-block entry points (c8b_blk_work)
+TAG_DTYPE = np.dtype([("port", "<i4"), ("idx", "<i4"), ("nvec", "<i4"), ("seq", "<i4"), ("f", FRAME_DTYPE), ("vec", "<f4", (256,))], align=True)
+assert TAG_DTYPE.itemsize == 16 + C.sizeof(C8bFrame) + 1024 and TAG_DTYPE.fields["f"][1] == 16
+
+
 class C8bTxFrame(C.Structure):
     _fields_ = [("format", C.c_int32), ("mcs", C.c_int32), ("psdu_off", C.c_int64), ("psdu_len", C.c_int32), ("cfo_hz", C.c_float),
                 ("out_off", C.c_int64)]
@@ -83,6 +88,12 @@ SYMBOLS = [
     ("c8b_demod", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64]),
     ("c8b_demod2", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64]),
     ("c8b_decode", _i, [_vp, _vp, _i64, _vp, _i, _vp, _i64, _vp, _i64]),
+    ("c8b_blk_create", _i, [C.POINTER(C8bCfg), _i, C.POINTER(_vp)]),
+    ("c8b_blk_destroy", None, [_vp]),
+    ("c8b_blk_last_error", C.c_char_p, [_vp]),
+    ("c8b_blk_ports", _i, [_i, _vp, _vp, _vp, _vp]),
+    ("c8b_blk_forecast", _i, [_i, _i]),
+    ("c8b_blk_work", _i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
 ]
 
 _lib = None

@@ -58,3 +58,5 @@ void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t
                              float2* chan, c8b_scan* scans, void* scratch, int maxCand, cudaStream_t st);
 void c8b_launch_trigger_events(const float* d_preac, int n, const int64_t* d_off, const int32_t* d_len, uint32_t* d_mask, const c8b_scan* d_scan,
                                void* scratch, int maxCand, int32_t* d_out, cudaStream_t st);
+// the device copy of the table blob of a context (null until c8b_lut_load); used by blocks.cu
+extern "C" const c8b_lut* c8b_ctx_lut(const c8b_ctx* ctx);

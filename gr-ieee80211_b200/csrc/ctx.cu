@@ -234,6 +234,8 @@ int c8b_lut_load_dev(c8b_ctx* ctx, const void* d_blob, size_t n)
     return C8B_OK;
 }
 
+const c8b_lut* c8b_ctx_lut(const c8b_ctx* ctx) { return ctx && ctx->lutLoaded ? ctx->d_lut : nullptr; }
+
 static int need_lut(c8b_ctx* ctx)
 {
     if (!ctx->lutLoaded) { ctx->err = "LUT not loaded: call c8b_lut_load first"; return C8B_ERR_LUT; }

@@ -179,6 +179,61 @@ int  c8b_stream_push(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1 /* NUL
                      c8b_frame* frames, int frames_cap, int* nframes, int64_t* frame_base, uint8_t* pdu, int64_t pdu_stride);
 int  c8b_stream_state(const c8b_ctx* ctx, int64_t* base, int64_t* fill, int64_t* overruns);
 
+/* ---- the seven receive blocks, one scheduler call at a time ------------------------------------------
+ * What the gr::block shells of gr/lib/<block>_impl.cc call from general_work(): same stream signatures, same consume /
+ * produce accounting at the stream level, same tags and messages as the reference's blocks
+ *   trigger  lib/trigger_impl.cc:59-117   in {float preac}                       out {u8 flags}
+ *   sync     lib/sync_impl.cc:61-153      in {u8 trigger, c64 preconj, c64 sig}  out {u8 sync}      tag rad/snr/rssi
+ *   signal   lib/signal_impl.cc:62-206    in {u8 sync, c64 sig}                  out {c64}          tag cfo/snr/rssi/seq/mcs/len/nsamp/chan
+ *   signal2  lib/signal2_impl.cc:63-212   in {u8 sync, c64 sig0, c64 sig1}       out {c64, c64}     (same tag, on port 0)
+ *   demod    lib/demod_impl.cc:59-342     in {c64}                               out {float LLR}    tag cfo/snr/rssi/format/mcs/len/cr/ampdu/trellis/total/sssnr0[/mu2x1chan]
+ *   demod2   lib/demod2_impl.cc:58-348    in {c64, c64}                          out {float LLR}    (+ sssnr1)
+ *   decode   lib/decode_impl.cc:60-162    in {float LLR}                         message port "out"
+ * so examples/rx.grc / rx2.grc connect them unchanged.  The state machines (which call consumes what) run on the host
+ * inside the library; every piece of arithmetic -- the trigger FSM over the samples, LTF autocorrelation and CFO, L-SIG
+ * FFTs / Viterbi, the CFO-rotated copy, header fields, per-symbol demod, Viterbi decode / CRC -- is a kernel launch on the
+ * block's own context.  One block = one c8b_blk = one context: safe under GNU Radio's thread-per-block scheduler. */
+#define C8B_BLK_TRIGGER 0
+#define C8B_BLK_SYNC 1
+#define C8B_BLK_SIGNAL 2
+#define C8B_BLK_SIGNAL2 3
+#define C8B_BLK_DEMOD 4
+#define C8B_BLK_DEMOD2 5
+#define C8B_BLK_DECODE 6
+
+/* One stream tag group: the reference attaches ONE pmt dict, split into one tag per key, at one item
+ * (lib/sync_impl.cc:124-136, lib/signal_impl.cc:135-152, lib/demod_impl.cc:224-263).  The values travel in `f`
+ * (sync: rad snr rssi; signal: cfo_hz snr rssi l_mcs l_len nsamp + seq + vec = chan[64]; demod: cfo_hz snr rssi format mcs
+ * len cr ampdu trellis total sssnr0 sssnr1 (+ vec = mu2x1chan[128] for an NDP)). */
+typedef struct c8b_tag {
+    int32_t port;          /* stream port the tag sits on (always 0 in this chain)                          */
+    int32_t idx;           /* item index relative to the first item of this call's buffer on that port      */
+    int32_t nvec;          /* complex values in vec: 64 (chan), 128 (mu2x1chan) or 0                        */
+    int32_t seq;           /* signal's packet counter (tag "seq", wraps at 1e9)                             */
+    c8b_frame f;
+    float   vec[256];
+} c8b_tag;
+
+typedef struct c8b_blk c8b_blk;
+/* cfg->mupos / mugid = demod::make(mupos, mugid); the block creates its own context and loads the tables */
+int  c8b_blk_create(const c8b_cfg* cfg, int kind, c8b_blk** out);
+void c8b_blk_destroy(c8b_blk* b);
+const char* c8b_blk_last_error(const c8b_blk* b);
+/* number of input / output stream ports of a block kind (decode: 1 / 0) and their item sizes in bytes */
+int  c8b_blk_ports(int kind, int* nin, int* nout, int in_item_bytes[3], int out_item_bytes[2]);
+/* forecast(): items required on every input port for noutput output items (1:1 except decode: noutput + 160) */
+int  c8b_blk_forecast(int kind, int noutput);
+/* general_work(): in[p] / ninput[p] = items available on input port p, out[q] = room for noutput items on output port q;
+ * in_tags = the tags on input port 0 inside [0, ninput[0]) with idx relative to in[0].  Returns through *consumed what
+ * consume_each() gets, through *produced the return value of general_work, the tags to attach at
+ * nitems_written(0) + idx, and for decode the concatenated PDU records published on port "out"
+ * ([fmt][len lo][len hi][MPDU][mcs], n = len + 4; NDP report [20][0][4][128 x (re,im) f32], n = 1027).  decode has no
+ * output stream: when out_tags is given it receives one record (port = idx = -1) per frame whose Viterbi pass finished,
+ * f.npdu telling how many MPDUs passed the CRC (what decode(ifdebug) prints, lib/decode_impl.cc:377-411,456-509). */
+int  c8b_blk_work(c8b_blk* b, int noutput, const int* ninput, const void* const* in, void* const* out,
+                  const c8b_tag* in_tags, int n_in_tags, int* consumed, int* produced,
+                  c8b_tag* out_tags, int out_tag_cap, int* n_out_tags, uint8_t* msg, int msg_cap, int* msg_bytes);
+
 /* per-kernel device time accumulated since the last reset (CUDA events on the ctx stream) */
 #define C8B_K_PRESISO 0
 #define C8B_K_DETECT 1

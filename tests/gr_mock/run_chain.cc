@@ -1,0 +1,173 @@
+// TEST INFRASTRUCTURE: plays the GNU Radio scheduler for the compiled block shells (gr-ieee80211_b200/gr/lib/
+// rx_blocks_impl.cc, built against the miniature runtime of tests/gr_mock/include): wires trigger -> sync -> signal[2] ->
+// demod[2] -> decode like examples/rx.grc / rx2.grc, feeds presiso's outputs and the capture from files, calls
+// general_work() with pseudo-random sizes until nothing moves, and dumps the published messages and all stream tags.
+//   run_chain NANT MUPOS MUGID SEED MAXCALL IFDEBUG INDIR OUTFILE
+// INDIR holds preac.f32, preconj.c64, sig.c64 [, sig1.c64]; OUTFILE gets lines
+//   MSG <hex bytes>          one per message on decode's port "out", in order
+//   TAG <block> <offset> <key> <value>
+#include <gnuradio/ieee80211/decode.h>
+#include <gnuradio/ieee80211/demod.h>
+#include <gnuradio/ieee80211/demod2.h>
+#include <gnuradio/ieee80211/signal.h>
+#include <gnuradio/ieee80211/signal2.h>
+#include <gnuradio/ieee80211/sync.h>
+#include <gnuradio/ieee80211/trigger.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+using gr::mock::edge;
+
+static std::vector<char> slurp(const std::string& p)
+{
+    std::ifstream f(p, std::ios::binary);
+    if (!f) { std::cerr << "cannot read " << p << std::endl; exit(2); }
+    return std::vector<char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+static uint32_t rng_state = 1;
+static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
+
+struct Graph {
+    std::vector<std::unique_ptr<edge>> edges;
+    edge* make_edge(int item) { edges.emplace_back(new edge); edges.back()->item = item; return edges.back().get(); }
+    void connect(gr::block& a, int pa, gr::block& b, int pb)
+    {
+        edge* e = make_edge(a.output_signature()->sizeof_stream_item(pa));
+        a.mock_out.at(pa).push_back(e);
+        b.mock_in.at(pb) = e;
+    }
+    edge* source(const std::vector<char>& data, int item, gr::block& b, int pb)
+    {
+        edge* e = make_edge(item);
+        e->data = data; e->nwritten = data.size() / item;
+        b.mock_in.at(pb) = e;
+        return e;
+    }
+};
+
+// one general_work() call with the sizes a scheduler could pick; returns whether anything moved
+static bool call(gr::block& b, int maxCall, bool big)
+{
+    const int nin = (int)b.mock_in.size(), nout = (int)b.mock_out.size();
+    int cap = big ? maxCall : 1 + (int)(rnd() % (uint32_t)maxCall);
+    size_t minAvail = (size_t)-1;
+    for (edge* e : b.mock_in) minAvail = std::min(minAvail, e->avail());
+    int noutput = cap;
+    gr_vector_int req(nin), ninput(nin);
+    if (nout > 0) {
+        noutput = (int)std::min<size_t>((size_t)cap, minAvail);
+        if (noutput == 0 && (b.name() == "demod" || b.name() == "demod2")) noutput = cap;   // output space alone wakes a block too
+    }
+    b.forecast(noutput, req);
+    const int extra = big ? 0 : (int)(rnd() % 64u);
+    for (int k = 0; k < nin; k++) ninput[k] = (int)std::min<size_t>(b.mock_in[k]->avail(), (size_t)std::max(req[k], noutput) + extra);
+    int most = 0;
+    for (int v : ninput) most = std::max(most, v);
+    if (noutput <= 0 && most <= 0) return false;
+    gr_vector_const_void_star in(nin);
+    for (int k = 0; k < nin; k++) in[k] = b.mock_in[k]->data.data();
+    std::vector<std::vector<char>> obuf(nout);
+    gr_vector_void_star out(nout);
+    for (int k = 0; k < nout; k++) {
+        obuf[k].assign((size_t)std::max(noutput, 1) * b.output_signature()->sizeof_stream_item(k), 0);
+        out[k] = obuf[k].data();
+    }
+    b.mock_consumed = 0;
+    const size_t tagsBefore = b.mock_tags_added.size(), msgBefore = b.mock_messages.size();
+    const int produced = b.general_work(noutput, ninput, in, out);
+    if (produced < 0 || produced > noutput || b.mock_consumed < 0) { std::cerr << b.name() << ": bad accounting" << std::endl; exit(3); }
+    for (int k = 0; k < nin; k++) {
+        edge* e = b.mock_in[k];
+        if ((size_t)b.mock_consumed > e->avail()) { std::cerr << b.name() << ": consumed more than available" << std::endl; exit(3); }
+        e->data.erase(e->data.begin(), e->data.begin() + (size_t)b.mock_consumed * e->item);
+        e->nread += b.mock_consumed;
+        std::vector<gr::tag_t> keep;
+        for (auto& t : e->tags) if (t.offset >= e->nread) keep.push_back(t);
+        e->tags.swap(keep);
+    }
+    for (int k = 0; k < nout; k++) {
+        const size_t bytes = (size_t)produced * b.output_signature()->sizeof_stream_item(k);
+        for (edge* e : b.mock_out[k]) { e->data.insert(e->data.end(), obuf[k].begin(), obuf[k].begin() + bytes); e->nwritten += produced; }
+        b.mock_written[k] += produced;
+    }
+    return b.mock_consumed > 0 || produced > 0 || b.mock_tags_added.size() != tagsBefore || b.mock_messages.size() != msgBefore;
+}
+
+static std::string show(const pmt::pmt_t& v)
+{
+    char buf[64];
+    if (auto p = dynamic_cast<const pmt::p_long*>(v.get())) return std::to_string(p->v);
+    if (auto p = dynamic_cast<const pmt::p_real*>(v.get())) { snprintf(buf, sizeof buf, "%.9g", p->v); return buf; }
+    if (auto p = dynamic_cast<const pmt::p_c32v*>(v.get())) {
+        double s = 0;
+        for (auto& c : p->v) s += std::abs(c);
+        snprintf(buf, sizeof buf, "c32[%zu]:%.6g", p->v.size(), s);
+        return buf;
+    }
+    return "?";
+}
+
+int main(int argc, char** argv)
+{
+    if (argc != 9) { std::cerr << "usage: run_chain NANT MUPOS MUGID SEED MAXCALL IFDEBUG INDIR OUTFILE" << std::endl; return 2; }
+    const int nant = atoi(argv[1]), mupos = atoi(argv[2]), mugid = atoi(argv[3]), maxCall = atoi(argv[5]);
+    rng_state = (uint32_t)atoi(argv[4]) * 2654435761u + 1u;
+    const bool dbg = atoi(argv[6]) != 0;
+    const std::string dir = argv[7];
+    using namespace gr::ieee80211;
+    std::shared_ptr<gr::block> trig, syn, sig, dem, dec;
+    try {
+        trig = trigger::make();
+        syn = sync::make();
+        if (nant == 2) { sig = signal2::make(); dem = demod2::make(); }
+        else { sig = signal::make(); dem = demod::make(mupos, mugid); }
+        dec = decode::make(dbg);
+    } catch (const std::exception& e) {
+        std::cerr << "make() failed: " << e.what() << std::endl;
+        return 4;
+    }
+    Graph g;
+    const std::vector<char> preac = slurp(dir + "/preac.f32"), preconj = slurp(dir + "/preconj.c64"), s0 = slurp(dir + "/sig.c64");
+    g.source(preac, 4, *trig, 0);
+    g.connect(*trig, 0, *syn, 0);
+    g.source(preconj, 8, *syn, 1);
+    g.source(s0, 8, *syn, 2);
+    g.connect(*syn, 0, *sig, 0);
+    g.source(s0, 8, *sig, 1);
+    if (nant == 2) g.source(slurp(dir + "/sig1.c64"), 8, *sig, 2);
+    for (int a = 0; a < nant; a++) g.connect(*sig, a, *dem, a);
+    g.connect(*dem, 0, *dec, 0);
+
+    gr::block* order[5] = { trig.get(), syn.get(), sig.get(), dem.get(), dec.get() };
+    for (int idle = 0; idle < 3;) {
+        bool moved = false;
+        for (gr::block* b : order)
+            for (int r = 1 + (int)(rnd() % 3u); r > 0; r--) moved |= call(*b, maxCall, idle > 0);
+        idle = moved ? 0 : idle + 1;
+    }
+
+    FILE* f = fopen(argv[8], "w");
+    if (!f) return 2;
+    for (auto& m : dec->mock_messages) {
+        const pmt::pmt_t blob = pmt::cdr(m.second);
+        const uint8_t* p = (const uint8_t*)pmt::blob_data(blob);
+        const size_t n = pmt::blob_length(blob);
+        if ((size_t)pmt::to_long(pmt::dict_ref(pmt::car(m.second), pmt::mp("len"), pmt::from_long(-1))) != n) { std::cerr << "len meta" << std::endl; return 3; }
+        fprintf(f, "MSG ");
+        for (size_t k = 0; k < n; k++) fprintf(f, "%02x", p[k]);
+        fprintf(f, "\n");
+    }
+    for (gr::block* b : order)
+        for (auto& t : b->mock_tags_added)
+            fprintf(f, "TAG %s %llu %s %s\n", b->name().c_str(), (unsigned long long)t.offset, pmt::symbol_to_string(t.key).c_str(), show(t.value).c_str());
+    fclose(f);
+    return 0;
+}

@@ -69,3 +69,90 @@ void hs_header2(const float* iq0_item, const float* iq1_item, c8b_frame* f, cons
 }
 
 }
+
+// ---- the block state machines of gr-ieee80211_b200/csrc/blocks.h over a host backend ---------------------------------
+// Per-frame arithmetic = the host build of phy_serial.cuh (the same routines the product's kernels run); the per-symbol
+// demod and the Viterbi decode have no host build, so the backend returns zero soft bits and a placeholder PDU record
+// [format][len lo][len hi][len x 0xA5][mcs]: this checks WHAT each scheduler call consumes, produces and tags, not bytes.
+#include "../../gr-ieee80211_b200/csrc/blocks.h"
+
+namespace {
+struct HostBlk {
+    int kind = 0, mupos = 0;
+    TrigState ts;
+    c8b_blocks::SyncState sy;
+    c8b_blocks::SignalState sg;
+    c8b_blocks::DemodState dm;
+    c8b_blocks::DecodeState dc;
+
+    int trigger(const float* in, int n, uint8_t* out) { for (int i = 0; i < n; i++) out[i] = trig_step(ts, in[i]); return 0; }
+    int sync_at(const float* sig, const float conj[2], c8b_blocks::SyncRes* r)
+    {
+        const SyncOut o = c8b::sync_at((const cf*)sig, mk(conj[0], conj[1]));
+        r->ok = o.ok; r->mIndex = o.mIndex; r->rad = o.rad; r->snr = o.snr; r->rssi = o.rssi;
+        return 0;
+    }
+    int signal_at(const float* in, float rad, c8b_blocks::SignalRes* r)
+    {
+        cf h[64];
+        r->mcs = r->len = r->nsamp = 0;
+        r->ok = c8b::signal_at(lut(), (const cf*)in, rad, h, &r->mcs, &r->len, &r->nsamp);
+        memcpy(r->chan, h, sizeof(h));
+        return 0;
+    }
+    int cfo_copy(const float* in0, const float* in1, float* out0, float* out1, int n, int copied, float rad)
+    {
+        for (int i = 0; i < n; i++) {
+            const cf w = cis(fmul((float)(copied + i + 224), rad));
+            ((cf*)out0)[i] = cmul(((const cf*)in0)[i], w);
+            if (in1) ((cf*)out1)[i] = cmul(((const cf*)in1)[i], w);
+        }
+        return 0;
+    }
+    int demod(int nant, const float* iq0, const float* iq1, int n, c8b_frame* f, const float* chan, std::vector<float>* llr)
+    {
+        float hinv[128], w2[528];
+        if (nant == 2) hs_header2(iq0, iq1, f, chan, hinv, w2);
+        else hs_header(iq0, f, chan, mupos, hinv);
+        llr->assign((size_t)std::max(f->total, 1024), 0.f);
+        return 0;
+    }
+    int decode(c8b_frame* f, const float*, int, uint8_t* pdu, int cap)
+    {
+        const int n = f->len + 4;
+        if (n > cap) return C8B_ERR_ARG;
+        pdu[0] = (uint8_t)f->format; pdu[1] = (uint8_t)(f->len & 255); pdu[2] = (uint8_t)(f->len >> 8);
+        memset(pdu + 3, 0xA5, (size_t)f->len);
+        pdu[3 + f->len] = (uint8_t)f->mcs;
+        f->npdu = 1; f->pdu_bytes = n;
+        return 0;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+void* hs_blk_create(int kind, int mupos) { HostBlk* b = new HostBlk; b->kind = kind; b->mupos = mupos; trig_reset(b->ts); return b; }
+void hs_blk_destroy(void* b) { delete static_cast<HostBlk*>(b); }
+int hs_blk_work(void* hb, int noutput, const int* ninput, const void* const* in, void* const* out, const c8b_tag* in_tags, int n_in_tags,
+                int* consumed, int* produced, c8b_tag* out_tags, int out_tag_cap, int* n_out_tags, uint8_t* msg, int msg_cap, int* msg_bytes)
+{
+    HostBlk* b = static_cast<HostBlk*>(hb);
+    c8b_blocks::WorkIO io;
+    io.noutput = noutput; io.ninput = ninput; io.in = in; io.out = out; io.in_tags = in_tags; io.n_in_tags = n_in_tags;
+    io.out_tags = out_tags; io.out_tag_cap = out_tag_cap; io.msg = msg; io.msg_cap = msg_cap;
+    int rc;
+    switch (b->kind) {
+    case C8B_BLK_TRIGGER: rc = c8b_blocks::trigger_work(*b, io); break;
+    case C8B_BLK_SYNC:    rc = c8b_blocks::sync_work(*b, b->sy, io); break;
+    case C8B_BLK_SIGNAL:  rc = c8b_blocks::signal_work(*b, b->sg, 1, io); break;
+    case C8B_BLK_SIGNAL2: rc = c8b_blocks::signal_work(*b, b->sg, 2, io); break;
+    case C8B_BLK_DEMOD:   rc = c8b_blocks::demod_work(*b, b->dm, 1, io); break;
+    case C8B_BLK_DEMOD2:  rc = c8b_blocks::demod_work(*b, b->dm, 2, io); break;
+    default:              rc = c8b_blocks::decode_work(*b, b->dc, io); break;
+    }
+    *consumed = io.consumed; *produced = io.produced; *n_out_tags = io.n_out_tags; *msg_bytes = io.msg_bytes;
+    return rc;
+}
+
+}

@@ -31,3 +31,29 @@ def lib():
         L.hs_header2.argtypes = [f32p, f32p, C.c_void_p, f32p, f32p, f32p]
         _lib = L
     return _lib
+
+
+class HostBackend:
+    """Backend of gr-ieee80211_b200/blocks.py over the host build of the block state machines (hs_blk_*): the per-frame
+    arithmetic is the host build of phy_serial.cuh, soft bits are zeros and PDUs placeholders (see hostsim.cc)."""
+
+    def __init__(self):
+        self.L = lib()
+        vp, i = C.c_void_p, C.c_int
+        self.L.hs_blk_create.restype = vp
+        self.L.hs_blk_create.argtypes = [i, i]
+        self.L.hs_blk_destroy.argtypes = [vp]
+        self.L.hs_blk_work.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp]
+
+    def create(self, kind, mupos=0, mugid=0):
+        return C.c_void_p(self.L.hs_blk_create(kind, mupos))
+
+    def destroy(self, h):
+        self.L.hs_blk_destroy(h)
+
+    def forecast(self, kind, noutput):
+        return noutput + 160 if kind == 6 else noutput
+
+    def work(self, h, *args):
+        rc = self.L.hs_blk_work(h, *args)
+        assert rc == 0, rc

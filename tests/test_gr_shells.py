@@ -1,0 +1,107 @@
+"""The gr::block shells (gr-ieee80211_b200/gr/lib/rx_blocks_impl.cc) compiled against a miniature of the GNU Radio runtime
+(tests/gr_mock: gr::block / io_signature / pmt with GNU Radio 3.10's names, signatures and access levels -- and the
+reference's own public headers include/gnuradio/ieee80211/*.h when /root/reference is mounted) and driven by a mock
+scheduler (tests/gr_mock/run_chain.cc).  CPU: they build, link against the product library and refuse to run without a
+GPU.  GPU: the messages on decode's port and the stream tags equal the oracle's one-pass results."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from __graft_entry__ import ROOT, load_pkg
+
+MOCK = os.path.join(ROOT, "tests", "gr_mock")
+EXE = os.path.join(MOCK, "build", "run_chain")
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "gr-ieee80211_b200", "csrc")])
+    subprocess.check_call(["make", "-s", "-C", MOCK])
+    assert os.path.exists(EXE)
+
+
+def test_shells_build_and_fail_loudly_without_gpu(tmp_path):
+    _build()
+    pkg = load_pkg()
+    if pkg._cabi.lib().c8b_device_count() > 0:
+        return
+    r = subprocess.run([EXE, "1", "0", "0", "1", "4096", "0", str(tmp_path), str(tmp_path / "out.txt")], capture_output=True, text=True)
+    assert r.returncode == 4 and "no CPU path" in r.stderr          # make() throws: no GPU, no block
+
+
+def _run(tmp_path, nant, x, x1=None, mupos=0, mugid=0, seed=1, max_call=4096, debug=0):
+    pkg = load_pkg()
+    rx = pkg.Receiver(device=0)
+    preac, preconj = rx.presiso(x)
+    rx.close()
+    preac.tofile(tmp_path / "preac.f32")
+    preconj.astype(np.complex64).tofile(tmp_path / "preconj.c64")
+    x.astype(np.complex64).tofile(tmp_path / "sig.c64")
+    if x1 is not None:
+        x1.astype(np.complex64).tofile(tmp_path / "sig1.c64")
+    out = tmp_path / "out.txt"
+    r = subprocess.run([EXE, str(nant), str(mupos), str(mugid), str(seed), str(max_call), str(debug), str(tmp_path), str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    msgs, tags = [], {}
+    for line in open(out):
+        w = line.split()
+        if w[0] == "MSG":
+            msgs.append(bytes.fromhex(w[1]))
+        else:
+            tags.setdefault((w[1], int(w[2])), {})[w[3]] = w[4]
+    return msgs, tags, r.stdout
+
+
+def _noisy(x, snr, seed):
+    rng = np.random.default_rng(seed)
+    s = 0.1875 / np.sqrt(2 * 10 ** (snr / 10))
+    return (x + s * (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size))).astype(np.complex64)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_call", [4096, 900])
+def test_shells_siso_equal_oracle(golden, tmp_path, max_call):
+    _build()
+    pkg = load_pkg()
+    g = golden["frames_siso"]
+    x = _noisy(g["iq"], 28.0, 21)
+    fo, _, po = ol.rx_item(x, max_frames=40)
+    want = pkg.blocks.split_messages(bytes(po))
+    msgs, tags, stdout = _run(tmp_path, 1, x, seed=max_call, max_call=max_call, debug=1)
+    assert msgs == want and len(want) >= 30
+    ok = fo[(fo["status"] != 9) & (fo["nsamp"] > 0)]
+    soff = doff = 0
+    for f in ok:
+        t = tags[("sync", int(f["sync_idx"]))]
+        assert set(t) == {"rad", "snr", "rssi"} and abs(float(t["rad"]) - float(f["rad"])) <= 1e-6
+        t = tags[("signal", soff)]
+        assert set(t) == {"cfo", "snr", "rssi", "seq", "mcs", "len", "nsamp", "chan"}
+        assert (int(t["mcs"]), int(t["len"]), int(t["nsamp"])) == (int(f["l_mcs"]), int(f["l_len"]), int(f["nsamp"])) and t["chan"].startswith("c32[64]")
+        soff += int(f["nsamp"]) + 320
+        if f["status"] == 0:
+            t = tags[("demod", doff)]
+            keys = {"cfo", "snr", "rssi", "format", "mcs", "len", "cr", "ampdu", "trellis", "total"} | ({"sssnr0"} if f["format"] == 2 else set())
+            assert set(t) == keys, (set(t) ^ keys)
+            for k in ("format", "mcs", "len", "cr", "ampdu", "trellis", "total"):
+                assert int(t[k]) == int(f[k]), (k, t[k], f[k])
+            doff += int(f["total"])
+    # decode(ifdebug = True): one "crc32 correct" line per published MPDU, counters as lib/decode_impl.cc:377-411
+    lines = [s for s in stdout.splitlines() if s.startswith("ieee80211 decode, ")]
+    good = [s for s in lines if " crc32 correct, " in s]
+    assert len(good) == len(want) and good[-1].split("total:")[1].split(",")[0] == str(len(want))
+
+
+@pytest.mark.gpu
+def test_shells_2x2_equal_oracle(golden, tmp_path):
+    _build()
+    pkg = load_pkg()
+    g = golden["frames_mimo"]
+    a, b = _noisy(g["iq0"], 30.0, 13579), _noisy(g["iq1"], 30.0, 24680)
+    _, _, po = ol.rx_item2(a, b, max_frames=32)
+    want = pkg.blocks.split_messages(bytes(po))
+    msgs, tags, _ = _run(tmp_path, 2, a, b, seed=5)
+    assert msgs == want and len(want) >= 16
+    assert any("sssnr1" in t for (blk, _), t in tags.items() if blk == "demod2")
