@@ -72,6 +72,197 @@ __device__ __forceinline__ uint2 acs(const float (&m)[64], float (&n)[64], const
     return make_uint2(wlo, whi);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Packed forward pass (C8B_TP_PACKED = 1, NOT the default): the same add-compare-select in the same float32 operation order, with the
+// adds and the decision differences issued as sm_100 two-wide FADD2 (add.rn.f32x2: two independent IEEE adds, so every
+// sum is the bit the scalar form produces).  The kernel is bound by instruction issue, not by the FP32 pipe, so halving the
+// FADD count is what pays: 14 instructions per butterfly PAIR (4 FADD2 adds, 2 FADD2 differences, 4 FMNMX, 4 SHF) instead
+// of 18.
+//
+// The 64 metrics live in 32 aligned register pairs.  Layout L_q pairs the two states that differ in bit q.  With the input
+// in L_q (q >= 1) the butterflies k and k' = k | 1 << (q-1) read their even predecessors from ONE pair (2k, 2k') and their
+// odd predecessors from another (2k+1, 2k'+1), and their results (k, k') and (k+32, k'+32) are pairs of L_(q-1): the
+// layout walks 5 -> 4 -> 3 -> 2 -> 1 -> 0 for free.  In L_0 a pair holds both predecessors of one butterfly; that step
+// adds (m_even, m_odd) + (A, B) and + (B, A), compares inside the pairs and writes (k, k+32) = a pair of L_5 again.
+// Period 6 divides the 30-step staging chunk.  Branch-metric pairs: the code is linear, so class(k') = class(k) ^ delta_q
+// and a step needs just the four pairs (tab[x], tab[x ^ delta_q]).
+// MEASURED (one B200, 56832-frame wave, profiles/ncu_vtp_packed_r01.md): bit-exact (all decode / chain tests, 1,048,486 MPDUs of
+// the bench identical) and 242 instead of 290 instructions per trellis step, but SLOWER: 9.3 ms against 8.5 ms for the scalar
+// butterflies.  FADD2 issues only to the FMA-heavy sub-pipe and reads / writes 64-bit operands: issue-slot utilisation drops from
+// 75 % to 58 % behind dispatch stalls (0.57 per issue) and math-pipe throttle (0.78), and the 23 KB loop body adds
+// instruction-fetch stalls (0.32).  Kept behind the knob as the record of that experiment.
+// Decision words keep their natural bit order (state n -> bit n & 31 of word n >> 5), so survivors and traceback are
+// unchanged: q <= 3 shifts the sign bits in per group of 2^q butterflies, q = 4 / 5 fill two half-words and merge them with
+// one PRMT / one shift-or per word.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 swap2(u64 v) { float lo, hi; upk2(v, lo, hi); return pk2(hi, lo); }   // free: FADD2 operand swizzle .LO_HI
+__device__ __forceinline__ u64 max2(u64 a, u64 b)
+{
+    float a0, a1, b0, b1;
+    upk2(a, a0, a1); upk2(b, b0, b1);
+    return pk2(fmaxf(a0, b0), fmaxf(a1, b1));
+}
+__device__ __forceinline__ uint32_t push_sign(float d, uint32_t w) { return __funnelshift_l(__float_as_uint(d), w, 1); }
+
+__host__ __device__ constexpr int rm_bit(int s, int q) { return ((s >> (q + 1)) << q) | (s & ((1 << q) - 1)); }
+__host__ __device__ constexpr int ins_bit(int p, int q, int b) { return ((p >> q) << (q + 1)) | (b << q) | (p & ((1 << q) - 1)); }
+
+// butterflies k = ins_bit(J, Q-1, 0) and k | 1 << (Q-1) of a step whose input is in layout L_Q; TP[x] = (tab[x], tab[x ^ delta_Q])
+template <int Q, int J>
+__device__ __forceinline__ void bf_pair(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], u64& dLo, u64& dHi)
+{
+    constexpr int k = ins_bit(J, Q - 1, 0);
+    constexpr int c = bm_class(k);
+    constexpr bool zeroA = c == 0 && bm_class(1 << (Q - 1)) == 0;       // (0, 0): adding it is the identity
+    constexpr bool zeroB = (c ^ 3) == 0 && bm_class(1 << (Q - 1)) == 0;
+    const u64 E = P[rm_bit(2 * k, Q)], O = P[rm_bit(2 * k + 1, Q)];
+    const u64 aLo = zeroA ? E : add2(E, TP[c]), bLo = zeroB ? O : add2(O, TP[c ^ 3]);
+    const u64 aHi = zeroB ? E : add2(E, TP[c ^ 3]), bHi = zeroA ? O : add2(O, TP[c]);
+    dLo = sub2(aLo, bLo);                                               // sign set <=> the odd predecessor is strictly larger
+    dHi = sub2(aHi, bHi);
+    N[rm_bit(k, Q - 1)] = max2(aLo, bLo);
+    N[rm_bit(k + 32, Q - 1)] = max2(aHi, bHi);
+}
+
+// Q <= 3: groups of 2^Q butterflies, sign bits shifted in from the highest state down (natural order)
+template <int Q, int G, int I>
+struct GroupPairs {
+    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], float (&dl)[1 << Q], float (&dh)[1 << Q])
+    {
+        constexpr int H = 1 << (Q - 1);
+        u64 a, b;
+        bf_pair<Q, G * H + I>(P, N, TP, a, b);
+        upk2(a, dl[I], dl[I + H]);
+        upk2(b, dh[I], dh[I + H]);
+        GroupPairs<Q, G, I - 1>::run(P, N, TP, dl, dh);
+    }
+};
+template <int Q, int G>
+struct GroupPairs<Q, G, -1> {
+    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], float (&)[1 << Q], float (&)[1 << Q]) {}
+};
+template <int Q, int G>
+struct Groups {
+    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], uint32_t& wlo, uint32_t& whi)
+    {
+        float dl[1 << Q], dh[1 << Q];
+        GroupPairs<Q, G, (1 << (Q - 1)) - 1>::run(P, N, TP, dl, dh);
+#pragma unroll
+        for (int o = (1 << Q) - 1; o >= 0; o--) { wlo = push_sign(dl[o], wlo); whi = push_sign(dh[o], whi); }
+        Groups<Q, G - 1>::run(P, N, TP, wlo, whi);
+    }
+};
+template <int Q>
+struct Groups<Q, -1> {
+    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], uint32_t&, uint32_t&) {}
+};
+
+// Q = 4, 5: A collects the states with bit Q-1 set, B the others, both from the highest pair index down
+template <int Q, int J>
+struct Halves {
+    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], uint32_t& aLo, uint32_t& bLo, uint32_t& aHi,
+                                               uint32_t& bHi)
+    {
+        u64 a, b;
+        float d0, d1;
+        bf_pair<Q, J>(P, N, TP, a, b);
+        upk2(a, d0, d1);
+        bLo = push_sign(d0, bLo); aLo = push_sign(d1, aLo);
+        upk2(b, d0, d1);
+        bHi = push_sign(d0, bHi); aHi = push_sign(d1, aHi);
+        Halves<Q, J - 1>::run(P, N, TP, aLo, bLo, aHi, bHi);
+    }
+};
+template <int Q>
+struct Halves<Q, -1> {
+    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], uint32_t&, uint32_t&, uint32_t&, uint32_t&) {}
+};
+
+// Q = 0: pair K holds (m[2K], m[2K+1]); TQ[c] = (tab[c], tab[c ^ 3]); result pair K of L_5 = states (K, K + 32)
+template <int K>
+struct Inner {
+    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TQ)[4], uint32_t& wlo, uint32_t& whi)
+    {
+        constexpr int c = bm_class(K);
+        float eLo, oLo, oHi, eHi;
+        upk2(add2(P[K], TQ[c]), eLo, oLo);
+        upk2(add2(P[K], TQ[c ^ 3]), eHi, oHi);
+        wlo = push_sign(__fsub_rn(eLo, oLo), wlo);
+        whi = push_sign(__fsub_rn(eHi, oHi), whi);
+        N[K] = pk2(fmaxf(eLo, oLo), fmaxf(eHi, oHi));
+        Inner<K - 1>::run(P, N, TQ, wlo, whi);
+    }
+};
+template <>
+struct Inner<-1> {
+    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], uint32_t&, uint32_t&) {}
+};
+
+// The four branch-metric pairs TP[x] = (tab[x], tab[x ^ DELTA]) of a step, tab = {0, t1, t0, t1 + t0}, made from the pair
+// T01 = (t0, t1) as it comes out of shared memory with two-wide arithmetic only (no register moves: building them with
+// mov.b64 makes ptxas re-materialise a pair at nearly every use).  C01 = (0.0f, 1.0f) is read from the table blob, i.e. a
+// run-time value the assembler cannot re-materialise either.  x * 0 is +-0 and m + (+-0) == m, fma(x, 1, y) == x + y rounded
+// once, t0 + t1 == t1 + t0: every metric is the bit the scalar form produces.
+template <int DELTA>
+__device__ __forceinline__ void metric_pairs(const u64 T01, const u64 C01, u64 (&TP)[4])
+{
+    const u64 S01 = swap2(T01);                                         // (t1, t0)
+    if constexpr (DELTA == 3) {
+        const u64 T33 = add2(S01, T01);                                 // (t1 + t0, t0 + t1)
+        TP[0] = mul2(T33, C01);                                         // (0, t3)
+        TP[3] = swap2(TP[0]);
+        TP[1] = S01;
+        TP[2] = T01;
+    } else if constexpr (DELTA == 1) {
+        TP[0] = mul2(T01, C01);                                         // (0, t1)
+        TP[1] = swap2(TP[0]);
+        TP[2] = fma2(S01, C01, T01);                                    // (t1 * 0 + t0, t0 * 1 + t1) = (t0, t3)
+        TP[3] = swap2(TP[2]);
+    } else if constexpr (DELTA == 2) {
+        const u64 C10 = swap2(C01);
+        TP[2] = mul2(T01, C10);                                         // (t0, 0)
+        TP[0] = swap2(TP[2]);
+        TP[3] = fma2(S01, C10, T01);                                    // (t1 * 1 + t0, t0 * 0 + t1) = (t3, t1)
+        TP[1] = swap2(TP[3]);
+    } else {
+        float t0, t1;
+        upk2(T01, t0, t1);
+        TP[0] = 0;                                                      // never read: adding (0, 0) is skipped
+        TP[1] = pk2(t1, t1);
+        TP[2] = pk2(t0, t0);
+        TP[3] = add2(S01, T01);
+    }
+}
+
+// one trellis step, input in layout L_Q, output in L_(Q-1) (Q = 0: L_5)
+template <int Q>
+__device__ __forceinline__ uint2 acs2(const u64 (&P)[32], u64 (&N)[32], const u64 T01, const u64 C01)
+{
+    u64 TP[4];
+    uint32_t wlo = 0, whi = 0;
+    if constexpr (Q == 0) {
+        metric_pairs<3>(T01, C01, TP);                                  // (tab[c], tab[c ^ 3]) = (A, B) of butterfly class c
+        Inner<31>::run(P, N, TP, wlo, whi);
+    } else {
+        metric_pairs<bm_class(1 << (Q - 1))>(T01, C01, TP);
+        if constexpr (Q <= 3) {
+            Groups<Q, (32 >> Q) - 1>::run(P, N, TP, wlo, whi);
+        } else {
+            uint32_t aLo = 0, bLo = 0, aHi = 0, bHi = 0;
+            Halves<Q, 15>::run(P, N, TP, aLo, bLo, aHi, bHi);
+            if constexpr (Q == 5) { wlo = (aLo << 16) | bLo; whi = (aHi << 16) | bHi; }
+            else { wlo = __byte_perm(bLo, aLo, 0x5140); whi = __byte_perm(bHi, aHi, 0x5140); }
+        }
+    }
+    return make_uint2(wlo, whi);
+}
+
 // chunk-relative soft-bit indices of step s for code rate cr; -1 = punctured (same closed forms as k_viterbi.cu)
 __device__ __forceinline__ void depunc(int cr, int t, int& i0, int& i1)
 {
@@ -147,6 +338,9 @@ __device__ void emit_record_t(uint8_t* __restrict__ out, int& w, int cap, int& n
     npdu++;
 }
 
+#ifndef C8B_TP_PACKED
+#define C8B_TP_PACKED 0                        // 0: scalar butterflies (default, faster); 1: FADD2 forward pass (acs2) -- measured SLOWER, see below
+#endif
 #ifndef C8B_TP_CTAS
 #define C8B_TP_CTAS 3                          // CTAs per SM (168 registers per thread, no spills; 4 would spill the metrics)
 #endif
@@ -217,6 +411,30 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         auto stage_wait = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); };
 
         // ---------------- forward pass ----------------
+#if C8B_TP_PACKED
+        const u64 C01 = *reinterpret_cast<const u64*>(lut->pair01);    // (0.0f, 1.0f), see metric_pairs
+        u64 m[32], n[32];                                              // layout L_5 at every multiple of 6 steps: pair k = states (k, k + 32)
+#pragma unroll
+        for (int i = 0; i < 32; i++) m[i] = pk2(-1000000000000000.0f, -1000000000000000.0f);     // lib/decode_impl.cc:171-176
+        m[0] = pk2(0.0f, -1000000000000000.0f);
+        stage(0, 0);
+        stage_wait();
+        for (int c = 0; c < nch; c++) {
+            if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
+            const u64* __restrict__ row = reinterpret_cast<const u64*>(pairs[warp][c & 1] + lane * ROWF2);   // (t0, t1) per step
+            uint2* __restrict__ sv = surv + (size_t)c * CS * TPB;
+#pragma unroll 1
+            for (int s = 0; s < CS; s += 6) {
+                sv[(size_t)(s + 0) * TPB] = acs2<5>(m, n, row[s + 0], C01);
+                sv[(size_t)(s + 1) * TPB] = acs2<4>(n, m, row[s + 1], C01);
+                sv[(size_t)(s + 2) * TPB] = acs2<3>(m, n, row[s + 2], C01);
+                sv[(size_t)(s + 3) * TPB] = acs2<2>(n, m, row[s + 3], C01);
+                sv[(size_t)(s + 4) * TPB] = acs2<1>(m, n, row[s + 4], C01);
+                sv[(size_t)(s + 5) * TPB] = acs2<0>(n, m, row[s + 5], C01);
+            }
+            stage_wait();
+        }
+#else
         float m[64], n[64];
 #pragma unroll
         for (int i = 0; i < 64; i++) m[i] = -1000000000000000.0f;     // lib/decode_impl.cc:171-176
@@ -236,6 +454,7 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
             }
             stage_wait();
         }
+#endif
 
         // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
         {

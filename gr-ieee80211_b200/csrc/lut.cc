@@ -98,4 +98,6 @@ void c8b_lut_build(c8b_lut* L)
             L->crcZ[p][i] = c;
         }
     }
+    L->pair01[0] = 0.0f;
+    L->pair01[1] = 1.0f;
 }

@@ -12,7 +12,7 @@
 #define C8B_DECODE_T_MAX 32782 // lib/decode_impl.h:36
 
 #define C8B_LUT_MAGIC 0x4c423843u /* "C8BL" */
-#define C8B_LUT_VERSION 4u
+#define C8B_LUT_VERSION 5u
 
 struct c8b_lut {
     uint32_t magic, version, bytes, pad0;
@@ -30,6 +30,7 @@ struct c8b_lut {
     uint8_t binToDataNL[64];   // FFT bin -> data index 0..51 in -28..28 order (255: null/pilot)
     uint32_t crc32tab[256];    // reflected 0xEDB88320
     uint32_t crcZ[6][32];      // crcZ[p][i] = CRC register (1<<i) advanced by 64*2^p zero bytes (lane-parallel CRC)
+    float pair01[2];           // {0.0f, 1.0f}: read as one 8-byte register pair by k_viterbi_tp (FMUL2 / FFMA2 selectors)
 };
 
 void c8b_lut_build(c8b_lut* L);   // host, by formula (lut.cc)

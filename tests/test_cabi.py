@@ -60,7 +60,8 @@ def test_lut_blob_matches_reference_tables(golden):
     binL, binNL = take(64, "u1"), take(64, "u1")
     crc = take(256, "<u4")
     crcz = take(6 * 32, "<u4").reshape(6, 32)
-    assert o == blob.size
+    pair01 = take(2, "<f4")
+    assert o == blob.size and pair01.tolist() == [0.0, 1.0]
     assert np.array_equal(ltfL, g["tab_LTF_L_26_F_FLOAT"]) and np.array_equal(ltfNL, g["tab_LTF_NL_28_F_FLOAT"])
     assert np.array_equal(ltfNL22, g["tab_LTF_NL_28_F_FLOAT_VHT22"])
     assert np.array_equal(pilotP[:127], g["tab_PILOT_P"])
