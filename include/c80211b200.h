@@ -14,6 +14,7 @@
  *   lib/signal2_impl.cc:63-212, lib/demod2_impl.cc:58-806 (2x2) c8b_demod2 / c8b_rx_batch2
  *   lib/decode_impl.cc:60-520   decode::general_work      c8b_decode / c8b_viterbi
  *   whole flowgraph examples/rx.grc:753-767               c8b_rx_batch / c8b_rx_batch_dev
+ *   the blocks' general_work(), call by call (all seven)  c8b_blk_create / c8b_blk_work   (gr/lib/rx_blocks_impl.cc)
  *   LUTs of lib/cloud80211phy.cc (c8p.h:151-195)          c8b_lut_blob / c8b_lut_load
  *
  * Conventions: every function returns 0 on success or a negative C8B_ERR_* code (never throws,

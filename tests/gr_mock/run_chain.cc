@@ -14,6 +14,7 @@
 #include <gnuradio/ieee80211/sync.h>
 #include <gnuradio/ieee80211/trigger.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -147,12 +148,16 @@ int main(int argc, char** argv)
     g.connect(*dem, 0, *dec, 0);
 
     gr::block* order[5] = { trig.get(), syn.get(), sig.get(), dem.get(), dec.get() };
+    const auto t0 = std::chrono::steady_clock::now();
     for (int idle = 0; idle < 3;) {
         bool moved = false;
         for (gr::block* b : order)
             for (int r = 1 + (int)(rnd() % 3u); r > 0; r--) moved |= call(*b, maxCall, idle > 0);
         idle = moved ? 0 : idle + 1;
     }
+
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << "run_chain: " << s0.size() / 8 << " samples, " << dec->mock_messages.size() << " messages, " << ms << " ms wall" << std::endl;
 
     FILE* f = fopen(argv[8], "w");
     if (!f) return 2;
