@@ -390,21 +390,39 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         const int nch = (Tmax + CS - 1) / CS;
 
         // stage chunk c: every lane copies the (t0,t1) pairs of ITS frame into its shared-memory row with cp.async
-        // (LDGSTS): the copies of the next chunk run under the butterflies of the current one and hold no registers; a
-        // punctured or past-the-end position is a zero-fill copy (src-size 0).  relTab[cr][s] = chunk-relative soft-bit
-        // indices of step s (i0 | i1 << 16, 0xffff = punctured).
+        // (LDGSTS): the copies of the next chunk run under the butterflies of the current one and hold no registers.
+        // relTab[cr][s] = chunk-relative soft-bit indices of step s (i0 | i1 << 16, 0xffff = punctured).  A chunk is a whole
+        // number of puncture periods, so the punctured slots of a row are the same in every chunk: they are zeroed once per
+        // frame and never copied; a position past the end of the packet is a zero-fill copy (src-size 0).  The table entries
+        // of ten steps are fetched together (LDS.64) ahead of their twenty copies -- one dependent LDS per step stalled the
+        // warp for a fifth of the kernel.
+        {
+            float2* r0 = pairs[warp][0] + lane * ROWF2;
+            float2* r1 = pairs[warp][1] + lane * ROWF2;
+#pragma unroll
+            for (int i = 0; i < CS; i++) { r0[i] = make_float2(0.f, 0.f); r1[i] = make_float2(0.f, 0.f); }
+            __syncwarp();
+        }
         auto stage = [&](int c, int buf) {
             const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(pairs[warp][buf] + lane * ROWF2);
             const float* __restrict__ lb = llr + (size_t)c * nraw;
             const int rem = lim - c * nraw;                          // soft bits left from the start of this chunk
-            const uint32_t* __restrict__ rt = relTab + cr * 32;
+            const uint2* __restrict__ rt = reinterpret_cast<const uint2*>(relTab + cr * 32);
 #pragma unroll
-            for (int sidx = 0; sidx < CS; sidx++) {
-                const uint32_t e = rt[sidx];
-                const int r0 = (int)(e & 0xffffu), r1 = (int)(e >> 16);
-                const bool ok0 = r0 != 0xffff && r0 < rem, ok1 = r1 != 0xffff && r1 < rem;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * sidx), "l"(lb + (ok0 ? r0 : 0)), "r"(ok0 ? 4 : 0) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * sidx + 4), "l"(lb + (ok1 ? r1 : 0)), "r"(ok1 ? 4 : 0) : "memory");
+            for (int b = 0; b < CS; b += 10) {
+                uint2 e[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) e[k] = rt[b / 2 + k];
+#pragma unroll
+                for (int k = 0; k < 10; k++) {
+                    const uint32_t ev = (k & 1) ? e[k >> 1].y : e[k >> 1].x;
+                    const int i0 = (int)(ev & 0xffffu), i1 = (int)(ev >> 16);
+                    const bool in0 = i0 < rem, in1 = i1 < rem;
+                    if (i0 != 0xffff)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * (b + k)), "l"(lb + (in0 ? i0 : 0)), "r"(in0 ? 4 : 0));
+                    if (i1 != 0xffff)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * (b + k) + 4), "l"(lb + (in1 ? i1 : 0)), "r"(in1 ? 4 : 0));
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };

@@ -69,6 +69,9 @@ public:
     }
     virtual int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
                              gr_vector_void_star& output_items) = 0;
+    virtual bool start() { return true; }
+    virtual bool stop() { return true; }
+    void set_output_multiple(int multiple) { mock_output_multiple = multiple; }
     void consume_each(int how_many_items) { mock_consumed = how_many_items; }
     uint64_t nitems_read(unsigned int which_input) { return mock_in.at(which_input)->nread; }
     uint64_t nitems_written(unsigned int which_output) { return mock_written.at(which_output); }
@@ -81,7 +84,7 @@ public:
     std::vector<mock::edge*> mock_in;
     std::vector<std::vector<mock::edge*>> mock_out;
     std::vector<uint64_t> mock_written;
-    int mock_consumed = 0;
+    int mock_consumed = 0, mock_output_multiple = 1;
 
 protected:
     block() {}

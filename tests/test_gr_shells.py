@@ -14,6 +14,7 @@ from __graft_entry__ import ROOT, load_pkg
 
 MOCK = os.path.join(ROOT, "tests", "gr_mock")
 EXE = os.path.join(MOCK, "build", "run_chain")
+EXE_RX = os.path.join(MOCK, "build", "run_rx")
 
 
 def _build():
@@ -28,11 +29,12 @@ def test_shells_build_and_fail_loudly_without_gpu(tmp_path):
     pkg = load_pkg()
     if pkg._cabi.lib().c8b_device_count() > 0:
         return
-    r = subprocess.run([EXE, "1", "0", "0", "1", "4096", "0", str(tmp_path), str(tmp_path / "out.txt")], capture_output=True, text=True)
-    assert r.returncode == 4 and "no CPU path" in r.stderr          # make() throws: no GPU, no block
+    for exe in (EXE, EXE_RX):
+        r = subprocess.run([exe, "1", "0", "0", "1", "4096", "0", str(tmp_path), str(tmp_path / "out.txt")], capture_output=True, text=True)
+        assert r.returncode == 4 and "no CPU path" in r.stderr      # make() throws: no GPU, no block
 
 
-def _run(tmp_path, nant, x, x1=None, mupos=0, mugid=0, seed=1, max_call=4096, debug=0):
+def _run(tmp_path, nant, x, x1=None, mupos=0, mugid=0, seed=1, max_call=4096, debug=0, exe=EXE):
     pkg = load_pkg()
     rx = pkg.Receiver(device=0)
     preac, preconj = rx.presiso(x)
@@ -43,7 +45,7 @@ def _run(tmp_path, nant, x, x1=None, mupos=0, mugid=0, seed=1, max_call=4096, de
     if x1 is not None:
         x1.astype(np.complex64).tofile(tmp_path / "sig1.c64")
     out = tmp_path / "out.txt"
-    r = subprocess.run([EXE, str(nant), str(mupos), str(mugid), str(seed), str(max_call), str(debug), str(tmp_path), str(out)],
+    r = subprocess.run([exe, str(nant), str(mupos), str(mugid), str(seed), str(max_call), str(debug), str(tmp_path), str(out)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     msgs, tags = [], {}
@@ -107,3 +109,24 @@ def test_shells_2x2_equal_oracle(golden, tmp_path):
     msgs, tags, _ = _run(tmp_path, 2, a, b, seed=5)
     assert msgs == want and len(want) >= 16
     assert any("sssnr1" in t for (blk, _), t in tags.items() if blk == "demod2")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nant,max_call", [(1, 8192), (1, 1500), (2, 8192)])
+def test_rx_sink_block_equals_oracle(golden, tmp_path, nant, max_call):
+    """gr::ieee80211::rx (gr/lib/rx_impl.cc): the chain as one sink block on the live-stream session, fed in random pieces"""
+    _build()
+    pkg = load_pkg()
+    if nant == 1:
+        x, x1 = _noisy(golden["frames_siso"]["iq"], 28.0, 33), None
+        _, _, po = ol.rx_item(x, max_frames=40)
+    else:
+        g = golden["frames_mimo"]
+        x, x1 = _noisy(g["iq0"], 30.0, 13579), _noisy(g["iq1"], 30.0, 24680)
+        _, _, po = ol.rx_item2(x, x1, max_frames=32)
+    want = pkg.blocks.split_messages(bytes(po))
+    msgs, _, stdout = _run(tmp_path, nant, x, x1, mugid=2, seed=max_call, max_call=max_call, debug=1, exe=EXE_RX)
+    assert msgs == want and len(want) >= 16
+    print([ln for ln in stdout.splitlines() if ln.startswith("run_rx:")])
+    good = [s for s in stdout.splitlines() if s.startswith("ieee80211 decode, ") and " crc32 correct, " in s]
+    assert len(good) == len(want)
