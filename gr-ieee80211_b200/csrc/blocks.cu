@@ -83,7 +83,7 @@ struct Buf {
 }  // namespace
 
 struct c8b_blk {
-    int kind = 0;
+    int kind = 0, device = 0;
     c8b_ctx* ctx = nullptr;
     cudaStream_t st = nullptr;
     const c8b_lut* lut = nullptr;
@@ -216,6 +216,7 @@ const char* c8b_blk_last_error(const c8b_blk* b) { return b ? b->err.c_str() : g
 void c8b_blk_destroy(c8b_blk* b)
 {
     if (!b) return;
+    cudaSetDevice(b->device);
     if (b->d_trig) cudaFree(b->d_trig);
     if (b->d_sync) cudaFree(b->d_sync);
     if (b->d_sig) cudaFree(b->d_sig);
@@ -237,6 +238,7 @@ int c8b_blk_create(const c8b_cfg* cfg, int kind, c8b_blk** out)
     c8b_blk* b = new (std::nothrow) c8b_blk;
     if (!b) { g_blkErr = "out of memory"; return C8B_ERR_NOMEM; }
     b->kind = kind;
+    b->device = c.device;
     int rc = c8b_create(&c, &b->ctx);
     if (rc) { g_blkErr = c8b_last_error(nullptr); delete b; return rc; }
     std::vector<uint8_t> blob(c8b_lut_size());
@@ -271,7 +273,8 @@ int c8b_blk_work(c8b_blk* b, int noutput, const int* ninput, const void* const* 
     c8b_blk_ports(b->kind, &nin, &nout, nullptr, nullptr);
     for (int k = 0; k < nin; k++) if (ninput[k] < 0 || (ninput[k] && !in[k])) { b->err = "c8b_blk_work: bad input port"; return C8B_ERR_ARG; }
     for (int k = 0; k < nout; k++) if (noutput && (!out || !out[k])) { b->err = "c8b_blk_work: bad output port"; return C8B_ERR_ARG; }
-    c8b_blocks::WorkIO io;
+    if (cudaSetDevice(b->device) != cudaSuccess) { b->err = "c8b_blk_work: cudaSetDevice failed"; return C8B_ERR_CUDA; }   // the calling
+    c8b_blocks::WorkIO io;                                       // thread may have another device current (one block thread per GPU)
     io.noutput = noutput; io.ninput = ninput; io.in = in; io.out = out;
     io.in_tags = in_tags; io.n_in_tags = n_in_tags;
     io.out_tags = out_tags; io.out_tag_cap = out_tags ? out_tag_cap : 0;
