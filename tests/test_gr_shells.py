@@ -34,6 +34,21 @@ def test_shells_build_and_fail_loudly_without_gpu(tmp_path):
         assert r.returncode == 4 and "no CPU path" in r.stderr      # make() throws: no GPU, no block
 
 
+def test_rx_pybind_binding_compiles():
+    """gr/python/ieee80211/bindings/rx_python.cc against pybind11 + the mock runtime (syntax / types only)"""
+    try:
+        import pybind11
+    except ImportError:
+        pytest.skip("pybind11 not installed")
+    import sysconfig
+    inc = ["-I" + sysconfig.get_paths()["include"], "-I" + pybind11.get_include()]
+    if os.path.isdir("/root/reference/include"):
+        inc.append("-I/root/reference/include")
+    inc += ["-I" + os.path.join(MOCK, "include"), "-I" + os.path.join(ROOT, "gr-ieee80211_b200", "gr", "include"), "-I" + os.path.join(ROOT, "include")]
+    src = os.path.join(ROOT, "gr-ieee80211_b200", "gr", "python", "ieee80211", "bindings", "rx_python.cc")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-fsyntax-only"] + inc + [src])
+
+
 def _run(tmp_path, nant, x, x1=None, mupos=0, mugid=0, seed=1, max_call=4096, debug=0, exe=EXE):
     pkg = load_pkg()
     rx = pkg.Receiver(device=0)

@@ -116,3 +116,58 @@ def test_chain_noise_and_junk_do_not_stall(golden):
     assert len(msgs) == len(full) >= 1
     got = [(int(t["f"]["l_mcs"]), int(t["f"]["l_len"])) for _, t in ch.tags["signal"]]
     assert got[:len(full)] == [(int(f["l_mcs"]), int(f["l_len"])) for f in full]
+
+
+def _tags(pkg, *recs):
+    t = np.zeros(len(recs), pkg._cabi.TAG_DTYPE)
+    for k, (idx, fields, nvec) in enumerate(recs):
+        t[k]["idx"], t[k]["nvec"] = idx, nvec
+        for name, v in fields.items():
+            t[k]["f"][name] = v
+    return t
+
+
+def test_block_error_paths_follow_the_reference(capfd):
+    """what the blocks do off the happy path (lib/signal_impl.cc:96-100, lib/demod_impl.cc:72-103, lib/decode_impl.cc:93-127,141-157)"""
+    pkg = load_pkg()
+    B = pkg.blocks
+    be = hs.HostBackend()
+    none = np.zeros(0, pkg._cabi.TAG_DTYPE)
+    # signal: a sync flag without a tag is reported, skipped (consumed up to and including it) and the block keeps searching
+    sg = B.Block(B.SIGNAL, be)
+    sync = np.zeros(50, np.uint8)
+    sync[5] = 1
+    c, outs, tg, msg = sg.work(50, [sync, np.zeros(50, np.complex64)], none)
+    assert (c, outs[0].size, tg.size) == (6, 0, 0)
+    assert "ieee80211 signal, error: input sync with no tag." in capfd.readouterr().out
+    # ... and an L-SIG that fails its checks costs 80 samples (S_DEMOD -> S_TRIGGER, :156-160)
+    sync = np.zeros(400, np.uint8)
+    sync[0] = 1
+    c, outs, tg, msg = sg.work(400, [sync, np.zeros(400, np.complex64)], _tags(pkg, (0, {"rad": 0.0, "snr": 10.0, "rssi": 1.0}, 0)))
+    assert (c, outs[0].size, tg.size) == (80, 0, 0)
+    sg.close()
+    # demod: no tag at the first item -> waits (consumes nothing, like DEMOD_S_RDTAG)
+    dm = B.Block(B.DEMOD, be)
+    c, outs, tg, msg = dm.work(100, [np.zeros(100, np.complex64)], none)
+    assert (c, outs[0].size) == (0, 0)
+    dm.close()
+    # decode: length over DECODE_B_MAX -> the frame's soft bits are swallowed, nothing is published
+    dc = B.Block(B.DECODE, be)
+    big = {"format": 0, "len": 5000, "total": 300, "cr": 0, "mcs": 0, "ampdu": 0, "trellis": 40022}
+    c, _, tg, msg = dc.work(0, [np.zeros(100, np.float32)], _tags(pkg, (0, big, 0)))
+    assert (c, msg) == (0, b"")
+    c1, _, _, m1 = dc.work(0, [np.zeros(100, np.float32)], none)
+    c2, _, _, m2 = dc.work(0, [np.zeros(400, np.float32)], none)
+    assert (c1, c2, m1, m2) == (100, 200, b"", b"")
+    # ... an NDP tag (trellis 0) publishes the channel report [20][0][4][128 x (re, im)] and swallows 1024 floats
+    ndp = _tags(pkg, (0, {"format": 2, "len": 0, "total": 1024, "trellis": 0}, 128))
+    ndp[0]["vec"][:] = np.arange(256, dtype=np.float32)
+    c, _, _, msg = dc.work(0, [np.zeros(2000, np.float32)], ndp)
+    assert c == 0 and len(msg) == 1027 and msg[:3] == bytes([20, 0, 4])
+    assert np.array_equal(np.frombuffer(msg[3:], np.float32), np.arange(256, dtype=np.float32))
+    c, _, _, msg = dc.work(0, [np.zeros(2000, np.float32)], none)
+    assert (c, msg) == (1024, b"")
+    # ... and back in IDLE it waits for the next tag
+    c, _, _, msg = dc.work(0, [np.zeros(50, np.float32)], none)
+    assert (c, msg) == (0, b"")
+    dc.close()
