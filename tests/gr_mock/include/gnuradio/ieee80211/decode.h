@@ -1,7 +1,2 @@
-// TEST INFRASTRUCTURE: stand-in for the reference's public header include/gnuradio/ieee80211/decode.h (class name, base and
-// make() signature only), used when /root/reference is not there to compile the shells against the real one.
-#pragma once
-#include <gnuradio/block.h>
-namespace gr { namespace ieee80211 {
-class decode : virtual public gr::block { public: typedef std::shared_ptr<decode> sptr; static sptr make(bool ifdebug); };
-} }
+// TEST INFRASTRUCTURE: see standin_blocks.h
+#include "standin_blocks.h"

@@ -1,7 +1,2 @@
-// TEST INFRASTRUCTURE: stand-in for the reference's public header include/gnuradio/ieee80211/demod2.h (class name, base and
-// make() signature only), used when /root/reference is not there to compile the shells against the real one.
-#pragma once
-#include <gnuradio/block.h>
-namespace gr { namespace ieee80211 {
-class demod2 : virtual public gr::block { public: typedef std::shared_ptr<demod2> sptr; static sptr make(); };
-} }
+// TEST INFRASTRUCTURE: see standin_blocks.h
+#include "standin_blocks.h"
