@@ -171,3 +171,44 @@ def test_block_error_paths_follow_the_reference(capfd):
     c, _, _, msg = dc.work(0, [np.zeros(50, np.float32)], none)
     assert (c, msg) == (0, b"")
     dc.close()
+
+
+def test_chain_2x2_equals_batch_detect(golden):
+    """signal2 / demod2 (lib/signal2_impl.cc:63-212, lib/demod2_impl.cc:58-348): antenna 0 drives detection, both antennas are copied"""
+    pkg = load_pkg()
+    H = hs.lib()
+    g = golden["frames_mimo"]
+    a, b = np.ascontiguousarray(g["iq0"]), np.ascontiguousarray(g["iq1"])
+    preac, preconj = _presiso(a)
+    maxf = 32
+    f = np.zeros(maxf, pkg.FRAME_DTYPE)
+    chan = np.zeros(128 * maxf, np.float32)
+    H.hs_detect(ol.c2f(a), preac, a.size, 0, maxf, f.ctypes.data, chan)
+    keep = (f["status"] != 9) & (f["nsamp"] > 0)
+    want, wchan = f[keep], chan.reshape(maxf, 128)[keep]
+    for k in range(want.size):
+        hinv, w2 = np.zeros(128, np.float32), np.zeros(528, np.float32)
+        H.hs_header2(ol.c2f(a), ol.c2f(b), want[k:k + 1].ctypes.data, wchan[k], hinv, w2)
+    assert want.size >= 16
+
+    ch = pkg.blocks.Chain(nant=2, backend=hs.HostBackend(), seed=5, max_call=3000)
+    msgs = ch.run(preac, preconj, a, b)
+    ch.close()
+    s0, s1 = np.concatenate(ch.trace["signal"]), np.concatenate(ch.trace["signal1"])
+    off = 0
+    assert len(ch.tags["signal"]) == want.size
+    for k, (o, t) in enumerate(ch.tags["signal"]):
+        fr = want[k]
+        n, st = int(fr["nsamp"]), int(fr["sync_idx"]) + 224
+        assert o == off and (t["f"]["l_mcs"], t["f"]["l_len"], t["f"]["nsamp"]) == (fr["l_mcs"], fr["l_len"], fr["nsamp"])
+        ph = ((np.arange(n, dtype=np.float32) + np.float32(224)) * np.float32(fr["rad"])).astype(np.float64)
+        assert np.allclose(s0[off:off + n], a[st:st + n] * np.exp(1j * ph), atol=2e-6)
+        assert np.allclose(s1[off:off + n], b[st:st + n] * np.exp(1j * ph), atol=2e-6)
+        off += n + 320
+    assert s0.size == s1.size == off
+    dem = want[want["status"] == 0]
+    assert len(ch.tags["demod"]) == dem.size == len(msgs)
+    for (o, t), fr in zip(ch.tags["demod"], dem):
+        for key in ("format", "mcs", "len", "cr", "nss", "trellis", "total"):
+            assert t["f"][key] == fr[key], (key, t["f"][key], fr[key])
+    assert sum(x.size for x in ch.trace["llr"]) == int(dem["total"].sum())
