@@ -38,6 +38,17 @@ SNR_DB = 30.0
 WORKLOAD = "configs[4]: VHT MCS7 1500-byte MPDU (47 sym, 4560 samples + 400 gap), AWGN 30 dB, CFO U(-100,100) kHz"
 
 
+def cpu_model():
+    """host CPU model string (the CPU baseline names the host it ran on)"""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def ncu_traffic(kernel):
     """dram read+write bytes per launch of `kernel` from the committed ncu --set full summary (profiles/ncu_r01.json), or None"""
     p = os.path.join(ROOT, "profiles", "ncu_r01.json")
@@ -203,6 +214,7 @@ def run_reference(args, rank):
         "dtype": "f32", "data": "synthetic", "frames_per_s": per_step * args.steps / t,
         "config": {"workload": WORKLOAD, "frames_per_step": per_step, "samples_per_item": ITEM, "frames_ok": ok},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "cpu_model": cpu_model(),
                          "sample": "%d steps x %d config-5 items through oracle/liboracle_rx.so (orx_rx_batch, %d threads)" % (args.steps, per_step, cores)},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -417,6 +429,7 @@ def main():
             dt1, _ = cpu_arm(max(8, nb // (4 * cores)), 1, seed=2)
             line["cpu_baseline"] = {"value": nb * ITEM / dt, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "frames_per_s": nb / dt, "single_thread_samples_per_s": max(8, nb // (4 * cores)) * ITEM / dt1,
+                                    "cpu_model": cpu_model(),
                                     "sample": "%d config-5 items through oracle/liboracle_rx.so (orx_rx_batch, %d threads), %d decoded"
                                               % (nb, cores, okc)}
         print(json.dumps(line))
