@@ -152,7 +152,13 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
     }
     // soft bits of this thread's data tones, scattered through the deinterleave map
     const uint8_t* __restrict__ b2d = legacy ? lut->binToDataL : lut->binToDataNL;
-    float* __restrict__ L = W.llr + g * ncbps;
+    // shared-memory row of a symbol: ncbps floats + LPAD.  With rows at multiples of 48 * nbpsc the four symbols of a warp
+    // scatter through the legacy deinterleaver into the same banks (11.5 wavefronts per store, 5.75 for BPSK; HT/VHT BPSK
+    // 2.1); four floats of padding bring that to 2.9 / 1.9 / 1.4 (bank model over the lane -> address map; the other HT/VHT
+    // maps are at 1.1-1.75 unpadded, and the 256-QAM row has no room to spare).  Multiples of 4 keep the rows float4-aligned.
+    const int lpad = (legacy || nbpsc == 1) ? 4 : 0;
+    const int lrow = ncbps + lpad;
+    float* __restrict__ L = W.llr + g * lrow;
     if (live) {
 #pragma unroll
         for (int k2 = 0; k2 < 8; k2++) {
@@ -190,12 +196,27 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
     nlive = nlive < 0 ? 0 : (nlive > SPW ? SPW : nlive);
     const int nfl = nlive * ncbps;                          // multiple of 4 (48 | 52 divide by 4)
     float* __restrict__ out = llrArena + fr->llr_off + (int64_t)wsym0 * ncbps;
-    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
-        float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
-        for (int i = lane; i < nfl / 4; i += 32) o4[i] = s4[i];
-    } else {
-        for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
+    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (lpad == 0) {
+        if (al16) {
+            const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
+            float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+            for (int i = lane; i < nfl / 4; i += 32) o4[i] = s4[i];
+        } else {
+            for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
+        }
+    } else {                                               // padded rows: symbol by symbol (ncbps * 4 bytes is a multiple of 16)
+        for (int r = 0; r < nlive; r++) {
+            const float* __restrict__ src = W.llr + r * lrow;
+            float* __restrict__ dst = out + r * ncbps;
+            if (al16) {
+                const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
+                float4* __restrict__ o4 = reinterpret_cast<float4*>(dst);
+                for (int i = lane; i < ncbps / 4; i += 32) o4[i] = s4[i];
+            } else {
+                for (int i = lane; i < ncbps; i += 32) dst[i] = src[i];
+            }
+        }
     }
 }
 
