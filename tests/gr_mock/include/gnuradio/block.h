@@ -6,14 +6,21 @@
 #include <gnuradio/io_signature.h>
 #include <pmt/pmt.h>
 
+// the real <gnuradio/block.h> pulls these in transitively and the reference's blocks rely on it (std::cout, memset,
+// std::max_element, std::chrono without their own #include)
+#include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <complex>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
 #include <memory>
 #include <string>
 #include <utility>
 #include <vector>
 
-typedef std::complex<float> gr_complex;
 typedef std::vector<int> gr_vector_int;
 typedef std::vector<const void*> gr_vector_const_void_star;
 typedef std::vector<void*> gr_vector_void_star;
@@ -33,10 +40,11 @@ struct tag_t {
 namespace mock {
 struct edge {
     int item = 1;
-    std::vector<char> data;          // items written and not yet consumed
+    std::vector<char> data;          // items written and not yet consumed (from byte `head` on)
+    size_t head = 0;                 // schedulers that do not erase consumed items advance this instead
     uint64_t nread = 0, nwritten = 0;
     std::vector<tag_t> tags;
-    size_t avail() const { return data.size() / (size_t)item; }
+    size_t avail() const { return (data.size() - head) / (size_t)item; }
 };
 }  // namespace mock
 

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE (see pmt/pmt.h): gr::io_signature::make / makev
 #pragma once
+#include <gnuradio/gr_complex.h>
 #include <memory>
 #include <vector>
 

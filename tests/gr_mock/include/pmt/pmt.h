@@ -23,6 +23,7 @@ struct p_c32v : pmt_base { std::vector<std::complex<float>> v; };
 struct p_blob : pmt_base { std::vector<uint8_t> v; };
 struct p_pair : pmt_base { pmt_t a, b; };
 struct p_dict : pmt_base { std::vector<std::pair<pmt_t, pmt_t>> kv; };
+struct p_list : pmt_base { std::vector<pmt_t> v; };
 
 inline const pmt_t PMT_NIL = std::make_shared<p_nil>();
 inline const pmt_t PMT_F = std::make_shared<p_bool>(false);
@@ -76,5 +77,23 @@ inline pmt_t dict_ref(const pmt_t& d, const pmt_t& k, const pmt_t& dflt)
     for (auto& kv : as<p_dict>(d, "dict").kv) if (symbol_to_string(kv.first) == symbol_to_string(k)) return kv.second;
     return dflt;
 }
+// the real dict is an association list that dict_add conses onto: dict_items lists the newest key first
+inline pmt_t dict_items(const pmt_t& d)
+{
+    auto l = std::make_shared<p_list>();
+    const auto& kv = as<p_dict>(d, "dict").kv;
+    for (auto it = kv.rbegin(); it != kv.rend(); ++it) l->v.push_back(cons(it->first, it->second));
+    return l;
+}
+inline size_t length(const pmt_t& p)
+{
+    if (auto l = dynamic_cast<const p_list*>(p.get())) return l->v.size();
+    if (auto d = dynamic_cast<const p_dict*>(p.get())) return d->kv.size();
+    if (auto c = dynamic_cast<const p_c32v*>(p.get())) return c->v.size();
+    if (auto b = dynamic_cast<const p_blob*>(p.get())) return b->v.size();
+    throw std::runtime_error("pmt: length of a non-sequence");
+}
+inline pmt_t nth(size_t n, const pmt_t& list) { return as<p_list>(list, "list").v.at(n); }
+inline bool is_null(const pmt_t& p) { return dynamic_cast<const p_nil*>(p.get()) != nullptr; }
 
 }  // namespace pmt

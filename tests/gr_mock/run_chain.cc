@@ -1,5 +1,7 @@
 // TEST INFRASTRUCTURE: plays the GNU Radio scheduler for the compiled block shells (gr-ieee80211_b200/gr/lib/
-// rx_blocks_impl.cc, built against the miniature runtime of tests/gr_mock/include): wires trigger -> sync -> signal[2] ->
+// rx_blocks_impl.cc, built against the miniature runtime of tests/gr_mock/include) -- and, linked as build/run_chain_ref
+// against the reference's own unmodified *_impl.cc objects (oracle/_ref, no GPU involved), for the reference's blocks, so
+// the two can be compared dump against dump: wires trigger -> sync -> signal[2] ->
 // demod[2] -> decode like examples/rx.grc / rx2.grc, feeds presiso's outputs and the capture from files, calls
 // general_work() with pseudo-random sizes until nothing moves, and dumps the published messages and all stream tags.
 //   run_chain NANT MUPOS MUGID SEED MAXCALL IFDEBUG INDIR OUTFILE
@@ -66,6 +68,9 @@ static bool call(gr::block& b, int maxCall, bool big)
     if (nout > 0) {
         noutput = (int)std::min<size_t>((size_t)cap, minAvail);
         if (noutput == 0 && (b.name() == "demod" || b.name() == "demod2")) noutput = cap;   // output space alone wakes a block too
+        // end of a finite capture: signal / demod size their work from ninput_items, so the closing rounds offer them the whole
+        // output space (the reference's demod needs noutput > nCBPS to finish the last symbols; oracle/ref_chain.cc does the same)
+        if (big && b.name() != "trigger" && b.name() != "sync") noutput = cap;
     }
     b.forecast(noutput, req);
     const int extra = big ? 0 : (int)(rnd() % 64u);

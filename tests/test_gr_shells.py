@@ -15,6 +15,7 @@ from __graft_entry__ import ROOT, load_pkg
 MOCK = os.path.join(ROOT, "tests", "gr_mock")
 EXE = os.path.join(MOCK, "build", "run_chain")
 EXE_RX = os.path.join(MOCK, "build", "run_rx")
+EXE_REF = os.path.join(MOCK, "build", "run_chain_ref")     # the same scheduler over the reference's unmodified blocks (CPU)
 
 
 def _build():
@@ -49,11 +50,14 @@ def test_rx_pybind_binding_compiles():
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-fsyntax-only"] + inc + [src])
 
 
-def _run(tmp_path, nant, x, x1=None, mupos=0, mugid=0, seed=1, max_call=4096, debug=0, exe=EXE):
-    pkg = load_pkg()
-    rx = pkg.Receiver(device=0)
-    preac, preconj = rx.presiso(x)
-    rx.close()
+def _run(tmp_path, nant, x, x1=None, mupos=0, mugid=0, seed=1, max_call=4096, debug=0, exe=EXE, presiso=None):
+    if presiso is None:
+        pkg = load_pkg()
+        rx = pkg.Receiver(device=0)
+        preac, preconj = rx.presiso(x)
+        rx.close()
+    else:
+        preac, preconj = presiso
     preac.tofile(tmp_path / "preac.f32")
     preconj.astype(np.complex64).tofile(tmp_path / "preconj.c64")
     x.astype(np.complex64).tofile(tmp_path / "sig.c64")
@@ -145,3 +149,70 @@ def test_rx_sink_block_equals_oracle(golden, tmp_path, nant, max_call):
     print([ln for ln in stdout.splitlines() if ln.startswith("run_rx:")])
     good = [s for s in stdout.splitlines() if s.startswith("ieee80211 decode, ") and " crc32 correct, " in s]
     assert len(good) == len(want)
+
+
+def _oracle_presiso(x):
+    n = x.size
+    preac, preconj = np.zeros(n, np.float32), np.zeros(2 * n, np.float32)
+    ol.oracle().orx_presiso(ol.c2f(x), n, preac, preconj)
+    return preac, preconj.view(np.complex64)
+
+
+@pytest.mark.skipif(not os.path.exists(EXE_REF) and not os.path.isdir("/root/reference/lib"), reason="reference block objects not built")
+def test_reference_blocks_under_the_mock_scheduler(golden, tmp_path):
+    """CPU: run_chain_ref = tests/gr_mock/run_chain.cc linked with the reference's own *_impl.cc objects; its messages are
+    the oracle's for two different call schedules (the dump the shells are compared with below)"""
+    _build()
+    x = _noisy(golden["frames_siso"]["iq"], 28.0, 21)
+    _, _, po = ol.rx_item(x, max_frames=40)
+    want = ol.split_pdus(po)
+    for seed, max_call in ((1, 4096), (7, 900)):
+        msgs, tags, _ = _run(tmp_path, 1, x, seed=seed, max_call=max_call, exe=EXE_REF, presiso=_oracle_presiso(x))
+        assert msgs == want and len(want) >= 30
+        assert sum(1 for (blk, _) in tags if blk == "signal") == 31 and sum(1 for (blk, _) in tags if blk == "demod") == 31
+
+
+def _same_tags(got, want):
+    """shell tags vs reference-block tags: same blocks / absolute offsets / keys; integers equal, floats to the parity gates"""
+    assert sorted(got) == sorted(want), (sorted(set(got) ^ set(want))[:8])
+    for k in want:
+        assert set(got[k]) == set(want[k]), (k, set(got[k]) ^ set(want[k]))
+        for key, w in want[k].items():
+            g = got[k][key]
+            if w.startswith("c32["):
+                assert g.split(":")[0] == w.split(":")[0]
+                a, b = float(g.split(":")[1]), float(w.split(":")[1])
+                assert abs(a - b) <= 2e-4 * max(abs(b), 1e-3), (k, key, g, w)
+            elif key in ("rad", "snr", "rssi", "cfo", "sssnr0", "sssnr1"):
+                a, b = float(g), float(w)
+                if np.isnan(b):
+                    assert np.isnan(a)
+                elif key == "rad":
+                    assert abs(a - b) <= 1e-6
+                elif key == "cfo":
+                    assert abs(a - b) <= 1e-6 * 3183098.9
+                else:
+                    assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (k, key, g, w)
+            else:
+                assert int(g) == int(w), (k, key, g, w)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "demod_impl.o")), reason="reference block objects not built")
+@pytest.mark.parametrize("nant,seed,max_call", [(1, 3, 4096), (1, 9, 1100), (2, 5, 4096)])
+def test_shells_equal_reference_blocks(golden, tmp_path, nant, seed, max_call):
+    """A/B under the same mock scheduler, same seed: the compiled shells (CUDA) against the reference's own unmodified blocks
+    (CPU) -- identical messages, and every stream tag at the identical absolute offset with the same keys and values"""
+    _build()
+    if nant == 1:
+        x, x1 = _noisy(golden["frames_siso"]["iq"], 28.0, 21), None
+    else:
+        g = golden["frames_mimo"]
+        x, x1 = _noisy(g["iq0"], 30.0, 13579), _noisy(g["iq1"], 30.0, 24680)
+    ps = _oracle_presiso(x)
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "gpu").mkdir()
+    rm, rt, _ = _run(tmp_path / "ref", nant, x, x1, seed=seed, max_call=max_call, exe=EXE_REF, presiso=ps)
+    gm, gt, _ = _run(tmp_path / "gpu", nant, x, x1, seed=seed, max_call=max_call, exe=EXE, presiso=ps)
+    assert gm == rm and len(rm) >= 16
+    _same_tags(gt, rt)
