@@ -169,8 +169,9 @@ struct c8b_blk {
     }
     int demod(int nant, const float* iq0, const float* iq1, int n, c8b_frame* f, const float* chan, std::vector<float>* llr)
     {
-        // soft bits of one frame: at most one symbol per 80 samples, 416 (one stream) / 832 (two streams) per symbol
-        const int64_t stride = std::max<int64_t>(((int64_t)f->nsamp / 80 + 1) * (nant == 2 ? 832 : 416), 1024);
+        // soft bits of one frame: a short-GI symbol takes 72 samples (the rule of llr_stride_for in ctx.cu), 416 (one stream) /
+        // 832 (two streams) soft bits per symbol
+        const int64_t stride = std::max<int64_t>(((int64_t)f->nsamp / 72 + 1) * (nant == 2 ? 832 : 416), 1024);
         llr->assign((size_t)stride, 0.f);
         const int64_t off = 0;
         const int32_t len = n;

@@ -20,6 +20,8 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
                         uint2* d_surv, int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram,
                         int64_t scram_stride, unsigned* d_counter, int grid, cudaStream_t st);
 int c8b_viterbi_max_grid(int num_sm);
+cudaError_t c8b_viterbi_prepare(void);       // per-device kernel attributes, set on the current device by c8b_create
+cudaError_t c8b_viterbi_tp_prepare(void);
 
 void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int maxLen, int64_t outBase,
                         float* preac, float2* preconj, uint32_t* mask, int maskStride, cudaStream_t st);

@@ -151,6 +151,8 @@ int c8b_create(const c8b_cfg* cfg, c8b_ctx** out)
     ctx->overlap = ctx->cfg.no_overlap == 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->numSM, cudaDevAttrMultiProcessorCount, ctx->device);
     if (ctx->cfg.chunk_items <= 0) ctx->cfg.chunk_items = c8b_viterbi_tp_wave(e == cudaSuccess && ctx->numSM > 0 ? ctx->numSM : 148);
+    if (e == cudaSuccess) e = c8b_viterbi_prepare();          // function attributes are per device: set on THIS context's device
+    if (e == cudaSuccess) e = c8b_viterbi_tp_prepare();
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_lut, sizeof(c8b_lut));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 64);
     if (e != cudaSuccess) { g_createErr = std::string("c8b_create: ") + cudaGetErrorString(e); delete ctx; return C8B_ERR_CUDA; }
@@ -593,17 +595,18 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
         rc = run_chunk(ctx, buf[k], (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, (c8b_frame*)ctx->frames.p,
                        (uint8_t*)ctx->pdu.p, pdu_stride, pl.base, buf1[k]);
         cudaEventRecord(freed[k], ctx->st);                       // the front end is the last reader of the staged IQ
-        if (rc == C8B_OK) {
+        if (rc == C8B_OK && er == cudaSuccess) {
             cudaStream_t sr = ctx->overlap ? ctx->stVit : ctx->st; // results follow the Viterbi pass of this chunk
-            cudaMemcpyAsync(frames + b * maxf, (c8b_frame*)ctx->frames.p + b * maxf, (size_t)(e - b) * maxf * sizeof(c8b_frame),
-                            cudaMemcpyDeviceToHost, sr);
-            cudaMemcpyAsync(pdu + b * maxf * pdu_stride, (uint8_t*)ctx->pdu.p + b * maxf * pdu_stride, (size_t)(e - b) * maxf * pdu_stride,
-                            cudaMemcpyDeviceToHost, sr);
+            er = cudaMemcpyAsync(frames + b * maxf, (c8b_frame*)ctx->frames.p + b * maxf, (size_t)(e - b) * maxf * sizeof(c8b_frame),
+                                 cudaMemcpyDeviceToHost, sr);
+            if (er == cudaSuccess)
+                er = cudaMemcpyAsync(pdu + b * maxf * pdu_stride, (uint8_t*)ctx->pdu.p + b * maxf * pdu_stride,
+                                     (size_t)(e - b) * maxf * pdu_stride, cudaMemcpyDeviceToHost, sr);
         }
     }
-    cudaStreamSynchronize(ctx->stCopy);
-    cudaStreamSynchronize(ctx->stVit);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->st);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stCopy);
+    const cudaError_t e3 = cudaStreamSynchronize(ctx->stVit), e4 = cudaStreamSynchronize(ctx->st);
+    if (e2 == cudaSuccess) e2 = e3 != cudaSuccess ? e3 : e4;
     for (int k = 0; k < 2; k++) { cudaEventDestroy(copied[k]); cudaEventDestroy(freed[k]); }
     if (rc) return rc;
     if (er != cudaSuccess || e2 != cudaSuccess) { ctx->err = std::string("c8b_rx_batch: ") + cudaGetErrorString(er != cudaSuccess ? er : e2); return C8B_ERR_CUDA; }

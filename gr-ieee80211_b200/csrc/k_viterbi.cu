@@ -516,6 +516,12 @@ k_viterbi(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int n
 
 int c8b_viterbi_max_grid(int num_sm) { return num_sm * C8B_VIT_BLOCKS; }
 
+// per-device opt-in to > 48 KB of dynamic shared memory (see c8b_viterbi_tp_prepare)
+cudaError_t c8b_viterbi_prepare(void)
+{
+    return cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NW * sizeof(WarpSmem) + 1024 + 768));
+}
+
 void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, uint2* d_surv,
                         int nwarps_alloc, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride,
                         unsigned* d_counter, int grid, cudaStream_t st)
@@ -525,8 +531,6 @@ void c8b_launch_viterbi(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, 
     if (grid > need) grid = need;
     if (grid * NW > nwarps_alloc) grid = nwarps_alloc / NW;
     const size_t smem = NW * sizeof(WarpSmem) + 1024 + 768;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st);
     k_viterbi<<<grid, NW * 32, smem, st>>>(d_lut, d_frames, nframes, d_llr, nllr, d_surv, d_pdu, pdu_stride, d_scram, scram_stride,
                                           d_counter);

@@ -583,6 +583,15 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
 
 }  // namespace
 
+static constexpr size_t tp_smem_bytes() { return sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2 + 1024 + 512; }
+
+// The dynamic shared-memory opt-in (> 48 KB) is a per-DEVICE function attribute: every context sets it on its own device
+// at c8b_create (two contexts on two GPUs in one process, block threads created concurrently).
+cudaError_t c8b_viterbi_tp_prepare(void)
+{
+    return cudaFuncSetAttribute(k_viterbi_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp_smem_bytes());
+}
+
 size_t c8b_viterbi_tp_scratch_bytes(int num_sm)
 {
     const size_t survPerCta = (size_t)(C8B_DECODE_T_MAX + CS + 2) * TPB;                 // uint2
@@ -603,9 +612,7 @@ void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframe
     if (grid > need) grid = need;
     uint2* surv = reinterpret_cast<uint2*>(d_scratch);
     uint32_t* words = reinterpret_cast<uint32_t*>(surv + (size_t)num_sm * C8B_TP_CTAS * survPerCta);
-    const size_t smem = sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2 + 1024 + 512;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_viterbi_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    const size_t smem = tp_smem_bytes();
     k_viterbi_tp<<<grid, TPB, smem, st>>>(d_lut, d_frames, nframes, d_llr, nllr, surv, words, survPerCta, wordsPerCta, d_pdu, pdu_stride,
                                         d_scram, scram_stride);
 }

@@ -95,12 +95,23 @@ class Receiver:
         self._ck(self.L.c8b_timing_read(self.h, ptr(ms), ptr(n), int(reset)), "c8b_timing_read")
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_cabi.K_NAMES)}
 
+    @staticmethod
+    def _items(off, length, nsamples):
+        """item table as the C ABI wants it, checked against the capture it indexes: the C ABI has no capture size argument,
+        so an item past the end of the array would be a host out-of-bounds read"""
+        off = np.ascontiguousarray(off, np.int64)
+        length = np.ascontiguousarray(length, np.int32)
+        if off.shape != length.shape or off.ndim != 1:
+            raise ValueError("off / length: two 1-D arrays of one size")
+        if off.size and (off.min() < 0 or length.min() < 0 or (off + length).max() > nsamples):
+            raise ValueError("item outside the capture (%d samples)" % nsamples)
+        return off, length
+
     # ---- whole chain --------------------------------------------------------------------------
     def rx_batch(self, iq, off, length, pdu_stride=4400):
         """iq: complex64 host array; item i = iq[off[i]:off[i]+length[i]].  Returns (frames, pdu)."""
         iqf = _c2f(iq)
-        off = np.ascontiguousarray(off, np.int64)
-        length = np.ascontiguousarray(length, np.int32)
+        off, length = self._items(off, length, iqf.size // 2)
         n, ns = off.size, off.size * self.max_frames
         frames = np.zeros(ns, FRAME_DTYPE)
         pdu = np.zeros(ns * pdu_stride, np.uint8)
@@ -110,9 +121,9 @@ class Receiver:
     def rx_batch2(self, iq0, iq1, off, length, pdu_stride=4400):
         """2x2: antenna 0 drives detection, both antennas are demodulated (signal2 + demod2)."""
         a, b = _c2f(iq0), _c2f(iq1)
-        assert a.size == b.size
-        off = np.ascontiguousarray(off, np.int64)
-        length = np.ascontiguousarray(length, np.int32)
+        if a.size != b.size:
+            raise ValueError("the two antennas' captures differ in length")
+        off, length = self._items(off, length, a.size // 2)
         n, ns = off.size, off.size * self.max_frames
         frames = np.zeros(ns, FRAME_DTYPE)
         pdu = np.zeros(ns * pdu_stride, np.uint8)
@@ -239,8 +250,7 @@ class Receiver:
 
     def detect(self, iq, off, length):
         iqf = _c2f(iq)
-        off = np.ascontiguousarray(off, np.int64)
-        length = np.ascontiguousarray(length, np.int32)
+        off, length = self._items(off, length, iqf.size // 2)
         n, ns = off.size, off.size * self.max_frames
         frames = np.zeros(ns, FRAME_DTYPE)
         chan = np.zeros(ns * 128, np.float32)
@@ -249,8 +259,7 @@ class Receiver:
 
     def demod(self, iq, off, length, frames, chan, llr_stride):
         iqf = _c2f(iq)
-        off = np.ascontiguousarray(off, np.int64)
-        length = np.ascontiguousarray(length, np.int32)
+        off, length = self._items(off, length, iqf.size // 2)
         n, ns = off.size, off.size * self.max_frames
         frames = np.ascontiguousarray(frames).copy()
         assert frames.size == ns
@@ -261,8 +270,9 @@ class Receiver:
 
     def demod2(self, iq0, iq1, off, length, frames, chan, llr_stride):
         a, b = _c2f(iq0), _c2f(iq1)
-        off = np.ascontiguousarray(off, np.int64)
-        length = np.ascontiguousarray(length, np.int32)
+        if a.size != b.size:
+            raise ValueError("the two antennas' captures differ in length")
+        off, length = self._items(off, length, a.size // 2)
         n, ns = off.size, off.size * self.max_frames
         frames = np.ascontiguousarray(frames).copy()
         assert frames.size == ns

@@ -153,8 +153,9 @@ int  c8b_rx_batch2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const i
                    c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
 /* Device-pointer entry points run on the ctx stream (created non-blocking): the caller must make sure d_iq is complete
  * (synchronise the producing stream) before calling.
- * as c8b_rx_batch_dev but results stay on the device (d_frames: nitems c8b_frame, d_pdu:
- * nitems*pdu_stride bytes); nothing is copied back and the call does not synchronise. */
+ * as c8b_rx_batch_dev but results stay on the device (d_frames: nitems*F c8b_frame records, d_pdu:
+ * nitems*F*pdu_stride bytes, F = cfg.max_frames -- both are cleared / written over their whole extent); nothing is
+ * copied back and the call does not synchronise. */
 int  c8b_rx_batch_dev_async(c8b_ctx* ctx, const float* d_iq, const int64_t* h_off, const int32_t* h_len, int nitems,
                             c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride);
 /* 2x2 with both antennas resident in device memory (same item table for both), results to host buffers */
