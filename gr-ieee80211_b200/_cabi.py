@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libc80211b200.so")
+# C8B_LIB: another build of the same library (kernel experiments: tools/build_variant.sh); default = the in-tree product
+LIB_PATH = os.environ.get("C8B_LIB") or os.path.join(HERE, "lib", "libc80211b200.so")
 
 K_NAMES = ("presiso", "detect", "header", "demod", "viterbi")
 

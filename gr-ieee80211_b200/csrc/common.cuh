@@ -37,7 +37,7 @@ void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1
                         c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st);
 void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf, int maxSym,
                        const c8b_frame* frames, const float2* w2, float* llr, cudaStream_t st);
-size_t c8b_viterbi_tp_scratch_bytes(int num_sm);
+size_t c8b_viterbi_tp_scratch_bytes(int num_sm, int nframes);
 void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, void* d_scratch,
                            int num_sm, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride, cudaStream_t st);
 void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,

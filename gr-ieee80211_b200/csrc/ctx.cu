@@ -289,7 +289,7 @@ static int launch_decode(c8b_ctx* ctx, c8b_frame* d_frames, int n, const float* 
                          uint8_t* d_scram, int64_t scram_stride, int grid, cudaStream_t st)
 {
     if (use_thread_per_frame(ctx, n)) {
-        EN(tp, c8b_viterbi_tp_scratch_bytes(ctx->numSM));
+        EN(tp, c8b_viterbi_tp_scratch_bytes(ctx->numSM, n));
         c8b_launch_viterbi_tp(ctx->d_lut, d_frames, n, d_llr, nllr, ctx->tp.p, ctx->numSM, d_pdu, pdu_stride, d_scram, scram_stride, st);
     } else {
         int r = ensure_surv(ctx);

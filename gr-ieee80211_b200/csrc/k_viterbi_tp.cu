@@ -72,197 +72,6 @@ __device__ __forceinline__ uint2 acs(const float (&m)[64], float (&n)[64], const
     return make_uint2(wlo, whi);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Packed forward pass (C8B_TP_PACKED = 1, NOT the default): the same add-compare-select in the same float32 operation order, with the
-// adds and the decision differences issued as sm_100 two-wide FADD2 (add.rn.f32x2: two independent IEEE adds, so every
-// sum is the bit the scalar form produces).  The kernel is bound by instruction issue, not by the FP32 pipe, so halving the
-// FADD count is what pays: 14 instructions per butterfly PAIR (4 FADD2 adds, 2 FADD2 differences, 4 FMNMX, 4 SHF) instead
-// of 18.
-//
-// The 64 metrics live in 32 aligned register pairs.  Layout L_q pairs the two states that differ in bit q.  With the input
-// in L_q (q >= 1) the butterflies k and k' = k | 1 << (q-1) read their even predecessors from ONE pair (2k, 2k') and their
-// odd predecessors from another (2k+1, 2k'+1), and their results (k, k') and (k+32, k'+32) are pairs of L_(q-1): the
-// layout walks 5 -> 4 -> 3 -> 2 -> 1 -> 0 for free.  In L_0 a pair holds both predecessors of one butterfly; that step
-// adds (m_even, m_odd) + (A, B) and + (B, A), compares inside the pairs and writes (k, k+32) = a pair of L_5 again.
-// Period 6 divides the 30-step staging chunk.  Branch-metric pairs: the code is linear, so class(k') = class(k) ^ delta_q
-// and a step needs just the four pairs (tab[x], tab[x ^ delta_q]).
-// MEASURED (one B200, 56832-frame wave, profiles/ncu_vtp_packed_r01.md): bit-exact (all decode / chain tests, 1,048,486 MPDUs of
-// the bench identical) and 242 instead of 290 instructions per trellis step, but SLOWER: 9.3 ms against 8.5 ms for the scalar
-// butterflies.  FADD2 issues only to the FMA-heavy sub-pipe and reads / writes 64-bit operands: issue-slot utilisation drops from
-// 75 % to 58 % behind dispatch stalls (0.57 per issue) and math-pipe throttle (0.78), and the 23 KB loop body adds
-// instruction-fetch stalls (0.32).  Kept behind the knob as the record of that experiment.
-// Decision words keep their natural bit order (state n -> bit n & 31 of word n >> 5), so survivors and traceback are
-// unchanged: q <= 3 shifts the sign bits in per group of 2^q butterflies, q = 4 / 5 fill two half-words and merge them with
-// one PRMT / one shift-or per word.
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ u64 swap2(u64 v) { float lo, hi; upk2(v, lo, hi); return pk2(hi, lo); }   // free: FADD2 operand swizzle .LO_HI
-__device__ __forceinline__ u64 max2(u64 a, u64 b)
-{
-    float a0, a1, b0, b1;
-    upk2(a, a0, a1); upk2(b, b0, b1);
-    return pk2(fmaxf(a0, b0), fmaxf(a1, b1));
-}
-__device__ __forceinline__ uint32_t push_sign(float d, uint32_t w) { return __funnelshift_l(__float_as_uint(d), w, 1); }
-
-__host__ __device__ constexpr int rm_bit(int s, int q) { return ((s >> (q + 1)) << q) | (s & ((1 << q) - 1)); }
-__host__ __device__ constexpr int ins_bit(int p, int q, int b) { return ((p >> q) << (q + 1)) | (b << q) | (p & ((1 << q) - 1)); }
-
-// butterflies k = ins_bit(J, Q-1, 0) and k | 1 << (Q-1) of a step whose input is in layout L_Q; TP[x] = (tab[x], tab[x ^ delta_Q])
-template <int Q, int J>
-__device__ __forceinline__ void bf_pair(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], u64& dLo, u64& dHi)
-{
-    constexpr int k = ins_bit(J, Q - 1, 0);
-    constexpr int c = bm_class(k);
-    constexpr bool zeroA = c == 0 && bm_class(1 << (Q - 1)) == 0;       // (0, 0): adding it is the identity
-    constexpr bool zeroB = (c ^ 3) == 0 && bm_class(1 << (Q - 1)) == 0;
-    const u64 E = P[rm_bit(2 * k, Q)], O = P[rm_bit(2 * k + 1, Q)];
-    const u64 aLo = zeroA ? E : add2(E, TP[c]), bLo = zeroB ? O : add2(O, TP[c ^ 3]);
-    const u64 aHi = zeroB ? E : add2(E, TP[c ^ 3]), bHi = zeroA ? O : add2(O, TP[c]);
-    dLo = sub2(aLo, bLo);                                               // sign set <=> the odd predecessor is strictly larger
-    dHi = sub2(aHi, bHi);
-    N[rm_bit(k, Q - 1)] = max2(aLo, bLo);
-    N[rm_bit(k + 32, Q - 1)] = max2(aHi, bHi);
-}
-
-// Q <= 3: groups of 2^Q butterflies, sign bits shifted in from the highest state down (natural order)
-template <int Q, int G, int I>
-struct GroupPairs {
-    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], float (&dl)[1 << Q], float (&dh)[1 << Q])
-    {
-        constexpr int H = 1 << (Q - 1);
-        u64 a, b;
-        bf_pair<Q, G * H + I>(P, N, TP, a, b);
-        upk2(a, dl[I], dl[I + H]);
-        upk2(b, dh[I], dh[I + H]);
-        GroupPairs<Q, G, I - 1>::run(P, N, TP, dl, dh);
-    }
-};
-template <int Q, int G>
-struct GroupPairs<Q, G, -1> {
-    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], float (&)[1 << Q], float (&)[1 << Q]) {}
-};
-template <int Q, int G>
-struct Groups {
-    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], uint32_t& wlo, uint32_t& whi)
-    {
-        float dl[1 << Q], dh[1 << Q];
-        GroupPairs<Q, G, (1 << (Q - 1)) - 1>::run(P, N, TP, dl, dh);
-#pragma unroll
-        for (int o = (1 << Q) - 1; o >= 0; o--) { wlo = push_sign(dl[o], wlo); whi = push_sign(dh[o], whi); }
-        Groups<Q, G - 1>::run(P, N, TP, wlo, whi);
-    }
-};
-template <int Q>
-struct Groups<Q, -1> {
-    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], uint32_t&, uint32_t&) {}
-};
-
-// Q = 4, 5: A collects the states with bit Q-1 set, B the others, both from the highest pair index down
-template <int Q, int J>
-struct Halves {
-    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TP)[4], uint32_t& aLo, uint32_t& bLo, uint32_t& aHi,
-                                               uint32_t& bHi)
-    {
-        u64 a, b;
-        float d0, d1;
-        bf_pair<Q, J>(P, N, TP, a, b);
-        upk2(a, d0, d1);
-        bLo = push_sign(d0, bLo); aLo = push_sign(d1, aLo);
-        upk2(b, d0, d1);
-        bHi = push_sign(d0, bHi); aHi = push_sign(d1, aHi);
-        Halves<Q, J - 1>::run(P, N, TP, aLo, bLo, aHi, bHi);
-    }
-};
-template <int Q>
-struct Halves<Q, -1> {
-    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], uint32_t&, uint32_t&, uint32_t&, uint32_t&) {}
-};
-
-// Q = 0: pair K holds (m[2K], m[2K+1]); TQ[c] = (tab[c], tab[c ^ 3]); result pair K of L_5 = states (K, K + 32)
-template <int K>
-struct Inner {
-    static __device__ __forceinline__ void run(const u64 (&P)[32], u64 (&N)[32], const u64 (&TQ)[4], uint32_t& wlo, uint32_t& whi)
-    {
-        constexpr int c = bm_class(K);
-        float eLo, oLo, oHi, eHi;
-        upk2(add2(P[K], TQ[c]), eLo, oLo);
-        upk2(add2(P[K], TQ[c ^ 3]), eHi, oHi);
-        wlo = push_sign(__fsub_rn(eLo, oLo), wlo);
-        whi = push_sign(__fsub_rn(eHi, oHi), whi);
-        N[K] = pk2(fmaxf(eLo, oLo), fmaxf(eHi, oHi));
-        Inner<K - 1>::run(P, N, TQ, wlo, whi);
-    }
-};
-template <>
-struct Inner<-1> {
-    static __device__ __forceinline__ void run(const u64 (&)[32], u64 (&)[32], const u64 (&)[4], uint32_t&, uint32_t&) {}
-};
-
-// The four branch-metric pairs TP[x] = (tab[x], tab[x ^ DELTA]) of a step, tab = {0, t1, t0, t1 + t0}, made from the pair
-// T01 = (t0, t1) as it comes out of shared memory with two-wide arithmetic only (no register moves: building them with
-// mov.b64 makes ptxas re-materialise a pair at nearly every use).  C01 = (0.0f, 1.0f) is read from the table blob, i.e. a
-// run-time value the assembler cannot re-materialise either.  x * 0 is +-0 and m + (+-0) == m, fma(x, 1, y) == x + y rounded
-// once, t0 + t1 == t1 + t0: every metric is the bit the scalar form produces.
-template <int DELTA>
-__device__ __forceinline__ void metric_pairs(const u64 T01, const u64 C01, u64 (&TP)[4])
-{
-    const u64 S01 = swap2(T01);                                         // (t1, t0)
-    if constexpr (DELTA == 3) {
-        const u64 T33 = add2(S01, T01);                                 // (t1 + t0, t0 + t1)
-        TP[0] = mul2(T33, C01);                                         // (0, t3)
-        TP[3] = swap2(TP[0]);
-        TP[1] = S01;
-        TP[2] = T01;
-    } else if constexpr (DELTA == 1) {
-        TP[0] = mul2(T01, C01);                                         // (0, t1)
-        TP[1] = swap2(TP[0]);
-        TP[2] = fma2(S01, C01, T01);                                    // (t1 * 0 + t0, t0 * 1 + t1) = (t0, t3)
-        TP[3] = swap2(TP[2]);
-    } else if constexpr (DELTA == 2) {
-        const u64 C10 = swap2(C01);
-        TP[2] = mul2(T01, C10);                                         // (t0, 0)
-        TP[0] = swap2(TP[2]);
-        TP[3] = fma2(S01, C10, T01);                                    // (t1 * 1 + t0, t0 * 0 + t1) = (t3, t1)
-        TP[1] = swap2(TP[3]);
-    } else {
-        float t0, t1;
-        upk2(T01, t0, t1);
-        TP[0] = 0;                                                      // never read: adding (0, 0) is skipped
-        TP[1] = pk2(t1, t1);
-        TP[2] = pk2(t0, t0);
-        TP[3] = add2(S01, T01);
-    }
-}
-
-// one trellis step, input in layout L_Q, output in L_(Q-1) (Q = 0: L_5)
-template <int Q>
-__device__ __forceinline__ uint2 acs2(const u64 (&P)[32], u64 (&N)[32], const u64 T01, const u64 C01)
-{
-    u64 TP[4];
-    uint32_t wlo = 0, whi = 0;
-    if constexpr (Q == 0) {
-        metric_pairs<3>(T01, C01, TP);                                  // (tab[c], tab[c ^ 3]) = (A, B) of butterfly class c
-        Inner<31>::run(P, N, TP, wlo, whi);
-    } else {
-        metric_pairs<bm_class(1 << (Q - 1))>(T01, C01, TP);
-        if constexpr (Q <= 3) {
-            Groups<Q, (32 >> Q) - 1>::run(P, N, TP, wlo, whi);
-        } else {
-            uint32_t aLo = 0, bLo = 0, aHi = 0, bHi = 0;
-            Halves<Q, 15>::run(P, N, TP, aLo, bLo, aHi, bHi);
-            if constexpr (Q == 5) { wlo = (aLo << 16) | bLo; whi = (aHi << 16) | bHi; }
-            else { wlo = __byte_perm(bLo, aLo, 0x5140); whi = __byte_perm(bHi, aHi, 0x5140); }
-        }
-    }
-    return make_uint2(wlo, whi);
-}
-
 // chunk-relative soft-bit indices of step s for code rate cr; -1 = punctured (same closed forms as k_viterbi.cu)
 __device__ __forceinline__ void depunc(int cr, int t, int& i0, int& i1)
 {
@@ -338,20 +147,116 @@ __device__ void emit_record_t(uint8_t* __restrict__ out, int& w, int cap, int& n
     npdu++;
 }
 
-#ifndef C8B_TP_PACKED
-#define C8B_TP_PACKED 0                        // 0: scalar butterflies (default, faster); 1: FADD2 forward pass (acs2) -- measured SLOWER, see below
-#endif
 #ifndef C8B_TP_CTAS
-#define C8B_TP_CTAS 3                          // CTAs per SM (168 registers per thread, no spills; 4 would spill the metrics)
+#define C8B_TP_CTAS 3                          // CTAs per SM (<= 170 registers per thread; 4 would spill the metrics)
 #endif
+
+// Shared memory per warp: two rings the lanes fill with cp.async a segment (SEG trellis steps) ahead of their use.
+//   llr  [32 lanes][ROWF2]  float2 (t0, t1) of step i at slot i % CS           (forward pass of the CURRENT frame group)
+//   surv [32 lanes][SROW]   uint4 = the decision words of steps (2p, 2p+1)      (traceback of the PREVIOUS frame group)
+constexpr int SEG = 10;                        // steps per staged segment (even; CS = 3 segments = every puncture period)
+constexpr int SROW = 17;                       // uint4 per lane row: 15 used; 17 * 16 B keeps the LDS.128 phases conflict-free
+struct WarpRings {
+    float2 llr[32 * ROWF2];
+    uint4 surv[32 * SROW];
+};
+static_assert(CS == 3 * SEG, "ring = three segments");
+
+// everything the traceback / packet assembly of a frame group needs again after the forward pass of the NEXT group
+// (re-read from the frame record instead of being held in registers across that pass)
+struct Done { int T, fmt, len, mcs, ampdu; };
+
+// ---------------- descramble (lib/decode_impl.cc:304-323), packetAssemble (:325-520) of one finished frame ----------------
+__device__ __noinline__ void finish_frame(c8b_frame* __restrict__ frames, int f, const uint32_t* __restrict__ crcTab, uint32_t* __restrict__ words,
+                                          uint8_t* __restrict__ pdu, int64_t pduStride, uint8_t* __restrict__ scram, int64_t scramStride)
+{
+    const c8b_frame* fr = frames + f;
+    const int T = fr->trellis, fmt = fr->format, len = fr->len, mcs = fr->mcs, ampdu = fr->ampdu;
+    const int nwords = (T + 31) >> 5;
+    // the traceback stores word j when it passes step 32 j + 6; a last word of fewer than 7 steps lies inside the six
+    // tail steps that lead into state 0: all zeros
+    if (32 * (nwords - 1) + 6 >= T) words[(size_t)(nwords - 1) * TPB] = 0u;
+    if (scram != nullptr) {
+        uint8_t* so = scram + (size_t)f * scramStride;
+        for (int i = 0; i < T && i < scramStride; i++) so[i] = (uint8_t)((words[(size_t)(i >> 5) * TPB] >> (i & 31)) & 1u);
+    }
+    {
+        const uint32_t w0 = words[0];
+        int st = 0;
+#pragma unroll
+        for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
+        uint32_t q[6];
+#pragma unroll
+        for (int wq = 0; wq < 5; wq++) {
+            uint32_t v = 0;
+            for (int b = 0; b < 32; b++) {
+                const int fb = ((st >> 6) ^ (st >> 3)) & 1;
+                st = ((st << 1) & 0x7e) | fb;
+                v |= (uint32_t)fb << b;
+            }
+            q[wq] = v;
+        }
+        q[5] = 0;
+        for (int w = 0; w < nwords; w++) {
+            uint32_t v = words[(size_t)w * TPB];
+            if (w == 0) v = (v ^ (q[0] << 7)) & ~0x7fu;
+            else {
+                const int o = (32 * w - 7) % 127, k = o >> 5;
+                const uint32_t lo = k == 0 ? q[0] : k == 1 ? q[1] : k == 2 ? q[2] : q[3];
+                const uint32_t hi = k == 0 ? q[1] : k == 1 ? q[2] : k == 2 ? q[3] : q[4];
+                v ^= __funnelshift_r(lo, hi, o & 31);
+            }
+            words[(size_t)w * TPB] = v;
+        }
+    }
+    uint8_t* out = pdu + (size_t)f * pduStride;
+    const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
+    int npdu = 0, w = 0;
+    if (fmt == C8B_F_VHT) {
+        int procd = 16;
+        if (procd < T) {
+            int bp = 2, tl = 0;                              // tl is NOT reset per subframe (:336)
+            while (true) {
+                procd += 32;
+                if (procd > T) break;
+                const int d0 = (int)get_byte(words, bp), d1 = (int)get_byte(words, bp + 1);
+                const int eof = d0 & 1;
+                tl |= ((d0 >> 2) & 1) << 12;
+                tl |= ((d0 >> 3) & 1) << 13;
+                tl |= (d0 >> 4) | (d1 << 4);
+                const int padded = (tl / 4 + ((tl % 4) != 0)) * 4;
+                procd += padded * 8;
+                if (procd > T) break;
+                bp += 4;
+                if (crc32_words(crcTab, words, bp, tl) == 558161692u) {
+                    emit_record_t(out, w, cap, npdu, fmt, tl, words, bp, tl, mcs);
+                    tl += 4;                                 // :415, carried into the next subframe
+                }
+                bp += padded;
+                if (eof) break;
+            }
+        }
+    } else if (!ampdu) {
+        if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
+            if (crc32_words(crcTab, words, 2, len) == 558161692u) emit_record_t(out, w, cap, npdu, fmt, len, words, 2, len, mcs);
+        }
+    }
+    frames[f].npdu = npdu; frames[f].pdu_bytes = w;
+}
+
+// Persistent CTAs: CTA b decodes the frame groups b, b + gridDim, ... (TPB frames each, one per thread).  The traceback
+// of a group does NOT follow its forward pass: it is folded, step for step, into the forward pass of the thread's NEXT
+// group (lib/decode_impl.cc:282-302 walks the survivors of the whole packet back from state 0 -- the walk is the same, it
+// just runs a group late), so that the survivor read-back streams from HBM under the butterflies instead of all CTAs
+// stalling on it together.  Survivors are double-buffered per CTA; the last group's traceback runs alone.
 __global__ void __launch_bounds__(TPB, C8B_TP_CTAS)
 k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
-             int64_t nllr, uint2* __restrict__ survAll, uint32_t* __restrict__ wordsAll, size_t survPerCta, size_t wordsPerCta,
+             int64_t nllr, uint8_t* __restrict__ scratch, size_t scratchPerCta, size_t survPerBuf,
              uint8_t* __restrict__ pdu, int64_t pduStride, uint8_t* __restrict__ scram, int64_t scramStride)
 {
     extern __shared__ __align__(16) uint8_t dynsm[];
-    float2 (*pairs)[2][32 * ROWF2] = reinterpret_cast<float2 (*)[2][32 * ROWF2]>(dynsm);   // [warp][buffer][frame row][step]
-    uint32_t* crcTab = reinterpret_cast<uint32_t*>(dynsm + sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2);
+    WarpRings* rings = reinterpret_cast<WarpRings*>(dynsm);
+    uint32_t* crcTab = reinterpret_cast<uint32_t*>(dynsm + sizeof(WarpRings) * (TPB / 32));
     uint32_t* relTab = crcTab + 256;                                 // [4 code rates][32]
     for (int i = threadIdx.x; i < 256; i += TPB) crcTab[i] = lut->crc32tab[i];
     for (int i = threadIdx.x; i < 128; i += TPB) {
@@ -361,229 +266,144 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint2* __restrict__ surv = survAll + (size_t)blockIdx.x * survPerCta + threadIdx.x;        // [t * TPB]
-    uint32_t* __restrict__ words = wordsAll + (size_t)blockIdx.x * wordsPerCta + threadIdx.x;  // [w * TPB]
+    float2* const lrow = rings[warp].llr + lane * ROWF2;
+    const uint4* const srow = rings[warp].surv + lane * SROW;
+    const uint32_t lrowS = (uint32_t)__cvta_generic_to_shared(lrow), srowS = (uint32_t)__cvta_generic_to_shared(srow);
+    // scratch of this CTA: two survivor buffers [pair * TPB] of uint4, then the decoded words [w * TPB]
+    uint4* const survCta = reinterpret_cast<uint4*>(scratch + (size_t)blockIdx.x * scratchPerCta) + threadIdx.x;
+    uint32_t* __restrict__ words = reinterpret_cast<uint32_t*>(scratch + (size_t)blockIdx.x * scratchPerCta + 2 * survPerBuf * sizeof(uint4)) + threadIdx.x;
 
-    for (int g = blockIdx.x; g * TPB < nframes; g += gridDim.x) {
+    int Tprev = 0, Pprev = 0, fprev = 0;                             // previous group: this thread's trellis length, the warp's padded length
+    for (int r = 0;; r++) {
+        const int g = blockIdx.x + r * gridDim.x;
         const int f = g * TPB + threadIdx.x;
-        // ---- this thread's frame ----
-        int T = 0, cr = 0, total = 0, fmt = 0, len = 0, mcs = 0, ampdu = 0;
+        // ---- this thread's frame of the current group (none past the end of the batch: T = 0) ----
+        int T = 0, cr = 0, total = 0;
         const float* llr = llrArena;
         if (f < nframes) {
             c8b_frame* fr = frames + f;
             const int status = fr->status;
             const int t = fr->trellis;
             const int64_t loff = fr->llr_off;
-            cr = fr->cr & 3; total = fr->total; fmt = fr->format; len = fr->len; mcs = fr->mcs; ampdu = fr->ampdu;
+            cr = fr->cr & 3; total = fr->total;
             fr->npdu = 0; fr->pdu_bytes = 0; fr->pdu_off = (int64_t)f * pduStride;
             if (status == C8B_ST_OK) {
-                if (len > C8B_DECODE_B_MAX || t > C8B_DECODE_T_MAX) fr->status = C8B_ST_DECODE_RANGE;     // lib/decode_impl.cc:93-97
+                if (fr->len > C8B_DECODE_B_MAX || t > C8B_DECODE_T_MAX) fr->status = C8B_ST_DECODE_RANGE;     // lib/decode_impl.cc:93-97
                 else if (t > 0 && total >= 0 && loff >= 0 && loff + total <= nllr) { T = t; llr = llrArena + loff; }
             }
         }
         const int lim = min(total, used_by(cr, T));                  // soft bits this packet consumes (pad steps read 0)
-        const int nraw = used_by(cr, CS);                            // soft bits per chunk of this frame
+        const int nraw = used_by(cr, CS);                            // soft bits per CS steps of this frame
         int Tmax = T;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
-        if (Tmax == 0) continue;                                     // warp-uniform
-        const int nch = (Tmax + CS - 1) / CS;
-
-        // stage chunk c: every lane copies the (t0,t1) pairs of ITS frame into its shared-memory row with cp.async
-        // (LDGSTS): the copies of the next chunk run under the butterflies of the current one and hold no registers.
-        // relTab[cr][s] = chunk-relative soft-bit indices of step s (i0 | i1 << 16, 0xffff = punctured).  A chunk is a whole
-        // number of puncture periods, so the punctured slots of a row are the same in every chunk: they are zeroed once per
-        // frame and never copied; a position past the end of the packet is a zero-fill copy (src-size 0).  The table entries
-        // of ten steps are fetched together (LDS.64) ahead of their twenty copies -- one dependent LDS per step stalled the
-        // warp for a fifth of the kernel.
-        {
-            float2* r0 = pairs[warp][0] + lane * ROWF2;
-            float2* r1 = pairs[warp][1] + lane * ROWF2;
-#pragma unroll
-            for (int i = 0; i < CS; i++) { r0[i] = make_float2(0.f, 0.f); r1[i] = make_float2(0.f, 0.f); }
-            __syncwarp();
+        if (Tmax == 0 && Pprev == 0) {                               // warp-uniform: nothing to run forward, nothing to walk back
+            if (g * TPB >= nframes) break;
+            continue;
         }
-        auto stage = [&](int c, int buf) {
-            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(pairs[warp][buf] + lane * ROWF2);
-            const float* __restrict__ lb = llr + (size_t)c * nraw;
-            const int rem = lim - c * nraw;                          // soft bits left from the start of this chunk
-            const uint2* __restrict__ rt = reinterpret_cast<const uint2*>(relTab + cr * 32);
+        const int Pcur = ((Tmax + SEG - 1) / SEG) * SEG;             // the warp's forward pass, padded to whole segments
+        const int nseg = max(Pcur, Pprev) / SEG;
+        uint4* __restrict__ svCur = survCta + (size_t)(r & 1) * survPerBuf;
+        const uint4* __restrict__ svPrev = survCta + (size_t)((r & 1) ^ 1) * survPerBuf;
+
+        // stage segment q: the (t0,t1) pairs of steps [q SEG, q SEG + SEG) of this lane's frame into its ring row (cp.async 4 B
+        // per soft bit; relTab[cr][s] = soft-bit indices of step s relative to the CS-step period, 0xffff = punctured: the
+        // punctured slots of a row are the same in every period, zeroed once per frame and never copied; past the end of the
+        // packet = zero-fill copy), and the decision-word pairs the traceback of the previous group walks during that segment
+        // (its steps Pprev - 1 - i, i in the segment: five 16-byte pairs, highest first).
+        if (Tmax > 0) {
 #pragma unroll
-            for (int b = 0; b < CS; b += 10) {
-                uint2 e[5];
+            for (int i = 0; i < CS; i++) lrow[i] = make_float2(0.f, 0.f);
+        }
+        auto stage = [&](int q) {
+            const int j = q % 3;
+            if (q * SEG < Pcur) {
+                const int c = q / 3;
+                const float* __restrict__ lb = llr + (size_t)c * nraw;
+                const int rem = lim - c * nraw;                      // soft bits left from the start of this period
+                const uint2* __restrict__ rt = reinterpret_cast<const uint2*>(relTab + cr * 32) + (SEG / 2) * j;
+                const uint32_t d0 = lrowS + 8 * SEG * j;
+                uint2 e[SEG / 2];
 #pragma unroll
-                for (int k = 0; k < 5; k++) e[k] = rt[b / 2 + k];
+                for (int k = 0; k < SEG / 2; k++) e[k] = rt[k];
 #pragma unroll
-                for (int k = 0; k < 10; k++) {
+                for (int k = 0; k < SEG; k++) {
                     const uint32_t ev = (k & 1) ? e[k >> 1].y : e[k >> 1].x;
                     const int i0 = (int)(ev & 0xffffu), i1 = (int)(ev >> 16);
                     const bool in0 = i0 < rem, in1 = i1 < rem;
                     if (i0 != 0xffff)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * (b + k)), "l"(lb + (in0 ? i0 : 0)), "r"(in0 ? 4 : 0));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * k), "l"(lb + (in0 ? i0 : 0)), "r"(in0 ? 4 : 0));
                     if (i1 != 0xffff)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * (b + k) + 4), "l"(lb + (in1 ? i1 : 0)), "r"(in1 ? 4 : 0));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * k + 4), "l"(lb + (in1 ? i1 : 0)), "r"(in1 ? 4 : 0));
                 }
+            }
+            if (q * SEG < Pprev) {
+                const uint4* __restrict__ src = svPrev + (size_t)((Pprev - q * SEG) / 2 - 1) * TPB;     // pair of steps (Pprev - q SEG - 2, .. - 1)
+                const uint32_t d1 = srowS + 16 * (SEG / 2) * j;
+#pragma unroll
+                for (int k = 0; k < SEG / 2; k++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1 + 16 * k), "l"(src - (size_t)k * TPB));
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        auto stage_wait = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); };
 
-        // ---------------- forward pass ----------------
-#if C8B_TP_PACKED
-        const u64 C01 = *reinterpret_cast<const u64*>(lut->pair01);    // (0.0f, 1.0f), see metric_pairs
-        u64 m[32], n[32];                                              // layout L_5 at every multiple of 6 steps: pair k = states (k, k + 32)
-#pragma unroll
-        for (int i = 0; i < 32; i++) m[i] = pk2(-1000000000000000.0f, -1000000000000000.0f);     // lib/decode_impl.cc:171-176
-        m[0] = pk2(0.0f, -1000000000000000.0f);
-        stage(0, 0);
-        stage_wait();
-        for (int c = 0; c < nch; c++) {
-            if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
-            const u64* __restrict__ row = reinterpret_cast<const u64*>(pairs[warp][c & 1] + lane * ROWF2);   // (t0, t1) per step
-            uint2* __restrict__ sv = surv + (size_t)c * CS * TPB;
-#pragma unroll 1
-            for (int s = 0; s < CS; s += 6) {
-                sv[(size_t)(s + 0) * TPB] = acs2<5>(m, n, row[s + 0], C01);
-                sv[(size_t)(s + 1) * TPB] = acs2<4>(n, m, row[s + 1], C01);
-                sv[(size_t)(s + 2) * TPB] = acs2<3>(m, n, row[s + 2], C01);
-                sv[(size_t)(s + 3) * TPB] = acs2<2>(n, m, row[s + 3], C01);
-                sv[(size_t)(s + 4) * TPB] = acs2<1>(m, n, row[s + 4], C01);
-                sv[(size_t)(s + 5) * TPB] = acs2<0>(n, m, row[s + 5], C01);
-            }
-            stage_wait();
-        }
-#else
         float m[64], n[64];
 #pragma unroll
         for (int i = 0; i < 64; i++) m[i] = -1000000000000000.0f;     // lib/decode_impl.cc:171-176
         m[0] = 0.0f;
-        stage(0, 0);
-        stage_wait();
-        for (int c = 0; c < nch; c++) {
-            if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
-            const float2* __restrict__ row = pairs[warp][c & 1] + lane * ROWF2;
-            uint2* __restrict__ sv = surv + (size_t)c * CS * TPB;
+        uint32_t h = 0;                                              // traceback: state in bits 0..5 (final state 0), decoded bits above
+        stage(0);
+        for (int q = 0; q < nseg; q++) {
+            stage(q + 1);                                            // (commits an empty group past the end)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");     // segment q has landed (each lane reads only what it copied)
+            const int j = q % 3;
+            const bool doF = q * SEG < Pcur, doT = q * SEG < Pprev;  // warp-uniform
+            const float2* __restrict__ row = lrow + SEG * j;
+            const uint4* __restrict__ sq = srow + (SEG / 2) * j;
+            uint4* __restrict__ sv = svCur + (size_t)(q * (SEG / 2)) * TPB;
+            int u = Pprev - 1 - q * SEG;                             // traceback step of the first iteration
 #pragma unroll 1
-            for (int s = 0; s < CS; s += 2) {
-                const uint2 w0 = acs(m, n, row[s]);
-                sv[(size_t)s * TPB] = w0;
-                const uint2 w1 = acs(n, m, row[s + 1]);
-                sv[(size_t)(s + 1) * TPB] = w1;
-            }
-            stage_wait();
-        }
-#endif
-
-        // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
-        {
-            uint32_t s = 0, acc = 0;
-            constexpr int TB = 32;                                   // decision words per block; the next block is in flight
-            uint2 wa[TB], wb[TB];
-            auto fetch = [&](uint2 (&w)[TB], int tb) {
-#pragma unroll
-                for (int k = 0; k < TB; k++) w[k] = (tb >= 0 && tb + k < T) ? surv[(size_t)(tb + k) * TPB] : make_uint2(0u, 0u);
-            };
-            auto walk = [&](const uint2 (&w)[TB], int tb) {
-#pragma unroll
-                for (int k = TB - 1; k >= 0; k--) {
-                    const int t = tb + k;
-                    if (t < T) {
-                        acc = (acc << 1) | (s >> 5);                 // decoded bit of step t = input bit of the state entered
-                        const uint32_t d = ((s & 32u ? w[k].y : w[k].x) >> (s & 31u)) & 1u;
-                        s = ((s & 31u) << 1) | d;
-                        if ((t & 31) == 0) { words[(size_t)(t >> 5) * TPB] = acc; acc = 0; }
+            for (int s = 0; s < SEG; s += 2) {
+                if (doF) {
+                    const uint2 w0 = acs(m, n, row[s]);
+                    const uint2 w1 = acs(n, m, row[s + 1]);
+                    sv[(size_t)(s >> 1) * TPB] = make_uint4(w0.x, w0.y, w1.x, w1.y);
+                }
+                if (doT) {
+                    // lib/decode_impl.cc:286-301: the predecessor of state s at step u is 2 (s & 31) + decision bit; the decoded bit
+                    // of step u is bit 5 of the state entered.  h = (h << 1) | decision keeps the state in its low six bits and
+                    // the decoded bits of the steps above u behind them: after step u = 32 j + 6, h IS word j of the packet.
+                    const uint4 d = sq[s >> 1];
+                    if (u < Tprev) {
+                        const uint32_t x = (h & 32u) ? d.w : d.z;
+                        h = (h << 1) | ((x >> (h & 31u)) & 1u);
+                        if ((u & 31) == 6) words[(size_t)(u >> 5) * TPB] = h;
                     }
-                }
-            };
-            int tb = ((Tmax - 1) / TB) * TB;
-            fetch(wa, tb);
-            for (; tb >= 0; tb -= 2 * TB) {
-                fetch(wb, tb - TB);
-                walk(wa, tb);
-                fetch(wa, tb - 2 * TB);
-                if (tb - TB >= 0) walk(wb, tb - TB);
-            }
-        }
-        if (T <= 0) continue;                                        // (lanes without a frame are done; no warp-level sync below)
-        const int nwords = (T + 31) >> 5;
-        if (scram != nullptr) {
-            uint8_t* so = scram + (size_t)f * scramStride;
-            for (int i = 0; i < T && i < scramStride; i++) so[i] = (uint8_t)((words[(size_t)(i >> 5) * TPB] >> (i & 31)) & 1u);
-        }
-
-        // ---------------- descramble (lib/decode_impl.cc:304-323) ----------------
-        {
-            const uint32_t w0 = words[0];
-            int st = 0;
-#pragma unroll
-            for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
-            uint32_t q[6];
-#pragma unroll
-            for (int wq = 0; wq < 5; wq++) {
-                uint32_t v = 0;
-                for (int b = 0; b < 32; b++) {
-                    const int fb = ((st >> 6) ^ (st >> 3)) & 1;
-                    st = ((st << 1) & 0x7e) | fb;
-                    v |= (uint32_t)fb << b;
-                }
-                q[wq] = v;
-            }
-            q[5] = 0;
-            for (int w = 0; w < nwords; w++) {
-                uint32_t v = words[(size_t)w * TPB];
-                if (w == 0) v = (v ^ (q[0] << 7)) & ~0x7fu;
-                else {
-                    const int o = (32 * w - 7) % 127, k = o >> 5;
-                    const uint32_t lo = k == 0 ? q[0] : k == 1 ? q[1] : k == 2 ? q[2] : q[3];
-                    const uint32_t hi = k == 0 ? q[1] : k == 1 ? q[2] : k == 2 ? q[3] : q[4];
-                    v ^= __funnelshift_r(lo, hi, o & 31);
-                }
-                words[(size_t)w * TPB] = v;
-            }
-        }
-
-        // ---------------- packetAssemble (lib/decode_impl.cc:325-520) ----------------
-        {
-            uint8_t* out = pdu + (size_t)f * pduStride;
-            const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
-            int npdu = 0, w = 0;
-            if (fmt == C8B_F_VHT) {
-                int procd = 16;
-                if (procd < T) {
-                    int bp = 2, tl = 0;                              // tl is NOT reset per subframe (:336)
-                    while (true) {
-                        procd += 32;
-                        if (procd > T) break;
-                        const int d0 = (int)get_byte(words, bp), d1 = (int)get_byte(words, bp + 1);
-                        const int eof = d0 & 1;
-                        tl |= ((d0 >> 2) & 1) << 12;
-                        tl |= ((d0 >> 3) & 1) << 13;
-                        tl |= (d0 >> 4) | (d1 << 4);
-                        const int padded = (tl / 4 + ((tl % 4) != 0)) * 4;
-                        procd += padded * 8;
-                        if (procd > T) break;
-                        bp += 4;
-                        if (crc32_words(crcTab, words, bp, tl) == 558161692u) {
-                            emit_record_t(out, w, cap, npdu, fmt, tl, words, bp, tl, mcs);
-                            tl += 4;                                 // :415, carried into the next subframe
-                        }
-                        bp += padded;
-                        if (eof) break;
+                    u--;
+                    if (u < Tprev) {
+                        const uint32_t x = (h & 32u) ? d.y : d.x;
+                        h = (h << 1) | ((x >> (h & 31u)) & 1u);
+                        if ((u & 31) == 6) words[(size_t)(u >> 5) * TPB] = h;
                     }
-                }
-            } else if (!ampdu) {
-                if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
-                    if (crc32_words(crcTab, words, 2, len) == 558161692u) emit_record_t(out, w, cap, npdu, fmt, len, words, 2, len, mcs);
+                    u--;
                 }
             }
-            frames[f].npdu = npdu; frames[f].pdu_bytes = w;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+        // ---- the previous group is walked back: descramble, A-MPDU walk, CRC-32, PDU records ----
+        if (Tprev > 0) finish_frame(frames, fprev, crcTab, words, pdu, pduStride, scram, scramStride);
+        Tprev = T; Pprev = Pcur; fprev = f;
+        if (Tmax == 0) Pprev = 0;
     }
 }
 
 }  // namespace
 
-static constexpr size_t tp_smem_bytes() { return sizeof(float2) * (TPB / 32) * 2 * 32 * ROWF2 + 1024 + 512; }
+static constexpr size_t tp_smem_bytes() { return sizeof(WarpRings) * (TPB / 32) + 1024 + 512; }
+// survivor pairs per buffer and CTA (uint4 = two steps), decoded words per CTA
+static constexpr size_t tp_surv_per_buf() { return (size_t)((C8B_DECODE_T_MAX + SEG) / 2 + 2) * TPB; }
+static constexpr size_t tp_words_per_cta() { return (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB; }
 
 // The dynamic shared-memory opt-in (> 48 KB) is a per-DEVICE function attribute: every context sets it on its own device
 // at c8b_create (two contexts on two GPUs in one process, block threads created concurrently).
@@ -592,12 +412,15 @@ cudaError_t c8b_viterbi_tp_prepare(void)
     return cudaFuncSetAttribute(k_viterbi_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp_smem_bytes());
 }
 
-size_t c8b_viterbi_tp_scratch_bytes(int num_sm)
+static constexpr size_t tp_scratch_per_cta() { return 2 * tp_surv_per_buf() * sizeof(uint4) + tp_words_per_cta() * sizeof(uint32_t); }
+static int tp_grid(int num_sm, int nframes)
 {
-    const size_t survPerCta = (size_t)(C8B_DECODE_T_MAX + CS + 2) * TPB;                 // uint2
-    const size_t wordsPerCta = (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB;        // uint32
-    return (size_t)num_sm * C8B_TP_CTAS * (survPerCta * sizeof(uint2) + wordsPerCta * sizeof(uint32_t));
+    const int full = num_sm * C8B_TP_CTAS, need = (nframes + TPB - 1) / TPB;
+    return need < full ? need : full;
 }
+
+// scratch for a launch over nframes frames: per resident CTA two survivor buffers + the decoded words
+size_t c8b_viterbi_tp_scratch_bytes(int num_sm, int nframes) { return (size_t)tp_grid(num_sm, nframes) * tp_scratch_per_cta(); }
 
 int c8b_viterbi_tp_wave(int num_sm) { return num_sm * C8B_TP_CTAS * TPB; }   // frames in one full wave
 
@@ -605,14 +428,7 @@ void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframe
                            int num_sm, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride, cudaStream_t st)
 {
     if (nframes <= 0) return;
-    const size_t survPerCta = (size_t)(C8B_DECODE_T_MAX + CS + 2) * TPB;
-    const size_t wordsPerCta = (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB;
-    int grid = num_sm * C8B_TP_CTAS;
-    const int need = (nframes + TPB - 1) / TPB;
-    if (grid > need) grid = need;
-    uint2* surv = reinterpret_cast<uint2*>(d_scratch);
-    uint32_t* words = reinterpret_cast<uint32_t*>(surv + (size_t)num_sm * C8B_TP_CTAS * survPerCta);
-    const size_t smem = tp_smem_bytes();
-    k_viterbi_tp<<<grid, TPB, smem, st>>>(d_lut, d_frames, nframes, d_llr, nllr, surv, words, survPerCta, wordsPerCta, d_pdu, pdu_stride,
-                                        d_scram, scram_stride);
+    k_viterbi_tp<<<tp_grid(num_sm, nframes), TPB, tp_smem_bytes(), st>>>(d_lut, d_frames, nframes, d_llr, nllr, reinterpret_cast<uint8_t*>(d_scratch),
+                                                                         tp_scratch_per_cta(), tp_surv_per_buf(), d_pdu, pdu_stride, d_scram,
+                                                                         scram_stride);
 }
