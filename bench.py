@@ -49,9 +49,29 @@ def cpu_model():
     return "unknown"
 
 
+def ncu_profile():
+    """the newest committed ncu --set full summary (profiles/ncu_rNN.json)"""
+    for name in ("ncu_r02.json", "ncu_r01.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def ncu_warp_instructions(kernel):
+    """warp instructions one launch of `kernel` executed in that capture (a property of the kernel on this workload), or None"""
+    try:
+        for k in json.load(open(ncu_profile())):
+            if k["kernel"] == kernel:
+                return float(str(k["warp_instructions"]).split()[0]), float(str(k.get("frames_per_launch", 56832)).split()[0])
+    except Exception:
+        pass
+    return None, None
+
+
 def ncu_traffic(kernel):
-    """dram read+write bytes per launch of `kernel` from the committed ncu --set full summary (profiles/ncu_r01.json), or None"""
-    p = os.path.join(ROOT, "profiles", "ncu_r01.json")
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full summary (profiles/ncu_rNN.json), or None"""
+    p = ncu_profile()
     try:
         for k in json.load(open(p)):
             if k["kernel"] == kernel:
@@ -59,6 +79,32 @@ def ncu_traffic(kernel):
                     x, u = sv.split()[:2]
                     return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
                 return val(k["dram_read"]) + val(k["dram_write"])
+    except Exception:
+        pass
+    return None
+
+
+def bind_near_gpu(torch, index):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the PCI device) BEFORE any pinned host buffer is
+    allocated: first-touch then places the staging memory on the GPU's own NUMA node, so N ranks do not all pull their
+    H2D traffic out of one socket's memory.  Returns a short description for the JSON line (None when sysfs says nothing)."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        cpus = open(base + "/local_cpulist").read().strip()
+        node = open(base + "/numa_node").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        ids &= set(os.sched_getaffinity(0))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return {"pci": bdf, "numa_node": int(node), "cpus": len(ids)}
     except Exception:
         pass
     return None
@@ -264,6 +310,9 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=4 * 56832, help="frames per host-buffer call of the e2e arm (4 pipeline chunks)")
     ap.add_argument("--chunk", type=int, default=56832, help="items per pipeline pass inside the library (3 CTAs x 148 SMs x 128 frames: one full wave of k_viterbi_tp)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --frames per GPU per step (the driver's default contract); strong: ONE batch of --frames frames per step, "
+                         "sharded over the ranks by item index (BASELINE configs[4]: the 1M-frame batch split over 1/2/4/8 GPUs)")
     ap.add_argument("--synth", default="tx", choices=["tx", "golden"],
                     help="tx: every frame unique, made on the device by the transmit synthesiser; golden: the generator's 16 frames replicated")
     args = ap.parse_args()
@@ -282,6 +331,7 @@ def main():
     pkg = load_pkg()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_near_gpu(torch, local)                               # pinned staging allocated below lands on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -295,6 +345,9 @@ def main():
         rx.load_lut_device(blob.data_ptr(), blob_n)
 
     nfr = args.frames
+    if args.scaling == "strong":                                     # rank r takes the contiguous shard r of the one batch
+        lo, hi = pkg.parallel.shard_range(args.frames, rank, world)
+        nfr = hi - lo
     psdu_sent = None
     if args.synth == "tx":
         iq, psdu_sent = make_batch_tx(torch, dev, pkg, rx, nfr, seed=rank)
@@ -395,18 +448,41 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_ok = int(((fr_np["status"] == 0) & (fr_np["npdu"] == 1)).sum())
+    fc32_records = fr_np[["status", "npdu", "pdu_bytes", "mcs", "len"]].copy()
+
+    # ---- the same through c8b_rx_batch_sc16: the capture in the radio's wire format (interleaved int16), half the H2D bytes ----
+    h16 = torch.empty((ne * ITEM, 2), dtype=torch.int16, pin_memory=True)
+    for b0 in range(0, ne * ITEM, 1 << 26):
+        e0 = min(ne * ITEM, b0 + (1 << 26))
+        h16[b0:e0].copy_(torch.view_as_real(iq[b0:e0]).mul(32768.0).round_().clamp_(-32768, 32767).to(torch.int16))
+    h16_np = h16.numpy()
+
+    def sc16_step():
+        for _ in range(calls):
+            rc = L.c8b_rx_batch_sc16(rx.h, C.c_void_p(h16_np.ctypes.data), pkg._cabi.ptr(off_e), pkg._cabi.ptr(ln_e), ne, C.c_void_p(fr_np.ctypes.data),
+                                     C.c_void_p(h_pdu.data_ptr()), PDU_STRIDE)
+            if rc:
+                raise RuntimeError("c8b_rx_batch_sc16: %d" % rc)
+
+    sc16_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sc16_step()
+    barrier()
+    sc16_s = time.perf_counter() - t0
+    sc16_ok = int(((fr_np["status"] == 0) & (fr_np["npdu"] == 1)).sum())
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks: max time, sums of work ----
-    cnt, tt = pkg.parallel.reduce_stats(torch, dist, world, dev, [frames_ok, nfr, nfr * ITEM, bytes_ok, nchk, e2e_ok], [ms, e2e_s * 1e3])
-    ms, e2e_ms = tt
-    frames_ok, frames_total, samples_total, bytes_ok, nchk, e2e_ok = cnt
+    cnt, tt = pkg.parallel.reduce_stats(torch, dist, world, dev, [frames_ok, nfr, nfr * ITEM, bytes_ok, nchk, e2e_ok, sc16_ok, calls * ne], [ms, e2e_s * 1e3, sc16_s * 1e3])
+    ms, e2e_ms, sc16_ms = tt
+    frames_ok, frames_total, samples_total, bytes_ok, nchk, e2e_ok, sc16_ok, e2e_frames_total = cnt
 
     if rank == 0:
         peak, peak_src = peaks()
         k = args.steps
         value = samples_total * k / (ms * 1e-3)
-        e2e_frames_total = calls * ne * world
         e2e_v = e2e_frames_total * ITEM * e2e_steps / (e2e_ms * 1e-3)
         nch = (nfr + args.chunk - 1) // args.chunk
         launches = (sum(v[1] for v in stage.values()) + nch) * k * world   # kernels launched inside the timed region, all ranks: 5 stage kernels + k_ndp per chunk
@@ -427,11 +503,22 @@ def main():
                 stages[name] = {"ms_per_launch": per, "launches": n, "share": tms / ms_serial, "alg_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
         vit = stages.get("viterbi", {})
         acs = per_launch_items * TRELLIS * 64 / (vit.get("ms_per_launch", 1) * 1e-3) if vit else None
+        # the bound that actually holds for the decode kernel: warp-instruction issue (one per cycle per SM sub-partition)
+        winst, wframes = ncu_warp_instructions("k_viterbi_tp")
+        issue = None
+        if vit and winst and clocks and clocks.get("sm_mhz"):
+            nsm = torch.cuda.get_device_properties(local).multi_processor_count
+            ach = winst * (per_launch_items / wframes) / (vit["ms_per_launch"] * 1e-3)
+            pk = nsm * 4 * clocks["sm_mhz"] * 1e6
+            issue = {"bound": "issue", "achieved": ach, "peak": pk, "unit": "warp-inst/s", "frac": ach / pk,
+                     "how": "warp instructions per launch from the committed ncu capture (%s) x frames, / the launch time measured here; "
+                            "peak = SMs x 4 schedulers x the SM clock sampled during the run" % os.path.basename(ncu_profile() or "none")}
         line = {
             "metric": "rx_iq_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": k, "warmup": args.warmup,
-            "ms_per_step": ms / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms / k, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "frames_per_s": frames_total * k / (ms * 1e-3),
-            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": nfr, "samples_per_item": ITEM, "chunk_items": args.chunk,
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": nfr, "frames_per_step_all_gpus": frames_total, "samples_per_item": ITEM,
+                       "chunk_items": args.chunk,
                        "l2": "inputs larger than L2 (%.1f GB of IQ per GPU per step)" % (nfr * ITEM * 8 / 1e9),
                        "input": ("every frame unique: random 1500-byte MPDUs modulated on the device by the transmit synthesiser (c8b_tx_batch_dev)"
                                  if args.synth == "tx" else "the reference generator's 16 frames replicated on the device"),
@@ -440,6 +527,11 @@ def main():
                     "d2h_bytes_per_step": calls * ne * (pkg.FRAME_DTYPE.itemsize + PDU_STRIDE), "frames_per_s": e2e_frames_total * e2e_steps / (e2e_ms * 1e-3),
                     "steps": e2e_steps, "calls_per_step": calls, "frames_per_call": ne, "frames_ok_last_call": e2e_ok,
                     "api": "c8b_rx_batch (host pinned buffers; H2D double-buffered per chunk, D2H of frame records + PDU bytes)"},
+            "e2e_sc16": {"value": e2e_frames_total * ITEM * e2e_steps / (sc16_ms * 1e-3), "unit": "samples/s",
+                         "h2d_bytes_per_step": calls * ne * ITEM * 4, "d2h_bytes_per_step": calls * ne * (pkg.FRAME_DTYPE.itemsize + PDU_STRIDE),
+                         "frames_ok_last_call": sc16_ok,
+                         "api": "c8b_rx_batch_sc16 (host pinned int16 I/Q = UHD sc16, widened on the device by x / 32768; 16-bit quantisation of the same batch)"},
+            "host_binding": numa,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_viterbi_tp", "achieved": vit.get("alg_GBps"), "peak": peak, "unit": "GB/s",
                          "frac": vit.get("frac_of_hbm_peak"), "traffic": ncu_traffic("k_viterbi_tp"), "peak_source": peak_src,
@@ -447,7 +539,7 @@ def main():
                                  "pipe (64-state add-compare-select per trellis step), not by HBM and not by tensor cores: see acs_per_s and "
                                  "profiles/; its DRAM traffic above the algorithmic bytes is the survivor memory of the full traceback "
                                  "(8 B per trellis step written and read back).  The HBM-streaming kernel is 'demod' in stages.",
-                         "acs_per_s": acs},
+                         "acs_per_s": acs, "issue": issue},
             "stages": stages,
             "stages_note": "per-kernel times from one extra single-stream pass (%.1f ms/step); the timed steps overlap k_viterbi of "
                            "chunk k with the front end of chunk k+1 on a second stream" % ms_serial,

@@ -51,7 +51,7 @@ assert TXFRAME_DTYPE.itemsize == C.sizeof(C8bTxFrame)
 
 class C8bCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("chunk_items", C.c_int32), ("max_item_len", C.c_int32), ("max_frames", C.c_int32),
-                ("mupos", C.c_int32), ("mugid", C.c_int32), ("no_overlap", C.c_int32), ("decode_mode", C.c_int32), ("frontend_mode", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("mupos", C.c_int32), ("mugid", C.c_int32), ("no_overlap", C.c_int32), ("decode_mode", C.c_int32), ("frontend_mode", C.c_int32), ("mmse", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 # every symbol include/c80211b200.h declares: (name, restype, argtypes)
@@ -68,6 +68,7 @@ SYMBOLS = [
     ("c8b_lut_load", _i, [_vp, _vp, _sz]),
     ("c8b_lut_load_dev", _i, [_vp, _vp, _sz]),
     ("c8b_rx_batch", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
+    ("c8b_rx_batch_sc16", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch2", _i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch_dev", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
     ("c8b_rx_batch_dev_async", _i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i64]),
@@ -80,6 +81,8 @@ SYMBOLS = [
     ("c8b_tx_batch", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _i64]),
     ("c8b_tx_batch_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _i64]),
     ("c8b_tx_random_psdu_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_uint64]),
+    ("c8b_tx_udp_parse", _i, [_vp, _i, _vp, _vp]),
+    ("c8b_tx_from_udp", _i, [_vp, _vp, _vp, _vp, _i, _i, C.c_float, _i, _vp, _i64, _vp, _vp]),
     ("c8b_timing_enable", _i, [_vp, _i]),
     ("c8b_timing_read", _i, [_vp, _vp, _vp, _i]),
     ("c8b_presiso", _i, [_vp, _vp, _i64, _vp, _vp]),

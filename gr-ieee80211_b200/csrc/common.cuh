@@ -25,6 +25,7 @@ cudaError_t c8b_viterbi_tp_prepare(void);
 
 void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int maxLen, int64_t outBase,
                         float* preac, float2* preconj, uint32_t* mask, int maskStride, cudaStream_t st);
+void c8b_launch_sc16_to_fc32(const short2* in, float2* out, int64_t n, cudaStream_t st);
 void c8b_launch_trigger(const float* preac, int64_t n, uint8_t* out, cudaStream_t st);
 void c8b_launch_detect(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                        int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
@@ -34,7 +35,9 @@ void c8b_launch_header(const c8b_lut* lut, const float2* iq, const int64_t* d_of
 void c8b_launch_demod(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int maxSym, const c8b_frame* frames,
                       const float2* hinv, float* llr, cudaStream_t st);
 void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf,
-                        c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st);
+                        int mmse, c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st);
+void c8b_launch_header2_w(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf, int mmse,
+                          c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st);
 void c8b_launch_demod2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf, int maxSym,
                        const c8b_frame* frames, const float2* w2, float* llr, cudaStream_t st);
 size_t c8b_viterbi_tp_scratch_bytes(int num_sm, int nframes);

@@ -6,6 +6,8 @@
 #include <vector>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
+
 #include "common.cuh"
 
 struct DevBuf {
@@ -25,7 +27,7 @@ struct c8b_ctx {
     bool lutLoaded = false;
     unsigned* d_counter = nullptr;
     // scratch (grown on demand)
-    DevBuf iq, iq1, mask, llrB, tp, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram;
+    DevBuf iq, iqf, iq1, mask, llrB, tp, preac, preconj, trig, off, len, frames, chan, hinv, w2, llr, surv, pdu, scram;
     int survWarps = 0;
     // live-stream session (c8b_stream_*): a device-resident window of the capture, ping-pong compacted
     struct Stream {
@@ -42,6 +44,14 @@ struct c8b_ctx {
     DevBuf cand;                // candidate records of the multi-frame detect path
     DevBuf txf, txplan, txpsdu, txiq;   // transmit synthesiser: descriptors, plans, staged PSDU bytes / samples
     c8b_scan* scanDev = nullptr;   // non-null while run_chunk serves a stream window
+    // item table (off / len) resident on the device: a pinned host mirror of what ctx->off / ctx->len hold for items
+    // [tabLo, tabHi), so that a batch call with an unchanged table (a bench step, a monitor re-scanning the same arena)
+    // uploads nothing, and a changed slice goes up asynchronously right before the chunk that needs it
+    int64_t* tabOff = nullptr;
+    int32_t* tabLen = nullptr;
+    size_t tabCap = 0;
+    int tabLo = 0, tabHi = 0;
+    cudaEvent_t evTab = nullptr;
     // timing
     bool timing = false;
     double ms[C8B_K_COUNT] = { 0 };
@@ -90,16 +100,25 @@ static cudaEvent_t ev_get(c8b_ctx* ctx)
     cudaEventCreate(&e);
     return e;
 }
+// One stage of the chain (tracing): an NVTX range around the launches -- the five ranges presiso / detect /
+// header / demod / viterbi are what a timeline shows per chunk -- and, when timing is on, a CUDA event pair on the stream.
+static const char* const kStageName[C8B_K_COUNT] = { "c8b presiso", "c8b detect (trigger+sync+signal)", "c8b header", "c8b demod", "c8b viterbi" };
 struct StageTimer {
     c8b_ctx* ctx; int k; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
     StageTimer(c8b_ctx* c, int kk, cudaStream_t ss = nullptr) : ctx(c), k(kk), s(ss ? ss : c->st)
     {
+        nvtxRangePushA(kStageName[k]);
         if (ctx->timing) { a = ev_get(ctx); b = ev_get(ctx); cudaEventRecord(a, s); }
     }
     ~StageTimer()
     {
         if (ctx->timing) { cudaEventRecord(b, s); ctx->pending.push_back({ k, a, b }); }
+        nvtxRangePop();
     }
+};
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 static void timing_collect(c8b_ctx* ctx)
 {
@@ -169,12 +188,15 @@ void c8b_destroy(c8b_ctx* ctx)
     for (auto e : ctx->evPool) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) { if (ctx->evFront[k]) cudaEventDestroy(ctx->evFront[k]); if (ctx->evVit[k]) cudaEventDestroy(ctx->evVit[k]); }
     if (ctx->stVit) cudaStreamDestroy(ctx->stVit);
-    DevBuf* bufs[] = { &ctx->iq, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->tp, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
+    DevBuf* bufs[] = { &ctx->iq, &ctx->iqf, &ctx->iq1, &ctx->w2, &ctx->mask, &ctx->llrB, &ctx->tp, &ctx->preac, &ctx->preconj, &ctx->trig, &ctx->off, &ctx->len, &ctx->frames, &ctx->chan,
                        &ctx->hinv, &ctx->llr, &ctx->surv, &ctx->pdu, &ctx->scram, &ctx->scan, &ctx->sw[0][0], &ctx->sw[0][1],
                        &ctx->sw[1][0], &ctx->sw[1][1], &ctx->txf, &ctx->txplan, &ctx->txpsdu, &ctx->txiq, &ctx->cand };
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->tabOff) cudaFreeHost(ctx->tabOff);
+    if (ctx->tabLen) cudaFreeHost(ctx->tabLen);
+    if (ctx->evTab) cudaEventDestroy(ctx->evTab);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     if (ctx->stCopy) cudaStreamDestroy(ctx->stCopy);
     delete ctx;
@@ -378,6 +400,7 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
                      const int32_t* h_len, int b, int e, c8b_frame* d_frames, uint8_t* d_pdu, int64_t pdu_stride, int64_t iqShift,
                      const float2* d_iq1 = nullptr)
 {
+    NvtxRange chunkRange("c8b chunk");
     const int n = e - b, maxf = ctx->cfg.max_frames;
     const size_t ns = (size_t)n * maxf;                          // frame slots of this chunk
     const ChunkPlan pl = plan(h_off + b, h_len + b, n);
@@ -424,8 +447,9 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     {
         StageTimer tm(ctx, C8B_K_HEADER);
         if (iq1)
-            c8b_launch_header2(ctx->d_lut, iq, iq1, d_off + b, n, maxf, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
-                               (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llrStride, ctx->st);
+            (ctx->cfg.frontend_mode == 1 ? c8b_launch_header2 : c8b_launch_header2_w)(
+                ctx->d_lut, iq, iq1, d_off + b, n, maxf, ctx->cfg.mmse, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
+                (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llrStride, ctx->st);
         else
             (ctx->cfg.frontend_mode == 1 ? c8b_launch_header : c8b_launch_header_w)(
                 ctx->d_lut, iq, d_off + b, n, maxf, ctx->cfg.mupos, d_frames + (size_t)b * maxf, (const float2*)ctx->chan.p,
@@ -469,8 +493,40 @@ static void join_viterbi(c8b_ctx* ctx)
     cudaStreamWaitEvent(ctx->st, ctx->evVit[1], 0);
 }
 
+// items [b, e) of the caller's table -> ctx->off / ctx->len at the same indices, unless the mirror says they are there already
+static int upload_items_range(c8b_ctx* ctx, const int64_t* off, const int32_t* len, int n, int b, int e)
+{
+    if ((size_t)n > ctx->tabCap || ctx->off.cap < (size_t)n * sizeof(int64_t) || ctx->len.cap < (size_t)n * sizeof(int32_t)) {
+        if (ctx->evTab) cudaEventSynchronize(ctx->evTab);
+        EN(off, (size_t)n * sizeof(int64_t));
+        EN(len, (size_t)n * sizeof(int32_t));
+        if (ctx->tabOff) cudaFreeHost(ctx->tabOff);
+        if (ctx->tabLen) cudaFreeHost(ctx->tabLen);
+        ctx->tabOff = nullptr; ctx->tabLen = nullptr; ctx->tabCap = 0; ctx->tabLo = ctx->tabHi = 0;
+        const size_t cap = (size_t)n + (size_t)n / 8 + 64;
+        CK(cudaHostAlloc((void**)&ctx->tabOff, cap * sizeof(int64_t), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&ctx->tabLen, cap * sizeof(int32_t), cudaHostAllocDefault));
+        ctx->tabCap = cap;
+        if (!ctx->evTab) CK(cudaEventCreateWithFlags(&ctx->evTab, cudaEventDisableTiming));
+    }
+    const size_t m = (size_t)(e - b);
+    if (ctx->tabLo <= b && e <= ctx->tabHi && memcmp(ctx->tabOff + b, off + b, m * sizeof(int64_t)) == 0 &&
+        memcmp(ctx->tabLen + b, len + b, m * sizeof(int32_t)) == 0)
+        return C8B_OK;
+    cudaEventSynchronize(ctx->evTab);                              // an earlier upload may still be reading the mirror
+    memcpy(ctx->tabOff + b, off + b, m * sizeof(int64_t));
+    memcpy(ctx->tabLen + b, len + b, m * sizeof(int32_t));
+    CK(cudaMemcpyAsync((int64_t*)ctx->off.p + b, ctx->tabOff + b, m * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync((int32_t*)ctx->len.p + b, ctx->tabLen + b, m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaEventRecord(ctx->evTab, ctx->st));
+    if (b <= ctx->tabHi && e >= ctx->tabLo && ctx->tabHi > ctx->tabLo) { if (b < ctx->tabLo) ctx->tabLo = b; if (e > ctx->tabHi) ctx->tabHi = e; }
+    else { ctx->tabLo = b; ctx->tabHi = e; }
+    return C8B_OK;
+}
+
 static int upload_items(c8b_ctx* ctx, const int64_t* off, const int32_t* len, int n)
 {
+    ctx->tabLo = ctx->tabHi = 0;                                   // the staged entry points overwrite the table: the mirror is void
     EN(off, (size_t)n * sizeof(int64_t));
     EN(len, (size_t)n * sizeof(int32_t));
     CK(cudaMemcpyAsync(ctx->off.p, off, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
@@ -489,11 +545,11 @@ static int rx_batch_dev_async2(c8b_ctx* ctx, const float* d_iq, const float* d_i
     if (nitems == 0) return C8B_OK;
     CK(cudaSetDevice(ctx->device));
     if ((r = check_items(ctx, off, len, nitems))) return r;
-    if ((r = upload_items(ctx, off, len, nitems))) return r;
     CK(cudaMemsetAsync(d_frames, 0, (size_t)nitems * ctx->cfg.max_frames * sizeof(c8b_frame), ctx->st));
     const int cs = ctx->cfg.chunk_items;
     for (int b = 0; b < nitems; b += cs) {
         const int e = b + cs < nitems ? b + cs : nitems;
+        if ((r = upload_items_range(ctx, off, len, nitems, b, e))) return r;
         r = run_chunk(ctx, (const float2*)d_iq, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, d_frames, d_pdu,
                       pdu_stride, 0, (const float2*)d_iq1);
         if (r) return r;
@@ -544,16 +600,19 @@ int c8b_rx_batch_dev(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const 
 
 // Host IQ: chunks are staged into two device buffers on the copy stream while the previous chunk is
 // processed on the compute stream; results of each chunk go back as soon as its Viterbi kernel ends.
-static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems,
+// sc16 = 1: h_iq holds interleaved int16 (I, Q) pairs -- the wire format of a USRP / UHD stream (sc16), half the bytes of
+// fc32 over PCIe; each chunk is widened on the device to exactly the floats UHD's own converter hands the reference
+// (x * (1 / 32768)) into one fc32 buffer the front end reads (the widening of chunk k+1 follows the front end of chunk k
+// on the compute stream, so one buffer is enough; the raw chunks are double-buffered like the fc32 ones).
+static int rx_batch_host(c8b_ctx* ctx, const void* h_iq, const float* h_iq1, int sc16, const int64_t* off, const int32_t* len, int nitems,
                          c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride)
 {
-    if (!ctx || !h_iq || !off || !len || nitems < 0 || !frames || !pdu || pdu_stride <= 0) return C8B_ERR_ARG;
+    if (!ctx || !h_iq || !off || !len || nitems < 0 || !frames || !pdu || pdu_stride <= 0 || (sc16 && h_iq1)) return C8B_ERR_ARG;
     int r = need_lut(ctx);
     if (r) return r;
     if (nitems == 0) return C8B_OK;
     CK(cudaSetDevice(ctx->device));
     if ((r = check_items(ctx, off, len, nitems))) return r;
-    if ((r = upload_items(ctx, off, len, nitems))) return r;
     const size_t maxf = (size_t)ctx->cfg.max_frames;
     EN(frames, (size_t)nitems * maxf * sizeof(c8b_frame));
     EN(pdu, (size_t)nitems * maxf * pdu_stride);
@@ -567,10 +626,13 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
         const ChunkPlan pl = plan(off + b, len + b, e - b);
         if (pl.end - pl.base > maxSpan) maxSpan = pl.end - pl.base;
     }
-    EN(iq, (size_t)2 * (maxSpan + 16) * sizeof(float2));
-    if (h_iq1) EN(iq1, (size_t)2 * (maxSpan + 16) * sizeof(float2));
-    float2* buf[2] = { (float2*)ctx->iq.p, (float2*)ctx->iq.p + (maxSpan + 16) };
-    float2* buf1[2] = { h_iq1 ? (float2*)ctx->iq1.p : nullptr, h_iq1 ? (float2*)ctx->iq1.p + (maxSpan + 16) : nullptr };
+    const size_t sampBytes = sc16 ? sizeof(short2) : sizeof(float2);
+    const int64_t slot = (maxSpan + 16 + 3) & ~(int64_t)3;        // samples per staging buffer (16-byte multiples for sc16 too)
+    EN(iq, (size_t)2 * slot * sampBytes);
+    if (sc16) EN(iqf, (size_t)slot * sizeof(float2));
+    if (h_iq1) EN(iq1, (size_t)2 * slot * sizeof(float2));
+    char* buf[2] = { (char*)ctx->iq.p, (char*)ctx->iq.p + (size_t)slot * sampBytes };
+    float2* buf1[2] = { h_iq1 ? (float2*)ctx->iq1.p : nullptr, h_iq1 ? (float2*)ctx->iq1.p + slot : nullptr };
     cudaEvent_t copied[2], freed[2];
     for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming); }
     int rc = C8B_OK;
@@ -578,7 +640,7 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
         const int b = c * cs, e = b + cs < nitems ? b + cs : nitems, k = c & 1;
         const ChunkPlan pl = plan(off + b, len + b, e - b);
         if (c >= 2) cudaStreamWaitEvent(ctx->stCopy, freed[k], 0);
-        cudaError_t er = cudaMemcpyAsync(buf[k], reinterpret_cast<const float2*>(h_iq) + pl.base, (size_t)(pl.end - pl.base) * sizeof(float2),
+        cudaError_t er = cudaMemcpyAsync(buf[k], reinterpret_cast<const char*>(h_iq) + (size_t)pl.base * sampBytes, (size_t)(pl.end - pl.base) * sampBytes,
                                          cudaMemcpyHostToDevice, ctx->stCopy);
         if (h_iq1 && er == cudaSuccess)
             er = cudaMemcpyAsync(buf1[k], reinterpret_cast<const float2*>(h_iq1) + pl.base, (size_t)(pl.end - pl.base) * sizeof(float2),
@@ -592,9 +654,16 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
         if (c + 1 < nchunks) er = stage(c + 1);
         const ChunkPlan pl = plan(off + b, len + b, e - b);
         cudaStreamWaitEvent(ctx->st, copied[k], 0);
-        rc = run_chunk(ctx, buf[k], (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, (c8b_frame*)ctx->frames.p,
-                       (uint8_t*)ctx->pdu.p, pdu_stride, pl.base, buf1[k]);
-        cudaEventRecord(freed[k], ctx->st);                       // the front end is the last reader of the staged IQ
+        const float2* src = reinterpret_cast<const float2*>(buf[k]);
+        if (sc16) {
+            c8b_launch_sc16_to_fc32(reinterpret_cast<const short2*>(buf[k]), (float2*)ctx->iqf.p, pl.end - pl.base, ctx->st);
+            cudaEventRecord(freed[k], ctx->st);                   // the widening is the last reader of the raw chunk
+            src = (const float2*)ctx->iqf.p;
+        }
+        rc = upload_items_range(ctx, off, len, nitems, b, e);
+        if (rc == C8B_OK) rc = run_chunk(ctx, src, (const int64_t*)ctx->off.p, (const int32_t*)ctx->len.p, off, len, b, e, (c8b_frame*)ctx->frames.p,
+                                         (uint8_t*)ctx->pdu.p, pdu_stride, pl.base, buf1[k]);
+        if (!sc16) cudaEventRecord(freed[k], ctx->st);            // the front end is the last reader of the staged IQ
         if (rc == C8B_OK && er == cudaSuccess) {
             cudaStream_t sr = ctx->overlap ? ctx->stVit : ctx->st; // results follow the Viterbi pass of this chunk
             er = cudaMemcpyAsync(frames + b * maxf, (c8b_frame*)ctx->frames.p + b * maxf, (size_t)(e - b) * maxf * sizeof(c8b_frame),
@@ -616,14 +685,20 @@ static int rx_batch_host(c8b_ctx* ctx, const float* h_iq, const float* h_iq1, co
 int c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, uint8_t* pdu,
                  int64_t pdu_stride)
 {
-    return rx_batch_host(ctx, h_iq, nullptr, off, len, nitems, frames, pdu, pdu_stride);
+    return rx_batch_host(ctx, h_iq, nullptr, 0, off, len, nitems, frames, pdu, pdu_stride);
+}
+
+int c8b_rx_batch_sc16(c8b_ctx* ctx, const int16_t* h_iq, const int64_t* off, const int32_t* len, int nitems, c8b_frame* frames, uint8_t* pdu,
+                      int64_t pdu_stride)
+{
+    return rx_batch_host(ctx, h_iq, nullptr, 1, off, len, nitems, frames, pdu, pdu_stride);
 }
 
 int c8b_rx_batch2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems,
                   c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride)
 {
     if (!h_iq1) return C8B_ERR_ARG;
-    return rx_batch_host(ctx, h_iq0, h_iq1, off, len, nitems, frames, pdu, pdu_stride);
+    return rx_batch_host(ctx, h_iq0, h_iq1, 0, off, len, nitems, frames, pdu, pdu_stride);
 }
 
 // ---- staged entry points (host buffers) -----------------------------------------------------------
@@ -810,8 +885,9 @@ int c8b_demod2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64
     const float2* iq1 = (const float2*)ctx->iq1.p - pl.base;
     {
         StageTimer tm(ctx, C8B_K_HEADER);
-        c8b_launch_header2(ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, maxf, (c8b_frame*)ctx->frames.p, (const float2*)ctx->chan.p,
-                           (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llr_stride, ctx->st);
+        (ctx->cfg.frontend_mode == 1 ? c8b_launch_header2 : c8b_launch_header2_w)(
+            ctx->d_lut, iq, iq1, (const int64_t*)ctx->off.p, nitems, maxf, ctx->cfg.mmse, (c8b_frame*)ctx->frames.p, (const float2*)ctx->chan.p,
+            (float2*)ctx->hinv.p, (float2*)ctx->w2.p, llr_stride, ctx->st);
     }
     {
         StageTimer tm(ctx, C8B_K_DEMOD);
@@ -1067,6 +1143,50 @@ int c8b_tx_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const 
     CK(cudaMemcpyAsync(h_iq, ctx->txiq.p, (size_t)iq_samples * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
+}
+
+// ---- MAC -> PHY UDP framing (lib/pktgen_impl.cc:57-70,96-118; tools/phy80211.py:1126-1137) -------------------------
+int c8b_tx_udp_parse(const uint8_t* pkt, int pkt_len, c8b_txframe* f, const uint8_t** psdu)
+{
+    if (!pkt || !f || pkt_len < 5) return C8B_ERR_ARG;                       // msgRead drops datagrams under 5 bytes (:65-67)
+    const int format = pkt[0], mcs = pkt[1], nss = pkt[2], len = pkt[3] | (pkt[4] << 8);
+    if (format == 3) return C8B_ERR_ARG;                                      // C8P_F_VHT_MU: two users per datagram, not synthesised here
+    if (len > 4095 || pkt_len < len + 5) return C8B_ERR_ARG;                  // pktPop :108-111
+    if (nss != 1) return C8B_ERR_ARG;
+    if (c8b_tx_nsamp(format, mcs, len) < 0) return C8B_ERR_ARG;
+    memset(f, 0, sizeof(*f));
+    f->format = format; f->mcs = mcs; f->psdu_len = len;
+    if (psdu) *psdu = pkt + 5;
+    return nss;
+}
+
+int c8b_tx_from_udp(c8b_ctx* ctx, const uint8_t* pkts, const int64_t* pkt_off, const int32_t* pkt_len, int npkts, int gap, float multiplier,
+                    int scrambler_seed, float* h_iq, int64_t iq_cap, int64_t* iq_used, c8b_txframe* frames_out)
+{
+    if (!ctx || !pkts || !pkt_off || !pkt_len || npkts < 0 || gap < 0 || !h_iq || iq_cap < 0) return C8B_ERR_ARG;
+    std::vector<c8b_txframe> fr;
+    std::vector<uint8_t> arena;
+    int64_t pos = 0;
+    for (int k = 0; k < npkts; k++) {
+        c8b_txframe f;
+        const uint8_t* body = nullptr;
+        if (frames_out) { memset(&frames_out[k], 0, sizeof(c8b_txframe)); frames_out[k].psdu_len = -1; }
+        if (pkt_off[k] < 0 || pkt_len[k] < 0) return C8B_ERR_ARG;
+        if (c8b_tx_udp_parse(pkts + pkt_off[k], pkt_len[k], &f, &body) < 0) continue;
+        f.psdu_off = (int64_t)arena.size();
+        arena.insert(arena.end(), body, body + f.psdu_len);
+        while (arena.size() & 3) arena.push_back(0);
+        f.out_off = pos + gap;
+        pos = f.out_off + c8b_tx_nsamp(f.format, f.mcs, f.psdu_len);
+        if (frames_out) frames_out[k] = f;
+        fr.push_back(f);
+    }
+    pos += gap;
+    if (pos > iq_cap) { ctx->err = "c8b_tx_from_udp: iq_cap too small"; return C8B_ERR_FULL; }
+    if (iq_used) *iq_used = pos;
+    arena.resize(arena.size() + 16, 0);
+    const int rc = c8b_tx_batch(ctx, arena.data(), (int64_t)arena.size(), fr.data(), (int)fr.size(), multiplier, scrambler_seed, h_iq, pos);
+    return rc ? rc : (int)fr.size();
 }
 
 }  // extern "C"

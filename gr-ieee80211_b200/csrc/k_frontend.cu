@@ -212,7 +212,7 @@ k_header(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const i
 __global__ void __launch_bounds__(64)
 k_header2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const float2* __restrict__ iq1,
           const int64_t* __restrict__ off, int nslots, int maxf, c8b_frame* __restrict__ frames, const float2* __restrict__ chan,
-          float2* __restrict__ hinv, float2* __restrict__ w2, int64_t llrStride)
+          float2* __restrict__ hinv, float2* __restrict__ w2, int64_t llrStride, int mmse)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
@@ -220,11 +220,12 @@ k_header2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const
     f.llr_off = (int64_t)i * llrStride;
     if (f.status == C8B_ST_OK) {
         cf hl[64], hv[64];
-        for (int k = 0; k < 64; k++) { const float2 c = chan[(size_t)i * 64 + k]; hl[k] = c8b::mk(c.x, c.y); }
+        for (int k = 0; k < 64; k++) { const float2 c = chan[(size_t)i * 64 + k]; hl[k] = c8b::mk(c.x, c.y); hv[k] = c8b::mk(0.f, 0.f); }
         RotSrc r0, r1;
         r0.x = reinterpret_cast<const cf*>(iq0 + off[i / maxf]) + f.sync_idx + 224; r0.rad = f.rad; r0.nsamp = f.nsamp;
         r1 = r0; r1.x = reinterpret_cast<const cf*>(iq1 + off[i / maxf]) + f.sync_idx + 224;
-        f.status = c8b::demod_header2(lut, r0, r1, f.nsamp, f.l_mcs, f.l_len, hl, &f, hv, reinterpret_cast<cf*>(w2 + (size_t)i * 264));
+        f.status = c8b::demod_header2(lut, r0, r1, f.nsamp, f.l_mcs, f.l_len, hl, &f, hv, reinterpret_cast<cf*>(w2 + (size_t)i * 264),
+                                       c8b::mmse_sigma2(mmse, f.snr, f.rssi));
         for (int k = 0; k < 64; k++) hinv[(size_t)i * 64 + k] = make_float2(hv[k].re, hv[k].im);
         if (f.status == C8B_ST_OK && (int64_t)f.total > llrStride) f.status = C8B_ST_OVERFLOW;
     }
@@ -234,10 +235,38 @@ k_header2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const
 }  // namespace
 
 void c8b_launch_header2(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf,
-                        c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st)
+                        int mmse, c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    k_header2<<<(nitems * maxf + 63) / 64, 64, 0, st>>>(lut, iq0, iq1, d_off, nitems * maxf, maxf, frames, chan, hinv, w2, llrStride);
+    k_header2<<<(nitems * maxf + 63) / 64, 64, 0, st>>>(lut, iq0, iq1, d_off, nitems * maxf, maxf, frames, chan, hinv, w2, llrStride, mmse);
+}
+
+// sc16 -> fc32: the widening UHD's converter applies before the reference sees gr_complex (int16 * (1 / 32768), exact in
+// float32).  Four samples per thread: 16 bytes in, 32 bytes out.
+namespace {
+__global__ void __launch_bounds__(256)
+k_sc16_to_fc32(const short2* __restrict__ in, float2* __restrict__ out, int64_t n)
+{
+    const float sc = 1.0f / 32768.0f;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(in + i) & 15) == 0)) {
+        const int4 v = *reinterpret_cast<const int4*>(in + i);
+        const short2 a = *reinterpret_cast<const short2*>(&v.x), b = *reinterpret_cast<const short2*>(&v.y);
+        const short2 c = *reinterpret_cast<const short2*>(&v.z), d = *reinterpret_cast<const short2*>(&v.w);
+        float4* o = reinterpret_cast<float4*>(out + i);
+        o[0] = make_float4(a.x * sc, a.y * sc, b.x * sc, b.y * sc);
+        o[1] = make_float4(c.x * sc, c.y * sc, d.x * sc, d.y * sc);
+    } else {
+        for (int64_t k = i; k < n && k < i + 4; k++) { const short2 a = in[k]; out[k] = make_float2(a.x * sc, a.y * sc); }
+    }
+}
+}  // namespace
+
+void c8b_launch_sc16_to_fc32(const short2* in, float2* out, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return;
+    const int64_t threads = (n + 3) / 4;
+    k_sc16_to_fc32<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, out, n);
 }
 
 void c8b_launch_presiso(const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int maxLen, int64_t outBase,

@@ -788,7 +788,286 @@ k_header_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// demod2 header states, two antennas (lib/demod2_impl.cc:72-277, :350-469, :632-758): warp version of demod_header2.
+// Same control flow (format detection on antenna 0, HT / VHT parsers, SIG-B), every per-bin loop spread over the lanes
+// (two bins per lane): the four LTF spectra, H from LTF1 +- LTF2, the VHT pilot-bin interpolation, the per-bin Gram
+// matrix and its inverse (zero forcing as the reference, or MMSE with cfg.mmse), the folded weights
+// (H^H H)^-1 H^H for k_demod2 in double, the two-stream SIG-B.  Sums whose order matters (pilot phase, SIG-B noise)
+// are formed in the reference's order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FW2 = 2;                         // warps (= frames) per CTA: the workspace is 14 KB per warp
+struct __align__(16) Ws2 {
+    Ws w;                                       // spectra (w.A: 4 windows), soft bits (w.F), Viterbi / DFT scratch
+    float2 H[256];                              // H[4 i + k], the reference's d_H_NL[i][k]
+    float2 HI[256];                             // inverse Gram per bin
+    float2 P[8];                                // pilot references pnl[4], pnl2[4]
+};
+
+__global__ void __launch_bounds__(FW2 * 32)
+k_header2_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const float2* __restrict__ iq1, const int64_t* __restrict__ off,
+            int nslots, int maxf, int mmse, c8b_frame* __restrict__ frames, const float2* __restrict__ chan, float2* __restrict__ hinvAll,
+            float2* __restrict__ w2All, int64_t llrStride)
+{
+    __shared__ Ws2 ws[FW2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = blockIdx.x * FW2 + warp;
+    if (sl >= nslots) return;
+    Ws2& V = ws[warp];
+    Ws& W = V.w;
+    c8b_frame* __restrict__ fr = frames + sl;
+    float2* __restrict__ hinv = hinvAll + (size_t)sl * 64;
+    float2* __restrict__ w2 = w2All + (size_t)sl * 264;
+    if (lane == 0) fr->llr_off = (int64_t)sl * llrStride;
+    if (fr->status != C8B_ST_OK) return;
+    const c8b_lut* L = lut;
+    RotW r0, r1;
+    r0.x = reinterpret_cast<const cf*>(iq0 + off[sl / maxf]) + fr->sync_idx + 224;
+    r0.rad = fr->rad; r0.nsamp = fr->nsamp;
+    r1 = r0; r1.x = reinterpret_cast<const cf*>(iq1 + off[sl / maxf]) + fr->sync_idx + 224;
+    const int nsamp = fr->nsamp, lmcs = fr->l_mcs, llen = fr->l_len;
+    const float sigma2 = mmse_sigma2(mmse, fr->snr, fr->rssi);
+    const float2* __restrict__ hl = chan + (size_t)sl * 64;
+
+    Mod m;
+    m.format = m.sumu = m.ampdu = m.nSym = m.nSymSamp = m.nSD = m.nSP = m.nSS = m.nLTF = 0;
+    m.mcs = m.len = m.mod = m.cr = m.nBPSCS = m.nDBPS = m.nCBPS = m.nCBPSS = 0;
+    const int nsig = nsamp + 320;
+    int pos = 0, trellis = 0, status = C8B_ST_OK;
+    float sssnr0 = 0.f, sssnr1 = 0.f;
+    bool legacy = lmcs > 0;
+    for (int i = lane; i < 256; i += 32) { V.H[i] = make_float2(0.f, 0.f); V.HI[i] = make_float2(0.f, 0.f); }
+    if (lane < 8) V.P[lane] = make_float2(0.f, 0.f);
+    // window k (0..3) of 64 rotated samples of antenna a starting at stream index `start` -> W.A[64 k ..]
+    auto win = [&](int k, int a, int start) {
+        const RotW& r = a ? r1 : r0;
+        for (int i = lane; i < 64; i += 32) W.A[64 * k + i] = st(r.at(start + C8B_SYM_SHIFT + i));
+    };
+    float* __restrict__ llrht = W.F, *llrvht = W.F + 96;           // 96 + 96 soft bits
+    auto Hk = [&](int i, int k) { return ld(&V.H[4 * i + k]); };
+    // zero-forcing / MMSE combine of one bin, the reference's operation order (:498-501)
+    auto zf = [&](int i, cf a1, cf a2, cf& s1, cf& s2) {
+        const cf t1 = cadd(cmul(a1, cconj(Hk(i, 0))), cmul(a2, cconj(Hk(i, 1))));
+        const cf t2 = cadd(cmul(a1, cconj(Hk(i, 2))), cmul(a2, cconj(Hk(i, 3))));
+        s1 = cadd(cmul(t1, ld(&V.HI[4 * i + 0])), cmul(t2, ld(&V.HI[4 * i + 2])));
+        s2 = cadd(cmul(t1, ld(&V.HI[4 * i + 1])), cmul(t2, ld(&V.HI[4 * i + 3])));
+    };
+    auto chan_estimate = [&](int start) {                          // nonLegacyChanEstimate :350-469
+        __syncwarp();
+        if (m.nSS == 1) {
+            if (m.nLTF == 1) {
+                win(0, 0, start);
+                fft64_groups(L, W.A, W, 1, lane);
+                for (int i = lane; i < 64; i += 32) if (!nl_null(i)) V.H[4 * i] = st(cdivs(ld(&W.A[i]), L->ltfNL[i]));
+            }
+        } else if (m.nSS == 2) {
+            win(0, 0, start); win(1, 1, start); win(2, 0, start + 80); win(3, 1, start + 80);
+            fft64_groups(L, W.A, W, 4, lane);
+            for (int i = lane; i < 64; i += 32) {
+                if (nl_null(i)) continue;
+                const float l2 = fmul(L->ltfNL[i], 0.5f);         // LTF_NL_28_F_FLOAT2
+                const cf f1 = ld(&W.A[i]), f2 = ld(&W.A[64 + i]), f12 = ld(&W.A[128 + i]), f22 = ld(&W.A[192 + i]);
+                V.H[4 * i + 0] = st(cscale(csub(f1, f12), l2)); V.H[4 * i + 1] = st(cscale(csub(f2, f22), l2));
+                V.H[4 * i + 2] = st(cscale(cadd(f1, f12), l2)); V.H[4 * i + 3] = st(cscale(cadd(f2, f22), l2));
+            }
+            __syncwarp();
+            const int pb[4] = { 7, 21, 43, 57 }, slot[4] = { 2, 3, 0, 1 };
+            if (m.format == C8B_F_VHT && lane < 16) {             // pilot tones interpolated :391-409
+                const int q = lane >> 2, k = lane & 3;
+                V.H[4 * pb[q] + k] = st(cdivs(cadd(Hk(pb[q] - 1, k), Hk(pb[q] + 1, k)), 2.0f));
+            }
+            __syncwarp();
+            for (int i = lane; i < 64; i += 32) {
+                if (nl_null(i)) continue;
+                const cf h0 = Hk(i, 0), h1 = Hk(i, 1), h2 = Hk(i, 2), h3 = Hk(i, 3);
+                const cf a = cadd(cmul(h0, cconj(h0)), cmul(h1, cconj(h1)));
+                const cf b = cadd(cmul(h0, cconj(h2)), cmul(h1, cconj(h3)));
+                const cf c = cadd(cmul(h2, cconj(h0)), cmul(h3, cconj(h1)));
+                const cf d = cadd(cmul(h2, cconj(h2)), cmul(h3, cconj(h3)));
+                cf hi[4];
+                gram_inverse(a, b, c, d, sigma2, hi);
+#pragma unroll
+                for (int k = 0; k < 4; k++) V.HI[4 * i + k] = st(hi[k]);
+            }
+            __syncwarp();
+            if (lane < 4) {
+                cf t1, t2;
+                zf(pb[lane], ld(&W.A[pb[lane]]), ld(&W.A[64 + pb[lane]]), t1, t2);
+                if (lane == 3) { t1 = mk(-t1.re, -t1.im); t2 = mk(-t2.re, -t2.im); }
+                V.P[slot[lane]] = st(cconj(t1)); V.P[4 + slot[lane]] = st(cconj(t2));
+            }
+        }
+        __syncwarp();
+    };
+
+    if (!legacy) {                                                // DEMOD_S_FORMAT
+        if (nsig < 160) status = C8B_ST_TRUNC;
+        else {
+            __syncwarp();
+            win(0, 0, 0); win(1, 0, 80);
+            fft64_groups(L, W.A, W, 2, lane);
+            {   // procNLSigDemodDeint (lib/cloud80211phy.cc:629-648) on antenna 0
+                cf a1 = cdiv(ld(&W.A[7]), ld(&hl[7])), a2 = cdiv(ld(&W.A[64 + 7]), ld(&hl[7]));
+                a1 = csub(a1, cdiv(ld(&W.A[21]), ld(&hl[21]))); a2 = csub(a2, cdiv(ld(&W.A[64 + 21]), ld(&hl[21])));
+                a1 = cadd(a1, cdiv(ld(&W.A[43]), ld(&hl[43]))); a2 = cadd(a2, cdiv(ld(&W.A[64 + 43]), ld(&hl[43])));
+                a1 = cadd(a1, cdiv(ld(&W.A[57]), ld(&hl[57]))); a2 = cadd(a2, cdiv(ld(&W.A[64 + 57]), ld(&hl[57])));
+                const cf p1 = cconj(a1), p2 = cconj(a2);
+                const float m1 = cabsf_(p1), m2 = cabsf_(p2);
+                for (int i = lane; i < 64; i += 32) {
+                    const int d = L->sigDemap[i];
+                    if (d < 0) continue;
+                    const cf h = ld(&hl[i]);
+                    const cf q1 = cdivs(cmul(cdiv(ld(&W.A[i]), h), p1), m1);
+                    const cf q2 = cdivs(cmul(cdiv(ld(&W.A[64 + i]), h), p2), m2);
+                    llrht[d] = q1.im; llrht[d + 48] = q2.im;
+                    llrvht[d] = q1.re; llrvht[d + 48] = q2.im;
+                }
+            }
+            __syncwarp();
+            uint8_t vb[48];
+            unpack_bits(sig_viterbi_w(L, llrvht, 48, W, lane), vb, 48);
+            if (check_vhta(vb)) {                                 // DEMOD_S_VHT
+                parse_vhta(vb, &m);
+                pos = 160;
+                const int need = 80 + m.nLTF * 80 + 80;
+                if (nsig - pos < need) status = C8B_ST_TRUNC;
+                else {
+                    chan_estimate(pos + 80);
+                    // vhtSigBDemod :632-758
+                    const int stb = pos + 80 + m.nLTF * 80;
+                    float2* __restrict__ q0 = W.B, *q1 = W.B + 64;    // [52] equalised SIG-B tones per stream
+                    float* __restrict__ coded = W.F + 192;            // [52]
+                    uint8_t sb[26];
+                    bool have = true;
+                    if (m.nSS == 1) {
+                        win(0, 0, stb);
+                        fft64_groups(L, W.A, W, 1, lane);
+                        for (int i = lane; i < 64; i += 32) if (!nl_null(i)) W.A[64 + i] = st(cdiv(ld(&W.A[i]), Hk(i, 0)));
+                        __syncwarp();
+                        const cf ps = cconj(cadd(cadd(csub(ld(&W.A[64 + 7]), ld(&W.A[64 + 21])), ld(&W.A[64 + 43])), ld(&W.A[64 + 57])));
+                        const float pa = cabsf_(ps);
+                        for (int i = lane; i < 64; i += 32) {
+                            const int d = L->binToDataNL[i];
+                            if (d == 255) continue;
+                            const cf q = cdivs(cmul(ld(&W.A[64 + i]), ps), pa);
+                            q0[d] = st(q);
+                            coded[L->deintNL[0][0][d]] = q.re;
+                        }
+                    } else if (m.nSS == 2) {
+                        win(0, 0, stb); win(1, 1, stb);
+                        fft64_groups(L, W.A, W, 2, lane);
+                        for (int i = lane; i < 64; i += 32) {
+                            if (nl_null(i)) continue;
+                            cf s1, s2;
+                            zf(i, ld(&W.A[i]), ld(&W.A[64 + i]), s1, s2);
+                            W.A[128 + i] = st(s1); W.A[192 + i] = st(s2);
+                        }
+                        __syncwarp();
+                        const float2* s1 = W.A + 128, *s2 = W.A + 192;
+                        cf acc = cmul(ld(&s1[7]), ld(&V.P[2]));
+                        acc = csub(acc, cmul(ld(&s1[21]), ld(&V.P[3]))); acc = cadd(acc, cmul(ld(&s1[43]), ld(&V.P[0]))); acc = cadd(acc, cmul(ld(&s1[57]), ld(&V.P[1])));
+                        acc = cadd(acc, cmul(ld(&s2[7]), ld(&V.P[6]))); acc = csub(acc, cmul(ld(&s2[21]), ld(&V.P[7])));
+                        acc = cadd(acc, cmul(ld(&s2[43]), ld(&V.P[4]))); acc = cadd(acc, cmul(ld(&s2[57]), ld(&V.P[5])));
+                        const cf ps = cconj(acc);
+                        const float pa = cabsf_(ps);
+                        for (int i = lane; i < 64; i += 32) {
+                            const int d = L->binToDataNL[i];
+                            if (d == 255) continue;
+                            const cf a = cdivs(cmul(ld(&s1[i]), ps), pa), b = cdivs(cmul(ld(&s2[i]), ps), pa);
+                            q0[d] = st(a); q1[d] = st(b);
+                            coded[L->deintNL[0][0][d]] = fdiv(fadd(a.re, b.re), 2.0f);
+                        }
+                    } else have = false;
+                    __syncwarp();
+                    if (have) {
+                        uint8_t enc[52];
+                        unpack_bits(sig_viterbi_w(L, coded, 26, W, lane), sb, 26);
+                        bcc_encode(sb, enc, 26);
+                        double n0 = 0.0, n1 = 0.0;
+                        for (int i = 0; i < 52; i++) {
+                            const float ref = enc[L->deintNL[0][0][i]] ? 1.0f : -1.0f;
+                            const cf a = ld(&q0[i]);
+                            const cf e0 = mk(fsub(a.re, ref), a.im);
+                            n0 += (double)fadd(fmul(e0.re, e0.re), fmul(e0.im, e0.im));
+                            if (m.nSS == 2) { const cf b = ld(&q1[i]); const cf e1 = mk(fsub(b.re, ref), b.im); n1 += (double)fadd(fmul(e1.re, e1.re), fmul(e1.im, e1.im)); }
+                        }
+                        sssnr0 = (float)(log10(52.0 / n0) * 10.0);
+                        if (m.nSS == 2) sssnr1 = (float)(log10(52.0 / n1) * 10.0);
+                    } else {
+                        for (int i = 0; i < 26; i++) sb[i] = 0;
+                    }
+                    parse_vhtb(sb, &m);
+                    const int nl = (llen * 8 + 22 + 23) / 24;
+                    const bool ok = m.len > 0 && m.len <= 4095 && m.nSS <= 2 && (nl * 80) >= (m.nSym * m.nSymSamp + 160 + 80 + m.nLTF * 80 + 80);
+                    pos += need;
+                    if (!ok) status = C8B_ST_FORMAT;
+                    trellis = m.nSym * m.nDBPS;
+                }
+            } else {
+                uint8_t hb[48];
+                unpack_bits(sig_viterbi_w(L, llrht, 48, W, lane), hb, 48);
+                if (check_ht(hb)) {                               // DEMOD_S_HT
+                    parse_ht(hb, &m);
+                    pos = 160;
+                    const int need = 80 + m.nLTF * 80;
+                    if (nsig - pos < need) status = C8B_ST_TRUNC;
+                    else {
+                        chan_estimate(pos + 80);
+                        const int nl = (llen * 8 + 22 + 23) / 24;
+                        const bool ok = m.len > 0 && m.len <= 4095 && m.nSS <= 2 && (nl * 80) >= (m.nSym * m.nSymSamp + 160 + 80 + m.nLTF * 80);
+                        pos += need;
+                        if (!ok) status = C8B_ST_FORMAT;
+                        trellis = m.len * 8 + 22;
+                    }
+                } else legacy = true;
+            }
+        }
+    }
+    if (status == C8B_ST_OK && legacy) { parse_l(lmcs, llen, &m); trellis = m.len * 8 + 22; }
+    if (status != C8B_ST_OK) { if (lane == 0) fr->status = status; return; }
+    __syncwarp();
+    for (int i = lane; i < 64; i += 32) {
+        const cf hh = (m.format == C8B_F_L) ? ld(&hl[i]) : Hk(i, 0);
+        const bool used = (m.format == C8B_F_L) ? !l_null(i) : !nl_null(i);
+        const double den = c8b::dadd(c8b::dmul((double)hh.re, (double)hh.re), c8b::dmul((double)hh.im, (double)hh.im));
+        hinv[i] = (used && m.nSS == 1) ? make_float2((float)((double)hh.re / den), (float)(-(double)hh.im / den)) : make_float2(0.f, 0.f);
+        float2 wv[4] = { make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f) };
+        if (m.nSS == 2 && !nl_null(i)) {
+            const cd h0 = dconj(tod(Hk(i, 0))), h1 = dconj(tod(Hk(i, 1))), h2 = dconj(tod(Hk(i, 2))), h3 = dconj(tod(Hk(i, 3)));
+            const cd i0 = tod(ld(&V.HI[4 * i + 0])), i1 = tod(ld(&V.HI[4 * i + 1])), i2 = tod(ld(&V.HI[4 * i + 2])), i3 = tod(ld(&V.HI[4 * i + 3]));
+            wv[0] = st(tof(dcadd(dcmul(h0, i0), dcmul(h2, i2))));    // stream 0 <- antenna 0
+            wv[1] = st(tof(dcadd(dcmul(h1, i0), dcmul(h3, i2))));    // stream 0 <- antenna 1
+            wv[2] = st(tof(dcadd(dcmul(h0, i1), dcmul(h2, i3))));    // stream 1 <- antenna 0
+            wv[3] = st(tof(dcadd(dcmul(h1, i1), dcmul(h3, i3))));    // stream 1 <- antenna 1
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) w2[4 * i + k] = wv[k];
+    }
+    if (lane < 8) w2[256 + lane] = V.P[lane];
+    if (m.nSS != 1 && m.nSS != 2) status = C8B_ST_FORMAT;
+    else if (m.nSS == 1 && m.format != C8B_F_L && m.nLTF != 1) status = C8B_ST_FORMAT;   // reference leaves H unset (:355-372)
+    else if (pos + m.nSym * m.nSymSamp > nsig) status = C8B_ST_TRUNC;
+    const int total = m.nSym * m.nCBPS;
+    if (status == C8B_ST_OK && (int64_t)total > llrStride) status = C8B_ST_OVERFLOW;
+    if (lane == 0) {
+        fr->format = m.format; fr->mcs = m.mcs; fr->len = m.len; fr->cr = m.cr; fr->ampdu = m.ampdu;
+        fr->nss = m.nSS; fr->nsym = m.nSym; fr->nsymsamp = m.nSymSamp; fr->ncbps = m.nCBPS; fr->ndbps = m.nDBPS;
+        fr->trellis = trellis; fr->total = total; fr->data_off = pos;
+        fr->sssnr0 = (m.format == C8B_F_VHT) ? sssnr0 : 0.f;
+        fr->sssnr1 = (m.format == C8B_F_VHT && m.nSS == 2) ? sssnr1 : 0.f;
+        fr->status = status;
+    }
+}
+
 }  // namespace
+
+void c8b_launch_header2_w(const c8b_lut* lut, const float2* iq0, const float2* iq1, const int64_t* d_off, int nitems, int maxf, int mmse,
+                          c8b_frame* frames, const float2* chan, float2* hinv, float2* w2, int64_t llrStride, cudaStream_t st)
+{
+    if (nitems <= 0) return;
+    const int ns = nitems * maxf;
+    k_header2_w<<<(ns + FW2 - 1) / FW2, FW2 * 32, 0, st>>>(lut, iq0, iq1, d_off, ns, maxf, mmse, frames, chan, hinv, w2, llrStride);
+}
 
 void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                          int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,

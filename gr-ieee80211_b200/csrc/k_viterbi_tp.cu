@@ -148,115 +148,22 @@ __device__ void emit_record_t(uint8_t* __restrict__ out, int& w, int cap, int& n
 }
 
 #ifndef C8B_TP_CTAS
-#define C8B_TP_CTAS 3                          // CTAs per SM (<= 170 registers per thread; 4 would spill the metrics)
+#define C8B_TP_CTAS 3                          // CTAs per SM: 3 (168 registers per thread, no spills) or 4 (128 registers; needs C8B_TP_RING)
 #endif
-
-// Shared memory per warp: two rings the lanes fill with cp.async a segment (SEG trellis steps) ahead of their use.
-//   llr  [32 lanes][ROWF2]  float2 (t0, t1) of step i at slot i % CS           (forward pass of the CURRENT frame group)
-//   surv [32 lanes][SROW]   uint4 = the decision words of steps (2p, 2p+1)      (traceback of the PREVIOUS frame group)
-constexpr int SEG = 10;                        // steps per staged segment (even; CS = 3 segments = every puncture period)
-constexpr int SROW = 17;                       // uint4 per lane row: 15 used; 17 * 16 B keeps the LDS.128 phases conflict-free
-struct WarpRings {
-    float2 llr[32 * ROWF2];
-    uint4 surv[32 * SROW];
-};
-static_assert(CS == 3 * SEG, "ring = three segments");
-
-// everything the traceback / packet assembly of a frame group needs again after the forward pass of the NEXT group
-// (re-read from the frame record instead of being held in registers across that pass)
-struct Done { int T, fmt, len, mcs, ampdu; };
-
-// ---------------- descramble (lib/decode_impl.cc:304-323), packetAssemble (:325-520) of one finished frame ----------------
-__device__ __noinline__ void finish_frame(c8b_frame* __restrict__ frames, int f, const uint32_t* __restrict__ crcTab, uint32_t* __restrict__ words,
-                                          uint8_t* __restrict__ pdu, int64_t pduStride, uint8_t* __restrict__ scram, int64_t scramStride)
-{
-    const c8b_frame* fr = frames + f;
-    const int T = fr->trellis, fmt = fr->format, len = fr->len, mcs = fr->mcs, ampdu = fr->ampdu;
-    const int nwords = (T + 31) >> 5;
-    // the traceback stores word j when it passes step 32 j + 6; a last word of fewer than 7 steps lies inside the six
-    // tail steps that lead into state 0: all zeros
-    if (32 * (nwords - 1) + 6 >= T) words[(size_t)(nwords - 1) * TPB] = 0u;
-    if (scram != nullptr) {
-        uint8_t* so = scram + (size_t)f * scramStride;
-        for (int i = 0; i < T && i < scramStride; i++) so[i] = (uint8_t)((words[(size_t)(i >> 5) * TPB] >> (i & 31)) & 1u);
-    }
-    {
-        const uint32_t w0 = words[0];
-        int st = 0;
-#pragma unroll
-        for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
-        uint32_t q[6];
-#pragma unroll
-        for (int wq = 0; wq < 5; wq++) {
-            uint32_t v = 0;
-            for (int b = 0; b < 32; b++) {
-                const int fb = ((st >> 6) ^ (st >> 3)) & 1;
-                st = ((st << 1) & 0x7e) | fb;
-                v |= (uint32_t)fb << b;
-            }
-            q[wq] = v;
-        }
-        q[5] = 0;
-        for (int w = 0; w < nwords; w++) {
-            uint32_t v = words[(size_t)w * TPB];
-            if (w == 0) v = (v ^ (q[0] << 7)) & ~0x7fu;
-            else {
-                const int o = (32 * w - 7) % 127, k = o >> 5;
-                const uint32_t lo = k == 0 ? q[0] : k == 1 ? q[1] : k == 2 ? q[2] : q[3];
-                const uint32_t hi = k == 0 ? q[1] : k == 1 ? q[2] : k == 2 ? q[3] : q[4];
-                v ^= __funnelshift_r(lo, hi, o & 31);
-            }
-            words[(size_t)w * TPB] = v;
-        }
-    }
-    uint8_t* out = pdu + (size_t)f * pduStride;
-    const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
-    int npdu = 0, w = 0;
-    if (fmt == C8B_F_VHT) {
-        int procd = 16;
-        if (procd < T) {
-            int bp = 2, tl = 0;                              // tl is NOT reset per subframe (:336)
-            while (true) {
-                procd += 32;
-                if (procd > T) break;
-                const int d0 = (int)get_byte(words, bp), d1 = (int)get_byte(words, bp + 1);
-                const int eof = d0 & 1;
-                tl |= ((d0 >> 2) & 1) << 12;
-                tl |= ((d0 >> 3) & 1) << 13;
-                tl |= (d0 >> 4) | (d1 << 4);
-                const int padded = (tl / 4 + ((tl % 4) != 0)) * 4;
-                procd += padded * 8;
-                if (procd > T) break;
-                bp += 4;
-                if (crc32_words(crcTab, words, bp, tl) == 558161692u) {
-                    emit_record_t(out, w, cap, npdu, fmt, tl, words, bp, tl, mcs);
-                    tl += 4;                                 // :415, carried into the next subframe
-                }
-                bp += padded;
-                if (eof) break;
-            }
-        }
-    } else if (!ampdu) {
-        if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
-            if (crc32_words(crcTab, words, 2, len) == 558161692u) emit_record_t(out, w, cap, npdu, fmt, len, words, 2, len, mcs);
-        }
-    }
-    frames[f].npdu = npdu; frames[f].pdu_bytes = w;
-}
-
-// Persistent CTAs: CTA b decodes the frame groups b, b + gridDim, ... (TPB frames each, one per thread).  The traceback
-// of a group does NOT follow its forward pass: it is folded, step for step, into the forward pass of the thread's NEXT
-// group (lib/decode_impl.cc:282-302 walks the survivors of the whole packet back from state 0 -- the walk is the same, it
-// just runs a group late), so that the survivor read-back streams from HBM under the butterflies instead of all CTAs
-// stalling on it together.  Survivors are double-buffered per CTA; the last group's traceback runs alone.
+#ifndef C8B_TP_RING
+#define C8B_TP_RING (C8B_TP_CTAS > 3)          // 1: soft bits staged through ONE CS-step ring per lane, a third (SEG steps) at a time,
+#endif                                         //    instead of two CS-step buffers: half the shared memory, so that 4 CTAs fit an SM
+constexpr int SEG = 10;                        // steps per ring segment (even; CS = 3 segments)
+constexpr int NBUF = C8B_TP_RING ? 1 : 2;
+constexpr int TBK = C8B_TP_CTAS > 3 ? 16 : 32; // decision words the traceback keeps in flight per block (registers)
 __global__ void __launch_bounds__(TPB, C8B_TP_CTAS)
 k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, int nframes, const float* __restrict__ llrArena,
-             int64_t nllr, uint8_t* __restrict__ scratch, size_t scratchPerCta, size_t survPerBuf,
+             int64_t nllr, uint2* __restrict__ survAll, uint32_t* __restrict__ wordsAll, size_t survPerCta, size_t wordsPerCta,
              uint8_t* __restrict__ pdu, int64_t pduStride, uint8_t* __restrict__ scram, int64_t scramStride)
 {
     extern __shared__ __align__(16) uint8_t dynsm[];
-    WarpRings* rings = reinterpret_cast<WarpRings*>(dynsm);
-    uint32_t* crcTab = reinterpret_cast<uint32_t*>(dynsm + sizeof(WarpRings) * (TPB / 32));
+    float2 (*pairs)[NBUF][32 * ROWF2] = reinterpret_cast<float2 (*)[NBUF][32 * ROWF2]>(dynsm);   // [warp][buffer][frame row][step]
+    uint32_t* crcTab = reinterpret_cast<uint32_t*>(dynsm + sizeof(float2) * (TPB / 32) * NBUF * 32 * ROWF2);
     uint32_t* relTab = crcTab + 256;                                 // [4 code rates][32]
     for (int i = threadIdx.x; i < 256; i += TPB) crcTab[i] = lut->crc32tab[i];
     for (int i = threadIdx.x; i < 128; i += TPB) {
@@ -266,144 +173,256 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* const lrow = rings[warp].llr + lane * ROWF2;
-    const uint4* const srow = rings[warp].surv + lane * SROW;
-    const uint32_t lrowS = (uint32_t)__cvta_generic_to_shared(lrow), srowS = (uint32_t)__cvta_generic_to_shared(srow);
-    // scratch of this CTA: two survivor buffers [pair * TPB] of uint4, then the decoded words [w * TPB]
-    uint4* const survCta = reinterpret_cast<uint4*>(scratch + (size_t)blockIdx.x * scratchPerCta) + threadIdx.x;
-    uint32_t* __restrict__ words = reinterpret_cast<uint32_t*>(scratch + (size_t)blockIdx.x * scratchPerCta + 2 * survPerBuf * sizeof(uint4)) + threadIdx.x;
+    uint2* __restrict__ surv = survAll + (size_t)blockIdx.x * survPerCta + threadIdx.x;        // [t * TPB]
+    uint32_t* __restrict__ words = wordsAll + (size_t)blockIdx.x * wordsPerCta + threadIdx.x;  // [w * TPB]
 
-    int Tprev = 0, Pprev = 0, fprev = 0;                             // previous group: this thread's trellis length, the warp's padded length
-    for (int r = 0;; r++) {
-        const int g = blockIdx.x + r * gridDim.x;
+    for (int g = blockIdx.x; g * TPB < nframes; g += gridDim.x) {
         const int f = g * TPB + threadIdx.x;
-        // ---- this thread's frame of the current group (none past the end of the batch: T = 0) ----
-        int T = 0, cr = 0, total = 0;
+        // ---- this thread's frame ----
+        int T = 0, cr = 0, total = 0, fmt = 0, len = 0, mcs = 0, ampdu = 0;
         const float* llr = llrArena;
         if (f < nframes) {
             c8b_frame* fr = frames + f;
             const int status = fr->status;
             const int t = fr->trellis;
             const int64_t loff = fr->llr_off;
-            cr = fr->cr & 3; total = fr->total;
+            cr = fr->cr & 3; total = fr->total; fmt = fr->format; len = fr->len; mcs = fr->mcs; ampdu = fr->ampdu;
             fr->npdu = 0; fr->pdu_bytes = 0; fr->pdu_off = (int64_t)f * pduStride;
             if (status == C8B_ST_OK) {
-                if (fr->len > C8B_DECODE_B_MAX || t > C8B_DECODE_T_MAX) fr->status = C8B_ST_DECODE_RANGE;     // lib/decode_impl.cc:93-97
+                if (len > C8B_DECODE_B_MAX || t > C8B_DECODE_T_MAX) fr->status = C8B_ST_DECODE_RANGE;     // lib/decode_impl.cc:93-97
                 else if (t > 0 && total >= 0 && loff >= 0 && loff + total <= nllr) { T = t; llr = llrArena + loff; }
             }
         }
         const int lim = min(total, used_by(cr, T));                  // soft bits this packet consumes (pad steps read 0)
-        const int nraw = used_by(cr, CS);                            // soft bits per CS steps of this frame
+        const int nraw = used_by(cr, CS);                            // soft bits per chunk of this frame
         int Tmax = T;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
-        if (Tmax == 0 && Pprev == 0) {                               // warp-uniform: nothing to run forward, nothing to walk back
-            if (g * TPB >= nframes) break;
-            continue;
-        }
-        const int Pcur = ((Tmax + SEG - 1) / SEG) * SEG;             // the warp's forward pass, padded to whole segments
-        const int nseg = max(Pcur, Pprev) / SEG;
-        uint4* __restrict__ svCur = survCta + (size_t)(r & 1) * survPerBuf;
-        const uint4* __restrict__ svPrev = survCta + (size_t)((r & 1) ^ 1) * survPerBuf;
+        if (Tmax == 0) continue;                                     // warp-uniform
+        const int nch = (Tmax + CS - 1) / CS;
 
-        // stage segment q: the (t0,t1) pairs of steps [q SEG, q SEG + SEG) of this lane's frame into its ring row (cp.async 4 B
-        // per soft bit; relTab[cr][s] = soft-bit indices of step s relative to the CS-step period, 0xffff = punctured: the
-        // punctured slots of a row are the same in every period, zeroed once per frame and never copied; past the end of the
-        // packet = zero-fill copy), and the decision-word pairs the traceback of the previous group walks during that segment
-        // (its steps Pprev - 1 - i, i in the segment: five 16-byte pairs, highest first).
-        if (Tmax > 0) {
+        // stage chunk c: every lane copies the (t0,t1) pairs of ITS frame into its shared-memory row with cp.async
+        // (LDGSTS): the copies of the next chunk run under the butterflies of the current one and hold no registers.
+        // relTab[cr][s] = chunk-relative soft-bit indices of step s (i0 | i1 << 16, 0xffff = punctured).  A chunk is a whole
+        // number of puncture periods, so the punctured slots of a row are the same in every chunk: they are zeroed once per
+        // frame and never copied; a position past the end of the packet is a zero-fill copy (src-size 0).  The table entries
+        // of ten steps are fetched together (LDS.64) ahead of their twenty copies -- one dependent LDS per step stalled the
+        // warp for a fifth of the kernel.
+        {
 #pragma unroll
-            for (int i = 0; i < CS; i++) lrow[i] = make_float2(0.f, 0.f);
+            for (int b = 0; b < NBUF; b++) {
+                float2* r0 = pairs[warp][b] + lane * ROWF2;
+#pragma unroll
+                for (int i = 0; i < CS; i++) r0[i] = make_float2(0.f, 0.f);
+            }
+            __syncwarp();
         }
-        auto stage = [&](int q) {
-            const int j = q % 3;
-            if (q * SEG < Pcur) {
-                const int c = q / 3;
-                const float* __restrict__ lb = llr + (size_t)c * nraw;
-                const int rem = lim - c * nraw;                      // soft bits left from the start of this period
-                const uint2* __restrict__ rt = reinterpret_cast<const uint2*>(relTab + cr * 32) + (SEG / 2) * j;
-                const uint32_t d0 = lrowS + 8 * SEG * j;
-                uint2 e[SEG / 2];
+        auto stage = [&](int c, int buf) {
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(pairs[warp][buf] + lane * ROWF2);
+            const float* __restrict__ lb = llr + (size_t)c * nraw;
+            const int rem = lim - c * nraw;                          // soft bits left from the start of this chunk
+            const uint2* __restrict__ rt = reinterpret_cast<const uint2*>(relTab + cr * 32);
 #pragma unroll
-                for (int k = 0; k < SEG / 2; k++) e[k] = rt[k];
+            for (int b = 0; b < CS; b += 10) {
+                uint2 e[5];
 #pragma unroll
-                for (int k = 0; k < SEG; k++) {
+                for (int k = 0; k < 5; k++) e[k] = rt[b / 2 + k];
+#pragma unroll
+                for (int k = 0; k < 10; k++) {
                     const uint32_t ev = (k & 1) ? e[k >> 1].y : e[k >> 1].x;
                     const int i0 = (int)(ev & 0xffffu), i1 = (int)(ev >> 16);
                     const bool in0 = i0 < rem, in1 = i1 < rem;
                     if (i0 != 0xffff)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * k), "l"(lb + (in0 ? i0 : 0)), "r"(in0 ? 4 : 0));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * (b + k)), "l"(lb + (in0 ? i0 : 0)), "r"(in0 ? 4 : 0));
                     if (i1 != 0xffff)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * k + 4), "l"(lb + (in1 ? i1 : 0)), "r"(in1 ? 4 : 0));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * (b + k) + 4), "l"(lb + (in1 ? i1 : 0)), "r"(in1 ? 4 : 0));
                 }
-            }
-            if (q * SEG < Pprev) {
-                const uint4* __restrict__ src = svPrev + (size_t)((Pprev - q * SEG) / 2 - 1) * TPB;     // pair of steps (Pprev - q SEG - 2, .. - 1)
-                const uint32_t d1 = srowS + 16 * (SEG / 2) * j;
-#pragma unroll
-                for (int k = 0; k < SEG / 2; k++)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1 + 16 * k), "l"(src - (size_t)k * TPB));
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        auto stage_wait = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); };
 
+        // ---------------- forward pass ----------------
         float m[64], n[64];
 #pragma unroll
         for (int i = 0; i < 64; i++) m[i] = -1000000000000000.0f;     // lib/decode_impl.cc:171-176
         m[0] = 0.0f;
-        uint32_t h = 0;                                              // traceback: state in bits 0..5 (final state 0), decoded bits above
-        stage(0);
+#if C8B_TP_RING
+        // ring: segment q = steps [q SEG, q SEG + SEG) lives in third q % 3 of the lane's row; its copies are issued while
+        // segment q - 1 is computed (the third they overwrite was consumed by segment q - 2)
+        auto stage_seg = [&](int q) {
+            const int j = q % 3, c = q / 3;
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(pairs[warp][0] + lane * ROWF2) + 8 * SEG * j;
+            const float* __restrict__ lb = llr + (size_t)c * nraw;
+            const int rem = lim - c * nraw;                          // soft bits left from the start of this CS-step period
+            const uint2* __restrict__ rt = reinterpret_cast<const uint2*>(relTab + cr * 32) + (SEG / 2) * j;
+            uint2 e[SEG / 2];
+#pragma unroll
+            for (int k = 0; k < SEG / 2; k++) e[k] = rt[k];
+#pragma unroll
+            for (int k = 0; k < SEG; k++) {
+                const uint32_t ev = (k & 1) ? e[k >> 1].y : e[k >> 1].x;
+                const int i0 = (int)(ev & 0xffffu), i1 = (int)(ev >> 16);
+                const bool in0 = i0 < rem, in1 = i1 < rem;
+                if (i0 != 0xffff)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * k), "l"(lb + (in0 ? i0 : 0)), "r"(in0 ? 4 : 0));
+                if (i1 != 0xffff)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8 * k + 4), "l"(lb + (in1 ? i1 : 0)), "r"(in1 ? 4 : 0));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        const int nseg = (Tmax + SEG - 1) / SEG;
+        stage_seg(0);
         for (int q = 0; q < nseg; q++) {
-            stage(q + 1);                                            // (commits an empty group past the end)
-            asm volatile("cp.async.wait_group 1;" ::: "memory");     // segment q has landed (each lane reads only what it copied)
-            const int j = q % 3;
-            const bool doF = q * SEG < Pcur, doT = q * SEG < Pprev;  // warp-uniform
-            const float2* __restrict__ row = lrow + SEG * j;
-            const uint4* __restrict__ sq = srow + (SEG / 2) * j;
-            uint4* __restrict__ sv = svCur + (size_t)(q * (SEG / 2)) * TPB;
-            int u = Pprev - 1 - q * SEG;                             // traceback step of the first iteration
+            if (q + 1 < nseg) stage_seg(q + 1);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");     // segment q has landed (every lane reads only its own copies)
+            const float2* __restrict__ row = pairs[warp][0] + lane * ROWF2 + SEG * (q % 3);
+            uint2* __restrict__ sv = surv + (size_t)q * SEG * TPB;
 #pragma unroll 1
             for (int s = 0; s < SEG; s += 2) {
-                if (doF) {
-                    const uint2 w0 = acs(m, n, row[s]);
-                    const uint2 w1 = acs(n, m, row[s + 1]);
-                    sv[(size_t)(s >> 1) * TPB] = make_uint4(w0.x, w0.y, w1.x, w1.y);
-                }
-                if (doT) {
-                    // lib/decode_impl.cc:286-301: the predecessor of state s at step u is 2 (s & 31) + decision bit; the decoded bit
-                    // of step u is bit 5 of the state entered.  h = (h << 1) | decision keeps the state in its low six bits and
-                    // the decoded bits of the steps above u behind them: after step u = 32 j + 6, h IS word j of the packet.
-                    const uint4 d = sq[s >> 1];
-                    if (u < Tprev) {
-                        const uint32_t x = (h & 32u) ? d.w : d.z;
-                        h = (h << 1) | ((x >> (h & 31u)) & 1u);
-                        if ((u & 31) == 6) words[(size_t)(u >> 5) * TPB] = h;
-                    }
-                    u--;
-                    if (u < Tprev) {
-                        const uint32_t x = (h & 32u) ? d.y : d.x;
-                        h = (h << 1) | ((x >> (h & 31u)) & 1u);
-                        if ((u & 31) == 6) words[(size_t)(u >> 5) * TPB] = h;
-                    }
-                    u--;
-                }
+                const uint2 w0 = acs(m, n, row[s]);
+                sv[(size_t)s * TPB] = w0;
+                const uint2 w1 = acs(n, m, row[s + 1]);
+                sv[(size_t)(s + 1) * TPB] = w1;
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+#else
+        stage(0, 0);
+        stage_wait();
+        for (int c = 0; c < nch; c++) {
+            if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
+            const float2* __restrict__ row = pairs[warp][c & 1] + lane * ROWF2;
+            uint2* __restrict__ sv = surv + (size_t)c * CS * TPB;
+#pragma unroll 1
+            for (int s = 0; s < CS; s += 2) {
+                const uint2 w0 = acs(m, n, row[s]);
+                sv[(size_t)s * TPB] = w0;
+                const uint2 w1 = acs(n, m, row[s + 1]);
+                sv[(size_t)(s + 1) * TPB] = w1;
+            }
+            stage_wait();
+        }
+#endif
 
-        // ---- the previous group is walked back: descramble, A-MPDU walk, CRC-32, PDU records ----
-        if (Tprev > 0) finish_frame(frames, fprev, crcTab, words, pdu, pduStride, scram, scramStride);
-        Tprev = T; Pprev = Pcur; fprev = f;
-        if (Tmax == 0) Pprev = 0;
+        // ---------------- traceback (lib/decode_impl.cc:282-302), final state 0 ----------------
+        {
+            uint32_t s = 0, acc = 0;
+            constexpr int TB = TBK;                                  // decision words per block; the next block is in flight
+            uint2 wa[TB], wb[TB];
+            auto fetch = [&](uint2 (&w)[TB], int tb) {
+#pragma unroll
+                for (int k = 0; k < TB; k++) w[k] = (tb >= 0 && tb + k < T) ? surv[(size_t)(tb + k) * TPB] : make_uint2(0u, 0u);
+            };
+            auto walk = [&](const uint2 (&w)[TB], int tb) {
+#pragma unroll
+                for (int k = TB - 1; k >= 0; k--) {
+                    const int t = tb + k;
+                    if (t < T) {
+                        acc = (acc << 1) | (s >> 5);                 // decoded bit of step t = input bit of the state entered
+                        const uint32_t d = ((s & 32u ? w[k].y : w[k].x) >> (s & 31u)) & 1u;
+                        s = ((s & 31u) << 1) | d;
+                        if ((t & 31) == 0) { words[(size_t)(t >> 5) * TPB] = acc; acc = 0; }
+                    }
+                }
+            };
+            int tb = ((Tmax - 1) / TB) * TB;
+            fetch(wa, tb);
+            for (; tb >= 0; tb -= 2 * TB) {
+                fetch(wb, tb - TB);
+                walk(wa, tb);
+                fetch(wa, tb - 2 * TB);
+                if (tb - TB >= 0) walk(wb, tb - TB);
+            }
+        }
+        if (T <= 0) continue;                                        // (lanes without a frame are done; no warp-level sync below)
+        const int nwords = (T + 31) >> 5;
+        if (scram != nullptr) {
+            uint8_t* so = scram + (size_t)f * scramStride;
+            for (int i = 0; i < T && i < scramStride; i++) so[i] = (uint8_t)((words[(size_t)(i >> 5) * TPB] >> (i & 31)) & 1u);
+        }
+
+        // ---------------- descramble (lib/decode_impl.cc:304-323) ----------------
+        {
+            const uint32_t w0 = words[0];
+            int st = 0;
+#pragma unroll
+            for (int i = 0; i < 7; i++) st |= (int)((w0 >> i) & 1u) << (6 - i);
+            uint32_t q[6];
+#pragma unroll
+            for (int wq = 0; wq < 5; wq++) {
+                uint32_t v = 0;
+                for (int b = 0; b < 32; b++) {
+                    const int fb = ((st >> 6) ^ (st >> 3)) & 1;
+                    st = ((st << 1) & 0x7e) | fb;
+                    v |= (uint32_t)fb << b;
+                }
+                q[wq] = v;
+            }
+            q[5] = 0;
+            for (int w = 0; w < nwords; w++) {
+                uint32_t v = words[(size_t)w * TPB];
+                if (w == 0) v = (v ^ (q[0] << 7)) & ~0x7fu;
+                else {
+                    const int o = (32 * w - 7) % 127, k = o >> 5;
+                    const uint32_t lo = k == 0 ? q[0] : k == 1 ? q[1] : k == 2 ? q[2] : q[3];
+                    const uint32_t hi = k == 0 ? q[1] : k == 1 ? q[2] : k == 2 ? q[3] : q[4];
+                    v ^= __funnelshift_r(lo, hi, o & 31);
+                }
+                words[(size_t)w * TPB] = v;
+            }
+        }
+
+        // ---------------- packetAssemble (lib/decode_impl.cc:325-520) ----------------
+        {
+            uint8_t* out = pdu + (size_t)f * pduStride;
+            const int cap = (int)min(pduStride, (int64_t)0x7fffffff);
+            int npdu = 0, w = 0;
+            if (fmt == C8B_F_VHT) {
+                int procd = 16;
+                if (procd < T) {
+                    int bp = 2, tl = 0;                              // tl is NOT reset per subframe (:336)
+                    while (true) {
+                        procd += 32;
+                        if (procd > T) break;
+                        const int d0 = (int)get_byte(words, bp), d1 = (int)get_byte(words, bp + 1);
+                        const int eof = d0 & 1;
+                        tl |= ((d0 >> 2) & 1) << 12;
+                        tl |= ((d0 >> 3) & 1) << 13;
+                        tl |= (d0 >> 4) | (d1 << 4);
+                        const int padded = (tl / 4 + ((tl % 4) != 0)) * 4;
+                        procd += padded * 8;
+                        if (procd > T) break;
+                        bp += 4;
+                        if (crc32_words(crcTab, words, bp, tl) == 558161692u) {
+                            emit_record_t(out, w, cap, npdu, fmt, tl, words, bp, tl, mcs);
+                            tl += 4;                                 // :415, carried into the next subframe
+                        }
+                        bp += padded;
+                        if (eof) break;
+                    }
+                }
+            } else if (!ampdu) {
+                if (len >= 0 && 16 + 8 * len <= 32 * nwords) {
+                    if (crc32_words(crcTab, words, 2, len) == 558161692u) emit_record_t(out, w, cap, npdu, fmt, len, words, 2, len, mcs);
+                }
+            }
+            frames[f].npdu = npdu; frames[f].pdu_bytes = w;
+        }
     }
 }
 
 }  // namespace
 
-static constexpr size_t tp_smem_bytes() { return sizeof(WarpRings) * (TPB / 32) + 1024 + 512; }
-// survivor pairs per buffer and CTA (uint4 = two steps), decoded words per CTA
-static constexpr size_t tp_surv_per_buf() { return (size_t)((C8B_DECODE_T_MAX + SEG) / 2 + 2) * TPB; }
-static constexpr size_t tp_words_per_cta() { return (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB; }
+static constexpr size_t tp_smem_bytes() { return sizeof(float2) * (TPB / 32) * NBUF * 32 * ROWF2 + 1024 + 512; }
+static constexpr size_t tp_surv_per_cta() { return (size_t)(C8B_DECODE_T_MAX + CS + 2) * TPB; }              // uint2
+static constexpr size_t tp_words_per_cta() { return (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB; }      // uint32
+static int tp_grid(int num_sm, int nframes)
+{
+    const int full = num_sm * C8B_TP_CTAS, need = (nframes + TPB - 1) / TPB;
+    return need < full ? need : full;
+}
 
 // The dynamic shared-memory opt-in (> 48 KB) is a per-DEVICE function attribute: every context sets it on its own device
 // at c8b_create (two contexts on two GPUs in one process, block threads created concurrently).
@@ -412,15 +431,11 @@ cudaError_t c8b_viterbi_tp_prepare(void)
     return cudaFuncSetAttribute(k_viterbi_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp_smem_bytes());
 }
 
-static constexpr size_t tp_scratch_per_cta() { return 2 * tp_surv_per_buf() * sizeof(uint4) + tp_words_per_cta() * sizeof(uint32_t); }
-static int tp_grid(int num_sm, int nframes)
+// scratch for a launch over nframes frames: per resident CTA the survivor words and the decoded words
+size_t c8b_viterbi_tp_scratch_bytes(int num_sm, int nframes)
 {
-    const int full = num_sm * C8B_TP_CTAS, need = (nframes + TPB - 1) / TPB;
-    return need < full ? need : full;
+    return (size_t)tp_grid(num_sm, nframes) * (tp_surv_per_cta() * sizeof(uint2) + tp_words_per_cta() * sizeof(uint32_t));
 }
-
-// scratch for a launch over nframes frames: per resident CTA two survivor buffers + the decoded words
-size_t c8b_viterbi_tp_scratch_bytes(int num_sm, int nframes) { return (size_t)tp_grid(num_sm, nframes) * tp_scratch_per_cta(); }
 
 int c8b_viterbi_tp_wave(int num_sm) { return num_sm * C8B_TP_CTAS * TPB; }   // frames in one full wave
 
@@ -428,7 +443,9 @@ void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframe
                            int num_sm, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride, cudaStream_t st)
 {
     if (nframes <= 0) return;
-    k_viterbi_tp<<<tp_grid(num_sm, nframes), TPB, tp_smem_bytes(), st>>>(d_lut, d_frames, nframes, d_llr, nllr, reinterpret_cast<uint8_t*>(d_scratch),
-                                                                         tp_scratch_per_cta(), tp_surv_per_buf(), d_pdu, pdu_stride, d_scram,
-                                                                         scram_stride);
+    const int grid = tp_grid(num_sm, nframes);
+    uint2* surv = reinterpret_cast<uint2*>(d_scratch);
+    uint32_t* words = reinterpret_cast<uint32_t*>(surv + (size_t)grid * tp_surv_per_cta());
+    k_viterbi_tp<<<grid, TPB, tp_smem_bytes(), st>>>(d_lut, d_frames, nframes, d_llr, nllr, surv, words, tp_surv_per_cta(), tp_words_per_cta(), d_pdu,
+                                                     pdu_stride, d_scram, scram_stride);
 }

@@ -678,8 +678,36 @@ C8B_HD cd dconj(cd a) { return dmk(a.re, -a.im); }
 C8B_HD cd tod(cf a) { return dmk((double)a.re, (double)a.im); }
 C8B_HD cf tof(cd a) { return mk((float)a.re, (float)a.im); }
 
+// Per-bin noise power for the MMSE option of the 2x2 equaliser (cfg.mmse): sync's tags give the mean power per time sample of
+// signal + noise (rssi, lib/sync_impl.cc:127) and their ratio (snr in dB, :126), so the noise of one bin of the unnormalised
+// 64-point DFT is 64 rssi / (1 + 10^(snr/10)).  0 (also for a noiseless capture, where the reference's snr is NaN) = the
+// reference's zero-forcing arithmetic, untouched.
+C8B_HD float mmse_sigma2(int mmse, float snr_db, float rssi)
+{
+    if (!mmse || !(snr_db == snr_db) || !(rssi > 0.f)) return 0.f;
+    return (float)(64.0 * (double)rssi / (1.0 + pow(10.0, (double)snr_db / 10.0)));
+}
+// (H^H H + sigma2 I)^-1 in place of the reference's (H^H H)^-1 (lib/demod2_impl.cc:410-429), rows rescaled so that each
+// stream keeps unit gain on itself (unbiased MMSE: the soft demapper's decision regions stay where they are).  a, b, c, d =
+// the Gram matrix as the reference forms it; hi[0..3] = the inverse in the reference's layout.
+C8B_HD void gram_inverse(cf a, cf b, cf c, cf d, float sigma2, cf* hi)
+{
+    cf ar = a, dr = d;
+    if (sigma2 > 0.f) { ar.re = fadd(a.re, sigma2); dr.re = fadd(d.re, sigma2); }
+    const cf inv = cdiv(mk(1.0f, 0.0f), csub(cmul(ar, dr), cmul(b, c)));
+    hi[0] = cmul(inv, dr); hi[1] = cmul(mk(-inv.re, -inv.im), b);
+    hi[2] = cmul(mk(-inv.re, -inv.im), c); hi[3] = cmul(inv, ar);
+    if (sigma2 > 0.f) {
+        // [s1 s2] = [t1 t2] hi with [t1 t2] = [x1 x2] [[a, b], [c, d]]: gain of stream k on itself = (M hi)_kk
+        const float g0 = fadd(cmul(a, hi[0]).re, cmul(b, hi[2]).re), g1 = fadd(cmul(c, hi[1]).re, cmul(d, hi[3]).re);
+        if (g0 > 0.f) { hi[0] = cdivs(hi[0], g0); hi[2] = cdivs(hi[2], g0); }
+        if (g1 > 0.f) { hi[1] = cdivs(hi[1], g1); hi[3] = cdivs(hi[3], g1); }
+    }
+}
+
 template <class Rot>
-C8B_HDN int demod_header2(const c8b_lut* L, Rot rot0, Rot rot1, int nsamp, int lmcs, int llen, const cf* hl, c8b_frame* f, cf* hinv, cf* w2)
+C8B_HDN int demod_header2(const c8b_lut* L, Rot rot0, Rot rot1, int nsamp, int lmcs, int llen, const cf* hl, c8b_frame* f, cf* hinv, cf* w2,
+                          float sigma2 = 0.f)
 {
     Mod m;
     m.format = m.sumu = m.ampdu = m.nSym = m.nSymSamp = m.nSD = m.nSP = m.nSS = m.nLTF = 0;
@@ -720,9 +748,7 @@ C8B_HDN int demod_header2(const c8b_lut* L, Rot rot0, Rot rot1, int nsamp, int l
                 const cf b = cadd(cmul(H[i][0], cconj(H[i][2])), cmul(H[i][1], cconj(H[i][3])));
                 const cf c = cadd(cmul(H[i][2], cconj(H[i][0])), cmul(H[i][3], cconj(H[i][1])));
                 const cf d = cadd(cmul(H[i][2], cconj(H[i][2])), cmul(H[i][3], cconj(H[i][3])));
-                const cf inv = cdiv(mk(1.0f, 0.0f), csub(cmul(a, d), cmul(b, c)));
-                HI[i][0] = cmul(inv, d); HI[i][1] = cmul(mk(-inv.re, -inv.im), b);
-                HI[i][2] = cmul(mk(-inv.re, -inv.im), c); HI[i][3] = cmul(inv, a);
+                gram_inverse(a, b, c, d, sigma2, HI[i]);
             }
             for (int q = 0; q < 4; q++) {
                 cf t1, t2;

@@ -50,11 +50,11 @@ class Receiver:
     """One context = one GPU + one stream.  `blob`: LUT blob to load (default: build locally; multi-GPU
     runs pass the blob broadcast from rank 0)."""
 
-    def __init__(self, device=0, chunk_items=0, max_item_len=0, max_frames=1, mupos=0, mugid=0, blob=None, overlap=True, decode_mode=0, frontend_mode=0):
+    def __init__(self, device=0, chunk_items=0, max_item_len=0, max_frames=1, mupos=0, mugid=0, blob=None, overlap=True, decode_mode=0, frontend_mode=0, mmse=0):
         self.L = _cabi.lib()
         if self.L.c8b_device_count() <= 0:
             raise C8bError("no CUDA device visible: gr-ieee80211_b200 has no CPU path")
-        cfg = C8bCfg(device=device, chunk_items=chunk_items, max_item_len=max_item_len, max_frames=max_frames, mupos=mupos, mugid=mugid, no_overlap=0 if overlap else 1, decode_mode=decode_mode, frontend_mode=frontend_mode)
+        cfg = C8bCfg(device=device, chunk_items=chunk_items, max_item_len=max_item_len, max_frames=max_frames, mupos=mupos, mugid=mugid, no_overlap=0 if overlap else 1, decode_mode=decode_mode, frontend_mode=frontend_mode, mmse=mmse)
         self.max_frames = max(1, int(max_frames))
         h = C.c_void_p()
         rc = self.L.c8b_create(C.byref(cfg), C.byref(h))
@@ -116,6 +116,16 @@ class Receiver:
         frames = np.zeros(ns, FRAME_DTYPE)
         pdu = np.zeros(ns * pdu_stride, np.uint8)
         self._ck(self.L.c8b_rx_batch(self.h, ptr(iqf), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch")
+        return frames, pdu.reshape(ns, pdu_stride)
+
+    def rx_batch_sc16(self, iq16, off, length, pdu_stride=4400):
+        """iq16: int16 array of interleaved (I, Q) pairs (UHD sc16 wire format), shape [n, 2] or [2 n]; off / length in samples"""
+        q = np.ascontiguousarray(iq16, np.int16).reshape(-1)
+        off, length = self._items(off, length, q.size // 2)
+        n, ns = off.size, off.size * self.max_frames
+        frames = np.zeros(ns, FRAME_DTYPE)
+        pdu = np.zeros(ns * pdu_stride, np.uint8)
+        self._ck(self.L.c8b_rx_batch_sc16(self.h, ptr(q), ptr(off), ptr(length), n, ptr(frames), ptr(pdu), pdu_stride), "c8b_rx_batch_sc16")
         return frames, pdu.reshape(ns, pdu_stride)
 
     def rx_batch2(self, iq0, iq1, off, length, pdu_stride=4400):
@@ -186,6 +196,22 @@ class Receiver:
         iq = np.zeros(int(offs[-1]), np.complex64)
         self._ck(self.L.c8b_tx_batch(self.h, ptr(arena), arena.size, ptr(d), d.size, multiplier, seed, ptr(iq.view(np.float32)), iq.size), "c8b_tx_batch")
         return iq, offs
+
+    def tx_from_udp(self, datagrams, gap=400, multiplier=12.0, seed=93):
+        """MAC -> PHY datagrams [format][mcs][nss][len16 LE][PSDU] (lib/pktgen_impl.cc:57-70, tools/phy80211.py genPktGrData) ->
+        (iq, descriptors): one frame per accepted datagram, `gap` zeros around each; a skipped datagram has psdu_len -1"""
+        blob = np.frombuffer(b"".join(bytes(d) for d in datagrams) + b"\0", np.uint8).copy()
+        ln = np.array([len(d) for d in datagrams], np.int32)
+        off = np.concatenate([[0], np.cumsum(ln[:-1])]).astype(np.int64) if len(datagrams) else np.zeros(0, np.int64)
+        cap = int(sum(2 * gap + 80 * (8 + (len(d) * 8 + 22) // 24 + 2) for d in datagrams)) + gap + 1024
+        iq = np.zeros(cap, np.complex64)
+        desc = np.zeros(max(len(datagrams), 1), TXFRAME_DTYPE)
+        used = C.c_int64(0)
+        rc = self.L.c8b_tx_from_udp(self.h, ptr(blob), ptr(off), ptr(ln), len(datagrams), gap, multiplier, seed, ptr(iq.view(np.float32)),
+                                    iq.size, C.byref(used), ptr(desc))
+        if rc < 0:
+            self._ck(rc, "c8b_tx_from_udp")
+        return iq[:used.value].copy(), desc[:len(datagrams)]
 
     def tx_random_psdu_dev(self, d_psdu_ptr, psdu_bytes, desc, seed=1):
         _producer_sync()

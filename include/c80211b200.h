@@ -114,7 +114,10 @@ typedef struct c8b_cfg {
     int32_t decode_mode;     /* 0: pick by batch size; 1: one warp per frame pair (k_viterbi, low latency);
                                 2: one thread per frame (k_viterbi_tp, throughput)                        */
     int32_t frontend_mode;   /* 0: warp-cooperative detect / header kernels; 1: one thread per item (k_detect, k_header) */
-    int32_t reserved[5];
+    int32_t mmse;            /* 2x2 equaliser of demod2: 0 = zero forcing (H^H H)^-1 H^H as the reference does
+                                (lib/demod2_impl.cc:410-429); 1 = MMSE (H^H H + sigma^2 I)^-1 H^H, unbiased, sigma^2 from sync's
+                                snr / rssi tags (north_star "LS/MMSE"; off by default: parity tests run the reference's form) */
+    int32_t reserved[4];
 } c8b_cfg;
 
 typedef struct c8b_ctx c8b_ctx;
@@ -147,6 +150,12 @@ int  c8b_rx_batch(c8b_ctx* ctx, const float* h_iq, const int64_t* off, const int
                   c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
 int  c8b_rx_batch_dev(c8b_ctx* ctx, const float* d_iq, const int64_t* off, const int32_t* len, int nitems,
                       c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
+/* as c8b_rx_batch with the capture in the radio's wire format: interleaved int16 (I, Q) pairs (UHD "sc16"), half the bytes
+ * of fc32 across PCIe.  Each sample is widened on the device to the float the reference's source block (UHD's sc16 -> fc32
+ * converter in front of examples/rx.grc) would have produced, x * (1 / 32768), so frames and PDUs equal c8b_rx_batch on the
+ * widened capture byte for byte.  off / len in samples. */
+int  c8b_rx_batch_sc16(c8b_ctx* ctx, const int16_t* h_iq, const int64_t* off, const int32_t* len, int nitems,
+                       c8b_frame* frames, uint8_t* pdu, int64_t pdu_stride);
 /* 2x2 receive (examples/rx2.grc:676-692: antenna 0 feeds presiso/trigger/sync, both antennas feed signal2 ->
  * demod2): h_iq0 / h_iq1 are the two antennas' captures with the SAME item offsets/lengths. */
 int  c8b_rx_batch2(c8b_ctx* ctx, const float* h_iq0, const float* h_iq1, const int64_t* off, const int32_t* len, int nitems,
@@ -274,6 +283,22 @@ int  c8b_tx_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, c
  * FCS (tools/mac80211.py:36-47); VHT regions (psdu_len a multiple of 4) get the one-MPDU A-MPDU delimiter of
  * tools/mac80211.py:333-360 in front.  A frame decoded by the receive path returns exactly these bytes. */
 int  c8b_tx_random_psdu_dev(c8b_ctx* ctx, uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, uint64_t seed);
+
+/* MAC -> PHY wire format: what the reference's TX chain takes on its UDP socket (lib/pktgen_impl.cc:57-70 msgRead, :96-118
+ * pktPop; written by tools/phy80211.py:1126-1137 genPktGrData): one datagram per frame,
+ *     [format:1][mcs:1][nss:1][len:2 little endian][len PSDU bytes]      (format 0 L, 1 HT, 2 VHT; VHT PSDU = A-MPDU)
+ * c8b_tx_udp_parse (host only, no GPU): checks one datagram the way pktPop does (>= 5 bytes, len <= 4095, the datagram holds
+ * len bytes after the header) and fills format / mcs / psdu_len of *f; *psdu points at the PSDU inside pkt.  Returns the
+ * number of spatial streams (1 here) or C8B_ERR_ARG for a malformed datagram, the MU format (3, two users per datagram) and
+ * nss != 1 (the synthesiser is one spatial stream).
+ * c8b_tx_from_udp: npkts datagrams (datagram k = pkts[pkt_off[k] .. pkt_off[k] + pkt_len[k])) -> one IQ arena: every
+ * accepted datagram becomes a frame, `gap` zero samples in front of each and after the last (tools/pktGenExample.py
+ * gapLen); malformed ones are skipped like the reference does.  frames_out (npkts records, may be NULL) gets the
+ * descriptors used (out_off = where each frame starts; psdu_len = -1 for a skipped datagram); *iq_used = samples written.
+ * Returns the number of frames synthesised or a negative error (C8B_ERR_FULL: iq_cap too small). */
+int  c8b_tx_udp_parse(const uint8_t* pkt, int pkt_len, c8b_txframe* f, const uint8_t** psdu);
+int  c8b_tx_from_udp(c8b_ctx* ctx, const uint8_t* pkts, const int64_t* pkt_off, const int32_t* pkt_len, int npkts, int gap,
+                     float multiplier, int scrambler_seed, float* h_iq, int64_t iq_cap, int64_t* iq_used, c8b_txframe* frames_out);
 
 /* ---- staged entry points (host buffers in/out; used for parity tests and ncu captures) ---------
  * Each mirrors one reference block on whole arrays. */

@@ -98,3 +98,31 @@ def test_lut_blob_matches_reference_tables(golden):
     assert np.allclose(twr, w.real, atol=1e-7) and np.allclose(twi, w.imag, atol=1e-7)
     assert sigDemap[0] == -1 and (sigDemap >= 0).sum() == 48 and (binL < 255).sum() == 48 and (binNL < 255).sum() == 52
     assert binNL[1] == 26 and binL[1] == 24 and binNL[36] == 0 and binL[38] == 0
+
+
+def test_tx_udp_parse_follows_pktgen():
+    """MAC -> PHY datagram [format][mcs][nss][len16 LE][PSDU] (lib/pktgen_impl.cc:57-70 msgRead, :96-118 pktPop; writer
+    tools/phy80211.py:1126-1137 genPktGrData): host-side parser of c8b_tx_from_udp, no GPU needed"""
+    import ctypes as C
+    import struct
+    pkg = load_pkg()
+    L = pkg._cabi.lib()
+    f = np.zeros(1, pkg.TXFRAME_DTYPE)
+    body = C.c_void_p()
+
+    def parse(b):
+        buf = (C.c_ubyte * max(len(b), 1)).from_buffer_copy(bytes(b) if b else b"\0")
+        rc = L.c8b_tx_udp_parse(buf, len(b), f.ctypes.data, C.byref(body))
+        return rc, (body.value - C.addressof(buf) if rc > 0 else None)
+
+    mpdu = bytes(range(100))
+    rc, o = parse(struct.pack("<BBBH", 2, 7, 1, len(mpdu)) + mpdu)          # genPktGrData(mpdu, VHT MCS7 one stream)
+    assert rc == 1 and o == 5 and (f[0]["format"], f[0]["mcs"], f[0]["psdu_len"]) == (2, 7, 100)
+    rc, _ = parse(struct.pack("<BBBH", 0, 3, 1, 40) + bytes(60))             # longer datagram than len: accepted (pktPop checks >=)
+    assert rc == 1 and f[0]["psdu_len"] == 40
+    assert parse(b"\x00\x00\x01\x10")[0] < 0                                 # under 5 bytes (msgRead :65-67)
+    assert parse(struct.pack("<BBBH", 0, 0, 1, 50) + bytes(49))[0] < 0       # shorter than its len field (pktPop :108-111)
+    assert parse(struct.pack("<BBBH", 0, 0, 1, 4096) + bytes(4096))[0] < 0   # len > 4095
+    assert parse(struct.pack("<BBBH", 3, 0, 1, 10) + bytes(10))[0] < 0       # C8P_F_VHT_MU: two users per datagram
+    assert parse(struct.pack("<BBBH", 1, 8, 2, 10) + bytes(10))[0] < 0       # two spatial streams: not this synthesiser
+    assert parse(struct.pack("<BBBH", 0, 9, 1, 10) + bytes(10))[0] < 0       # no legacy MCS 9

@@ -146,3 +146,27 @@ def test_two_items_each_with_several_frames(golden):
                 assert bytes(pdu[s, :fr[s]["pdu_bytes"]]) == recs[k]
             else:
                 assert fr[s]["status"] == 9
+
+
+def test_sc16_ingest_equals_fc32_on_the_widened_capture(golden):
+    """c8b_rx_batch_sc16: the capture as interleaved int16 (UHD sc16) -- widened on the device by x * (1 / 32768), exactly the
+    floats the fc32 entry point gets from the same quantised capture: frame records and PDUs byte for byte, multi-chunk"""
+    pkg = load_pkg()
+    g = golden["frames_siso"]
+    rng = np.random.default_rng(5)
+    s = 0.1875 / np.sqrt(2 * 10 ** 2.8)
+    x = g["iq"] + s * (rng.standard_normal(g["iq"].size) + 1j * rng.standard_normal(g["iq"].size))
+    q = np.empty((x.size, 2), np.int16)
+    q[:, 0] = np.clip(np.round(x.real * 32768 * 0.9), -32768, 32767)
+    q[:, 1] = np.clip(np.round(x.imag * 32768 * 0.9), -32768, 32767)
+    wide = (q[:, 0].astype(np.float32) * np.float32(1 / 32768) + 1j * (q[:, 1].astype(np.float32) * np.float32(1 / 32768))).astype(np.complex64)
+    offs = g["offs"]
+    off, ln = offs[:-1], np.diff(offs).astype(np.int32)
+    for chunk in (0, 7):
+        rx = pkg.Receiver(device=0, chunk_items=chunk)
+        fa, pa = rx.rx_batch(wide, off, ln)
+        fb, pb = rx.rx_batch_sc16(q, off, ln)
+        fc, pc = rx.rx_batch_sc16(q, off, ln)                   # again: the item table is already resident
+        rx.close()
+        assert fa.tobytes() == fb.tobytes() == fc.tobytes() and np.array_equal(pa, pb) and np.array_equal(pb, pc)
+        assert int((fa["npdu"] == 1).sum()) >= 30

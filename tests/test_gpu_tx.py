@@ -164,3 +164,56 @@ def test_device_traffic_closed_loop():
             assert (f["status"], f["npdu"]) == (fo[0]["status"], fo[0]["npdu"]), (i, d[i], f["status"], fo[0]["status"])
             lost.append((i, int(f["status"])))
     assert len(lost) <= n // 200, lost
+
+
+def test_udp_in_udp_out_loop():
+    """both directions of the UDP PDU framing: MAC -> PHY datagrams [format][mcs][nss][len16][PSDU]
+    (lib/pktgen_impl.cc:57-70, tools/phy80211.py genPktGrData) through c8b_tx_from_udp, the waveform through the receive
+    chain, and PHY -> MAC records [format][len16][MPDU][mcs] (lib/decode_impl.cc:512-516) carrying the same bytes"""
+    import struct
+    import zlib
+    pkg = load_pkg()
+    rng = np.random.default_rng(11)
+
+    def mpdu(n):
+        b = bytes(rng.integers(0, 256, n - 4, dtype=np.uint8))
+        return b + struct.pack("<I", zlib.crc32(b))
+
+    def ampdu(m):                                                # tools/mac80211.py:333-360, one subframe, EOF set
+        ln = len(m)
+        hdr = bytearray(4)
+        hdr[0] = 1 | ((ln >> 12 & 1) << 2) | ((ln >> 13 & 1) << 3) | ((ln & 0xF) << 4)
+        hdr[1] = (ln >> 4) & 0xFF
+        c = 0xFF
+        for bit in range(16):
+            b = (hdr[bit // 8] >> (bit % 8)) & 1
+            top = (c >> 7) & 1
+            c = (c << 1) & 0xFF
+            if top ^ b:
+                c ^= 0x07
+        c ^= 0xFF
+        hdr[2] = int("{:08b}".format(c)[::-1], 2)
+        hdr[3] = 0x4E
+        out = bytes(hdr) + m
+        return out + bytes((-len(out)) % 4)
+
+    sent, dgrams = [], []
+    for fmt, mcs, n in [(0, 0, 60), (0, 7, 300), (1, 3, 500), (1, 7, 1200), (2, 0, 100), (2, 5, 700), (2, 8, 1500)]:
+        m = mpdu(n)
+        psdu = ampdu(m) if fmt == 2 else m
+        sent.append((fmt, mcs, m))
+        dgrams.append(struct.pack("<BBBH", fmt, mcs, 1, len(psdu)) + psdu)
+    dgrams.insert(3, b"\x01\x02")                                # junk datagrams are skipped, like pktgen does
+    dgrams.insert(5, struct.pack("<BBBH", 3, 0, 1, 4) + bytes(4))
+    rx = pkg.Receiver(device=0, max_frames=16)
+    iq, desc = rx.tx_from_udp(dgrams, gap=500)
+    assert [int(d["psdu_len"]) for d in desc].count(-1) == 2 and iq.size > 0
+    fr, pdu = rx.rx_batch(iq, [0], [iq.size])
+    rx.close()
+    recs = []
+    for k in range(16):
+        if fr[k]["npdu"] > 0:
+            recs += pkg.blocks.split_messages(bytes(pdu[k, :fr[k]["pdu_bytes"]]))
+    assert len(recs) == len(sent)
+    for r, (fmt, mcs, m) in zip(recs, sent):
+        assert r == bytes([fmt]) + struct.pack("<H", len(m)) + m + bytes([mcs])
