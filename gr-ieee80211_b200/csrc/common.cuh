@@ -57,11 +57,11 @@ void c8b_tx_scrambler(int seed, uint32_t out[4]);
 void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
                    float2* d_out, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);
 void c8b_launch_tx_fill(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, uint8_t* d_psdu, uint64_t seed, cudaStream_t st);
-size_t c8b_detect_multi_scratch(int nitems, int maxCand);
+size_t c8b_detect_multi_scratch(int nitems, int maxLen);   // maxLen: longest item, samples
 void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                              int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
-                             float2* chan, c8b_scan* scans, void* scratch, int maxCand, cudaStream_t st);
+                             float2* chan, c8b_scan* scans, void* scratch, int maxLen, cudaStream_t st);
 void c8b_launch_trigger_events(const float* d_preac, int n, const int64_t* d_off, const int32_t* d_len, uint32_t* d_mask, const c8b_scan* d_scan,
-                               void* scratch, int maxCand, int32_t* d_out, cudaStream_t st);
+                               void* scratch, int cap, int32_t* d_out, cudaStream_t st);
 // the device copy of the table blob of a context (null until c8b_lut_load); used by blocks.cu
 extern "C" const c8b_lut* c8b_ctx_lut(const c8b_ctx* ctx);

@@ -41,6 +41,9 @@ struct c8b_ctx {
         int64_t overruns = 0;   // windows dropped because nothing in them could be decided
     } strm;
     DevBuf sw[2][2], scan;      // [antenna][ping-pong]
+    // pinned read-back staging of a stream pass: frame records + scan result, then the PDU area of the frames taken
+    void* hStage = nullptr;
+    size_t hStageCap = 0;
     DevBuf cand;                // candidate records of the multi-frame detect path
     DevBuf txf, txplan, txpsdu, txiq;   // transmit synthesiser: descriptors, plans, staged PSDU bytes / samples
     c8b_scan* scanDev = nullptr;   // non-null while run_chunk serves a stream window
@@ -194,6 +197,7 @@ void c8b_destroy(c8b_ctx* ctx)
     for (auto b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->hStage) cudaFreeHost(ctx->hStage);
     if (ctx->tabOff) cudaFreeHost(ctx->tabOff);
     if (ctx->tabLen) cudaFreeHost(ctx->tabLen);
     if (ctx->evTab) cudaEventDestroy(ctx->evTab);
@@ -432,13 +436,12 @@ static int run_chunk(c8b_ctx* ctx, const float2* d_iq, const int64_t* d_off, con
     {
         // few long items with many frames each (a capture, a stream window): the per-trigger work runs in parallel
         const bool multi = ctx->cfg.frontend_mode == 0 && maxf > 1 && n <= 64;
-        const int maxCand = 4 * maxf + 64;
-        if (multi) EN(cand, c8b_detect_multi_scratch(n, maxCand));
+        if (multi) EN(cand, c8b_detect_multi_scratch(n, pl.maxLen));
         StageTimer tm(ctx, C8B_K_DETECT);
         if (multi)
             c8b_launch_detect_multi(ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p,
                                     (const uint32_t*)ctx->mask.p, maskStride, d_frames + (size_t)b * maxf, (float2*)ctx->chan.p, ctx->scanDev,
-                                    ctx->cand.p, maxCand, ctx->st);
+                                    ctx->cand.p, pl.maxLen, ctx->st);
         else
             (ctx->cfg.frontend_mode == 1 ? c8b_launch_detect : c8b_launch_detect_w)(
                 ctx->d_lut, iq, d_off + b, d_len + b, n, b, maxf, pl.base, (const float*)ctx->preac.p, (const uint32_t*)ctx->mask.p, maskStride,
@@ -500,7 +503,8 @@ static int upload_items_range(c8b_ctx* ctx, const int64_t* off, const int32_t* l
         if (ctx->evTab) cudaEventSynchronize(ctx->evTab);
         EN(off, (size_t)n * sizeof(int64_t));
         EN(len, (size_t)n * sizeof(int32_t));
-        if (ctx->tabOff) cudaFreeHost(ctx->tabOff);
+        if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    if (ctx->tabOff) cudaFreeHost(ctx->tabOff);
         if (ctx->tabLen) cudaFreeHost(ctx->tabLen);
         ctx->tabOff = nullptr; ctx->tabLen = nullptr; ctx->tabCap = 0; ctx->tabLo = ctx->tabHi = 0;
         const size_t cap = (size_t)n + (size_t)n / 8 + 64;
@@ -759,7 +763,7 @@ int c8b_trigger_events(c8b_ctx* ctx, const float* h_preac, int64_t n, int from, 
     CK(cudaSetDevice(ctx->device));
     EN(preac, (size_t)(n + 64) * sizeof(float));
     EN(mask, (size_t)((n + 31) / 32 + 2) * sizeof(uint32_t));
-    EN(cand, c8b_detect_multi_scratch(1, cap));
+    EN(cand, c8b_detect_multi_scratch(1, (int)n));
     EN(scan, sizeof(c8b_scan));
     EN(trig, (size_t)(4 + 4 * cap) * sizeof(int32_t));
     const int64_t off = 0;
@@ -959,28 +963,43 @@ static int stream_process(c8b_ctx* ctx, bool flush, c8b_frame* frames, int frame
     ctx->scanDev = nullptr;
     if (r) return r;
     join_viterbi(ctx);
-    std::vector<c8b_frame> fr((size_t)maxf);
-    CK(cudaMemcpyAsync(fr.data(), ctx->frames.p, (size_t)maxf * sizeof(c8b_frame), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(&sc, ctx->scan.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
+    // read back through ONE pinned staging buffer: [frame records][scan result] in the first round trip, the PDU area of the
+    // frames taken (contiguous slots) in the second -- not a copy per frame
+    const size_t frBytes = (size_t)maxf * sizeof(c8b_frame), need = frBytes + 256 + (size_t)maxf * pdu_stride;
+    if (ctx->hStageCap < need) {
+        if (ctx->hStage) cudaFreeHost(ctx->hStage);
+        ctx->hStage = nullptr; ctx->hStageCap = 0;
+        CK(cudaHostAlloc(&ctx->hStage, need + need / 4, cudaHostAllocDefault));
+        ctx->hStageCap = need + need / 4;
+    }
+    c8b_frame* fr = reinterpret_cast<c8b_frame*>(ctx->hStage);
+    c8b_scan* hsc = reinterpret_cast<c8b_scan*>(reinterpret_cast<uint8_t*>(ctx->hStage) + frBytes);
+    uint8_t* hpdu = reinterpret_cast<uint8_t*>(ctx->hStage) + frBytes + 256;
+    CK(cudaMemcpyAsync(fr, ctx->frames.p, frBytes, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hsc, ctx->scan.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    sc = *hsc;
     *stalled = sc.stalled;
     int take = sc.nf;
     if (flush) {                                                   // end of stream: every record the batch semantics produced
         take = 0;
         while (take < maxf && fr[take].status != C8B_ST_EMPTY && fr[take].nsamp > 0) take++;
     }
+    if (*nframes + take > frames_cap) { ctx->err = "c8b_stream_push: more frames than frames_cap"; return C8B_ERR_FULL; }
+    bool anyPdu = false;
+    for (int k = 0; k < take; k++) anyPdu |= fr[k].pdu_bytes > 0;
+    if (anyPdu) {
+        CK(cudaMemcpyAsync(hpdu, ctx->pdu.p, (size_t)take * pdu_stride, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
     for (int k = 0; k < take; k++) {
-        if (*nframes >= frames_cap) { ctx->err = "c8b_stream_push: more frames than frames_cap"; return C8B_ERR_FULL; }
         const int o = (*nframes)++;
         frames[o] = fr[k];
         frames[o].item = o;
         frames[o].pdu_off = (int64_t)o * pdu_stride;
         frame_base[o] = S.base;
-        if (fr[k].pdu_bytes > 0)
-            CK(cudaMemcpyAsync(pdu + (size_t)o * pdu_stride, (const uint8_t*)ctx->pdu.p + (size_t)k * pdu_stride, (size_t)fr[k].pdu_bytes,
-                               cudaMemcpyDeviceToHost, ctx->st));
+        if (fr[k].pdu_bytes > 0) memcpy(pdu + (size_t)o * pdu_stride, hpdu + (size_t)k * pdu_stride, (size_t)fr[k].pdu_bytes);
     }
-    CK(cudaStreamSynchronize(ctx->st));
     if (flush) {
         S.base += S.fill; S.fill = 0; S.from = 0; S.posAbs = S.base;
         return C8B_OK;

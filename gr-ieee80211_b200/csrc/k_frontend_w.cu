@@ -415,18 +415,72 @@ struct Cand {
 };
 struct CandHead { int32_t n, overflow, safeEnd, nTrig; };
 
+// The scan itself is cut into SEGMENTS that run in parallel, one warp each.  A cut may sit at any bitmap word that follows
+// C8B_CUT_WORDS all-zero words (192 samples below the threshold): the FSM is then in its reset state (nPlateau, conjAc and
+// fPlateauEnd clear at the first sample below the threshold; a count-down armed by an earlier plateau has run out after 80
+// samples), and no sync hold-off is pending (a trigger fires 80 samples after the sample that armed it and holds sync for
+// 111: 191 in all) -- exactly the state the scan of the whole item has there, so the segments' triggers, latches and
+// restart points are the ones of one serial pass.  Nominal cuts every C8B_SEG_WORDS words are moved forward to the first
+// such word (a segment with no quiet stretch simply runs on into the next); between frames of a real capture the channel
+// is quiet for longer than 192 samples (SIFS is 320), so a 1 M-sample window splits into ~128 segments.
+constexpr int C8B_CUT_WORDS = 6;               // all-zero bitmap words in front of a cut (>= 191 samples)
+constexpr int C8B_SEG_WORDS = 256;             // nominal segment: 8192 samples
+constexpr int C8B_SEG_CAP = 96;                // candidates per segment (a hold-off of 111 samples: <= 74 per 8192)
+
+struct SegTab { int32_t nseg; int32_t start[1]; };             // start[0 .. nseg], start[nseg] = item length (variable length)
+__host__ __device__ inline size_t segtab_bytes(int nsegMax) { return ((size_t)(nsegMax + 2) * sizeof(int32_t) + 15) & ~(size_t)15; }
+
+__global__ void __launch_bounds__(256)
+k_seg_cuts(const int32_t* __restrict__ len, int nitems, const uint32_t* __restrict__ maskAll, int maskStride, const c8b_scan* __restrict__ scans,
+           uint8_t* __restrict__ tabs, int nsegMax, int segWords)
+{
+    const int it = blockIdx.x;
+    if (it >= nitems) return;
+    SegTab* tb = reinterpret_cast<SegTab*>(tabs + (size_t)it * segtab_bytes(nsegMax));
+    const uint32_t* __restrict__ mask = maskAll + (size_t)it * maskStride;
+    const int n = len[it], from = scans ? scans[it].from : 0;
+    const int nwords = n >> 5;                                  // whole words only: the partial last word stays in the last segment
+    const int w0 = from >> 5;
+    __shared__ int32_t cut[1024];
+    const int nnom = min(nsegMax - 1, 1023);
+    for (int k = threadIdx.x + 1; k <= nnom; k += blockDim.x) {
+        const long long wk = (long long)w0 + (long long)k * segWords;
+        int found = -1;
+        if (wk < nwords) {
+            int zeros = 0;
+            const int lo = (int)wk - C8B_CUT_WORDS, hi = min(nwords, (int)wk + segWords);
+            for (int w = max(lo, w0 + 1); w < hi; w++) {       // first w >= wk with words w-6 .. w-1 all zero
+                if (w >= (int)wk && zeros >= C8B_CUT_WORDS) { found = w; break; }
+                zeros = mask[w] == 0u ? zeros + 1 : 0;
+            }
+        }
+        cut[k] = found;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ns = 0;
+        tb->start[ns++] = from;
+        for (int k = 1; k <= nnom; k++) if (cut[k] > 0) tb->start[ns++] = cut[k] * 32;
+        tb->start[ns] = n;
+        tb->nseg = ns;
+    }
+}
+
 __global__ void __launch_bounds__(32)
 k_trig_scan(const int32_t* __restrict__ len, int nitems, int64_t outBase, const int64_t* __restrict__ off, const float* __restrict__ preacAll,
-            const uint32_t* __restrict__ maskAll, int maskStride, const c8b_scan* __restrict__ scans, Cand* __restrict__ cands,
-            CandHead* __restrict__ heads, int maxCand)
+            const uint32_t* __restrict__ maskAll, int maskStride, const uint8_t* __restrict__ tabs, int nsegMax, Cand* __restrict__ cands,
+            CandHead* __restrict__ heads)
 {
-    const int lane = threadIdx.x, it = blockIdx.x;
+    const int lane = threadIdx.x, it = blockIdx.x / nsegMax, sg = blockIdx.x % nsegMax;
     if (it >= nitems) return;
+    const SegTab* tb = reinterpret_cast<const SegTab*>(tabs + (size_t)it * segtab_bytes(nsegMax));
+    if (sg >= tb->nseg) return;
     const float* __restrict__ preac = preacAll + (off[it] - outBase);
     const uint32_t* __restrict__ mask = maskAll + (size_t)it * maskStride;
     const int n = len[it];
-    Cand* __restrict__ cd = cands + (size_t)it * maxCand;
-    const int from = scans ? scans[it].from : 0;
+    const int maxCand = C8B_SEG_CAP;
+    Cand* __restrict__ cd = cands + ((size_t)it * nsegMax + sg) * C8B_SEG_CAP;
+    const int from = tb->start[sg], segEnd = tb->start[sg + 1];
     TrigState ts;
     trig_reset(ts);
     int latch = -1, skipUntil = 0, nc = 0, nTrig = 0, safe = from, overflow = 0;
@@ -437,7 +491,7 @@ k_trig_scan(const int32_t* __restrict__ len, int nitems, int64_t outBase, const 
     __shared__ float pvb[SB * 1024];
     int supBase = -(1 << 30);
     uint32_t nzs[SB] = { 0, 0, 0, 0 }, mvs[SB] = { 0, 0, 0, 0 };
-    const int nwords = (n + 31) >> 5;
+    const int nwords = (segEnd + 31) >> 5;                       // (cuts are word aligned; the last segment ends with the item)
     for (int w = from >> 5; w < nwords && !done;) {
         const int kfirst = w == (from >> 5) ? (from & 31) : 0;
         int jb = 0, blkBase = 0;
@@ -510,21 +564,26 @@ k_trig_scan(const int32_t* __restrict__ len, int nitems, int64_t outBase, const 
         w++;
     }
     int safeEnd = -1;                                             // scan ran to the end in the reset state: everything is decided
-    if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && n >= skipUntil) safeEnd = n;
-    if (lane == 0) { heads[it].n = nc; heads[it].overflow = overflow; heads[it].safeEnd = safeEnd >= 0 ? safeEnd : safe; heads[it].nTrig = nTrig; }
+    if (!done && ts.nPlateau == 0 && ts.fPlateau == 0 && segEnd >= skipUntil) safeEnd = segEnd;
+    if (lane == 0) {
+        CandHead* hd = heads + (size_t)it * nsegMax + sg;
+        hd->n = nc; hd->overflow = overflow; hd->safeEnd = safeEnd >= 0 ? safeEnd : safe; hd->nTrig = nTrig;
+    }
 }
 
 __global__ void __launch_bounds__(FW * 32)
 k_cand_eval(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
-            int nitems, Cand* __restrict__ cands, const CandHead* __restrict__ heads, int maxCand)
+            int nitems, Cand* __restrict__ cands, const CandHead* __restrict__ heads, const uint8_t* __restrict__ tabs, int nsegMax)
 {
     __shared__ Ws ws[FW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t gid = (int64_t)blockIdx.x * FW + warp;
-    const int it = (int)(gid / maxCand), c = (int)(gid % maxCand);
-    if (it >= nitems || c >= heads[it].n) return;
+    const int64_t slot = gid / C8B_SEG_CAP;                        // (item, segment)
+    const int it = (int)(slot / nsegMax), sg = (int)(slot % nsegMax), c = (int)(gid % C8B_SEG_CAP);
+    if (it >= nitems) return;
+    if (sg >= reinterpret_cast<const SegTab*>(tabs + (size_t)it * segtab_bytes(nsegMax))->nseg || c >= heads[slot].n) return;
     Ws& W = ws[warp];
-    Cand* __restrict__ cd = cands + (size_t)it * maxCand + c;
+    Cand* __restrict__ cd = cands + (size_t)slot * C8B_SEG_CAP + c;
     if (cd->stall) return;
     const cf* __restrict__ x = reinterpret_cast<const cf*>(iq + off[it]);
     const int n = len[it], i = cd->trig, latch = cd->latch;
@@ -544,14 +603,13 @@ k_cand_eval(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, cons
 
 __global__ void __launch_bounds__(32)
 k_cand_accept(const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, const Cand* __restrict__ cands,
-              const CandHead* __restrict__ heads, int maxCand, c8b_frame* __restrict__ frames, float2* __restrict__ chan,
-              c8b_scan* __restrict__ scans)
+              const CandHead* __restrict__ heads, const uint8_t* __restrict__ tabs, int nsegMax, c8b_frame* __restrict__ frames,
+              float2* __restrict__ chan, c8b_scan* __restrict__ scans)
 {
     const int it = blockIdx.x, lane = threadIdx.x;                // one warp per item: the rules run uniformly, the copies by lane
     if (it >= nitems) return;
     const int n = len[it];
-    const Cand* __restrict__ cd = cands + (size_t)it * maxCand;
-    const CandHead hd = heads[it];
+    const int nseg = reinterpret_cast<const SegTab*>(tabs + (size_t)it * segtab_bytes(nsegMax))->nseg;
     c8b_frame* __restrict__ f = frames + (size_t)it * maxf;
     float2* __restrict__ h = chan + (size_t)it * maxf * 64;
     c8b_scan* sc = scans ? scans + it : nullptr;
@@ -562,9 +620,16 @@ k_cand_accept(const int32_t* __restrict__ len, int nitems, int itemBase, int max
     int pos = sc ? sc->pos0 : 0, nf = 0, nEv = 0, nLsigFail = 0;
     int safe = sc ? sc->from : 0, posS = pos, nfS = 0, stalled = 0;
     bool syncStalled = false, sigStalled = false, done = false;
+    int nTrig = 0, nCand = 0;
+    CandHead hd = heads[(size_t)it * nsegMax];
+    for (int sg = 0; sg < nseg && !done; sg++) {                  // the segments in stream order: one candidate list
+    hd = heads[(size_t)it * nsegMax + sg];
+    const Cand* __restrict__ cd = cands + ((size_t)it * nsegMax + sg) * C8B_SEG_CAP;
+    nTrig += hd.nTrig;
     for (int c = 0; c < hd.n && !done; c++) {
         const Cand& q = cd[c];
-        if (q.safe > safe || c == 0) { safe = q.safe; posS = pos; nfS = nf; }     // the restart point before this trigger's plateau
+        if (q.safe > safe || nCand == 0) { safe = q.safe; posS = pos; nfS = nf; }     // the restart point before this trigger's plateau
+        nCand++;
         if (syncStalled) continue;
         if (q.stall) {
             if (live) { stalled = 1; done = true; } else syncStalled = true;
@@ -591,14 +656,15 @@ k_cand_accept(const int32_t* __restrict__ len, int nitems, int itemBase, int max
         if (pos > n) { done = true; stalled = 1; }
         if (nf >= maxf) { done = true; if (!stalled) stalled = 2; }
     }
-    if (!done && hd.overflow) { done = true; stalled = 2; }       // candidate records used up: the scan stopped there
+    if (!done && hd.overflow) { done = true; stalled = 2; }       // candidate records of this segment used up: its scan stopped there
+    }
     if (!done && !syncStalled) {
-        // the scan's own end state: the restart point it reached after the last candidate
-        if (hd.safeEnd > safe || hd.n == 0) { safe = hd.safeEnd; posS = pos; nfS = nf; }
+        // the scan's own end state: the restart point the last segment reached after its last candidate
+        if (hd.safeEnd > safe || nCand == 0) { safe = hd.safeEnd; posS = pos; nfS = nf; }
     }
     if (lane == 0) {
         if (sc) { sc->safe = safe; sc->pos = posS; sc->nf = nfS; sc->stalled = stalled; }
-        if (nf == 0) f->status = hd.nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
+        if (nf == 0) f->status = nTrig == 0 ? C8B_ST_NO_TRIGGER : nEv == 0 ? C8B_ST_SYNC : (nLsigFail ? C8B_ST_LSIG : C8B_ST_TRUNC);
     }
 }
 
@@ -1089,41 +1155,85 @@ __global__ void k_preac_mask(const float* __restrict__ preac, int n, uint32_t* _
     const uint32_t m = __ballot_sync(FULL, i < n && preac[i < n ? i : 0] > 0.3f);
     if ((threadIdx.x & 31) == 0 && i < n) mask[i >> 5] = m;
 }
-__global__ void k_cand_export(const Cand* __restrict__ cands, const CandHead* __restrict__ heads, int cap, int32_t* __restrict__ out)
+__global__ void k_cand_export(const Cand* __restrict__ cands, const CandHead* __restrict__ heads, const uint8_t* __restrict__ tabs, int nsegMax, int cap,
+                              int32_t* __restrict__ out)
 {
-    const int n = heads[0].n;
-    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = n; out[1] = heads[0].safeEnd; out[2] = heads[0].overflow; out[3] = heads[0].nTrig; }
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n && c < cap; c += gridDim.x * blockDim.x) {
-        out[4 + 4 * c + 0] = cands[c].trig; out[4 + 4 * c + 1] = cands[c].latch; out[4 + 4 * c + 2] = cands[c].safe; out[4 + 4 * c + 3] = cands[c].stall;
+    // one item: the segments' candidate lists concatenated in stream order (single thread: a test entry point)
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nseg = reinterpret_cast<const SegTab*>(tabs)->nseg;
+    int n = 0, overflow = 0, nTrig = 0, safeEnd = 0;
+    bool stop = false;
+    for (int sg = 0; sg < nseg && !stop; sg++) {
+        const CandHead hd = heads[sg];
+        nTrig += hd.nTrig;
+        safeEnd = hd.safeEnd;
+        for (int c = 0; c < hd.n; c++, n++) {
+            const Cand& q = cands[(size_t)sg * C8B_SEG_CAP + c];
+            if (n < cap) { out[4 + 4 * n + 0] = q.trig; out[4 + 4 * n + 1] = q.latch; out[4 + 4 * n + 2] = q.safe; out[4 + 4 * n + 3] = q.stall; }
+            else overflow = 1;
+            if (q.stall) { safeEnd = q.safe; stop = true; n++; break; }   // the serial scan ends at the first stalled trigger
+        }
+        if (hd.overflow) { overflow = 1; stop = true; }
     }
+    out[0] = n < cap ? n : cap; out[1] = safeEnd; out[2] = overflow; out[3] = nTrig;
+}
+}  // namespace
+
+static int seg_words_cfg()
+{
+    // C8B_SEG_WORDS (environment): nominal segment length in bitmap words, for tests that want many cuts in a short capture
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("C8B_SEG_WORDS"); v = e ? atoi(e) : 0; if (v < 8) v = C8B_SEG_WORDS; }
+    return v;
+}
+static int nseg_max_for(int maxLen) { return maxLen / (32 * seg_words_cfg()) + 2; }
+
+size_t c8b_detect_multi_scratch(int nitems, int maxLen)
+{
+    const int nsm = nseg_max_for(maxLen);
+    return (size_t)nitems * (segtab_bytes(nsm) + (size_t)nsm * (sizeof(CandHead) + (size_t)C8B_SEG_CAP * sizeof(Cand))) + 512;
+}
+
+namespace {
+struct MultiScratch { uint8_t* tabs; CandHead* heads; Cand* cands; int nsegMax; };
+MultiScratch carve(void* scratch, int nitems, int maxLen)
+{
+    MultiScratch m;
+    m.nsegMax = nseg_max_for(maxLen);
+    uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
+    m.tabs = p;
+    p += ((size_t)nitems * segtab_bytes(m.nsegMax) + 255) & ~(size_t)255;
+    m.heads = reinterpret_cast<CandHead*>(p);
+    p += ((size_t)nitems * m.nsegMax * sizeof(CandHead) + 255) & ~(size_t)255;
+    m.cands = reinterpret_cast<Cand*>(p);
+    return m;
 }
 }  // namespace
 
 // d_item: {int64 off = 0; int32 len = n} already on the device; out = 4 header ints + 4 ints per event
 void c8b_launch_trigger_events(const float* d_preac, int n, const int64_t* d_off, const int32_t* d_len, uint32_t* d_mask, const c8b_scan* d_scan,
-                               void* scratch, int maxCand, int32_t* d_out, cudaStream_t st)
+                               void* scratch, int cap, int32_t* d_out, cudaStream_t st)
 {
-    CandHead* heads = reinterpret_cast<CandHead*>(scratch);
-    Cand* cands = reinterpret_cast<Cand*>(reinterpret_cast<char*>(scratch) + 256);
+    const MultiScratch m = carve(scratch, 1, n);
+    const int maskStride = (n + 31) / 32 + 1;
     k_preac_mask<<<(n + 255) / 256, 256, 0, st>>>(d_preac, n, d_mask);
-    k_trig_scan<<<1, 32, 0, st>>>(d_len, 1, 0, d_off, d_preac, d_mask, (n + 31) / 32 + 1, d_scan, cands, heads, maxCand);
-    k_cand_export<<<4, 256, 0, st>>>(cands, heads, maxCand, d_out);
+    k_seg_cuts<<<1, 256, 0, st>>>(d_len, 1, d_mask, maskStride, d_scan, m.tabs, m.nsegMax, seg_words_cfg());
+    k_trig_scan<<<m.nsegMax, 32, 0, st>>>(d_len, 1, 0, d_off, d_preac, d_mask, maskStride, m.tabs, m.nsegMax, m.cands, m.heads);
+    k_cand_export<<<1, 32, 0, st>>>(m.cands, m.heads, m.tabs, m.nsegMax, cap, d_out);
 }
 
-size_t c8b_detect_multi_scratch(int nitems, int maxCand) { return (size_t)nitems * maxCand * sizeof(Cand) + (size_t)nitems * sizeof(CandHead) + 256; }
-
-// few long items with many frames each: trigger scan -> per-trigger sync / signal in parallel -> accept rules
+// few long items with many frames each: segment cuts -> trigger scans in parallel -> per-trigger sync / signal in parallel -> accept rules
 void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                              int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
-                             float2* chan, c8b_scan* scans, void* scratch, int maxCand, cudaStream_t st)
+                             float2* chan, c8b_scan* scans, void* scratch, int maxLen, cudaStream_t st)
 {
     if (nitems <= 0) return;
-    CandHead* heads = reinterpret_cast<CandHead*>(scratch);
-    Cand* cands = reinterpret_cast<Cand*>(reinterpret_cast<char*>(scratch) + (((size_t)nitems * sizeof(CandHead) + 255) & ~(size_t)255));
-    k_trig_scan<<<nitems, 32, 0, st>>>(d_len, nitems, outBase, d_off, preac, mask, maskStride, scans, cands, heads, maxCand);
-    const int64_t warps = (int64_t)nitems * maxCand;
-    k_cand_eval<<<(unsigned)((warps + FW - 1) / FW), FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, cands, heads, maxCand);
-    k_cand_accept<<<nitems, 32, 0, st>>>(d_len, nitems, itemBase, maxf, cands, heads, maxCand, frames, chan, scans);
+    const MultiScratch m = carve(scratch, nitems, maxLen);
+    k_seg_cuts<<<nitems, 256, 0, st>>>(d_len, nitems, mask, maskStride, scans, m.tabs, m.nsegMax, seg_words_cfg());
+    k_trig_scan<<<nitems * m.nsegMax, 32, 0, st>>>(d_len, nitems, outBase, d_off, preac, mask, maskStride, m.tabs, m.nsegMax, m.cands, m.heads);
+    const int64_t warps = (int64_t)nitems * m.nsegMax * C8B_SEG_CAP;
+    k_cand_eval<<<(unsigned)((warps + FW - 1) / FW), FW * 32, 0, st>>>(lut, iq, d_off, d_len, nitems, m.cands, m.heads, m.tabs, m.nsegMax);
+    k_cand_accept<<<nitems, 32, 0, st>>>(d_len, nitems, itemBase, maxf, m.cands, m.heads, m.tabs, m.nsegMax, frames, chan, scans);
 }
 
 void c8b_launch_header_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, int nitems, int maxf, int mupos, c8b_frame* frames,

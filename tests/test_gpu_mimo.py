@@ -117,9 +117,9 @@ def test_header2_warp_kernel_equals_the_thread_kernel(golden, snr):
             n = int(f1[i]["total"]) if f1[i]["status"] == 0 else 0
             err = np.abs(l0[i, :n] - l1[i, :n]) / np.maximum(1.0, np.abs(l1[i, :n]))
             assert n == 0 or err.max() <= 1e-4, (i, float(err.max()))
-            if snr is not None:                                  # (the SIG-B SNR of a noiseless frame is rounding noise, ~140 dB)
-                assert abs(float(f0[i]["sssnr0"]) - float(f1[i]["sssnr0"])) <= 1e-2 * max(1.0, abs(float(f1[i]["sssnr0"])))
-                assert abs(float(f0[i]["sssnr1"]) - float(f1[i]["sssnr1"])) <= 1e-2 * max(1.0, abs(float(f1[i]["sssnr1"])))
+            for key in ("sssnr0", "sssnr1"):                     # (the SIG-B SNR of a noiseless frame is rounding noise, ~140 dB)
+                if abs(float(f1[i][key])) < 60.0:
+                    assert abs(float(f0[i][key]) - float(f1[i][key])) <= 1e-2 * max(1.0, abs(float(f1[i][key]))), (i, key)
             assert b0[i]["status"] == b1[i]["status"] and b0[i]["pdu_bytes"] == b1[i]["pdu_bytes"]
             assert bytes(p0[i, :b0[i]["pdu_bytes"]]) == bytes(p1[i, :b1[i]["pdu_bytes"]])
 

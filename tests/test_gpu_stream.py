@@ -121,3 +121,20 @@ def test_stream_two_antennas(golden):
         rx.stream_begin(2, 0)
         assert _stream(rx, a, _pushes(rng, a.size, k), x1=b) == want
     rx.close()
+
+
+def test_trigger_scan_with_many_segment_cuts():
+    """the trigger scan runs as parallel segments cut at quiet stretches (k_seg_cuts / k_trig_scan); with the nominal segment
+    shrunk to 8 bitmap words (C8B_SEG_WORDS, read once per process) every capture of these two files is cut dozens of times:
+    the adversarial trigger / hold-off model and the stream-equals-one-pass tests must hold unchanged"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("C8B_SEG_WORDS"):
+        pytest.skip("already inside the re-run")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, C8B_SEG_WORDS="8")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(here, "test_gpu_trigger_scan.py"),
+                        os.path.join(here, "test_gpu_stream.py"), os.path.join(here, "test_gpu_flowgraph.py")],
+                       env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -21,7 +21,13 @@ x = np.tile(one, reps)
 rng = np.random.default_rng(1)
 s = 0.1875 / np.sqrt(2 * 10 ** 3.0)
 x = (x + s * (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size))).astype(np.complex64)
-rx = pkg.Receiver(device=0, max_frames=256, chunk_items=1)
+try:                                                                # a radio driver's DMA ring is page-locked: so is the source here
+    import torch
+    xt = torch.from_numpy(x).pin_memory()
+    x = xt.numpy()
+except Exception:
+    pass
+rx = pkg.Receiver(device=0, max_frames=512, chunk_items=1)
 for push in [int(a) for a in sys.argv[1:]] or [16384, 65536, 262144, 1048576]:
     for rep in range(2):                                            # first pass warms the scratch allocations
         rx.stream_begin(1, 1 << 22)
