@@ -1,13 +1,16 @@
 // blocks.cu -- C ABI c8b_blk_*: the seven receive blocks of the reference, one scheduler call at a time
 // (include/c80211b200.h).  The state machines are the host templates of blocks.h; this file is their sm_100a backend:
-//   k_blk_trigger  : the trigger FSM (lib/trigger_impl.cc:59-117) continued from the state the previous call left in
-//                    device memory; one warp, 32 samples per coalesced load, every lane steps the same FSM
-//   k_blk_sync     : ltf_autoCorrelation + ltf_cfo of one trigger (lib/sync_impl.cc:155-196)
-//   k_blk_signal   : L-SIG of one sync flag: 3 x (CFO rotation, DFT64), LS channel, 24-step Viterbi, parity / rate / length
-//                    (lib/signal_impl.cc:108-162)
-//   k_blk_cfo_copy : the S_COPY loop (lib/signal_impl.cc:164-192), one thread per sample
-//   demod / demod2 / decode run the batch path's kernels on ONE frame (k_header_w / k_header2, k_demod / k_demod2,
-//   k_viterbi) through c8b_demod / c8b_demod2 / c8b_decode.
+//   k_one_trigger_w : the trigger FSM (lib/trigger_impl.cc:59-117) continued from the state the previous call left in device
+//                     memory, a bitmap word (32 samples) per step in closed form (k_frontend_w.cu)
+//   k_one_sync_w    : ltf_autoCorrelation + ltf_cfo of one trigger (lib/sync_impl.cc:155-196), the batch path's warp routine
+//   k_one_signal_w  : L-SIG of one sync flag (lib/signal_impl.cc:108-162) AND the S_COPY samples of the same call (:164-192)
+//                     in one launch
+//   k_blk_cfo_copy  : S_COPY of the later calls of a frame, one thread per sample
+//   demod / demod2 / decode run the batch path's kernels on ONE frame (k_header_w / k_header2_w, k_demod / k_demod2,
+//   k_viterbi) through c8b_one_demod / c8b_one_decode (ctx.cu): packed staging, one copy each way.
+// What a scheduler call costs here is driver calls and one host <-> device round trip, so every op is: inputs -> one
+// pinned staging buffer -> ONE asynchronous H2D copy -> kernel(s) -> small results written straight into mapped host
+// memory (a posted write, no copy call) / bulk results in ONE D2H copy -> ONE synchronise.
 // No CPU path: c8b_blk_create fails without a CUDA device like c8b_create does.
 #include <new>
 #include <string>
@@ -21,44 +24,6 @@ namespace {
 using c8b::cf;
 using c8b_blocks::SignalRes;
 using c8b_blocks::SyncRes;
-
-__global__ void __launch_bounds__(32)
-k_blk_trigger(c8b::TrigState* __restrict__ state, const float* __restrict__ in, int n, uint8_t* __restrict__ out)
-{
-    const int lane = threadIdx.x;
-    c8b::TrigState s = *state;                                    // every lane carries the same FSM
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const float mine = i < n ? in[i] : 0.f;
-        const int cnt = min(32, n - base);
-        uint8_t o = 0;
-        for (int k = 0; k < cnt; k++) {
-            const float v = __shfl_sync(0xffffffffu, mine, k);
-            const uint8_t r = c8b::trig_step(s, v);
-            if (k == lane) o = r;
-        }
-        if (i < n) out[i] = o;
-    }
-    __syncwarp();
-    if (lane == 0) *state = s;
-}
-
-__global__ void k_blk_sync(const float2* __restrict__ sig, float2 conj, SyncRes* __restrict__ res)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    const c8b::SyncOut o = c8b::sync_at(reinterpret_cast<const cf*>(sig), c8b::mk(conj.x, conj.y));
-    res->ok = o.ok; res->mIndex = o.mIndex; res->rad = o.rad; res->snr = o.snr; res->rssi = o.rssi;
-}
-
-__global__ void k_blk_signal(const c8b_lut* __restrict__ lut, const float2* __restrict__ in, float rad, SignalRes* __restrict__ res)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    cf h[64];
-    int mcs = 0, len = 0, nsamp = 0;
-    const int ok = c8b::signal_at(lut, reinterpret_cast<const cf*>(in), rad, h, &mcs, &len, &nsamp);
-    res->ok = ok; res->mcs = mcs; res->len = len; res->nsamp = nsamp;
-    for (int k = 0; k < 64; k++) { res->chan[2 * k] = h[k].re; res->chan[2 * k + 1] = h[k].im; }
-}
 
 __global__ void __launch_bounds__(256)
 k_blk_cfo_copy(const float2* __restrict__ in0, const float2* __restrict__ in1, float2* __restrict__ out0, float2* __restrict__ out1,
@@ -88,11 +53,13 @@ struct c8b_blk {
     cudaStream_t st = nullptr;
     const c8b_lut* lut = nullptr;
     std::string err;
-    // device scratch of the small kernels
+    // device scratch of the small kernels; h_pin = pinned + mapped host staging ([results 4 KB][bulk]), d_res its device alias
     c8b::TrigState* d_trig = nullptr;
-    SyncRes* d_sync = nullptr;
-    SignalRes* d_sig = nullptr;
     Buf d_a, d_b, d_c, d_d;
+    uint8_t* h_pin = nullptr;
+    uint8_t* d_res = nullptr;
+    size_t pinCap = 0;
+    uint32_t seq = 0;                                             // completion flag at h_pin + 3584 (see c8b_launch_flag)
     // block state (blocks.h)
     c8b_blocks::SyncState sy;
     c8b_blocks::SignalState sg;
@@ -117,73 +84,134 @@ struct c8b_blk {
     }
 #define BK(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
 
+    int pin(size_t bulk)                                          // pinned staging: 4 KB of mapped results + `bulk` bytes
+    {
+        if (pinCap >= bulk + 4096) return C8B_OK;
+        if (h_pin) { cudaStreamSynchronize(st); cudaFreeHost(h_pin); h_pin = nullptr; pinCap = 0; }
+        const size_t want = 4096 + bulk + bulk / 2 + 65536;
+        cudaError_t e = cudaHostAlloc((void**)&h_pin, want, cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&d_res, h_pin, 0);
+        if (e != cudaSuccess) return fail("cudaHostAlloc(mapped)", e);
+        pinCap = want;
+        return C8B_OK;
+    }
+
+    int finish()                                                  // completion flag last in the stream, then poll it from the host
+    {
+        seq++;
+        c8b_launch_flag(reinterpret_cast<uint32_t*>(d_res + 3584), seq, st);
+        if (c8b_wait_flag(reinterpret_cast<volatile uint32_t*>(h_pin + 3584), seq, st) != 0) {
+            const cudaError_t e = cudaStreamSynchronize(st);
+            return fail("block op", e != cudaSuccess ? e : cudaGetLastError());
+        }
+        return C8B_OK;
+    }
+
     // ---- Ops backend of blocks.h ----
     int trigger(const float* in, int n, uint8_t* out)
     {
         int r;
-        if ((r = grow(d_a, (size_t)n * sizeof(float))) || (r = grow(d_b, (size_t)n))) return r;
-        BK(cudaMemcpyAsync(d_a.p, in, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
-        k_blk_trigger<<<1, 32, 0, st>>>(d_trig, (const float*)d_a.p, n, (uint8_t*)d_b.p);
+        if ((r = grow(d_a, (size_t)n * sizeof(float))) || (r = grow(d_b, (size_t)n)) || (r = pin((size_t)n * 5))) return r;
+        float* hin = reinterpret_cast<float*>(h_pin + 4096);
+        uint8_t* hout = h_pin + 4096 + (size_t)n * sizeof(float);
+        memcpy(hin, in, (size_t)n * sizeof(float));
+        BK(cudaMemcpyAsync(d_a.p, hin, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+        c8b_launch_one_trigger(d_trig, (const float*)d_a.p, n, (uint8_t*)d_b.p, st);
         BK(cudaGetLastError());
-        BK(cudaMemcpyAsync(out, d_b.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-        BK(cudaStreamSynchronize(st));
+        BK(cudaMemcpyAsync(hout, d_b.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+        if ((r = finish())) return r;
+        memcpy(out, hout, (size_t)n);
         return C8B_OK;
     }
     int sync_at(const float* sig, const float conj[2], SyncRes* res)
     {
         int r;
-        if ((r = grow(d_a, 240 * sizeof(float2)))) return r;
-        BK(cudaMemcpyAsync(d_a.p, sig, 240 * sizeof(float2), cudaMemcpyHostToDevice, st));
-        k_blk_sync<<<1, 32, 0, st>>>((const float2*)d_a.p, make_float2(conj[0], conj[1]), d_sync);
+        if ((r = grow(d_a, 240 * sizeof(float2))) || (r = pin(240 * sizeof(float2)))) return r;
+        memcpy(h_pin + 4096, sig, 240 * sizeof(float2));
+        BK(cudaMemcpyAsync(d_a.p, h_pin + 4096, 240 * sizeof(float2), cudaMemcpyHostToDevice, st));
+        c8b_launch_one_sync((const float2*)d_a.p, conj[0], conj[1], d_res, st);     // result: a posted write into mapped host memory
         BK(cudaGetLastError());
-        BK(cudaMemcpyAsync(res, d_sync, sizeof(*res), cudaMemcpyDeviceToHost, st));
-        BK(cudaStreamSynchronize(st));
+        if ((r = finish())) return r;
+        memcpy(res, h_pin, sizeof(*res));
         return C8B_OK;
     }
-    int signal_at(const float* in, float rad, SignalRes* res)
+    // L-SIG at in0 (>= 224 samples) and, in the same round trip, ncopy samples behind it CFO-corrected (both antennas of
+    // signal2); *rot0 / *rot1 point into the pinned staging and stay valid until the next op
+    int signal_at(const float* in0, const float* in1, int ncopy, float rad, SignalRes* res, const float** rot0, const float** rot1)
     {
+        const size_t nin = (size_t)(224 + ncopy) * sizeof(float2), nout = (size_t)ncopy * sizeof(float2);
+        const size_t a1 = (nin + 255) & ~(size_t)255, o1 = (nout + 255) & ~(size_t)255;
         int r;
-        if ((r = grow(d_a, 224 * sizeof(float2)))) return r;
-        BK(cudaMemcpyAsync(d_a.p, in, 224 * sizeof(float2), cudaMemcpyHostToDevice, st));
-        k_blk_signal<<<1, 32, 0, st>>>(lut, (const float2*)d_a.p, rad, d_sig);
+        if ((r = grow(d_a, 2 * a1)) || (r = grow(d_b, 2 * o1 + 256)) || (r = pin(2 * a1 + 2 * o1))) return r;
+        uint8_t* hin = h_pin + 4096;
+        uint8_t* hout = hin + 2 * a1;
+        memcpy(hin, in0, nin);
+        if (in1) memcpy(hin + a1, in1, nin);
+        BK(cudaMemcpyAsync(d_a.p, hin, in1 ? a1 + nin : nin, cudaMemcpyHostToDevice, st));
+        c8b_launch_one_signal(lut, (const float2*)d_a.p, in1 ? (const float2*)((uint8_t*)d_a.p + a1) : nullptr, rad, d_res, (float2*)d_b.p,
+                              in1 ? (float2*)((uint8_t*)d_b.p + o1) : nullptr, ncopy, st);
         BK(cudaGetLastError());
-        BK(cudaMemcpyAsync(res, d_sig, sizeof(*res), cudaMemcpyDeviceToHost, st));
-        BK(cudaStreamSynchronize(st));
+        if (ncopy > 0) BK(cudaMemcpyAsync(hout, d_b.p, in1 ? o1 + nout : nout, cudaMemcpyDeviceToHost, st));
+        if ((r = finish())) return r;
+        memcpy(res, h_pin, sizeof(*res));
+        *rot0 = ncopy > 0 ? reinterpret_cast<const float*>(hout) : nullptr;
+        *rot1 = (ncopy > 0 && in1) ? reinterpret_cast<const float*>(hout + o1) : nullptr;
         return C8B_OK;
     }
     int cfo_copy(const float* in0, const float* in1, float* out0, float* out1, int n, int copied, float rad)
     {
-        const size_t bytes = (size_t)n * sizeof(float2);
+        const size_t bytes = (size_t)n * sizeof(float2), al = (bytes + 255) & ~(size_t)255;
         int r;
-        if ((r = grow(d_a, bytes)) || (r = grow(d_b, bytes))) return r;
-        if (in1 && ((r = grow(d_c, bytes)) || (r = grow(d_d, bytes)))) return r;
-        BK(cudaMemcpyAsync(d_a.p, in0, bytes, cudaMemcpyHostToDevice, st));
-        if (in1) BK(cudaMemcpyAsync(d_c.p, in1, bytes, cudaMemcpyHostToDevice, st));
-        k_blk_cfo_copy<<<(n + 255) / 256, 256, 0, st>>>((const float2*)d_a.p, in1 ? (const float2*)d_c.p : nullptr, (float2*)d_b.p,
-                                                        in1 ? (float2*)d_d.p : nullptr, n, copied, rad);
+        if ((r = grow(d_a, 2 * al)) || (r = grow(d_b, 2 * al)) || (r = pin(4 * al))) return r;
+        uint8_t* hin = h_pin + 4096;
+        uint8_t* hout = hin + 2 * al;
+        memcpy(hin, in0, bytes);
+        if (in1) memcpy(hin + al, in1, bytes);
+        BK(cudaMemcpyAsync(d_a.p, hin, in1 ? al + bytes : bytes, cudaMemcpyHostToDevice, st));
+        k_blk_cfo_copy<<<(n + 255) / 256, 256, 0, st>>>((const float2*)d_a.p, in1 ? (const float2*)((uint8_t*)d_a.p + al) : nullptr, (float2*)d_b.p,
+                                                        in1 ? (float2*)((uint8_t*)d_b.p + al) : nullptr, n, copied, rad);
         BK(cudaGetLastError());
-        BK(cudaMemcpyAsync(out0, d_b.p, bytes, cudaMemcpyDeviceToHost, st));
-        if (in1) BK(cudaMemcpyAsync(out1, d_d.p, bytes, cudaMemcpyDeviceToHost, st));
-        BK(cudaStreamSynchronize(st));
+        BK(cudaMemcpyAsync(hout, d_b.p, in1 ? al + bytes : bytes, cudaMemcpyDeviceToHost, st));
+        if ((r = finish())) return r;
+        memcpy(out0, hout, bytes);
+        if (in1) memcpy(out1, hout + al, bytes);
         return C8B_OK;
     }
-    int demod(int nant, const float* iq0, const float* iq1, int n, c8b_frame* f, const float* chan, std::vector<float>* llr)
+    // demod: two staging slots, frames collected in submission order
+    int mq_head = 0, mq_n = 0;
+    int demod_submit(int nant, const float* iq0, const float* iq1, int n, const c8b_frame* f, const float* chan)
     {
-        // soft bits of one frame: a short-GI symbol takes 72 samples (the rule of llr_stride_for in ctx.cu), 416 (one stream) /
-        // 832 (two streams) soft bits per symbol
-        const int64_t stride = std::max<int64_t>(((int64_t)f->nsamp / 72 + 1) * (nant == 2 ? 832 : 416), 1024);
-        llr->assign((size_t)stride, 0.f);
-        const int64_t off = 0;
-        const int32_t len = n;
-        const int rc = nant == 2 ? c8b_demod2(ctx, iq0, iq1, &off, &len, 1, f, chan, llr->data(), stride)
-                                 : c8b_demod(ctx, iq0, &off, &len, 1, f, chan, llr->data(), stride);
-        if (rc) err = c8b_last_error(ctx);
+        if (mq_n >= 2) return C8B_ERR_FULL;
+        const int rc = c8b_one_demod_submit(ctx, (mq_head + mq_n) & 1, nant, iq0, iq1, n, f, chan);
+        if (rc) { err = c8b_last_error(ctx); return rc; }
+        mq_n++;
+        return C8B_OK;
+    }
+    int demod_collect(bool wait, c8b_frame* f, const float** soft, int* nsoft)
+    {
+        if (mq_n == 0) return 0;
+        const int rc = c8b_one_demod_collect(ctx, mq_head, wait ? 1 : 0, f, soft, nsoft);
+        if (rc < 0) { err = c8b_last_error(ctx); return rc; }
+        if (rc == 1) { mq_head ^= 1; mq_n--; }
         return rc;
     }
-    int decode(c8b_frame* f, const float* llr, int nllr, uint8_t* pdu, int pdu_cap)
+    // decode: frames go through the ctx's staging slots round robin; collected in submission order
+    int dq_head = 0, dq_n = 0;
+    int decode_submit(const c8b_frame* f, const float* llr, int nllr)
     {
-        const int rc = c8b_decode(ctx, llr, nllr, f, 1, pdu, pdu_cap, nullptr, 0);
-        if (rc) err = c8b_last_error(ctx);
+        if (dq_n >= C8B_ONE_SLOTS) return C8B_ERR_FULL;          // (decode_work publishes before it submits: at most one gathering + 3 in flight)
+        const int slot = (dq_head + dq_n) % C8B_ONE_SLOTS;
+        const int rc = c8b_one_decode_submit(ctx, slot, f, llr, nllr);
+        if (rc) { err = c8b_last_error(ctx); return rc; }
+        dq_n++;
+        return C8B_OK;
+    }
+    int decode_collect(bool wait, c8b_frame* f, const uint8_t** pdu)
+    {
+        if (dq_n == 0) return 0;
+        const int rc = c8b_one_decode_collect(ctx, dq_head, wait ? 1 : 0, f, pdu);
+        if (rc < 0) { err = c8b_last_error(ctx); return rc; }
+        if (rc == 1) { dq_head = (dq_head + 1) % C8B_ONE_SLOTS; dq_n--; }
         return rc;
     }
 #undef BK
@@ -219,8 +247,7 @@ void c8b_blk_destroy(c8b_blk* b)
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->d_trig) cudaFree(b->d_trig);
-    if (b->d_sync) cudaFree(b->d_sync);
-    if (b->d_sig) cudaFree(b->d_sig);
+    if (b->h_pin) cudaFreeHost(b->h_pin);
     for (Buf* q : { &b->d_a, &b->d_b, &b->d_c, &b->d_d }) if (q->p) cudaFree(q->p);
     if (b->ctx) c8b_destroy(b->ctx);
     delete b;
@@ -254,8 +281,6 @@ int c8b_blk_create(const c8b_cfg* cfg, int kind, c8b_blk** out)
     c8b::trig_reset(ts);
     cudaError_t e = cudaMalloc(&b->d_trig, sizeof(ts));
     if (e == cudaSuccess) e = cudaMemcpy(b->d_trig, &ts, sizeof(ts), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_sync, sizeof(SyncRes));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_sig, sizeof(SignalRes));
     if (e != cudaSuccess) {
         g_blkErr = std::string("c8b_blk_create: ") + cudaGetErrorString(e);
         c8b_blk_destroy(b);

@@ -9,7 +9,8 @@
 //
 // Deviation from the reference that a downstream block cannot see: demod / demod2 / decode gather a whole frame before
 // they run their kernels (one launch per frame instead of one FFT per symbol per call), so the SAME items and tags leave
-// the block, but later within the stream of scheduler calls.  The 320 pad samples signal never writes
+// the block, but later within the stream of scheduler calls; decode publishes a frame's MPDUs one call after its last soft
+// bit arrived (or when called without input), while the GPU already works on it.  The 320 pad samples signal never writes
 // (lib/signal_impl.cc:194-201) and the 1024 NDP floats demod never writes (lib/demod_impl.cc:251-257) are zeros here.
 #pragma once
 #include <stdint.h>
@@ -127,6 +128,9 @@ int signal_work(Ops& ops, SignalState& s, int nant, WorkIO& io)
     int nProc = std::min(io.ninput[0], io.ninput[1]);
     if (nant == 2) nProc = std::min(nProc, io.ninput[2]);
     int nUsed = 0, nPassed = 0;
+    const float* rot0 = nullptr;                                  // S_COPY samples the backend already corrected together with the L-SIG
+    const float* rot1 = nullptr;
+    int nrot = 0;
 
     if (s.st == 0) {                                              // :75-106
         int i;
@@ -143,7 +147,9 @@ int signal_work(Ops& ops, SignalState& s, int nant, WorkIO& io)
     if (s.st == 1) {                                              // :108-162
         if (nProc - nUsed >= 224) {
             SignalRes r;
-            const int rc = ops.signal_at(in1 + 2 * (size_t)nUsed, s.rad, &r);     // both blocks read the L-SIG on antenna 0
+            // both blocks read the L-SIG on antenna 0; the samples S_COPY would hand on in this same call ride along
+            nrot = std::max(0, std::min(io.noutput, nProc - nUsed - 224));
+            const int rc = ops.signal_at(in1 + 2 * (size_t)nUsed, in2 ? in2 + 2 * (size_t)nUsed : nullptr, nrot, s.rad, &r, &rot0, &rot1);
             if (rc) return rc;
             if (r.ok) {
                 s.nSample = r.nsamp; s.nCopied = 0;
@@ -172,8 +178,13 @@ int signal_work(Ops& ops, SignalState& s, int nant, WorkIO& io)
         const bool last = !(nGen < left);
         if (last) nGen = left;
         if (nGen > 0) {
-            const int rc = ops.cfo_copy(in1 + 2 * (size_t)nUsed, in2 ? in2 + 2 * (size_t)nUsed : nullptr, out1, out2, nGen, s.nCopied, s.rad);
-            if (rc) return rc;
+            if (rot0 && s.nCopied == 0 && nGen <= nrot && (!in2 || rot1)) {
+                memcpy(out1, rot0, sizeof(float) * 2 * (size_t)nGen);
+                if (in2) memcpy(out2, rot1, sizeof(float) * 2 * (size_t)nGen);
+            } else {
+                const int rc = ops.cfo_copy(in1 + 2 * (size_t)nUsed, in2 ? in2 + 2 * (size_t)nUsed : nullptr, out1, out2, nGen, s.nCopied, s.rad);
+                if (rc) return rc;
+            }
         }
         s.nCopied += nGen;
         nUsed += nGen;
@@ -194,13 +205,21 @@ int signal_work(Ops& ops, SignalState& s, int nant, WorkIO& io)
 }
 
 // ---- demod / demod2 (lib/demod_impl.cc:59-342, lib/demod2_impl.cc:58-348) ---------------------------------------------
+// Two halves that share a call: the INPUT side reads the tag (RDTAG), gathers the frame's nsamp + 320 samples and submits
+// them to the backend (header states + per-symbol demod on the device, asynchronous); the OUTPUT side collects finished
+// frames in order and emits tag + soft bits as the output space allows.  Up to two frames are in flight, so the device
+// works on frame k while the samples of frame k + 1 are gathered.
 struct DemodState {
-    int st = 0;                    // 0 RDTAG, 1 gather (FORMAT..CLEAN of the reference), 2 emit LLRs
-    c8b_tag tag;                   // signal's tag of the frame in progress
+    int st = 0;                    // input side: 0 RDTAG, 1 gather (FORMAT..CLEAN of the reference)
+    c8b_tag tag;                   // signal's tag of the frame being gathered
     int need = 0, have = 0;        // samples of the frame: nsamp + 320
     std::vector<float> buf[2];     // gathered samples per antenna, behind 224 zeros (the L-LTF/L-SIG part signal consumed)
+    c8b_tag qtag[2];               // signal's tags of the frames in flight, oldest first
+    int nq = 0;
+    bool emitting = false;         // output side: a collected frame is being handed on
     std::vector<float> llr;
     c8b_frame f;
+    c8b_tag etag;
     int emitted = 0, total = 0;
     bool tagPending = false;
 };
@@ -210,74 +229,117 @@ int demod_work(Ops& ops, DemodState& s, int nant, WorkIO& io)
 {
     int nProc = io.ninput[0];
     if (nant == 2) nProc = std::min(nProc, io.ninput[1]);
+    const bool canRead = s.nq < 2 && nProc > 0 && (s.st == 1 || io.tag_at(0) != nullptr);
+    // ---- output side: the oldest frame in flight, when it is done (waited for only if this call has nothing else to do) ----
+    while (!s.emitting && s.nq > 0) {
+        const float* soft = nullptr;
+        int nsoft = 0;
+        const int rc = ops.demod_collect(!canRead, &s.f, &soft, &nsoft);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+        s.etag = s.qtag[0];
+        s.qtag[0] = s.qtag[1];
+        s.nq--;
+        if (s.f.status == C8B_ST_OK) s.total = s.f.total;
+        else if (s.f.status == C8B_ST_NDP) s.total = 1024;        // :251-257
+        else continue;                                            // DEMOD_S_CLEAN: dropped, nothing leaves the block
+        s.llr.assign((size_t)std::max(s.total, 1024), 0.f);
+        memcpy(s.llr.data(), soft, sizeof(float) * (size_t)std::min(std::max(s.total, s.f.status == C8B_ST_NDP ? 256 : 0), nsoft));
+        s.emitted = 0; s.tagPending = true; s.emitting = true;
+    }
+    if (s.emitting && io.noutput > 0) {                           // tag at the first soft bit (:224-263), then `total` floats
+        if (s.tagPending) {
+            c8b_tag* t = io.new_tag(0);
+            if (!t) return C8B_ERR_FULL;
+            t->f = s.f;
+            t->f.snr = s.etag.f.snr; t->f.rssi = s.etag.f.rssi; t->f.cfo_hz = s.etag.f.cfo_hz;
+            t->seq = s.etag.seq;
+            if (s.f.status == C8B_ST_NDP) {
+                t->f.total = 1024; t->f.trellis = 0;
+                t->nvec = 128;
+                memcpy(t->vec, s.llr.data(), sizeof(float) * 256);    // tag "mu2x1chan" (:238-249)
+                std::fill(s.llr.begin(), s.llr.end(), 0.f);
+            }
+            s.tagPending = false;
+        }
+        const int n = std::min(io.noutput, s.total - s.emitted);
+        memcpy(io.out[0], s.llr.data() + s.emitted, sizeof(float) * (size_t)n);
+        s.emitted += n;
+        io.produced = n;
+        if (s.emitted >= s.total) s.emitting = false;
+    }
+    // ---- input side ----
+    if (s.nq >= 2 || nProc <= 0) return 0;
     if (s.st == 0) {                                              // DEMOD_S_RDTAG (:72-103): a frame starts at a tagged item
         const c8b_tag* t = io.tag_at(0);
-        if (!t || nProc <= 0) return 0;
+        if (!t) return 0;
         s.tag = *t;
         s.need = t->f.nsamp + 320;                                // :93
         s.have = 0;
         for (int a = 0; a < nant; a++) s.buf[a].assign(2 * (size_t)(224 + s.need), 0.f);
         s.st = 1;
     }
-    if (s.st == 1) {
-        const int n = std::min(nProc, s.need - s.have);
-        for (int a = 0; a < nant; a++)
-            memcpy(s.buf[a].data() + 2 * (size_t)(224 + s.have), io.in[a], sizeof(float) * 2 * (size_t)n);
-        s.have += n;
-        io.consumed = n;
-        if (s.have < s.need) return 0;
-        // the whole frame is here: header states + per-symbol demod in one go on the device
-        memset(&s.f, 0, sizeof(s.f));
-        s.f.status = C8B_ST_OK;
-        s.f.sync_idx = 0; s.f.rad = 0.f;                          // the input is signal's CFO-corrected copy
-        s.f.snr = s.tag.f.snr; s.f.rssi = s.tag.f.rssi; s.f.cfo_hz = s.tag.f.cfo_hz;
-        s.f.l_mcs = s.tag.f.l_mcs; s.f.l_len = s.tag.f.l_len; s.f.nsamp = s.tag.f.nsamp;
-        const int rc = ops.demod(nant, s.buf[0].data(), nant == 2 ? s.buf[1].data() : nullptr, 224 + s.need, &s.f, s.tag.vec, &s.llr);
-        if (rc) return rc;
-        if (s.f.status == C8B_ST_OK) { s.total = s.f.total; }
-        else if (s.f.status == C8B_ST_NDP) { s.total = 1024; }    // :251-257
-        else { s.st = 0; return 0; }                              // DEMOD_S_CLEAN: dropped, nothing leaves the block
-        s.emitted = 0; s.tagPending = true;
-        s.st = 2;
-        return 0;
-    }
-    // emit: tag at the first soft bit (:224-263), then the frame's `total` floats as output space allows
-    if (io.noutput <= 0) return 0;
-    if (s.tagPending) {
-        c8b_tag* t = io.new_tag(0);
-        if (!t) return C8B_ERR_FULL;
-        t->f = s.f;
-        t->f.snr = s.tag.f.snr; t->f.rssi = s.tag.f.rssi; t->f.cfo_hz = s.tag.f.cfo_hz;
-        t->seq = s.tag.seq;
-        if (s.f.status == C8B_ST_NDP) {
-            t->f.total = 1024; t->f.trellis = 0;
-            t->nvec = 128;
-            memcpy(t->vec, s.llr.data(), sizeof(float) * 256);    // tag "mu2x1chan" (:238-249)
-            std::fill(s.llr.begin(), s.llr.end(), 0.f);
-        }
-        s.tagPending = false;
-    }
-    const int n = std::min(io.noutput, s.total - s.emitted);
-    memcpy(io.out[0], s.llr.data() + s.emitted, sizeof(float) * (size_t)n);
-    s.emitted += n;
-    io.produced = n;
-    if (s.emitted >= s.total) s.st = 0;
+    const int n = std::min(nProc, s.need - s.have);
+    for (int a = 0; a < nant; a++)
+        memcpy(s.buf[a].data() + 2 * (size_t)(224 + s.have), io.in[a], sizeof(float) * 2 * (size_t)n);
+    s.have += n;
+    io.consumed = n;
+    if (s.have < s.need) return 0;
+    // the whole frame is here: header states + per-symbol demod in one go on the device
+    c8b_frame f;
+    memset(&f, 0, sizeof(f));
+    f.status = C8B_ST_OK;
+    f.sync_idx = 0; f.rad = 0.f;                                  // the input is signal's CFO-corrected copy
+    f.snr = s.tag.f.snr; f.rssi = s.tag.f.rssi; f.cfo_hz = s.tag.f.cfo_hz;
+    f.l_mcs = s.tag.f.l_mcs; f.l_len = s.tag.f.l_len; f.nsamp = s.tag.f.nsamp;
+    const int rc = ops.demod_submit(nant, s.buf[0].data(), nant == 2 ? s.buf[1].data() : nullptr, 224 + s.need, &f, s.tag.vec);
+    if (rc) return rc;
+    s.qtag[s.nq++] = s.tag;
+    s.st = 0;
     return 0;
 }
 
 // ---- decode (lib/decode_impl.cc:60-162) --------------------------------------------------------------------------------
+// The block has no stream output, only messages: a frame whose soft bits are all here is SUBMITTED to the backend and the
+// call returns; its MPDUs are published by a later call (in submission order), or by a call with no input -- what the shell's
+// stop() / a drained scheduler issues.  The GPU round trip of one frame thereby overlaps the gathering of the next.
 struct DecodeState {
     int st = 0;                    // 0 IDLE, 1 gather (DECODE), 2 CLEAN
     c8b_frame f;
     int total = 0, have = 0;
     std::vector<float> llr;
-    std::vector<uint8_t> pdu;
+    int inflight = 0;              // frames submitted and not yet published
 };
+
+template <class Ops>
+int decode_publish(Ops& ops, DecodeState& s, WorkIO& io, bool wait)
+{
+    while (s.inflight > 0) {
+        c8b_frame f;
+        const uint8_t* pdu = nullptr;
+        // room for the record first: a finished frame must not be taken off the queue and then dropped
+        if (io.msg_cap - io.msg_bytes < 2 * 4400 || io.n_out_tags >= io.out_tag_cap) return io.msg_bytes > 0 || io.n_out_tags > 0 ? 0 : C8B_ERR_FULL;
+        const int rc = ops.decode_collect(wait, &f, &pdu);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
+        s.inflight--;
+        if (c8b_tag* t = io.new_tag(-1)) { t->port = -1; t->f = f; }      // report of the finished frame (debug lines of the shell)
+        if (f.npdu > 0 && f.pdu_bytes > 0) {                     // [fmt][len lo][len hi][MPDU][mcs] per CRC-passing MPDU (:512-516)
+            memcpy(io.msg + io.msg_bytes, pdu, (size_t)f.pdu_bytes);
+            io.msg_bytes += f.pdu_bytes;
+        }
+    }
+    return 0;
+}
 
 template <class Ops>
 int decode_work(Ops& ops, DecodeState& s, WorkIO& io)
 {
     const int nProc = io.ninput[0];
+    {
+        const int rc = decode_publish(ops, s, io, nProc <= 0);    // nothing to read: wait for what is in flight
+        if (rc) return rc;
+    }
     if (s.st == 0) {                                              // :67-127
         const c8b_tag* t = io.tag_at(0);
         if (!t || nProc <= 0) return 0;
@@ -286,6 +348,8 @@ int decode_work(Ops& ops, DecodeState& s, WorkIO& io)
         if (s.f.len > 4095 || s.f.trellis > 32782) { s.st = 2; }  // :93-97
         else if (s.f.trellis == 0) {                              // VHT NDP channel report (:100-121)
             s.st = 2;
+            const int rc = decode_publish(ops, s, io, true);      // messages stay in stream order
+            if (rc) return rc;
             const int n = 3 + 1024;
             if (io.msg_bytes + n > io.msg_cap) return C8B_ERR_FULL;
             uint8_t* m = io.msg + io.msg_bytes;
@@ -305,15 +369,14 @@ int decode_work(Ops& ops, DecodeState& s, WorkIO& io)
         io.consumed = n;
         if (s.have < s.total) return 0;
         s.f.status = C8B_ST_OK; s.f.llr_off = 0; s.f.npdu = 0; s.f.pdu_bytes = 0;
-        s.pdu.assign(2 * 4400, 0);
-        const int rc = ops.decode(&s.f, s.llr.data(), s.total, s.pdu.data(), (int)s.pdu.size());
-        if (rc) return rc;
-        if (c8b_tag* t = io.new_tag(-1)) { t->port = -1; t->f = s.f; }   // report of the finished frame (debug lines of the shell)
-        if (s.f.npdu > 0 && s.f.pdu_bytes > 0) {                  // [fmt][len lo][len hi][MPDU][mcs] per CRC-passing MPDU (:512-516)
-            if (io.msg_bytes + s.f.pdu_bytes > io.msg_cap) return C8B_ERR_FULL;
-            memcpy(io.msg + io.msg_bytes, s.pdu.data(), (size_t)s.f.pdu_bytes);
-            io.msg_bytes += s.f.pdu_bytes;
+        if (s.inflight >= 3) {                                    // every staging slot but one is busy: wait for the oldest frames first
+            const int rp = decode_publish(ops, s, io, true);
+            if (rp) return rp;
         }
+        if (s.inflight >= 4) { s.have = s.total; return 0; }      // (no room to publish into: the caller comes back with this frame still gathered)
+        const int rc = ops.decode_submit(&s.f, s.llr.data(), s.total);
+        if (rc) return rc;
+        s.inflight++;
         s.st = 0;
         return 0;
     }

@@ -63,5 +63,19 @@ void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t
                              float2* chan, c8b_scan* scans, void* scratch, int maxLen, cudaStream_t st);
 void c8b_launch_trigger_events(const float* d_preac, int n, const int64_t* d_off, const int32_t* d_len, uint32_t* d_mask, const c8b_scan* d_scan,
                                void* scratch, int cap, int32_t* d_out, cudaStream_t st);
+// completion flag in mapped pinned memory: enqueue c8b_launch_flag last, then poll with c8b_wait_flag (0 = reached, -1 = stream error)
+void c8b_launch_flag(uint32_t* d_flag, uint32_t seq, cudaStream_t st);
+int c8b_wait_flag(const volatile uint32_t* h_flag, uint32_t seq, cudaStream_t st);
+// one frame per call on a context (ctx.cu; used by blocks.cu): packed staging, one copy each way
+int c8b_one_demod_submit(c8b_ctx* ctx, int slot, int nant, const float* iq0, const float* iq1, int n, const c8b_frame* f, const float* chan);
+int c8b_one_demod_collect(c8b_ctx* ctx, int slot, int wait, c8b_frame* f, const float** llr_out, int* llr_n);   // 1 done, 0 not yet, < 0 error
+#define C8B_ONE_SLOTS 4
+int c8b_one_decode_submit(c8b_ctx* ctx, int slot, const c8b_frame* f, const float* llr, int nllr);
+int c8b_one_decode_collect(c8b_ctx* ctx, int slot, int wait, c8b_frame* f, const uint8_t** pdu_out);   // 1 done, 0 not yet, < 0 error
+// one event of one block per launch (csrc/blocks.cu); res: c8b_blocks::SyncRes / SignalRes, device or mapped host memory
+void c8b_launch_one_sync(const float2* d_sig, float conj_re, float conj_im, void* res, cudaStream_t st);
+void c8b_launch_one_signal(const c8b_lut* lut, const float2* d_in, const float2* d_in1, float rad, void* res, float2* d_out0, float2* d_out1,
+                           int ncopy, cudaStream_t st);
+void c8b_launch_one_trigger(void* d_state, const float* d_in, int n, uint8_t* d_out, cudaStream_t st);
 // the device copy of the table blob of a context (null until c8b_lut_load); used by blocks.cu
 extern "C" const c8b_lut* c8b_ctx_lut(const c8b_ctx* ctx);

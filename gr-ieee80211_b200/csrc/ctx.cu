@@ -41,6 +41,12 @@ struct c8b_ctx {
         int64_t overruns = 0;   // windows dropped because nothing in them could be decided
     } strm;
     DevBuf sw[2][2], scan;      // [antenna][ping-pong]
+    // one frame per call (the per-block entry points, blocks.cu): packed input / output blocks, pinned + device
+    struct OneSlot { void* host = nullptr; size_t hostCap = 0; DevBuf dev; cudaEvent_t ev = nullptr; uint32_t seq = 0; int64_t aux = 0, aux2 = 0; };
+    uint32_t* oneFlagH = nullptr;   // C8B_ONE_SLOTS completion words in mapped pinned memory (c8b_launch_flag / c8b_wait_flag)
+    uint32_t* oneFlagD = nullptr;
+    uint32_t oneSeq = 0;
+    OneSlot one[C8B_ONE_SLOTS];     // staging slots of the asynchronous one-frame ops (demod: 0 and 1; decode: all, round robin)
     // pinned read-back staging of a stream pass: frame records + scan result, then the PDU area of the frames taken
     void* hStage = nullptr;
     size_t hStageCap = 0;
@@ -198,6 +204,8 @@ void c8b_destroy(c8b_ctx* ctx)
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    if (ctx->oneFlagH) cudaFreeHost(ctx->oneFlagH);
+    for (auto& sl : ctx->one) { if (sl.host) cudaFreeHost(sl.host); if (sl.dev.p) cudaFree(sl.dev.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     if (ctx->tabOff) cudaFreeHost(ctx->tabOff);
     if (ctx->tabLen) cudaFreeHost(ctx->tabLen);
     if (ctx->evTab) cudaEventDestroy(ctx->evTab);
@@ -504,6 +512,8 @@ static int upload_items_range(c8b_ctx* ctx, const int64_t* off, const int32_t* l
         EN(off, (size_t)n * sizeof(int64_t));
         EN(len, (size_t)n * sizeof(int32_t));
         if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    if (ctx->oneFlagH) cudaFreeHost(ctx->oneFlagH);
+    for (auto& sl : ctx->one) { if (sl.host) cudaFreeHost(sl.host); if (sl.dev.p) cudaFree(sl.dev.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     if (ctx->tabOff) cudaFreeHost(ctx->tabOff);
         if (ctx->tabLen) cudaFreeHost(ctx->tabLen);
         ctx->tabOff = nullptr; ctx->tabLen = nullptr; ctx->tabCap = 0; ctx->tabLo = ctx->tabHi = 0;
@@ -968,6 +978,8 @@ static int stream_process(c8b_ctx* ctx, bool flush, c8b_frame* frames, int frame
     const size_t frBytes = (size_t)maxf * sizeof(c8b_frame), need = frBytes + 256 + (size_t)maxf * pdu_stride;
     if (ctx->hStageCap < need) {
         if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    if (ctx->oneFlagH) cudaFreeHost(ctx->oneFlagH);
+    for (auto& sl : ctx->one) { if (sl.host) cudaFreeHost(sl.host); if (sl.dev.p) cudaFree(sl.dev.p); if (sl.ev) cudaEventDestroy(sl.ev); }
         ctx->hStage = nullptr; ctx->hStageCap = 0;
         CK(cudaHostAlloc(&ctx->hStage, need + need / 4, cudaHostAllocDefault));
         ctx->hStageCap = need + need / 4;
@@ -1209,3 +1221,160 @@ int c8b_tx_from_udp(c8b_ctx* ctx, const uint8_t* pkts, const int64_t* pkt_off, c
 }
 
 }  // extern "C"
+
+// ---- one frame per call: what the demod / demod2 / decode blocks of csrc/blocks.cu run ---------------------------------
+// c8b_demod / c8b_decode stage every array with its own copy and clear their scratch (they serve arbitrary batches); a
+// gr::block call hands over ONE frame, and what it costs is the number of driver calls.  Here the inputs of the frame
+// travel as one packed block (one pinned staging buffer, one H2D copy), the kernels run on it in place, and the results
+// come back as one block (one D2H copy, one synchronise).
+namespace {
+struct OneHdr {                      // head of the packed block, identical on host and device
+    int64_t off;                     // item table of the one item: offset 0 ...
+    int32_t len, pad;                // ... and its length in samples
+    c8b_frame f;                     // the frame record (in: detect fields; out: everything)
+    float chan[128];                 // legacy channel (tag "chan")
+};
+constexpr size_t ONE_HDR = (sizeof(OneHdr) + 255) & ~(size_t)255;
+
+int one_buffers(c8b_ctx* ctx, int slot, size_t bytes)
+{
+    c8b_ctx::OneSlot& sl = ctx->one[slot];
+    if (sl.hostCap < bytes) {
+        if (sl.host) cudaFreeHost(sl.host);
+        sl.host = nullptr; sl.hostCap = 0;
+        const size_t want = bytes + bytes / 2 + 65536;
+        if (cudaHostAlloc(&sl.host, want, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "cudaHostAlloc (per-frame staging)"; return C8B_ERR_NOMEM; }
+        sl.hostCap = want;
+    }
+    if (!sl.ev && cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "cudaEventCreate"; return C8B_ERR_CUDA; }
+    if (!ctx->oneFlagH) {
+        if (cudaHostAlloc((void**)&ctx->oneFlagH, 256, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&ctx->oneFlagD, ctx->oneFlagH, 0) != cudaSuccess) { ctx->err = "cudaHostAlloc (completion flags)"; return C8B_ERR_NOMEM; }
+        memset(ctx->oneFlagH, 0, 256);
+    }
+    return ensure(ctx, sl.dev, bytes + 256);
+}
+}  // namespace
+
+// header states + per-symbol demod of one frame, asynchronous (slot 0 / 1, collected in submission order).  iq0 / iq1: n
+// samples per antenna (the stream the signal block hands on, behind the 224 samples it consumed); f: detect fields set;
+// chan: 64 complex.  Layout of a slot: [soft bits][header][samples][1/H, weights] -- ONE H2D copy (header + samples), ONE
+// D2H copy (soft bits + header).  collect: *f = the finished record, *llr_out = its soft bits in the slot's pinned buffer
+// (llr_n floats, valid until the slot is submitted again).
+int c8b_one_demod_submit(c8b_ctx* ctx, int slot, int nant, const float* iq0, const float* iq1, int n, const c8b_frame* f, const float* chan)
+{
+    if (!ctx || slot < 0 || slot >= 2 || !iq0 || (nant == 2 && !iq1) || n <= 0 || !f || !chan) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t stride = llr_stride_for(f->nsamp > 0 ? f->nsamp : n) * (nant == 2 ? 2 : 1);
+    const size_t llrBytes = ((size_t)stride * sizeof(float) + 255) & ~(size_t)255, iqBytes = ((size_t)n * sizeof(float2) + 255) & ~(size_t)255;
+    const size_t oHdr = llrBytes, oIq0 = oHdr + ONE_HDR, oIq1 = oIq0 + iqBytes, oAux = oIq1 + (nant == 2 ? iqBytes : 0);
+    const size_t total = oAux + 64 * sizeof(float2) + 264 * sizeof(float2) + 256;
+    if ((r = one_buffers(ctx, slot, total))) return r;
+    c8b_ctx::OneSlot& sl = ctx->one[slot];
+    uint8_t* h = reinterpret_cast<uint8_t*>(sl.host);
+    uint8_t* d = reinterpret_cast<uint8_t*>(sl.dev.p);
+    OneHdr* hh = reinterpret_cast<OneHdr*>(h + oHdr);
+    hh->off = 0; hh->len = n; hh->pad = 0; hh->f = *f;
+    memcpy(hh->chan, chan, sizeof(hh->chan));
+    memcpy(h + oIq0, iq0, (size_t)n * sizeof(float2));
+    if (nant == 2) memcpy(h + oIq1, iq1, (size_t)n * sizeof(float2));
+    CK(cudaMemcpyAsync(d + oHdr, h + oHdr, oAux - oHdr, cudaMemcpyHostToDevice, ctx->st));
+    OneHdr* dh = reinterpret_cast<OneHdr*>(d + oHdr);
+    const float2* dq0 = reinterpret_cast<const float2*>(d + oIq0);
+    const float2* dq1 = nant == 2 ? reinterpret_cast<const float2*>(d + oIq1) : nullptr;
+    float2* dhinv = reinterpret_cast<float2*>(d + oAux);
+    float2* dw2 = dhinv + 64;
+    float* dllr = reinterpret_cast<float*>(d);
+    {
+        StageTimer tm(ctx, C8B_K_HEADER);
+        if (nant == 2)
+            (ctx->cfg.frontend_mode == 1 ? c8b_launch_header2 : c8b_launch_header2_w)(ctx->d_lut, dq0, dq1, &dh->off, 1, 1, ctx->cfg.mmse, &dh->f,
+                                                                                       reinterpret_cast<const float2*>(dh->chan), dhinv, dw2, stride, ctx->st);
+        else
+            (ctx->cfg.frontend_mode == 1 ? c8b_launch_header : c8b_launch_header_w)(ctx->d_lut, dq0, &dh->off, 1, 1, ctx->cfg.mupos, &dh->f,
+                                                                                     reinterpret_cast<const float2*>(dh->chan), dhinv, stride, dllr, ctx->st);
+    }
+    {
+        StageTimer tm(ctx, C8B_K_DEMOD);
+        const int maxSym = (int)(stride / 48 + 1);
+        c8b_launch_demod(ctx->d_lut, dq0, &dh->off, 1, 1, maxSym, &dh->f, dhinv, dllr, ctx->st);
+        if (nant == 2) c8b_launch_demod2(ctx->d_lut, dq0, dq1, &dh->off, 1, 1, maxSym, &dh->f, dw2, dllr, ctx->st);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h, d, oHdr + ONE_HDR, cudaMemcpyDeviceToHost, ctx->st));       // the soft bits and the frame record in one copy
+    sl.seq = ++ctx->oneSeq;
+    sl.aux = (int64_t)oHdr;
+    sl.aux2 = stride;
+    c8b_launch_flag(ctx->oneFlagD + 8 + slot, sl.seq, ctx->st);
+    CK(cudaEventRecord(sl.ev, ctx->st));
+    return C8B_OK;
+}
+
+int c8b_one_demod_collect(c8b_ctx* ctx, int slot, int wait, c8b_frame* f, const float** llr_out, int* llr_n)
+{
+    if (!ctx || slot < 0 || slot >= 2 || !ctx->one[slot].ev || !f || !llr_out || !llr_n) return C8B_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    c8b_ctx::OneSlot& sl = ctx->one[slot];
+    const volatile uint32_t* flag = ctx->oneFlagH + 8 + slot;
+    if (wait) {
+        if (c8b_wait_flag(flag, sl.seq, ctx->st) != 0) CK(cudaEventSynchronize(sl.ev));
+    } else if (*flag != sl.seq) return 0;
+    const uint8_t* h = reinterpret_cast<const uint8_t*>(sl.host);
+    *f = reinterpret_cast<const OneHdr*>(h + sl.aux)->f;
+    *llr_out = reinterpret_cast<const float*>(h);
+    *llr_n = (int)sl.aux2;
+    return 1;
+}
+
+// decode of one frame, asynchronous: submit copies the frame record and its f->total soft bits into staging slot `slot`
+// (0 .. C8B_ONE_SLOTS-1; the caller cycles through them and collects in the same order) and enqueues copy-in, the decode
+// kernel and copy-out on the ctx stream without waiting; collect(wait = 0) says whether that slot has finished (1) or not
+// (0), collect(wait = 1) waits for it.  *pdu_out: the PDU records (f->pdu_bytes bytes) in the slot's pinned buffer, valid
+// until the slot is submitted again.  Layout of a slot: [PDU area][header][soft bits] -- one H2D copy (header + soft bits),
+// one D2H copy (PDU area + header).
+int c8b_one_decode_submit(c8b_ctx* ctx, int slot, const c8b_frame* f, const float* llr, int nllr)
+{
+    if (!ctx || slot < 0 || slot >= C8B_ONE_SLOTS || !f || !llr || nllr < 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    const size_t llrBytes = (size_t)nllr * sizeof(float), pduCap = 2 * 4400 + 256;
+    const size_t oHdr = pduCap, oLlr = oHdr + ONE_HDR, total = oLlr + llrBytes + 256;
+    if ((r = one_buffers(ctx, slot, total))) return r;
+    if ((r = ensure_surv(ctx))) return r;
+    uint8_t* h = reinterpret_cast<uint8_t*>(ctx->one[slot].host);
+    uint8_t* d = reinterpret_cast<uint8_t*>(ctx->one[slot].dev.p);
+    OneHdr* hh = reinterpret_cast<OneHdr*>(h + oHdr);
+    hh->off = 0; hh->len = 0; hh->pad = 0; hh->f = *f;
+    hh->f.llr_off = 0;
+    memcpy(h + oLlr, llr, llrBytes);
+    CK(cudaMemcpyAsync(d + oHdr, h + oHdr, ONE_HDR + llrBytes, cudaMemcpyHostToDevice, ctx->st));
+    OneHdr* dh = reinterpret_cast<OneHdr*>(d + oHdr);
+    {
+        StageTimer tm(ctx, C8B_K_VITERBI);
+        c8b_launch_viterbi(ctx->d_lut, &dh->f, 1, reinterpret_cast<const float*>(d + oLlr), nllr, (uint2*)ctx->surv.p, ctx->survWarps, d, (int64_t)(2 * 4400),
+                           nullptr, 0, ctx->d_counter, 1, ctx->st);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h, d, oHdr + ONE_HDR, cudaMemcpyDeviceToHost, ctx->st));
+    ctx->one[slot].seq = ++ctx->oneSeq;
+    c8b_launch_flag(ctx->oneFlagD + 8 + slot, ctx->one[slot].seq, ctx->st);          // (word 0 belongs to c8b_one_demod)
+    CK(cudaEventRecord(ctx->one[slot].ev, ctx->st));
+    return C8B_OK;
+}
+
+int c8b_one_decode_collect(c8b_ctx* ctx, int slot, int wait, c8b_frame* f, const uint8_t** pdu_out)
+{
+    if (!ctx || slot < 0 || slot >= C8B_ONE_SLOTS || !ctx->one[slot].ev || !f || !pdu_out) return C8B_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const volatile uint32_t* flag = ctx->oneFlagH + 8 + slot;
+    if (wait) {
+        if (c8b_wait_flag(flag, ctx->one[slot].seq, ctx->st) != 0) CK(cudaEventSynchronize(ctx->one[slot].ev));
+    } else if (*flag != ctx->one[slot].seq) return 0;
+    const uint8_t* h = reinterpret_cast<const uint8_t*>(ctx->one[slot].host);
+    *f = reinterpret_cast<const OneHdr*>(h + 2 * 4400 + 256)->f;
+    *pdu_out = h;
+    return 1;
+}

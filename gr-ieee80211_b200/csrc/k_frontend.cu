@@ -262,6 +262,33 @@ k_sc16_to_fc32(const short2* __restrict__ in, float2* __restrict__ out, int64_t 
 }
 }  // namespace
 
+// Completion flag in mapped host memory: the last thing an op enqueues.  The host thread then polls that word instead of
+// calling cudaStreamSynchronize -- with one thread per block (GNU Radio's scheduler) the waits of five blocks inside the
+// driver queue up behind each other, a load from pinned memory does not.
+namespace {
+__global__ void k_flag(volatile uint32_t* flag, uint32_t seq)
+{
+    __threadfence_system();
+    *flag = seq;
+}
+}  // namespace
+void c8b_launch_flag(uint32_t* d_flag, uint32_t seq, cudaStream_t st) { k_flag<<<1, 1, 0, st>>>(d_flag, seq); }
+
+int c8b_wait_flag(const volatile uint32_t* h_flag, uint32_t seq, cudaStream_t st)
+{
+    for (unsigned spins = 0;; spins++) {
+        if (*h_flag == seq) return 0;
+        if ((spins & 0xffff) == 0xffff) {                             // every ~65k polls: has the stream died / drained without the flag?
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaSuccess) return *h_flag == seq ? 0 : -1;
+            if (e != cudaErrorNotReady) return -1;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
 void c8b_launch_sc16_to_fc32(const short2* in, float2* out, int64_t n, cudaStream_t st)
 {
     if (n <= 0) return;

@@ -1135,6 +1135,135 @@ void c8b_launch_header2_w(const c8b_lut* lut, const float2* iq0, const float2* i
     k_header2_w<<<(ns + FW2 - 1) / FW2, FW2 * 32, 0, st>>>(lut, iq0, iq1, d_off, ns, maxf, mmse, frames, chan, hinv, w2, llrStride);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One event of one block per launch: the kernels behind the per-block entry points (csrc/blocks.cu, c8b_blk_work), the
+// same warp routines as the batch path.  Result layouts are those of c8b_blocks::SyncRes / SignalRes (blocks.h); the result
+// pointers may be mapped host memory (a 20-byte / 1 KB posted write instead of a device-to-host copy).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(32)
+k_one_sync_w(const float2* __restrict__ sig, float2 conj, int32_t* __restrict__ res)
+{
+    __shared__ Ws w;
+    const SyncOut o = sync_at_w(reinterpret_cast<const cf*>(sig), mk(conj.x, conj.y), w, threadIdx.x);
+    if (threadIdx.x == 0) {
+        res[0] = o.ok; res[1] = o.mIndex;
+        reinterpret_cast<float*>(res)[2] = o.rad; reinterpret_cast<float*>(res)[3] = o.snr; reinterpret_cast<float*>(res)[4] = o.rssi;
+    }
+}
+
+// L-SIG of one sync flag (in = >= 224 samples from the flag) and, in the same launch, the S_COPY loop of the call that
+// found it (lib/signal_impl.cc:108-192): ncopy samples from in + 224 rotated by the CFO phase into out0 (out1: antenna 1
+// of signal2 from in1 + 224).  The host decides afterwards how many of them the block's accounting hands on (it knows
+// nsamp only from this kernel's result); ncopy = 0: the L-SIG alone.
+__global__ void __launch_bounds__(128)
+k_one_signal_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ in, const float2* __restrict__ in1, float rad, int32_t* __restrict__ res,
+               float2* __restrict__ out0, float2* __restrict__ out1, int ncopy)
+{
+    __shared__ Ws w;
+    if (threadIdx.x < 32) {
+        int mcs = 0, len = 0, nsamp = 0;
+        const int ok = signal_at_w(lut, reinterpret_cast<const cf*>(in), rad, reinterpret_cast<float2*>(res + 4), &mcs, &len, &nsamp, w, threadIdx.x);
+        if (threadIdx.x == 0) { res[0] = ok; res[1] = mcs; res[2] = len; res[3] = nsamp; }
+    } else {
+        for (int i = threadIdx.x - 32; i < ncopy; i += 96) {
+            const cf ph = cis(fmul((float)(i + 224), rad));          // lib/signal_impl.cc:172-173, d_nSampleCopied = i
+            out0[i] = st(cmul(ld(&in[224 + i]), ph));
+            if (in1) out1[i] = st(cmul(ld(&in1[224 + i]), ph));
+        }
+    }
+}
+
+// The trigger FSM (lib/trigger_impl.cc:59-117) over one call's samples, a bitmap word (32 samples, lane = sample) at a
+// time, continued from the state the previous call left: the FSM changes course only where a plateau reaches its 21st
+// sample (count-down armed) and where the count-down ends (0x01); between those the word is applied in closed form, and
+// the 0x02 flags ("new maximum of the plateau") are the lanes that beat the running prefix maximum of their run.
+__global__ void __launch_bounds__(32)
+k_one_trigger_w(TrigState* __restrict__ state, const float* __restrict__ in, int n, uint8_t* __restrict__ out)
+{
+    const int lane = threadIdx.x;
+    TrigState s = *state;
+    constexpr int WB = 8;                                         // words fetched together: the loads of a block are independent,
+    for (int blk = 0; blk < n; blk += 32 * WB) {                   // only the FSM that walks them is serial
+        float pvs[WB];
+        uint32_t aboves[WB];
+#pragma unroll
+        for (int w = 0; w < WB; w++) {
+            const int i = blk + 32 * w + lane;
+            pvs[w] = i < n ? in[i] : 0.f;
+        }
+#pragma unroll
+        for (int w = 0; w < WB; w++) aboves[w] = __ballot_sync(FULL, blk + 32 * w + lane < n && pvs[w] > 0.3f);
+#pragma unroll
+        for (int w = 0; w < WB; w++) {
+            const int base = blk + 32 * w;
+            if (base >= n) break;
+            const int i = base + lane, kmax = min(32, n - base);
+            const float pv = pvs[w];
+            const uint32_t above = aboves[w];
+            uint32_t fl = 0;
+            if (above == 0u && kmax == 32 && !s.fPlateau) {         // a quiet word with no count-down running: the reset state
+                s.nPlateau = 0; s.fPlateauEnd = 0; s.conjAc = 0.0f;
+                out[i] = 0;
+                continue;
+            }
+            for (int k = 0; k < kmax;) {
+                const uint32_t rest = above >> k;
+                if (!(rest & 1u)) {                                   // samples k .. k + gap - 1 below the threshold (:96-101)
+                    const int gap = rest ? __ffs(rest) - 1 : kmax - k;
+                    s.nPlateau = 0; s.fPlateauEnd = 0; s.conjAc = 0.0f;
+                    if (s.fPlateau) {
+                        if (s.countDown <= gap) { if (lane == k + s.countDown - 1) fl |= 1u; s.countDown = 0; s.fPlateau = 0; }
+                        else s.countDown -= gap;
+                    }
+                    k += gap;
+                    continue;
+                }
+                const uint32_t inv = ~rest;
+                const int P = min(inv ? __ffs(inv) - 1 : 32, kmax - k);      // run above the threshold: samples k .. k + P - 1
+                const bool inRun = lane >= k && lane < k + P;
+                float incl = inRun ? pv : -1.0f;                          // inclusive prefix maximum over the run (preac >= 0)
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl = fmaxf(incl, t); }
+                float excl = __shfl_up_sync(FULL, incl, 1);
+                if (lane == 0) excl = -1.0f;
+                if (inRun && pv > fmaxf(s.conjAc, excl)) fl |= 2u;         // :82-87
+                const float runMax = __shfl_sync(FULL, incl, k + P - 1);
+                int done = 0;                                             // samples of the run already accounted for
+                if (s.fPlateau) {                                         // a count-down from an earlier plateau runs through (:103-111)
+                    if (s.countDown <= P) { if (lane == k + s.countDown - 1) fl |= 1u; done = s.countDown; s.countDown = 0; s.fPlateau = 0; }
+                    else { s.countDown -= P; done = P; }
+                }
+                if (!s.fPlateau && s.fPlateauEnd == 0 && done < P) {      // armed at the first sample with nPlateau > 20 (:88-93)
+                    const int r = max(done + 1, 21 - s.nPlateau);
+                    if (r <= P) { s.fPlateau = 1; s.fPlateauEnd = 1; s.countDown = 79 - (P - r); }
+                }
+                s.nPlateau += P;
+                s.conjAc = fmaxf(s.conjAc, runMax);
+                k += P;
+            }
+            if (i < n) out[i] = (uint8_t)fl;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *state = s;
+}
+}  // namespace
+
+void c8b_launch_one_sync(const float2* d_sig, float conj_re, float conj_im, void* res, cudaStream_t st)
+{
+    k_one_sync_w<<<1, 32, 0, st>>>(d_sig, make_float2(conj_re, conj_im), reinterpret_cast<int32_t*>(res));
+}
+void c8b_launch_one_signal(const c8b_lut* lut, const float2* d_in, const float2* d_in1, float rad, void* res, float2* d_out0, float2* d_out1,
+                           int ncopy, cudaStream_t st)
+{
+    k_one_signal_w<<<1, 128, 0, st>>>(lut, d_in, d_in1, rad, reinterpret_cast<int32_t*>(res), d_out0, d_out1, ncopy);
+}
+void c8b_launch_one_trigger(void* d_state, const float* d_in, int n, uint8_t* d_out, cudaStream_t st)
+{
+    k_one_trigger_w<<<1, 32, 0, st>>>(reinterpret_cast<TrigState*>(d_state), d_in, n, d_out);
+}
+
 void c8b_launch_detect_w(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,
                          int maxf, int64_t outBase, const float* preac, const uint32_t* mask, int maskStride, c8b_frame* frames,
                          float2* chan, c8b_scan* scans, cudaStream_t st)

@@ -78,6 +78,19 @@ public:
         for (auto& r : ninput_items_required) r = c8b_blk_forecast(KIND, noutput_items);
     }
 
+    // decode publishes a frame's MPDUs one call after its last soft bit (the GPU works on it meanwhile): when the flowgraph
+    // stops, a call without input collects what is still in flight
+    bool stop() override
+    {
+        if (KIND == C8B_BLK_DECODE) {
+            gr_vector_int none(1, 0);
+            gr_vector_const_void_star in(1, nullptr);
+            gr_vector_void_star out;
+            general_work(0, none, in, out);                         // at most four frames in flight: one call publishes them all
+        }
+        return true;
+    }
+
     int general_work(int noutput_items, gr_vector_int& ninput_items, gr_vector_const_void_star& input_items,
                      gr_vector_void_star& output_items) override
     {

@@ -35,6 +35,13 @@ static std::vector<char> slurp(const std::string& p)
     return std::vector<char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
 }
 
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <thread>
+static std::map<std::string, std::pair<double, long>> g_wall;   // block name -> (ms inside general_work, calls)
+static std::mutex g_wall_mu;
 static uint32_t rng_state = 1;
 static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
 
@@ -79,7 +86,7 @@ static bool call(gr::block& b, int maxCall, bool big)
     for (int v : ninput) most = std::max(most, v);
     if (noutput <= 0 && most <= 0) return false;
     gr_vector_const_void_star in(nin);
-    for (int k = 0; k < nin; k++) in[k] = b.mock_in[k]->data.data();
+    for (int k = 0; k < nin; k++) in[k] = b.mock_in[k]->data.data() + b.mock_in[k]->head;
     std::vector<std::vector<char>> obuf(nout);
     gr_vector_void_star out(nout);
     for (int k = 0; k < nout; k++) {
@@ -88,16 +95,26 @@ static bool call(gr::block& b, int maxCall, bool big)
     }
     b.mock_consumed = 0;
     const size_t tagsBefore = b.mock_tags_added.size(), msgBefore = b.mock_messages.size();
+    const auto tw0 = std::chrono::steady_clock::now();
     const int produced = b.general_work(noutput, ninput, in, out);
+    {
+        std::lock_guard<std::mutex> lk(g_wall_mu);
+        auto& acc = g_wall[b.name()];
+        acc.first += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+        acc.second++;
+    }
     if (produced < 0 || produced > noutput || b.mock_consumed < 0) { std::cerr << b.name() << ": bad accounting" << std::endl; exit(3); }
     for (int k = 0; k < nin; k++) {
         edge* e = b.mock_in[k];
         if ((size_t)b.mock_consumed > e->avail()) { std::cerr << b.name() << ": consumed more than available" << std::endl; exit(3); }
-        e->data.erase(e->data.begin(), e->data.begin() + (size_t)b.mock_consumed * e->item);
+        e->head += (size_t)b.mock_consumed * e->item;              // (no erase per call: the sources hold the whole capture)
         e->nread += b.mock_consumed;
-        std::vector<gr::tag_t> keep;
-        for (auto& t : e->tags) if (t.offset >= e->nread) keep.push_back(t);
-        e->tags.swap(keep);
+        if (e->head > (1u << 22) && e->head * 2 > e->data.size()) { e->data.erase(e->data.begin(), e->data.begin() + (ptrdiff_t)e->head); e->head = 0; }
+        if (e->tags.size() > 64) {
+            std::vector<gr::tag_t> keep;
+            for (auto& t : e->tags) if (t.offset >= e->nread) keep.push_back(t);
+            e->tags.swap(keep);
+        }
     }
     for (int k = 0; k < nout; k++) {
         const size_t bytes = (size_t)produced * b.output_signature()->sizeof_stream_item(k);
@@ -105,6 +122,160 @@ static bool call(gr::block& b, int maxCall, bool big)
         b.mock_written[k] += produced;
     }
     return b.mock_consumed > 0 || produced > 0 || b.mock_tags_added.size() != tagsBefore || b.mock_messages.size() != msgBefore;
+}
+
+// ---- thread-per-block mode (RUN_CHAIN_TPB=1): GNU Radio 3.10's default scheduler gives every block its own thread; the
+// blocks of a chain then work on different frames at the same time and the chain runs at the pace of its slowest block.
+// One mutex guards the edges; a call snapshots its input windows (items + tags) under it, runs general_work on the
+// snapshot with the lock released, and commits consumption / output / tags under it again.  Call sizes are the largest
+// the edges allow (what the executor offers a block that keeps up), capped at MAXCALL.
+struct Tpb {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<uint64_t> epoch{ 0 };
+    std::atomic<long long> lastNs{ 0 };
+    std::atomic<bool> stop{ false }, flush{ false };
+    std::chrono::steady_clock::time_point t0;
+};
+
+static bool call_tpb(gr::block& b, const std::vector<edge*>& rin, const std::vector<std::vector<edge*>>& rout, int maxCall, Tpb& T)
+{
+    const int nin = (int)rin.size(), nout = (int)rout.size();
+    std::vector<edge> pin((size_t)nin), pout((size_t)nout);
+    std::vector<const char*> inp((size_t)nin, nullptr);
+    gr_vector_int req(nin), ninput(nin);
+    int noutput = maxCall;
+    const bool flush = T.flush.load();
+    {
+        std::unique_lock<std::mutex> lk(T.mu);
+        size_t minAvail = (size_t)-1;
+        for (edge* e : rin) minAvail = std::min(minAvail, e->avail());
+        if (nout > 0) {
+            noutput = (int)std::min<size_t>((size_t)maxCall, minAvail);
+            if (noutput == 0 && (b.name() == "demod" || b.name() == "demod2")) noutput = maxCall;
+            if (flush && b.name() != "trigger" && b.name() != "sync") noutput = maxCall;
+        }
+        b.forecast(noutput, req);
+        int most = 0;
+        for (int k = 0; k < nin; k++) { ninput[k] = (int)std::min<size_t>(rin[k]->avail(), (size_t)std::max(req[k], noutput)); most = std::max(most, ninput[k]); }
+        if (noutput <= 0 && most <= 0) return false;
+        if (nout == 0 && most <= 0 && !flush) return false;          // a sink with nothing to read (woken again by its neighbour)
+        for (int k = 0; k < nin; k++) {
+            // the items are read in place: run_tpb reserved every edge for the whole run, so an append by the producer never
+            // moves them; only the counters and the tags of the window are snapshot
+            edge* e = rin[k];
+            pin[k].item = e->item;
+            inp[k] = e->data.data() + e->head;
+            pin[k].nread = e->nread; pin[k].nwritten = e->nread + (uint64_t)ninput[k];
+            for (auto& t : e->tags) if (t.offset >= e->nread && t.offset < e->nread + (uint64_t)ninput[k]) pin[k].tags.push_back(t);
+        }
+    }
+    for (int k = 0; k < nin; k++) b.mock_in[k] = &pin[k];
+    for (int k = 0; k < nout; k++) { pout[k].item = b.output_signature()->sizeof_stream_item(k); b.mock_out[k].assign(1, &pout[k]); }
+    gr_vector_const_void_star in(nin);
+    for (int k = 0; k < nin; k++) in[k] = inp[k];
+    std::vector<std::vector<char>> obuf(nout);
+    gr_vector_void_star out(nout);
+    for (int k = 0; k < nout; k++) { obuf[k].assign((size_t)std::max(noutput, 1) * pout[k].item, 0); out[k] = obuf[k].data(); }
+    b.mock_consumed = 0;
+    const size_t tagsBefore = b.mock_tags_added.size(), msgBefore = b.mock_messages.size();
+    const auto tw0 = std::chrono::steady_clock::now();
+    const int produced = b.general_work(noutput, ninput, in, out);
+    const double wms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+    if (produced < 0 || produced > noutput || b.mock_consumed < 0) { std::cerr << b.name() << ": bad accounting" << std::endl; exit(3); }
+    const bool moved = b.mock_consumed > 0 || produced > 0 || b.mock_tags_added.size() != tagsBefore || b.mock_messages.size() != msgBefore;
+    {
+        std::unique_lock<std::mutex> lk(T.mu);
+        for (int k = 0; k < nin; k++) {
+            edge* e = rin[k];
+            if ((size_t)b.mock_consumed > e->avail()) { std::cerr << b.name() << ": consumed more than available" << std::endl; exit(3); }
+            e->head += (size_t)b.mock_consumed * e->item;            // (no compaction in this mode: readers hold pointers into the edge)
+            e->nread += b.mock_consumed;
+            if (e->tags.size() > 64) {
+                size_t q = 0;
+                for (auto& t : e->tags) if (t.offset >= e->nread) e->tags[q++] = t;
+                e->tags.resize(q);
+            }
+        }
+        for (int k = 0; k < nout; k++) {
+            const size_t bytes = (size_t)produced * pout[k].item;
+            for (edge* e : rout[k]) {
+                e->data.insert(e->data.end(), obuf[k].begin(), obuf[k].begin() + (ptrdiff_t)bytes);
+                e->nwritten += produced;
+                for (auto& t : pout[k].tags) e->tags.push_back(t);
+            }
+            b.mock_written[k] += produced;
+        }
+        auto& acc = g_wall[b.name()];
+        acc.first += wms; acc.second++;
+        if (moved) {
+            T.epoch++;
+            T.lastNs = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - T.t0).count();
+        }
+    }
+    if (moved) T.cv.notify_all();
+    return moved;
+}
+
+static double run_tpb(gr::block* const order[5], int maxCall)
+{
+    Tpb T;
+    std::vector<std::vector<edge*>> rin(5);
+    std::vector<std::vector<std::vector<edge*>>> rout(5);
+    for (int i = 0; i < 5; i++) { rin[i] = order[i]->mock_in; rout[i] = order[i]->mock_out; }
+    // room for everything the run can append: the samples once per edge, the soft bits at <= 416 per 72 samples and antenna
+    size_t nsamp = 0;
+    for (edge* e : rin[0]) nsamp = std::max(nsamp, e->avail());
+    for (int i = 0; i < 5; i++)
+        for (auto& port : rout[i])
+            for (edge* e : port) e->data.reserve(e->data.size() + (size_t)e->item * (e->item == 4 ? nsamp * 12 + (1u << 20) : nsamp * 2 + (1u << 20)));
+    T.t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int i = 0; i < 5; i++)
+        th.emplace_back([&, i]() {
+            int still = 0;                                       // calls in a row that moved nothing
+            while (!T.stop.load()) {
+                if (call_tpb(*order[i], rin[i], rout[i], maxCall, T)) { still = 0; continue; }
+                // a state machine may change state without consuming or producing (RDTAG -> FORMAT ...): GNU Radio's executor
+                // calls such a block again at once; only after three such calls does the thread wait for a neighbour
+                if (++still < 3) continue;
+                // wait for a neighbour to move something: poll the progress counter for a while (a futex wake-up costs tens of
+                // microseconds, a frame is worth about a hundred), then sleep on the condition variable
+                const uint64_t e0 = T.epoch.load();
+                const auto tw = std::chrono::steady_clock::now();
+                bool woke = false;
+                while (std::chrono::steady_clock::now() - tw < std::chrono::microseconds(300))
+                    if (T.epoch.load(std::memory_order_relaxed) != e0 || T.stop.load() || T.flush.load()) { woke = true; break; }
+                if (!woke) {
+                    std::unique_lock<std::mutex> lk(T.mu);
+                    T.cv.wait_for(lk, std::chrono::microseconds(200));
+                }
+                still = 0;
+            }
+        });
+    uint64_t seen = T.epoch.load();
+    int quiet = 0;
+    long long idleNs = 0, lastBeforeFlush = 0;
+    while (true) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        const uint64_t e = T.epoch.load();
+        if (e != seen) { seen = e; quiet = 0; continue; }
+        if (++quiet < 25) continue;                                  // 50 ms without a move
+        if (!T.flush.load()) {
+            // the quiet 50 ms that led here are the scheduler waiting, not the chain working: they do not count
+            lastBeforeFlush = T.lastNs.load();
+            idleNs = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - T.t0).count() - lastBeforeFlush;
+            T.flush = true; quiet = 0; T.cv.notify_all();
+            continue;
+        }
+        break;
+    }
+    T.stop = true;
+    T.cv.notify_all();
+    for (auto& t : th) t.join();
+    for (int i = 0; i < 5; i++) { order[i]->mock_in = rin[i]; order[i]->mock_out = rout[i]; }
+    const long long last = T.lastNs.load();
+    return (double)(last > lastBeforeFlush ? last - idleNs : last) * 1e-6;      // (items that only moved in the closing phase)
 }
 
 static std::string show(const pmt::pmt_t& v)
@@ -154,15 +325,23 @@ int main(int argc, char** argv)
 
     gr::block* order[5] = { trig.get(), syn.get(), sig.get(), dem.get(), dec.get() };
     const auto t0 = std::chrono::steady_clock::now();
-    for (int idle = 0; idle < 3;) {
-        bool moved = false;
-        for (gr::block* b : order)
-            for (int r = 1 + (int)(rnd() % 3u); r > 0; r--) moved |= call(*b, maxCall, idle > 0);
-        idle = moved ? 0 : idle + 1;
+    const bool tpb = getenv("RUN_CHAIN_TPB") && atoi(getenv("RUN_CHAIN_TPB")) != 0;
+    double ms;
+    if (tpb) ms = run_tpb(order, maxCall);                        // one thread per block; ms = up to the last item that moved
+    else {
+        for (int idle = 0; idle < 3;) {
+            bool moved = false;
+            for (gr::block* b : order)
+                for (int r = 1 + (int)(rnd() % 3u); r > 0; r--) moved |= call(*b, maxCall, idle > 0);
+            idle = moved ? 0 : idle + 1;
+        }
+        for (gr::block* b : order) b->stop();                     // (GNU Radio calls stop() on every block: decode publishes what is in flight)
+        ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
-
-    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    std::cout << "run_chain: " << s0.size() / 8 << " samples, " << dec->mock_messages.size() << " messages, " << ms << " ms wall" << std::endl;
+    if (tpb) for (gr::block* b : order) b->stop();
+    std::cout << "run_chain: " << s0.size() / 8 << " samples, " << dec->mock_messages.size() << " messages, " << ms << " ms wall"
+              << (tpb ? " (thread per block)" : " (one thread, round robin)") << std::endl;
+    for (auto& kv : g_wall) std::cout << "run_chain:   " << kv.first << " " << kv.second.first << " ms in " << kv.second.second << " calls" << std::endl;
 
     FILE* f = fopen(argv[8], "w");
     if (!f) return 2;

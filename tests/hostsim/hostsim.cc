@@ -92,8 +92,9 @@ struct HostBlk {
         r->ok = o.ok; r->mIndex = o.mIndex; r->rad = o.rad; r->snr = o.snr; r->rssi = o.rssi;
         return 0;
     }
-    int signal_at(const float* in, float rad, c8b_blocks::SignalRes* r)
+    int signal_at(const float* in, const float*, int, float rad, c8b_blocks::SignalRes* r, const float** rot0, const float** rot1)
     {
+        *rot0 = *rot1 = nullptr;                                  // (this backend corrects the S_COPY samples in cfo_copy)
         cf h[64];
         r->mcs = r->len = r->nsamp = 0;
         r->ok = c8b::signal_at(lut(), (const cf*)in, rad, h, &r->mcs, &r->len, &r->nsamp);
@@ -109,23 +110,50 @@ struct HostBlk {
         }
         return 0;
     }
-    int demod(int nant, const float* iq0, const float* iq1, int n, c8b_frame* f, const float* chan, std::vector<float>* llr)
+    // demod: header states on the host at submission (zero soft bits); collect hands the queue out in order
+    std::vector<c8b_frame> mq;
+    std::vector<float> msoft;
+    int demod_submit(int nant, const float* iq0, const float* iq1, int, const c8b_frame* fin, const float* chan)
     {
+        c8b_frame f = *fin;
         float hinv[128], w2[528];
-        if (nant == 2) hs_header2(iq0, iq1, f, chan, hinv, w2);
-        else hs_header(iq0, f, chan, mupos, hinv);
-        llr->assign((size_t)std::max(f->total, 1024), 0.f);
+        if (nant == 2) hs_header2(iq0, iq1, &f, chan, hinv, w2);
+        else hs_header(iq0, &f, chan, mupos, hinv);
+        mq.push_back(f);
         return 0;
     }
-    int decode(c8b_frame* f, const float*, int, uint8_t* pdu, int cap)
+    int demod_collect(bool, c8b_frame* f, const float** soft, int* nsoft)
     {
-        const int n = f->len + 4;
-        if (n > cap) return C8B_ERR_ARG;
-        pdu[0] = (uint8_t)f->format; pdu[1] = (uint8_t)(f->len & 255); pdu[2] = (uint8_t)(f->len >> 8);
-        memset(pdu + 3, 0xA5, (size_t)f->len);
-        pdu[3 + f->len] = (uint8_t)f->mcs;
-        f->npdu = 1; f->pdu_bytes = n;
+        if (mq.empty()) return 0;
+        *f = mq.front();
+        mq.erase(mq.begin());
+        msoft.assign((size_t)std::max(f->total, 1024), 0.f);
+        *soft = msoft.data();
+        *nsoft = (int)msoft.size();
+        return 1;
+    }
+    // decode: the placeholder record is made at submission; collect hands the queue out in order
+    std::vector<std::pair<c8b_frame, std::vector<uint8_t>>> dq;
+    std::vector<uint8_t> cur;
+    int decode_submit(const c8b_frame* fin, const float*, int)
+    {
+        c8b_frame f = *fin;
+        std::vector<uint8_t> pdu((size_t)f.len + 4);
+        pdu[0] = (uint8_t)f.format; pdu[1] = (uint8_t)(f.len & 255); pdu[2] = (uint8_t)(f.len >> 8);
+        memset(pdu.data() + 3, 0xA5, (size_t)f.len);
+        pdu[3 + f.len] = (uint8_t)f.mcs;
+        f.npdu = 1; f.pdu_bytes = f.len + 4;
+        dq.emplace_back(f, pdu);
         return 0;
+    }
+    int decode_collect(bool, c8b_frame* f, const uint8_t** pdu)
+    {
+        if (dq.empty()) return 0;
+        *f = dq.front().first;
+        cur = dq.front().second;
+        dq.erase(dq.begin());
+        *pdu = cur.data();
+        return 1;
     }
 };
 }  // namespace
