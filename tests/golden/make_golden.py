@@ -192,6 +192,39 @@ def frames_sgi():
     print("frames_sgi:", [len(x) for x in items])
 
 
+def frames_sgi_true():
+    """Short-GI frames the reference's receiver DECODES.  The generator writes the SIG fields for short GI but builds 80-sample
+    symbols (frames_sgi: every symbol after the first is off the 72-sample raster, CRC fails).  The reference's demod reads the
+    window [8, 72) of every symbol -- 8 samples into the cyclic prefix, the same offset its channel estimate has from the LTF
+    (C8P_SYM_SAMP_SHIFT) -- so the waveform it decodes on a 72-sample raster is the FIRST 72 samples of each 80-sample DATA
+    symbol (a transmitter's own short-GI symbol [8-sample prefix][body] would sit 8 samples off that estimate).  These
+    frames pass the CRC: the well-conditioned parity case for nSymSamp = 72 on every symbol.  HT MCS 0 / 5 / 7, VHT MCS 3 / 7."""
+    phy = phy80211.phy80211(ifDebug=False)
+    rng = np.random.default_rng(72)
+    items, mpdus = [], []
+    for fmt, mcs, nbytes in ((p8h.F.HT, 5, 94), (p8h.F.VHT, 7, 94), (p8h.F.HT, 0, 60), (p8h.F.HT, 7, 700), (p8h.F.VHT, 3, 400)):
+        body = bytes(rng.integers(0, 256, nbytes - 4, dtype=np.uint8))
+        import zlib
+        mp = body + (zlib.crc32(body) & 0xffffffff).to_bytes(4, "little")
+        mod = p8h.modulation(phyFormat=fmt, mcs=mcs, bw=p8h.BW.BW20, nSTS=1, shortGi=True)
+        if fmt == p8h.F.VHT:
+            quiet(phy.genFromAmpdu, mac80211.genAmpduVHT([mp]), mod, vhtPartialAid=0, vhtGroupId=0)
+        else:
+            quiet(phy.genFromMpdu, mp, mod)
+        x = np.asarray(quiet(phy.genFinalSig, multiplier=12.0, cfoHz=0.0, num=1, gap=True, gapLen=400)[0], dtype=np.complex64)
+        # frame = 400 zeros + preamble + data + 400 zeros; data starts after L-STF/L-LTF/L-SIG (400) + SIG (160) + STF (80) + LTF (80) [+ SIG-B (80)]
+        pre = 400 + 400 + 160 + 80 + 80 + (80 if fmt == p8h.F.VHT else 0)
+        nsym = (x.size - 400 - pre) // 80
+        assert pre + nsym * 80 + 400 == x.size, (x.size, pre, nsym)
+        data = x[pre:pre + nsym * 80].reshape(nsym, 80)[:, :72]
+        items.append(np.concatenate([x[:pre], data.reshape(-1), x[pre + nsym * 80:]]).astype(np.complex64))
+        mpdus.append(np.frombuffer(mp, np.uint8))
+    offs = np.cumsum([0] + [len(v) for v in items]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "frames_sgi_true.npz"), iq=np.concatenate(items), offs=offs,
+                        exp_mpdu=np.concatenate(mpdus), exp_len=np.array([m.size for m in mpdus], np.int32))
+    print("frames_sgi_true:", [len(v) for v in items])
+
+
 def frames_mu():
     """VHT sounding and MU-MIMO as one station antenna sees them (tools/cmu_ap.py:64-200 is the reference's recipe):
       * NDP: genFromAmpdu with an empty A-MPDU, nSTS = 2 -> two transmit streams; the station receives h0*tx0 + h1*tx1.
@@ -307,7 +340,7 @@ def ref_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi", "mu", "tx"]
+    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi", "sgi_true", "mu", "tx"]
     if "mu" in which:
         frames_mu()
     if "tx" in which:
@@ -324,3 +357,5 @@ if __name__ == "__main__":
         frames_564()
     if "sgi" in which:
         frames_sgi()
+    if "sgi_true" in which:
+        frames_sgi_true()

@@ -52,6 +52,36 @@ def test_demod_llrs_match_oracle(rx, golden, snr):
     print("worst relative LLR error %.3g" % worst)
 
 
+@pytest.mark.parametrize("snr", [None, 30.0])
+def test_short_gi_every_symbol(rx, snr):
+    """nSymSamp = 72 on EVERY symbol: frames_sgi_true is the 72-sample-raster waveform the reference's receiver decodes (the
+    first 72 samples of each 80-sample DATA symbol; the oracle is pinned to the reference's own blocks on it in
+    tests/test_ref_chain.py).  All soft bits within the LLR gate, PDUs byte for byte."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frames_sgi_true.npz"))
+    iq, offs = g["iq"], g["offs"]
+    if snr is not None:
+        rng = np.random.default_rng(6)
+        iq = (iq + (0.1875 / np.sqrt(2 * 10 ** (snr / 10))) * (rng.standard_normal(iq.size) + 1j * rng.standard_normal(iq.size))).astype(np.complex64)
+    off, ln = offs[:-1], np.diff(offs).astype(np.int32)
+    fr, chan = rx.detect(iq, off, ln)
+    fr2, llr = rx.demod(iq, off, ln, fr, chan, 64 * 416)
+    fb, pdu = rx.rx_batch(iq, off, ln)
+    worst = 0.0
+    for i in range(len(off)):
+        fo, lo, po = ol.rx_item(iq[offs[i]:offs[i + 1]], max_frames=1)
+        for k in HDR:
+            assert fr2[i][k] == fo[0][k], (i, k, fr2[i][k], fo[0][k])
+        assert fr2[i]["nsymsamp"] == 72 and fo[0]["nsym"] >= 4
+        n = int(fo[0]["total"])
+        err = np.abs(llr[i, :n] - lo[:n]) / np.maximum(1.0, np.abs(lo[:n]))
+        worst = max(worst, float(err.max()))
+        assert err.max() <= LLR_RTOL, (i, int(np.argmax(err)) // int(fo[0]["ncbps"]), float(err.max()))
+        assert fb[i]["pdu_bytes"] == po.size and bytes(pdu[i, :po.size]) == bytes(po)
+    assert int((fb["npdu"] == 1).sum()) == 3
+    print("worst relative LLR error over all short-GI symbols %.3g" % worst)
+
+
 def test_short_gi_flag_uses_72_sample_raster(rx):
     """frames announcing short GI: nSymSamp = 72 on the GPU exactly as in the oracle (fields, LLRs, no PDU)"""
     import os

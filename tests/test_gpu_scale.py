@@ -143,3 +143,51 @@ def test_config5_vht_mcs7_1500B_shard():
         assert bytes(po) == bytes(pdu[i, :po.size]), int(i)
         if good[i]:
             assert bytes(pdu[i, 3:1503]) == bytes(mpdus[int(i) % 16])
+
+
+def test_config5_the_bench_batch_failures_fail_in_the_reference_too():
+    """The batch bench.py times (configs[4]: 1 048 576 unique VHT MCS7 1500-byte frames made by the transmit synthesiser, AWGN
+    30 dB, rank-0 seed): EVERY frame the GPU does not decode to its own MPDU is re-run through the oracle and through the
+    reference's own blocks (oracle/_ref, when built) and must fail there the same way -- same drop code, same records; every
+    decoded frame equals the bytes that were sent (checked on the device, as bench.py does)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    pkg = load_pkg()
+    dev = torch.device("cuda", 0)
+    n = 1 << 20
+    rx = pkg.Receiver(device=0)
+    iq, psdu = bench.make_batch_tx(torch, dev, pkg, rx, n, seed=0)
+    off = np.arange(n, dtype=np.int64) * bench.ITEM
+    ln = np.full(n, bench.ITEM, np.int32)
+    d_frames = torch.zeros(n * pkg.FRAME_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_pdu = torch.zeros(n * bench.PDU_STRIDE, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    rx.rx_batch_dev_async(iq.data_ptr(), off, ln, d_frames.data_ptr(), d_pdu.data_ptr(), bench.PDU_STRIDE)
+    rx.sync()
+    rx.close()
+    fr = np.frombuffer(d_frames.cpu().numpy().tobytes(), dtype=pkg.FRAME_DTYPE)
+    good = (fr["status"] == 0) & (fr["npdu"] == 1) & (fr["pdu_bytes"] == bench.MPDU_LEN + 4)
+    same = torch.zeros(n, dtype=torch.bool, device=dev)
+    for b in range(0, n, 65536):
+        e = min(n, b + 65536)
+        same[b:e] = (d_pdu.view(n, bench.PDU_STRIDE)[b:e, 3:3 + bench.MPDU_LEN] == psdu[b:e, 4:4 + bench.MPDU_LEN]).all(dim=1)
+    same = same.cpu().numpy()
+    assert np.array_equal(same & good, good)                       # every decoded frame carries the MPDU that was sent
+    bad = np.nonzero(~good)[0]
+    assert 0 < bad.size < n * 5e-4, bad.size
+    h = iq.view(n, bench.ITEM)[torch.from_numpy(bad).to(dev)].cpu().numpy()
+    hp = d_pdu.view(n, bench.PDU_STRIDE)[torch.from_numpy(bad).to(dev)].cpu().numpy()
+    ref = ol.have_refchain()
+    for k, i in enumerate(bad):
+        x = np.ascontiguousarray(h[k])
+        fo, _, po = ol.rx_item(x, max_frames=1)
+        assert fo[0]["status"] == fr[i]["status"] and fo[0]["npdu"] == fr[i]["npdu"] and po.size == fr[i]["pdu_bytes"], (int(i), fo[0]["status"], fr[i]["status"])
+        assert bytes(po) == bytes(hp[k, :po.size]), int(i)
+        if ref:
+            c = ol.RefChain()
+            c.run(x, record=False)
+            assert c.messages() == ol.split_pdus(po), int(i)       # the reference's blocks publish exactly the oracle's records (none, mostly)
+            c.close()
+    print("config 5, 1M frames: %d not decoded; oracle%s agree on every one" % (bad.size, " and reference blocks" if ref else ""))

@@ -92,6 +92,23 @@ def test_short_gi_every_symbol():
         assert info["frames"] == 3 and info["soft_bits"] == 4056
 
 
+def test_short_gi_frames_that_decode():
+    """frames_sgi_true: the 72-sample-raster waveform the reference's receiver decodes (first 72 samples of every 80-sample DATA
+    symbol, see make_golden.frames_sgi_true): oracle == reference blocks on every symbol, and the HT MCS0 / MCS5 and VHT MCS3
+    frames come back as their MPDUs"""
+    g = np.load(os.path.join(HERE, "golden", "frames_sgi_true.npz"))
+    for snr in (None, 30):
+        x = g["iq"] if snr is None else _noisy(g["iq"], snr, 10)
+        bad, info = ol.chain_vs_oracle(x, seed=4, max_call=1800)
+        _check(bad, info)
+        assert info["frames"] == 5 and info["soft_bits"] == 17056 and info["messages"] == 3
+    eo = np.cumsum(np.r_[0, g["exp_len"]])
+    offs = g["offs"]
+    for i in (0, 2, 4):
+        fo, _, po = ol.rx_item(g["iq"][offs[i]:offs[i + 1]], max_frames=1)
+        assert fo[0]["nsymsamp"] == 72 and ol.split_pdus(po)[0][3:3 + g["exp_len"][i]] == bytes(g["exp_mpdu"][eo[i]:eo[i + 1]])
+
+
 def test_564_byte_frames_all_rates():
     """config 2 / 3 / 4 frame sizes: L MCS0-7, VHT MCS0-8 (SISO), HT MCS8-15 (2x2), 30 dB"""
     g = np.load(os.path.join(HERE, "golden", "frames_564.npz"))
