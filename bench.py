@@ -84,6 +84,25 @@ def ncu_traffic(kernel):
     return None
 
 
+def api_arms():
+    """The reference-facing API of north_star beside the batched call (rank 0, N = 1, outside the timed region): the live-stream
+    session fed 1M-sample pushes (tools/bench_stream.py) and the seven gr::block shells under the thread-per-block mock
+    scheduler (tools/bench_blocks.py), both on the reference's dense demo capture; 20 M samples/s = real time of one channel."""
+    out = {}
+    for key, cmd, pick in (("e2e_stream", [sys.executable, os.path.join(ROOT, "tools", "bench_stream.py"), "1048576"], "1048576"),
+                           ("e2e_blocks", [sys.executable, os.path.join(ROOT, "tools", "bench_blocks.py"), "8192", "16"], "thread_per_block")):
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+            d = json.loads(line[7:])[pick]
+            out[key] = {"value": d["samples_per_s"], "unit": "samples/s", "x_real_time_20MHz": d["samples_per_s"] / 20e6,
+                        "api": ("c8b_stream_push, 1 Mi-sample pushes from pinned memory, %d of %d PDUs" % (d["pdus"], d["sent"])) if key == "e2e_stream"
+                        else ("the seven gr::block shells (c8b_blk_work), thread per block, %d messages from %d samples" % (d["messages"], d["samples"]))}
+        except Exception as e:                                       # noqa: BLE001 -- an arm that cannot run reports why
+            out[key] = {"value": None, "error": repr(e)[:200]}
+    return out
+
+
 def bind_near_gpu(torch, index):
     """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the PCI device) BEFORE any pinned host buffer is
     allocated: first-touch then places the staging memory on the GPU's own NUMA node, so N ranks do not all pull their
@@ -557,6 +576,7 @@ def main():
                                     "frames_per_s": nb / dt, "single_thread_samples_per_s": n1 * ITEM / dt1,
                                     "cpu_model": cpu_model(),
                                     "sample": "%d config-5 items through %s, %d threads, %d decoded" % (nb, CPU_SAMPLE[kind], cores, okc)}
+            line.update(api_arms())
             if kind == "reference":                                          # the restated oracle beside it, for the record
                 dtp, _ = cpu_arm(nb, cores, seed=1, kind="port")
                 line["cpu_baseline"]["port_samples_per_s"] = nb * ITEM / dtp

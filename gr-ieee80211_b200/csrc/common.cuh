@@ -55,7 +55,8 @@ size_t c8b_tx_plan_bytes(int nframes);
 uint32_t c8b_tx_eof_word(void);
 void c8b_tx_scrambler(int seed, uint32_t out[4]);
 void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
-                   float2* d_out, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);
+                   float2* d_out, float2* d_out1, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);
+int c8b_tx_nss_host(int format, int mcs);
 void c8b_launch_tx_fill(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, uint8_t* d_psdu, uint64_t seed, cudaStream_t st);
 size_t c8b_detect_multi_scratch(int nitems, int maxLen);   // maxLen: longest item, samples
 void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,

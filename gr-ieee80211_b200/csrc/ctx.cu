@@ -1094,7 +1094,7 @@ int c8b_tx_nsamp(int format, int mcs, int psdu_len)
 }
 
 static int tx_run(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
-                  int seed, float* d_iq, int64_t iq_samples)
+                  int seed, float* d_iq, float* d_iq1, int64_t iq_samples)
 {
     if (seed < 1 || seed > 127) { ctx->err = "c8b_tx_batch: scrambler seed 1..127"; return C8B_ERR_ARG; }
     int maxSlots = 0;
@@ -1102,6 +1102,7 @@ static int tx_run(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const
         int nsym = 0, nslots = 0;
         const c8b_txframe& f = frames[i];
         if (!c8b_tx_geometry_host(f.format, f.mcs, f.psdu_len, &nsym, &nslots)) { ctx->err = "c8b_tx_batch: unsupported format / mcs / length"; return C8B_ERR_ARG; }
+        if (c8b_tx_nss_host(f.format, f.mcs) == 2 && !d_iq1) { ctx->err = "c8b_tx_batch: a two-stream frame needs the two-antenna call (c8b_tx_batch2)"; return C8B_ERR_ARG; }
         if (f.psdu_off < 0 || f.psdu_off + f.psdu_len > psdu_bytes || f.out_off < 0 || f.out_off + (int64_t)nslots * 80 > iq_samples) {
             ctx->err = "c8b_tx_batch: frame outside the PSDU / IQ arena";
             return C8B_ERR_ARG;
@@ -1113,7 +1114,7 @@ static int tx_run(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const
     CK(cudaMemcpyAsync(ctx->txf.p, frames, (size_t)nframes * sizeof(c8b_txframe), cudaMemcpyHostToDevice, ctx->st));
     uint32_t scr[4];
     c8b_tx_scrambler(seed, scr);
-    c8b_launch_tx(ctx->d_lut, (const c8b_txframe*)ctx->txf.p, nframes, maxSlots, ctx->txplan.p, d_psdu, (float2*)d_iq, multiplier, scr,
+    c8b_launch_tx(ctx->d_lut, (const c8b_txframe*)ctx->txf.p, nframes, maxSlots, ctx->txplan.p, d_psdu, (float2*)d_iq, (float2*)d_iq1, multiplier, scr,
                   c8b_tx_eof_word(), ctx->st);
     CK(cudaGetLastError());
     return C8B_OK;
@@ -1122,12 +1123,18 @@ static int tx_run(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const
 int c8b_tx_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
                      int scrambler_seed, float* d_iq, int64_t iq_samples)
 {
-    if (!ctx || !d_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !d_iq || iq_samples < 0) return C8B_ERR_ARG;
+    return c8b_tx_batch2_dev(ctx, d_psdu, psdu_bytes, frames, nframes, multiplier, scrambler_seed, d_iq, nullptr, iq_samples);
+}
+
+int c8b_tx_batch2_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                      int scrambler_seed, float* d_iq0, float* d_iq1, int64_t iq_samples)
+{
+    if (!ctx || !d_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !d_iq0 || iq_samples < 0) return C8B_ERR_ARG;
     int r = need_lut(ctx);
     if (r) return r;
     if (nframes == 0) return C8B_OK;
     CK(cudaSetDevice(ctx->device));
-    r = tx_run(ctx, d_psdu, psdu_bytes, frames, nframes, multiplier, scrambler_seed, d_iq, iq_samples);
+    r = tx_run(ctx, d_psdu, psdu_bytes, frames, nframes, multiplier, scrambler_seed, d_iq0, d_iq1, iq_samples);
     if (r) return r;
     CK(cudaStreamSynchronize(ctx->st));                            // the descriptor array is the caller's again
     return C8B_OK;
@@ -1159,19 +1166,29 @@ int c8b_tx_random_psdu_dev(c8b_ctx* ctx, uint8_t* d_psdu, int64_t psdu_bytes, co
 int c8b_tx_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
                  int scrambler_seed, float* h_iq, int64_t iq_samples)
 {
-    if (!ctx || !h_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !h_iq || iq_samples < 0) return C8B_ERR_ARG;
+    return c8b_tx_batch2(ctx, h_psdu, psdu_bytes, frames, nframes, multiplier, scrambler_seed, h_iq, nullptr, iq_samples);
+}
+
+int c8b_tx_batch2(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                  int scrambler_seed, float* h_iq0, float* h_iq1, int64_t iq_samples)
+{
+    if (!ctx || !h_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !h_iq0 || iq_samples < 0) return C8B_ERR_ARG;
     int r = need_lut(ctx);
     if (r) return r;
     CK(cudaSetDevice(ctx->device));
+    const size_t arena = ((size_t)(iq_samples + 16) * sizeof(float2) + 255) & ~(size_t)255;
     EN(txpsdu, (size_t)psdu_bytes + 16);
-    EN(txiq, (size_t)(iq_samples + 16) * sizeof(float2));
+    EN(txiq, arena * (h_iq1 ? 2 : 1));
+    float* d0 = (float*)ctx->txiq.p;
+    float* d1 = h_iq1 ? (float*)((uint8_t*)ctx->txiq.p + arena) : nullptr;
     CK(cudaMemcpyAsync(ctx->txpsdu.p, h_psdu, (size_t)psdu_bytes, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemsetAsync(ctx->txiq.p, 0, (size_t)iq_samples * sizeof(float2), ctx->st));
+    CK(cudaMemsetAsync(ctx->txiq.p, 0, arena * (h_iq1 ? 2 : 1), ctx->st));
     if (nframes > 0) {
-        r = tx_run(ctx, (const uint8_t*)ctx->txpsdu.p, psdu_bytes, frames, nframes, multiplier, scrambler_seed, (float*)ctx->txiq.p, iq_samples);
+        r = tx_run(ctx, (const uint8_t*)ctx->txpsdu.p, psdu_bytes, frames, nframes, multiplier, scrambler_seed, d0, d1, iq_samples);
         if (r) return r;
     }
-    CK(cudaMemcpyAsync(h_iq, ctx->txiq.p, (size_t)iq_samples * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_iq0, d0, (size_t)iq_samples * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    if (h_iq1) CK(cudaMemcpyAsync(h_iq1, d1, (size_t)iq_samples * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     return C8B_OK;
 }
@@ -1183,10 +1200,14 @@ int c8b_tx_udp_parse(const uint8_t* pkt, int pkt_len, c8b_txframe* f, const uint
     const int format = pkt[0], mcs = pkt[1], nss = pkt[2], len = pkt[3] | (pkt[4] << 8);
     if (format == 3) return C8B_ERR_ARG;                                      // C8P_F_VHT_MU: two users per datagram, not synthesised here
     if (len > 4095 || pkt_len < len + 5) return C8B_ERR_ARG;                  // pktPop :108-111
-    if (nss != 1) return C8B_ERR_ARG;
-    if (c8b_tx_nsamp(format, mcs, len) < 0) return C8B_ERR_ARG;
+    if (nss != 1 && nss != 2) return C8B_ERR_ARG;
+    int code = mcs;                                                           // descriptor mcs: HT 8-15 already say two streams, VHT adds 16
+    if (format == 2 && nss == 2) code = mcs + 16;
+    if (format == 0 && nss != 1) return C8B_ERR_ARG;
+    if (format == 1 && (nss == 2) != (mcs >= 8)) return C8B_ERR_ARG;
+    if (c8b_tx_nsamp(format, code, len) < 0) return C8B_ERR_ARG;
     memset(f, 0, sizeof(*f));
-    f->format = format; f->mcs = mcs; f->psdu_len = len;
+    f->format = format; f->mcs = code; f->psdu_len = len;
     if (psdu) *psdu = pkt + 5;
     return nss;
 }
@@ -1203,7 +1224,7 @@ int c8b_tx_from_udp(c8b_ctx* ctx, const uint8_t* pkts, const int64_t* pkt_off, c
         const uint8_t* body = nullptr;
         if (frames_out) { memset(&frames_out[k], 0, sizeof(c8b_txframe)); frames_out[k].psdu_len = -1; }
         if (pkt_off[k] < 0 || pkt_len[k] < 0) return C8B_ERR_ARG;
-        if (c8b_tx_udp_parse(pkts + pkt_off[k], pkt_len[k], &f, &body) < 0) continue;
+        if (c8b_tx_udp_parse(pkts + pkt_off[k], pkt_len[k], &f, &body) != 1) continue;     // (two-stream frames need two arenas: c8b_tx_batch2)
         f.psdu_off = (int64_t)arena.size();
         arena.insert(arena.end(), body, body + f.psdu_len);
         while (arena.size() & 3) arena.push_back(0);

@@ -1,4 +1,4 @@
-// k_tx.cu -- on-device synthesiser of 20 MHz one-stream 802.11a/g/n/ac transmit waveforms: the reference's
+// k_tx.cu -- on-device synthesiser of 20 MHz one- and two-stream 802.11a/g/n/ac transmit waveforms: the reference's
 // encode -> modulation -> IFFT/CP -> pad chain (lib/encode_impl.cc:130-241, lib/modulation_impl.cc, lib/pad_impl.cc:37-80,
 // lib/cloud80211phy.cc:2594-3161) in the form of its Python twin tools/phy80211.py (genFromMpdu / genFromAmpdu /
 // genFinalSig), which is the generator every receive test of the reference and of this repo is fed from -- the waveforms
@@ -14,6 +14,12 @@
 // procConcat2Symbol (first sample of a field and last sample of the field before it halved,
 // tools/phy80211header.py:894-901), tone scaling (:966-967), pilots (polarity sequence, per-symbol rotation for HT / VHT,
 // tools/phy80211.py:770-812) and the CFO rotation of genFinalSig (:832-838) are folded into the same pass.
+// Two spatial streams (HT MCS 8-15, VHT with two space-time streams; lib/encode2_impl.cc, lib/modulation2_impl.cc,
+// tools/phy80211.py:223-235,459-510,712-760): stream k goes to antenna k (direct mapping).  What changes per stream is
+// closed-form too: the stream parser (blocks of s = max(nBPSCS / 2, 1) coded bits alternate between the streams), the
+// second stream's interleaver rotation (the receive LUT deintNL[1]), its pilot pattern (HT), the LTF signs of the P matrix
+// (R on the VHT pilot tones), the 1 / sqrt(2) power split and the cyclic shifts (200 ns = 4 samples on the legacy part,
+// 400 ns = 8 samples from the HT / VHT-STF on) -- a cyclic shift is an index offset into the inverse DFT's output.
 #include "common.cuh"
 
 namespace {
@@ -22,6 +28,7 @@ constexpr int TXS = 4;              // slots per CTA (64 threads each)
 
 struct TxPlan {                     // per frame, filled by k_tx_plan
     int32_t format, mcs, nbpsc, cr, ncbps, ndbps, nsym, nslots;
+    int32_t nss, npre;              // spatial streams (1, 2); slots in front of the DATA field
     int32_t psdu_len;               // bytes handed in (MPDU, or A-MPDU for VHT)
     int32_t nbits;                  // nsym * ndbps
     int32_t tail0;                  // L / HT: first tail bit (16 + 8 * psdu_len)
@@ -32,8 +39,17 @@ struct TxPlan {                     // per frame, filled by k_tx_plan
     double cfo_step;                // rad / sample
 };
 
+// mcs of a descriptor: legacy 0-7; HT 0-15 (8-15: two streams); VHT: MCS 0-8 + 16 for two space-time streams
+__host__ __device__ inline int tx_nss(int format, int mcs)
+{
+    if (format == C8B_F_HT) return mcs >= 8 ? 2 : 1;
+    if (format == C8B_F_VHT) return mcs >= 16 ? 2 : 1;
+    return 1;
+}
 __host__ __device__ inline int tx_rate(int format, int mcs, int* nbpsc, int* cr)
 {
+    if (format == C8B_F_HT && mcs >= 8 && mcs <= 15) mcs -= 8;
+    if (format == C8B_F_VHT && mcs >= 16 && mcs <= 24) mcs -= 16;
     // legacy: signalParserL table; HT 0-7 / VHT 0-8: modulation class of tools/phy80211header.py:258-365
     const int lb[8] = { 1, 1, 2, 2, 4, 4, 6, 6 };
     const int lc[8] = { C8B_CR_12, C8B_CR_34, C8B_CR_12, C8B_CR_34, C8B_CR_12, C8B_CR_34, C8B_CR_23, C8B_CR_34 };
@@ -53,10 +69,11 @@ __host__ __device__ inline int tx_geometry(int format, int mcs, int len, int* ns
 {
     int nbpsc = 0, cr = 0;
     if (!tx_rate(format, mcs, &nbpsc, &cr) || len < 0 || len > 4095 || (len == 0 && format != C8B_F_VHT)) return 0;
-    const int ndbps = tx_ndbps((format == C8B_F_L ? 48 : 52) * nbpsc, cr);
+    const int nss = tx_nss(format, mcs);
+    const int ndbps = tx_ndbps((format == C8B_F_L ? 48 : 52) * nbpsc * nss, cr);
     const int bits = 8 * len + 16 + 6;
     *nsym = len == 0 ? 0 : (bits + ndbps - 1) / ndbps;
-    *nslots = (format == C8B_F_L ? 5 : format == C8B_F_HT ? 9 : 10) + *nsym;
+    *nslots = (format == C8B_F_L ? 5 : format == C8B_F_HT ? 8 + nss : 9 + nss) + *nsym;      // nLTF = nss
     return 1;
 }
 
@@ -84,15 +101,17 @@ __global__ void k_tx_plan(const c8b_txframe* __restrict__ fr, int n, TxPlan* __r
     int nsym = 0, nslots = 0;
     if (!tx_geometry(f.format, f.mcs, f.psdu_len, &nsym, &nslots)) { P.nslots = 0; plan[i] = P; return; }
     tx_rate(f.format, f.mcs, &P.nbpsc, &P.cr);
-    P.ncbps = (f.format == C8B_F_L ? 48 : 52) * P.nbpsc;
+    P.nss = tx_nss(f.format, f.mcs);
+    P.npre = f.format == C8B_F_L ? 5 : f.format == C8B_F_HT ? 8 + P.nss : 9 + P.nss;
+    P.ncbps = (f.format == C8B_F_L ? 48 : 52) * P.nbpsc * P.nss;
     P.ndbps = tx_ndbps(P.ncbps, P.cr);
     P.nsym = nsym; P.nslots = nslots; P.nbits = nsym * P.ndbps;
     P.tail0 = 16 + 8 * f.psdu_len;
     // L-SIG (tools/phy80211.py:236-258): rate, reserved, 12-bit length, even parity, 6 tail
     const uint32_t rateL[8] = { 0xB, 0xF, 0xA, 0xE, 0x9, 0xD, 0x8, 0xC };   // C_LEGACY_RATE_BIT, bit k = element k
     int llen = f.psdu_len;
-    if (f.format == C8B_F_HT) llen = ((36 + 4 * nsym - 20) / 4) * 3 - 3;    // txTime = 20 + 8 + 4 + 4 nLTF + 4 nSym
-    if (f.format == C8B_F_VHT) llen = ((40 + 4 * nsym - 20) / 4) * 3 - 3;   // + VHT-SIG-B
+    if (f.format == C8B_F_HT) llen = ((32 + 4 * P.nss + 4 * nsym - 20) / 4) * 3 - 3;    // txTime = 20 + 8 + 4 + 4 nLTF + 4 nSym
+    if (f.format == C8B_F_VHT) llen = ((36 + 4 * P.nss + 4 * nsym - 20) / 4) * 3 - 3;   // + VHT-SIG-B
     uint32_t ls = (f.format == C8B_F_L ? rateL[f.mcs] : rateL[0]) | ((uint32_t)(llen & 0xfff) << 5);
     ls |= (uint32_t)(__popc(ls) & 1) << 17;
     P.lsig = ls;
@@ -101,7 +120,7 @@ __global__ void k_tx_plan(const c8b_txframe* __restrict__ fr, int n, TxPlan* __r
         b |= (uint64_t)crc8_bits(b, 34) << 34;
         P.sig48 = b;
     } else if (f.format == C8B_F_VHT) {                                     // VHT-SIG-A (:355-428): SU, group id 0, partial AID 0, 1 stream
-        uint64_t b = (1ull << 2) | (1ull << 23) | ((uint64_t)(f.mcs & 0xf) << 28) | (1ull << 33);
+        uint64_t b = (1ull << 2) | ((uint64_t)(P.nss - 1) << 10) | (1ull << 23) | ((uint64_t)(f.mcs & 0xf) << 28) | (1ull << 33);
         b |= (uint64_t)crc8_bits(b, 34) << 34;
         P.sig48 = b;
         // VHT-SIG-B (:520-552): ceil(len / 4) in 17 bits, 3 reserved ones, 6 tail; NDP pattern for an empty A-MPDU
@@ -164,27 +183,31 @@ __device__ __forceinline__ float qam_level(int sign, int m)   // Gray-mapped amp
 
 __global__ void __launch_bounds__(TXS * 64)
 k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int nframes, int maxSlots, const uint8_t* __restrict__ psduAll,
-           float2* __restrict__ out, float gain, uint4 scrSeq, uint32_t eof)
+           float2* __restrict__ out0, float2* __restrict__ out1, float gain, uint4 scrSeq, uint32_t eof)
 {
+    const int iss = blockIdx.y;                                             // spatial stream = antenna
     __shared__ float2 X[TXS][64];
     __shared__ float2 tw[64];
     const int g = threadIdx.x >> 6, k = threadIdx.x & 63;
     if (threadIdx.x < 64) tw[k] = make_float2(L->twr[k], -L->twi[k]);      // exp(+2 pi j k / 64)
     const int64_t sid = (int64_t)blockIdx.x * TXS + g;                     // global slot id
     const int f = (int)(sid / maxSlots), s = (int)(sid % maxSlots);
-    const bool live = f < nframes && s < plan[f < nframes ? f : 0].nslots;
+    const bool live = f < nframes && s < plan[f < nframes ? f : 0].nslots && iss < plan[f < nframes ? f : 0].nss;
     float2 v = make_float2(0.f, 0.f);
     float scale = 0.f;
-    int shift = 48;
+    int shift = 48, csd = 0;
     TxPlan P;
     if (live) {
         P = plan[f];
         const uint32_t scr[4] = { scrSeq.x, scrSeq.y, scrSeq.z, scrSeq.w };
         const uint8_t* __restrict__ psdu = psduAll + P.psdu_off;
         const int sc = k < 32 ? k : k - 64;                                 // subcarrier of FFT bin k
-        const int nPre = P.format == C8B_F_L ? 5 : P.format == C8B_F_HT ? 9 : 10;
+        const int nPre = P.npre, nLtf = P.nss;
         const bool pilotBin = (k == 7 || k == 21 || k == 43 || k == 57);
         const float pbase[4] = { 1.f, 1.f, 1.f, -1.f };                     // C_PILOT_L / C_PILOT_HT 1SS / C_PILOT_VHT, subcarriers -21 -7 7 21
+        const float pht2[2][4] = { { 1.f, 1.f, -1.f, -1.f }, { 1.f, -1.f, -1.f, 1.f } };   // C_PILOT_HT, two streams
+        // cyclic shift of this stream (tools/phy80211header.py:713-725,950-956): 200 ns on the legacy part, 400 ns after it
+        if (P.nss == 2 && iss == 1) csd = s < 7 ? 4 : 8;
         const int pslot = k == 43 ? 0 : k == 57 ? 1 : k == 7 ? 2 : 3;
         auto stf = [&]() {                                                  // C_STF_L_26 (+ zeros at +-27, +-28 for HT / VHT)
             float r = 0.f;
@@ -210,8 +233,13 @@ k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int n
                 v = q ? make_float2(0.f, a) : make_float2(a, 0.f);
             }
         } else if (s == 7 && P.format != C8B_F_L) { v = stf(); scale = rsqrtf(12.f); }   // HT-STF / VHT-STF
-        else if (s == 8 && P.format != C8B_F_L) { v = make_float2(L->ltfNL[k], 0.f); scale = rsqrtf(56.f); }   // HT-LTF / VHT-LTF (P = R = 1 for one stream)
-        else if (s == 9 && P.format == C8B_F_VHT) {                         // VHT-SIG-B: 26 bits, BPSK on 52 tones, pilots without polarity
+        else if (s >= 8 && s < 8 + nLtf && P.format != C8B_F_L) {            // HT-LTF / VHT-LTF l: stream sign P[iss][l], VHT pilot tones R[l]
+            const int l = s - 8;
+            float sg = (l == 1 && iss == 0) ? -1.f : 1.f;                   // C_P_LTF_VHT_4 rows 0 / 1, columns 0 / 1
+            if (P.format == C8B_F_VHT && pilotBin) sg = l == 1 ? -1.f : 1.f; // C_R_LTF_VHT_4
+            v = make_float2(L->ltfNL[k] * sg, 0.f);
+            scale = rsqrtf(56.f);
+        } else if (s == 8 + nLtf && P.format == C8B_F_VHT) {               // VHT-SIG-B: 26 bits, BPSK on 52 tones, pilots without polarity
             scale = rsqrtf(56.f);
             const int d = L->binToDataNL[k];
             if (pilotBin) v = make_float2(pbase[pslot], 0.f);
@@ -229,15 +257,18 @@ k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int n
             if (pilotBin) {
                 const int idx0 = leg ? 1 : P.format == C8B_F_HT ? 3 : 4;    // tools/phy80211.py:786-801
                 const float pol = L->pilotP[(idx0 + q) % 127];
-                v = make_float2(pol * (leg ? pbase[pslot] : pbase[(pslot + q) & 3]), 0.f);
+                const float* pb4 = (P.format == C8B_F_HT && P.nss == 2) ? pht2[iss] : pbase;
+                v = make_float2(pol * (leg ? pbase[pslot] : pb4[(pslot + q) & 3]), 0.f);
             } else if (d != 255) {
                 const int nb = P.nbpsc;
                 const int mi = nb == 1 ? 0 : nb == 2 ? 1 : nb == 4 ? 2 : nb == 6 ? 3 : 4;
                 int bits = 0;
                 auto src = [&](int x) { return data_bit(P, psdu, scr, eof, x); };
+                const int sp = nb / 2 > 1 ? nb / 2 : 1;                     // stream parser block (tools/phy80211.py:712-733)
                 for (int b = 0; b < nb; b++) {
                     const int j = d * nb + b;
-                    const int c = leg ? L->deintL[mi][j] : L->deintNL[0][mi][j];
+                    int c = leg ? L->deintL[mi][j] : L->deintNL[iss][mi][j];    // position in this stream's symbol before interleaving
+                    if (P.nss == 2) c = iss * sp + 2 * sp * (c / sp) + c % sp;  // ... and in the encoder's output
                     const int m = mother_index(P.cr, q * P.ncbps + c);
                     bits |= bcc_out(src, m >> 1, m & 1) << b;
                 }
@@ -273,11 +304,11 @@ k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int n
     __syncthreads();
     X[g][k] = make_float2(ar, ai);
     __syncthreads();
-    const float gsc = gain * scale * (1.0f / 64.0f);
+    const float gsc = gain * scale * (1.0f / 64.0f) * (P.nss == 2 ? 0.70710678118654752f : 1.0f);       // procToneScaling: / sqrt(N_tone nSS)
     const bool halfFirst = s == 2 || s >= 4, halfLast = (s == 1 || s >= 3) && s + 1 < P.nslots;    // procConcat2Symbol
-    float2* __restrict__ o = out + P.out_off + (int64_t)s * 80;
+    float2* __restrict__ o = (iss ? out1 : out0) + P.out_off + (int64_t)s * 80;
     for (int n = k; n < 80; n += 64) {
-        const float2 x = X[g][(n + shift) & 63];
+        const float2 x = X[g][(n + shift + csd) & 63];
         float a = gsc;
         if ((n == 0 && halfFirst) || (n == 79 && halfLast)) a *= 0.5f;
         float re = x.x * a, im = x.y * a;
@@ -356,13 +387,15 @@ int c8b_tx_geometry_host(int format, int mcs, int len, int* nsym, int* nslots) {
 
 size_t c8b_tx_plan_bytes(int nframes) { return (size_t)nframes * sizeof(TxPlan); }
 
+int c8b_tx_nss_host(int format, int mcs) { return tx_nss(format, mcs); }
+
 void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
-                   float2* d_out, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st)
+                   float2* d_out, float2* d_out1, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st)
 {
     if (nframes <= 0 || maxSlots <= 0) return;
     TxPlan* plan = reinterpret_cast<TxPlan*>(d_plan);
     k_tx_plan<<<(nframes + 127) / 128, 128, 0, st>>>(d_frames, nframes, plan);
     const int64_t slots = (int64_t)nframes * maxSlots;
-    k_tx_slots<<<(unsigned)((slots + TXS - 1) / TXS), TXS * 64, 0, st>>>(lut, plan, nframes, maxSlots, d_psdu, d_out, gain,
-                                                                      make_uint4(scr[0], scr[1], scr[2], scr[3]), eof);
+    const dim3 grid((unsigned)((slots + TXS - 1) / TXS), d_out1 ? 2 : 1);                   // y = spatial stream
+    k_tx_slots<<<grid, TXS * 64, 0, st>>>(lut, plan, nframes, maxSlots, d_psdu, d_out, d_out1, gain, make_uint4(scr[0], scr[1], scr[2], scr[3]), eof);
 }

@@ -197,6 +197,20 @@ class Receiver:
         self._ck(self.L.c8b_tx_batch(self.h, ptr(arena), arena.size, ptr(d), d.size, multiplier, seed, ptr(iq.view(np.float32)), iq.size), "c8b_tx_batch")
         return iq, offs
 
+    def tx_batch2(self, psdus, fmt, mcs, gap=400, cfo=None, multiplier=12.0 * 2 ** 0.5, seed=93):
+        """two antennas: HT mcs 8-15 / VHT mcs 16 + MCS are two-stream frames (stream k on antenna k); returns (iq0, iq1, item offsets)"""
+        d, arena, offs = self.tx_layout(psdus, fmt, mcs, gap, cfo)
+        iq0 = np.zeros(int(offs[-1]), np.complex64)
+        iq1 = np.zeros(int(offs[-1]), np.complex64)
+        self._ck(self.L.c8b_tx_batch2(self.h, ptr(arena), arena.size, ptr(d), d.size, multiplier, seed, ptr(iq0.view(np.float32)),
+                                      ptr(iq1.view(np.float32)), iq0.size), "c8b_tx_batch2")
+        return iq0, iq1, offs
+
+    def tx_batch2_dev(self, d_psdu_ptr, psdu_bytes, desc, d_iq0_ptr, d_iq1_ptr, iq_samples, multiplier=12.0 * 2 ** 0.5, seed=93):
+        _producer_sync()
+        self._ck(self.L.c8b_tx_batch2_dev(self.h, C.c_void_p(d_psdu_ptr), psdu_bytes, ptr(desc), desc.size, multiplier, seed,
+                                          C.c_void_p(d_iq0_ptr), C.c_void_p(d_iq1_ptr), iq_samples), "c8b_tx_batch2_dev")
+
     def tx_from_udp(self, datagrams, gap=400, multiplier=12.0, seed=93):
         """MAC -> PHY datagrams [format][mcs][nss][len16 LE][PSDU] (lib/pktgen_impl.cc:57-70, tools/phy80211.py genPktGrData) ->
         (iq, descriptors): one frame per accepted datagram, `gap` zeros around each; a skipped datagram has psdu_len -1"""

@@ -263,7 +263,7 @@ int  c8b_timing_read(c8b_ctx* ctx, double ms[C8B_K_COUNT], int64_t launches[C8B_
  * generator's (float32 rounding apart); they are what the receive entry points above are tested with. */
 typedef struct c8b_txframe {
     int32_t format;        /* C8B_F_L / C8B_F_HT / C8B_F_VHT                                         */
-    int32_t mcs;
+    int32_t mcs;           /* L 0-7; HT 0-15 (8-15: two streams); VHT 0-8, + 16 for two space-time streams */
     int64_t psdu_off;      /* byte offset of the MPDU (L, HT) or A-MPDU (VHT) in the PSDU arena       */
     int32_t psdu_len;      /* bytes, <= 4095                                                          */
     float   cfo_hz;        /* carrier offset applied to the frame (genFinalSig cfoHz)                 */
@@ -278,6 +278,16 @@ int  c8b_tx_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const
 /* device buffers: only the frames' own samples are written (gaps keep what they hold); asynchronous on the ctx stream */
 int  c8b_tx_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
                       int scrambler_seed, float* d_iq, int64_t iq_samples);
+/* Two spatial streams on two antennas (lib/encode2_impl.cc, lib/modulation2_impl.cc; generator tools/phy80211.py with nSTS = 2,
+ * the recipe of tools/pktGenExample.py:206-217): descriptors with HT mcs 8-15, or VHT mcs 16 + MCS (0-8) for two space-time
+ * streams, become stream k on antenna k (direct mapping, cyclic shifts 200 / 400 ns on the second, P-matrix LTFs, power split
+ * 1 / sqrt 2; the reference recipes use multiplier 12 sqrt 2); one-stream descriptors in the same batch go to antenna 0 only.
+ * Both arenas have iq_samples samples and share the descriptors' out_off.  The one-antenna calls above reject two-stream
+ * descriptors. */
+int  c8b_tx_batch2(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                   int scrambler_seed, float* h_iq0, float* h_iq1, int64_t iq_samples);
+int  c8b_tx_batch2_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
+                       int scrambler_seed, float* d_iq0, float* d_iq1, int64_t iq_samples);
 
 /* synthetic traffic for closed-loop runs: fills every frame's PSDU region (device memory) with a random MPDU carrying a valid
  * FCS (tools/mac80211.py:36-47); VHT regions (psdu_len a multiple of 4) get the one-MPDU A-MPDU delimiter of
@@ -288,12 +298,13 @@ int  c8b_tx_random_psdu_dev(c8b_ctx* ctx, uint8_t* d_psdu, int64_t psdu_bytes, c
  * pktPop; written by tools/phy80211.py:1126-1137 genPktGrData): one datagram per frame,
  *     [format:1][mcs:1][nss:1][len:2 little endian][len PSDU bytes]      (format 0 L, 1 HT, 2 VHT; VHT PSDU = A-MPDU)
  * c8b_tx_udp_parse (host only, no GPU): checks one datagram the way pktPop does (>= 5 bytes, len <= 4095, the datagram holds
- * len bytes after the header) and fills format / mcs / psdu_len of *f; *psdu points at the PSDU inside pkt.  Returns the
- * number of spatial streams (1 here) or C8B_ERR_ARG for a malformed datagram, the MU format (3, two users per datagram) and
- * nss != 1 (the synthesiser is one spatial stream).
+ * len bytes after the header) and fills format / mcs / psdu_len of *f (mcs in the descriptor's coding: VHT + 16 for two
+ * streams); *psdu points at the PSDU inside pkt.  Returns the number of spatial streams (1 or 2) or C8B_ERR_ARG for a
+ * malformed datagram, the MU format (3, two users per datagram) and stream counts the synthesiser does not make.
  * c8b_tx_from_udp: npkts datagrams (datagram k = pkts[pkt_off[k] .. pkt_off[k] + pkt_len[k])) -> one IQ arena: every
- * accepted datagram becomes a frame, `gap` zero samples in front of each and after the last (tools/pktGenExample.py
- * gapLen); malformed ones are skipped like the reference does.  frames_out (npkts records, may be NULL) gets the
+ * accepted one-stream datagram becomes a frame, `gap` zero samples in front of each and after the last
+ * (tools/pktGenExample.py gapLen); malformed ones are skipped like the reference does, two-stream ones too (they need the two
+ * arenas of c8b_tx_batch2: parse them with c8b_tx_udp_parse).  frames_out (npkts records, may be NULL) gets the
  * descriptors used (out_off = where each frame starts; psdu_len = -1 for a skipped datagram); *iq_used = samples written.
  * Returns the number of frames synthesised or a negative error (C8B_ERR_FULL: iq_cap too small). */
 int  c8b_tx_udp_parse(const uint8_t* pkt, int pkt_len, c8b_txframe* f, const uint8_t** psdu);

@@ -124,5 +124,10 @@ def test_tx_udp_parse_follows_pktgen():
     assert parse(struct.pack("<BBBH", 0, 0, 1, 50) + bytes(49))[0] < 0       # shorter than its len field (pktPop :108-111)
     assert parse(struct.pack("<BBBH", 0, 0, 1, 4096) + bytes(4096))[0] < 0   # len > 4095
     assert parse(struct.pack("<BBBH", 3, 0, 1, 10) + bytes(10))[0] < 0       # C8P_F_VHT_MU: two users per datagram
-    assert parse(struct.pack("<BBBH", 1, 8, 2, 10) + bytes(10))[0] < 0       # two spatial streams: not this synthesiser
+    rc, _ = parse(struct.pack("<BBBH", 1, 11, 2, 10) + bytes(10))            # HT MCS11, two streams (c8b_tx_batch2)
+    assert rc == 2 and f[0]["mcs"] == 11
+    rc, _ = parse(struct.pack("<BBBH", 2, 5, 2, 12) + bytes(12))             # VHT MCS5 x 2 streams: descriptor mcs 16 + 5
+    assert rc == 2 and f[0]["mcs"] == 21
+    assert parse(struct.pack("<BBBH", 1, 3, 2, 10) + bytes(10))[0] < 0       # HT MCS3 is one stream
+    assert parse(struct.pack("<BBBH", 2, 5, 3, 12) + bytes(12))[0] < 0       # three streams
     assert parse(struct.pack("<BBBH", 0, 9, 1, 10) + bytes(10))[0] < 0       # no legacy MCS 9

@@ -217,3 +217,60 @@ def test_udp_in_udp_out_loop():
     assert len(recs) == len(sent)
     for r, (fmt, mcs, m) in zip(recs, sent):
         assert r == bytes([fmt]) + struct.pack("<H", len(m)) + m + bytes([mcs])
+
+
+def test_two_stream_waveforms_equal_the_generator(golden):
+    """c8b_tx_batch2 against tools/phy80211.py with nSTS = 2 (the recipe of tools/pktGenExample.py:206-217; golden
+    frames_mimo.npz: HT MCS8-15, VHT 2SS MCS0-8, one CFO case): both antennas sample for sample"""
+    pkg = load_pkg()
+    g, t = golden["frames_mimo"], _tx_golden()
+    ps = _psdus(t)
+    mpdu, ampdu = ps[0], ps[17]                                  # the MPDU / A-MPDU every frame of frames_mimo carries
+    fmt = g["meta"][:, 0].astype(np.int32)
+    mcs = g["meta"][:, 1].astype(np.int32)
+    cfo = g["meta"][:, 2].astype(np.float32)
+    code = np.where(fmt == 2, mcs + 16, mcs)
+    rx = pkg.Receiver(device=0)
+    iq0, iq1, offs = rx.tx_batch2([ampdu if f == 2 else mpdu for f in fmt], fmt, code, gap=400, cfo=cfo)
+    rx.close()
+    assert np.array_equal(offs, g["offs"])
+    peak = float(np.max(np.abs(g["iq0"])))
+    for i in range(len(fmt)):
+        for a, (got, ref) in enumerate(((iq0, g["iq0"]), (iq1, g["iq1"]))):
+            err = float(np.max(np.abs(got[offs[i]:offs[i + 1]] - ref[offs[i]:offs[i + 1]])))
+            assert err <= (2e-6 if cfo[i] == 0 else 2e-5) * peak, (i, a, fmt[i], mcs[i], err / peak)
+
+
+@pytest.mark.parametrize("fmt,codes", [(1, range(8, 16)), (2, range(16, 25))])
+def test_two_stream_loopback_random_traffic(fmt, codes):
+    """unique two-stream frames (random lengths) through c8b_tx_batch2 -> c8b_rx_batch2: every MPDU comes back; the oracle's
+    2x2 chain agrees"""
+    pkg = load_pkg()
+    rng = np.random.default_rng(300 + fmt)
+    rx = pkg.Receiver(device=0)
+    ps, ms, want = [], [], []
+    for c in codes:
+        for ln in (int(rng.integers(40, 300)), 4 * int(rng.integers(150, 380))):
+            body = bytes(rng.integers(0, 256, ln - 4, dtype=np.uint8))
+            m = body + (__import__("zlib").crc32(body) & 0xffffffff).to_bytes(4, "little")
+            if fmt == 2:
+                n = len(m)
+                d0 = ((n & 0xf) << 4) | (((n >> 12) & 3) << 2) | 1
+                ps.append(bytes([d0, (n >> 4) & 0xff, 0, 0x4E]) + m + bytes((-n) % 4))
+            else:
+                ps.append(m)
+            ms.append(c)
+            want.append(m)
+    a, b, offs = rx.tx_batch2(ps, fmt, ms, gap=300)
+    s = 0.1875 * np.sqrt(2) / np.sqrt(2 * 10 ** 3.2)
+    a = (a + s * (rng.standard_normal(a.size) + 1j * rng.standard_normal(a.size))).astype(np.complex64)
+    b = (b + s * (rng.standard_normal(b.size) + 1j * rng.standard_normal(b.size))).astype(np.complex64)
+    off, ln = offs[:-1], np.diff(offs).astype(np.int32)
+    fr, pdu = rx.rx_batch2(a, b, off, ln)
+    rx.close()
+    for i, m in enumerate(want):
+        assert fr[i]["status"] == 0 and fr[i]["nss"] == 2 and fr[i]["npdu"] == 1, (i, ms[i], fr[i]["status"], fr[i]["npdu"])
+        assert bytes(pdu[i, 3:3 + len(m)]) == m, (i, ms[i])
+        if i % 5 == 0:
+            _, _, po = ol.rx_item2(a[offs[i]:offs[i + 1]], b[offs[i]:offs[i + 1]], max_frames=1)
+            assert bytes(po) == bytes(pdu[i, :po.size])

@@ -25,6 +25,7 @@ rx = pkg.Receiver(device=0)
 preac, preconj = rx.presiso(x)
 rx.close()
 exe = os.path.join(ROOT, "tests", "gr_mock", "build", "run_chain")
+results = {}
 with tempfile.TemporaryDirectory() as d:
     preac.tofile(os.path.join(d, "preac.f32"))
     preconj.astype(np.complex64).tofile(os.path.join(d, "preconj.c64"))
@@ -45,3 +46,5 @@ with tempfile.TemporaryDirectory() as d:
               ("thread per block" if tpb == "1" else "one thread", max_call, x.size, nmsg, ms, x.size / ms / 1e3, x.size / ms / 1e3 / 20.0))
         for ln in lines[1:]:
             print(ln)
+        results["thread_per_block" if tpb == "1" else "one_thread"] = {"samples_per_s": x.size / ms * 1e3, "messages": nmsg, "samples": int(x.size)}
+print("RESULT " + __import__("json").dumps(results))

@@ -28,6 +28,7 @@ try:                                                                # a radio dr
 except Exception:
     pass
 rx = pkg.Receiver(device=0, max_frames=512, chunk_items=1)
+results = {}
 for push in [int(a) for a in sys.argv[1:]] or [16384, 65536, 262144, 1048576]:
     for rep in range(2):                                            # first pass warms the scratch allocations
         rx.stream_begin(1, 1 << 22)
@@ -43,5 +44,7 @@ for push in [int(a) for a in sys.argv[1:]] or [16384, 65536, 262144, 1048576]:
         stages = rx.timing_read(reset=True)
     print("push %8d samples: %7.1f M samples/s (%.1fx real time), %d frames, %d PDUs of %d sent, %.2f ms per push" %
           (push, x.size / dt / 1e6, x.size / dt / 20e6, nf, npdu, 25 * reps, 1e3 * dt / ((x.size + push - 1) // push)))
+    results[str(push)] = {"samples_per_s": x.size / dt, "frames": nf, "pdus": npdu, "sent": 25 * reps}
     print("          device ms per stage (passes):", {k: (round(v[0], 2), v[1]) for k, v in stages.items()}, "wall %.1f ms" % (1e3 * dt))
 rx.close()
+print("RESULT " + __import__("json").dumps(results))
