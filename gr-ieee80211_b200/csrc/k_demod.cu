@@ -16,6 +16,10 @@
 
 namespace {
 
+#ifndef C8B_DEMOD_V
+#define C8B_DEMOD_V 2
+#endif
+
 constexpr int DW = 4;               // warps per CTA
 constexpr int SPW = 4;              // symbols per warp
 constexpr int SPB = DW * SPW;       // symbols per CTA
@@ -62,6 +66,7 @@ __device__ __forceinline__ void cfo_rot(float ph, float* sn, float* cs)
     *cs = __cosf(r);
 }
 
+#if C8B_DEMOD_V == 1
 __global__ void __launch_bounds__(DW * 32, 8)
 k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int maxf,
         const c8b_frame* __restrict__ frames, const float2* __restrict__ hinvAll, float* __restrict__ llrArena)
@@ -219,6 +224,201 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
         }
     }
 }
+
+#else
+// soft bits of one data tone through the deinterleaver in closed form (lut.h demapTab): NB bits per tone, s = max(NB/2, 1) per
+// axis, axis h starts NCOL*s floats after axis 0, bit c of an axis sits at NCOL*((c + R) mod s).  NCOL is 16 (legacy) or 13.
+template <int NCOL, int NB>
+__device__ __forceinline__ void demap_tone(float* __restrict__ Lb, int R, cpx q)
+{
+    if (NB == 1) {
+        Lb[0] = q.x;
+    } else if (NB == 2) {
+        Lb[0] = q.x * 1.4142135623730951f; Lb[NCOL] = q.y * 1.4142135623730951f;
+    } else if (NB == 4) {                                                  // s = 2: R in {0, 1}
+        q = { q.x * 3.1622776601683795f, q.y * 3.1622776601683795f };
+        float* __restrict__ A0 = Lb + R * NCOL;
+        float* __restrict__ A1 = Lb + (R ^ 1) * NCOL;
+        A0[0] = q.x; A1[0] = 2.0f - fabsf(q.x);
+        A0[2 * NCOL] = q.y; A1[2 * NCOL] = 2.0f - fabsf(q.y);
+    } else if (NB == 6) {                                                  // s = 3: R in {0, 1, 2}
+        q = { q.x * 6.48074069840786f, q.y * 6.48074069840786f };
+        const float a = 4.0f - fabsf(q.x), b = 4.0f - fabsf(q.y);
+        const int t1 = R == 2 ? 0 : R + 1, t2 = R == 0 ? 2 : R - 1;
+        float* __restrict__ A0 = Lb + R * NCOL;
+        float* __restrict__ A1 = Lb + t1 * NCOL;
+        float* __restrict__ A2 = Lb + t2 * NCOL;
+        A0[0] = q.x; A1[0] = a; A2[0] = 2.0f - fabsf(a);
+        A0[3 * NCOL] = q.y; A1[3 * NCOL] = b; A2[3 * NCOL] = 2.0f - fabsf(b);
+    } else {                                                               // s = 4: R in {0 .. 3}
+        q = { q.x * 13.038404810405298f, q.y * 13.038404810405298f };
+        const float a = 8.0f - fabsf(q.x), b = 8.0f - fabsf(q.y);
+        const float a2 = 4.0f - fabsf(a), b2 = 4.0f - fabsf(b);
+        float* __restrict__ A0 = Lb + R * NCOL;
+        float* __restrict__ A1 = Lb + ((R + 1) & 3) * NCOL;
+        float* __restrict__ A2 = Lb + ((R + 2) & 3) * NCOL;
+        float* __restrict__ A3 = Lb + ((R + 3) & 3) * NCOL;
+        A0[0] = q.x; A1[0] = a; A2[0] = a2; A3[0] = 2.0f - fabsf(a2);
+        A0[4 * NCOL] = q.y; A1[4 * NCOL] = b; A2[4 * NCOL] = b2; A3[4 * NCOL] = 2.0f - fabsf(b2);
+    }
+}
+
+template <int NCOL, int NB>
+__device__ __forceinline__ void demap_symbol(float* __restrict__ L, const uint4 te, const cpx* v, cpx ps)
+{
+    const unsigned w[4] = { te.x, te.y, te.z, te.w };
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        const unsigned e = (k2 & 1) ? (w[k2 >> 1] >> 16) : (w[k2 >> 1] & 0xFFFFu);
+        if (e == 0xFFFFu) continue;                                        // null / pilot bin
+        demap_tone<NCOL, NB>(L + (e & 511u), (int)(e >> 9), cmul(v[k2], ps));
+    }
+}
+
+__global__ void __launch_bounds__(DW * 32, 8)
+k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int maxf,
+        const c8b_frame* __restrict__ frames, const float2* __restrict__ hinvAll, float* __restrict__ llrArena)
+{
+    __shared__ WarpBuf wb[DW];
+    const int item = blockIdx.y;
+    const c8b_frame* __restrict__ fr = frames + item;
+    // every word whose address follows from the block index is requested up front: one round trip instead of a chain of them
+    const int status = fr->status, nss = fr->nss, nsym = fr->nsym, fmt = fr->format, ncbps = fr->ncbps;
+    const int nsymsamp = fr->nsymsamp, data_off = fr->data_off, sync_idx = fr->sync_idx;
+    const float rad = fr->rad;
+    const int64_t llr_off = fr->llr_off;
+    const int64_t ioff = off[maxf == 1 ? item : item / maxf];
+    if (status != C8B_ST_OK || nss != 1) return;          // 2-stream frames: k_demod2
+    const int sym0 = blockIdx.x * SPB;
+    if (sym0 >= nsym) return;
+    const bool legacy = fmt == C8B_F_L;
+    const int nbpsc = legacy ? ncbps / 48 : ncbps / 52;
+    const int mi = nbpsc == 1 ? 0 : nbpsc == 2 ? 1 : nbpsc == 4 ? 2 : nbpsc == 6 ? 3 : 4;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, j = lane & 7;                 // symbol within warp, thread within symbol
+    WarpBuf& W = wb[warp];
+    const int sidx = sym0 + warp * SPW + g;
+    const bool live = sidx < nsym;
+    const int k0 = data_off + sidx * nsymsamp + C8B_SYM_SHIFT;           // index in the signal block's output stream
+    const float2* __restrict__ x = iq + ioff + sync_idx + 224 + k0;      // blockIdx.y = frame slot
+
+    cpx v[8];
+    if (live) {
+        float2 s[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) s[m] = __ldg(x + j + 8 * m);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            float sn, cs;
+            cfo_rot(__fmul_rn((float)(k0 + j + 8 * m + 224), rad), &sn, &cs);     // lib/signal_impl.cc:172-173
+            v[m] = { s[m].x * cs - s[m].y * sn, s[m].x * sn + s[m].y * cs };
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = { 0.f, 0.f };
+    }
+    dft8(v);
+    {
+        const float4* __restrict__ tw = reinterpret_cast<const float4*>(lut->tw8[8 * j]);     // W64^(j*k1), k1 = 0..7
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const float4 t = __ldg(tw + p);
+            if (p) v[2 * p] = cmul(v[2 * p], cpx{ t.x, t.y });
+            v[2 * p + 1] = cmul(v[2 * p + 1], cpx{ t.z, t.w });
+        }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 8; k1++) W.xch[g * XS + k1 * 9 + j] = make_float2(v[k1].x, v[k1].y);
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 8; n1++) { const float2 t = W.xch[g * XS + j * 9 + n1]; v[n1] = { t.x, t.y }; }
+    dft8(v);                                               // v[k2] = bin j + 8*k2
+
+    // equalise: s = F * (1/H)
+    const float2* __restrict__ hinv = hinvAll + (size_t)item * 64;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        const float2 h = __ldg(hinv + j + 8 * k2);
+        v[k2] = cmul(v[k2], cpx{ h.x, h.y });
+    }
+    // pilots: bin 7 = (j 7, k2 0), 21 = (5, 2), 43 = (3, 5), 57 = (1, 7)
+    if (j == 7) W.pil[g * 4 + 0] = make_float2(v[0].x, v[0].y);
+    if (j == 5) W.pil[g * 4 + 1] = make_float2(v[2].x, v[2].y);
+    if (j == 3) W.pil[g * 4 + 2] = make_float2(v[5].x, v[5].y);
+    if (j == 1) W.pil[g * 4 + 3] = make_float2(v[7].x, v[7].y);
+    __syncwarp();
+    cpx ps;
+    {
+        // pilot values: base {1,1,1,-1}; HT/VHT rotate left once per symbol (pilotShift, demod_impl.cc:549-557);
+        // polarity index starts at 1 (L), 3 (HT), 4 (VHT) (demod_impl.cc:214,191,164)
+        const int p0 = legacy ? 1 : (fmt == C8B_F_HT ? 3 : 4);
+        const float P = __ldg(&lut->pilotP[(p0 + sidx) % 127]);
+        const int sh = legacy ? 0 : (sidx & 3);
+        // pilot[m] of this symbol = base[(m + sh) & 3], base[3] = -1
+        const float q2 = (((2 + sh) & 3) == 3 ? -P : P), q3 = (((3 + sh) & 3) == 3 ? -P : P);
+        const float q0 = (((0 + sh) & 3) == 3 ? -P : P), q1 = (((1 + sh) & 3) == 3 ? -P : P);
+        const float2 s7 = W.pil[g * 4 + 0], s21 = W.pil[g * 4 + 1], s43 = W.pil[g * 4 + 2], s57 = W.pil[g * 4 + 3];
+        float re = __fadd_rn(__fadd_rn(__fadd_rn(s7.x * q2, s21.x * q3), s43.x * q0), s57.x * q1);
+        float im = __fadd_rn(__fadd_rn(__fadd_rn(s7.y * q2, s21.y * q3), s43.y * q0), s57.y * q1);
+        const float inv = 1.0f / sqrtf(re * re + im * im);
+        ps = { re * inv, -im * inv };                      // conj(sum) / |sum|
+    }
+    // soft bits of this thread's data tones, scattered through the deinterleaver (closed form: demapTab) into the symbol's
+    // shared-memory row: ncbps floats + LPAD.  With rows at multiples of 48 * nbpsc the four symbols of a warp scatter
+    // through the legacy deinterleaver into the same banks (11.5 wavefronts per store, 5.75 for BPSK; HT/VHT BPSK 2.1); four
+    // floats of padding bring that to 2.9 / 1.9 / 1.4 (bank model over the lane -> address map; the other HT/VHT maps are at
+    // 1.1-1.75 unpadded, and the 256-QAM row has no room to spare).  Multiples of 4 keep the rows float4-aligned.
+    const int lpad = (legacy || nbpsc == 1) ? 4 : 0;
+    const int lrow = ncbps + lpad;
+    float* __restrict__ L = W.llr + g * lrow;
+    if (live) {
+        const uint4 te = __ldg(reinterpret_cast<const uint4*>(lut->demapTab[(legacy ? 0 : 4) + mi] + 8 * j));
+        if (legacy) {
+            if (nbpsc == 1) demap_symbol<16, 1>(L, te, v, ps);
+            else if (nbpsc == 2) demap_symbol<16, 2>(L, te, v, ps);
+            else if (nbpsc == 4) demap_symbol<16, 4>(L, te, v, ps);
+            else demap_symbol<16, 6>(L, te, v, ps);
+        } else {
+            if (nbpsc == 1) demap_symbol<13, 1>(L, te, v, ps);
+            else if (nbpsc == 2) demap_symbol<13, 2>(L, te, v, ps);
+            else if (nbpsc == 4) demap_symbol<13, 4>(L, te, v, ps);
+            else if (nbpsc == 6) demap_symbol<13, 6>(L, te, v, ps);
+            else demap_symbol<13, 8>(L, te, v, ps);
+        }
+    }
+    __syncwarp();
+    // coalesced copy-out of the warp's live symbols
+    const int wsym0 = sym0 + warp * SPW;
+    int nlive = nsym - wsym0;
+    nlive = nlive < 0 ? 0 : (nlive > SPW ? SPW : nlive);
+    const int nfl = nlive * ncbps;                          // multiple of 4 (48 | 52 divide by 4)
+    float* __restrict__ out = llrArena + llr_off + (int64_t)wsym0 * ncbps;
+    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (lpad == 0) {
+        if (al16) {
+            const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
+            float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+            for (int i = lane; i < nfl / 4; i += 32) o4[i] = s4[i];
+        } else {
+            for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
+        }
+    } else {                                               // padded rows: symbol by symbol (ncbps * 4 bytes is a multiple of 16)
+        for (int r = 0; r < nlive; r++) {
+            const float* __restrict__ src = W.llr + r * lrow;
+            float* __restrict__ dst = out + r * ncbps;
+            if (al16) {
+                const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
+                float4* __restrict__ o4 = reinterpret_cast<float4*>(dst);
+                for (int i = lane; i < ncbps / 4; i += 32) o4[i] = s4[i];
+            } else {
+                for (int i = lane; i < ncbps; i += 32) dst[i] = src[i];
+            }
+        }
+    }
+}
+
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // k_demod2: per-symbol loop of the 2x2 block (lib/demod2_impl.cc:279-330; htChanUpdate :471-551,

@@ -100,4 +100,26 @@ void c8b_lut_build(c8b_lut* L)
     }
     L->pair01[0] = 0.0f;
     L->pair01[1] = 1.0f;
+    // per-thread demap entries: read the closed form (base + rotation) off the maps built above
+    for (int mode = 0; mode < 9; mode++) {
+        const bool leg = mode < 4;
+        const int nb = leg ? nbL[mode] : nbN[mode - 4], s = nb / 2 > 1 ? nb / 2 : 1, ncol = leg ? 16 : 13;
+        const uint16_t* map = leg ? L->deintL[mode] : L->deintNL[0][mode - 4];
+        for (int j = 0; j < 8; j++)
+            for (int k2 = 0; k2 < 8; k2++) {
+                const int dd = leg ? L->binToDataL[j + 8 * k2] : L->binToDataNL[j + 8 * k2];
+                uint16_t e = 0xFFFF;
+                if (dd != 255) {
+                    int base = map[dd * nb];
+                    for (int c = 1; c < s; c++) if (map[dd * nb + c] < base) base = map[dd * nb + c];
+                    e = (uint16_t)(base | (((map[dd * nb] - base) / ncol) << 9));
+                }
+                L->demapTab[mode][8 * j + k2] = e;
+            }
+    }
+    for (int j = 0; j < 8; j++)
+        for (int k1 = 0; k1 < 8; k1++) {
+            L->tw8[8 * j + k1][0] = L->twr[(j * k1) & 63];
+            L->tw8[8 * j + k1][1] = L->twi[(j * k1) & 63];
+        }
 }

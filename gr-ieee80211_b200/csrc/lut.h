@@ -12,7 +12,7 @@
 #define C8B_DECODE_T_MAX 32782 // lib/decode_impl.h:36
 
 #define C8B_LUT_MAGIC 0x4c423843u /* "C8BL" */
-#define C8B_LUT_VERSION 5u
+#define C8B_LUT_VERSION 6u
 
 struct c8b_lut {
     uint32_t magic, version, bytes, pad0;
@@ -31,6 +31,12 @@ struct c8b_lut {
     uint32_t crc32tab[256];    // reflected 0xEDB88320
     uint32_t crcZ[6][32];      // crcZ[p][i] = CRC register (1<<i) advanced by 64*2^p zero bytes (lane-parallel CRC)
     float pair01[2];           // {0.0f, 1.0f}: read as one 8-byte register pair by k_viterbi_tp (FMUL2 / FFMA2 selectors)
+    // k_demod's per-thread views of the tables above (thread j of a symbol owns FFT bins j + 8*k2):
+    // demapTab[mode][8*j + k2], mode = 0..3 legacy nBPSC 1,2,4,6; 4..8 HT/VHT nBPSCS 1,2,4,6,8.  0xFFFF: null / pilot bin.
+    // Otherwise bits 0-8 = B, bits 9-10 = R: soft bit h*s + c of the bin's data tone (s = max(nBPSC/2, 1), h < nBPSC/s, c < s)
+    // lands at B + N_COL*((c + R) mod s) + h*N_COL*s -- the deinterleaver's two permutations in closed form (N_COL 16 / 13).
+    alignas(16) uint16_t demapTab[9][64];
+    alignas(16) float tw8[64][2];   // tw8[8*j + k1] = W64^(j*k1) as (re, im): the 8x8 DFT's twiddles, one row per thread
 };
 
 void c8b_lut_build(c8b_lut* L);   // host, by formula (lut.cc)

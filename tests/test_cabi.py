@@ -61,7 +61,29 @@ def test_lut_blob_matches_reference_tables(golden):
     crc = take(256, "<u4")
     crcz = take(6 * 32, "<u4").reshape(6, 32)
     pair01 = take(2, "<f4")
+    o = (o + 15) & ~15                                   # alignas(16)
+    demap = take(9 * 64, "<u2").reshape(9, 8, 8)
+    tw8 = take(128, "<f4").reshape(8, 8, 2)
     assert o == blob.size and pair01.tolist() == [0.0, 1.0]
+    # k_demod's per-thread tables restate deintL / deintNL[0] / binToData* / tw*: entry (B, R) of bin j + 8*k2 puts soft bit
+    # h*s + c at B + N_COL*((c + R) mod s) + h*N_COL*s
+    for mode in range(9):
+        leg = mode < 4
+        nb = (1, 2, 4, 6)[mode] if leg else (1, 2, 4, 6, 8)[mode - 4]
+        s_, ncol = max(nb // 2, 1), 16 if leg else 13
+        mp = deintL[mode] if leg else deintNL[0, mode - 4]
+        b2d = binL if leg else binNL
+        for j in range(8):
+            for k2 in range(8):
+                e, d = int(demap[mode, j, k2]), int(b2d[j + 8 * k2])
+                assert (e == 0xFFFF) == (d == 255)
+                if d != 255:
+                    B, R = e & 511, e >> 9
+                    got = [B + ncol * ((c + R) % s_) + h * ncol * s_ for h in range(nb // s_) for c in range(s_)]
+                    assert got == mp[d * nb:(d + 1) * nb].tolist(), (mode, j, k2)
+    for j in range(8):
+        for k1 in range(8):
+            assert tw8[j, k1, 0] == twr[(j * k1) & 63] and tw8[j, k1, 1] == twi[(j * k1) & 63]
     assert np.array_equal(ltfL, g["tab_LTF_L_26_F_FLOAT"]) and np.array_equal(ltfNL, g["tab_LTF_NL_28_F_FLOAT"])
     assert np.array_equal(ltfNL22, g["tab_LTF_NL_28_F_FLOAT_VHT22"])
     assert np.array_equal(pilotP[:127], g["tab_PILOT_P"])
