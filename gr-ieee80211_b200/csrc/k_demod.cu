@@ -10,15 +10,12 @@
 // Mapping: 8 threads per symbol, 4 symbols per warp, 4 warps per CTA (16 consecutive symbols of one
 // frame).  64 = 8 x 8: thread j takes samples j+8m, does an 8-point DFT in registers, multiplies by
 // W64^(j*k1), the 8x8 transpose goes through padded (conflict-free) shared memory, and a second
-// 8-point DFT leaves thread k1 with bins k1+8*k2.  LLRs are scattered through the deinterleave map into
+// 8-point DFT leaves thread k1 with bins k1+8*k2.  LLRs are scattered through the deinterleaver -- in closed form: a
+// per-thread table entry gives each data tone's base position and rotation, no map is staged or looked up -- into
 // a shared-memory line per symbol and leave the SM as 16-byte coalesced stores.
 #include "common.cuh"
 
 namespace {
-
-#ifndef C8B_DEMOD_V
-#define C8B_DEMOD_V 2
-#endif
 
 constexpr int DW = 4;               // warps per CTA
 constexpr int SPW = 4;              // symbols per warp
@@ -66,166 +63,6 @@ __device__ __forceinline__ void cfo_rot(float ph, float* sn, float* cs)
     *cs = __cosf(r);
 }
 
-#if C8B_DEMOD_V == 1
-__global__ void __launch_bounds__(DW * 32, 8)
-k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int maxf,
-        const c8b_frame* __restrict__ frames, const float2* __restrict__ hinvAll, float* __restrict__ llrArena)
-{
-    __shared__ WarpBuf wb[DW];
-    __shared__ uint16_t smap[416];
-    const int item = blockIdx.y;
-    const c8b_frame* __restrict__ fr = frames + item;
-    if (fr->status != C8B_ST_OK || fr->nss != 1) return;          // 2-stream frames: k_demod2
-    const int nsym = fr->nsym;
-    const int sym0 = blockIdx.x * SPB;
-    if (sym0 >= nsym) return;
-    const int fmt = fr->format, ncbps = fr->ncbps, nss = fr->nss;
-    const bool legacy = fmt == C8B_F_L;
-    const int nbpsc = legacy ? ncbps / 48 : ncbps / (52 * (nss > 0 ? nss : 1));
-    const int mi = nbpsc == 1 ? 0 : nbpsc == 2 ? 1 : nbpsc == 4 ? 2 : nbpsc == 6 ? 3 : 4;
-    {   // deinterleave map of this frame
-        const uint16_t* __restrict__ src = legacy ? lut->deintL[mi > 3 ? 3 : mi] : lut->deintNL[0][mi];
-        for (int i = threadIdx.x; i < ncbps && i < 416; i += DW * 32) smap[i] = src[i];
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 3, j = lane & 7;                 // symbol within warp, thread within symbol
-    WarpBuf& W = wb[warp];
-    const int sidx = sym0 + warp * SPW + g;
-    const bool live = sidx < nsym;
-    const int nsymsamp = fr->nsymsamp;
-    const float rad = fr->rad;
-    const int k0 = fr->data_off + sidx * nsymsamp + C8B_SYM_SHIFT;       // index in the signal block's output stream
-    const float2* __restrict__ x = iq + off[item / maxf] + fr->sync_idx + 224 + k0;      // blockIdx.y = frame slot
-
-    cpx v[8];
-    if (live) {
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const int n = j + 8 * m;
-            const float2 s = __ldg(x + n);
-            float sn, cs;
-            cfo_rot(__fmul_rn((float)(k0 + n + 224), rad), &sn, &cs);     // lib/signal_impl.cc:172-173
-            v[m] = { s.x * cs - s.y * sn, s.x * sn + s.y * cs };
-        }
-    } else {
-#pragma unroll
-        for (int m = 0; m < 8; m++) v[m] = { 0.f, 0.f };
-    }
-    dft8(v);
-#pragma unroll
-    for (int k1 = 1; k1 < 8; k1++) {
-        const int t = (j * k1) & 63;
-        v[k1] = cmul(v[k1], cpx{ __ldg(&lut->twr[t]), __ldg(&lut->twi[t]) });
-    }
-#pragma unroll
-    for (int k1 = 0; k1 < 8; k1++) W.xch[g * XS + k1 * 9 + j] = make_float2(v[k1].x, v[k1].y);
-    __syncwarp();
-#pragma unroll
-    for (int n1 = 0; n1 < 8; n1++) { const float2 t = W.xch[g * XS + j * 9 + n1]; v[n1] = { t.x, t.y }; }
-    dft8(v);                                               // v[k2] = bin j + 8*k2
-
-    // equalise: s = F * (1/H)
-    const float2* __restrict__ hinv = hinvAll + (size_t)item * 64;
-#pragma unroll
-    for (int k2 = 0; k2 < 8; k2++) {
-        const float2 h = __ldg(hinv + j + 8 * k2);
-        v[k2] = cmul(v[k2], cpx{ h.x, h.y });
-    }
-    // pilots: bin 7 = (j 7, k2 0), 21 = (5, 2), 43 = (3, 5), 57 = (1, 7)
-    if (j == 7) W.pil[g * 4 + 0] = make_float2(v[0].x, v[0].y);
-    if (j == 5) W.pil[g * 4 + 1] = make_float2(v[2].x, v[2].y);
-    if (j == 3) W.pil[g * 4 + 2] = make_float2(v[5].x, v[5].y);
-    if (j == 1) W.pil[g * 4 + 3] = make_float2(v[7].x, v[7].y);
-    __syncwarp();
-    cpx ps;
-    {
-        // pilot values: base {1,1,1,-1}; HT/VHT rotate left once per symbol (pilotShift, demod_impl.cc:549-557);
-        // polarity index starts at 1 (L), 3 (HT), 4 (VHT) (demod_impl.cc:214,191,164)
-        const int p0 = legacy ? 1 : (fmt == C8B_F_HT ? 3 : 4);
-        const float P = __ldg(&lut->pilotP[(p0 + sidx) % 127]);
-        const int sh = legacy ? 0 : (sidx & 3);
-        // pilot[m] of this symbol = base[(m + sh) & 3], base[3] = -1
-        const float q2 = (((2 + sh) & 3) == 3 ? -P : P), q3 = (((3 + sh) & 3) == 3 ? -P : P);
-        const float q0 = (((0 + sh) & 3) == 3 ? -P : P), q1 = (((1 + sh) & 3) == 3 ? -P : P);
-        const float2 s7 = W.pil[g * 4 + 0], s21 = W.pil[g * 4 + 1], s43 = W.pil[g * 4 + 2], s57 = W.pil[g * 4 + 3];
-        float re = __fadd_rn(__fadd_rn(__fadd_rn(s7.x * q2, s21.x * q3), s43.x * q0), s57.x * q1);
-        float im = __fadd_rn(__fadd_rn(__fadd_rn(s7.y * q2, s21.y * q3), s43.y * q0), s57.y * q1);
-        const float inv = 1.0f / sqrtf(re * re + im * im);
-        ps = { re * inv, -im * inv };                      // conj(sum) / |sum|
-    }
-    // soft bits of this thread's data tones, scattered through the deinterleave map
-    const uint8_t* __restrict__ b2d = legacy ? lut->binToDataL : lut->binToDataNL;
-    // shared-memory row of a symbol: ncbps floats + LPAD.  With rows at multiples of 48 * nbpsc the four symbols of a warp
-    // scatter through the legacy deinterleaver into the same banks (11.5 wavefronts per store, 5.75 for BPSK; HT/VHT BPSK
-    // 2.1); four floats of padding bring that to 2.9 / 1.9 / 1.4 (bank model over the lane -> address map; the other HT/VHT
-    // maps are at 1.1-1.75 unpadded, and the 256-QAM row has no room to spare).  Multiples of 4 keep the rows float4-aligned.
-    const int lpad = (legacy || nbpsc == 1) ? 4 : 0;
-    const int lrow = ncbps + lpad;
-    float* __restrict__ L = W.llr + g * lrow;
-    if (live) {
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) {
-            const int d = b2d[j + 8 * k2];
-            if (d == 255) continue;
-            cpx q = cmul(v[k2], ps);
-            const uint16_t* __restrict__ mp = smap + d * nbpsc;
-            if (nbpsc == 1) {
-                L[mp[0]] = q.x;
-            } else if (nbpsc == 2) {
-                q = { q.x * 1.4142135623730951f, q.y * 1.4142135623730951f };
-                L[mp[0]] = q.x; L[mp[1]] = q.y;
-            } else if (nbpsc == 4) {
-                q = { q.x * 3.1622776601683795f, q.y * 3.1622776601683795f };
-                L[mp[0]] = q.x; L[mp[1]] = 2.0f - fabsf(q.x);
-                L[mp[2]] = q.y; L[mp[3]] = 2.0f - fabsf(q.y);
-            } else if (nbpsc == 6) {
-                q = { q.x * 6.48074069840786f, q.y * 6.48074069840786f };
-                const float a = 4.0f - fabsf(q.x), b = 4.0f - fabsf(q.y);
-                L[mp[0]] = q.x; L[mp[1]] = a; L[mp[2]] = 2.0f - fabsf(a);
-                L[mp[3]] = q.y; L[mp[4]] = b; L[mp[5]] = 2.0f - fabsf(b);
-            } else {
-                q = { q.x * 13.038404810405298f, q.y * 13.038404810405298f };
-                const float a = 8.0f - fabsf(q.x), b = 8.0f - fabsf(q.y);
-                const float a2 = 4.0f - fabsf(a), b2 = 4.0f - fabsf(b);
-                L[mp[0]] = q.x; L[mp[1]] = a; L[mp[2]] = a2; L[mp[3]] = 2.0f - fabsf(a2);
-                L[mp[4]] = q.y; L[mp[5]] = b; L[mp[6]] = b2; L[mp[7]] = 2.0f - fabsf(b2);
-            }
-        }
-    }
-    __syncwarp();
-    // coalesced copy-out of the warp's live symbols
-    const int wsym0 = sym0 + warp * SPW;
-    int nlive = nsym - wsym0;
-    nlive = nlive < 0 ? 0 : (nlive > SPW ? SPW : nlive);
-    const int nfl = nlive * ncbps;                          // multiple of 4 (48 | 52 divide by 4)
-    float* __restrict__ out = llrArena + fr->llr_off + (int64_t)wsym0 * ncbps;
-    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    if (lpad == 0) {
-        if (al16) {
-            const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
-            float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
-            for (int i = lane; i < nfl / 4; i += 32) o4[i] = s4[i];
-        } else {
-            for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
-        }
-    } else {                                               // padded rows: symbol by symbol (ncbps * 4 bytes is a multiple of 16)
-        for (int r = 0; r < nlive; r++) {
-            const float* __restrict__ src = W.llr + r * lrow;
-            float* __restrict__ dst = out + r * ncbps;
-            if (al16) {
-                const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
-                float4* __restrict__ o4 = reinterpret_cast<float4*>(dst);
-                for (int i = lane; i < ncbps / 4; i += 32) o4[i] = s4[i];
-            } else {
-                for (int i = lane; i < ncbps; i += 32) dst[i] = src[i];
-            }
-        }
-    }
-}
-
-#else
 // soft bits of one data tone through the deinterleaver in closed form (lut.h demapTab): NB bits per tone, s = max(NB/2, 1) per
 // axis, axis h starts NCOL*s floats after axis 0, bit c of an axis sits at NCOL*((c + R) mod s).  NCOL is 16 (legacy) or 13.
 template <int NCOL, int NB>
@@ -235,6 +72,26 @@ __device__ __forceinline__ void demap_tone(float* __restrict__ Lb, int R, cpx q)
         Lb[0] = q.x;
     } else if (NB == 2) {
         Lb[0] = q.x * 1.4142135623730951f; Lb[NCOL] = q.y * 1.4142135623730951f;
+    } else if (NB == 4 && NCOL == 13) {
+        // HT/VHT 16 / 64-QAM: the axis' VALUES are rotated by R and stored at the fixed offsets NCOL*m.  With the offsets the
+        // same in every lane the stores of a warp spread over the banks (bank model: 64-QAM 1.25 wavefronts per store against
+        // 1.75 with rotated addresses; measured 1.036 -> 1.027 ms per chunk); the other maps gain nothing from it.
+        q = { q.x * 3.1622776601683795f, q.y * 3.1622776601683795f };
+        const float a = 2.0f - fabsf(q.x), b = 2.0f - fabsf(q.y);
+        const bool r1 = R != 0;
+        Lb[0] = r1 ? a : q.x; Lb[NCOL] = r1 ? q.x : a;
+        Lb[2 * NCOL] = r1 ? b : q.y; Lb[3 * NCOL] = r1 ? q.y : b;
+    } else if (NB == 6 && NCOL == 13) {
+        q = { q.x * 6.48074069840786f, q.y * 6.48074069840786f };
+        const float a = 4.0f - fabsf(q.x), b = 4.0f - fabsf(q.y);
+        const float a2 = 2.0f - fabsf(a), b2 = 2.0f - fabsf(b);
+        const bool r0 = R == 0, r1 = R == 1;                               // position m holds value (m - R) mod 3
+        Lb[0] = r0 ? q.x : (r1 ? a2 : a);
+        Lb[NCOL] = r0 ? a : (r1 ? q.x : a2);
+        Lb[2 * NCOL] = r0 ? a2 : (r1 ? a : q.x);
+        Lb[3 * NCOL] = r0 ? q.y : (r1 ? b2 : b);
+        Lb[4 * NCOL] = r0 ? b : (r1 ? q.y : b2);
+        Lb[5 * NCOL] = r0 ? b2 : (r1 ? b : q.y);
     } else if (NB == 4) {                                                  // s = 2: R in {0, 1}
         q = { q.x * 3.1622776601683795f, q.y * 3.1622776601683795f };
         float* __restrict__ A0 = Lb + R * NCOL;
@@ -320,10 +177,10 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
     }
     dft8(v);
     {
-        const float4* __restrict__ tw = reinterpret_cast<const float4*>(lut->tw8[8 * j]);     // W64^(j*k1), k1 = 0..7
+        const float4* __restrict__ tw = reinterpret_cast<const float4*>(lut->tw8[0][j]);      // W64^(j*k1), k1 = 2p, 2p + 1
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            const float4 t = __ldg(tw + p);
+            const float4 t = __ldg(tw + 8 * p);
             if (p) v[2 * p] = cmul(v[2 * p], cpx{ t.x, t.y });
             v[2 * p + 1] = cmul(v[2 * p + 1], cpx{ t.z, t.w });
         }
@@ -418,8 +275,6 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
     }
 }
 
-#endif
-
 // ---------------------------------------------------------------------------------------------------
 // k_demod2: per-symbol loop of the 2x2 block (lib/demod2_impl.cc:279-330; htChanUpdate :471-551,
 // vhtChanUpdate :553-630; procSymDeintNL2SS1/SS2 c8p.cc:2238-2338; procSymDepasNL :2442-2451) for
@@ -427,7 +282,7 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
 // (same 8x8 DFT as k_demod); the two halves swap spectra with 8 shuffles, then half a computes
 // stream a = F0*w[2a] + F1*w[2a+1] (the folded (H^H H)^-1 H^H), the 8-pilot common phase is shared
 // through shared memory, and each half demaps / deinterleaves its own stream straight into the
-// stream-deparsed position of the symbol's LLR line.
+// stream-deparsed position of the symbol's LLR line (closed form: demap2_tone).
 // HBM traffic per symbol: 2 x 640 B in, 4*nCBPS B out (3776 B at HT MCS15).
 // ---------------------------------------------------------------------------------------------------
 constexpr int SPW2 = 2;             // symbols per warp
@@ -439,54 +294,119 @@ struct __align__(16) WarpBuf2 {
     float llr[SPW2 * 832];          // deparsed soft bits of the warp's symbols, contiguous
 };
 
+// One data tone of one stream of a 2-stream symbol: NB soft bits through the stream's deinterleaver (c8p.cc:2238-2338) and the
+// stream parser (c8p.cc:2442-2451) in closed form.  Stream-local position of bit h*S + c: k = B + 13*((c + R) mod S) + 13*S*h
+// (as in demap_tone); the parser sends k to k + S*floor(k / S) + a*S.  The table entry carries P0 = the parsed position of k = B,
+// R and beta = B mod S, so position m of axis h is P0 + 13*m + S*floor((beta + 13*m) / S) + 26*S*h and holds value (m - R) mod S.
+template <int NB>
+__device__ __forceinline__ void demap2_tone(float* __restrict__ Lb, int R, int beta, cpx q)
+{
+    constexpr int S = NB / 2 > 1 ? NB / 2 : 1;
+    if (NB == 1) {
+        Lb[0] = q.x;
+    } else if (NB == 2) {
+        Lb[0] = q.x * 1.4142135623730951f; Lb[26] = q.y * 1.4142135623730951f;
+    } else if (NB == 4) {
+        q = { q.x * 3.1622776601683795f, q.y * 3.1622776601683795f };
+        const float a = 2.0f - fabsf(q.x), b = 2.0f - fabsf(q.y);
+        const bool r1 = R != 0;
+        float* __restrict__ A1 = Lb + 13 + S * ((beta + 13) / S);
+        Lb[0] = r1 ? a : q.x; A1[0] = r1 ? q.x : a;
+        Lb[26 * S] = r1 ? b : q.y; A1[26 * S] = r1 ? q.y : b;
+    } else if (NB == 6) {
+        q = { q.x * 6.48074069840786f, q.y * 6.48074069840786f };
+        const float a = 4.0f - fabsf(q.x), b = 4.0f - fabsf(q.y);
+        const float a2 = 2.0f - fabsf(a), b2 = 2.0f - fabsf(b);
+        const bool r0 = R == 0, r1 = R == 1;
+        float* __restrict__ A1 = Lb + 13 + S * ((beta + 13) / S);
+        float* __restrict__ A2 = Lb + 26 + S * ((beta + 26) / S);
+        Lb[0] = r0 ? q.x : (r1 ? a2 : a);
+        A1[0] = r0 ? a : (r1 ? q.x : a2);
+        A2[0] = r0 ? a2 : (r1 ? a : q.x);
+        Lb[26 * S] = r0 ? q.y : (r1 ? b2 : b);
+        A1[26 * S] = r0 ? b : (r1 ? q.y : b2);
+        A2[26 * S] = r0 ? b2 : (r1 ? b : q.y);
+    } else {
+        q = { q.x * 13.038404810405298f, q.y * 13.038404810405298f };
+        const float a = 8.0f - fabsf(q.x), b = 8.0f - fabsf(q.y);
+        const float a2 = 4.0f - fabsf(a), b2 = 4.0f - fabsf(b);
+        const float a3 = 2.0f - fabsf(a2), b3 = 2.0f - fabsf(b2);
+        // value c goes to position (c + R) & 3
+        const int m0 = R, m1 = (R + 1) & 3, m2 = (R + 2) & 3, m3 = (R + 3) & 3;
+        float* __restrict__ A0 = Lb + 13 * m0 + S * ((beta + 13 * m0) >> 2);
+        float* __restrict__ A1 = Lb + 13 * m1 + S * ((beta + 13 * m1) >> 2);
+        float* __restrict__ A2 = Lb + 13 * m2 + S * ((beta + 13 * m2) >> 2);
+        float* __restrict__ A3 = Lb + 13 * m3 + S * ((beta + 13 * m3) >> 2);
+        A0[0] = q.x; A1[0] = a; A2[0] = a2; A3[0] = a3;
+        A0[26 * S] = q.y; A1[26 * S] = b; A2[26 * S] = b2; A3[26 * S] = b3;
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void demap2_symbol(float* __restrict__ L, const uint4 te, const cpx* v, cpx ps)
+{
+    const unsigned w[4] = { te.x, te.y, te.z, te.w };
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        const unsigned e = (k2 & 1) ? (w[k2 >> 1] >> 16) : (w[k2 >> 1] & 0xFFFFu);
+        if (e == 0xFFFFu) continue;                                        // null / pilot bin
+        demap2_tone<NB>(L + (e & 1023u), (int)((e >> 10) & 3u), (int)(e >> 12), cmul(v[k2], ps));
+    }
+}
+
 __global__ void __launch_bounds__(DW * 32)
 k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const float2* __restrict__ iq1,
          const int64_t* __restrict__ off, int maxf, const c8b_frame* __restrict__ frames, const float2* __restrict__ w2All,
          float* __restrict__ llrArena)
 {
     __shared__ WarpBuf2 wb[DW];
-    __shared__ uint16_t smap[2][416];
     const int item = blockIdx.y;
     const c8b_frame* __restrict__ fr = frames + item;
-    if (fr->status != C8B_ST_OK || fr->nss != 2) return;
-    const int nsym = fr->nsym;
+    // every word whose address follows from the block index is requested up front (one round trip, not a chain)
+    const int status = fr->status, nss = fr->nss, nsym = fr->nsym, fmt = fr->format, ncbps = fr->ncbps;
+    const int nsymsamp = fr->nsymsamp, data_off = fr->data_off, sync_idx = fr->sync_idx;
+    const float rad = fr->rad;
+    const int64_t llr_off = fr->llr_off;
+    const int64_t ioff = off[maxf == 1 ? item : item / maxf];
+    if (status != C8B_ST_OK || nss != 2) return;
     const int sym0 = blockIdx.x * SPB2;
     if (sym0 >= nsym) return;
-    const int fmt = fr->format, ncbps = fr->ncbps, ncbpss = ncbps >> 1;
+    const int ncbpss = ncbps >> 1;
     const int nbpsc = ncbpss / 52;
     const int mi = nbpsc == 1 ? 0 : nbpsc == 2 ? 1 : nbpsc == 4 ? 2 : nbpsc == 6 ? 3 : 4;
-    for (int i = threadIdx.x; i < ncbpss && i < 416; i += DW * 32) { smap[0][i] = lut->deintNL[0][mi][i]; smap[1][i] = lut->deintNL[1][mi][i]; }
-    __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 4, a = (lane >> 3) & 1, j = lane & 7;   // symbol in warp, antenna / stream, thread in the DFT
     WarpBuf2& W = wb[warp];
     const int sidx = sym0 + warp * SPW2 + g;
     const bool live = sidx < nsym;
-    const int nsymsamp = fr->nsymsamp;
-    const float rad = fr->rad;
-    const int k0 = fr->data_off + sidx * nsymsamp + C8B_SYM_SHIFT;
-    const float2* __restrict__ x = (a ? iq1 : iq0) + off[item / maxf] + fr->sync_idx + 224 + k0;
+    const int k0 = data_off + sidx * nsymsamp + C8B_SYM_SHIFT;
+    const float2* __restrict__ x = (a ? iq1 : iq0) + ioff + sync_idx + 224 + k0;
 
     cpx v[8];
     if (live) {
+        float2 s[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) s[m] = __ldg(x + j + 8 * m);
 #pragma unroll
         for (int m = 0; m < 8; m++) {
-            const int n = j + 8 * m;
-            const float2 s = __ldg(x + n);
             float sn, cs;
-            cfo_rot(__fmul_rn((float)(k0 + n + 224), rad), &sn, &cs);     // lib/signal2_impl.cc:172-177
-            v[m] = { s.x * cs - s.y * sn, s.x * sn + s.y * cs };
+            cfo_rot(__fmul_rn((float)(k0 + j + 8 * m + 224), rad), &sn, &cs);     // lib/signal2_impl.cc:172-177
+            v[m] = { s[m].x * cs - s[m].y * sn, s[m].x * sn + s[m].y * cs };
         }
     } else {
 #pragma unroll
         for (int m = 0; m < 8; m++) v[m] = { 0.f, 0.f };
     }
     dft8(v);
+    {
+        const float4* __restrict__ tw = reinterpret_cast<const float4*>(lut->tw8[0][j]);      // W64^(j*k1), k1 = 2p, 2p + 1
 #pragma unroll
-    for (int k1 = 1; k1 < 8; k1++) {
-        const int t = (j * k1) & 63;
-        v[k1] = cmul(v[k1], cpx{ __ldg(&lut->twr[t]), __ldg(&lut->twi[t]) });
+        for (int p = 0; p < 4; p++) {
+            const float4 t = __ldg(tw + 8 * p);
+            if (p) v[2 * p] = cmul(v[2 * p], cpx{ t.x, t.y });
+            v[2 * p + 1] = cmul(v[2 * p + 1], cpx{ t.z, t.w });
+        }
     }
     float2* __restrict__ xb = W.xch + (g * 2 + a) * XS;
 #pragma unroll
@@ -542,46 +462,22 @@ k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const 
         const float inv = 1.0f / sqrtf(re * re + im * im);
         ps = { re * inv, -im * inv };
     }
+    // soft bits of this half's stream through its deinterleaver and the stream parser, both in closed form (lut.h demapTab2)
     float* __restrict__ L = W.llr + g * ncbps;
-    const int sp = nbpsc / 2 > 1 ? nbpsc / 2 : 1;                                // stream parser block (c8p.cc:2445)
     if (live) {
-        const uint16_t* __restrict__ mapA = smap[a];
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) {
-            const int d = lut->binToDataNL[j + 8 * k2];
-            if (d == 255) continue;
-            cpx q = cmul(v[k2], ps);
-            float b[8];
-            if (nbpsc == 1) { b[0] = q.x; }
-            else if (nbpsc == 2) { q = { q.x * 1.4142135623730951f, q.y * 1.4142135623730951f }; b[0] = q.x; b[1] = q.y; }
-            else if (nbpsc == 4) {
-                q = { q.x * 3.1622776601683795f, q.y * 3.1622776601683795f };
-                b[0] = q.x; b[1] = 2.0f - fabsf(q.x); b[2] = q.y; b[3] = 2.0f - fabsf(q.y);
-            } else if (nbpsc == 6) {
-                q = { q.x * 6.48074069840786f, q.y * 6.48074069840786f };
-                const float aa = 4.0f - fabsf(q.x), bb = 4.0f - fabsf(q.y);
-                b[0] = q.x; b[1] = aa; b[2] = 2.0f - fabsf(aa); b[3] = q.y; b[4] = bb; b[5] = 2.0f - fabsf(bb);
-            } else {
-                q = { q.x * 13.038404810405298f, q.y * 13.038404810405298f };
-                const float aa = 8.0f - fabsf(q.x), bb = 8.0f - fabsf(q.y), a2 = 4.0f - fabsf(aa), b2 = 4.0f - fabsf(bb);
-                b[0] = q.x; b[1] = aa; b[2] = a2; b[3] = 2.0f - fabsf(a2); b[4] = q.y; b[5] = bb; b[6] = b2; b[7] = 2.0f - fabsf(b2);
-            }
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                if (t < nbpsc) {
-                    const int k = mapA[d * nbpsc + t];                            // deinterleaved position in stream a
-                    const int blk = k / sp;
-                    L[(2 * blk + a) * sp + (k - blk * sp)] = b[t];               // stream de-parse
-                }
-            }
-        }
+        const uint4 te = __ldg(reinterpret_cast<const uint4*>(lut->demapTab2[mi][a] + 8 * j));
+        if (nbpsc == 1) demap2_symbol<1>(L, te, v, ps);
+        else if (nbpsc == 2) demap2_symbol<2>(L, te, v, ps);
+        else if (nbpsc == 4) demap2_symbol<4>(L, te, v, ps);
+        else if (nbpsc == 6) demap2_symbol<6>(L, te, v, ps);
+        else demap2_symbol<8>(L, te, v, ps);
     }
     __syncwarp();
     const int wsym0 = sym0 + warp * SPW2;
     int nlive = nsym - wsym0;
     nlive = nlive < 0 ? 0 : (nlive > SPW2 ? SPW2 : nlive);
     const int nfl = nlive * ncbps;
-    float* __restrict__ out = llrArena + fr->llr_off + (int64_t)wsym0 * ncbps;
+    float* __restrict__ out = llrArena + llr_off + (int64_t)wsym0 * ncbps;
     if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
         float4* __restrict__ o4 = reinterpret_cast<float4*>(out);

@@ -117,9 +117,26 @@ void c8b_lut_build(c8b_lut* L)
                 L->demapTab[mode][8 * j + k2] = e;
             }
     }
+    for (int m = 0; m < 5; m++)
+        for (int a = 0; a < 2; a++) {
+            const int nb = nbN[m], s = nb / 2 > 1 ? nb / 2 : 1;
+            const uint16_t* map = L->deintNL[a][m];
+            for (int j = 0; j < 8; j++)
+                for (int k2 = 0; k2 < 8; k2++) {
+                    const int dd = L->binToDataNL[j + 8 * k2];
+                    uint16_t e = 0xFFFF;
+                    if (dd != 255) {
+                        int base = map[dd * nb];
+                        for (int c = 1; c < s; c++) if (map[dd * nb + c] < base) base = map[dd * nb + c];
+                        const int R = (map[dd * nb] - base) / 13, p0 = base + s * (base / s) + a * s;
+                        e = (uint16_t)(p0 | (R << 10) | ((base % s) << 12));
+                    }
+                    L->demapTab2[m][a][8 * j + k2] = e;
+                }
+        }
     for (int j = 0; j < 8; j++)
         for (int k1 = 0; k1 < 8; k1++) {
-            L->tw8[8 * j + k1][0] = L->twr[(j * k1) & 63];
-            L->tw8[8 * j + k1][1] = L->twi[(j * k1) & 63];
+            L->tw8[k1 >> 1][j][2 * (k1 & 1)] = L->twr[(j * k1) & 63];
+            L->tw8[k1 >> 1][j][2 * (k1 & 1) + 1] = L->twi[(j * k1) & 63];
         }
 }

@@ -36,7 +36,11 @@ struct c8b_lut {
     // Otherwise bits 0-8 = B, bits 9-10 = R: soft bit h*s + c of the bin's data tone (s = max(nBPSC/2, 1), h < nBPSC/s, c < s)
     // lands at B + N_COL*((c + R) mod s) + h*N_COL*s -- the deinterleaver's two permutations in closed form (N_COL 16 / 13).
     alignas(16) uint16_t demapTab[9][64];
-    alignas(16) float tw8[64][2];   // tw8[8*j + k1] = W64^(j*k1) as (re, im): the 8x8 DFT's twiddles, one row per thread
+    // demapTab2[m][a][8*j + k2], m = nBPSCS 1,2,4,6,8, a = stream of a 2-stream symbol: bits 0-9 = P0, 10-11 = R, 12-13 = beta
+    // (k_demod.cu demap2_tone): the stream's deinterleaver (rotated by 22 tones for stream 2) and the stream parser in closed form
+    alignas(16) uint16_t demapTab2[5][2][64];
+    alignas(16) float tw8[4][8][4]; // tw8[p][j] = W64^(j*2p), W64^(j*(2p+1)) as (re, im, re, im): the 8x8 DFT's twiddles; the 8
+                                    // threads of a symbol read one 128-byte line per p
 };
 
 void c8b_lut_build(c8b_lut* L);   // host, by formula (lut.cc)

@@ -63,7 +63,8 @@ def test_lut_blob_matches_reference_tables(golden):
     pair01 = take(2, "<f4")
     o = (o + 15) & ~15                                   # alignas(16)
     demap = take(9 * 64, "<u2").reshape(9, 8, 8)
-    tw8 = take(128, "<f4").reshape(8, 8, 2)
+    demap2 = take(5 * 2 * 64, "<u2").reshape(5, 2, 8, 8)
+    tw8 = take(128, "<f4").reshape(4, 8, 2, 2)             # [k1 / 2][j][k1 % 2][re, im]
     assert o == blob.size and pair01.tolist() == [0.0, 1.0]
     # k_demod's per-thread tables restate deintL / deintNL[0] / binToData* / tw*: entry (B, R) of bin j + 8*k2 puts soft bit
     # h*s + c at B + N_COL*((c + R) mod s) + h*N_COL*s
@@ -81,9 +82,23 @@ def test_lut_blob_matches_reference_tables(golden):
                     B, R = e & 511, e >> 9
                     got = [B + ncol * ((c + R) % s_) + h * ncol * s_ for h in range(nb // s_) for c in range(s_)]
                     assert got == mp[d * nb:(d + 1) * nb].tolist(), (mode, j, k2)
+    # two-stream symbols: deinterleaver of stream a + stream parser (c = a*s + 2*s*(k // s) + k % s)
+    for m, nb in enumerate((1, 2, 4, 6, 8)):
+        s_ = max(nb // 2, 1)
+        for a in range(2):
+            for j in range(8):
+                for k2 in range(8):
+                    e, d = int(demap2[m, a, j, k2]), int(binNL[j + 8 * k2])
+                    assert (e == 0xFFFF) == (d == 255)
+                    if d != 255:
+                        P0, R, beta = e & 1023, (e >> 10) & 3, e >> 12
+                        got = [P0 + 13 * ((c + R) % s_) + s_ * ((beta + 13 * ((c + R) % s_)) // s_) + 26 * s_ * h
+                               for h in range(nb // s_) for c in range(s_)]
+                        k = deintNL[a, m, d * nb:(d + 1) * nb].astype(int)
+                        assert got == (a * s_ + 2 * s_ * (k // s_) + k % s_).tolist(), (m, a, j, k2)
     for j in range(8):
         for k1 in range(8):
-            assert tw8[j, k1, 0] == twr[(j * k1) & 63] and tw8[j, k1, 1] == twi[(j * k1) & 63]
+            assert tw8[k1 >> 1, j, k1 & 1, 0] == twr[(j * k1) & 63] and tw8[k1 >> 1, j, k1 & 1, 1] == twi[(j * k1) & 63]
     assert np.array_equal(ltfL, g["tab_LTF_L_26_F_FLOAT"]) and np.array_equal(ltfNL, g["tab_LTF_NL_28_F_FLOAT"])
     assert np.array_equal(ltfNL22, g["tab_LTF_NL_28_F_FLOAT_VHT22"])
     assert np.array_equal(pilotP[:127], g["tab_PILOT_P"])

@@ -26,5 +26,8 @@ rx.close()
 n = len(off)
 dev_ms = sum(v[0] for v in st.values())
 print("config 2: %d frames, %d samples, %d decoded" % (n, int(ln.sum()), int((fr["npdu"] == 1).sum())))
+ok = fr["status"] == 0
+alg = float((fr["nsym"][ok].astype(np.int64) * (640 + 4 * fr["ncbps"][ok].astype(np.int64))).sum())     # k_demod: 640 B in + 4 nCBPS out per symbol
+print("k_demod: %.2f GB algorithmic in %.3f ms = %.0f GB/s" % (alg / 1e9, st["demod"][0], alg / st["demod"][0] / 1e6))
 print("device ms per stage (launches):", {k: (round(v[0], 3), v[1]) for k, v in st.items()},
       "sum %.2f ms = %.2f M frames/s, %.2f G samples/s kernel-only" % (dev_ms, n / dev_ms / 1e3, ln.sum() / dev_ms / 1e6))

@@ -3,6 +3,7 @@
   python tools/ncu_lines.py <report.ncu-rep> <kernel-name> [min_share_percent]"""
 import csv
 import io
+import re
 import subprocess
 import sys
 
@@ -20,7 +21,11 @@ lines = []
 for r in rows[hdr + 1:]:
     if len(r) < len(H) or not r[0].isdigit():
         continue
-    g = lambda n: int(r[ci[n]] or 0) if r[ci[n]] not in ("-", "") else 0
+    def g(n):
+        m = re.match(r"-?\d+", r[ci[n]] or "")
+        return int(m.group()) if m else 0
+    if len(r) != len(H):                                 # a source line with quotes in it (inline asm) splits badly: skip
+        continue
     lines.append((int(r[0]), r[1], g("# Samples"), g("Instructions Executed"), g("stall_long_sb"), g("stall_short_sb"), g("stall_wait"),
                   g("stall_math"), g("stall_barrier"), g("stall_mio"), g("stall_lg")))
 ts = sum(l[2] for l in lines) or 1
