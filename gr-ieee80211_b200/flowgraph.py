@@ -163,6 +163,7 @@ class rx_top_block:
         self.max_frames = max_frames
         self.rx = Receiver(device=device, chunk_items=1, max_frames=max_frames, mupos=mupos, mugid=mugid, blob=blob)
         self.frames = None
+        self.truncated = False
         self._streaming = False
 
     def close(self):
@@ -180,6 +181,11 @@ class rx_top_block:
             _, chan = self.rx.detect(x0, [0], [x0.size])
         keep = fr["status"] != 9                                # C8B_ST_EMPTY
         self.frames = fr[keep]
+        # the scan of an item stops when its max_frames records are used: say so instead of losing the rest silently
+        self.truncated = bool(self.max_frames > 1 and keep.sum() >= self.max_frames)
+        if self.truncated:
+            self.decode.printer("ieee80211 rx: all %d frame records of the capture are used, later frames were not examined "
+                                "(raise max_frames, or feed the capture through work())" % self.max_frames)
         for k in np.nonzero(keep)[0]:
             self._publish(fr[k], chan[k], pdu[k], 0)
         return self.frames

@@ -90,3 +90,21 @@ def test_work_calls_equal_run(golden):
     assert tb.sync.offsets == sync_run and len(sync_run) == 25
     assert a == b
     tb.close()
+
+
+def test_run_reports_used_up_frame_records(golden):
+    """run() over a capture with more frames than max_frames keeps the first max_frames frames -- and says so"""
+    pkg = load_pkg()
+    fg = pkg.flowgraph
+    g = golden["frames_siso"]
+    offs = g["offs"]
+    x = np.ascontiguousarray(g["iq"][offs[1]:offs[26]])
+    lines = []
+    tb = fg.rx_top_block(nant=1, ifdebug=False, printer=lines.append, max_frames=8)
+    fr = tb.run(x)
+    assert len(fr) == 8 and tb.truncated and any("frame records" in s for s in lines)
+    tb.close()
+    tb = fg.rx_top_block(nant=1, ifdebug=False, printer=lines.append, max_frames=64)
+    fr = tb.run(x)
+    assert len(fr) == 25 and not tb.truncated
+    tb.close()
