@@ -63,6 +63,22 @@ __device__ __forceinline__ void cfo_rot(float ph, float* sn, float* cs)
     *cs = __cosf(r);
 }
 
+// shared memory -> global as ONE bulk copy by the copy engine (cp.async.bulk, SASS UBLKCP): the line the warp scattered leaves
+// the SM without passing the load / store pipe again (the lane loop costs an LDS.128 + STG.128 wavefront per 128 bytes, a
+// quarter of this kernel's L1 traffic).  src / dst 16-byte aligned, bytes a multiple of 16.  Every lane that wrote the line has
+// fenced its writes towards the async proxy and the warp has synchronised before one lane calls this.
+__device__ __forceinline__ void bulk_store(float* dst, const float* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_drain()            // the shared-memory side of every bulk copy of this thread is done
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // soft bits of one data tone through the deinterleaver in closed form (lut.h demapTab): NB bits per tone, s = max(NB/2, 1) per
 // axis, axis h starts NCOL*s floats after axis 0, bit c of an axis sits at NCOL*((c + R) mod s).  NCOL is 16 (legacy) or 13.
 template <int NCOL, int NB>
@@ -244,34 +260,27 @@ k_demod(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const in
             else demap_symbol<13, 8>(L, te, v, ps);
         }
     }
+    bulk_store_fence();
     __syncwarp();
-    // coalesced copy-out of the warp's live symbols
+    // copy-out of the warp's live symbols: one bulk copy (per row when the rows are padded), lane loop when the frame's soft-bit
+    // stream is not 16-byte aligned in the arena
     const int wsym0 = sym0 + warp * SPW;
     int nlive = nsym - wsym0;
     nlive = nlive < 0 ? 0 : (nlive > SPW ? SPW : nlive);
     const int nfl = nlive * ncbps;                          // multiple of 4 (48 | 52 divide by 4)
     float* __restrict__ out = llrArena + llr_off + (int64_t)wsym0 * ncbps;
     const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    if (lpad == 0) {
-        if (al16) {
-            const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
-            float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
-            for (int i = lane; i < nfl / 4; i += 32) o4[i] = s4[i];
-        } else {
-            for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
+    if (al16) {
+        if (lane == 0 && nlive > 0) {
+            if (lpad == 0) bulk_store(out, W.llr, (uint32_t)nfl * 4u);
+            else for (int r = 0; r < nlive; r++) bulk_store(out + r * ncbps, W.llr + r * lrow, (uint32_t)ncbps * 4u);
+            bulk_store_drain();
         }
-    } else {                                               // padded rows: symbol by symbol (ncbps * 4 bytes is a multiple of 16)
-        for (int r = 0; r < nlive; r++) {
-            const float* __restrict__ src = W.llr + r * lrow;
-            float* __restrict__ dst = out + r * ncbps;
-            if (al16) {
-                const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
-                float4* __restrict__ o4 = reinterpret_cast<float4*>(dst);
-                for (int i = lane; i < ncbps / 4; i += 32) o4[i] = s4[i];
-            } else {
-                for (int i = lane; i < ncbps; i += 32) dst[i] = src[i];
-            }
-        }
+    } else if (lpad == 0) {
+        for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
+    } else {
+        for (int r = 0; r < nlive; r++)
+            for (int i = lane; i < ncbps; i += 32) out[r * ncbps + i] = W.llr[r * lrow + i];
     }
 }
 
@@ -472,6 +481,7 @@ k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const 
         else if (nbpsc == 6) demap2_symbol<6>(L, te, v, ps);
         else demap2_symbol<8>(L, te, v, ps);
     }
+    bulk_store_fence();
     __syncwarp();
     const int wsym0 = sym0 + warp * SPW2;
     int nlive = nsym - wsym0;
@@ -479,9 +489,7 @@ k_demod2(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq0, const 
     const int nfl = nlive * ncbps;
     float* __restrict__ out = llrArena + llr_off + (int64_t)wsym0 * ncbps;
     if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        const float4* __restrict__ s4 = reinterpret_cast<const float4*>(W.llr);
-        float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
-        for (int i = lane; i < nfl / 4; i += 32) o4[i] = s4[i];
+        if (lane == 0 && nlive > 0) { bulk_store(out, W.llr, (uint32_t)nfl * 4u); bulk_store_drain(); }
     } else {
         for (int i = lane; i < nfl; i += 32) out[i] = W.llr[i];
     }
