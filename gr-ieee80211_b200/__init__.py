@@ -8,4 +8,4 @@ from . import synth  # noqa: F401
 from . import flowgraph  # noqa: F401
 from . import blocks  # noqa: F401
 from .rx import Receiver, lut_blob  # noqa: F401
-from ._cabi import C8bError, FRAME_DTYPE, TXFRAME_DTYPE, K_NAMES  # noqa: F401
+from ._cabi import C8bError, FRAME_DTYPE, TXFRAME_DTYPE, TXMU_DTYPE, K_NAMES  # noqa: F401

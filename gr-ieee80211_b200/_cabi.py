@@ -49,6 +49,16 @@ TXFRAME_DTYPE = np.dtype([("format", "<i4"), ("mcs", "<i4"), ("psdu_off", "<i8")
 assert TXFRAME_DTYPE.itemsize == C.sizeof(C8bTxFrame)
 
 
+class C8bTxMu(C.Structure):
+    _fields_ = [("mcs", C.c_int32 * 2), ("psdu_len", C.c_int32 * 2), ("psdu_off", C.c_int64 * 2), ("group_id", C.c_int32), ("cfo_hz", C.c_float),
+                ("out_off", C.c_int64), ("q_index", C.c_int64)]
+
+
+TXMU_DTYPE = np.dtype([("mcs", "<i4", (2,)), ("psdu_len", "<i4", (2,)), ("psdu_off", "<i8", (2,)), ("group_id", "<i4"), ("cfo_hz", "<f4"),
+                       ("out_off", "<i8"), ("q_index", "<i8")], align=True)
+assert TXMU_DTYPE.itemsize == C.sizeof(C8bTxMu)
+
+
 class C8bCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("chunk_items", C.c_int32), ("max_item_len", C.c_int32), ("max_frames", C.c_int32),
                 ("mupos", C.c_int32), ("mugid", C.c_int32), ("no_overlap", C.c_int32), ("decode_mode", C.c_int32), ("frontend_mode", C.c_int32), ("mmse", C.c_int32), ("reserved", C.c_int32 * 4)]
@@ -82,6 +92,9 @@ SYMBOLS = [
     ("c8b_tx_batch_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _i64]),
     ("c8b_tx_batch2", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
     ("c8b_tx_batch2_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
+    ("c8b_tx_mu_nsamp", _i, [_i, _i, _i, _i]),
+    ("c8b_tx_mu_batch", _i, [_vp, _vp, _i64, _vp, _i, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
+    ("c8b_tx_mu_batch_dev", _i, [_vp, _vp, _i64, _vp, _i, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
     ("c8b_tx_random_psdu_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_uint64]),
     ("c8b_tx_udp_parse", _i, [_vp, _i, _vp, _vp]),
     ("c8b_tx_from_udp", _i, [_vp, _vp, _vp, _vp, _i, _i, C.c_float, _i, _vp, _i64, _vp, _vp]),

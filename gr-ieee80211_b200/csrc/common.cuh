@@ -57,6 +57,9 @@ void c8b_tx_scrambler(int seed, uint32_t out[4]);
 void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
                    float2* d_out, float2* d_out1, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);
 int c8b_tx_nss_host(int format, int mcs);
+int c8b_tx_mu_geometry_host(int mcs0, int len0, int mcs1, int len1, int* nsym, int* nslots);
+void c8b_launch_tx_mu(const c8b_lut* lut, const c8b_txmu* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu, const float2* d_q,
+                      float2* d_out0, float2* d_out1, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st);
 void c8b_launch_tx_fill(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, uint8_t* d_psdu, uint64_t seed, cudaStream_t st);
 size_t c8b_detect_multi_scratch(int nitems, int maxLen);   // maxLen: longest item, samples
 void c8b_launch_detect_multi(const c8b_lut* lut, const float2* iq, const int64_t* d_off, const int32_t* d_len, int nitems, int itemBase,

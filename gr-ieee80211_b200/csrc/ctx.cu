@@ -1140,6 +1140,85 @@ int c8b_tx_batch2_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, c
     return C8B_OK;
 }
 
+// ---- two-user MU-MIMO (genAmpduMu) ---------------------------------------------------------------------------------
+int c8b_tx_mu_nsamp(int mcs0, int len0, int mcs1, int len1)
+{
+    int nsym = 0, nslots = 0;
+    return c8b_tx_mu_geometry_host(mcs0, len0, mcs1, len1, &nsym, &nslots) ? nslots * 80 : C8B_ERR_ARG;
+}
+
+static int tx_run_mu(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* d_q, int nq,
+                     float multiplier, int seed, float* d_iq0, float* d_iq1, int64_t iq_samples)
+{
+    if (seed < 1 || seed > 127) { ctx->err = "c8b_tx_mu_batch: scrambler seed 1..127"; return C8B_ERR_ARG; }
+    int maxSlots = 0;
+    for (int i = 0; i < nframes; i++) {
+        int nsym = 0, nslots = 0;
+        const c8b_txmu& f = frames[i];
+        if (!c8b_tx_mu_geometry_host(f.mcs[0], f.psdu_len[0], f.mcs[1], f.psdu_len[1], &nsym, &nslots) || f.group_id < 1 || f.group_id > 62) {
+            ctx->err = "c8b_tx_mu_batch: VHT MCS 0-8, A-MPDUs of 4..4092 bytes (multiples of 4), group id 1..62";
+            return C8B_ERR_ARG;
+        }
+        for (int u = 0; u < 2; u++)
+            if (f.psdu_off[u] < 0 || f.psdu_off[u] + f.psdu_len[u] > psdu_bytes) { ctx->err = "c8b_tx_mu_batch: A-MPDU outside the PSDU arena"; return C8B_ERR_ARG; }
+        if (f.out_off < 0 || f.out_off + (int64_t)nslots * 80 > iq_samples || f.q_index < 0 || f.q_index >= nq) {
+            ctx->err = "c8b_tx_mu_batch: frame outside the IQ arena / q_index outside the matrix sets";
+            return C8B_ERR_ARG;
+        }
+        if (nslots > maxSlots) maxSlots = nslots;
+    }
+    EN(txf, (size_t)nframes * sizeof(c8b_txmu));
+    EN(txplan, c8b_tx_plan_bytes(2 * nframes));
+    CK(cudaMemcpyAsync(ctx->txf.p, frames, (size_t)nframes * sizeof(c8b_txmu), cudaMemcpyHostToDevice, ctx->st));
+    uint32_t scr[4];
+    c8b_tx_scrambler(seed, scr);
+    c8b_launch_tx_mu(ctx->d_lut, (const c8b_txmu*)ctx->txf.p, nframes, maxSlots, ctx->txplan.p, d_psdu, (const float2*)d_q, (float2*)d_iq0, (float2*)d_iq1,
+                     multiplier, scr, c8b_tx_eof_word(), ctx->st);
+    CK(cudaGetLastError());
+    return C8B_OK;
+}
+
+int c8b_tx_mu_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* d_q, int nq,
+                        float multiplier, int scrambler_seed, float* d_iq0, float* d_iq1, int64_t iq_samples)
+{
+    if (!ctx || !d_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !d_q || nq < 1 || !d_iq0 || !d_iq1 || iq_samples < 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    if (nframes == 0) return C8B_OK;
+    CK(cudaSetDevice(ctx->device));
+    r = tx_run_mu(ctx, d_psdu, psdu_bytes, frames, nframes, d_q, nq, multiplier, scrambler_seed, d_iq0, d_iq1, iq_samples);
+    if (r) return r;
+    CK(cudaStreamSynchronize(ctx->st));                            // the descriptor array is the caller's again
+    return C8B_OK;
+}
+
+int c8b_tx_mu_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* h_q, int nq,
+                    float multiplier, int scrambler_seed, float* h_iq0, float* h_iq1, int64_t iq_samples)
+{
+    if (!ctx || !h_psdu || psdu_bytes < 0 || !frames || nframes < 0 || !h_q || nq < 1 || !h_iq0 || !h_iq1 || iq_samples < 0) return C8B_ERR_ARG;
+    int r = need_lut(ctx);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    const size_t arena = ((size_t)(iq_samples + 16) * sizeof(float2) + 255) & ~(size_t)255;
+    const size_t qBytes = (size_t)nq * 256 * sizeof(float2), qOff = ((size_t)psdu_bytes + 16 + 255) & ~(size_t)255;
+    EN(txpsdu, qOff + qBytes);                                      // [A-MPDUs][matrix sets]
+    EN(txiq, arena * 2);
+    float* d0 = (float*)ctx->txiq.p;
+    float* d1 = (float*)((uint8_t*)ctx->txiq.p + arena);
+    const float* dq = (const float*)((uint8_t*)ctx->txpsdu.p + qOff);
+    CK(cudaMemcpyAsync(ctx->txpsdu.p, h_psdu, (size_t)psdu_bytes, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync((void*)dq, h_q, qBytes, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->txiq.p, 0, arena * 2, ctx->st));
+    if (nframes > 0) {
+        r = tx_run_mu(ctx, (const uint8_t*)ctx->txpsdu.p, psdu_bytes, frames, nframes, dq, nq, multiplier, scrambler_seed, d0, d1, iq_samples);
+        if (r) return r;
+    }
+    CK(cudaMemcpyAsync(h_iq0, d0, (size_t)iq_samples * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h_iq1, d1, (size_t)iq_samples * sizeof(float2), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return C8B_OK;
+}
+
 int c8b_tx_random_psdu_dev(c8b_ctx* ctx, uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, uint64_t seed)
 {
     if (!ctx || !d_psdu || psdu_bytes < 0 || !frames || nframes < 0) return C8B_ERR_ARG;

@@ -36,6 +36,7 @@ struct TxPlan {                     // per frame, filled by k_tx_plan
     uint32_t lsig, sigb, svc_crc;   // L-SIG 24 bits, VHT-SIG-B 26 bits, SIG-B CRC carried in the service field
     uint64_t sig48;                 // HT-SIG / VHT-SIG-A 48 bits
     int64_t psdu_off, out_off;
+    int64_t q_off;                  // MU-MIMO: first element of the frame's 64 x 2 x 2 spatial mapping matrices
     double cfo_step;                // rad / sample
 };
 
@@ -181,6 +182,85 @@ __device__ __forceinline__ float qam_level(int sign, int m)   // Gray-mapped amp
     return sign ? (float)m : -(float)m;
 }
 
+// constellation point of data tone d (0..47 / 0..51) of DATA symbol q in spatial stream iss: the nBPSC coded bits the
+// interleaver (and, for two streams of ONE encoder, the stream parser) puts there, Gray-mapped (tools/phy80211.py:712-760)
+__device__ __forceinline__ float2 tx_data_tone(const c8b_lut* __restrict__ L, const TxPlan& P, const uint8_t* __restrict__ psdu,
+                                               const uint32_t* __restrict__ scr, uint32_t eof, int q, int d, int iss)
+{
+    const bool leg = P.format == C8B_F_L;
+    const int nb = P.nbpsc;
+    const int mi = nb == 1 ? 0 : nb == 2 ? 1 : nb == 4 ? 2 : nb == 6 ? 3 : 4;
+    int bits = 0;
+    auto src = [&](int x) { return data_bit(P, psdu, scr, eof, x); };
+    const int sp = nb / 2 > 1 ? nb / 2 : 1;                     // stream parser block (tools/phy80211.py:712-733)
+    for (int b = 0; b < nb; b++) {
+        const int j = d * nb + b;
+        int c = leg ? L->deintL[mi][j] : L->deintNL[iss][mi][j];    // position in this stream's symbol before interleaving
+        if (P.nss == 2) c = iss * sp + 2 * sp * (c / sp) + c % sp;  // ... and in the encoder's output
+        const int m = mother_index(P.cr, q * P.ncbps + c);
+        bits |= bcc_out(src, m >> 1, m & 1) << b;
+    }
+    const int h = nb >> 1;                                      // bits per axis
+    if (nb == 1) return make_float2(bits ? 1.f : -1.f, 0.f);
+    const int bi = bits & ((1 << h) - 1), bq = bits >> h;
+    auto axis = [&](int a) {
+        const int b1 = (a >> 1) & 1, b2 = (a >> 2) & 1, b3 = (a >> 3) & 1;
+        int m = 1;
+        if (h == 2) m = b1 ? 1 : 3;
+        else if (h == 3) m = b1 ? (b2 ? 3 : 1) : (b2 ? 5 : 7);
+        else if (h == 4) m = b1 ? (b2 ? (b3 ? 5 : 7) : (b3 ? 3 : 1)) : (b2 ? (b3 ? 11 : 9) : (b3 ? 13 : 15));
+        return qam_level(a & 1, m);
+    };
+    const float nrm = h == 1 ? 0.70710678118654752f : h == 2 ? 0.31622776601683794f : h == 3 ? 0.15430334996209191f : 0.076696498884737041f;
+    return make_float2(axis(bi) * nrm, axis(bq) * nrm);
+}
+
+// C_STF_L_26 on FFT bin k (+ zeros at +-27, +-28 for HT / VHT)
+__device__ __forceinline__ float2 tx_stf(int k)
+{
+    const int sc = k < 32 ? k : k - 64;
+    float r = 0.f;
+    if (sc != 0 && (sc & 3) == 0 && sc >= -24 && sc <= 24) {
+        const int q = (sc + 24) >> 2;                               // 0..12, 6 = DC
+        const int sg[13] = { 1, -1, 1, -1, -1, 1, 0, -1, -1, 1, 1, 1, 1 };
+        r = 0.70710678118654752f * (float)sg[q];
+    }
+    return make_float2(r, r);
+}
+
+// the slot's 64 bins (X[g], already synchronised) -> 80 samples: inverse DFT, cyclic prefix / shift, the generator's windowing
+// (procConcat2Symbol: boundary samples halved), amplitude and carrier offset
+__device__ __forceinline__ void tx_emit(float2 (*X)[64], const float2* tw, int g, int k, int s, int shift, int csd, float gsc, int nslots,
+                                        double cfo_step, float2* __restrict__ o)
+{
+    float ar = 0.f, ai = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 64; q++) {
+        const float2 x = X[g][q], w = tw[(q * k) & 63];
+        ar = fmaf(x.x, w.x, fmaf(-x.y, w.y, ar));
+        ai = fmaf(x.x, w.y, fmaf(x.y, w.x, ai));
+    }
+    __syncthreads();
+    X[g][k] = make_float2(ar, ai);
+    __syncthreads();
+    const bool halfFirst = s == 2 || s >= 4, halfLast = (s == 1 || s >= 3) && s + 1 < nslots;    // procConcat2Symbol
+    for (int n = k; n < 80; n += 64) {
+        const float2 x = X[g][(n + shift + csd) & 63];
+        float a = gsc;
+        if ((n == 0 && halfFirst) || (n == 79 && halfLast)) a *= 0.5f;
+        float re = x.x * a, im = x.y * a;
+        if (cfo_step != 0.0) {                                              // genSignalWithCfo: exp(j i step), i from the first frame sample
+            double ph = (double)(s * 80 + n) * cfo_step;
+            ph -= 6.283185307179586476925 * floor(ph * 0.15915494309189533577);
+            float sn, cs;
+            sincosf((float)ph, &sn, &cs);
+            const float r2 = re * cs - im * sn;
+            im = re * sn + im * cs; re = r2;
+        }
+        o[n] = make_float2(re, im);
+    }
+}
+
 __global__ void __launch_bounds__(TXS * 64)
 k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int nframes, int maxSlots, const uint8_t* __restrict__ psduAll,
            float2* __restrict__ out0, float2* __restrict__ out1, float gain, uint4 scrSeq, uint32_t eof)
@@ -201,7 +281,6 @@ k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int n
         P = plan[f];
         const uint32_t scr[4] = { scrSeq.x, scrSeq.y, scrSeq.z, scrSeq.w };
         const uint8_t* __restrict__ psdu = psduAll + P.psdu_off;
-        const int sc = k < 32 ? k : k - 64;                                 // subcarrier of FFT bin k
         const int nPre = P.npre, nLtf = P.nss;
         const bool pilotBin = (k == 7 || k == 21 || k == 43 || k == 57);
         const float pbase[4] = { 1.f, 1.f, 1.f, -1.f };                     // C_PILOT_L / C_PILOT_HT 1SS / C_PILOT_VHT, subcarriers -21 -7 7 21
@@ -209,15 +288,7 @@ k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int n
         // cyclic shift of this stream (tools/phy80211header.py:713-725,950-956): 200 ns on the legacy part, 400 ns after it
         if (P.nss == 2 && iss == 1) csd = s < 7 ? 4 : 8;
         const int pslot = k == 43 ? 0 : k == 57 ? 1 : k == 7 ? 2 : 3;
-        auto stf = [&]() {                                                  // C_STF_L_26 (+ zeros at +-27, +-28 for HT / VHT)
-            float r = 0.f;
-            if (sc != 0 && (sc & 3) == 0 && sc >= -24 && sc <= 24) {
-                const int q = (sc + 24) >> 2;                               // 0..12, 6 = DC
-                const int sg[13] = { 1, -1, 1, -1, -1, 1, 0, -1, -1, 1, 1, 1, 1 };
-                r = 0.70710678118654752f * (float)sg[q];
-            }
-            return make_float2(r, r);
-        };
+        auto stf = [&]() { return tx_stf(k); };
         if (s < 2) { v = stf(); scale = rsqrtf(12.f); shift = s == 0 ? 32 : 48; }
         else if (s < 4) { v = make_float2(L->ltfL[k], 0.f); scale = rsqrtf(52.f); shift = s == 2 ? 32 : 48; }
         else if (s == 4 || (s < 7 && P.format != C8B_F_L)) {               // L-SIG, HT-SIG 1/2, VHT-SIG-A 1/2: BPSK / QBPSK, 48 tones
@@ -260,68 +331,160 @@ k_tx_slots(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int n
                 const float* pb4 = (P.format == C8B_F_HT && P.nss == 2) ? pht2[iss] : pbase;
                 v = make_float2(pol * (leg ? pbase[pslot] : pb4[(pslot + q) & 3]), 0.f);
             } else if (d != 255) {
-                const int nb = P.nbpsc;
-                const int mi = nb == 1 ? 0 : nb == 2 ? 1 : nb == 4 ? 2 : nb == 6 ? 3 : 4;
-                int bits = 0;
-                auto src = [&](int x) { return data_bit(P, psdu, scr, eof, x); };
-                const int sp = nb / 2 > 1 ? nb / 2 : 1;                     // stream parser block (tools/phy80211.py:712-733)
-                for (int b = 0; b < nb; b++) {
-                    const int j = d * nb + b;
-                    int c = leg ? L->deintL[mi][j] : L->deintNL[iss][mi][j];    // position in this stream's symbol before interleaving
-                    if (P.nss == 2) c = iss * sp + 2 * sp * (c / sp) + c % sp;  // ... and in the encoder's output
-                    const int m = mother_index(P.cr, q * P.ncbps + c);
-                    bits |= bcc_out(src, m >> 1, m & 1) << b;
-                }
-                const int h = nb >> 1;                                      // bits per axis
-                if (nb == 1) v = make_float2(bits ? 1.f : -1.f, 0.f);
-                else {
-                    const int bi = bits & ((1 << h) - 1), bq = bits >> h;
-                    auto axis = [&](int a) {
-                        const int b1 = (a >> 1) & 1, b2 = (a >> 2) & 1, b3 = (a >> 3) & 1;
-                        int m = 1;
-                        if (h == 2) m = b1 ? 1 : 3;
-                        else if (h == 3) m = b1 ? (b2 ? 3 : 1) : (b2 ? 5 : 7);
-                        else if (h == 4) m = b1 ? (b2 ? (b3 ? 5 : 7) : (b3 ? 3 : 1)) : (b2 ? (b3 ? 11 : 9) : (b3 ? 13 : 15));
-                        return qam_level(a & 1, m);
-                    };
-                    const float nrm = h == 1 ? 0.70710678118654752f : h == 2 ? 0.31622776601683794f : h == 3 ? 0.15430334996209191f : 0.076696498884737041f;
-                    v = make_float2(axis(bi) * nrm, axis(bq) * nrm);
-                }
+                v = tx_data_tone(L, P, psdu, scr, eof, q, d, iss);
             }
         }
     }
     X[g][k] = v;
     __syncthreads();
-    if (!live) return;
-    // inverse DFT, output index m = k
-    float ar = 0.f, ai = 0.f;
-#pragma unroll 8
-    for (int q = 0; q < 64; q++) {
-        const float2 x = X[g][q], w = tw[(q * k) & 63];
-        ar = fmaf(x.x, w.x, fmaf(-x.y, w.y, ar));
-        ai = fmaf(x.x, w.y, fmaf(x.y, w.x, ai));
-    }
-    __syncthreads();
-    X[g][k] = make_float2(ar, ai);
-    __syncthreads();
+    if (!live) return;                                                      // (threads that have exited do not count at the barriers below)
     const float gsc = gain * scale * (1.0f / 64.0f) * (P.nss == 2 ? 0.70710678118654752f : 1.0f);       // procToneScaling: / sqrt(N_tone nSS)
-    const bool halfFirst = s == 2 || s >= 4, halfLast = (s == 1 || s >= 3) && s + 1 < P.nslots;    // procConcat2Symbol
-    float2* __restrict__ o = (iss ? out1 : out0) + P.out_off + (int64_t)s * 80;
-    for (int n = k; n < 80; n += 64) {
-        const float2 x = X[g][(n + shift + csd) & 63];
-        float a = gsc;
-        if ((n == 0 && halfFirst) || (n == 79 && halfLast)) a *= 0.5f;
-        float re = x.x * a, im = x.y * a;
-        if (P.cfo_step != 0.0) {                                            // genSignalWithCfo: exp(j i step), i from the first frame sample
-            double ph = (double)(s * 80 + n) * P.cfo_step;
-            ph -= 6.283185307179586476925 * floor(ph * 0.15915494309189533577);
-            float sn, cs;
-            sincosf((float)ph, &sn, &cs);
-            const float r2 = re * cs - im * sn;
-            im = re * sn + im * cs; re = r2;
-        }
-        o[n] = make_float2(re, im);
+    tx_emit(X, tw, g, k, s, shift, csd, gsc, P.nslots, P.cfo_step, (iss ? out1 : out0) + P.out_off + (int64_t)s * 80);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-user VHT MU-MIMO (genAmpduMu, tools/phy80211.py:180-221): one space-time stream per user, each with its own A-MPDU,
+// MCS, VHT-SIG-B and padding to the common symbol count; from the VHT-STF on, the two streams (stream 1 cyclically shifted by
+// 400 ns) go through the per-subcarrier spatial mapping matrix Q (procSpatialMapping: antenna t = sum_u Q[k][t][u] X_u[k]).
+// The legacy part is the two-antenna one (200 ns shift on antenna 1).  plan[2 f + u] = user u of frame f.
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int tx_mu_geometry(int mcs0, int len0, int mcs1, int len1, int* nsym, int* nslots)
+{
+    int ns = 0;
+    const int mcs[2] = { mcs0, mcs1 }, len[2] = { len0, len1 };
+    for (int u = 0; u < 2; u++) {
+        int nbpsc = 0, cr = 0;
+        if (!tx_rate(C8B_F_VHT, mcs[u], &nbpsc, &cr) || len[u] < 4 || len[u] > 4095 || (len[u] & 3)) return 0;
+        const int ndbps = tx_ndbps(52 * nbpsc, cr);
+        const int n = (8 * len[u] + 16 + 6 + ndbps - 1) / ndbps;
+        if (n > ns) ns = n;
     }
+    *nsym = ns;
+    *nslots = 11 + ns;                                                      // L-STF 2, L-LTF 2, L-SIG, SIG-A 2, VHT-STF, 2 VHT-LTF, SIG-B
+    return 1;
+}
+
+__global__ void k_tx_plan_mu(const c8b_txmu* __restrict__ fr, int n, TxPlan* __restrict__ plan)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const c8b_txmu f = fr[i];
+    int nsym = 0, nslots = 0;
+    const bool ok = tx_mu_geometry(f.mcs[0], f.psdu_len[0], f.mcs[1], f.psdu_len[1], &nsym, &nslots) != 0;
+    // L-SIG: txTime = 20 + 8 + 4 + 4 nLTF + 4 + 4 nSym with two VHT-LTFs (procPktLenAggreMu, tools/phy80211header.py:509-525)
+    const int llen = ((36 + 4 * 2 + 4 * nsym - 20) / 4) * 3 - 3;
+    uint32_t ls = 0xBu | ((uint32_t)(llen & 0xfff) << 5);
+    ls |= (uint32_t)(__popc(ls) & 1) << 17;
+    // VHT-SIG-A, MU form (tools/phy80211.py:355-428): group id, one space-time stream for users 0 and 1, BCC everywhere
+    uint64_t a = (1ull << 2) | ((uint64_t)(f.group_id & 63) << 4) | (1ull << 10) | (1ull << 13) | (1ull << 23) | (0x1full << 29);
+    a |= (uint64_t)crc8_bits(a, 34) << 34;
+    for (int u = 0; u < 2; u++) {
+        TxPlan P;
+        memset(&P, 0, sizeof P);
+        P.format = C8B_F_VHT; P.mcs = f.mcs[u]; P.psdu_len = f.psdu_len[u]; P.psdu_off = f.psdu_off[u]; P.out_off = f.out_off;
+        P.cfo_step = (double)f.cfo_hz * 2.0 * 3.14159265358979323846 / 20000000.0;
+        P.q_off = f.q_index * 256;
+        if (ok) {
+            tx_rate(C8B_F_VHT, f.mcs[u], &P.nbpsc, &P.cr);
+            P.nss = 1; P.npre = 11;
+            P.ncbps = 52 * P.nbpsc;
+            P.ndbps = tx_ndbps(P.ncbps, P.cr);
+            P.nsym = nsym; P.nslots = nslots; P.nbits = nsym * P.ndbps;
+            P.lsig = ls; P.sig48 = a;
+            // VHT-SIG-B, MU form (:571-600): floor(len / 4) in 16 bits, MCS in 4, 6 tail; its CRC rides in the service field
+            const uint32_t sb = (uint32_t)(f.psdu_len[u] / 4) | ((uint32_t)(f.mcs[u] & 0xf) << 16);
+            P.sigb = sb;
+            P.svc_crc = crc8_bits(sb, 20);
+            const int psdu = (nsym * P.ndbps - 16 - 6) / 8;
+            P.npadeof = (psdu - f.psdu_len[u]) / 4;
+        }
+        plan[2 * i + u] = P;
+    }
+}
+
+__global__ void __launch_bounds__(TXS * 64)
+k_tx_slots_mu(const c8b_lut* __restrict__ L, const TxPlan* __restrict__ plan, int nframes, int maxSlots, const uint8_t* __restrict__ psduAll,
+              const float2* __restrict__ Q, float2* __restrict__ out0, float2* __restrict__ out1, float gain, uint4 scrSeq, uint32_t eof)
+{
+    const int t = blockIdx.y;                                               // transmit antenna
+    __shared__ float2 X[TXS][64];
+    __shared__ float2 tw[64];
+    const int g = threadIdx.x >> 6, k = threadIdx.x & 63;
+    if (threadIdx.x < 64) tw[k] = make_float2(L->twr[k], -L->twi[k]);      // exp(+2 pi j k / 64)
+    __syncthreads();
+    const int64_t sid = (int64_t)blockIdx.x * TXS + g;
+    const int f = (int)(sid / maxSlots), s = (int)(sid % maxSlots);
+    const bool live = f < nframes && s < plan[2 * (f < nframes ? f : 0)].nslots;
+    float2 v = make_float2(0.f, 0.f);
+    float scale = 0.f;
+    int shift = 48, csd = 0, nslots = 0;
+    double cfo = 0.0;
+    int64_t outOff = 0;
+    if (live) {
+        const TxPlan P0 = plan[2 * f];
+        nslots = P0.nslots; cfo = P0.cfo_step; outOff = P0.out_off;
+        const uint32_t scr[4] = { scrSeq.x, scrSeq.y, scrSeq.z, scrSeq.w };
+        const bool pilotBin = (k == 7 || k == 21 || k == 43 || k == 57);
+        const float pbase[4] = { 1.f, 1.f, 1.f, -1.f };
+        const int pslot = k == 43 ? 0 : k == 57 ? 1 : k == 7 ? 2 : 3;
+        if (s < 7) {                                                        // legacy part: as any two-antenna frame
+            if (t == 1) csd = 4;
+            if (s < 2) { v = tx_stf(k); scale = rsqrtf(12.f); shift = s == 0 ? 32 : 48; }
+            else if (s < 4) { v = make_float2(L->ltfL[k], 0.f); scale = rsqrtf(52.f); shift = s == 2 ? 32 : 48; }
+            else {
+                scale = rsqrtf(52.f);
+                const int c = L->sigDemap[k];
+                if (pilotBin) v = make_float2(pbase[pslot], 0.f);
+                else if (c >= 0) {
+                    const uint64_t bits = s == 4 ? (uint64_t)P0.lsig : P0.sig48;
+                    const int cc = c + (s == 6 ? 48 : 0);
+                    auto src = [&](int x) { return x < 0 ? 0 : (int)((bits >> x) & 1ull); };
+                    const float a = bcc_out(src, cc >> 1, cc & 1) ? 1.f : -1.f;
+                    v = s == 6 ? make_float2(0.f, a) : make_float2(a, 0.f);
+                }
+            }
+        } else {                                                            // VHT part: X_0, X_1 of this bin, then row t of Q
+            float2 xu[2];
+            scale = s == 7 ? rsqrtf(12.f) : rsqrtf(56.f);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const TxPlan& P = u ? plan[2 * f + 1] : P0;
+                float2 x = make_float2(0.f, 0.f);
+                if (s == 7) x = tx_stf(k);
+                else if (s < 10) {                                          // VHT-LTF l: P[u][l] on data tones, R[l] on pilot tones
+                    const int l = s - 8;
+                    const float sg = pilotBin ? (l == 1 ? -1.f : 1.f) : ((l == 1 && u == 0) ? -1.f : 1.f);
+                    x = make_float2(L->ltfNL[k] * sg, 0.f);
+                } else if (s == 10) {                                       // the user's own VHT-SIG-B
+                    const int d = L->binToDataNL[k];
+                    if (pilotBin) x = make_float2(pbase[pslot], 0.f);
+                    else if (d != 255) {
+                        const int c = L->deintNL[0][0][d];
+                        const uint32_t bits = P.sigb;
+                        auto src = [&](int y) { return y < 0 ? 0 : (int)((bits >> y) & 1u); };
+                        x = make_float2(bcc_out(src, c >> 1, c & 1) ? 1.f : -1.f, 0.f);
+                    }
+                } else {
+                    const int q = s - 11;
+                    const int d = L->binToDataNL[k];
+                    if (pilotBin) x = make_float2(L->pilotP[(4 + q) % 127] * pbase[(pslot + q) & 3], 0.f);
+                    else if (d != 255) x = tx_data_tone(L, P, psduAll + P.psdu_off, scr, eof, q, d, 0);     // each user is a one-stream frame
+                }
+                xu[u] = x;
+            }
+            const float2 w = tw[(8 * k) & 63];                              // stream 1: 400 ns = 8 samples (C_CYCLIC_SHIFT_NL)
+            xu[1] = make_float2(xu[1].x * w.x - xu[1].y * w.y, xu[1].x * w.y + xu[1].y * w.x);
+            const float2* __restrict__ q = Q + P0.q_off + 4 * ((k + 32) & 63) + 2 * t;     // Q[natural index][t][u]
+            const float2 q0 = q[0], q1 = q[1];
+            v = make_float2(q0.x * xu[0].x - q0.y * xu[0].y + q1.x * xu[1].x - q1.y * xu[1].y,
+                            q0.x * xu[0].y + q0.y * xu[0].x + q1.x * xu[1].y + q1.y * xu[1].x);
+        }
+    }
+    X[g][k] = v;
+    __syncthreads();
+    if (!live) return;
+    const float gsc = gain * scale * (1.0f / 64.0f) * 0.70710678118654752f;
+    tx_emit(X, tw, g, k, s, shift, csd, gsc, nslots, cfo, (t ? out1 : out0) + outOff + (int64_t)s * 80);
 }
 
 // Synthetic traffic: every frame gets its own random MPDU with a valid FCS (CRC-32 as tools/mac80211.py:36-47 appends it),
@@ -388,6 +551,19 @@ int c8b_tx_geometry_host(int format, int mcs, int len, int* nsym, int* nslots) {
 size_t c8b_tx_plan_bytes(int nframes) { return (size_t)nframes * sizeof(TxPlan); }
 
 int c8b_tx_nss_host(int format, int mcs) { return tx_nss(format, mcs); }
+
+int c8b_tx_mu_geometry_host(int mcs0, int len0, int mcs1, int len1, int* nsym, int* nslots) { return tx_mu_geometry(mcs0, len0, mcs1, len1, nsym, nslots); }
+
+void c8b_launch_tx_mu(const c8b_lut* lut, const c8b_txmu* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu, const float2* d_q,
+                      float2* d_out0, float2* d_out1, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st)
+{
+    if (nframes <= 0 || maxSlots <= 0) return;
+    TxPlan* plan = reinterpret_cast<TxPlan*>(d_plan);                       // two entries per frame
+    k_tx_plan_mu<<<(nframes + 127) / 128, 128, 0, st>>>(d_frames, nframes, plan);
+    const int64_t slots = (int64_t)nframes * maxSlots;
+    const dim3 grid((unsigned)((slots + TXS - 1) / TXS), 2);                // y = transmit antenna
+    k_tx_slots_mu<<<grid, TXS * 64, 0, st>>>(lut, plan, nframes, maxSlots, d_psdu, d_q, d_out0, d_out1, gain, make_uint4(scr[0], scr[1], scr[2], scr[3]), eof);
+}
 
 void c8b_launch_tx(const c8b_lut* lut, const c8b_txframe* d_frames, int nframes, int maxSlots, void* d_plan, const uint8_t* d_psdu,
                    float2* d_out, float2* d_out1, float gain, const uint32_t scr[4], uint32_t eof, cudaStream_t st)

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from ._cabi import C8bCfg, C8bError, FRAME_DTYPE, TXFRAME_DTYPE, ptr
+from ._cabi import C8bCfg, C8bError, FRAME_DTYPE, TXFRAME_DTYPE, TXMU_DTYPE, ptr
 
 
 def lut_blob():
@@ -210,6 +210,34 @@ class Receiver:
         _producer_sync()
         self._ck(self.L.c8b_tx_batch2_dev(self.h, C.c_void_p(d_psdu_ptr), psdu_bytes, ptr(desc), desc.size, multiplier, seed,
                                           C.c_void_p(d_iq0_ptr), C.c_void_p(d_iq1_ptr), iq_samples), "c8b_tx_batch2_dev")
+
+    def tx_mu_batch(self, ampdus, mcs, q, group_id=2, gap=400, cfo=None, multiplier=18.0, seed=93):
+        """two-user VHT MU-MIMO frames (tools/phy80211.py genAmpduMu + genFinalSig): ampdus = [(A-MPDU of user 0, of user 1), ...],
+        mcs = [(mcs0, mcs1), ...], q = complex array (64, 2, 2) -- or (nq, 64, 2, 2) with one set per frame -- of spatial mapping
+        matrices, subcarriers -32 .. 31, [antenna, user].  Returns (iq0, iq1, item offsets)."""
+        n = len(ampdus)
+        q = np.ascontiguousarray(np.asarray(q, np.complex64).reshape(-1, 64, 2, 2))
+        cfo = np.zeros(n, np.float32) if cfo is None else np.broadcast_to(np.asarray(cfo, np.float32), (n,))
+        d = np.zeros(n, TXMU_DTYPE)
+        offs = np.zeros(n + 1, np.int64)
+        po, parts = 0, []
+        for i, (a0, a1) in enumerate(ampdus):
+            ns = self.L.c8b_tx_mu_nsamp(int(mcs[i][0]), len(a0), int(mcs[i][1]), len(a1))
+            if ns < 0:
+                raise ValueError("unsupported MU frame: mcs %s, A-MPDU lengths %d / %d" % (mcs[i], len(a0), len(a1)))
+            d[i]["mcs"] = mcs[i]
+            d[i]["psdu_len"] = (len(a0), len(a1))
+            d[i]["psdu_off"] = (po, po + len(a0))
+            d[i]["group_id"], d[i]["cfo_hz"], d[i]["out_off"], d[i]["q_index"] = group_id, cfo[i], offs[i] + gap, i if q.shape[0] == n and n > 1 else 0
+            offs[i + 1] = offs[i] + 2 * gap + ns
+            po += len(a0) + len(a1)
+            parts += [bytes(a0), bytes(a1)]
+        arena = np.frombuffer(b"".join(parts) + b"\0", np.uint8).copy()
+        iq0 = np.zeros(int(offs[-1]), np.complex64)
+        iq1 = np.zeros(int(offs[-1]), np.complex64)
+        self._ck(self.L.c8b_tx_mu_batch(self.h, ptr(arena), arena.size, ptr(d), d.size, ptr(q.view(np.float32)), q.shape[0], multiplier, seed,
+                                        ptr(iq0.view(np.float32)), ptr(iq1.view(np.float32)), iq0.size), "c8b_tx_mu_batch")
+        return iq0, iq1, offs
 
     def tx_from_udp(self, datagrams, gap=400, multiplier=12.0, seed=93):
         """MAC -> PHY datagrams [format][mcs][nss][len16 LE][PSDU] (lib/pktgen_impl.cc:57-70, tools/phy80211.py genPktGrData) ->

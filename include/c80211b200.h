@@ -289,6 +289,28 @@ int  c8b_tx_batch2(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, cons
 int  c8b_tx_batch2_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txframe* frames, int nframes, float multiplier,
                        int scrambler_seed, float* d_iq0, float* d_iq1, int64_t iq_samples);
 
+/* Two-user VHT MU-MIMO transmit waveform (tools/phy80211.py:180-221 genAmpduMu, :571-633 VHT-SIG-B per
+ * user, :763-786 data symbols through the spatial mapping; lib/encode2_impl.cc / lib/modulation2_impl.cc carry the same frame in the
+ * reference's TX flowgraph, tools/cmu_ap.py drives it).  One space-time stream per user, each with its own A-MPDU (a multiple of
+ * 4 bytes) and VHT MCS 0-8, padded to the common symbol count; from the VHT-STF on, antenna t of subcarrier k carries
+ * sum_u Q[k][t][u] * X_u[k].  q: nq sets of 64 x 2 x 2 complex floats (re, im), subcarriers in the order -32 .. 31, row = antenna,
+ * column = user -- the bfQ list of the generator.  A station receives its frame with cfg.mupos = its user position and
+ * cfg.mugid = group_id (lib/demod_impl.cc:238-249). */
+typedef struct c8b_txmu {
+    int32_t mcs[2];        /* VHT MCS of user 0 / 1                                                     */
+    int32_t psdu_len[2];   /* A-MPDU bytes of user 0 / 1 (4 .. 4092, multiple of 4)                     */
+    int64_t psdu_off[2];   /* their byte offsets in the PSDU arena                                       */
+    int32_t group_id;      /* 1 .. 62                                                                   */
+    float   cfo_hz;
+    int64_t out_off;       /* first sample of the frame in both antenna arenas                          */
+    int64_t q_index;       /* which of the nq matrix sets this frame is mapped with                     */
+} c8b_txmu;
+int  c8b_tx_mu_nsamp(int mcs0, int len0, int mcs1, int len1);
+int  c8b_tx_mu_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* h_q, int nq,
+                     float multiplier, int scrambler_seed, float* h_iq0, float* h_iq1, int64_t iq_samples);
+int  c8b_tx_mu_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* d_q, int nq,
+                         float multiplier, int scrambler_seed, float* d_iq0, float* d_iq1, int64_t iq_samples);
+
 /* synthetic traffic for closed-loop runs: fills every frame's PSDU region (device memory) with a random MPDU carrying a valid
  * FCS (tools/mac80211.py:36-47); VHT regions (psdu_len a multiple of 4) get the one-MPDU A-MPDU delimiter of
  * tools/mac80211.py:333-360 in front.  A frame decoded by the receive path returns exactly these bytes. */

@@ -15,6 +15,9 @@ container (needs /root/reference); the GPU box and the test-suite only read the 
   frames_mu.npz       VHT NDP (2 transmit streams, one receive antenna) and 2-user MU-MIMO frames seen at each user
                       position (tools/cmu_ap.py recipe with a flat 2x2 channel and its zero-forcing precoder).
 
+  frames_mu_tx.npz    2-user MU-MIMO frames as TRANSMITTED (both antennas), their A-MPDUs and the per-subcarrier spatial
+                      mapping matrices: the MU side of the transmit synthesiser.
+
   frames_tx.npz       the PSDU bytes behind frames_siso / frames_bench (inputs of genFromMpdu / genFromAmpdu) for the
                       transmit synthesiser test.
 
@@ -259,6 +262,41 @@ def frames_mu():
     print("frames_mu: %d items, %d samples; meta = (3 NDP | 4 MU, mcs, cfo | user position)" % (len(items), offs[-1]))
 
 
+def frames_mu_tx():
+    """Two-user VHT MU-MIMO frames as the access point TRANSMITS them (genAmpduMu, tools/phy80211.py:180-221): both antenna
+    waveforms, the A-MPDUs of the two users and the per-subcarrier spatial-mapping matrices -- for the MU side of the transmit
+    synthesiser (c8b_tx_mu_batch).  Q differs from subcarrier to subcarrier so its indexing is pinned too."""
+    phy = phy80211.phy80211(ifDebug=False)
+    rng = np.random.default_rng(8021111)
+    bfQ = []
+    for k in range(64):
+        a = rng.normal(0, 1, (2, 2)) + 1j * rng.normal(0, 1, (2, 2))
+        a = a / np.linalg.norm(a) * np.sqrt(2)
+        bfQ.append(a)
+    pk = [mac_ampdu(["1234567 packet for station 000"]), mac_ampdu(["7654321 packet for station 111", "and a second subframe"])]
+    iq0, iq1, meta = [], [], []
+    for mcs0, mcs1, cfo in ((0, 0, 0.0), (4, 2, 0.0), (7, 8, 35e3), (1, 5, 0.0)):
+        quiet(phy.genAmpduMu, nUser=2, bfQ=bfQ, groupId=2, ampdu0=pk[0], mod0=p8h.modulation(p8h.F.VHT, mcs0, p8h.BW.BW20, 1, False),
+              ampdu1=pk[1], mod1=p8h.modulation(p8h.F.VHT, mcs1, p8h.BW.BW20, 1, False))
+        ss = quiet(phy.genFinalSig, multiplier=18.0, cfoHz=cfo, num=1, gap=True, gapLen=400)
+        iq0.append(np.asarray(ss[0], np.complex64)); iq1.append(np.asarray(ss[1], np.complex64)); meta.append((mcs0, mcs1, cfo))
+    offs = np.cumsum([0] + [len(x) for x in iq0]).astype(np.int64)
+    # the same two A-MPDUs through a zero-forcing precoder and the flat channel of frames_mu, as each station receives them:
+    # what the reference's receive chain makes of user 1's TWO-subframe A-MPDU (tests/test_ref_chain.py)
+    H = np.array([[1.0, 0.5 * np.exp(0.9j)], [0.6 * np.exp(-0.4j), 0.9 * np.exp(2.0j)]])
+    Qz = H.conj().T @ np.linalg.inv(H @ H.conj().T)
+    Qz = Qz / np.linalg.norm(Qz) * np.sqrt(2)
+    quiet(phy.genAmpduMu, nUser=2, bfQ=[Qz.copy() for _ in range(64)], groupId=2, ampdu0=pk[0], mod0=p8h.modulation(p8h.F.VHT, 0, p8h.BW.BW20, 1, False),
+          ampdu1=pk[1], mod1=p8h.modulation(p8h.F.VHT, 0, p8h.BW.BW20, 1, False))
+    ss = [np.asarray(x, np.complex128) for x in quiet(phy.genFinalSig, multiplier=18.0, cfoHz=0.0, num=1, gap=True, gapLen=400)]
+    zf = [(H[u, 0] * ss[0] + H[u, 1] * ss[1]).astype(np.complex64) for u in range(2)]
+    np.savez_compressed(os.path.join(HERE, "frames_mu_tx.npz"), iq0=np.concatenate(iq0), iq1=np.concatenate(iq1), offs=offs,
+                        meta=np.array(meta, np.float64), q=np.array(bfQ).astype(np.complex64),
+                        ampdu0=np.frombuffer(bytes(pk[0]), np.uint8), ampdu1=np.frombuffer(bytes(pk[1]), np.uint8),
+                        zf_rx0=zf[0], zf_rx1=zf[1])
+    print("frames_mu_tx: %d frames, %d samples per antenna, A-MPDUs of %d / %d bytes" % (len(iq0), offs[-1], len(pk[0]), len(pk[1])))
+
+
 def frames_tx():
     """The PSDUs (MPDU for legacy / HT, A-MPDU for VHT) behind the waveforms of frames_siso.npz and frames_bench.npz, in the
     same order, so the transmit synthesiser (c8b_tx_batch) can be compared with the generator's samples."""
@@ -340,9 +378,11 @@ def ref_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi", "sgi_true", "mu", "tx"]
+    which = sys.argv[1:] or ["siso", "bench", "ref", "mimo", "564", "sgi", "sgi_true", "mu", "mu_tx", "tx"]
     if "mu" in which:
         frames_mu()
+    if "mu_tx" in which:
+        frames_mu_tx()
     if "tx" in which:
         frames_tx()
     if "siso" in which:

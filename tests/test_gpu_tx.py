@@ -274,3 +274,67 @@ def test_two_stream_loopback_random_traffic(fmt, codes):
         if i % 5 == 0:
             _, _, po = ol.rx_item2(a[offs[i]:offs[i + 1]], b[offs[i]:offs[i + 1]], max_frames=1)
             assert bytes(po) == bytes(pdu[i, :po.size])
+
+
+def _mu_golden():
+    return np.load(HERE + "/golden/frames_mu_tx.npz")
+
+
+def test_mu_waveforms_equal_the_generator():
+    """c8b_tx_mu_batch against tools/phy80211.py genAmpduMu + genFinalSig (golden frames_mu_tx.npz: two users, MCS pairs
+    (0,0) (4,2) (7,8) (1,5), different A-MPDU lengths, a spatial mapping matrix that differs on every subcarrier, one CFO
+    case): both antennas sample for sample"""
+    pkg = load_pkg()
+    g = _mu_golden()
+    a0, a1 = bytes(g["ampdu0"]), bytes(g["ampdu1"])
+    mcs = [(int(m[0]), int(m[1])) for m in g["meta"]]
+    cfo = g["meta"][:, 2].astype(np.float32)
+    rx = pkg.Receiver(device=0)
+    iq0, iq1, offs = rx.tx_mu_batch([(a0, a1)] * len(mcs), mcs, g["q"], group_id=2, gap=400, cfo=cfo, multiplier=18.0)
+    rx.close()
+    assert np.array_equal(offs, g["offs"])
+    peak = float(np.max(np.abs(g["iq0"])))
+    for i in range(len(mcs)):
+        for a, (got, ref) in enumerate(((iq0, g["iq0"]), (iq1, g["iq1"]))):
+            err = float(np.max(np.abs(got[offs[i]:offs[i + 1]] - ref[offs[i]:offs[i + 1]])))
+            assert err <= (2e-6 if cfo[i] == 0 else 2e-5) * peak, (i, a, mcs[i], err / peak)
+
+
+def test_mu_loopback_each_station_gets_its_frame():
+    """access point -> flat 2x2 channel -> the two stations (tools/cmu_ap.py's recipe): frames precoded with the zero-forcing
+    Q = H^H (H H^H)^-1 reach station u as its own stream; demod(mupos = u, mugid) + decode return user u's first MPDU, and
+    exactly the PDU bytes of the oracle's chain on the same samples.  (Of a two-subframe A-MPDU the reference's MU receive
+    path publishes the first subframe only -- its own blocks and the oracle agree on that, tests/test_ref_chain.py.)"""
+    pkg = load_pkg()
+    g = _mu_golden()
+    a = [bytes(g["ampdu0"]), bytes(g["ampdu1"])]
+    H = np.array([[1.0, 0.5 * np.exp(0.9j)], [0.6 * np.exp(-0.4j), 0.9 * np.exp(2.0j)]])
+    Q = H.conj().T @ np.linalg.inv(H @ H.conj().T)
+    Q = Q / np.linalg.norm(Q) * np.sqrt(2)
+    q = np.broadcast_to(Q.astype(np.complex64), (64, 2, 2)).copy()
+    pairs = [(0, 0), (3, 1), (5, 7), (8, 4), (2, 6)]
+    tx = pkg.Receiver(device=0)
+    iq0, iq1, offs = tx.tx_mu_batch([(a[0], a[1])] * len(pairs), pairs, q, group_id=2, gap=400, multiplier=18.0)
+    tx.close()
+    rng = np.random.default_rng(77)
+    O = ol.oracle()
+    try:
+        for u in range(2):
+            y = (H[u, 0] * iq0.astype(np.complex128) + H[u, 1] * iq1.astype(np.complex128))
+            y = (y + 1e-3 * (rng.standard_normal(y.size) + 1j * rng.standard_normal(y.size))).astype(np.complex64)
+            rx = pkg.Receiver(device=0, mupos=u, mugid=2)
+            fr, pdu = rx.rx_batch(y, offs[:-1], np.diff(offs).astype(np.int32), pdu_stride=4400)
+            rx.close()
+            p = a[u]
+            n0 = (p[0] >> 4) | (p[1] << 4) | (((p[0] >> 2) & 3) << 12)      # first subframe of the station's A-MPDU
+            first = p[4:4 + n0]
+            O.orx_set_mupos(u)
+            for i in range(len(pairs)):
+                fo, _, po = ol.rx_item(y[offs[i]:offs[i + 1]], max_frames=1)
+                assert fr[i]["status"] == 0 and fr[i]["format"] == 2 and fr[i]["mcs"] == pairs[i][u], (u, i, fr[i]["status"], fr[i]["mcs"])
+                nb = int(fr[i]["pdu_bytes"])
+                assert nb == fo[0]["pdu_bytes"] and bytes(pdu[i, :nb]) == bytes(po[:nb]), (u, i)
+                recs = pkg.rx.split_pdus(pdu[i, :nb])
+                assert len(recs) >= 1 and recs[0][3:-1] == first, (u, i, len(recs))
+    finally:
+        O.orx_set_mupos(0)

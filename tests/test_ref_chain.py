@@ -82,6 +82,17 @@ def test_mu_mimo_and_ndp(golden, mupos):
     assert info["statuses"][:2] == [7, 7] and info["messages"] == 4
 
 
+@pytest.mark.parametrize("mupos", [0, 1])
+def test_mu_mimo_two_subframe_ampdu(mupos):
+    """a 2-user frame whose user 1 carries a TWO-subframe A-MPDU (golden frames_mu_tx.npz zf_rx*: the generator's frame through a
+    zero-forcing precoder and a flat channel): the reference's blocks publish ONE message per station -- in the MU receive path
+    the walk over the A-MPDU ends after the first subframe -- and the oracle restates exactly that"""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames_mu_tx.npz"))
+    bad, info = ol.chain_vs_oracle(g["zf_rx%d" % mupos], mupos=mupos, mugid=2, max_frames=4)
+    _check(bad, info)
+    assert info["frames"] == 1 and info["statuses"] == [0] and info["messages"] == 1
+
+
 def test_short_gi_every_symbol():
     """72-sample raster: every symbol's soft bits of the reference's demod equal the oracle's"""
     g = np.load(os.path.join(HERE, "golden", "frames_sgi.npz"))
