@@ -93,6 +93,8 @@ SYMBOLS = [
     ("c8b_tx_batch2", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
     ("c8b_tx_batch2_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
     ("c8b_tx_mu_nsamp", _i, [_i, _i, _i, _i]),
+    ("c8b_tx_udp_parse_mu", _i, [_vp, _i, _vp, _vp, _vp]),
+    ("c8b_tx_udp_parse_bfq", _i, [_vp, _i, _vp]),
     ("c8b_tx_mu_batch", _i, [_vp, _vp, _i64, _vp, _i, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
     ("c8b_tx_mu_batch_dev", _i, [_vp, _vp, _i64, _vp, _i, _vp, _i, C.c_float, _i, _vp, _vp, _i64]),
     ("c8b_tx_random_psdu_dev", _i, [_vp, _vp, _i64, _vp, _i, C.c_uint64]),

@@ -1147,6 +1147,26 @@ int c8b_tx_mu_nsamp(int mcs0, int len0, int mcs1, int len1)
     return c8b_tx_mu_geometry_host(mcs0, len0, mcs1, len1, &nsym, &nslots) ? nslots * 80 : C8B_ERR_ARG;
 }
 
+int c8b_tx_udp_parse_mu(const uint8_t* pkt, int pkt_len, c8b_txmu* f, const uint8_t** psdu0, const uint8_t** psdu1)
+{
+    if (!pkt || !f || pkt_len < 10 || pkt[0] != 3) return C8B_ERR_ARG;
+    const int mcs0 = pkt[1], nss0 = pkt[2], len0 = pkt[3] | (pkt[4] << 8), mcs1 = pkt[5], nss1 = pkt[6], len1 = pkt[7] | (pkt[8] << 8), gid = pkt[9];
+    if (len0 + len1 > 4095 || pkt_len < len0 + len1 + 10) return C8B_ERR_ARG;     // pktPop :127-130
+    if (nss0 != 1 || nss1 != 1 || gid < 1 || gid > 62 || c8b_tx_mu_nsamp(mcs0, len0, mcs1, len1) < 0) return C8B_ERR_ARG;
+    memset(f, 0, sizeof(*f));
+    f->mcs[0] = mcs0; f->mcs[1] = mcs1; f->psdu_len[0] = len0; f->psdu_len[1] = len1; f->group_id = gid;
+    if (psdu0) *psdu0 = pkt + 10;
+    if (psdu1) *psdu1 = pkt + 10 + len0;
+    return C8B_OK;
+}
+
+int c8b_tx_udp_parse_bfq(const uint8_t* pkt, int pkt_len, float* q_out)
+{
+    if (!pkt || !q_out || pkt_len != 2049 || pkt[0] != 10) return C8B_ERR_ARG;  // C8P_F_VHT_BFQ, exactly 256 complex floats
+    memcpy(q_out, pkt + 1, 2048);
+    return C8B_OK;
+}
+
 static int tx_run_mu(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* d_q, int nq,
                      float multiplier, int seed, float* d_iq0, float* d_iq1, int64_t iq_samples)
 {

@@ -306,6 +306,15 @@ typedef struct c8b_txmu {
     int64_t q_index;       /* which of the nq matrix sets this frame is mapped with                     */
 } c8b_txmu;
 int  c8b_tx_mu_nsamp(int mcs0, int len0, int mcs1, int len1);
+/* the MAC -> PHY datagrams of the MU demo (host only, no GPU): the two-user frame
+ *     [3][mcs0][nss0][len0:2 LE][mcs1][nss1][len1:2 LE][group id][A-MPDU 0][A-MPDU 1]
+ * (lib/pktgen_impl.cc:101-113 pktPop, written by tools/phy80211.py:1139-1161 genPktGrDataMu) -> mcs / psdu_len / group_id of *f,
+ * *psdu0 / *psdu1 = the A-MPDUs inside pkt; C8B_ERR_ARG for a malformed datagram (pktPop's checks) or one the synthesiser does
+ * not make (nss != 1, lengths that are not multiples of 4); and the spatial mapping update
+ *     [10][64 x 2 x 2 x (re, im) float32]      (2049 bytes; lib/modulation2_impl.cc:117-121, tools/phy80211.py:1163-1171)
+ * -> q_out[512], one matrix set in the layout c8b_tx_mu_batch takes. */
+int  c8b_tx_udp_parse_mu(const uint8_t* pkt, int pkt_len, c8b_txmu* f, const uint8_t** psdu0, const uint8_t** psdu1);
+int  c8b_tx_udp_parse_bfq(const uint8_t* pkt, int pkt_len, float* q_out);
 int  c8b_tx_mu_batch(c8b_ctx* ctx, const uint8_t* h_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* h_q, int nq,
                      float multiplier, int scrambler_seed, float* h_iq0, float* h_iq1, int64_t iq_samples);
 int  c8b_tx_mu_batch_dev(c8b_ctx* ctx, const uint8_t* d_psdu, int64_t psdu_bytes, const c8b_txmu* frames, int nframes, const float* d_q, int nq,

@@ -168,3 +168,39 @@ def test_tx_udp_parse_follows_pktgen():
     assert parse(struct.pack("<BBBH", 1, 3, 2, 10) + bytes(10))[0] < 0       # HT MCS3 is one stream
     assert parse(struct.pack("<BBBH", 2, 5, 3, 12) + bytes(12))[0] < 0       # three streams
     assert parse(struct.pack("<BBBH", 0, 9, 1, 10) + bytes(10))[0] < 0       # no legacy MCS 9
+
+
+def test_tx_udp_parse_mu_and_bfq():
+    """the MU demo's datagrams (tools/phy80211.py:1139-1171 genPktGrDataMu / genPktGrBfQ; lib/pktgen_impl.cc:101-113,
+    lib/modulation2_impl.cc:117-121), host-side parsers, no GPU needed"""
+    import ctypes as C
+    import struct
+    pkg = load_pkg()
+    L = pkg._cabi.lib()
+    f = np.zeros(1, pkg.TXMU_DTYPE)
+    p0, p1 = C.c_void_p(), C.c_void_p()
+
+    def parse(b):
+        buf = (C.c_ubyte * max(len(b), 1)).from_buffer_copy(bytes(b))
+        rc = L.c8b_tx_udp_parse_mu(buf, len(b), f.ctypes.data, C.byref(p0), C.byref(p1))
+        return rc, ((p0.value - C.addressof(buf), p1.value - C.addressof(buf)) if rc == 0 else None)
+
+    a0, a1 = bytes(range(100)), bytes(range(192))
+    hdr = lambda m0, n0, l0, m1, n1, l1, g: struct.pack("<BBBHBBHB", 3, m0, n0, l0, m1, n1, l1, g)
+    rc, o = parse(hdr(4, 1, len(a0), 2, 1, len(a1), 2) + a0 + a1)            # genPktGrDataMu
+    assert rc == 0 and o == (10, 110)
+    assert f[0]["mcs"].tolist() == [4, 2] and f[0]["psdu_len"].tolist() == [100, 192] and f[0]["group_id"] == 2
+    assert parse(hdr(4, 1, 100, 2, 1, 192, 2) + a0 + a1[:-1])[0] < 0          # shorter than the two length fields say (pktPop :127-130)
+    assert parse(hdr(4, 1, 2048, 2, 1, 2048, 2) + bytes(4096))[0] < 0         # more than 4095 bytes in all
+    assert parse(hdr(4, 2, 100, 2, 1, 192, 2) + a0 + a1)[0] < 0               # two streams for one user: not synthesised
+    assert parse(hdr(9, 1, 100, 2, 1, 192, 2) + a0 + a1)[0] < 0               # no VHT MCS 9 at 20 MHz
+    assert parse(hdr(4, 1, 100, 2, 1, 192, 0) + a0 + a1)[0] < 0               # group id 0 is single user
+    assert parse(hdr(4, 1, 98, 2, 1, 192, 2) + a0[:98] + a1)[0] < 0           # an A-MPDU is a multiple of 4 bytes
+    assert parse(struct.pack("<BBBH", 2, 0, 1, 8) + bytes(8))[0] < 0          # not an MU datagram
+    rng = np.random.default_rng(5)
+    q = (rng.normal(0, 1, (64, 2, 2)) + 1j * rng.normal(0, 1, (64, 2, 2))).astype(np.complex64)
+    pkt = bytes([10]) + b"".join(struct.pack("<ff", float(q[k, i, j].real), float(q[k, i, j].imag)) for k in range(64) for i in range(2) for j in range(2))
+    out = np.zeros(512, np.float32)
+    buf = (C.c_ubyte * len(pkt)).from_buffer_copy(pkt)
+    assert L.c8b_tx_udp_parse_bfq(buf, len(pkt), out.ctypes.data) == 0 and np.array_equal(out.view(np.complex64).reshape(64, 2, 2), q)
+    assert L.c8b_tx_udp_parse_bfq(buf, len(pkt) - 1, out.ctypes.data) < 0     # lib/modulation2_impl.cc:117: exactly 2049 bytes
