@@ -23,11 +23,13 @@ constexpr unsigned FULL = 0xffffffffu;
 struct __align__(16) Ws {                       // per-warp workspace
     float2 A[256];                              // complex scratch: products / rotated windows / spectra
     float2 B[256];
-    float4 Lg[112];                             // per-lag (msum.re, msum.im, s1, s2)
+    union {
+        float4 Lg[112];                         // per-lag (msum.re, msum.im, s1, s2): sync only, which runs no DFT
+        float2 X[4][72];                        // DFT transposes (row stride 9)
+    };
     float F[256];                               // float scratch: powers / ac / soft bits
     float M[2][64];                             // Viterbi metrics
     uint32_t Dec[48][2];                        // Viterbi decisions
-    float2 X[4][72];                            // DFT transposes (row stride 9)
 };
 
 struct cpx { float x, y; };
@@ -300,7 +302,7 @@ __device__ __forceinline__ int walk_word(TrigState& ts, const uint32_t m, int& k
     return -1;
 }
 
-__global__ void __launch_bounds__(FW * 32)
+__global__ void __launch_bounds__(FW * 32, 6)
 k_detect_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off,
            const int32_t* __restrict__ len, int nitems, int itemBase, int maxf, int64_t outBase, const float* __restrict__ preacAll,
            const uint32_t* __restrict__ maskAll, int maskStride, c8b_frame* __restrict__ frames, float2* __restrict__ chan)
@@ -680,7 +682,7 @@ struct RotW {
     }
 };
 
-__global__ void __launch_bounds__(FW * 32)
+__global__ void __launch_bounds__(FW * 32, 6)
 k_header_w(const c8b_lut* __restrict__ lut, const float2* __restrict__ iq, const int64_t* __restrict__ off, int nslots, int maxf,
            int mupos, c8b_frame* __restrict__ frames, const float2* __restrict__ chan, float2* __restrict__ hinvAll, int64_t llrStride,
            float* __restrict__ llrAll)
