@@ -14,6 +14,9 @@ namespace {
 
 using c8b::cf;
 
+#ifndef C8B_PRESISO_CTAS
+#define C8B_PRESISO_CTAS 6
+#endif
 constexpr int PWARPS = 4;           // warps per CTA, each sweeping its own segment
 constexpr int PSEG = 160;           // rows (32 samples) of output per warp segment
 constexpr int PDEPTH = 4;           // rows of iq in flight per warp = rows per unrolled group
@@ -87,7 +90,7 @@ __device__ __forceinline__ void presiso_row(PState& S, const float2 c, const int
 // does not start the item first runs one group of history rows (3 are needed: x[i-16] of the products, the 15-sample
 // tree, the 48 lag) without output.
 template <bool CONJ, bool MASK>
-__global__ void __launch_bounds__(PWARPS * 32, 6)
+__global__ void __launch_bounds__(PWARPS * 32, C8B_PRESISO_CTAS)
 k_presiso(const float2* __restrict__ iq, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int nitems, int nseg,
           int64_t outBase, float* __restrict__ preac, float2* __restrict__ preconj, uint32_t* __restrict__ mask, int maskStride)
 {
