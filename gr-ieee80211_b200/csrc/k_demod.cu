@@ -12,7 +12,7 @@
 // W64^(j*k1), the 8x8 transpose goes through padded (conflict-free) shared memory, and a second
 // 8-point DFT leaves thread k1 with bins k1+8*k2.  LLRs are scattered through the deinterleaver -- in closed form: a
 // per-thread table entry gives each data tone's base position and rotation, no map is staged or looked up -- into
-// a shared-memory line per symbol and leave the SM as 16-byte coalesced stores.
+// a shared-memory line per symbol and leave the SM as one bulk copy per warp (cp.async.bulk, see bulk_store).
 #include "common.cuh"
 
 namespace {
