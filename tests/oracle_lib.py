@@ -410,3 +410,23 @@ def chain_vs_oracle(iq0, iq1=None, mupos=0, mugid=0, max_frames=64, seed=0, max_
     info = dict(frames=len(frames), messages=len(msgs), soft_bits=nllr, calls=c.calls(), statuses=[int(f["status"]) for f in frames])
     c.close()
     return bad, info
+
+
+def colliding_captures(g, rng, n=10, snr=28):
+    """captures in which a second frame starts INSIDE the first (its preamble over the payload, over the SIG fields, or right
+    behind the preamble) and a third follows closely: what trigger / sync hold-off / signal's S_COPY swallow make of it"""
+    iq, offs = g["iq"], g["offs"]
+    out = []
+    for _ in range(n):
+        a, b, c = (int(v) for v in rng.integers(1, len(offs) - 1, 3))
+        fa, fb, fc = (iq[offs[k]:offs[k + 1]] for k in (a, b, c))
+        d1 = int(rng.choice([200, 330, 420, 700, 1500, fa.size // 2]))
+        d2 = d1 + int(rng.integers(300, fb.size + 400))
+        x = np.zeros(max(fa.size, d1 + fb.size, d2 + fc.size) + 200, np.complex64)
+        x[:fa.size] += fa
+        x[d1:d1 + fb.size] += np.complex64(rng.uniform(0.3, 1.5)) * fb
+        x[d2:d2 + fc.size] += np.complex64(rng.uniform(0.3, 1.5)) * fc
+        sg = 0.1875 / np.sqrt(2 * 10 ** (snr / 10))
+        r2 = np.random.default_rng(int(rng.integers(1 << 30)))
+        out.append((x + sg * (r2.standard_normal(x.size) + 1j * r2.standard_normal(x.size))).astype(np.complex64))
+    return out

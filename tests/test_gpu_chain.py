@@ -170,3 +170,58 @@ def test_sc16_ingest_equals_fc32_on_the_widened_capture(golden):
         rx.close()
         assert fa.tobytes() == fb.tobytes() == fc.tobytes() and np.array_equal(pa, pb) and np.array_equal(pb, pc)
         assert int((fa["npdu"] == 1).sum()) >= 30
+
+
+@pytest.mark.parametrize("frontend_mode,nitems", [(0, 10), (0, 70), (1, 10)])
+def test_colliding_frames_vs_oracle(golden, frontend_mode, nitems):
+    """a second frame starting inside the first, a third close behind (tests/oracle_lib.py colliding_captures; the reference's
+    own blocks equal the oracle on the same recipe, tests/test_ref_chain.py): the trigger inside a payload, sync's hold-off and
+    signal's swallow rule on all three detect kernels -- the segment-parallel scan (few items), the warp-per-item kernel
+    (> 64 items) and the one-thread kernel -- and through the stream session in pieces"""
+    pkg = load_pkg()
+    caps = ol.colliding_captures(golden["frames_siso"], np.random.default_rng(4242 + nitems), n=nitems)
+    off = np.cumsum([0] + [c.size for c in caps]).astype(np.int64)
+    iq = np.concatenate(caps)
+    MF = 8
+    rx = pkg.Receiver(device=0, max_frames=MF, frontend_mode=frontend_mode)
+    fr, pdu = rx.rx_batch(iq, off[:-1], np.diff(off).astype(np.int32), pdu_stride=4400)
+    rx.close()
+    nf = 0
+    for it, x in enumerate(caps[:24]):
+        fo, _, po = ol.rx_item(x, max_frames=MF)
+        recs = ol.split_pdus(po)
+        r = 0
+        for k in range(MF):
+            s = it * MF + k
+            if k >= len(fo):
+                assert fr[s]["status"] == 9 or (k == 0 and len(fo) == 0), (it, k, fr[s]["status"])
+                continue
+            for key in ("status", "sync_idx", "trig_idx", "format", "mcs", "len", "nsym", "npdu", "pdu_bytes"):
+                assert fr[s][key] == fo[k][key], (it, k, key, fr[s][key], fo[k][key])
+            got = ol.split_pdus(bytes(pdu[s, :fr[s]["pdu_bytes"]]))
+            assert got == recs[r:r + len(got)], (it, k)
+            r += len(got)
+            nf += 1
+    assert nf >= min(nitems, 24)
+    if nitems == 10 and frontend_mode == 0:                                  # the same captures as a live stream, pushed in pieces
+        rx = pkg.Receiver(device=0, max_frames=64, chunk_items=1)
+        for it, x in enumerate(caps[:6]):
+            fo, _, po = ol.rx_item(x, max_frames=16)
+            rx.stream_begin(1, 1 << 16)
+            got, rng = [], np.random.default_rng(it)
+            k = 0
+            while k < x.size:
+                n = int(rng.integers(500, 4000))
+                f2, base, p2 = rx.stream_push(x[k:k + n], flush=k + n >= x.size, frames_cap=64)
+                for q in range(f2.size):
+                    got.append((int(base[q]) + int(f2[q]["sync_idx"]), int(f2[q]["status"]), bytes(p2[q, :f2[q]["pdu_bytes"]])))
+                k += n
+            want = []
+            recs, r = ol.split_pdus(po), 0
+            for f in fo:
+                npd = int(f["npdu"])
+                want.append((int(f["sync_idx"]), int(f["status"]), b"".join(recs[r:r + npd])))
+                r += npd
+            assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in want], (it, got[:3], want[:3])
+            assert [c for _, _, c in got] == [c for _, _, c in want], it
+        rx.close()

@@ -62,6 +62,16 @@ def test_siso_truncated_and_piecewise(golden):
     assert 4 in seen and 0 in seen          # frames cut short (S_COPY never finishes) and whole ones
 
 
+def test_colliding_frames(golden):
+    rng = np.random.default_rng(4242)
+    nf = 0
+    for k, x in enumerate(ol.colliding_captures(golden["frames_siso"], rng)):
+        bad, info = ol.chain_vs_oracle(x, seed=k, max_call=2500 if k & 1 else 0, max_frames=16)
+        _check(bad, info)
+        nf += info["frames"]
+    assert nf >= 10
+
+
 @pytest.mark.parametrize("snr,seed,max_call", [(None, 0, 0), (25, 1, 0), (10, 3, 1700)])
 def test_2x2_capture(golden, snr, seed, max_call):
     """signal2 / demod2: HT MCS8-15 and VHT 2SS frames, both antennas"""
