@@ -406,3 +406,32 @@ def test_maximum_length_two_stream_frames(fmt, code, ln):
         assert fr[0]["status"] == 6 and fr[0]["npdu"] == 0
     else:
         assert fr[0]["status"] == 0 and fr[0]["nss"] == 2 and fr[0]["npdu"] == 1 and bytes(pdu[0, 3:nb - 1]) == mpdu
+
+
+@pytest.mark.parametrize("cfo", [-232e3, -150e3, 232e3])
+def test_loopback_at_the_carrier_offset_limit(cfo):
+    """+-232 kHz (40 ppm between two 5.8 GHz radios, the standard's worst case): sync's estimate, the rotation fused into the
+    demod kernels and the oracle's agree frame for frame at every format"""
+    pkg = load_pkg()
+    rng = np.random.default_rng(int(abs(cfo)) + (cfo > 0))
+    ps, fm, ms = [], [], []
+    for fmt, mcs in ((0, 0), (0, 4), (0, 7), (1, 2), (1, 7), (2, 0), (2, 5), (2, 8)):
+        body = bytes(rng.integers(0, 256, int(rng.integers(60, 900)), dtype=np.uint8))
+        mpdu = body + (__import__("zlib").crc32(body) & 0xffffffff).to_bytes(4, "little")
+        ps.append(_one_mpdu_ampdu(mpdu) if fmt == 2 else mpdu)
+        fm.append(fmt)
+        ms.append(mcs)
+    rx = pkg.Receiver(device=0)
+    iq, offs = rx.tx_batch(ps, fm, ms, gap=300, cfo=[cfo] * len(ps))
+    s = 0.1875 / np.sqrt(2 * 10 ** 3.2)
+    x = (iq + s * (rng.standard_normal(iq.size) + 1j * rng.standard_normal(iq.size))).astype(np.complex64)
+    fr, pdu = rx.rx_batch(x, offs[:-1], np.diff(offs).astype(np.int32))
+    rx.close()
+    for i in range(len(ps)):
+        fo, _, po = ol.rx_item(x[offs[i]:offs[i + 1]], max_frames=1)
+        for k in ("status", "sync_idx", "format", "mcs", "len", "npdu", "pdu_bytes"):
+            assert fr[i][k] == fo[0][k], (i, k, fr[i][k], fo[0][k])
+        assert abs(fr[i]["cfo_hz"] - fo[0]["cfo_hz"]) <= 1e-6 * 20e6 / (2 * np.pi) + 1e-3 * abs(fo[0]["cfo_hz"]) * 1e-3
+        nb = int(fr[i]["pdu_bytes"])
+        assert bytes(pdu[i, :nb]) == bytes(po[:nb]), i
+        assert fr[i]["status"] == 0 and fr[i]["npdu"] == 1 and abs(fr[i]["cfo_hz"] + cfo) < 3e3, (i, fr[i]["cfo_hz"])
