@@ -415,12 +415,23 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
 
 }  // namespace
 
-static constexpr size_t tp_smem_bytes() { return sizeof(float2) * (TPB / 32) * NBUF * 32 * ROWF2 + 1024 + 512; }
+// C8B_TP_RESIDENT: CTAs per SM a launch actually places (default: all C8B_TP_CTAS the registers allow).  With fewer, the dynamic
+// shared memory is padded so that no more fit, and the registers / shared memory left over host front-end CTAs of the next chunk.
+#ifndef C8B_TP_RESIDENT
+#define C8B_TP_RESIDENT C8B_TP_CTAS
+#endif
+static constexpr size_t tp_smem_need() { return sizeof(float2) * (TPB / 32) * NBUF * 32 * ROWF2 + 1024 + 512; }
+static constexpr size_t tp_smem_bytes()
+{
+    // one more CTA than wanted must not fit: (R + 1) * (bytes + 1 KB reserved per CTA) > 228 KB
+    return C8B_TP_RESIDENT < C8B_TP_CTAS && tp_smem_need() <= (size_t)(228 * 1024 / (C8B_TP_RESIDENT + 1) - 1024)
+               ? (size_t)(228 * 1024 / (C8B_TP_RESIDENT + 1) - 1024 + 256) : tp_smem_need();
+}
 static constexpr size_t tp_surv_per_cta() { return (size_t)(C8B_DECODE_T_MAX + CS + 2) * TPB; }              // uint2
 static constexpr size_t tp_words_per_cta() { return (size_t)((C8B_DECODE_T_MAX + 63) / 32 + 1) * TPB; }      // uint32
 static int tp_grid(int num_sm, int nframes)
 {
-    const int full = num_sm * C8B_TP_CTAS, need = (nframes + TPB - 1) / TPB;
+    const int full = num_sm * C8B_TP_RESIDENT, need = (nframes + TPB - 1) / TPB;
     return need < full ? need : full;
 }
 
@@ -437,7 +448,7 @@ size_t c8b_viterbi_tp_scratch_bytes(int num_sm, int nframes)
     return (size_t)tp_grid(num_sm, nframes) * (tp_surv_per_cta() * sizeof(uint2) + tp_words_per_cta() * sizeof(uint32_t));
 }
 
-int c8b_viterbi_tp_wave(int num_sm) { return num_sm * C8B_TP_CTAS * TPB; }   // frames in one full wave
+int c8b_viterbi_tp_wave(int num_sm) { return num_sm * C8B_TP_RESIDENT * TPB; }   // frames in one full wave
 
 void c8b_launch_viterbi_tp(const c8b_lut* d_lut, c8b_frame* d_frames, int nframes, const float* d_llr, int64_t nllr, void* d_scratch,
                            int num_sm, uint8_t* d_pdu, int64_t pdu_stride, uint8_t* d_scram, int64_t scram_stride, cudaStream_t st)
