@@ -23,8 +23,11 @@ from .rx import Receiver, split_pdus
 FORMAT_NAME = {0: "legacy", 1: "ht", 2: "vht"}
 
 
-def read_bin(path):
-    """fc32 interleaved capture, as written by tools/phy80211.py genMultiSigBinFile / blocks.file_source(gr_complex)."""
+def read_bin(path, sc16=False):
+    """fc32 interleaved capture, as written by tools/phy80211.py genMultiSigBinFile / blocks.file_source(gr_complex); sc16 = a
+    UHD-style capture of interleaved int16 I/Q (`uhd_rx_cfile --wire sc16 -s`), widened the way UHD does: x / 32768"""
+    if sc16:
+        return (np.fromfile(path, dtype="<i2").astype(np.float32) * np.float32(1.0 / 32768.0)).view(np.complex64)
     return np.fromfile(path, dtype=np.complex64)
 
 
