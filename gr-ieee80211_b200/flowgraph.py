@@ -157,38 +157,58 @@ class rx_top_block:
     """examples/rx.grc (nant=1: presiso -> trigger -> sync -> signal -> demod -> decode) or rx2.grc (nant=2: signal2 ->
     demod2).  run(capture) = tb.run() on a file_source: processes the whole capture, fills the blocks' tags, publishes PDUs."""
 
-    def __init__(self, nant=1, ifdebug=False, mupos=0, mugid=2, udp=None, on_pdu=None, max_frames=4096, device=0, printer=print, blob=None):
+    def __init__(self, nant=1, ifdebug=False, mupos=0, mugid=2, udp=None, on_pdu=None, max_frames=None, device=0, printer=print, blob=None):
         self.nant = nant
         self.trigger, self.sync = trigger(), sync()
         self.signal = signal() if nant == 1 else signal2()
         self.demod = demod(mupos, mugid) if nant == 1 else demod2()
         self.decode = decode(ifdebug, udp=udp, on_pdu=on_pdu, printer=printer)
+        # frame records per pass.  None: sized by the capture in run() (a frame is at least 400 samples, at most 4096 records) and
+        # 512 per window pass in work() -- the library reserves soft-bit scratch per record, so a fixed 4096 costs gigabytes
         self.max_frames = max_frames
-        self.rx = Receiver(device=device, chunk_items=1, max_frames=max_frames, mupos=mupos, mugid=mugid, blob=blob)
+        self._rx, self._rx_mf = None, None
+        self._rx_args = dict(device=device, chunk_items=1, mupos=mupos, mugid=mugid, blob=blob)
         self.frames = None
         self.truncated = False
         self._streaming = False
 
+    def _receiver(self, max_frames):
+        if self._rx is None or self._rx_mf != max_frames:
+            if self._rx is not None:
+                self._rx.close()
+            self._rx, self._rx_mf = Receiver(max_frames=max_frames, **self._rx_args), max_frames
+        return self._rx
+
+    @property
+    def rx(self):
+        return self._receiver(self._rx_mf or self.max_frames or 512)
+
     def close(self):
-        self.rx.close()
+        if self._rx is not None:
+            self._rx.close()
+            self._rx = None
 
     def run(self, capture0, capture1=None, pdu_stride=4400):
         x0 = read_bin(capture0) if isinstance(capture0, str) else np.asarray(capture0, np.complex64)
         if self.nant == 2:
             x1 = read_bin(capture1) if isinstance(capture1, str) else np.asarray(capture1, np.complex64)
             n = min(x0.size, x1.size)
-            fr, pdu = self.rx.rx_batch2(x0[:n], x1[:n], [0], [n], pdu_stride=pdu_stride)
-            _, chan = self.rx.detect(x0[:n], [0], [n])
+            mf = self.max_frames or min(4096, n // 400 + 1)
+            rx = self._receiver(mf)
+            fr, pdu = rx.rx_batch2(x0[:n], x1[:n], [0], [n], pdu_stride=pdu_stride)
+            _, chan = rx.detect(x0[:n], [0], [n])
         else:
-            fr, pdu = self.rx.rx_batch(x0, [0], [x0.size], pdu_stride=pdu_stride)
-            _, chan = self.rx.detect(x0, [0], [x0.size])
+            mf = self.max_frames or min(4096, x0.size // 400 + 1)
+            rx = self._receiver(mf)
+            fr, pdu = rx.rx_batch(x0, [0], [x0.size], pdu_stride=pdu_stride)
+            _, chan = rx.detect(x0, [0], [x0.size])
         keep = fr["status"] != 9                                # C8B_ST_EMPTY
         self.frames = fr[keep]
-        # the scan of an item stops when its max_frames records are used: say so instead of losing the rest silently
-        self.truncated = bool(self.max_frames > 1 and keep.sum() >= self.max_frames)
+        # the scan of an item stops when its frame records are used: say so instead of losing the rest silently
+        self.truncated = bool(mf > 1 and keep.sum() >= mf)
         if self.truncated:
             self.decode.printer("ieee80211 rx: all %d frame records of the capture are used, later frames were not examined "
-                                "(raise max_frames, or feed the capture through work())" % self.max_frames)
+                                "(raise max_frames, or feed the capture through work())" % mf)
         for k in np.nonzero(keep)[0]:
             self._publish(fr[k], chan[k], pdu[k], 0)
         return self.frames
@@ -216,11 +236,13 @@ class rx_top_block:
     def work(self, x0, x1=None, flush=False, window=0):
         """the scheduler's general_work calls: feed the next piece of the capture (any size); frames are published as soon
         as they are decidable, identically to run() over the whole capture.  flush=True ends the stream."""
+        mf = self.max_frames or 512
+        rx = self._receiver(mf) if not self._streaming else self._rx
         if not self._streaming:
-            self.rx.stream_begin(self.nant, window)
+            rx.stream_begin(self.nant, window)
             self._streaming = True
-        fr, base, pdu = self.rx.stream_push(np.asarray(x0, np.complex64), None if x1 is None else np.asarray(x1, np.complex64),
-                                            flush=flush, frames_cap=max(self.max_frames, 64) + len(x0) // 320)    # a frame is at least 400 samples
+        fr, base, pdu = rx.stream_push(np.asarray(x0, np.complex64), None if x1 is None else np.asarray(x1, np.complex64),
+                                       flush=flush, frames_cap=max(mf, 64) + len(x0) // 320)    # a frame is at least 400 samples
         for k in range(fr.size):
             self._publish(fr[k], None, pdu[k], base[k])
         if flush:
