@@ -222,6 +222,23 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
             const float* __restrict__ lb = llr + (size_t)c * nraw;
             const int rem = lim - c * nraw;                          // soft bits left from the start of this chunk
             const uint2* __restrict__ rt = reinterpret_cast<const uint2*>(relTab + cr * 32);
+            if (rem >= nraw) {                                       // the whole chunk lies inside the packet: no end test per copy
+#pragma unroll
+                for (int b = 0; b < CS; b += 10) {
+                    uint2 e[5];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) e[k] = rt[b / 2 + k];
+#pragma unroll
+                    for (int k = 0; k < 10; k++) {
+                        const uint32_t ev = (k & 1) ? e[k >> 1].y : e[k >> 1].x;
+                        const uint32_t i0 = ev & 0xffffu, i1 = ev >> 16;
+                        if (i0 != 0xffffu) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 8 * (b + k)), "l"(lb + i0));
+                        if (i1 != 0xffffu) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 8 * (b + k) + 4), "l"(lb + i1));
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                return;
+            }
 #pragma unroll
             for (int b = 0; b < CS; b += 10) {
                 uint2 e[5];
@@ -312,10 +329,32 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
             constexpr int TB = TBK;                                  // decision words per block; the next block is in flight
             uint2 wa[TB], wb[TB];
             auto fetch = [&](uint2 (&w)[TB], int tb) {
+                if (tb >= 0 && tb + TB <= T) {                       // whole block inside the frame: plain loads
+                    const uint2* __restrict__ p = surv + (size_t)tb * TPB;
+#pragma unroll
+                    for (int k = 0; k < TB; k++) w[k] = p[(size_t)k * TPB];
+                    return;
+                }
 #pragma unroll
                 for (int k = 0; k < TB; k++) w[k] = (tb >= 0 && tb + k < T) ? surv[(size_t)(tb + k) * TPB] : make_uint2(0u, 0u);
             };
             auto walk = [&](const uint2 (&w)[TB], int tb) {
+                if (TB == 32 && tb + TB <= T) {
+                    // the whole block lies inside the frame: no per-step test, and state + decoded bits share one register --
+                    // S <- 2 S + decision never drops a bit, so what leaves the 6 state bits IS the decoded sequence (bit 5 of
+                    // the state entered at step t is that step's input bit); it is collected twice per block
+                    uint32_t S = s;
+#pragma unroll
+                    for (int k = TB - 1; k >= 0; k--) {
+                        const uint32_t x = (S & 32u) ? w[k].y : w[k].x;
+                        S = (S << 1) | ((x >> (S & 31u)) & 1u);
+                        if (k == 16) { acc = (S >> 6) << 16; S &= 63u; }
+                    }
+                    words[(size_t)(tb >> 5) * TPB] = acc | (S >> 6);
+                    acc = 0;
+                    s = S & 63u;
+                    return;
+                }
 #pragma unroll
                 for (int k = TB - 1; k >= 0; k--) {
                     const int t = tb + k;
