@@ -20,6 +20,9 @@
 namespace {
 
 constexpr int TPB = 128;                       // threads (= frames) per CTA (224 x 2 CTAs = 14 warps per SM at 144 registers spills: slower)
+#ifndef C8B_TP_UNROLL
+#define C8B_TP_UNROLL 2                        // trellis steps per trip of the forward loop (divides CS, even)
+#endif
 constexpr int CS = 30;                         // trellis steps per staged chunk (multiple of every puncture period and of 2)
 constexpr int ROWF2 = CS + 1;                  // float2 per shared-memory row (odd -> conflict-free 8-byte column walks)
 
@@ -313,11 +316,14 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
             const float2* __restrict__ row = pairs[warp][c & 1] + lane * ROWF2;
             uint2* __restrict__ sv = surv + (size_t)c * CS * TPB;
 #pragma unroll 1
-            for (int s = 0; s < CS; s += 2) {
-                const uint2 w0 = acs(m, n, row[s]);
-                sv[(size_t)s * TPB] = w0;
-                const uint2 w1 = acs(n, m, row[s + 1]);
-                sv[(size_t)(s + 1) * TPB] = w1;
+            for (int s = 0; s < CS; s += C8B_TP_UNROLL) {
+#pragma unroll
+                for (int u = 0; u < C8B_TP_UNROLL; u += 2) {
+                    const uint2 w0 = acs(m, n, row[s + u]);
+                    sv[(size_t)(s + u) * TPB] = w0;
+                    const uint2 w1 = acs(n, m, row[s + u + 1]);
+                    sv[(size_t)(s + u + 1) * TPB] = w1;
+                }
             }
             stage_wait();
         }
