@@ -20,6 +20,10 @@
 namespace {
 
 constexpr int TPB = 128;                       // threads (= frames) per CTA (224 x 2 CTAs = 14 warps per SM at 144 registers spills: slower)
+#ifndef C8B_TP_SURV_WARP
+#define C8B_TP_SURV_WARP 0
+#endif
+constexpr int SVS = C8B_TP_SURV_WARP ? 32 : TPB;   // survivor words between two trellis steps of one thread
 #ifndef C8B_TP_UNROLL
 #define C8B_TP_UNROLL 2                        // trellis steps per trip of the forward loop (divides CS, even)
 #endif
@@ -176,7 +180,12 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if C8B_TP_SURV_WARP
+    // every warp owns a contiguous survivor stream [step][lane]: its traceback reads 256-byte rows back to back
+    uint2* __restrict__ surv = survAll + (size_t)blockIdx.x * survPerCta + (size_t)(threadIdx.x >> 5) * (survPerCta / (TPB / 32)) + (threadIdx.x & 31);
+#else
     uint2* __restrict__ surv = survAll + (size_t)blockIdx.x * survPerCta + threadIdx.x;        // [t * TPB]
+#endif
     uint32_t* __restrict__ words = wordsAll + (size_t)blockIdx.x * wordsPerCta + threadIdx.x;  // [w * TPB]
 
     for (int g = blockIdx.x; g * TPB < nframes; g += gridDim.x) {
@@ -298,13 +307,13 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
             else asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 1;" ::: "memory");     // segment q has landed (every lane reads only its own copies)
             const float2* __restrict__ row = pairs[warp][0] + lane * ROWF2 + SEG * (q % 3);
-            uint2* __restrict__ sv = surv + (size_t)q * SEG * TPB;
+            uint2* __restrict__ sv = surv + (size_t)q * SEG * SVS;
 #pragma unroll 1
             for (int s = 0; s < SEG; s += 2) {
                 const uint2 w0 = acs(m, n, row[s]);
-                sv[(size_t)s * TPB] = w0;
+                sv[(size_t)s * SVS] = w0;
                 const uint2 w1 = acs(n, m, row[s + 1]);
-                sv[(size_t)(s + 1) * TPB] = w1;
+                sv[(size_t)(s + 1) * SVS] = w1;
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -314,15 +323,15 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
         for (int c = 0; c < nch; c++) {
             if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
             const float2* __restrict__ row = pairs[warp][c & 1] + lane * ROWF2;
-            uint2* __restrict__ sv = surv + (size_t)c * CS * TPB;
+            uint2* __restrict__ sv = surv + (size_t)c * CS * SVS;
 #pragma unroll 1
             for (int s = 0; s < CS; s += C8B_TP_UNROLL) {
 #pragma unroll
                 for (int u = 0; u < C8B_TP_UNROLL; u += 2) {
                     const uint2 w0 = acs(m, n, row[s + u]);
-                    sv[(size_t)(s + u) * TPB] = w0;
+                    sv[(size_t)(s + u) * SVS] = w0;
                     const uint2 w1 = acs(n, m, row[s + u + 1]);
-                    sv[(size_t)(s + u + 1) * TPB] = w1;
+                    sv[(size_t)(s + u + 1) * SVS] = w1;
                 }
             }
             stage_wait();
@@ -336,13 +345,13 @@ k_viterbi_tp(const c8b_lut* __restrict__ lut, c8b_frame* __restrict__ frames, in
             uint2 wa[TB], wb[TB];
             auto fetch = [&](uint2 (&w)[TB], int tb) {
                 if (tb >= 0 && tb + TB <= T) {                       // whole block inside the frame: plain loads
-                    const uint2* __restrict__ p = surv + (size_t)tb * TPB;
+                    const uint2* __restrict__ p = surv + (size_t)tb * SVS;
 #pragma unroll
-                    for (int k = 0; k < TB; k++) w[k] = p[(size_t)k * TPB];
+                    for (int k = 0; k < TB; k++) w[k] = p[(size_t)k * SVS];
                     return;
                 }
 #pragma unroll
-                for (int k = 0; k < TB; k++) w[k] = (tb >= 0 && tb + k < T) ? surv[(size_t)(tb + k) * TPB] : make_uint2(0u, 0u);
+                for (int k = 0; k < TB; k++) w[k] = (tb >= 0 && tb + k < T) ? surv[(size_t)(tb + k) * SVS] : make_uint2(0u, 0u);
             };
             auto walk = [&](const uint2 (&w)[TB], int tb) {
                 if (TB == 32 && tb + TB <= T) {
