@@ -149,15 +149,44 @@ __device__ SyncOut sync_at_w(const cf* __restrict__ sig, cf conjAvg, Ws& W, int 
         ac[i] = fdiv(fdiv(cabsf_(mk(g.x, g.y)), fsqrt(g.z)), fsqrt(g.w));
     }
     __syncwarp();
-    float best = -1.f;
+    // first maximum (:97: best = ac[0], then every strictly larger value in index order), lane-parallel: every lane starts from
+    // ac[0] like the serial scan does (a NaN there wins, as in the reference), keeps the first maximum of its own indices,
+    // and the warp keeps the larger value -- the smaller index on a tie
+    float best = ac[0];
     int bi = 0;
-    for (int i = 0; i < C8B_SYNC_RES; i++) { const float a = ac[i]; if (i == 0 || a > best) { best = a; bi = i; } }   // first maximum (:97)
+    for (int i = lane; i < C8B_SYNC_RES; i += 32) { const float a = ac[i]; if (a > best) { best = a; bi = i; } }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, d);
+        const int oi = __shfl_xor_sync(FULL, bi, d);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
     SyncOut o; o.ok = 0; o.mIndex = 0; o.rad = o.snr = o.rssi = 0.f;
     if ((double)best > 0.5) {                                     // :99
         const float thr = (float)((double)best * 0.8);
+        // shoulders: the nearest index at or below / at or above the maximum whose correlation is under 0.8 of it (:100-110),
+        // from four ballots over the 111 values instead of two serial walks
         int l = bi, r = bi;
-        for (int j = bi; j >= 0; j--) if (ac[j] < thr) { l = j; break; }
-        for (int j = bi; j < C8B_SYNC_RES; j++) if (ac[j] < thr) { r = j; break; }
+        uint32_t under[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int i = 32 * q + lane; under[q] = __ballot_sync(FULL, i < C8B_SYNC_RES && ac[i] < thr); }
+        {
+            const int qb = bi >> 5, sb = bi & 31;
+            bool found = false;
+#pragma unroll
+            for (int q = 3; q >= 0; q--) {
+                if (q > qb || found) continue;
+                const uint32_t m = q == qb ? under[q] & (0xffffffffu >> (31 - sb)) : under[q];
+                if (m) { l = 32 * q + 31 - __clz(m); found = true; }
+            }
+            found = false;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (q < qb || found) continue;
+                const uint32_t m = q == qb ? under[q] & (0xffffffffu << sb) : under[q];
+                if (m) { r = 32 * q + __ffs(m) - 1; found = true; }
+            }
+        }
         o.ok = 1; o.mIndex = (l + r) / 2;
         const cf* __restrict__ s = sig + o.mIndex;                // ltf_cfo :181-196
         const float radStf = fdiv(atan2f_(conjAvg.im, conjAvg.re), 16.0f);
